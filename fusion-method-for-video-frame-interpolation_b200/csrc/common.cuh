@@ -1,0 +1,69 @@
+// common.cuh -- shared host/device helpers for libfvfi.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "fvfi.h"
+
+namespace fvfi {
+
+void set_error(const char* fmt, ...);
+
+#define FVFI_CHECK_ARG(cond, ...)            \
+    do {                                     \
+        if (!(cond)) {                       \
+            ::fvfi::set_error(__VA_ARGS__);  \
+            return FVFI_EINVAL;              \
+        }                                    \
+    } while (0)
+
+#define FVFI_CUDA(expr)                                                                   \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            ::fvfi::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                              __FILE__, __LINE__);                                        \
+            return FVFI_ECUDA;                                                            \
+        }                                                                                 \
+    } while (0)
+
+#define FVFI_LAUNCH_CHECK()                                                               \
+    do {                                                                                  \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess) {                                                          \
+            ::fvfi::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                              __FILE__, __LINE__);                                        \
+            return FVFI_ECUDA;                                                            \
+        }                                                                                 \
+    } while (0)
+
+int sm_count();
+
+__host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Streaming (read-once / write-once) global accesses: keep them out of L1 so the gathered
+// frame tiles stay resident.
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float v;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+    float4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream4(float4* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+}  // namespace fvfi

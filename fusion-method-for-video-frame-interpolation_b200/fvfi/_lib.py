@@ -1,0 +1,82 @@
+"""ctypes binding of libfvfi.so (C-ABI declared in include/fvfi.h).
+
+The reference hands raw ``tensor.data_ptr()`` values and torch's current stream to
+CuPy-launched kernels (src/adacof/cupy_module/adacof.py:337-354); this module keeps that
+convention.  The library is built in-tree by ../build.py; a missing library is a hard error
+when an op is called -- there is no fallback path.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_fp = ctypes.c_void_p
+c_int = ctypes.c_int
+c_size = ctypes.c_size_t
+
+
+class FvfiError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libfvfi.so")
+
+
+_PROTOS = {
+    "fvfi_version": (c_int, []),
+    "fvfi_last_error": (ctypes.c_char_p, []),
+    "fvfi_device_sm_count": (c_int, []),
+    "fvfi_adacof_forward": (c_int, [c_fp] * 5 + [c_int] * 9 + [c_fp]),
+    "fvfi_adacof_backward": (c_int, [c_fp] * 9 + [c_int] * 10 + [c_fp]),
+    "fvfi_adacofnet_tail": (c_int, [c_fp] * 11 + [c_int] * 5 + [c_fp]),
+    "fvfi_adacofnet_warp_blend": (c_int, [c_fp] * 13 + [c_int] * 7 + [c_fp]),
+    "fvfi_fusion_blend": (c_int, [c_fp] * 3 + [c_size, c_fp]),
+    "fvfi_adacof_forward_host": (c_int, [c_fp] * 5 + [c_int] * 8),
+    "fvfi_adacof_backward_host": (c_int, [c_fp] * 8 + [c_int] * 8),
+    "fvfi_pyr_plan_create": (c_int, [c_int, c_int, c_int, c_int, ctypes.c_double, ctypes.POINTER(c_fp)]),
+    "fvfi_pyr_plan_destroy": (None, [c_fp]),
+    "fvfi_pyr_num_levels": (c_int, [c_fp]),
+    "fvfi_pyr_level_shape": (c_int, [c_fp, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "fvfi_pyr_next_size": (c_int, [c_int, ctypes.c_double]),
+    "fvfi_pyr_workspace_bytes": (c_size, [c_fp, c_int]),
+    "fvfi_pyr_decompose": (c_int, [c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "fvfi_pyr_reconstruct": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp]),
+    "fvfi_pyr_build_complex": (c_int, [c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "fvfi_pyr_reconstruct_complex": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp]),
+}
+
+
+def lib():
+    """Load libfvfi.so (once).  Raises FvfiError if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise FvfiError(
+                "libfvfi.so not found at %s -- build it with "
+                "`python fusion-method-for-video-frame-interpolation_b200/build.py`; "
+                "there is no CPU / PyTorch fallback for the hot path" % path)
+        L = ctypes.CDLL(path)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise FvfiError("libfvfi error %d: %s" % (rc, lib().fvfi_last_error().decode()))
+
+
+def ptr(t):
+    """data_ptr of a tensor or None -> NULL."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

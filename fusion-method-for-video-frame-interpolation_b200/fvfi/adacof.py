@@ -1,0 +1,124 @@
+"""AdaCoF warp operator -- drop-in for the reference's ``src/adacof/cupy_module/adacof.py``.
+
+``FunctionAdaCoF.apply(input, weight, offset_i, offset_j, dilation)`` keeps the reference
+signature (adacof.py:311-314) and preconditions (asserts at :326-332, NotImplementedError for
+CPU tensors at :356-357).  Forward is one fused sm_100a kernel instead of a per-call
+regex-specialised NVRTC kernel; backward is one fused kernel instead of three plus four
+memsets (adacof.py:382-438).
+
+``gin_mode`` (module attribute, default "zeros") selects what ``gradInput`` is:
+  "zeros" -- reference semantics, gradInput == 0 (adacof.py:382,445)
+  "true"  -- extension: the true adjoint (warp-aggregated atomic scatter)
+"""
+import math
+
+import torch
+
+from . import _lib
+
+gin_mode = "zeros"
+algo = 0  # 0 auto, 1 direct, 2 tiled (see include/fvfi.h)
+
+_GIN = {"none": 0, "zeros": 1, "true": 2}
+
+
+def _geometry(input, weight, dilation):
+    intSample, intInputDepth, intInputHeight, intInputWidth = input.shape
+    intFilterSize = int(math.sqrt(weight.size(1)))
+    intOutputHeight, intOutputWidth = weight.size(2), weight.size(3)
+    # adacof.py:326-327
+    assert (intInputHeight - ((intFilterSize - 1) * dilation + 1) == intOutputHeight - 1)
+    assert (intInputWidth - ((intFilterSize - 1) * dilation + 1) == intOutputWidth - 1)
+    return (intSample, intInputDepth, intInputHeight, intInputWidth, intOutputHeight, intOutputWidth,
+            intFilterSize)
+
+
+def adacof_forward(input, weight, offset_i, offset_j, dilation, out=None, algo_=None):
+    B, C, Hin, Win, H, W, F = _geometry(input, weight, dilation)
+    # adacof.py:329-332
+    assert (input.is_contiguous() == True)
+    assert (weight.is_contiguous() == True)
+    assert (offset_i.is_contiguous() == True)
+    assert (offset_j.is_contiguous() == True)
+    if not input.is_cuda:
+        raise NotImplementedError()  # adacof.py:356-357: the reference has no CPU path either
+    assert input.dtype == torch.float32 and weight.dtype == torch.float32
+    if out is None:
+        out = torch.empty((B, C, H, W), dtype=input.dtype, device=input.device)
+    with torch.cuda.device(input.device):
+        _lib.check(_lib.lib().fvfi_adacof_forward(
+            input.data_ptr(), weight.data_ptr(), offset_i.data_ptr(), offset_j.data_ptr(), out.data_ptr(),
+            B, C, Hin, Win, H, W, F, int(dilation), algo if algo_ is None else algo_, _lib.stream_ptr()))
+    return out
+
+
+def adacof_backward(gradOutput, input, weight, offset_i, offset_j, dilation, mode="zeros", algo_=None):
+    B, C, Hin, Win, H, W, F = _geometry(input, weight, dilation)
+    assert (gradOutput.is_contiguous() == True)  # adacof.py:380
+    if not input.is_cuda:
+        raise NotImplementedError()
+    gin = None
+    if mode != "none":
+        gin = torch.empty_like(input)
+    gw = torch.empty_like(weight)
+    gi = torch.empty_like(weight)
+    gj = torch.empty_like(weight)
+    with torch.cuda.device(input.device):
+        _lib.check(_lib.lib().fvfi_adacof_backward(
+            gradOutput.data_ptr(), input.data_ptr(), weight.data_ptr(), offset_i.data_ptr(),
+            offset_j.data_ptr(), _lib.ptr(gin), gw.data_ptr(), gi.data_ptr(), gj.data_ptr(),
+            B, C, Hin, Win, H, W, F, int(dilation), _GIN[mode], algo if algo_ is None else algo_,
+            _lib.stream_ptr()))
+    return gin, gw, gi, gj
+
+
+class FunctionAdaCoF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, weight, offset_i, offset_j, dilation):
+        ctx.save_for_backward(input, weight, offset_i, offset_j)
+        ctx.dilation = dilation
+        return adacof_forward(input, weight, offset_i, offset_j, dilation)
+
+    @staticmethod
+    def backward(ctx, gradOutput):
+        input, weight, offset_i, offset_j = ctx.saved_tensors
+        if not gradOutput.is_contiguous():
+            gradOutput = gradOutput.contiguous()
+        mode = gin_mode if ctx.needs_input_grad[0] else "none"
+        gin, gw, gi, gj = adacof_backward(gradOutput, input, weight, offset_i, offset_j, ctx.dilation, mode)
+        return gin, gw, gi, gj, None
+
+
+def adacofnet_warp_blend(frame0_padded, frame2_padded, Weight1, Alpha1, Beta1, Weight2, Alpha2, Beta2,
+                         Occlusion, dilation, want_t=True):
+    """Fused lines 195-213 of src/fusion_net/fusion_adacofnet.py: both warps, the occlusion blend
+    and the flow-variance uncertainty mask in one pass over the six coefficient maps.
+    Returns (tensorAdaCoF1, tensorAdaCoF2, frame1, UncertaintyMask)."""
+    B, C, Hin, Win, H, W, F = _geometry(frame0_padded, Weight1, dilation)
+    assert C == 3
+    for t in (frame0_padded, frame2_padded, Weight1, Alpha1, Beta1, Weight2, Alpha2, Beta2, Occlusion):
+        assert t.is_contiguous() and t.is_cuda and t.dtype == torch.float32
+    new = lambda c: torch.empty((B, c, H, W), dtype=torch.float32, device=Weight1.device)
+    t1 = new(3) if want_t else None
+    t2 = new(3) if want_t else None
+    frame, mask = new(3), new(1)
+    with torch.cuda.device(Weight1.device):
+        _lib.check(_lib.lib().fvfi_adacofnet_warp_blend(
+            frame0_padded.data_ptr(), frame2_padded.data_ptr(), Weight1.data_ptr(), Alpha1.data_ptr(),
+            Beta1.data_ptr(), Weight2.data_ptr(), Alpha2.data_ptr(), Beta2.data_ptr(), Occlusion.data_ptr(),
+            _lib.ptr(t1), _lib.ptr(t2), frame.data_ptr(), mask.data_ptr(), B, Hin, Win, H, W, F, int(dilation),
+            _lib.stream_ptr()))
+    return t1, t2, frame, mask
+
+
+def adacofnet_tail(t1, t2, Occlusion, Weight1, Alpha1, Beta1, Weight2, Alpha2, Beta2):
+    """Occlusion blend + uncertainty mask only (fusion_adacofnet.py:198-213)."""
+    B, C, H, W = t1.shape
+    frame = torch.empty_like(t1)
+    mask = torch.empty((B, 1, H, W), dtype=t1.dtype, device=t1.device)
+    with torch.cuda.device(t1.device):
+        _lib.check(_lib.lib().fvfi_adacofnet_tail(
+            t1.data_ptr(), t2.data_ptr(), Occlusion.data_ptr(), Weight1.data_ptr(), Alpha1.data_ptr(),
+            Beta1.data_ptr(), Weight2.data_ptr(), Alpha2.data_ptr(), Beta2.data_ptr(), frame.data_ptr(),
+            mask.data_ptr(), B, C, H, W, Weight1.size(1), _lib.stream_ptr()))
+    return frame, mask

@@ -1,0 +1,137 @@
+/*
+ * fvfi.h -- C-ABI of libfvfi.so: the B200-native (sm_100a) frame-synthesis hot path of
+ * stefan01/Fusion-Method-for-Video-Frame-Interpolation.
+ *
+ * Drop-in boundary.  Every entry point replaces one call the reference
+ * makes today from Python into CuPy/NVRTC kernels, torch elementwise chains or the absent
+ * third-party `steerable` package.  The citation on each function is the reference
+ * interface it replaces (paths relative to the reference root).
+ *
+ * Conventions (same as the reference's CuPy launches, src/adacof/cupy_module/adacof.py:337-354):
+ *   - all tensor pointers are DEVICE pointers to contiguous fp32 NCHW storage that the
+ *     CALLER allocated (torch's caching allocator stays in charge); the library never
+ *     allocates user-visible tensors.  `*_host` variants take HOST pointers and do the
+ *     host<->device copies themselves (used for the end-to-end measurement).
+ *   - `stream` is a cudaStream_t / CUstream passed as void* (torch.cuda.current_stream().cuda_stream);
+ *     nothing synchronises the host except the `*_host` variants.
+ *   - return 0 on success; non-zero = error, text in fvfi_last_error() (thread-local).
+ *     The Python mirror raises (AssertionError / RuntimeError) like the reference does.
+ *   - re-entrant; no global mutable state except immutable plans.
+ */
+#ifndef FVFI_H
+#define FVFI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    FVFI_OK = 0,
+    FVFI_EINVAL = 1, /* bad shape / argument (the reference's Python asserts, adacof.py:326-332) */
+    FVFI_ECUDA = 2,  /* CUDA runtime error */
+    FVFI_ENOMEM = 3
+};
+
+/* gradInput modes of fvfi_adacof_backward */
+enum {
+    FVFI_GIN_NONE = 0,  /* gin pointer ignored */
+    FVFI_GIN_ZEROS = 1, /* reference semantics: gradInput = zeros (adacof.py:382,445) */
+    FVFI_GIN_TRUE = 2   /* extension: true adjoint, scatter with warp-aggregated atomics */
+};
+
+int fvfi_version(void);
+const char* fvfi_last_error(void);
+/* Device properties the library was built for / sees: returns SM count of the current device, or -1. */
+int fvfi_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * AdaCoF warp.  Replaces FunctionAdaCoF.forward + kernel_AdaCoF_updateOutput
+ * (src/adacof/cupy_module/adacof.py:313-361, :6-65).
+ *   input  [B,C,Hin,Win]   weight/off_i/off_j [B,F*F,H,W]   output [B,C,H,W]
+ *   requires Hin == H + (F-1)*dilation, Win == W + (F-1)*dilation  (adacof.py:326-327)
+ * algo: 0 = auto, 1 = direct (global gathers), 2 = tiled (smem-staged frame tile)
+ */
+int fvfi_adacof_forward(const float* input, const float* weight, const float* off_i, const float* off_j,
+                        float* output, int B, int C, int Hin, int Win, int H, int W, int F, int dilation,
+                        int algo, void* stream);
+
+/* Replaces FunctionAdaCoF.backward + kernel_AdaCoF_updateGradWeight/-Alpha/-Beta
+ * (adacof.py:364-445, :67-258) with ONE fused kernel.  C must be 3 (the reference hard-codes
+ * three channels, adacof.py:86,150,215).  gw/goi/goj [B,F*F,H,W] are fully overwritten
+ * (no pre-zeroing needed).  gin [B,C,Hin,Win] per gin_mode. */
+int fvfi_adacof_backward(const float* gout, const float* input, const float* weight, const float* off_i,
+                         const float* off_j, float* gin, float* gw, float* goi, float* goj, int B, int C,
+                         int Hin, int Win, int H, int W, int F, int dilation, int gin_mode, int algo,
+                         void* stream);
+
+/* Occlusion blend + flow-variance uncertainty mask of AdaCoFNet.forward
+ * (src/fusion_net/fusion_adacofnet.py:198-213), one pass over the six coefficient maps.
+ *   t1,t2,frame [B,C,H,W]  occ,mask [B,1,H,W]  w*,a*,b* [B,FF,H,W]; frame/mask may be NULL. */
+int fvfi_adacofnet_tail(const float* t1, const float* t2, const float* occ, const float* w1, const float* a1,
+                        const float* b1, const float* w2, const float* a2, const float* b2, float* frame,
+                        float* mask, int B, int C, int H, int W, int FF, void* stream);
+
+/* Both warps of AdaCoFNet.forward + blend + uncertainty mask in ONE kernel
+ * (fusion_adacofnet.py:195-213): each coefficient map is read from HBM once.
+ *   in1,in2 [B,3,Hin,Win] (replicate-padded frames)  t1,t2,frame [B,3,H,W]  occ,mask [B,1,H,W] */
+int fvfi_adacofnet_warp_blend(const float* in1, const float* in2, const float* w1, const float* a1,
+                              const float* b1, const float* w2, const float* a2, const float* b2,
+                              const float* occ, float* t1, float* t2, float* frame, float* mask, int B,
+                              int Hin, int Win, int H, int W, int F, int dilation, void* stream);
+
+/* FusionNet's last step (src/fusion_net/fusion_net.py:67-77): out = clamp(base + tanh(x), 0, 1). */
+int fvfi_fusion_blend(const float* base, const float* x_pre_tanh, float* out, size_t n, void* stream);
+
+/* Host-buffer variants for end-to-end timing: pointers are HOST memory (pinned preferred);
+ * the call does H2D, the kernel(s), D2H and synchronises. */
+int fvfi_adacof_forward_host(const float* input, const float* weight, const float* off_i, const float* off_j,
+                             float* output, int B, int C, int Hin, int Win, int H, int W, int F, int dilation);
+int fvfi_adacof_backward_host(const float* gout, const float* input, const float* weight, const float* off_i,
+                              const float* off_j, float* gw, float* goi, float* goj, int B, int C, int Hin,
+                              int Win, int H, int W, int F, int dilation);
+
+/* ---------------------------------------------------------------------------------------
+ * Complex steerable pyramid.  Replaces steerable.SCFpyr_PyTorch.build / .reconstruct (third
+ * party, absent; call sites src/train/pyramid.py:28-33,37,44) fused with
+ * Pyramid.coeff_to_values / values_to_coeff (src/train/pyramid.py:48-112).
+ * A plan owns the immutable device tables (level sizes, FFT factorizations, twiddles).
+ */
+typedef struct fvfi_pyr_plan fvfi_pyr_plan;
+
+int fvfi_pyr_plan_create(int H, int W, int height, int nbands, double scale_factor, fvfi_pyr_plan** out);
+void fvfi_pyr_plan_destroy(fvfi_pyr_plan* plan);
+int fvfi_pyr_num_levels(const fvfi_pyr_plan* plan); /* height - 2 */
+/* level 0..L-1 = band levels (finest first); level L = low-pass residual */
+int fvfi_pyr_level_shape(const fvfi_pyr_plan* plan, int level, int* h, int* w);
+/* Level-size rule shared with the oracle: n_next = ceil((n - 0.5) / s)  (SURVEY.md F2, Appendix A.4). */
+int fvfi_pyr_next_size(int n, double scale_factor);
+size_t fvfi_pyr_workspace_bytes(const fvfi_pyr_plan* plan, int N);
+
+/* Decompose N planes.  img [N,H,W] -> high [N,1,H,W], phase[l]/amp[l] [N*nb,1,h_l,w_l] (channel
+ * = plane*nb + band, src/train/pyramid.py:64-66), low [N,1,h_L,w_L].  amp_max (optional,
+ * [L,N] per-level per-plane max amplitude over the nb bands) feeds PhaseNet.normalize_vals
+ * (src/phase_net/phase_net.py:42-78).  high may be NULL (skipped). */
+int fvfi_pyr_decompose(const fvfi_pyr_plan* plan, const float* img, int N, float* high, float* const* phase,
+                       float* const* amp, float* low, float* amp_max, void* workspace, void* stream);
+
+/* Reconstruct N planes from (high, phase, amp, low).  phase[l]/amp[l] may be NULL for a level
+ * that contributes nothing (the reference passes the int 0, src/phase_net/phase_net.py:91-93;
+ * get_last/first_value_levels zero-fill, src/train/utils.py:242-320); high/low may be NULL (zeros). */
+int fvfi_pyr_reconstruct(const fvfi_pyr_plan* plan, const float* high, const float* const* phase,
+                         const float* const* amp, const float* low, int N, float* img, void* workspace,
+                         void* stream);
+
+/* Complex coefficient interface (the SCFpyr_PyTorch.build/reconstruct layout, band tensors
+ * [N,h_l,w_l,2], src/train/pyramid.py:58): bands[l*nb + b]. */
+int fvfi_pyr_build_complex(const fvfi_pyr_plan* plan, const float* img, int N, float* high,
+                           float* const* bands, float* low, void* workspace, void* stream);
+int fvfi_pyr_reconstruct_complex(const fvfi_pyr_plan* plan, const float* high, const float* const* bands,
+                                 const float* low, int N, float* img, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVFI_H */
