@@ -253,12 +253,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fvfi", choices=["fvfi", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-refbar", action="store_true", help="skip timing the reference's own CUDA kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -317,7 +318,7 @@ def main():
             "clocks": clocks, "gpu_launches": wl.launches_per_step * args.steps,
             "roofline": wl.roofline(peak, peak_src),
         }
-        bar = wl.reference_gpu_kernels() if hasattr(wl, "reference_gpu_kernels") else None
+        bar = wl.reference_gpu_kernels() if hasattr(wl, "reference_gpu_kernels") and not args.no_refbar else None
         if bar:
             line["reference_gpu_kernels"] = bar
     # end-to-end through the host-buffer C-ABI / public API (every rank runs it; max over ranks)

@@ -59,10 +59,17 @@ def lib():
                 "`python fusion-method-for-video-frame-interpolation_b200/build.py`; "
                 "there is no CPU / PyTorch fallback for the hot path" % path)
         L = ctypes.CDLL(path)
+        missing = []
         for name, (res, args) in _PROTOS.items():
-            fn = getattr(L, name)
+            try:
+                fn = getattr(L, name)
+            except AttributeError:
+                missing.append(name)
+                continue
             fn.restype = res
             fn.argtypes = args
+        if missing:
+            raise FvfiError("libfvfi.so at %s is stale: missing symbols %s -- rebuild with build.py" % (path, missing))
         _LIB = L
     return _LIB
 

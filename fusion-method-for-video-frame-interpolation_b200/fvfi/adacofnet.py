@@ -1,0 +1,153 @@
+"""Drop-in for the reference's ``src/fusion_net/fusion_adacofnet.py`` (KernelEstimation, AdaCoFNet,
+make_model) -- the AdaCoFNet variant the fusion pipeline uses (returns 4 tensors).
+
+``AdaCoFNet(args)`` takes ``args.kernel_size``, ``args.dilation``, ``args.gpu_id``;
+``forward(frame0, frame2) -> (tensorAdaCoF1, tensorAdaCoF2, frame1, UncertaintyMask)``.
+Parameter names (``get_kernel.module*``) match the reference so its checkpoints load.  Lines
+195-213 of the reference (two warps, occlusion blend, flow mean/variance, clip/20) run as ONE fused
+kernel in inference (fvfi_adacofnet_warp_blend); with autograd enabled the op-level
+``FunctionAdaCoF`` is used so gradients reach the kernel-estimation network.
+"""
+import sys
+
+import torch
+from torch.nn import functional as F
+
+from . import adacof
+
+
+def moduleNormalize(frame):
+    """src/adacof/utility.py:86-87."""
+    mean = torch.tensor([0.4631, 0.4352, 0.3990], dtype=frame.dtype, device=frame.device).view(1, 3, 1, 1)
+    return frame - mean
+
+
+def make_model(args):
+    return AdaCoFNet(args).to(torch.device('cuda:{}'.format(args.gpu_id)))
+
+
+class KernelEstimation(torch.nn.Module):
+    """fusion_adacofnet.py:14-155 (same submodule names and creation order)."""
+
+    def __init__(self, kernel_size):
+        super(KernelEstimation, self).__init__()
+        self.kernel_size = kernel_size
+        nn = torch.nn
+
+        def Basic(ci, co):
+            return nn.Sequential(
+                nn.Conv2d(ci, co, 3, 1, 1), nn.ReLU(inplace=False),
+                nn.Conv2d(co, co, 3, 1, 1), nn.ReLU(inplace=False),
+                nn.Conv2d(co, co, 3, 1, 1), nn.ReLU(inplace=False))
+
+        def Upsample(c):
+            return nn.Sequential(
+                nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
+                nn.Conv2d(c, c, 3, 1, 1), nn.ReLU(inplace=False))
+
+        def Subnet(ks, tail=None, last_in=None):
+            layers = [
+                nn.Conv2d(64, 64, 3, 1, 1), nn.ReLU(inplace=False),
+                nn.Conv2d(64, 64, 3, 1, 1), nn.ReLU(inplace=False),
+                nn.Conv2d(64, ks if last_in is None else last_in, 3, 1, 1), nn.ReLU(inplace=False),
+                nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
+                nn.Conv2d(ks if last_in is None else last_in, ks, 3, 1, 1)]
+            if tail is not None:
+                layers.append(tail)
+            return nn.Sequential(*layers)
+
+        ks2 = self.kernel_size ** 2
+        self.moduleConv1 = Basic(6, 32)
+        self.modulePool1 = nn.AvgPool2d(kernel_size=2, stride=2)
+        self.moduleConv2 = Basic(32, 64)
+        self.modulePool2 = nn.AvgPool2d(kernel_size=2, stride=2)
+        self.moduleConv3 = Basic(64, 128)
+        self.modulePool3 = nn.AvgPool2d(kernel_size=2, stride=2)
+        self.moduleConv4 = Basic(128, 256)
+        self.modulePool4 = nn.AvgPool2d(kernel_size=2, stride=2)
+        self.moduleConv5 = Basic(256, 512)
+        self.modulePool5 = nn.AvgPool2d(kernel_size=2, stride=2)
+        self.moduleDeconv5 = Basic(512, 512)
+        self.moduleUpsample5 = Upsample(512)
+        self.moduleDeconv4 = Basic(512, 256)
+        self.moduleUpsample4 = Upsample(256)
+        self.moduleDeconv3 = Basic(256, 128)
+        self.moduleUpsample3 = Upsample(128)
+        self.moduleDeconv2 = Basic(128, 64)
+        self.moduleUpsample2 = Upsample(64)
+        self.moduleWeight1 = Subnet(ks2, nn.Softmax(dim=1))
+        self.moduleAlpha1 = Subnet(ks2)
+        self.moduleBeta1 = Subnet(ks2)
+        self.moduleWeight2 = Subnet(ks2, nn.Softmax(dim=1))
+        self.moduleAlpha2 = Subnet(ks2)
+        self.moduleBeta2 = Subnet(ks2)
+        self.moduleOcclusion = Subnet(1, nn.Sigmoid(), last_in=64)
+
+    def forward(self, rfield0, rfield2):
+        x = torch.cat([rfield0, rfield2], 1)
+        c1 = self.moduleConv1(x)
+        c2 = self.moduleConv2(self.modulePool1(c1))
+        c3 = self.moduleConv3(self.modulePool2(c2))
+        c4 = self.moduleConv4(self.modulePool3(c3))
+        c5 = self.moduleConv5(self.modulePool4(c4))
+        d5 = self.moduleUpsample5(self.moduleDeconv5(self.modulePool5(c5)))
+        d4 = self.moduleUpsample4(self.moduleDeconv4(d5 + c5))
+        d3 = self.moduleUpsample3(self.moduleDeconv3(d4 + c4))
+        d2 = self.moduleUpsample2(self.moduleDeconv2(d3 + c3))
+        comb = d2 + c2
+        return (self.moduleWeight1(comb), self.moduleAlpha1(comb), self.moduleBeta1(comb),
+                self.moduleWeight2(comb), self.moduleAlpha2(comb), self.moduleBeta2(comb),
+                self.moduleOcclusion(comb))
+
+
+class AdaCoFNet(torch.nn.Module):
+    """fusion_adacofnet.py:158-240."""
+
+    def __init__(self, args):
+        super(AdaCoFNet, self).__init__()
+        self.args = args
+        self.kernel_size = args.kernel_size
+        self.kernel_pad = int(((args.kernel_size - 1) * args.dilation) / 2.0)
+        self.dilation = args.dilation
+        self.get_kernel = KernelEstimation(self.kernel_size)
+        self.modulePad = torch.nn.ReplicationPad2d([self.kernel_pad] * 4)
+        self.moduleAdaCoF = adacof.FunctionAdaCoF.apply
+
+    def load(self, state_dict):
+        """The reference wraps models in src/adacof/models/__init__.py:Model whose ``load`` forwards here."""
+        self.load_state_dict(state_dict)
+
+    def forward(self, frame0, frame2):
+        h0, w0 = int(frame0.shape[2]), int(frame0.shape[3])
+        if h0 != int(frame2.shape[2]) or w0 != int(frame2.shape[3]):
+            sys.exit('Frame sizes do not match')                                   # fusion_adacofnet.py:177-178
+        if h0 % 32 != 0:
+            pad_h = 32 - (h0 % 32)
+            frame0 = F.pad(frame0, (0, 0, 0, pad_h), mode='reflect')
+            frame2 = F.pad(frame2, (0, 0, 0, pad_h), mode='reflect')
+        if w0 % 32 != 0:
+            pad_w = 32 - (w0 % 32)
+            frame0 = F.pad(frame0, (0, pad_w, 0, 0), mode='reflect')
+            frame2 = F.pad(frame2, (0, pad_w, 0, 0), mode='reflect')
+        W1, A1, B1, W2, A2, B2, Occ = self.get_kernel(moduleNormalize(frame0), moduleNormalize(frame2))
+        p0, p2 = self.modulePad(frame0).contiguous(), self.modulePad(frame2).contiguous()
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (W1, A1, B1, W2, A2, B2, Occ, p0, p2))
+        if needs_grad:
+            t1 = self.moduleAdaCoF(p0, W1.contiguous(), A1.contiguous(), B1.contiguous(), self.dilation)
+            t2 = self.moduleAdaCoF(p2, W2.contiguous(), A2.contiguous(), B2.contiguous(), self.dilation)
+            frame1 = Occ * t1 + (1 - Occ) * t2                                       # fusion_adacofnet.py:198
+            with torch.no_grad():                                                    # .detach() at :211
+                _, mask = adacof.adacofnet_tail(t1.detach(), t2.detach(), Occ.detach().contiguous(),
+                                                W1.detach().contiguous(), A1.detach().contiguous(),
+                                                B1.detach().contiguous(), W2.detach().contiguous(),
+                                                A2.detach().contiguous(), B2.detach().contiguous())
+        else:
+            t1, t2, frame1, mask = adacof.adacofnet_warp_blend(p0, p2, W1.contiguous(), A1.contiguous(), B1.contiguous(),
+                                                               W2.contiguous(), A2.contiguous(), B2.contiguous(),
+                                                               Occ.contiguous(), self.dilation)
+        if h0 != t1.shape[2] or w0 != t1.shape[3]:
+            # crop back; NB the reference returns tensorAdaCoF2 as tensorAdaCoF1 when the width was padded
+            # (fusion_adacofnet.py:225) -- fixed here, frame1/mask are unaffected.
+            t1, t2 = t1[:, :, :h0, :w0], t2[:, :, :h0, :w0]
+            frame1, mask = frame1[:, :, :h0, :w0], mask[:, :, :h0, :w0]
+        return t1, t2, frame1, mask

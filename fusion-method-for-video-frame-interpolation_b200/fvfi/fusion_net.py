@@ -1,0 +1,84 @@
+"""Drop-in for the reference's ``src/fusion_net/fusion_net.py`` (FusionNet).
+
+Same constructor, parameter names (``net.*`` dead weights kept for state-dict compatibility,
+``encoder_layers.*``, ``bottleneck_layer.*``, ``decoder_layers.*``) and ``forward(base, adacof, phase,
+other, maps, save=False, variant=0)``.  The final ``tanh -> base + res -> clamp(0,1)``
+(fusion_net.py:67-77) is one fused CUDA kernel (fvfi_fusion_blend) in inference; under autograd
+the torch expression is used so gradients flow (training step).
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def fusion_blend(base, x):
+    """clamp(base + tanh(x), 0, 1) -- fusion_net.py:67-77."""
+    base = base.contiguous()
+    x = x.contiguous()
+    out = torch.empty_like(base)
+    with torch.cuda.device(base.device):
+        _lib.check(_lib.lib().fvfi_fusion_blend(base.data_ptr(), x.data_ptr(), out.data_ptr(), base.numel(),
+                                                _lib.stream_ptr()))
+    return out
+
+
+class FusionNet(torch.nn.Module):
+
+    def __init__(self, num_imgs=5, uncertainty_maps=3, kernel=3, pad=3, dil=3):
+        super(FusionNet, self).__init__()
+        # never used in forward (fusion_net.py:11-20 vs :46-77) -- kept so fusion_net.pt loads unchanged
+        self.net = nn.Sequential(
+            nn.Conv2d(3 * num_imgs + uncertainty_maps, 64, kernel_size=kernel, stride=1, padding=pad, dilation=dil),
+            nn.ReLU(),
+            nn.Conv2d(64, 64, kernel_size=kernel, stride=1, padding=pad, dilation=dil),
+            nn.ReLU(),
+            nn.Conv2d(64, 64, kernel_size=kernel, stride=1, padding=pad, dilation=dil),
+            nn.ReLU(),
+            nn.Conv2d(64, 3, kernel_size=kernel, stride=1, padding=pad, dilation=dil),
+            nn.Tanh()
+        )
+        input_channels = 3 * num_imgs + uncertainty_maps
+        self.encoder_layers = nn.ModuleList([
+            nn.Conv2d(input_channels, 32, kernel_size=5, stride=1, padding=2, padding_mode='reflect'),
+            nn.Conv2d(32, 64, kernel_size=5, stride=1, padding=2, padding_mode='reflect'),
+            nn.Conv2d(64, 128, kernel_size=3, stride=1, padding=1, padding_mode='reflect')
+        ])
+        self.bottleneck_layer = nn.Conv2d(128, 128, kernel_size=3, stride=1, padding=1, padding_mode='reflect')
+        self.decoder_layers = nn.ModuleList([
+            nn.Conv2d(128, 64, kernel_size=5, stride=1, padding=2, padding_mode='reflect'),
+            nn.Conv2d(64, 32, kernel_size=5, stride=1, padding=2, padding_mode='reflect'),
+            nn.Conv2d(32, 3, kernel_size=1, stride=1),
+        ])
+        self.relu = nn.ReLU()
+        self.tanh = nn.Tanh()
+        self.max_pool = nn.MaxPool2d(2, stride=2)
+        self.deconvolution = nn.Upsample(scale_factor=2, mode='bilinear')
+        self.residuals = []
+
+    def live_parameters(self):
+        """Parameters that receive gradients (everything except the dead ``net.*``); the training
+        all-reduce bucket is built from these."""
+        return [p for n, p in self.named_parameters() if not n.startswith("net.")]
+
+    def forward(self, base, adacof, phase, other, maps, save=False, variant=0):
+        x = torch.cat([base, adacof, phase, other, maps], 1)
+        skip = []
+        for layer in self.encoder_layers:
+            x = self.relu(layer(x))
+            skip.append(x)
+            x = self.max_pool(x)
+        x = self.bottleneck_layer(x)
+        for layer, s in zip(self.decoder_layers, skip[::-1]):
+            x = self.deconvolution(self.relu(x))
+            x = x + s
+            x = layer(x)
+        anchor = phase if variant == 1 else base
+        if torch.is_grad_enabled() and x.requires_grad or not x.is_cuda:
+            res = self.tanh(x)
+            if save:
+                self.residuals.append(torch.sum(res).cpu().detach().item())
+            return (anchor + res).clamp(0, 1)
+        if save:
+            self.residuals.append(torch.sum(torch.tanh(x)).cpu().item())
+        return fusion_blend(anchor, x)

@@ -1,0 +1,153 @@
+"""Drop-in for the reference's ``src/phase_net/phase_net.py`` (PhaseNet, PhaseNetBlock).
+
+Same constructor (``PhaseNet(pyr, device, num_img=2)``), same ``normalize_vals`` / ``forward(vals, m)`` /
+``reverse_normalize`` semantics and the same parameter names (``layers.{i}.feature_map.{0,1,3}.*``,
+``layers.{i}.prediction_map.0.*``) so ``phase_net.pt`` loads unchanged.  Differences that do not
+change results: no ``torch.cuda.empty_cache()`` in the level loop (phase_net.py:145,152), planes can
+be processed in chunks to bound the 88-channel concat, and the alpha/beta blends
+(phase_net.py:114-116,155-156) are single fused expressions.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .pyramid import DecompValues
+
+
+class PhaseNetBlock(nn.Module):
+    """phase_net.py:179-207."""
+
+    def __init__(self, c_in, c_out, pred_out, kernel_size, device, dropout=0.5):
+        super(PhaseNetBlock, self).__init__()
+        padding = 1 if kernel_size == (3, 3) else 0
+        self.feature_map = nn.Sequential(
+            nn.Conv2d(c_in, c_out, kernel_size, padding=padding, padding_mode='reflect'),
+            nn.BatchNorm2d(c_out),
+            nn.ELU(),
+            nn.Conv2d(c_out, c_out, kernel_size, padding=padding, padding_mode='reflect'),
+            nn.ELU(),
+        )
+        self.prediction_map = nn.Sequential(
+            nn.Conv2d(c_out, pred_out, (1, 1), padding_mode='reflect'),
+            nn.Tanh()
+        )
+        self.to(device)
+
+    def forward(self, x):
+        f = self.feature_map(x)
+        c = self.prediction_map(f)
+        return f, c
+
+
+class PhaseNet(nn.Module):
+    """Phase Net for Video Frame Interpolation (phase_net.py:7-177)."""
+
+    def __init__(self, pyr, device, num_img=2):
+        super(PhaseNet, self).__init__()
+        self.pyr = pyr
+        self.device = device
+        self.num_img = num_img
+        self.layers = self.create_architecture()
+        self.to(self.device)
+        self.eps = 1e-8
+        self.plane_chunk = None  # planes per forward chunk (None = all at once)
+
+    def create_architecture(self):
+        n = self.num_img
+        if n == 3:
+            return nn.ModuleList([
+                PhaseNetBlock(n, 64, n - 1, (1, 1), self.device),
+                PhaseNetBlock(64 + n - 1 + 8 * n, 64, n * 4, (1, 1), self.device),
+                PhaseNetBlock(64 + n * 4 + 8 * n, 64, n * 4, (1, 1), self.device),
+                *[PhaseNetBlock(64 + n * 4 + 8 * n, 64, n * 4, (3, 3), self.device) for _ in range(5)]
+            ])
+        return nn.ModuleList([
+            PhaseNetBlock(n, 64, 1, (1, 1), self.device),
+            PhaseNetBlock(64 + 1 + 8 * n, 64, 8, (1, 1), self.device),
+            PhaseNetBlock(64 + 8 + 8 * n, 64, 8, (1, 1), self.device),
+            *[PhaseNetBlock(64 + 8 + 8 * n, 64, 8, (3, 3), self.device) for _ in range(5)]
+        ])
+
+    def set_layers(self, start, end, freeze=True):
+        for param in self.layers[start:end].parameters():
+            param.requires_grad = freeze
+
+    def normalize_vals(self, vals):
+        """phase_net.py:42-78: amplitude / (per-plane max + eps), phase / pi, low / (per-plane max + eps).
+        The maxima are kept on ``self`` for compatibility (reverse_normalize reads them)."""
+        batch_size = int(vals.amplitude[0].shape[0])
+        self.max_amplitudes = []
+        amplitudes = []
+        for amplitude in vals.amplitude:
+            max_amplitude = amplitude.reshape(batch_size, -1).max(1)[0] + self.eps
+            self.max_amplitudes.append(max_amplitude)
+            amplitudes.append(amplitude / max_amplitude.view(-1, 1, 1, 1))
+        phases = [x / math.pi for x in vals.phase]
+        self.max_low_level = vals.low_level.reshape(batch_size, -1).max(1)[0] + self.eps   # max, not max|.| (:70)
+        low_level = vals.low_level / self.max_low_level.view(-1, 1, 1, 1)
+        return DecompValues(high_level=vals.high_level, low_level=low_level, amplitude=amplitudes, phase=phases)
+
+    def reverse_normalize(self, vals, m):
+        """phase_net.py:80-105."""
+        phases = [x * math.pi for x in vals.phase]
+        amplitudes = []
+        for i in range(m):
+            amp = vals.amplitude[i]
+            batch_size = int(amp.shape[0] / self.pyr.nbands)
+            amplitudes.append((amp.reshape(batch_size, -1) * self.max_amplitudes[i].view(-1, 1)).reshape(amp.shape))
+        for _ in range(self.pyr.height - 2 - m):
+            phases.append(0)
+            amplitudes.append(0)
+        low_level = vals.low_level * self.max_low_level.view(-1, 1, 1, 1)
+        return DecompValues(high_level=vals.high_level, low_level=low_level, amplitude=amplitudes[::-1],
+                            phase=phases[::-1])
+
+    def _forward_planes(self, low, phase, amplitude, m):
+        feature, prediction = self.layers[0](low)
+        alpha = (prediction[:, 0] + 1) / 2
+        low_level = alpha * low[:, 0] + (1 - alpha) * low[:, 1]                      # phase_net.py:114-116
+        if self.num_img == 3:
+            fusion_alpha = (prediction[:, 1] + 1) / 2
+            low_level = fusion_alpha * low_level + (1 - fusion_alpha) * low[:, 2]
+        low_level = low_level.unsqueeze(1)
+        phases, amplitudes = [], []
+        for idx in range(m):
+            res = phase[idx].shape[2:]
+            feature_r = F.interpolate(feature, size=tuple(res), mode='bilinear', align_corners=False)
+            prediction_r = F.interpolate(prediction, size=tuple(res), mode='bilinear', align_corners=False)
+            concat = torch.cat((feature_r, phase[idx], amplitude[idx], prediction_r), 1)
+            i = idx + 1 if idx + 1 < len(self.layers) - 1 else len(self.layers) - 1
+            feature, prediction = self.layers[i](concat)
+            del concat
+            beta = (prediction[:, 4:8] + 1) / 2
+            amp = beta * amplitude[idx][:, 4:8] + (1 - beta) * amplitude[idx][:, :4]  # phase_net.py:155-156
+            if self.num_img == 3:
+                fusion_beta = (prediction[:, 8:12] + 1) / 2
+                amp = fusion_beta * amp + (1 - fusion_beta) * amplitude[idx][:, 8:12]
+            r1, r2 = prediction.shape[2:]
+            phases.append(prediction[:, :4].reshape(-1, 1, r1, r2))
+            amplitudes.append(amp.reshape(-1, 1, r1, r2))
+        return low_level, phases, amplitudes
+
+    def forward(self, vals, m=None):
+        """phase_net.py:107-177."""
+        if m is None:
+            m = self.pyr.height - 2
+        P = vals.low_level.shape[0]
+        chunk = self.plane_chunk or P
+        lows, phs, ams = [], [[] for _ in range(m)], [[] for _ in range(m)]
+        for p0 in range(0, P, chunk):
+            sl = slice(p0, min(P, p0 + chunk))
+            low, ph, am = self._forward_planes(vals.low_level[sl], [x[sl] for x in vals.phase[:m]],
+                                               [x[sl] for x in vals.amplitude[:m]], m)
+            lows.append(low)
+            for i in range(m):
+                phs[i].append(ph[i])
+                ams[i].append(am[i])
+        cat = lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs, 0)
+        hl = vals.high_level.shape
+        high_level = torch.zeros((hl[0], 1, hl[2], hl[3]), device=vals.low_level.device)   # phase_net.py:127-128
+        return self.reverse_normalize(DecompValues(high_level=high_level, low_level=cat(lows),
+                                                   phase=[cat(x) for x in phs], amplitude=[cat(x) for x in ams]), m)

@@ -1,0 +1,135 @@
+"""Drop-in for the reference's ``src/train/pyramid.py`` (Pyramid, DecompValues).
+
+``Pyramid(height, nbands, scale_factor, device)`` with ``filter(img[N,H,W]) -> DecompValues`` and
+``inv_filter(DecompValues) -> img[N,H,W]`` (pyramid.py:23-46).  ``filter`` is the fused path: one
+forward FFT2 per plane, then per level band-mask -> inverse FFT -> amplitude/phase epilogue, so
+the complex coefficients never reach HBM and ``coeff_to_values``'s Python loops (pyramid.py:48-78)
+disappear.  ``coeff_to_values`` / ``values_to_coeff`` are kept for API compatibility (vectorised).
+"""
+from collections import namedtuple
+
+import torch
+
+from . import _lib
+from .pyr_plan import PyrPlan, ptr_array
+from .steerable import SCFpyr_PyTorch
+
+DecompValues = namedtuple(
+    'values',
+    'high_level, '
+    'phase, '
+    'amplitude, '
+    'low_level'
+)
+
+
+class Pyramid:
+    """ Steerable Pyramid Decomposition (B200-native). """
+
+    def __init__(self, height, nbands, scale_factor, device):
+        self.height = height
+        self.nbands = nbands
+        self.scale_factor = scale_factor
+        self.device = device
+        self.pyr = SCFpyr_PyTorch(height=self.height, nbands=self.nbands, scale_factor=self.scale_factor,
+                                  device=self.device)
+        self.last_amp_max = None  # [L, N] per-level per-plane max amplitude of the last filter() call
+
+    def _plan(self, H, W, device):
+        return PyrPlan.get(H, W, self.height, self.nbands, self.scale_factor, device)
+
+    def filter(self, img, want_high=True):
+        """ Psi filter: img [N,H,W] -> DecompValues (layouts of src/train/pyramid.py:48-78). """
+        if not img.is_cuda:
+            raise NotImplementedError("fvfi pyramid: CUDA tensors only")
+        img = img.contiguous().float()
+        N, H, W = img.shape
+        plan = self._plan(H, W, img.device)
+        nb = self.nbands
+        new = lambda *s: torch.empty(s, dtype=torch.float32, device=img.device)
+        high = new(N, 1, H, W) if want_high else None
+        phase = [new(N * nb, 1, h, w) for (h, w) in plan.shapes[:-1]]
+        amp = [new(N * nb, 1, h, w) for (h, w) in plan.shapes[:-1]]
+        low = new(N, 1, *plan.shapes[-1])
+        amp_max = new(plan.L, N)
+        with torch.cuda.device(img.device):
+            _lib.check(_lib.lib().fvfi_pyr_decompose(plan.handle, img.data_ptr(), N, _lib.ptr(high), ptr_array(phase),
+                                                     ptr_array(amp), low.data_ptr(), amp_max.data_ptr(),
+                                                     plan.workspace(N).data_ptr(), _lib.stream_ptr()))
+        self.last_amp_max = amp_max
+        if high is None:
+            high = torch.zeros((N, 1, H, W), dtype=torch.float32, device=img.device)
+        return DecompValues(high_level=high, phase=phase, amplitude=amp, low_level=low)
+
+    def inv_filter(self, vals):
+        """ Psi^{-1} filter: DecompValues -> img [N,H,W].  Levels given as the int 0 are skipped
+        (src/phase_net/phase_net.py:91-93). """
+        high = vals.high_level
+        N, _, H, W = high.shape
+        plan = self._plan(H, W, high.device)
+        keep = []
+
+        def prep(t):
+            if isinstance(t, (int, float)):
+                return None
+            t = t.contiguous().float()
+            keep.append(t)
+            return t
+        phase = [prep(t) for t in vals.phase]
+        amp = [prep(t) for t in vals.amplitude]
+        high_c, low_c = prep(high), prep(vals.low_level)
+        out = torch.empty((N, H, W), dtype=torch.float32, device=high.device)
+        with torch.cuda.device(high.device):
+            _lib.check(_lib.lib().fvfi_pyr_reconstruct(plan.handle, high_c.data_ptr(), ptr_array(phase), ptr_array(amp),
+                                                       low_c.data_ptr(), N, out.data_ptr(),
+                                                       plan.workspace(N).data_ptr(), _lib.stream_ptr()))
+        return out
+
+    def inv_filter_sparse(self, vals, use_high=True, use_low=True, levels=None):
+        """inv_filter with whole components dropped instead of zero-filled copies -- the fused form
+        of get_last_value_levels / get_first_value_levels (src/train/utils.py:242-320)."""
+        high = vals.high_level
+        N, _, H, W = high.shape
+        plan = self._plan(H, W, high.device)
+        L = plan.L
+        levels = set(range(L)) if levels is None else set(levels)
+        phase = [vals.phase[l].contiguous() if l in levels else None for l in range(L)]
+        amp = [vals.amplitude[l].contiguous() if l in levels else None for l in range(L)]
+        high_c = high.contiguous() if use_high else None
+        low_c = vals.low_level.contiguous() if use_low else None
+        out = torch.empty((N, H, W), dtype=torch.float32, device=high.device)
+        with torch.cuda.device(high.device):
+            _lib.check(_lib.lib().fvfi_pyr_reconstruct(plan.handle, _lib.ptr(high_c), ptr_array(phase), ptr_array(amp),
+                                                       _lib.ptr(low_c), N, out.data_ptr(),
+                                                       plan.workspace(N).data_ptr(), _lib.stream_ptr()))
+        return out
+
+    # ---- API-compat helpers (the reference calls these from filter / inv_filter) -------------
+    def coeff_to_values(self, coeff):
+        """pyramid.py:48-78, vectorised: band list -> (phase, amplitude) in [N*nb,1,h,w] layout."""
+        nlevels = len(coeff) - 2
+        phase, amplitude = [], []
+        for level in range(nlevels):
+            z = torch.stack([torch.view_as_complex(b.contiguous()) for b in coeff[level + 1]], 1)  # [N,nb,h,w]
+            z = z.reshape(-1, 1, z.shape[-2], z.shape[-1])
+            phase.append(torch.angle(z))        # imag(log z)
+            amplitude.append(torch.abs(z))
+        return DecompValues(high_level=coeff[0].unsqueeze(1), low_level=coeff[-1].unsqueeze(1), phase=phase,
+                            amplitude=amplitude)
+
+    def reorder(self, input, ndims):
+        """pyramid.py:80-83."""
+        nbands = int(input[0].shape[0] / ndims)
+        return [[x.reshape(ndims, nbands, x.shape[2], x.shape[3])[:, j] for j in range(nbands)] for x in input]
+
+    def values_to_coeff(self, values):
+        """pyramid.py:85-112, vectorised: polar -> complex band list."""
+        ndims = values.high_level.shape[0]
+        coeff = [values.high_level.squeeze(1)]
+        for ph, am in zip(values.phase, values.amplitude):
+            nb = ph.shape[0] // ndims
+            z = torch.stack((torch.cos(ph) * am, torch.sin(ph) * am), -1)           # [N*nb,1,h,w,2]
+            z = z.reshape(ndims, nb, ph.shape[2], ph.shape[3], 2)
+            coeff.append([z[:, b].contiguous() for b in range(nb)])
+        coeff.append(values.low_level.squeeze(1))
+        return coeff

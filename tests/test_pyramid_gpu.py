@@ -1,0 +1,159 @@
+"""GPU parity tests of the steerable pyramid kernels (through the C-ABI) against the CPU oracle
+(oracle/steerable_shim.py, fp64 mode) and the golden fixtures of the reference's Pyramid wrapper.
+
+Tolerances (fp32 kernels vs fp64 oracle; coefficients are NOT normalised -- a band at level l has
+magnitude ~ image_sum/(h_l w_l)-scaled spectra, so errors are stated relative to the level max):
+  complex band coefficients : 1e-5 * max|band level|   (3e-6 of it is the closed-form angular mask vs
+                                                        the oracle's 1024-step LUT)
+  reconstruction            : 3e-5 absolute on [0,1] images (north star: 1e-4)
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import steerable_shim as ss
+
+pytestmark = pytest.mark.gpu
+S2 = np.sqrt(2)
+CASES = [(2, 256, 256, 12), (1, 90, 150, 8), (2, 135, 241, 9), (3, 48, 64, 6), (1, 33, 57, 5)]
+
+
+def _img(N, H, W, seed=0):
+    return torch.rand((N, H, W), generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.mark.parametrize("N,H,W,height", CASES)
+def test_build_complex_vs_oracle(N, H, W, height):
+    from fvfi.steerable import SCFpyr_PyTorch
+    img = _img(N, H, W)
+    ref = ss.SCFpyr_PyTorch(height=height, nbands=4, scale_factor=S2, precision="fp64").build(img.unsqueeze(1))
+    got = SCFpyr_PyTorch(height=height, nbands=4, scale_factor=S2, device="cuda").build(img.unsqueeze(1).cuda())
+    assert len(got) == height and len(got[1]) == 4
+    assert float((got[0].cpu() - ref[0]).abs().max()) <= 2e-6
+    assert float((got[-1].cpu() - ref[-1]).abs().max()) <= 1e-5 * float(ref[-1].abs().max())
+    for l in range(1, height - 1):
+        scale = max(float(b.abs().max()) for b in ref[l])
+        for b in range(4):
+            assert got[l][b].shape == ref[l][b].shape
+            err = float((got[l][b].cpu() - ref[l][b]).abs().max())
+            assert err <= 1e-5 * scale, (l, b, err, scale)
+
+
+@pytest.mark.parametrize("N,H,W,height", CASES)
+def test_reconstruct_complex_vs_oracle(N, H, W, height):
+    from fvfi.steerable import SCFpyr_PyTorch
+    img = _img(N, H, W, seed=1)
+    opyr = ss.SCFpyr_PyTorch(height=height, nbands=4, scale_factor=S2, precision="fp64")
+    c = opyr.build(img.unsqueeze(1))
+    # perturb the coefficients so the band spectra are no longer one-sided (what PhaseNet does)
+    g = torch.Generator().manual_seed(5)
+    c2 = [c[0]] + [[b * (0.5 + torch.rand(b.shape, generator=g)) for b in lv] for lv in c[1:-1]] + [c[-1] * 1.1]
+    ref = opyr.reconstruct(c2)
+    gpyr = SCFpyr_PyTorch(height=height, nbands=4, scale_factor=S2, device="cuda")
+    dev = [c2[0].cuda()] + [[b.cuda() for b in lv] for lv in c2[1:-1]] + [c2[-1].cuda()]
+    got = gpyr.reconstruct(dev)
+    assert float((got.cpu() - ref).abs().max()) <= 3e-5
+    # skipped level (int 0) == zero contribution
+    dev0 = list(dev)
+    dev0[2] = 0
+    c0 = list(c2)
+    c0[2] = 0
+    assert float((gpyr.reconstruct(dev0).cpu() - opyr.reconstruct(c0)).abs().max()) <= 3e-5
+
+
+@pytest.mark.parametrize("N,H,W,height", CASES)
+def test_filter_round_trip_and_values(N, H, W, height):
+    from fvfi.pyramid import Pyramid
+    img = _img(N, H, W, seed=2)
+    pyr = Pyramid(height=height, nbands=4, scale_factor=S2, device=torch.device("cuda"))
+    vals = pyr.filter(img.cuda())
+    sizes = ss.level_sizes(H, W, height, S2)
+    assert vals.high_level.shape == (N, 1, H, W) and vals.low_level.shape == (N, 1) + sizes[-1]
+    assert len(vals.phase) == height - 2
+    oc = ss.SCFpyr_PyTorch(height=height, nbands=4, scale_factor=S2, precision="fp64").build(img.unsqueeze(1))
+    for l, (h, w) in enumerate(sizes[:-1]):
+        assert vals.phase[l].shape == (N * 4, 1, h, w) and vals.amplitude[l].shape == (N * 4, 1, h, w)
+        z = torch.stack([torch.view_as_complex(b) for b in oc[1 + l]], 1).reshape(N * 4, 1, h, w)  # plane*nb + band
+        scale = float(z.abs().max())
+        amp, ph = vals.amplitude[l].cpu(), vals.phase[l].cpu()
+        assert float((amp - z.abs()).abs().max()) <= 1e-5 * scale
+        # polar -> complex comparison avoids the ill-conditioned phase of near-zero coefficients
+        zz = torch.polar(amp, ph)
+        assert float((zz - z.to(torch.complex64)).abs().max()) <= 1.5e-5 * scale
+        assert float(ph.abs().max()) <= np.pi + 1e-6
+        # fused per-(level, plane) max amplitude (PhaseNet.normalize_vals, phase_net.py:47-59)
+        want = amp.reshape(N, -1).max(1)[0]
+        assert torch.allclose(pyr.last_amp_max[l].cpu(), want, rtol=0, atol=0)
+    rec = pyr.inv_filter(vals)
+    # the algorithm's own round-trip error is ~1e-5 (LUT masks) and larger for tiny odd sizes, so the
+    # reference point is the oracle's round trip, not the image
+    opyr = ss.SCFpyr_PyTorch(height=height, nbands=4, scale_factor=S2, precision="fp64")
+    orec = opyr.reconstruct(oc)
+    assert float((rec.cpu() - orec).abs().max()) <= 3e-5
+    if min(H, W) >= 48:
+        assert float((rec.cpu() - img).abs().max()) <= 4e-5
+    # dropping components == zero-filled copies (utils.py:242-320)
+    zero_low = vals._replace(low_level=torch.zeros_like(vals.low_level))
+    a = pyr.inv_filter(zero_low)
+    b = pyr.inv_filter_sparse(vals, use_low=False)
+    assert float((a - b).abs().max()) <= 1e-6
+
+
+def test_golden_reference_wrapper(golden_dir):
+    from fvfi.pyramid import Pyramid
+    files = sorted(glob.glob(os.path.join(golden_dir, "pyramid_ref_*.npz")))
+    assert files
+    for f in files:
+        z = np.load(f)
+        N, H, W, height, seed = [int(v) for v in z["meta"]]
+        img = _img(N, H, W, seed)
+        pyr = Pyramid(height=height, nbands=4, scale_factor=S2, device=torch.device("cuda"))
+        vals = pyr.filter(img.cuda())
+        assert np.abs(vals.high_level.cpu().numpy() - z["high"]).max() <= 2e-6
+        assert np.abs(vals.low_level.cpu().numpy() - z["low"]).max() <= 1e-5 * np.abs(z["low"]).max()
+        for l in range(height - 2):
+            amp_ref, ph_ref = z["amp%d" % l], z["phase%d" % l]
+            scale = amp_ref.max()
+            amp, ph = vals.amplitude[l].cpu().numpy(), vals.phase[l].cpu().numpy()
+            assert np.abs(amp - amp_ref).max() <= 1.5e-5 * scale
+            assert np.abs(amp * np.exp(1j * ph) - amp_ref * np.exp(1j * ph_ref)).max() <= 2e-5 * scale
+        # reference inv_filter of the reference values
+        rvals = vals._replace(high_level=torch.from_numpy(z["high"]).cuda(), low_level=torch.from_numpy(z["low"]).cuda(),
+                              phase=[torch.from_numpy(z["phase%d" % l]).cuda() for l in range(height - 2)],
+                              amplitude=[torch.from_numpy(z["amp%d" % l]).cuda() for l in range(height - 2)])
+        assert np.abs(pyr.inv_filter(rvals).cpu().numpy() - z["rec"]).max() <= 3e-5
+
+
+def test_full_size_1080p_properties():
+    """Config-3 geometry (1080x1920, height 17, every odd/prime FFT length): round trip, linearity,
+    energy split; checked against the fp64 oracle on one plane."""
+    from fvfi.pyramid import Pyramid
+    from fvfi.pyr_plan import calc_pyr_height
+    H, W = 1080, 1920
+    img = _img(2, H, W, seed=3)
+    height = calc_pyr_height(img)
+    assert height == 17
+    pyr = Pyramid(height=height, nbands=4, scale_factor=S2, device=torch.device("cuda"))
+    x = img.cuda()
+    vals = pyr.filter(x)
+    rec = pyr.inv_filter(vals)
+    assert float((rec - x).abs().max()) <= 5e-5
+    v2 = pyr.filter(2 * x)
+    assert float((v2.amplitude[1] - 2 * vals.amplitude[1]).abs().max()) <= 1e-4 * float(vals.amplitude[1].max())
+    oc = ss.SCFpyr_PyTorch(height=height, nbands=4, scale_factor=S2, precision="fp64").build(img[:1].unsqueeze(1))
+    for l in (0, 1, 5, 14):
+        z = torch.stack([torch.view_as_complex(b) for b in oc[1 + l]], 1)[0]           # [nb,h,w]
+        got = torch.polar(vals.amplitude[l][:4, 0].cpu(), vals.phase[l][:4, 0].cpu())
+        assert float((got - z.to(torch.complex64)).abs().max()) <= 2e-5 * float(z.abs().max()), l
+
+
+def test_errors():
+    from fvfi import FvfiError
+    from fvfi.pyramid import Pyramid
+    with pytest.raises(NotImplementedError):
+        Pyramid(6, 4, S2, torch.device("cpu")).filter(torch.rand(1, 32, 32))
+    with pytest.raises(FvfiError):  # pyramid too tall for the image
+        Pyramid(30, 4, S2, torch.device("cuda")).filter(torch.rand(1, 32, 32).cuda())
