@@ -292,11 +292,14 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    from fvfi import _lib as _fl
+    launches0 = _fl.lib().fvfi_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         wl.step(timed=True)
     e1.record()
+    launches = _fl.lib().fvfi_launch_count() - launches0
     barrier()
     clocks = sampler.stop()
     ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
@@ -315,7 +318,7 @@ def main():
             "config": dict({"workload": wl.name, "frames_per_step_per_gpu": wl.frames_per_step,
                             "l2": "inputs larger than L2 (no flush needed)", "sharding": "frame pairs by batch, no collectives"},
                            **getattr(wl, "config_extra", {})),
-            "clocks": clocks, "gpu_launches": wl.launches_per_step * args.steps,
+            "clocks": clocks, "gpu_launches": int(launches),
             "roofline": wl.roofline(peak, peak_src),
         }
         bar = wl.reference_gpu_kernels() if hasattr(wl, "reference_gpu_kernels") and not args.no_refbar else None

@@ -1,6 +1,8 @@
 // capi.cu -- error plumbing and misc entry points of the C-ABI (include/fvfi.h).
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace fvfi {
@@ -12,6 +14,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
     int dev = 0, n = 0;
@@ -25,4 +30,5 @@ extern "C" {
 int fvfi_version(void) { return 100; }
 const char* fvfi_last_error(void) { return fvfi::g_err; }
 int fvfi_device_sm_count(void) { return fvfi::sm_count(); }
+unsigned long long fvfi_launch_count(void) { return fvfi::g_launches.load(); }
 }

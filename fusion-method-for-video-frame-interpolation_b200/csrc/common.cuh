@@ -10,6 +10,7 @@
 namespace fvfi {
 
 void set_error(const char* fmt, ...);
+void note_launch();  // counts kernel launches issued by this library (fvfi_launch_count)
 
 #define FVFI_CHECK_ARG(cond, ...)            \
     do {                                     \
@@ -31,6 +32,7 @@ void set_error(const char* fmt, ...);
 
 #define FVFI_LAUNCH_CHECK()                                                               \
     do {                                                                                  \
+        ::fvfi::note_launch();                                                            \
         cudaError_t _e = cudaGetLastError();                                              \
         if (_e != cudaSuccess) {                                                          \
             ::fvfi::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \

@@ -1,0 +1,191 @@
+// imgproc.cu -- the per-pixel stages that the reference bounces to the CPU:
+//   RGB <-> Lab   (src/train/transform.py:6-49: skimage.color on the host, then L/100, (a,b+128)/255)
+//   Gaussian sigma blur     (scipy.ndimage.gaussian_filter(h, 5), interpolate_twoframe.py:212-213)
+//   k x k median            (scipy.ndimage.median_filter(f, size=50), interpolate_twoframe.py:221-222)
+// Device-resident replacements so the fusion pipeline never leaves the GPU.
+#include "common.cuh"
+
+namespace fvfi {
+
+// ---- colour ------------------------------------------------------------------------------------
+// sRGB (IEC 61966-2-1) -> linear -> XYZ (D65 / 2 deg) -> CIE L*a*b*, as skimage.color.rgb2lab.
+__device__ __forceinline__ float srgb_to_lin(float c) {
+    return c > 0.04045f ? powf((c + 0.055f) / 1.055f, 2.4f) : c / 12.92f;
+}
+__device__ __forceinline__ float lin_to_srgb(float c) {
+    return c > 0.0031308f ? 1.055f * powf(fmaxf(c, 0.f), 1.f / 2.4f) - 0.055f : c * 12.92f;
+}
+__device__ __forceinline__ float lab_f(float t) { return t > 0.008856f ? cbrtf(t) : 7.787f * t + 16.f / 116.f; }
+__device__ __forceinline__ float lab_finv(float f) { return f > 0.2068966f ? f * f * f : (f - 16.f / 116.f) / 7.787f; }
+
+__global__ void rgb2lab_kernel(const float* __restrict__ rgb, float* __restrict__ lab, size_t plane, int B) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (p >= plane) return;
+    const float* src = rgb + (size_t)n * 3 * plane + p;
+    const float r = srgb_to_lin(src[0]), g = srgb_to_lin(src[plane]), b = srgb_to_lin(src[2 * plane]);
+    const float x = (0.412453f * r + 0.357580f * g + 0.180423f * b) / 0.95047f;
+    const float y = (0.212671f * r + 0.715160f * g + 0.072169f * b);
+    const float z = (0.019334f * r + 0.119193f * g + 0.950227f * b) / 1.08883f;
+    const float fx = lab_f(x), fy = lab_f(y), fz = lab_f(z);
+    float* dst = lab + (size_t)n * 3 * plane + p;
+    dst[0] = (116.f * fy - 16.f) / 100.f;                    // transform.py:9  L / light
+    dst[plane] = (500.f * (fx - fy) + 128.f) / 255.f;        // transform.py:10-11
+    dst[2 * plane] = (200.f * (fy - fz) + 128.f) / 255.f;
+    (void)B;
+}
+
+__global__ void lab2rgb_kernel(const float* __restrict__ lab, float* __restrict__ rgb, size_t plane, int B) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (p >= plane) return;
+    const float* src = lab + (size_t)n * 3 * plane + p;
+    const float L = src[0] * 100.f;                          // transform.py:31-33
+    const float a = src[plane] * 255.f - 128.f, b = src[2 * plane] * 255.f - 128.f;
+    const float fy = (L + 16.f) / 116.f;
+    const float fx = a / 500.f + fy;
+    const float fz = fmaxf(fy - b / 200.f, 0.f);             // skimage clips negative z
+    const float x = lab_finv(fx) * 0.95047f, y = lab_finv(fy), z = lab_finv(fz) * 1.08883f;
+    const float r = 3.2404813432f * x - 1.5371515163f * y - 0.4985363262f * z;
+    const float g = -0.9692549500f * x + 1.8759900015f * y + 0.0415559266f * z;
+    const float bl = 0.0556466391f * x - 0.2040413384f * y + 1.0573110696f * z;
+    float* dst = rgb + (size_t)n * 3 * plane + p;
+    dst[0] = fminf(fmaxf(lin_to_srgb(r), 0.f), 1.f);
+    dst[plane] = fminf(fmaxf(lin_to_srgb(g), 0.f), 1.f);
+    dst[2 * plane] = fminf(fmaxf(lin_to_srgb(bl), 0.f), 1.f);
+    (void)B;
+}
+
+// ---- scipy 'reflect' boundary: (d c b a | a b c d | d c b a) ---------------------------------------
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    const int period = 2 * n;
+    int m = i % period;
+    if (m < 0) m += period;
+    return m < n ? m : period - 1 - m;
+}
+
+// ---- separable Gaussian (one axis per launch), weights in constant-size smem -------------------------
+constexpr int GAUSS_MAX_RADIUS = 64;
+
+template <bool ALONG_X>
+__global__ void __launch_bounds__(256) gauss1d_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                      float sigma, int radius) {
+    __shared__ float wts[2 * GAUSS_MAX_RADIUS + 1];
+    __shared__ float norm;
+    if (threadIdx.x <= radius) {
+        const float v = expf(-0.5f * (float)(threadIdx.x * threadIdx.x) / (sigma * sigma));
+        wts[radius + threadIdx.x] = v;
+        wts[radius - threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i <= 2 * radius; ++i) s += wts[i];
+        norm = 1.f / s;
+    }
+    __syncthreads();
+    const size_t plane = (size_t)H * W;
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= plane) return;
+    const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+    const float* src = in + (size_t)blockIdx.y * plane;
+    float acc = 0.f;
+    for (int t = -radius; t <= radius; ++t) {
+        const float v = ALONG_X ? src[(size_t)y * W + reflect_idx(x + t, W)] : src[(size_t)reflect_idx(y + t, H) * W + x];
+        acc = fmaf(v, wts[radius + t], acc);
+    }
+    out[(size_t)blockIdx.y * plane + p] = acc * norm;
+}
+
+// ---- exact k x k median (rank k*k/2, window [i - k/2, i + k - k/2 - 1], reflect) -------------------------
+// v1: the CTA stages its (16+k-1)^2 neighbourhood as order-preserving uint keys in shared memory and
+// every thread binary-searches the key space for the rank-th smallest (32 counting passes).
+__device__ __forceinline__ unsigned f2key(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+constexpr int MED_T = 16;
+
+__global__ void __launch_bounds__(MED_T * MED_T) median_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
+                                                               int W, int k, int rank) {
+    extern __shared__ unsigned keys[];
+    const int S = MED_T + k - 1;
+    const int x0 = blockIdx.x * MED_T, y0 = blockIdx.y * MED_T;
+    const size_t plane = (size_t)H * W;
+    const float* src = in + (size_t)blockIdx.z * plane;
+    const int lo_off = k / 2;
+    for (int q = threadIdx.x; q < S * S; q += blockDim.x) {
+        const int r = q / S, c = q - r * S;
+        keys[q] = f2key(src[(size_t)reflect_idx(y0 + r - lo_off, H) * W + reflect_idx(x0 + c - lo_off, W)]);
+    }
+    __syncthreads();
+    const int tx = threadIdx.x % MED_T, ty = threadIdx.x / MED_T;
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= W || y >= H) return;
+    const unsigned* base = keys + ty * S + tx;
+    // smallest v with count(key <= v) >= rank + 1
+    unsigned lo = 0u, hi = 0xffffffffu;
+    while (lo < hi) {
+        const unsigned mid = lo + ((hi - lo) >> 1);
+        int cnt = 0;
+        for (int r = 0; r < k; ++r) {
+            const unsigned* row = base + r * S;
+            for (int c = 0; c < k; ++c) cnt += (row[c] <= mid);
+        }
+        if (cnt >= rank + 1) hi = mid; else lo = mid + 1;
+    }
+    out[(size_t)blockIdx.z * plane + (size_t)y * W + x] = key2f(lo);
+}
+
+}  // namespace fvfi
+
+using namespace fvfi;
+
+extern "C" int fvfi_rgb2lab(const float* rgb, float* lab, int B, int H, int W, void* stream) {
+    FVFI_CHECK_ARG(rgb && lab && B > 0 && H > 0 && W > 0 && B <= 65535, "rgb2lab: bad argument");
+    const size_t plane = (size_t)H * W;
+    dim3 grid((unsigned)((plane + 255) / 256), B);
+    rgb2lab_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rgb, lab, plane, B);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
+
+extern "C" int fvfi_lab2rgb(const float* lab, float* rgb, int B, int H, int W, void* stream) {
+    FVFI_CHECK_ARG(rgb && lab && B > 0 && H > 0 && W > 0 && B <= 65535, "lab2rgb: bad argument");
+    const size_t plane = (size_t)H * W;
+    dim3 grid((unsigned)((plane + 255) / 256), B);
+    lab2rgb_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lab, rgb, plane, B);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
+
+extern "C" int fvfi_gaussian_filter(const float* in, float* out, float* tmp, int N, int H, int W, float sigma,
+                                    void* stream) {
+    FVFI_CHECK_ARG(in && out && tmp && N > 0 && H > 0 && W > 0 && N <= 65535 && sigma > 0.f, "gaussian_filter: bad argument");
+    const int radius = (int)(4.0f * sigma + 0.5f);  // scipy: truncate = 4.0
+    FVFI_CHECK_ARG(radius <= GAUSS_MAX_RADIUS, "gaussian_filter: sigma too large (radius %d > %d)", radius, GAUSS_MAX_RADIUS);
+    const size_t plane = (size_t)H * W;
+    dim3 grid((unsigned)((plane + 255) / 256), N);
+    // scipy filters axis 0 (rows, i.e. along y) first, then axis 1
+    gauss1d_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, tmp, H, W, sigma, radius);
+    FVFI_LAUNCH_CHECK();
+    gauss1d_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(tmp, out, H, W, sigma, radius);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
+
+extern "C" int fvfi_median_filter(const float* in, float* out, int N, int H, int W, int size, void* stream) {
+    FVFI_CHECK_ARG(in && out && N > 0 && H > 0 && W > 0 && N <= 65535, "median_filter: bad argument");
+    FVFI_CHECK_ARG(size >= 1 && size <= 96, "median_filter: size must be 1..96");
+    const int S = MED_T + size - 1;
+    const size_t smem = (size_t)S * S * sizeof(unsigned);
+    if (smem > 48 * 1024) FVFI_CUDA(cudaFuncSetAttribute(median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(W, MED_T), ceil_div(H, MED_T), N);
+    median_kernel<<<grid, MED_T * MED_T, smem, (cudaStream_t)stream>>>(in, out, H, W, size, (size * size) / 2);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}

@@ -28,11 +28,16 @@ _PROTOS = {
     "fvfi_version": (c_int, []),
     "fvfi_last_error": (ctypes.c_char_p, []),
     "fvfi_device_sm_count": (c_int, []),
+    "fvfi_launch_count": (ctypes.c_ulonglong, []),
     "fvfi_adacof_forward": (c_int, [c_fp] * 5 + [c_int] * 9 + [c_fp]),
     "fvfi_adacof_backward": (c_int, [c_fp] * 9 + [c_int] * 10 + [c_fp]),
     "fvfi_adacofnet_tail": (c_int, [c_fp] * 11 + [c_int] * 5 + [c_fp]),
     "fvfi_adacofnet_warp_blend": (c_int, [c_fp] * 13 + [c_int] * 7 + [c_fp]),
     "fvfi_fusion_blend": (c_int, [c_fp] * 3 + [c_size, c_fp]),
+    "fvfi_rgb2lab": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_fp]),
+    "fvfi_lab2rgb": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_fp]),
+    "fvfi_gaussian_filter": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, ctypes.c_float, c_fp]),
+    "fvfi_median_filter": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "fvfi_adacof_forward_host": (c_int, [c_fp] * 5 + [c_int] * 8),
     "fvfi_adacof_backward_host": (c_int, [c_fp] * 8 + [c_int] * 8),
     "fvfi_pyr_plan_create": (c_int, [c_int, c_int, c_int, c_int, ctypes.c_double, ctypes.POINTER(c_fp)]),

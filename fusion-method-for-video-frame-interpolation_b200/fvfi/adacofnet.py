@@ -117,7 +117,7 @@ class AdaCoFNet(torch.nn.Module):
         """The reference wraps models in src/adacof/models/__init__.py:Model whose ``load`` forwards here."""
         self.load_state_dict(state_dict)
 
-    def forward(self, frame0, frame2):
+    def forward(self, frame0, frame2, return_warped=True):
         h0, w0 = int(frame0.shape[2]), int(frame0.shape[3])
         if h0 != int(frame2.shape[2]) or w0 != int(frame2.shape[3]):
             sys.exit('Frame sizes do not match')                                   # fusion_adacofnet.py:177-178
@@ -144,10 +144,11 @@ class AdaCoFNet(torch.nn.Module):
         else:
             t1, t2, frame1, mask = adacof.adacofnet_warp_blend(p0, p2, W1.contiguous(), A1.contiguous(), B1.contiguous(),
                                                                W2.contiguous(), A2.contiguous(), B2.contiguous(),
-                                                               Occ.contiguous(), self.dilation)
-        if h0 != t1.shape[2] or w0 != t1.shape[3]:
+                                                               Occ.contiguous(), self.dilation, want_t=return_warped)
+        if h0 != frame1.shape[2] or w0 != frame1.shape[3]:
             # crop back; NB the reference returns tensorAdaCoF2 as tensorAdaCoF1 when the width was padded
             # (fusion_adacofnet.py:225) -- fixed here, frame1/mask are unaffected.
-            t1, t2 = t1[:, :, :h0, :w0], t2[:, :, :h0, :w0]
-            frame1, mask = frame1[:, :, :h0, :w0], mask[:, :, :h0, :w0]
+            if t1 is not None:
+                t1, t2 = t1[:, :, :h0, :w0], t2[:, :, :h0, :w0]
+            frame1, mask = frame1[:, :, :h0, :w0].contiguous(), mask[:, :, :h0, :w0].contiguous()
         return t1, t2, frame1, mask

@@ -1,0 +1,122 @@
+"""The end-to-end fusion recipe of the reference (``interp``,
+src/fusion_net/interpolate_twoframe.py:82-334) as a device-resident, batched module.
+
+``FusionPipeline(H, W, device)`` owns the three networks (state-dict compatible with the reference's
+``phase_net.pt`` / ``fusion_net.pt`` / AdaCoF checkpoints) and the pyramid plan;
+``pipe(rgb1, rgb2)`` maps two batches of frames [B,3,H,W] in [0,1] to the interpolated frame
+[B,3,H,W].  Nothing leaves the GPU: Lab conversion, pyramid, PhaseNet, the four AdaCoFNet passes
+(each = kernel estimation + ONE fused two-warp/blend/uncertainty kernel), Gaussian / median
+uncertainty maps and the FusionNet blend all run on the current CUDA stream (the reference makes
+>= 9 host round trips per frame).
+"""
+import math
+import types
+
+import torch
+
+from . import filters, transform, utils
+from .adacofnet import AdaCoFNet
+from .fusion_net import FusionNet
+from .phase_net import PhaseNet
+from .pyramid import Pyramid
+
+
+class FusionPipeline(torch.nn.Module):
+    def __init__(self, H, W, device, kernel_size=5, dilation=1, phase_plane_chunk=None):
+        super().__init__()
+        self.H, self.W = int(H), int(W)
+        self.device = torch.device(device)
+        height = utils.calc_pyr_height(torch.empty(3, H, W, device="meta"))                    # :124-129
+        self.pyr = Pyramid(height=height, nbands=4, scale_factor=math.sqrt(2), device=self.device)
+        self.phase_net = PhaseNet(self.pyr, self.device, num_img=2).eval()                     # :135-137
+        self.fusion_net = FusionNet().to(self.device).eval()                                   # :143-145
+        self.adacof = AdaCoFNet(types.SimpleNamespace(kernel_size=kernel_size, dilation=dilation, gpu_id=0)
+                                ).to(self.device).eval()                                       # :99-103
+        self.phase_net.plane_chunk = phase_plane_chunk
+        self.stages = None  # set to a dict to capture intermediates (tests)
+        self.timing = None  # set to a list to collect (stage, start_event, end_event) (bench)
+
+    def _tick(self, name):
+        """Stage timer: CUDA events on the current stream, only when ``self.timing`` is a list."""
+        if self.timing is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.timing.append((name, ev))
+
+    def load_state(self, state):
+        self.phase_net.load_state_dict(state["phase_net"])
+        self.fusion_net.load_state_dict(state["fusion_net"])
+        self.adacof.load_state_dict(state["adacof"])
+
+    @torch.no_grad()
+    def forward(self, rgb1, rgb2):
+        B, _, H, W = rgb1.shape
+        assert (H, W) == (self.H, self.W) and rgb2.shape == rgb1.shape
+        pyr, r_shape = self.pyr, (B, 3, H, W)
+        self._tick('start')
+        lab1, lab2 = transform.rgb2lab(rgb1), transform.rgb2lab(rgb2)                           # :148-149
+        _, _, ada_pred, flow_var_map = self.adacof(rgb1, rgb2, return_warped=False)                                  # :156
+        flow_var_map = flow_var_map.squeeze(1)
+        self._tick('lab+adacofnet#1')
+        # PhaseNet branch (:168-192)
+        vals = pyr.filter(torch.cat((lab1.reshape(-1, H, W), lab2.reshape(-1, H, W)), 0), want_high=False)
+        vals_in = self.phase_net.normalize_vals(utils.get_concat_layers_inf(pyr, utils.separate_vals(vals, 2)))
+        del vals
+        self._tick('pyr.filter(12 planes/frame)+normalize')
+        vals_pred = self.phase_net(vals_in)
+        self._tick('phase_net')
+        del vals_in
+        lab_pred = pyr.inv_filter_sparse(vals_pred, use_high=False).reshape(r_shape)            # high_level is zeros (:127-128)
+        del vals_pred
+        self._tick('pyr.inv_filter(3 planes/frame)')
+        phase_pred = transform.lab2rgb(lab_pred)                                                # :192
+        # uncertainty maps (:197-225)
+        vals_ada, vals_ph = utils.separate_vals(
+            pyr.filter(torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0)), 2)
+        self._tick('lab2rgb+pyr.filter(6 planes/frame)')
+        h_freq = pyr.inv_filter_sparse(vals_ada, use_low=False, levels=[0]).reshape(r_shape).mean(1)     # get_last_value_levels(.,1)
+        h_freq_ph = pyr.inv_filter_sparse(vals_ph, use_low=False, levels=[0]).reshape(r_shape).mean(1)
+        h_freq_diff = ((h_freq - h_freq_ph).abs() * 100).clamp(min=0, max=1.0)
+        self._tick('pyr.inv_filter(level0 x2)')
+        phase_uncertainty = filters.gaussian_filter(h_freq_diff, 5)
+        self._tick('gaussian')
+        L = len(vals_ph.phase)
+        # subtract_values + get_first_value_levels(., 6): only the 6 coarsest levels and the low pass are used
+        keep = range(L - 6, L)
+        vals_diff = vals_ph._replace(
+            low_level=(vals_ph.low_level - vals_ada.low_level).abs(),
+            phase=[(vals_ph.phase[l] - vals_ada.phase[l]).abs() if l in keep else None for l in range(L)],
+            amplitude=[(vals_ph.amplitude[l] - vals_ada.amplitude[l]).abs() if l in keep else None for l in range(L)])
+        freq_diff = pyr.inv_filter_sparse(vals_diff, use_high=False, levels=keep).reshape(r_shape).mean(1) * 30
+        del vals_diff, vals_ada, vals_ph
+        self._tick('pyr.inv_filter(coarse6)')
+        ada_uncertainty = ((freq_diff - filters.median_filter(freq_diff, 50)).abs() * 5).clamp(0, 1)
+        self._tick('median50')
+        # baseline (:228-238)
+        inb1 = self.adacof(rgb1, phase_pred, return_warped=False)[2]
+        inb2 = self.adacof(phase_pred, rgb2, return_warped=False)[2]
+        base = self.adacof(inb1, inb2, return_warped=False)[2]
+        self._tick('adacofnet#2-4')
+        # fusion (:324-330)
+        other = torch.cat([lab1, lab2], 1)
+        maps = torch.stack([ada_uncertainty, phase_uncertainty, flow_var_map], 1)
+        final = self.fusion_net(base, ada_pred, phase_pred, other, maps, variant=0)
+        self._tick('fusion_net')
+        if self.stages is not None:
+            self.stages.update(lab1=lab1, lab2=lab2, ada_pred=ada_pred, flow_var_map=flow_var_map, lab_pred=lab_pred,
+                               phase_pred=phase_pred, phase_uncertainty=phase_uncertainty,
+                               ada_uncertainty=ada_uncertainty, freq_diff=freq_diff, h_freq_diff=h_freq_diff, base=base,
+                               final=final)
+        return final
+
+    def interpolate_host(self, rgb1_host, rgb2_host, out_host=None):
+        """End-to-end call on HOST (pinned) tensors: H2D copy of the two frames, the pipeline, D2H of the result."""
+        d1 = rgb1_host.to(self.device, non_blocking=True)
+        d2 = rgb2_host.to(self.device, non_blocking=True)
+        out = self.forward(d1, d2)
+        if out_host is None:
+            out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host

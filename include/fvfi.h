@@ -46,6 +46,8 @@ int fvfi_version(void);
 const char* fvfi_last_error(void);
 /* Device properties the library was built for / sees: returns SM count of the current device, or -1. */
 int fvfi_device_sm_count(void);
+/* Number of CUDA kernels this library has launched in the calling process (evidence for bench.py's gpu_launches). */
+unsigned long long fvfi_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------
  * AdaCoF warp.  Replaces FunctionAdaCoF.forward + kernel_AdaCoF_updateOutput
@@ -84,6 +86,19 @@ int fvfi_adacofnet_warp_blend(const float* in1, const float* in2, const float* w
 
 /* FusionNet's last step (src/fusion_net/fusion_net.py:67-77): out = clamp(base + tanh(x), 0, 1). */
 int fvfi_fusion_blend(const float* base, const float* x_pre_tanh, float* out, size_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-pixel stages the reference runs on the host CPU, device-resident here.
+ * rgb/lab [B,3,H,W] planar.  Replaces rgb2lab / lab2rgb (src/train/transform.py:6-49: skimage.color,
+ * then L/100 and (a,b+128)/255). */
+int fvfi_rgb2lab(const float* rgb, float* lab, int B, int H, int W, void* stream);
+int fvfi_lab2rgb(const float* lab, float* rgb, int B, int H, int W, void* stream);
+/* scipy.ndimage.gaussian_filter(x, sigma) on N maps [N,H,W] (truncate 4, mode 'reflect';
+ * src/fusion_net/interpolate_twoframe.py:212-213).  tmp: scratch of the same size. */
+int fvfi_gaussian_filter(const float* in, float* out, float* tmp, int N, int H, int W, float sigma, void* stream);
+/* scipy.ndimage.median_filter(x, size=size) on N maps (rank size*size/2, mode 'reflect';
+ * interpolate_twoframe.py:221-222).  Exact. */
+int fvfi_median_filter(const float* in, float* out, int N, int H, int W, int size, void* stream);
 
 /* Host-buffer variants for end-to-end timing: pointers are HOST memory (pinned preferred);
  * the call does H2D, the kernel(s), D2H and synchronises. */
