@@ -22,7 +22,8 @@ class PipelineWorkload:
         torch.backends.cudnn.allow_tf32 = self.tf32
         torch.backends.cuda.matmul.allow_tf32 = self.tf32
         torch.backends.cudnn.benchmark = True
-        self.pipe = FusionPipeline(self.H, self.W, device, phase_plane_chunk=int(os.environ.get("FVFI_PLANE_CHUNK", "12")))
+        self.pipe = FusionPipeline(self.H, self.W, device, phase_plane_chunk=int(os.environ.get("FVFI_PLANE_CHUNK", "6")))
+        self.pipe.max_batch = int(os.environ.get("FVFI_MAX_BATCH", "4"))
         self.pipe.load_state(fp.seeded_state(0))
         r1, r2 = fp.seeded_frames(1, self.H, self.W, seed)
         g = torch.Generator().manual_seed(seed)
@@ -37,7 +38,8 @@ class PipelineWorkload:
         self.stage_ms = {}
         self.nsteps = 0
         self.config_extra = {"tf32_convs": self.tf32, "convs": "cuDNN via torch.nn.Conv2d (scaffolding)",
-                             "phase_plane_chunk": self.pipe.phase_net.plane_chunk}
+                             "phase_plane_chunk": self.pipe.phase_net.plane_chunk,
+                             "sub_batch": self.pipe.max_batch}
 
     def step(self, timed=False):
         self.pipe.timing = [] if timed else None
@@ -50,6 +52,8 @@ class PipelineWorkload:
     def _collect(self):
         for tl in getattr(self, "_pending", []):
             for (n0, e0), (n1, e1) in zip(tl[:-1], tl[1:]):
+                if n1 == 'start':
+                    continue  # boundary between two sub-batches
                 self.stage_ms[n1] = self.stage_ms.get(n1, 0.0) + e0.elapsed_time(e1)
             self.nsteps += 1
         self._pending = []

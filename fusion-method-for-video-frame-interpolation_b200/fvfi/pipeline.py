@@ -34,6 +34,7 @@ class FusionPipeline(torch.nn.Module):
                                 ).to(self.device).eval()                                       # :99-103
         self.phase_net.plane_chunk = phase_plane_chunk
         self.stages = None  # set to a dict to capture intermediates (tests)
+        self.max_batch = 4  # frame pairs per sub-batch at full HD (see forward)
         self.timing = None  # set to a list to collect (stage, start_event, end_event) (bench)
 
     def _tick(self, name):
@@ -51,6 +52,24 @@ class FusionPipeline(torch.nn.Module):
 
     @torch.no_grad()
     def forward(self, rgb1, rgb2):
+        B = rgb1.shape[0]
+        if B > self.max_batch:
+            # every stage is per-sample, so a large batch is a loop over sub-batches (keeps every tensor
+            # below 2^31 elements -- torch's bilinear upsample / cuDNN limit -- and the working set bounded)
+            outs = [self.forward(rgb1[i:i + self.max_batch], rgb2[i:i + self.max_batch])
+                    for i in range(0, B, self.max_batch)]
+            return torch.cat(outs, 0)
+        base, ada_pred, phase_pred, other, maps = self.fusion_inputs(rgb1, rgb2)
+        final = self.fusion_net(base, ada_pred, phase_pred, other, maps, variant=0)                 # :330
+        self._tick('fusion_net')
+        if self.stages is not None:
+            self.stages["final"] = final
+        return final
+
+    @torch.no_grad()
+    def fusion_inputs(self, rgb1, rgb2):
+        """Everything of the recipe up to FusionNet's five inputs (``Trainer.predict`` runs exactly this part
+        under no_grad, src/fusion_net/trainer.py:65-213)."""
         B, _, H, W = rgb1.shape
         assert (H, W) == (self.H, self.W) and rgb2.shape == rgb1.shape
         pyr, r_shape = self.pyr, (B, 3, H, W)
@@ -101,14 +120,11 @@ class FusionPipeline(torch.nn.Module):
         # fusion (:324-330)
         other = torch.cat([lab1, lab2], 1)
         maps = torch.stack([ada_uncertainty, phase_uncertainty, flow_var_map], 1)
-        final = self.fusion_net(base, ada_pred, phase_pred, other, maps, variant=0)
-        self._tick('fusion_net')
         if self.stages is not None:
             self.stages.update(lab1=lab1, lab2=lab2, ada_pred=ada_pred, flow_var_map=flow_var_map, lab_pred=lab_pred,
                                phase_pred=phase_pred, phase_uncertainty=phase_uncertainty,
-                               ada_uncertainty=ada_uncertainty, freq_diff=freq_diff, h_freq_diff=h_freq_diff, base=base,
-                               final=final)
-        return final
+                               ada_uncertainty=ada_uncertainty, freq_diff=freq_diff, h_freq_diff=h_freq_diff, base=base)
+        return base, ada_pred, phase_pred, other, maps
 
     def interpolate_host(self, rgb1_host, rgb2_host, out_host=None):
         """End-to-end call on HOST (pinned) tensors: H2D copy of the two frames, the pipeline, D2H of the result."""
