@@ -98,8 +98,16 @@ __global__ void __launch_bounds__(256) gauss1d_kernel(const float* __restrict__ 
 }
 
 // ---- exact k x k median (rank k*k/2, window [i - k/2, i + k - k/2 - 1], reflect) -------------------------
-// v1: the CTA stages its (16+k-1)^2 neighbourhood as order-preserving uint keys in shared memory and
-// every thread binary-searches the key space for the rank-th smallest (32 counting passes).
+// Order statistics must be exact (scipy's rank filter), so no histogram approximation.
+//
+// Fast path (median_rank_kernel): a CTA owns a 32x16 output tile.  It stages the (32+k-1)x(16+k-1)
+// neighbourhood as (order-preserving key, position) pairs, BITONIC-SORTS it once in shared memory, and
+// replaces every sample by its RANK in the region.  A window's median is then "the rank-th set bit" of a
+// window-membership bitmap over rank space: one warp per output row builds the bitmap of its first window
+// (k*k bit sets) and SLIDES it along x -- k bit clears + k bit sets per pixel -- and finds the wanted set bit
+// with popcounts + a warp scan + __fns.  ~60 warp instructions per pixel instead of 32 counting passes over
+// k*k samples.
+// Fallback (median_bisect_kernel): per-thread bisection over the key space, any k <= 96.
 __device__ __forceinline__ unsigned f2key(float f) {
     const unsigned u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -108,10 +116,100 @@ __device__ __forceinline__ float key2f(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+constexpr int MR_TW = 32, MR_TH = 16, MR_THREADS = MR_TH * 32;
+constexpr int MR_MAX_N = 8192;
+
+__global__ void __launch_bounds__(MR_THREADS) median_rank_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                 int H, int W, int k, int rank, int npad) {
+    extern __shared__ unsigned long long pairs[];                      // npad (key << 32 | pos)
+    const int RW = MR_TW + k - 1, RH = MR_TH + k - 1, n = RW * RH;
+    unsigned short* rank_of = (unsigned short*)(pairs + npad);         // n
+    const int nwords = (n + 31) >> 5;
+    const int wpl = (nwords + 31) >> 5;                                // bitmap words per lane
+    unsigned* bitmaps = (unsigned*)(rank_of + ((n + 1) & ~1));         // MR_TH x (wpl*32)
+    const int x0 = blockIdx.x * MR_TW, y0 = blockIdx.y * MR_TH;
+    const size_t plane = (size_t)H * W;
+    const float* src = in + (size_t)blockIdx.z * plane;
+    const int lo_off = k / 2;
+    for (int q = threadIdx.x; q < npad; q += MR_THREADS) {
+        unsigned long long v = 0xffffffffffffffffull;
+        if (q < n) {
+            const int r = q / RW, c = q - r * RW;
+            const unsigned key = f2key(src[(size_t)reflect_idx(y0 + r - lo_off, H) * W + reflect_idx(x0 + c - lo_off, W)]);
+            v = ((unsigned long long)key << 32) | (unsigned)q;
+        }
+        pairs[q] = v;
+    }
+    __syncthreads();
+    for (int kk = 2; kk <= npad; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npad; i += MR_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = pairs[i], b = pairs[ixj];
+                    if ((a > b) == ((i & kk) == 0)) { pairs[i] = b; pairs[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int r = threadIdx.x; r < n; r += MR_THREADS) rank_of[(unsigned)(pairs[r] & 0xffffffffu)] = (unsigned short)r;
+    const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    unsigned* bm = bitmaps + ty * (wpl * 32);
+    for (int i = lane; i < wpl * 32; i += 32) bm[i] = 0u;
+    __syncthreads();
+    const int y = y0 + ty;
+    if (y >= H) return;
+    // first window of this output row
+    for (int q = lane; q < k * k; q += 32) {
+        const int dy = q / k, dx = q - dy * k;
+        const unsigned r = rank_of[(ty + dy) * RW + dx];
+        atomicOr(&bm[r >> 5], 1u << (r & 31));
+    }
+    __syncwarp();
+    const int xe = min(MR_TW, W - x0);
+    for (int tx = 0; tx < xe; ++tx) {
+        if (tx > 0) {   // slide: drop column tx-1, add column tx+k-1
+            for (int dy = lane; dy < k; dy += 32) {
+                const unsigned rr = rank_of[(ty + dy) * RW + tx - 1];
+                atomicAnd(&bm[rr >> 5], ~(1u << (rr & 31)));
+                const unsigned ra = rank_of[(ty + dy) * RW + tx + k - 1];
+                atomicOr(&bm[ra >> 5], 1u << (ra & 31));
+            }
+            __syncwarp();
+        }
+        // locate the (rank+1)-th set bit: lane owns words [lane*wpl, lane*wpl + wpl)
+        int cnt = 0;
+        for (int i = 0; i < wpl; ++i) cnt += __popc(bm[lane * wpl + i]);
+        int incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int excl = incl - cnt;
+        const unsigned owner = __ballot_sync(0xffffffffu, excl <= rank && rank < incl);
+        if (owner && lane == __ffs(owner) - 1) {
+            int need = rank - excl;   // 0-based index among this lane's set bits
+            for (int i = 0; i < wpl; ++i) {
+                const unsigned wv = bm[lane * wpl + i];
+                const int pc = __popc(wv);
+                if (need < pc) {
+                    const unsigned bit = __fns(wv, 0, need + 1);
+                    const int r = ((lane * wpl + i) << 5) + (int)bit;
+                    out[(size_t)blockIdx.z * plane + (size_t)y * W + x0 + tx] = key2f((unsigned)(pairs[r] >> 32));
+                    break;
+                }
+                need -= pc;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 constexpr int MED_T = 16;
 
-__global__ void __launch_bounds__(MED_T * MED_T) median_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
-                                                               int W, int k, int rank) {
+__global__ void __launch_bounds__(MED_T * MED_T) median_bisect_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                      int H, int W, int k, int rank) {
     extern __shared__ unsigned keys[];
     const int S = MED_T + k - 1;
     const int x0 = blockIdx.x * MED_T, y0 = blockIdx.y * MED_T;
@@ -127,8 +225,7 @@ __global__ void __launch_bounds__(MED_T * MED_T) median_kernel(const float* __re
     const int x = x0 + tx, y = y0 + ty;
     if (x >= W || y >= H) return;
     const unsigned* base = keys + ty * S + tx;
-    // smallest v with count(key <= v) >= rank + 1
-    unsigned lo = 0u, hi = 0xffffffffu;
+    unsigned lo = 0u, hi = 0xffffffffu;   // smallest v with count(key <= v) >= rank + 1
     while (lo < hi) {
         const unsigned mid = lo + ((hi - lo) >> 1);
         int cnt = 0;
@@ -181,11 +278,26 @@ extern "C" int fvfi_gaussian_filter(const float* in, float* out, float* tmp, int
 extern "C" int fvfi_median_filter(const float* in, float* out, int N, int H, int W, int size, void* stream) {
     FVFI_CHECK_ARG(in && out && N > 0 && H > 0 && W > 0 && N <= 65535, "median_filter: bad argument");
     FVFI_CHECK_ARG(size >= 1 && size <= 96, "median_filter: size must be 1..96");
+    const int rank = (size * size) / 2;
+    const int n = (MR_TW + size - 1) * (MR_TH + size - 1);
+    if (n <= MR_MAX_N) {
+        int npad = 1;
+        while (npad < n) npad <<= 1;
+        const int nwords = (n + 31) / 32, wpl = (nwords + 31) / 32;
+        const size_t smem = (size_t)npad * 8 + (size_t)((n + 1) & ~1) * 2 + (size_t)MR_TH * wpl * 32 * 4;
+        if (smem > 48 * 1024)
+            FVFI_CUDA(cudaFuncSetAttribute(median_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(ceil_div(W, MR_TW), ceil_div(H, MR_TH), N);
+        median_rank_kernel<<<grid, MR_THREADS, smem, (cudaStream_t)stream>>>(in, out, H, W, size, rank, npad);
+        FVFI_LAUNCH_CHECK();
+        return FVFI_OK;
+    }
     const int S = MED_T + size - 1;
     const size_t smem = (size_t)S * S * sizeof(unsigned);
-    if (smem > 48 * 1024) FVFI_CUDA(cudaFuncSetAttribute(median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024)
+        FVFI_CUDA(cudaFuncSetAttribute(median_bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(W, MED_T), ceil_div(H, MED_T), N);
-    median_kernel<<<grid, MED_T * MED_T, smem, (cudaStream_t)stream>>>(in, out, H, W, size, (size * size) / 2);
+    median_bisect_kernel<<<grid, MED_T * MED_T, smem, (cudaStream_t)stream>>>(in, out, H, W, size, rank);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }
