@@ -14,6 +14,7 @@ import torch
 from torch.nn import functional as F
 
 from . import adacof
+from . import conv as tc
 
 
 def moduleNormalize(frame):
@@ -83,7 +84,53 @@ class KernelEstimation(torch.nn.Module):
         self.moduleBeta2 = Subnet(ks2)
         self.moduleOcclusion = Subnet(1, nn.Sigmoid(), last_in=64)
 
+    @staticmethod
+    def _seq_tc(seq, x):
+        """Run an nn.Sequential of Conv2d / ReLU / Upsample / Softmax / Sigmoid with conv+activation fused."""
+        mods = list(seq)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, torch.nn.Conv2d):
+                nxt = mods[i + 1] if i + 1 < len(mods) else None
+                if isinstance(nxt, torch.nn.ReLU):
+                    x = tc.conv_module(m, x, "relu")
+                    i += 2
+                    continue
+                if isinstance(nxt, torch.nn.Sigmoid):
+                    x = tc.conv_module(m, x, "sigmoid")
+                    i += 2
+                    continue
+                x = tc.conv_module(m, x, None)
+            else:
+                x = m(x)
+            i += 1
+        return x
+
+    def _forward_tc(self, rfield0, rfield2):
+        """tcgen05 path of fusion_adacofnet.py:109-155: every conv(+ReLU/sigmoid) is one fused kernel, the
+        pooling / bilinear upsampling / softmax run on NHWC tensors, the seven heads are returned NCHW-contiguous
+        (the warp kernel streams each coefficient plane)."""
+        run = self._seq_tc
+        x = tc.to_nhwc(torch.cat([rfield0, rfield2], 1))
+        c1 = run(self.moduleConv1, x)
+        c2 = run(self.moduleConv2, self.modulePool1(c1))
+        del c1
+        c3 = run(self.moduleConv3, self.modulePool2(c2))
+        c4 = run(self.moduleConv4, self.modulePool3(c3))
+        c5 = run(self.moduleConv5, self.modulePool4(c4))
+        d5 = run(self.moduleUpsample5, run(self.moduleDeconv5, self.modulePool5(c5)))
+        d4 = run(self.moduleUpsample4, run(self.moduleDeconv4, d5 + c5))
+        d3 = run(self.moduleUpsample3, run(self.moduleDeconv3, d4 + c4))
+        d2 = run(self.moduleUpsample2, run(self.moduleDeconv2, d3 + c3))
+        comb = d2 + c2
+        heads = (self.moduleWeight1, self.moduleAlpha1, self.moduleBeta1, self.moduleWeight2, self.moduleAlpha2,
+                 self.moduleBeta2, self.moduleOcclusion)
+        return tuple(run(h, comb).contiguous() for h in heads)
+
     def forward(self, rfield0, rfield2):
+        if tc.use_tc(rfield0) and not self.training:
+            return self._forward_tc(rfield0, rfield2)
         x = torch.cat([rfield0, rfield2], 1)
         c1 = self.moduleConv1(x)
         c2 = self.moduleConv2(self.modulePool1(c1))

@@ -1,0 +1,98 @@
+"""Tensor-core convolution op (C-ABI: fvfi_conv2d_* in include/fvfi.h): stride-1 "same" convolutions of
+the three networks on tcgen05 with 3xTF32 error compensation (fp32-grade results), NHWC activations
+(torch ``channels_last``), fused bias + activation.
+
+``Conv2dTC.apply_module(conv, x, act)`` runs an ``nn.Conv2d`` (weights stay in the module, so reference
+checkpoints load unchanged) through the kernel; packed weights are cached per weight version.
+"""
+import torch
+
+from . import _lib
+
+enabled = True   # use the tcgen05 kernels for inference convolutions (False -> torch/cuDNN scaffolding)
+
+
+def use_tc(x):
+    """Tensor-core path applies to CUDA inference (autograd off: the kernel has no backward; training uses
+    the torch/cuDNN path)."""
+    return enabled and x.is_cuda and not torch.is_grad_enabled()
+
+
+ACT = {None: 0, "none": 0, "relu": 1, "elu": 2, "tanh": 3, "sigmoid": 4}
+_pack_cache = {}
+
+
+def _packed(weight):
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device))
+    hit = _pack_cache.get(id(weight))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    Cout, Cin, KH, KW = weight.shape
+    L = _lib.lib()
+    parts = []
+    w = weight.detach().contiguous().float()
+    for o in range(0, Cout, 256):
+        wo = w[o:o + 256].contiguous()
+        n = L.fvfi_conv2d_packed_weight_floats(wo.shape[0], Cin, KH, KW)
+        buf = torch.empty(n, dtype=torch.float32, device=weight.device)
+        with torch.cuda.device(weight.device):
+            _lib.check(L.fvfi_conv2d_pack_weights(wo.data_ptr(), buf.data_ptr(), wo.shape[0], Cin, KH, KW, _lib.stream_ptr()))
+        parts.append((o, wo.shape[0], buf, wo))
+    _pack_cache[id(weight)] = (key, parts)
+    return parts
+
+
+def to_nhwc(x):
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None):
+    """x [B,Cin,H,W] (any memory format; channels_last avoids a copy) -> [B,Cout,H,W] channels_last.
+    Equivalent to act(F.conv2d(pad(x), weight, bias)) with 'same' padding (K//2) in zeros or reflect mode."""
+    if not x.is_cuda:
+        raise NotImplementedError("fvfi.conv.conv2d: CUDA tensors only")
+    B, Cin, H, W = x.shape
+    Cout, Cin_w, KH, KW = weight.shape
+    assert Cin == Cin_w and KH == KW and KH in (1, 3, 5)
+    xc = to_nhwc(x.float())
+    assert xc.stride(1) == 1
+    ldx = xc.stride(3)                       # floats per pixel
+    if out is None:
+        out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    ldy = out.stride(3)
+    L = _lib.lib()
+    pad_mode = {"zeros": 0, "reflect": 1}[padding_mode]
+    b = None if bias is None else bias.detach().contiguous().float()
+    with torch.cuda.device(x.device):
+        for (o, n, buf, _) in _packed(weight):
+            _lib.check(L.fvfi_conv2d_nhwc(xc.data_ptr(), ldx, buf.data_ptr(), None if b is None else b.data_ptr() + 4 * o,
+                                          out.data_ptr() + 4 * o, ldy, B, H, W, Cin, n, KH, KW, pad_mode, ACT[act],
+                                          _lib.stream_ptr()))
+    return out
+
+
+def conv_module(conv, x, act=None):
+    """Run an nn.Conv2d (stride 1, dilation 1, padding == K//2) through the tensor-core kernel."""
+    k = conv.kernel_size[0]
+    assert conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+    assert conv.padding == (k // 2, k // 2) or (k == 1 and conv.padding == (0, 0))
+    mode = "zeros" if k == 1 else conv.padding_mode
+    return conv2d(x, conv.weight, conv.bias, mode, act)
+
+
+_fold_cache = {}
+
+
+def conv_bn_module(conv, bn, x, act=None):
+    """conv -> BatchNorm2d (eval: running statistics) -> act, with the BN affine folded into the weights."""
+    key = (conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.running_mean._version, bn.running_var._version)
+    hit = _fold_cache.get(id(conv))
+    if hit is None or hit[0] != key:
+        scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach()
+        w = (conv.weight.detach() * scale.view(-1, 1, 1, 1)).contiguous()
+        b = ((conv.bias.detach() if conv.bias is not None else 0) - bn.running_mean) * scale + bn.bias.detach()
+        hit = (key, w, b.contiguous())
+        _fold_cache[id(conv)] = hit
+    k = conv.kernel_size[0]
+    mode = "zeros" if k == 1 else conv.padding_mode
+    return conv2d(x, hit[1], hit[2], mode, act)

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import conv as tc
 
 
 def fusion_blend(base, x):
@@ -64,15 +65,29 @@ class FusionNet(torch.nn.Module):
     def forward(self, base, adacof, phase, other, maps, save=False, variant=0):
         x = torch.cat([base, adacof, phase, other, maps], 1)
         skip = []
-        for layer in self.encoder_layers:
-            x = self.relu(layer(x))
-            skip.append(x)
-            x = self.max_pool(x)
-        x = self.bottleneck_layer(x)
-        for layer, s in zip(self.decoder_layers, skip[::-1]):
-            x = self.deconvolution(self.relu(x))
-            x = x + s
-            x = layer(x)
+        if tc.use_tc(x):
+            # tcgen05 path (fusion_net.py:52-65): conv+ReLU fused, pooling / upsampling on NHWC tensors
+            x = tc.to_nhwc(x)
+            for layer in self.encoder_layers:
+                x = tc.conv_module(layer, x, "relu")
+                skip.append(x)
+                x = self.max_pool(x)
+            x = tc.conv_module(self.bottleneck_layer, x, "relu")    # ReLU of the first decoder step folded in
+            for i, (layer, s) in enumerate(zip(self.decoder_layers, skip[::-1])):
+                x = self.deconvolution(x if i == 0 else self.relu(x))
+                x = x + s
+                x = tc.conv_module(layer, x, None)
+            x = x.contiguous()
+        else:
+            for layer in self.encoder_layers:
+                x = self.relu(layer(x))
+                skip.append(x)
+                x = self.max_pool(x)
+            x = self.bottleneck_layer(x)
+            for layer, s in zip(self.decoder_layers, skip[::-1]):
+                x = self.deconvolution(self.relu(x))
+                x = x + s
+                x = layer(x)
         anchor = phase if variant == 1 else base
         if torch.is_grad_enabled() and x.requires_grad or not x.is_cuda:
             res = self.tanh(x)

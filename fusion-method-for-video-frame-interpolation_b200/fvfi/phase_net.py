@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import conv as tc
 from .pyramid import DecompValues
 
 
@@ -36,6 +37,12 @@ class PhaseNetBlock(nn.Module):
         self.to(device)
 
     def forward(self, x):
+        if tc.use_tc(x) and not self.training:
+            # tcgen05 path: conv+BN(folded)+ELU, conv+ELU, 1x1 conv+tanh -- three fused kernels (phase_net.py:190-200)
+            f = tc.conv_bn_module(self.feature_map[0], self.feature_map[1], x, "elu")
+            f = tc.conv_module(self.feature_map[3], f, "elu")
+            c = tc.conv_module(self.prediction_map[0], f, "tanh")
+            return f, c
         f = self.feature_map(x)
         c = self.prediction_map(f)
         return f, c

@@ -100,6 +100,21 @@ int fvfi_gaussian_filter(const float* in, float* out, float* tmp, int N, int H, 
  * interpolate_twoframe.py:221-222).  Exact. */
 int fvfi_median_filter(const float* in, float* out, int N, int H, int W, int size, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Convolution on the tcgen05 tensor cores (3xTF32 error-compensated, fp32 in/out), NHWC activations.
+ * Replaces torch.nn.Conv2d -> cuDNN for the stride-1 "same" convolutions of PhaseNetBlock
+ * (src/phase_net/phase_net.py:190-199), KernelEstimation (src/fusion_net/fusion_adacofnet.py:19-83) and
+ * FusionNet (src/fusion_net/fusion_net.py:24-36).
+ *   weight_oihw [Cout,Cin,KH,KW] -> packed (fvfi_conv2d_packed_weight_floats floats), once per weight update.
+ *   x: NHWC, x_pixel_stride floats between pixels (>= Cin); y likewise.  Cout <= 256 per call.
+ *   KH == KW in {1,3,5}; pad_mode 0 = zeros, 1 = reflect (torch 'reflect'); activation 0 none, 1 ReLU, 2 ELU,
+ *   3 tanh, 4 sigmoid; bias [Cout] or NULL. */
+size_t fvfi_conv2d_packed_weight_floats(int Cout, int Cin, int KH, int KW);
+int fvfi_conv2d_pack_weights(const float* weight_oihw, float* packed, int Cout, int Cin, int KH, int KW, void* stream);
+int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias, float* y,
+                     int y_pixel_stride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad_mode,
+                     int activation, void* stream);
+
 /* Host-buffer variants for end-to-end timing: pointers are HOST memory (pinned preferred);
  * the call does H2D, the kernel(s), D2H and synchronises. */
 int fvfi_adacof_forward_host(const float* input, const float* weight, const float* off_i, const float* off_j,

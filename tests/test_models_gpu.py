@@ -53,7 +53,18 @@ def test_gaussian_and_median_vs_scipy(H, W):
         assert np.array_equal(m, ref), size       # order statistics: bit exact
 
 
-def test_models_vs_oracle_nets():
+@pytest.fixture(params=["tcgen05", "cudnn"])
+def conv_backend(request):
+    """Every network test runs on both convolution back ends: the tcgen05 3xTF32 kernels (product path) and the
+    torch/cuDNN scaffolding (also the autograd path)."""
+    from fvfi import conv
+    old = conv.enabled
+    conv.enabled = request.param == "tcgen05"
+    yield request.param
+    conv.enabled = old
+
+
+def test_models_vs_oracle_nets(conv_backend):
     """PhaseNet / FusionNet / AdaCoFNet mirrors vs the oracle restatements with one seeded state_dict."""
     import types
     from fvfi.adacofnet import AdaCoFNet
@@ -88,7 +99,7 @@ def test_models_vs_oracle_nets():
         assert float((a.cpu() - b).abs().max()) <= 1e-4, name
 
 
-def test_pipeline_vs_reference_golden(golden_dir):
+def test_pipeline_vs_reference_golden(golden_dir, conv_backend):
     """Full fusion recipe on the GPU vs the fixtures produced by the reference modules on CPU.
     Tolerance: 1e-4 max abs on [0,1] images (the north-star bound) -- measured error is reported."""
     from fvfi.pipeline import FusionPipeline
@@ -103,7 +114,7 @@ def test_pipeline_vs_reference_golden(golden_dir):
         rgb1, rgb2 = fp.seeded_frames(B, H, W, seed)
         out = pipe(rgb1.cuda(), rgb2.cuda()).cpu().numpy()
         errs = {k: float(np.abs(pipe.stages[k].cpu().numpy() - z[k]).max()) for k in z.files if k in pipe.stages}
-        print(os.path.basename(f), {k: "%.1e" % v for k, v in errs.items()})
+        print(conv_backend, os.path.basename(f), {k: "%.1e" % v for k, v in errs.items()})
         assert errs["lab1"] <= 3e-6 and errs["ada_pred"] <= 1e-4 and errs["flow_var_map"] <= 1e-4
         assert errs["lab_pred"] <= 1e-4 and errs["phase_pred"] <= 2e-4   # lab2rgb amplifies Lab error ~2x near black
         assert errs["phase_uncertainty"] <= 1e-3 and errs["ada_uncertainty"] <= 5e-3   # x100 / x150 gains before the clamp
