@@ -79,18 +79,61 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// Called by ALL lanes of the (converged) MMA warp; one elected lane issues.  Keeping the control flow warp-uniform
+// lets the compiler keep descriptors in uniform registers instead of R2UR-ing per instruction.
 __device__ __forceinline__ void tc_commit(unsigned long long* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
                                             unsigned idesc, unsigned accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, pe;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One K=8 step of one filter tap for MT accumulator tiles, 3xTF32: per tile  D += A_lo*B_hi ; D += A_hi*B_lo ; D += A_hi*B_hi.
+// A single asm block: the tensor core consumes an MMA of N <= 128 every 40-64 cycles, which one warp can only sustain
+// if the issue stream is ~3 instructions per MMA (measured: a C++ loop with per-MMA descriptor arithmetic and elect
+// costs ~120 cycles per MMA).  Tile t: A descriptor + 8*t (eight pixels = 8 x 16 B), TMEM columns + t*Npad.
+#define FVFI_MMA3(D, AL, AH)                                                              \
+    "@pe tcgen05.mma.cta_group::1.kind::tf32 [" D "], " AL ", %4, %6, pa;\n\t"            \
+    "@pe tcgen05.mma.cta_group::1.kind::tf32 [" D "], " AH ", %5, %6, pt;\n\t"            \
+    "@pe tcgen05.mma.cta_group::1.kind::tf32 [" D "], " AH ", %4, %6, pt;\n\t"
+template <int MT>
+__device__ __forceinline__ void tc_mma_kstep(unsigned d, unsigned np, unsigned long long al, unsigned long long ah,
+                                             unsigned long long bh, unsigned long long bl, unsigned idesc, unsigned acc) {
+    if (MT == 1) {
+        asm volatile(
+            "{\n\t.reg .pred pe, pa, pt;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+            FVFI_MMA3("%0", "%2", "%3") "}"
+            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc) : "memory");
+    } else if (MT == 2) {
+        asm volatile(
+            "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 al1, ah1;\n\t.reg .b32 d1;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+            "add.u64 al1, %2, 8;\n\tadd.u64 ah1, %3, 8;\n\tadd.u32 d1, %0, %1;\n\t"
+            FVFI_MMA3("%0", "%2", "%3") FVFI_MMA3("d1", "al1", "ah1") "}"
+            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 al1, ah1, al2, ah2, al3, ah3;\n\t.reg .b32 d1, d2, d3;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+            "add.u64 al1, %2, 8;\n\tadd.u64 ah1, %3, 8;\n\tadd.u32 d1, %0, %1;\n\t"
+            "add.u64 al2, %2, 16;\n\tadd.u64 ah2, %3, 16;\n\tadd.u32 d2, d1, %1;\n\t"
+            "add.u64 al3, %2, 24;\n\tadd.u64 ah3, %3, 24;\n\tadd.u32 d3, d2, %1;\n\t"
+            FVFI_MMA3("%0", "%2", "%3") FVFI_MMA3("d1", "al1", "ah1") FVFI_MMA3("d2", "al2", "ah2") FVFI_MMA3("d3", "al3", "ah3") "}"
+            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc) : "memory");
+    }
+}
+
 __device__ __forceinline__ void tc_ld16(unsigned taddr, float* v) {
     unsigned r[16];
     asm volatile(
@@ -121,8 +164,9 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-    switch (act) {
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v) {
+    switch (ACT) {
         case ACT_RELU: return fmaxf(v, 0.f);
         case ACT_ELU: return v > 0.f ? v : expm1f(v);
         case ACT_TANH: return tanhf(v);
@@ -163,6 +207,7 @@ __global__ void conv_pack_weights_kernel(const float* __restrict__ w, float* __r
 }
 
 // ---- the convolution ---------------------------------------------------------------------------------
+template <int ACT>
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [A stages: hi, lo] [B stages] [barriers] [tmem ptr]
@@ -175,6 +220,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
     unsigned long long* b_empty = bars + 4 + CV_MAX_BSTAGES; // [bstages] count 1 (tcgen05.commit)
     unsigned long long* acc_full = bars + 4 + 2 * CV_MAX_BSTAGES;
     unsigned* tmem_ptr = (unsigned*)(acc_full + 1);
+    int* pixoff = (int*)(tmem_ptr + 2);                      // [NPIX] global pixel index of every region pixel, -1 = zero pad
+    float* bias_s = (float*)(((size_t)(pixoff + A.NPIX) + 15) & ~(size_t)15);   // [Npad], 16 B aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int taps = A.KH * A.KW;
@@ -200,42 +247,63 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
         // ================= activation loaders: region -> (hi, lo) canonical tiles =================
         const int padT = A.KH / 2, padL = A.KW / 2;
         const float* X = A.x + (size_t)img * A.H * A.W * A.ldx;
-        const bool vec = ((A.ldx & 3) == 0) && ((((size_t)A.x) & 15) == 0);
+        const bool vec = ((A.ldx & 3) == 0) && ((A.Cin & 3) == 0) && ((((size_t)A.x) & 15) == 0);
+        // the region -> image mapping does not depend on the channel chunk: compute it once
+        for (int pix = threadIdx.x; pix < A.NPIX; pix += CV_LOADERS) {
+            const int r = pix / A.RW, cc = pix - r * A.RW;
+            int gy = y0 + r - padT, gx = x0 + cc - padL;
+            bool ok = true;
+            if (A.pad_mode == PAD_REFLECT) {
+                gy = reflect101(gy, A.H);
+                gx = reflect101(gx, A.W);
+            } else {
+                ok = (gy >= 0 && gy < A.H && gx >= 0 && gx < A.W);
+            }
+            pixoff[pix] = ok ? gy * A.W + gx : -1;
+        }
+        for (int n = threadIdx.x; n < A.Npad; n += CV_LOADERS) bias_s[n] = (A.bias && n < A.Cout) ? __ldg(A.bias + n) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(CV_LOADERS) : "memory");
+        const int total = A.NPIX * 4;
+        constexpr int U = 5;                                       // loads in flight per thread
         for (int c = 0; c < A.nchunks; ++c) {
             const int s = c % CV_ASTAGES;
             if (c >= CV_ASTAGES) mbar_wait(&a_empty[s], ((c / CV_ASTAGES) - 1) & 1);
             float4* hi = (float4*)(a_base + (size_t)s * A.a_stage_bytes);
             float4* lo = (float4*)(a_base + (size_t)s * A.a_stage_bytes + a_half);
             const int cbase = c * CV_CHUNK;
-            for (int q = threadIdx.x; q < A.NPIX * 4; q += CV_LOADERS) {
-                const int pix = q >> 2, kc = q & 3;              // 4 consecutive threads read one pixel's 64 B
-                const int r = pix / A.RW, cc = pix - r * A.RW;
-                int gy = y0 + r - padT, gx = x0 + cc - padL;
-                bool ok = true;
-                if (A.pad_mode == PAD_REFLECT) {
-                    gy = reflect101(gy, A.H);
-                    gx = reflect101(gx, A.W);
-                } else {
-                    ok = (gy >= 0 && gy < A.H && gx >= 0 && gx < A.W);
-                }
-                const int ch = cbase + kc * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok && ch < A.Cin) {
-                    const float* p = X + ((size_t)gy * A.W + gx) * A.ldx + ch;
-                    if (vec && ch + 3 < A.Cin) {
-                        v = __ldg((const float4*)p);
-                    } else {
-                        v.x = __ldg(p);
-                        if (ch + 1 < A.Cin) v.y = __ldg(p + 1);
-                        if (ch + 2 < A.Cin) v.z = __ldg(p + 2);
-                        if (ch + 3 < A.Cin) v.w = __ldg(p + 3);
+            for (int q0 = threadIdx.x; q0 < total; q0 += CV_LOADERS * U) {
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int q = q0 + u * CV_LOADERS;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q < total) {
+                        const int pix = q >> 2, ch = cbase + (q & 3) * 4;   // 4 consecutive threads read one pixel's 64 B
+                        const int off = pixoff[pix];
+                        if (off >= 0 && ch < A.Cin) {
+                            const float* p = X + (size_t)off * A.ldx + ch;
+                            if (vec) {
+                                v[u] = __ldg((const float4*)p);
+                            } else {
+                                v[u].x = __ldg(p);
+                                if (ch + 1 < A.Cin) v[u].y = __ldg(p + 1);
+                                if (ch + 2 < A.Cin) v[u].z = __ldg(p + 2);
+                                if (ch + 3 < A.Cin) v[u].w = __ldg(p + 3);
+                            }
+                        }
                     }
                 }
-                float4 h;
-                h.x = to_tf32_rna(v.x); h.y = to_tf32_rna(v.y); h.z = to_tf32_rna(v.z); h.w = to_tf32_rna(v.w);
-                const int o = kc * A.NPIX + pix;
-                hi[o] = h;
-                lo[o] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int q = q0 + u * CV_LOADERS;
+                    if (q < total) {
+                        float4 h;
+                        h.x = to_tf32_rna(v[u].x); h.y = to_tf32_rna(v[u].y); h.z = to_tf32_rna(v[u].z); h.w = to_tf32_rna(v[u].w);
+                        const int o = (q & 3) * A.NPIX + (q >> 2);
+                        hi[o] = h;
+                        lo[o] = make_float4(v[u].x - h.x, v[u].y - h.y, v[u].z - h.z, v[u].w - h.w);
+                    }
+                }
             }
             fence_async_smem();          // generic-proxy stores -> visible to the tensor-core (async) proxy
             mbar_arrive(&a_full[s]);
@@ -245,6 +313,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
         tc_fence_after();
         const int m = warp * 32 + lane;                          // accumulator row = TMEM lane
         const int orow = y0 + (m >> 3);
+        const bool vec_out = (A.Cout & 3) == 0 && (A.ldy & 3) == 0 && ((((size_t)A.y) & 15) == 0);
         for (int t = 0; t < A.MT; ++t) {
             const int ocol = x0 + t * 8 + (m & 7);
             const bool inb = (orow < A.H && ocol < A.W);
@@ -254,11 +323,14 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
                 tc_ld16(tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(t * A.Npad + n0), v);
                 if (!inb) continue;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int n = n0 + i;
-                    if (n < A.Cout) v[i] = apply_act(v[i] + (A.bias ? __ldg(A.bias + n) : 0.f), A.act);
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 b4 = *(const float4*)(bias_s + n0 + i);        // smem broadcast
+                    v[i] = apply_act<ACT>(v[i] + b4.x);
+                    v[i + 1] = apply_act<ACT>(v[i + 1] + b4.y);
+                    v[i + 2] = apply_act<ACT>(v[i + 2] + b4.z);
+                    v[i + 3] = apply_act<ACT>(v[i + 3] + b4.w);
                 }
-                if ((A.Cout & 3) == 0 && (A.ldy & 3) == 0 && ((((size_t)A.y) & 15) == 0)) {
+                if (vec_out) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4)
                         if (n0 + i < A.Cout) *(float4*)(dst + n0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -284,41 +356,47 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
                 }
         }
     } else {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        // ================= MMA issuer: whole warp runs the (uniform) loops, one elected lane issues =================
+        {
             // instruction descriptor: D=F32, A=B=TF32, K-major both, N = Npad, M = 128
             const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(A.Npad >> 3) << 17) | ((128u >> 4) << 24);
             const unsigned a_lbo = (unsigned)A.NPIX * 16u, a_sbo = (unsigned)A.RW * 16u;
             const unsigned b_lbo = (unsigned)A.Npad * 16u, b_sbo = 128u;
             const unsigned b_half = A.b_stage_bytes / 2;
+            // descriptors = constant part + (byte offset >> 4) in the 14-bit start-address field (smem < 256 KB: no carry)
+            const unsigned long long a_desc0 = make_desc(0, a_lbo, a_sbo), b_desc0 = make_desc(0, b_lbo, b_sbo);
+            const unsigned long long a_kstep = (2u * a_lbo) >> 4, b_kstep = (2u * b_lbo) >> 4;
+            const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
             int it = 0;
             for (int c = 0; c < A.nchunks; ++c) {
                 const int sa = c % CV_ASTAGES;
                 mbar_wait(&a_full[sa], (c / CV_ASTAGES) & 1);
-                const unsigned a_hi = smem_u32(a_base + (size_t)sa * A.a_stage_bytes), a_lo = a_hi + a_half;
+                const unsigned a_st = smem_u32(a_base + (size_t)sa * A.a_stage_bytes) >> 4;
+                const unsigned long long a_hi0 = a_desc0 + a_st, a_lo0 = a_hi0 + (a_half >> 4);
+                int dy = 0, dx = 0;
                 for (int tp = 0; tp < taps; ++tp, ++it) {
                     const int sb = it % A.bstages;
                     mbar_wait(&b_full[sb], (it / A.bstages) & 1);
                     tc_fence_after();
-                    const unsigned b_hi = smem_u32(b_base + (size_t)sb * A.b_stage_bytes), b_lo = b_hi + b_half;
-                    const int dy = tp / A.KW, dx = tp - dy * A.KW;
-                    for (int t = 0; t < A.MT; ++t) {
-                        const unsigned pix_off = (unsigned)(dy * A.RW + dx + 8 * t) * 16u;
-                        const unsigned d = tmem + (unsigned)(t * A.Npad);
-                        for (int ks = 0; ks < 2; ++ks) {   // two K=8 steps per 16-channel chunk
-                            const unsigned ak = (unsigned)(2 * ks) * a_lbo + pix_off;
-                            const unsigned bk = (unsigned)(2 * ks) * b_lbo;
-                            const unsigned long long dah = make_desc(a_hi + ak, a_lbo, a_sbo);
-                            const unsigned long long dal = make_desc(a_lo + ak, a_lbo, a_sbo);
-                            const unsigned long long dbh = make_desc(b_hi + bk, b_lbo, b_sbo);
-                            const unsigned long long dbl = make_desc(b_lo + bk, b_lbo, b_sbo);
-                            const unsigned acc0 = (c == 0 && tp == 0 && ks == 0) ? 0u : 1u;   // first MMA of this tile
-                            tc_mma_tf32(d, dal, dbh, idesc, acc0);      // small terms first
-                            tc_mma_tf32(d, dah, dbl, idesc, 1u);
-                            tc_mma_tf32(d, dah, dbh, idesc, 1u);
-                        }
+                    const unsigned b_st = smem_u32(b_base + (size_t)sb * A.b_stage_bytes) >> 4;
+                    const unsigned long long dbh0 = b_desc0 + b_st, dbl0 = dbh0 + (b_half >> 4);
+                    const unsigned long long dbh1 = dbh0 + b_kstep, dbl1 = dbl0 + b_kstep;
+                    const unsigned tap_off = (unsigned)(dy * A.RW + dx);             // in 16 B units (one pixel)
+                    const unsigned acc_first = (c == 0 && tp == 0) ? 0u : 1u;
+                    const unsigned long long dah = a_hi0 + tap_off, dal = a_lo0 + tap_off;
+                    const unsigned np = (unsigned)A.Npad;
+                    if (A.MT == 4) {
+                        tc_mma_kstep<4>(tmem_u, np, dal, dah, dbh0, dbl0, idesc, acc_first);
+                        tc_mma_kstep<4>(tmem_u, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
+                    } else if (A.MT == 2) {
+                        tc_mma_kstep<2>(tmem_u, np, dal, dah, dbh0, dbl0, idesc, acc_first);
+                        tc_mma_kstep<2>(tmem_u, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
+                    } else {
+                        tc_mma_kstep<1>(tmem_u, np, dal, dah, dbh0, dbl0, idesc, acc_first);
+                        tc_mma_kstep<1>(tmem_u, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
                     }
                     tc_commit(&b_empty[sb]);           // weights of this (chunk, tap) consumed
+                    if (++dx == A.KW) { dx = 0; ++dy; }
                 }
                 tc_commit(&a_empty[sa]);               // region of this chunk consumed
             }
@@ -348,7 +426,7 @@ static int conv_geometry(ConvArgs& a, size_t* smem_bytes) {
         a.RH = CV_ROWS + a.KH - 1;
         a.NPIX = a.RW * a.RH;
         a.a_stage_bytes = (unsigned)a.NPIX * CV_CHUNK * 4u * 2u;       // hi + lo
-        const size_t fixed = (size_t)CV_ASTAGES * a.a_stage_bytes + 256;
+        const size_t fixed = (size_t)CV_ASTAGES * a.a_stage_bytes + 256 + (size_t)a.NPIX * 4 + 1024 + 16;
         if (fixed + 2 * (size_t)a.b_stage_bytes > budget) continue;
         int bs = (int)((budget - fixed) / a.b_stage_bytes);
         a.bstages = bs > CV_MAX_BSTAGES ? CV_MAX_BSTAGES : bs;
@@ -399,9 +477,17 @@ extern "C" int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float*
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.KH = KH; a.KW = KW; a.pad_mode = pad_mode; a.act = activation;
     size_t smem = 0;
     if (int rc = conv_geometry(a, &smem)) return rc;
-    FVFI_CUDA(cudaFuncSetAttribute(conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(W, 8 * a.MT), ceil_div(H, CV_ROWS), B);
-    conv_tf32x3_kernel<<<grid, CV_THREADS, smem, (cudaStream_t)stream>>>(a);
+    void (*kern)(const ConvArgs) = nullptr;
+    switch (activation) {
+        case ACT_RELU: kern = conv_tf32x3_kernel<ACT_RELU>; break;
+        case ACT_ELU: kern = conv_tf32x3_kernel<ACT_ELU>; break;
+        case ACT_TANH: kern = conv_tf32x3_kernel<ACT_TANH>; break;
+        case ACT_SIGMOID: kern = conv_tf32x3_kernel<ACT_SIGMOID>; break;
+        default: kern = conv_tf32x3_kernel<ACT_NONE>; break;
+    }
+    FVFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, CV_THREADS, smem, (cudaStream_t)stream>>>(a);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }
