@@ -29,7 +29,7 @@ constexpr int CV_ASTAGES = 2;
 constexpr int CV_MAX_BSTAGES = 4;
 constexpr unsigned CV_SPIN_LIMIT = 200u * 1000u * 1000u;   // bounded waits: trap instead of hanging the GPU
 
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4, ACT_SOFTMAX = 5 };   // softmax over channels
 enum { PAD_ZERO = 0, PAD_REFLECT = 1 };
 
 struct ConvArgs {
@@ -39,6 +39,7 @@ struct ConvArgs {
     float* y;              // [B,H,W,Cout] NHWC
     int B, H, W, Cin, Cout, Npad, KH, KW, pad_mode, act;
     int ldx, ldy;          // floats per pixel in the input / output storage (channel-slice views)
+    int out_nchw;          // 1: y is planar [B,Cout,H,W] (coefficient maps for the warp kernel)
     int MT, RW, RH, NPIX;  // tiles per CTA, staged region geometry
     int nchunks, bstages, tmem_cols;
     unsigned a_stage_bytes, b_stage_bytes;
@@ -314,23 +315,53 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
         const int m = warp * 32 + lane;                          // accumulator row = TMEM lane
         const int orow = y0 + (m >> 3);
         const bool vec_out = (A.Cout & 3) == 0 && (A.ldy & 3) == 0 && ((((size_t)A.y) & 15) == 0);
+        const size_t plane = (size_t)A.H * A.W;
         for (int t = 0; t < A.MT; ++t) {
             const int ocol = x0 + t * 8 + (m & 7);
             const bool inb = (orow < A.H && ocol < A.W);
-            float* dst = A.y + (((size_t)img * A.H + orow) * A.W + ocol) * A.ldy;
+            const unsigned tbase = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(t * A.Npad);
+            float* dst = A.out_nchw ? A.y + (size_t)img * A.Cout * plane + (size_t)orow * A.W + ocol
+                                    : A.y + (((size_t)img * A.H + orow) * A.W + ocol) * A.ldy;
+            float smax = -INFINITY, sinv = 1.f;
+            if (ACT == ACT_SOFTMAX) {          // pass 1 over TMEM: channel max and sum(exp)
+                float ssum = 0.f;
+                for (int n0 = 0; n0 < A.Npad; n0 += 16) {
+                    float v[16];
+                    tc_ld16(tbase + n0, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < A.Cout) {
+                            const float z = v[i] + bias_s[n0 + i];
+                            if (z > smax) { ssum = ssum * expf(smax - z); smax = z; }
+                            ssum += expf(z - smax);
+                        }
+                }
+                sinv = 1.f / ssum;
+            }
             for (int n0 = 0; n0 < A.Npad; n0 += 16) {
                 float v[16];
-                tc_ld16(tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(t * A.Npad + n0), v);
+                tc_ld16(tbase + n0, v);
                 if (!inb) continue;
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
                     const float4 b4 = *(const float4*)(bias_s + n0 + i);        // smem broadcast
-                    v[i] = apply_act<ACT>(v[i] + b4.x);
-                    v[i + 1] = apply_act<ACT>(v[i + 1] + b4.y);
-                    v[i + 2] = apply_act<ACT>(v[i + 2] + b4.z);
-                    v[i + 3] = apply_act<ACT>(v[i + 3] + b4.w);
+                    if (ACT == ACT_SOFTMAX) {
+                        v[i] = expf(v[i] + b4.x - smax) * sinv;
+                        v[i + 1] = expf(v[i + 1] + b4.y - smax) * sinv;
+                        v[i + 2] = expf(v[i + 2] + b4.z - smax) * sinv;
+                        v[i + 3] = expf(v[i + 3] + b4.w - smax) * sinv;
+                    } else {
+                        v[i] = apply_act<ACT>(v[i] + b4.x);
+                        v[i + 1] = apply_act<ACT>(v[i + 1] + b4.y);
+                        v[i + 2] = apply_act<ACT>(v[i + 2] + b4.z);
+                        v[i + 3] = apply_act<ACT>(v[i + 3] + b4.w);
+                    }
                 }
-                if (vec_out) {
+                if (A.out_nchw) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < A.Cout) dst[(size_t)(n0 + i) * plane] = v[i];   // 8 consecutive px per row: full 32 B sectors
+                } else if (vec_out) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4)
                         if (n0 + i < A.Cout) *(float4*)(dst + n0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -464,16 +495,17 @@ extern "C" int fvfi_conv2d_pack_weights(const float* weight_oihw, float* packed,
 
 extern "C" int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias, float* y,
                                 int y_pixel_stride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad_mode,
-                                int activation, void* stream) {
+                                int activation, int out_nchw, void* stream) {
     FVFI_CHECK_ARG(x && packed_weight && y, "conv2d: null pointer");
     FVFI_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && B <= 65535, "conv2d: bad dimension");
     FVFI_CHECK_ARG((KH == 1 || KH == 3 || KH == 5) && KW == KH, "conv2d: kernel must be 1x1, 3x3 or 5x5");
     FVFI_CHECK_ARG(pad_mode == PAD_ZERO || pad_mode == PAD_REFLECT, "conv2d: pad_mode must be 0 (zero) or 1 (reflect)");
     FVFI_CHECK_ARG(pad_mode != PAD_REFLECT || (H > KH / 2 && W > KW / 2), "conv2d: reflect padding needs H,W > pad");
-    FVFI_CHECK_ARG(activation >= 0 && activation <= 4, "conv2d: bad activation");
+    FVFI_CHECK_ARG(activation >= 0 && activation <= 5, "conv2d: bad activation");
+    FVFI_CHECK_ARG(activation != ACT_SOFTMAX || Cout <= 256, "conv2d: softmax needs all channels in one call");
     ConvArgs a{};
-    a.x = x; a.wpack = packed_weight; a.bias = bias; a.y = y; a.ldx = x_pixel_stride; a.ldy = y_pixel_stride;
-    FVFI_CHECK_ARG(x_pixel_stride >= Cin && y_pixel_stride >= Cout, "conv2d: pixel stride smaller than channel count");
+    a.x = x; a.wpack = packed_weight; a.bias = bias; a.y = y; a.ldx = x_pixel_stride; a.ldy = y_pixel_stride; a.out_nchw = out_nchw ? 1 : 0;
+    FVFI_CHECK_ARG(x_pixel_stride >= Cin && (out_nchw || y_pixel_stride >= Cout), "conv2d: pixel stride smaller than channel count");
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.KH = KH; a.KW = KW; a.pad_mode = pad_mode; a.act = activation;
     size_t smem = 0;
     if (int rc = conv_geometry(a, &smem)) return rc;
@@ -484,6 +516,7 @@ extern "C" int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float*
         case ACT_ELU: kern = conv_tf32x3_kernel<ACT_ELU>; break;
         case ACT_TANH: kern = conv_tf32x3_kernel<ACT_TANH>; break;
         case ACT_SIGMOID: kern = conv_tf32x3_kernel<ACT_SIGMOID>; break;
+        case ACT_SOFTMAX: kern = conv_tf32x3_kernel<ACT_SOFTMAX>; break;
         default: kern = conv_tf32x3_kernel<ACT_NONE>; break;
     }
     FVFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -301,3 +301,78 @@ extern "C" int fvfi_median_filter(const float* in, float* out, int N, int H, int
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }
+
+// ---- bilinear resize on NHWC tensors ------------------------------------------------------------------
+// torch.nn.Upsample / F.interpolate(mode='bilinear') as the three networks use it: scale 2 with
+// align_corners=True (KernelEstimation, fusion_adacofnet.py:31), scale 2 with align_corners=False (FusionNet,
+// fusion_net.py:41) and arbitrary output size with align_corners=False (PhaseNet, phase_net.py:138-139).
+// One thread = one output pixel x 4 channels (float4); the output may be a channel slice of a wider NHWC
+// buffer (y_pixel_stride), which is how PhaseNet's 88-channel concat is assembled without torch.cat.
+namespace fvfi {
+__global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi,
+                                                                   int Wi, int Ho, int Wo, int C, int ldx, int ldy,
+                                                                   float sy, float sx, int align_corners) {
+    const int c4 = (C + 3) >> 2;
+    const size_t total = (size_t)Ho * Wo * c4;
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    const int cg = (int)(q % c4);
+    const size_t p = q / c4;
+    const int ox = (int)(p % Wo), oy = (int)(p / Wo);
+    const int n = blockIdx.y;
+    // source coordinates exactly as ATen's area_pixel_compute_source_index
+    float fy, fx;
+    if (align_corners) {
+        fy = sy * oy;
+        fx = sx * ox;
+    } else {
+        fy = fmaxf(sy * (oy + 0.5f) - 0.5f, 0.f);
+        fx = fmaxf(sx * (ox + 0.5f) - 0.5f, 0.f);
+    }
+    const int y0 = min((int)fy, Hi - 1), x0 = min((int)fx, Wi - 1);
+    const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float* X = x + (size_t)n * Hi * Wi * ldx;
+    const int ch = cg * 4;
+    const float* p00 = X + ((size_t)y0 * Wi + x0) * ldx + ch;
+    const float* p01 = X + ((size_t)y0 * Wi + x1) * ldx + ch;
+    const float* p10 = X + ((size_t)y1 * Wi + x0) * ldx + ch;
+    const float* p11 = X + ((size_t)y1 * Wi + x1) * ldx + ch;
+    float* dst = y + ((size_t)n * Ho * Wo + p) * ldy + ch;
+    const bool vec = (ch + 3 < C) && ((ldx & 3) == 0) && ((ldy & 3) == 0) && ((((size_t)x) & 15) == 0) && ((((size_t)y) & 15) == 0);
+    if (vec) {
+        const float4 a = __ldg((const float4*)p00), b = __ldg((const float4*)p01), c = __ldg((const float4*)p10),
+                     d = __ldg((const float4*)p11);
+        float4 o;
+        o.x = hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x);
+        o.y = hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y);
+        o.z = hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z);
+        o.w = hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w);
+        *(float4*)dst = o;
+    } else {
+        for (int i = 0; i < 4 && ch + i < C; ++i)
+            dst[i] = hy * (hx * __ldg(p00 + i) + lx * __ldg(p01 + i)) + ly * (hx * __ldg(p10 + i) + lx * __ldg(p11 + i));
+    }
+}
+}  // namespace fvfi
+
+extern "C" int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi,
+                                         int Ho, int Wo, int C, int align_corners, void* stream) {
+    FVFI_CHECK_ARG(x && y && B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0 && B <= 65535, "resize_bilinear: bad argument");
+    FVFI_CHECK_ARG(x_pixel_stride >= C && y_pixel_stride >= C, "resize_bilinear: pixel stride smaller than channel count");
+    float sy, sx;
+    if (align_corners) {
+        sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+        sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+    } else {
+        sy = (float)Hi / (float)Ho;
+        sx = (float)Wi / (float)Wo;
+    }
+    const size_t total = (size_t)Ho * Wo * ((C + 3) / 4);
+    dim3 grid((unsigned)((total + 255) / 256), B);
+    fvfi::resize_bilinear_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride,
+                                                                              sy, sx, align_corners);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}

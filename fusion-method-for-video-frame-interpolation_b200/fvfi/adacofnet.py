@@ -85,26 +85,25 @@ class KernelEstimation(torch.nn.Module):
         self.moduleOcclusion = Subnet(1, nn.Sigmoid(), last_in=64)
 
     @staticmethod
-    def _seq_tc(seq, x):
-        """Run an nn.Sequential of Conv2d / ReLU / Upsample / Softmax / Sigmoid with conv+activation fused."""
+    def _seq_tc(seq, x, nchw_last=False):
+        """Run an nn.Sequential of Conv2d / ReLU / Upsample / Softmax / Sigmoid: conv + activation is one tcgen05 kernel,
+        bilinear upsampling is the NHWC resize kernel; with ``nchw_last`` the final conv writes planar NCHW."""
         mods = list(seq)
+        last_conv = max(i for i, m in enumerate(mods) if isinstance(m, torch.nn.Conv2d))
         i = 0
         while i < len(mods):
             m = mods[i]
             if isinstance(m, torch.nn.Conv2d):
                 nxt = mods[i + 1] if i + 1 < len(mods) else None
-                if isinstance(nxt, torch.nn.ReLU):
-                    x = tc.conv_module(m, x, "relu")
-                    i += 2
-                    continue
-                if isinstance(nxt, torch.nn.Sigmoid):
-                    x = tc.conv_module(m, x, "sigmoid")
-                    i += 2
-                    continue
-                x = tc.conv_module(m, x, None)
+                act = {torch.nn.ReLU: "relu", torch.nn.Sigmoid: "sigmoid", torch.nn.Softmax: "softmax"}.get(type(nxt))
+                x = tc.conv_module(m, x, act, nchw_out=nchw_last and i == last_conv)
+                i += 2 if act else 1
+            elif isinstance(m, torch.nn.Upsample):
+                x = tc.resize_bilinear(x, (x.shape[2] * 2, x.shape[3] * 2), bool(m.align_corners))
+                i += 1
             else:
                 x = m(x)
-            i += 1
+                i += 1
         return x
 
     def _forward_tc(self, rfield0, rfield2):
@@ -126,7 +125,7 @@ class KernelEstimation(torch.nn.Module):
         comb = d2 + c2
         heads = (self.moduleWeight1, self.moduleAlpha1, self.moduleBeta1, self.moduleWeight2, self.moduleAlpha2,
                  self.moduleBeta2, self.moduleOcclusion)
-        return tuple(run(h, comb).contiguous() for h in heads)
+        return tuple(run(h, comb, nchw_last=True) for h in heads)
 
     def forward(self, rfield0, rfield2):
         if tc.use_tc(rfield0) and not self.training:

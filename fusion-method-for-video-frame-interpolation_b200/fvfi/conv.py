@@ -18,7 +18,7 @@ def use_tc(x):
     return enabled and x.is_cuda and not torch.is_grad_enabled()
 
 
-ACT = {None: 0, "none": 0, "relu": 1, "elu": 2, "tanh": 3, "sigmoid": 4}
+ACT = {None: 0, "none": 0, "relu": 1, "elu": 2, "tanh": 3, "sigmoid": 4, "softmax": 5}
 _pack_cache = {}
 
 
@@ -46,9 +46,11 @@ def to_nhwc(x):
     return x.contiguous(memory_format=torch.channels_last)
 
 
-def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None):
-    """x [B,Cin,H,W] (any memory format; channels_last avoids a copy) -> [B,Cout,H,W] channels_last.
-    Equivalent to act(F.conv2d(pad(x), weight, bias)) with 'same' padding (K//2) in zeros or reflect mode."""
+def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_out=False):
+    """x [B,Cin,H,W] (any memory format; channels_last avoids a copy) -> [B,Cout,H,W] channels_last
+    (``nchw_out=True``: plain contiguous NCHW, written directly by the epilogue).
+    Equivalent to act(F.conv2d(pad(x), weight, bias)) with 'same' padding (K//2) in zeros or reflect mode;
+    act 'softmax' is over the channel dimension."""
     if not x.is_cuda:
         raise NotImplementedError("fvfi.conv.conv2d: CUDA tensors only")
     B, Cin, H, W = x.shape
@@ -58,8 +60,11 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None):
     assert xc.stride(1) == 1
     ldx = xc.stride(3)                       # floats per pixel
     if out is None:
-        out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
-    ldy = out.stride(3)
+        out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device,
+                          memory_format=torch.contiguous_format if nchw_out else torch.channels_last)
+    ldy = Cout if nchw_out else out.stride(3)
+    if nchw_out:
+        assert out.is_contiguous() and Cout <= 256
     L = _lib.lib()
     pad_mode = {"zeros": 0, "reflect": 1}[padding_mode]
     b = None if bias is None else bias.detach().contiguous().float()
@@ -67,17 +72,33 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None):
         for (o, n, buf, _) in _packed(weight):
             _lib.check(L.fvfi_conv2d_nhwc(xc.data_ptr(), ldx, buf.data_ptr(), None if b is None else b.data_ptr() + 4 * o,
                                           out.data_ptr() + 4 * o, ldy, B, H, W, Cin, n, KH, KW, pad_mode, ACT[act],
-                                          _lib.stream_ptr()))
+                                          1 if nchw_out else 0, _lib.stream_ptr()))
     return out
 
 
-def conv_module(conv, x, act=None):
+def resize_bilinear(x, size, align_corners, out=None, out_channel_offset=0):
+    """F.interpolate(x, size=size, mode='bilinear', align_corners=align_corners) on NHWC storage.  ``out`` may be a
+    wider channels_last buffer; the result is written to channels [out_channel_offset, out_channel_offset + C)."""
+    B, C, Hi, Wi = x.shape
+    Ho, Wo = int(size[0]), int(size[1])
+    xc = to_nhwc(x.float())
+    if out is None:
+        out = torch.empty((B, C, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    assert out.stride(1) == 1 and out.shape[2] == Ho and out.shape[3] == Wo
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().fvfi_resize_bilinear_nhwc(xc.data_ptr(), xc.stride(3), out.data_ptr() + 4 * out_channel_offset,
+                                                        out.stride(3), B, Hi, Wi, Ho, Wo, C, 1 if align_corners else 0,
+                                                        _lib.stream_ptr()))
+    return out
+
+
+def conv_module(conv, x, act=None, nchw_out=False):
     """Run an nn.Conv2d (stride 1, dilation 1, padding == K//2) through the tensor-core kernel."""
     k = conv.kernel_size[0]
     assert conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
     assert conv.padding == (k // 2, k // 2) or (k == 1 and conv.padding == (0, 0))
     mode = "zeros" if k == 1 else conv.padding_mode
-    return conv2d(x, conv.weight, conv.bias, mode, act)
+    return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out)
 
 
 _fold_cache = {}

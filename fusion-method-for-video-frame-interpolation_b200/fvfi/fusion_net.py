@@ -74,7 +74,8 @@ class FusionNet(torch.nn.Module):
                 x = self.max_pool(x)
             x = tc.conv_module(self.bottleneck_layer, x, "relu")    # ReLU of the first decoder step folded in
             for i, (layer, s) in enumerate(zip(self.decoder_layers, skip[::-1])):
-                x = self.deconvolution(x if i == 0 else self.relu(x))
+                x = x if i == 0 else self.relu(x)
+                x = tc.resize_bilinear(x, (x.shape[2] * 2, x.shape[3] * 2), False)
                 x = x + s
                 x = tc.conv_module(layer, x, None)
             x = x.contiguous()

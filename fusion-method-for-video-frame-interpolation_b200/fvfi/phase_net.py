@@ -122,9 +122,19 @@ class PhaseNet(nn.Module):
         phases, amplitudes = [], []
         for idx in range(m):
             res = phase[idx].shape[2:]
-            feature_r = F.interpolate(feature, size=tuple(res), mode='bilinear', align_corners=False)
-            prediction_r = F.interpolate(prediction, size=tuple(res), mode='bilinear', align_corners=False)
-            concat = torch.cat((feature_r, phase[idx], amplitude[idx], prediction_r), 1)
+            if tc.use_tc(feature) and not self.training:
+                # NHWC concat assembled in place: resize kernels write straight into their channel slices
+                cf, cp, cv = feature.shape[1], prediction.shape[1], phase[idx].shape[1]
+                concat = torch.empty((feature.shape[0], cf + 2 * cv + cp, res[0], res[1]), dtype=torch.float32,
+                                     device=feature.device, memory_format=torch.channels_last)
+                tc.resize_bilinear(feature, res, False, out=concat, out_channel_offset=0)
+                concat[:, cf:cf + cv] = phase[idx]
+                concat[:, cf + cv:cf + 2 * cv] = amplitude[idx]
+                tc.resize_bilinear(prediction, res, False, out=concat, out_channel_offset=cf + 2 * cv)
+            else:
+                feature_r = F.interpolate(feature, size=tuple(res), mode='bilinear', align_corners=False)
+                prediction_r = F.interpolate(prediction, size=tuple(res), mode='bilinear', align_corners=False)
+                concat = torch.cat((feature_r, phase[idx], amplitude[idx], prediction_r), 1)
             i = idx + 1 if idx + 1 < len(self.layers) - 1 else len(self.layers) - 1
             feature, prediction = self.layers[i](concat)
             del concat

@@ -108,12 +108,19 @@ int fvfi_median_filter(const float* in, float* out, int N, int H, int W, int siz
  *   weight_oihw [Cout,Cin,KH,KW] -> packed (fvfi_conv2d_packed_weight_floats floats), once per weight update.
  *   x: NHWC, x_pixel_stride floats between pixels (>= Cin); y likewise.  Cout <= 256 per call.
  *   KH == KW in {1,3,5}; pad_mode 0 = zeros, 1 = reflect (torch 'reflect'); activation 0 none, 1 ReLU, 2 ELU,
- *   3 tanh, 4 sigmoid; bias [Cout] or NULL. */
+ *   3 tanh, 4 sigmoid, 5 softmax over the Cout channels; bias [Cout] or NULL.
+ *   out_nchw != 0: y is planar [B,Cout,H,W] (the layout the AdaCoF warp streams its coefficient maps in). */
 size_t fvfi_conv2d_packed_weight_floats(int Cout, int Cin, int KH, int KW);
 int fvfi_conv2d_pack_weights(const float* weight_oihw, float* packed, int Cout, int Cin, int KH, int KW, void* stream);
 int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias, float* y,
                      int y_pixel_stride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad_mode,
-                     int activation, void* stream);
+                     int activation, int out_nchw, void* stream);
+
+/* Bilinear resize of NHWC tensors (torch.nn.Upsample / F.interpolate 'bilinear' semantics, both align_corners
+ * modes; src/fusion_net/fusion_adacofnet.py:31, src/fusion_net/fusion_net.py:41, src/phase_net/phase_net.py:138-139).
+ * x [B,Hi,Wi,C] with x_pixel_stride floats per pixel -> y [B,Ho,Wo,C] (may be a channel slice: y_pixel_stride). */
+int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi,
+                              int Ho, int Wo, int C, int align_corners, void* stream);
 
 /* Host-buffer variants for end-to-end timing: pointers are HOST memory (pinned preferred);
  * the call does H2D, the kernel(s), D2H and synchronises. */

@@ -40,3 +40,36 @@ def test_conv_matches_fp32(B, Cin, Cout, K, H, W, mode, act):
     assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
     print('max abs err %.2e (max |ref| %.2f)' % (err, float(ref.abs().max())))
     assert err <= 2e-5 * max(1.0, float(ref.abs().max())), err
+
+
+@pytest.mark.parametrize("align", [True, False])
+def test_resize_bilinear_nhwc_matches_torch(align):
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for (B, C, Hi, Wi, Ho, Wo) in [(2, 64, 17, 30, 34, 60), (1, 8, 23, 23, 32, 32), (1, 1, 8, 11, 12, 16), (2, 25, 20, 28, 40, 56)]:
+        x = torch.randn((B, C, Hi, Wi), device="cuda", generator=g)
+        y = conv.resize_bilinear(x, (Ho, Wo), align)
+        ref = F.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=align)
+        assert float((y - ref).abs().max()) <= 2e-6
+    # channel-slice destination (PhaseNet concat assembly)
+    x = torch.randn((1, 64, 11, 11), device="cuda", generator=g)
+    buf = torch.zeros((1, 88, 16, 16), device="cuda").contiguous(memory_format=torch.channels_last)
+    conv.resize_bilinear(x, (16, 16), False, out=buf, out_channel_offset=8)
+    assert float((buf[:, 8:72] - F.interpolate(x, size=(16, 16), mode="bilinear", align_corners=False)).abs().max()) <= 2e-6
+    assert float(buf[:, :8].abs().max()) == 0.0 and float(buf[:, 72:].abs().max()) == 0.0
+
+
+def test_conv_softmax_and_nchw_epilogues():
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn((2, 25, 40, 72), device="cuda", generator=g)
+    w = torch.randn((25, 25, 3, 3), device="cuda", generator=g) / 15
+    b = torch.randn((25,), device="cuda", generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    y = conv.conv2d(x, w, b, "zeros", "softmax", nchw_out=True)
+    assert y.is_contiguous() and float((y.double() - torch.softmax(ref, 1)).abs().max()) <= 5e-6
+    y = conv.conv2d(x, w, b, "zeros", None, nchw_out=True)
+    assert y.is_contiguous() and float((y.double() - ref).abs().max()) <= 2e-5
+    w1 = torch.randn((1, 25, 3, 3), device="cuda", generator=g) / 15
+    y = conv.conv2d(x, w1, b[:1], "zeros", "sigmoid", nchw_out=True)
+    assert float((y.double() - torch.sigmoid(F.conv2d(x.double(), w1.double(), b[:1].double(), padding=1))).abs().max()) <= 2e-6
