@@ -11,10 +11,15 @@
 //    host in double with the same LUT interpolation the oracle uses) and the angular factor
 //    A_b = 2 sqrt(c) cos(theta - pi b/nb)^(nb-1) [cos > 0] evaluated in closed form from the
 //    frequency coordinates (no atan2, no table).  Every level depends only on X, so all levels are
-//    independent launches; reconstruction sums the level spectra in one gather.
-//  * Every 1-D transform (any length: 764 = 4*191, 1358 = 2*7*97, 241, ...) is a shared-memory
-//    Stockham FFT (fft_smem.cuh); rows are transformed in batches of rows, columns in tiles of
-//    CT adjacent columns, so global traffic is one read + one write of the array per pass.
+//    independent: the large levels are one launch each, all small levels share ONE launch per pass
+//    (job table + tile prefix), and reconstruction sums the level spectra in one gather.
+//  * Every 1-D transform of any length (764 = 4*191, 1358 = 2*7*97, 241, ...) runs in shared memory
+//    with register butterflies (fft_engine.cuh): mixed radix up to 16/15 for smooth lengths (three
+//    stages at 1080 / 1920), Bluestein on a smooth length for the rest.  Row passes work on batches
+//    of rows (autosort network, natural order in and out, coalesced); column passes on tiles of 8
+//    adjacent columns (64-byte row segments) with an in-place network whose digit-reversed output
+//    order is absorbed by the store.  Inverse transforms are conj -> forward -> conj with the
+//    conjugations fused into the spectrum loader and the output epilogue.
 //  * Fused epilogues/prologues: amplitude |z|, phase atan2(im,re), the per-(level,plane) amplitude
 //    maximum (PhaseNet.normalize_vals, src/phase_net/phase_net.py:47-59) are produced by the last
 //    row pass of the band IFFT -- the complex band never goes to HBM; reconstruction reads
@@ -23,17 +28,24 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <vector>
 
 #include "common.cuh"
-#include "fft_smem.cuh"
+#include "fft_plan.hpp"
 
 namespace fvfi {
 
 constexpr int MAX_LEVELS = 40;
 constexpr int MAX_BANDS = 8;
-constexpr int ROW_ELEMS = 4096;   // complex elements per CTA in a row pass  (2 buffers = 64 KB)
-constexpr int COL_ELEMS = 8704;   // complex elements per CTA in a column pass (3 buffers = 204 KB)
+constexpr int MAX_SET = 24;                       // jobs per merged launch
+constexpr int PYR_THREADS = 256;
+#ifndef PYR_MIN_CTAS
+#define PYR_MIN_CTAS 3
+#endif
+constexpr size_t COL_SMEM_MAX = 113 * 1024;       // in-place column tile: two CTAs per SM
+constexpr size_t ROW_SMEM_TARGET = 72 * 1024;     // row batch: three CTAs per SM
+constexpr int SMALL_LEVEL_ELEMS = 300 * 520;      // levels at or below this size share one launch per pass
 
 struct LevelGeom {
     int h, w;
@@ -50,16 +62,42 @@ struct AngParams {
     float inv_hh, inv_hw;  // 2/H, 2/W of the FULL image (grid coordinates, prepare_grid)
 };
 
+// One entry per level (0..L-1 bands, L = low residual, L+1 = full-size plane: image FFT / high residual).
+struct LevelJob {
+    int h, w, nb, is_band;
+    int ct_shift, rb;            // column tile = 1 << ct_shift columns; rows per CTA in a row pass
+    int col_tiles, row_tiles;
+    unsigned mag_w;              // ceil(2^32 / w)
+    long long t_off;             // intermediate T of this level starts at regionB + N * t_off (complex elements)
+    long long c_off;             // per-plane offset of the level spectrum in region C
+    const float* radial;         // D_l (band levels), low-pass product (L), hi0 (L+1)
+    FftPlan fy, fx;              // column / row transforms
+};
+
+struct SetEntry {
+    int job, start, mode, pad_;
+    const float* p0;
+    const float* p1;
+    float* q0;
+    float* q1;
+    float* aux;
+};
+struct LaunchSet {
+    int n, total;
+    SetEntry e[MAX_SET];
+};
+
 }  // namespace fvfi
 
 struct fvfi_pyr_plan {
     int H, W, height, nbands, L;
     double scale;
     std::vector<fvfi::LevelGeom> lv;            // L band levels + low residual (index L)
-    std::vector<fvfi::Fft1D> fy, fx;            // per level (index L = low)
+    std::vector<fvfi::LevelJob> jobs;           // host copy of the job table (L + 2 entries)
+    const fvfi::LevelJob* d_jobs = nullptr;     // device job table
     std::vector<const float*> radial;           // device, per level (index L = low-pass product)
     const float* hi0 = nullptr;                 // device [H*W], unshifted
-    std::map<int, float2*> tw;                  // device twiddle tables by length
+    std::map<std::pair<int, int>, fvfi::FftPlan> fft_cache;   // (length, stockham) -> plan with device tables
     std::vector<void*> owned;
     size_t level_elems = 0;                     // sum_l h_l*w_l  (l = 0..L)
     fvfi::AngParams ang_build, ang_rec;
@@ -71,23 +109,6 @@ namespace fvfi {
 // host: plan
 // ------------------------------------------------------------------------------------------------
 static int next_size(int n, double s) { return (int)ceil((n - 0.5) / s - 1e-9); }
-
-static void factorize(int n, Fft1D& f) {
-    std::vector<int> primes;
-    int rem = n;
-    for (int d = 2; d * d <= rem; ++d)
-        while (rem % d == 0) { primes.push_back(d); rem /= d; }
-    if (rem > 1) primes.push_back(rem);
-    int twos = 0;
-    std::vector<int> others;
-    for (int p : primes) { if (p == 2) ++twos; else others.push_back(p); }
-    std::sort(others.begin(), others.end(), [](int a, int b) { return a > b; });
-    f.n = n;
-    f.nfac = 0;
-    for (int p : others) f.fac[f.nfac++] = p;
-    for (int i = 0; i < twos / 2; ++i) f.fac[f.nfac++] = 4;
-    if (twos & 1) f.fac[f.nfac++] = 2;
-}
 
 // numpy.interp on an increasing abscissa (end-clamped) -- what upstream's pointOp does.
 static double interp(double x, const std::vector<double>& X, const std::vector<double>& Y) {
@@ -115,22 +136,65 @@ static int upload(fvfi_pyr_plan* p, const std::vector<T>& v, const T** out) {
     return FVFI_OK;
 }
 
-static int make_fft(fvfi_pyr_plan* p, int n, Fft1D& f) {
-    factorize(n, f);
-    if (f.nfac > FFT_MAX_FACTORS) { set_error("pyramid: too many FFT factors for n=%d", n); return FVFI_EINVAL; }
-    auto it = p->tw.find(n);
-    if (it == p->tw.end()) {
-        std::vector<float2> t(n);
-        for (int k = 0; k < n; ++k) {
-            const double a = -2.0 * M_PI * (double)k / (double)n;
-            t[k] = make_float2((float)cos(a), (float)sin(a));
-        }
-        const float2* d = nullptr;
-        if (int rc = upload(p, t, &d)) return rc;
-        p->tw[n] = (float2*)d;
-        it = p->tw.find(n);
+
+// FFT plan with device-resident tables, cached per (length, network kind)
+static int get_fft(fvfi_pyr_plan* p, int n, bool stockham, FftPlan* out) {
+    auto key = std::make_pair(n, stockham ? 1 : 0);
+    auto it = p->fft_cache.find(key);
+    if (it != p->fft_cache.end()) { *out = it->second; return FVFI_OK; }
+    HostFftPlan H;
+    if (!fft_make_plan(n, stockham, H)) { set_error("pyramid: no FFT plan for length %d", n); return FVFI_EINVAL; }
+    FftPlan f = H.p;
+    if (int rc = upload(p, H.tw, &f.tw)) return rc;
+    f.perm = nullptr;
+    f.chirp = nullptr;
+    f.bhat = nullptr;
+    if (f.bluestein) {
+        if (int rc = upload(p, H.chirp, &f.chirp)) return rc;
+        if (int rc = upload(p, H.bhat, &f.bhat)) return rc;
+    } else if (!stockham) {
+        if (int rc = upload(p, H.perm, &f.perm)) return rc;
     }
-    f.tw = it->second;
+    p->fft_cache[key] = f;
+    *out = f;
+    return FVFI_OK;
+}
+
+static size_t row_bytes_per_row(const FftPlan& fx) {
+    return (size_t)(fx.bluestein ? 1 : 2) * fft_row_pitch(fx.M, fx.pad) * sizeof(float2);
+}
+
+static int build_jobs(fvfi_pyr_plan* p) {
+    const int L = p->L, nb = p->nbands;
+    p->jobs.assign(L + 2, LevelJob{});
+    for (int l = 0; l <= L + 1; ++l) {
+        LevelJob& J = p->jobs[l];
+        const bool full = (l == L + 1);
+        J.h = full ? p->H : p->lv[l].h;
+        J.w = full ? p->W : p->lv[l].w;
+        J.nb = (l < L) ? nb : 1;
+        J.is_band = (l < L) ? 1 : 0;
+        J.radial = full ? p->hi0 : p->radial[l];
+        J.t_off = full ? (long long)nb * (long long)p->level_elems : (long long)nb * (long long)p->lv[l].off;
+        J.c_off = full ? 0 : (long long)p->lv[l].off;
+        J.mag_w = fft_magic((unsigned)J.w);
+        if (int rc = get_fft(p, J.h, false, &J.fy)) return rc;
+        if (int rc = get_fft(p, J.w, true, &J.fx)) return rc;
+        int cs = 3;
+        while (cs > 0 && ((size_t)J.fy.M << cs) * sizeof(float2) > COL_SMEM_MAX) --cs;
+        if (((size_t)J.fy.M << cs) * sizeof(float2) > 220 * 1024) { set_error("pyramid: column length %d too large", J.h); return FVFI_EINVAL; }
+        J.ct_shift = cs;
+        const size_t per_row = row_bytes_per_row(J.fx);
+        if (per_row > 220 * 1024) { set_error("pyramid: row length %d too large", J.w); return FVFI_EINVAL; }
+        int rb = (int)(ROW_SMEM_TARGET / per_row);
+        rb = std::max(1, std::min(std::min(rb, 16), J.h));
+        J.rb = rb;
+        J.col_tiles = ceil_div(J.w, 1 << cs);
+        J.row_tiles = ceil_div(J.h, rb);
+    }
+    const LevelJob* d = nullptr;
+    if (int rc = upload(p, p->jobs, &d)) return rc;
+    p->d_jobs = d;
     return FVFI_OK;
 }
 
@@ -139,8 +203,6 @@ static int build_plan(fvfi_pyr_plan* p) {
     const double s = p->scale, dlt = log2(s);
     // level sizes (SURVEY.md Appendix A.4 / oracle.steerable_shim.level_sizes)
     p->lv.resize(L + 1);
-    p->fy.resize(L + 1);
-    p->fx.resize(L + 1);
     p->radial.resize(L + 1);
     int h = H, w = W;
     size_t off = 0;
@@ -149,13 +211,16 @@ static int build_plan(fvfi_pyr_plan* p) {
         p->lv[l].w = w;
         p->lv[l].off = off;
         off += (size_t)h * w;
-        if (int rc = make_fft(p, h, p->fy[l])) return rc;
-        if (int rc = make_fft(p, w, p->fx[l])) return rc;
         h = next_size(h, s);
         w = next_size(w, s);
     }
     p->level_elems = off;
-    if (p->lv[L].h < 2 || p->lv[L].w < 2) { set_error("pyramid: height %d too large for %dx%d", p->height, H, W); return FVFI_EINVAL; }
+    // the level-size rule stops shrinking at 2 samples: a pyramid that tall has degenerate (repeated) levels
+    for (int l = 0; l < L; ++l)
+        if (p->lv[l + 1].h >= p->lv[l].h || p->lv[l + 1].w >= p->lv[l].w || p->lv[l + 1].h < 2 || p->lv[l + 1].w < 2) {
+            set_error("pyramid: height %d too large for %dx%d", p->height, H, W);
+            return FVFI_EINVAL;
+        }
 
     // raised-cosine tables (upstream rcosFn(1, -0.5))
     const int NT = 259;
@@ -233,8 +298,9 @@ static int build_plan(fvfi_pyr_plan* p) {
     p->ang_rec.scale = (float)sqrt(cst);
     p->ang_rec.fac = pw_p[order & 3];
     p->ang_rec.one_sided = 0;
-    return FVFI_OK;
+    return build_jobs(p);
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -242,7 +308,7 @@ static int build_plan(fvfi_pyr_plan* p) {
 __device__ __forceinline__ int sfreq(int k, int n) { return k < ((n + 1) >> 1) ? k : k - n; }
 __device__ __forceinline__ int wrapi(int f, int n) { return f < 0 ? f + n : f; }
 
-// angular factor of band b at signed frequency (fy, fx) of the full grid, times the band's complex constant
+// angular factor of band b at signed frequency (fy, fx) of the full grid
 __device__ __forceinline__ float ang_factor(const AngParams& A, int b, int fy, int fx) {
     const float xv = (float)fx * A.inv_hw, yv = (float)fy * A.inv_hh;
     const float r2 = xv * xv + yv * yv;
@@ -253,105 +319,244 @@ __device__ __forceinline__ float ang_factor(const AngParams& A, int b, int fy, i
     return v;
 }
 
-struct Tile {  // carve dynamic smem
-    float2 *a, *b, *c;
-};
+// atan2f for the phase epilogue: octant reduction + degree-7 minimax in t^2 (|error| < 4e-7 rad, measured against
+// float64 over the whole circle in tests/test_pyramid_gpu.py); atan2(0, 0) = 0 like torch.angle; the sign follows
+// the sign bit of y (so -0.0 gives -pi on the negative real axis, as atan2f does).
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
+    const float s = t * t;
+    float r = 3.866738916e-03f;
+    r = fmaf(r, s, -2.002674765e-02f);
+    r = fmaf(r, s, 4.891432155e-02f);
+    r = fmaf(r, s, -8.009681718e-02f);
+    r = fmaf(r, s, 1.086575908e-01f);
+    r = fmaf(r, s, -1.425704493e-01f);
+    r = fmaf(r, s, 1.999868117e-01f);
+    r = fmaf(r, s, -3.333332310e-01f);
+    r = fmaf(r * s, t, t);
+    if (ay > ax) r = 1.57079632679489662f - r;
+    if (x < 0.f) r = 3.14159265358979324f - r;
+    return copysignf(r, y);
+}
+
+__device__ __forceinline__ const SetEntry& find_entry(const LaunchSet& S, int bx) {
+    int i = 0;
+    while (i + 1 < S.n && bx >= S.e[i + 1].start) ++i;
+    return S.e[i];
+}
+
+struct PtrTable { const float* p[MAX_BANDS]; };
+struct MutPtrTable { float* p[MAX_BANDS]; };
 
 // ------------------------------------------------------------------------------------------------
 // K1: row pass, forward, with input prologue.  in -> FFT along x -> T[n][b][y][kx]
-//   MODE 0: real input  in0[n][y][x]
-//   MODE 1: polar input phase=in0, amp=in1 at channel (n*nbB + b)   (values_to_coeff, pyramid.py:103-108)
-//   MODE 2: complex interleaved in0[(b)][n][y][x][2] via pointer table (band tensors [N,h,w,2])
-// grid: (ceil(h/RB), nbB, N)
+//   mode 0: real input  p0[n][y][x]
+//   mode 1: polar input phase = p0, amp = p1 at channel (n*nb + b)   (values_to_coeff, pyramid.py:103-108)
+//   mode 2: complex interleaved tab.p[b][n][y][x][2] (band tensors [N,h,w,2])
+// grid: (row tiles of all jobs, nb, N)
 // ------------------------------------------------------------------------------------------------
-struct PtrTable { const float* p[MAX_BANDS]; };
-
-template <int MODE>
-__global__ void __launch_bounds__(256) k_rows_fwd(Fft1D P, int h, int w, int RB, int nbB, const float* __restrict__ in0,
-                                                  const float* __restrict__ in1, PtrTable tab,
-                                                  float2* __restrict__ T) {
+__global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_fwd(const LevelJob* __restrict__ jobs, const LaunchSet S, PtrTable tab,
+                                                             float2* __restrict__ regionB) {
     extern __shared__ float2 smem[];
+    const SetEntry& E = find_entry(S, blockIdx.x);
+    const LevelJob& J = jobs[E.job];
+    const int mode = E.mode;
+    const int nbB = (mode == 0) ? 1 : J.nb;
+    const int b = blockIdx.y, n = blockIdx.z, N = gridDim.z;
+    if (b >= nbB) return;
+    const int h = J.h, w = J.w, rb = J.rb;
+    const int y0 = (blockIdx.x - E.start) * rb;
+    const int rows = min(rb, h - y0);
+    const int pitch = fft_row_pitch(J.fx.M, J.fx.pad);
     float2* a = smem;
-    float2* bq = smem + RB * w;
-    const int y0 = blockIdx.x * RB, b = blockIdx.y, n = blockIdx.z, N = gridDim.z;
-    const int rows = min(RB, h - y0);
-    for (int q = threadIdx.x; q < rows * w; q += blockDim.x) {
-        const int r = q / w, x = q - r * w;
-        const size_t pix = (size_t)(y0 + r) * w + x;
-        float2 z;
-        if (MODE == 0) {
-            z = make_float2(in0[(size_t)n * h * w + pix], 0.f);
-        } else if (MODE == 1) {
-            const size_t o = ((size_t)n * nbB + b) * h * w + pix;
-            const float ph = in0[o], am = in1[o];
-            float sn, cs;
-            sincosf(ph, &sn, &cs);
-            z = make_float2(cs * am, sn * am);  // pyramid.py:105-106
-        } else {
-            const float2* src = (const float2*)tab.p[b];
-            z = src[(size_t)n * h * w + pix];
+    float2* bq = smem + (size_t)rb * pitch;
+    const unsigned mag_w = J.mag_w;
+    const size_t plane = (size_t)h * w;
+    constexpr int U = 4;                      // independent global loads in flight per thread
+    const int total = rows * w;
+    for (int q0 = threadIdx.x; q0 < total; q0 += U * blockDim.x) {
+        float2 z[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = q0 + u * blockDim.x;
+            z[u] = make_float2(0.f, 0.f);
+            if (q < total) {
+                const size_t pix = (size_t)y0 * w + q;
+                if (mode == 0) {
+                    z[u].x = __ldg(E.p0 + (size_t)n * plane + pix);
+                } else if (mode == 1) {
+                    const size_t o = ((size_t)n * nbB + b) * plane + pix;
+                    z[u] = make_float2(__ldg(E.p0 + o), __ldg(E.p1 + o));      // (phase, amplitude)
+                } else {
+                    z[u] = __ldg((const float2*)tab.p[b] + (size_t)n * plane + pix);
+                }
+            }
         }
-        a[r * w + x] = z;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = q0 + u * blockDim.x;
+            if (q < total) {
+                const int r = (int)fast_div((unsigned)q, (unsigned)w, mag_w), x = q - r * w;
+                float2 v = z[u];
+                if (mode == 1) {
+                    float sn, cs;
+                    sincosf(z[u].x, &sn, &cs);
+                    v = make_float2(cs * z[u].y, sn * z[u].y);  // pyramid.py:105-106
+                }
+                fft_put<false>(J.fx, a, r, x, v, 0, pitch);
+            }
+        }
     }
     __syncthreads();
-    float2* res = fft_smem<false>(P, a, bq, rows, w, 1);
-    float2* dst = T + (((size_t)n * nbB + b) * h + y0) * w;
-    for (int q = threadIdx.x; q < rows * w; q += blockDim.x) dst[q] = res[q];
-    (void)N;
+    const FftResult R = fft_forward<false>(J.fx, a, bq, rows, 0, pitch, false, FftCtx{(int)threadIdx.x, (int)blockDim.x});
+    float2* dst = regionB + (size_t)N * J.t_off + ((size_t)n * nbB + b) * plane + (size_t)y0 * w;
+    for (int q = threadIdx.x; q < rows * w; q += blockDim.x) {
+        const int r = (int)fast_div((unsigned)q, (unsigned)w, mag_w), x = q - r * w;
+        dst[q] = fft_get<false>(J.fx, R, r, x, 0, pitch);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: column pass, forward, + combine (reconstruction) or plain in-place (decomposition of X).
-//   For each band b: FFT along y of T[n][b][:, tile]; acc += fft * ang_b * fac ; out = acc * radial
-//   plain (nbB==1, A==nullptr-like flag): out = fft * radial (radial may be null -> 1)
-// grid: (ceil(w/CT), N)
+// K2: column pass, forward.  T[n][b][:, tile] -> FFT along y ->
+//   entry mode 1 (combine, reconstruction of a band level): out = radial * sum_b fft_b * ang_b * (i)^(nb-1)
+//   entry mode 0 (plain): out = fft * radial   (use_radial == 0: radial ignored -> image spectrum X)
+// out = outbase + n*out_stride (+ J.c_off if add_c_off).   grid: (column tiles of all jobs, 1, N)
 // ------------------------------------------------------------------------------------------------
-template <bool ANG>
-__global__ void __launch_bounds__(512) k_cols_fwd(Fft1D P, int h, int w, int CT, int nbB, const float2* __restrict__ T,
-                                                  const float* __restrict__ radial, AngParams A,
-                                                  float2* __restrict__ out, size_t out_plane_stride) {
+__global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_fwd(const LevelJob* __restrict__ jobs, const LaunchSet S, AngParams A,
+                                                             const float2* __restrict__ regionB, float2* __restrict__ outbase,
+                                                             size_t out_stride, int add_c_off, int use_radial) {
     extern __shared__ float2 smem[];
-    const int E = h * CT;
-    float2* a = smem;
-    float2* bq = smem + E;
-    float2* acc = smem + 2 * E;
-    const int x0 = blockIdx.x * CT, n = blockIdx.y;
+    const SetEntry& E = find_entry(S, blockIdx.x);
+    const LevelJob& J = jobs[E.job];
+    const bool combine = E.mode == 1;
+    const int nbB = combine ? J.nb : 1;
+    const int n = blockIdx.z, N = gridDim.z;
+    const int h = J.h, w = J.w, cs = J.ct_shift, CT = 1 << cs;
+    const int x0 = (blockIdx.x - E.start) << cs;
     const int cols = min(CT, w - x0);
+    const int E_ = h << cs;
+    float2* a = smem;
+    float2* acc = smem + ((size_t)J.fy.M << cs);
+    const size_t plane = (size_t)h * w;
+    const FftCtx cx{(int)threadIdx.x, (int)blockDim.x};
+    FftResult R{a, nullptr};
     for (int b = 0; b < nbB; ++b) {
-        const float2* src = T + ((size_t)n * nbB + b) * h * w;
-        for (int q = threadIdx.x; q < E; q += blockDim.x) {
-            const int y = q / CT, c = q - y * CT;
-            a[q] = (c < cols) ? src[(size_t)y * w + x0 + c] : make_float2(0.f, 0.f);
+        const float2* src = regionB + (size_t)N * J.t_off + ((size_t)n * nbB + b) * plane;
+        {
+            constexpr int U = 8;
+            for (int q0 = threadIdx.x; q0 < E_; q0 += U * blockDim.x) {
+                float2 z[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int q = q0 + u * blockDim.x;
+                    const int y = q >> cs, c = q & (CT - 1);
+                    z[u] = make_float2(0.f, 0.f);
+                    if (q < E_ && c < cols) z[u] = __ldcs(src + (size_t)y * w + x0 + c);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int q = q0 + u * blockDim.x;
+                    if (q < E_) fft_put<true>(J.fy, a, q & (CT - 1), q >> cs, z[u], cs, 0);
+                }
+            }
         }
         __syncthreads();
-        float2* res = fft_smem<false>(P, a, bq, CT, 1, CT);
-        if (ANG) {
-            for (int q = threadIdx.x; q < E; q += blockDim.x) {
-                const int ky = q / CT, c = q - ky * CT;
+        R = fft_forward<true>(J.fy, a, nullptr, CT, cs, 0, true, cx);
+        if (combine) {
+            for (int q = threadIdx.x; q < E_; q += blockDim.x) {
+                const int pos = q >> cs, c = q & (CT - 1);
+                const int ky = R.perm ? (int)__ldg(R.perm + pos) : pos;
                 const float g = ang_factor(A, b, sfreq(ky, h), sfreq(min(x0 + c, w - 1), w));
-                const float2 v = cmul(make_float2(res[q].x * g, res[q].y * g), A.fac);
+                const float2 rv = fft_get<true>(J.fy, R, c, pos, cs, 0);
+                const float2 v = cmul(make_float2(rv.x * g, rv.y * g), A.fac);
                 acc[q] = (b == 0) ? v : cadd(acc[q], v);
             }
-        } else {
-            for (int q = threadIdx.x; q < E; q += blockDim.x) acc[q] = res[q];
+            __syncthreads();
         }
-        __syncthreads();
     }
-    float2* dst = out + (size_t)n * out_plane_stride;
-    for (int q = threadIdx.x; q < E; q += blockDim.x) {
-        const int ky = q / CT, c = q - ky * CT;
+    const float* radial = use_radial ? J.radial : nullptr;
+    float2* dst = outbase + (size_t)n * out_stride + (add_c_off ? (size_t)J.c_off : 0);
+    for (int q = threadIdx.x; q < E_; q += blockDim.x) {
+        const int pos = q >> cs, c = q & (CT - 1);
         if (c >= cols) continue;
+        const int ky = R.perm ? (int)__ldg(R.perm + pos) : pos;
         const size_t o = (size_t)ky * w + x0 + c;
         const float m = radial ? __ldg(radial + o) : 1.f;
-        dst[o] = make_float2(acc[q].x * m, acc[q].y * m);
+        const float2 rv = combine ? acc[q] : fft_get<true>(J.fy, R, c, pos, cs, 0);
+        dst[o] = make_float2(rv.x * m, rv.y * m);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: column pass, inverse, with spectrum loader.
-//   GATHER == false (decomposition): value = X[n][fy mod H][fx mod W] * radial[ky][kx] * ang_b * fac
-//   GATHER == true  (reconstruction): value = sum over levels of Y_l[n][fy mod h_l][fx mod w_l] (+ high spectrum)
-// out: T[n][b][y][kx]     grid: (ceil(w/CT), N)
+// K3: column pass of the band IFFT with the spectrum loader (decomposition).
+//   value = conj( X[n][fy mod H][fx mod W] * radial[ky][kx] * ang_b * (-i)^(nb-1) ); forward FFT along y; the row pass
+//   conjugates again at the very end (IFFT2 = conj FFT2 conj).   out: T[n][b][y][kx]
+// grid: (column tiles of all jobs, nb, N)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_decomp(const LevelJob* __restrict__ jobs, const LaunchSet S,
+                                                                    AngParams A, int H, int W, const float2* __restrict__ X,
+                                                                    float2* __restrict__ regionB) {
+    extern __shared__ float2 smem[];
+    const SetEntry& E = find_entry(S, blockIdx.x);
+    const LevelJob& J = jobs[E.job];
+    const int b = blockIdx.y, n = blockIdx.z, N = gridDim.z;
+    if (b >= J.nb) return;
+    const int h = J.h, w = J.w, cs = J.ct_shift, CT = 1 << cs;
+    const int x0 = (blockIdx.x - E.start) << cs;
+    const int cols = min(CT, w - x0);
+    const int E_ = h << cs;
+    const bool band = J.is_band != 0;
+    float2* a = smem;
+    const float2* Xn = X + (size_t)n * H * W;
+    const float* radial = J.radial;
+    {
+        constexpr int U = 4;                  // two dependent global loads per element: batch them
+        for (int q0 = threadIdx.x; q0 < E_; q0 += U * blockDim.x) {
+            float m[U];
+            float2 xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u * blockDim.x;
+                const int ky = q >> cs, c = q & (CT - 1);
+                m[u] = (q < E_ && c < cols) ? __ldg(radial + (size_t)ky * w + x0 + c) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u * blockDim.x;
+                const int ky = q >> cs, c = q & (CT - 1);
+                const int fy = sfreq(ky, h), fx = sfreq(x0 + c, w);
+                if (band && m[u] != 0.f) m[u] *= ang_factor(A, b, fy, fx);
+                xv[u] = make_float2(0.f, 0.f);
+                if (m[u] != 0.f) xv[u] = __ldg(Xn + (size_t)wrapi(fy, H) * W + wrapi(fx, W));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u * blockDim.x;
+                if (q < E_) {
+                    float2 v = make_float2(xv[u].x * m[u], xv[u].y * m[u]);
+                    if (band) v = cmul(v, A.fac);
+                    v.y = -v.y;
+                    fft_put<true>(J.fy, a, q & (CT - 1), q >> cs, v, cs, 0);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const FftResult R = fft_forward<true>(J.fy, a, nullptr, CT, cs, 0, true, FftCtx{(int)threadIdx.x, (int)blockDim.x});
+    float2* dst = regionB + (size_t)N * J.t_off + ((size_t)n * J.nb + b) * h * w;
+    for (int q = threadIdx.x; q < E_; q += blockDim.x) {
+        const int pos = q >> cs, c = q & (CT - 1);
+        if (c >= cols) continue;
+        const int y = R.perm ? (int)__ldg(R.perm + pos) : pos;
+        dst[(size_t)y * w + x0 + c] = fft_get<true>(J.fy, R, c, pos, cs, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: column pass of the final IFFT of the reconstruction: value = conj( sum over levels of
+//   Y_l[n][fy mod h_l][fx mod w_l] (+ high spectrum) ); out: T of the full-size job.   grid: (column tiles, 1, N)
 // ------------------------------------------------------------------------------------------------
 struct GatherArgs {
     int nlev;                     // number of level spectra (band levels + low)
@@ -362,55 +567,17 @@ struct GatherArgs {
     const float2* Yhigh;          // [N][H][W] or null
 };
 
-template <bool ANG>
-__global__ void __launch_bounds__(512) k_cols_inv_decomp(Fft1D P, int h, int w, int H, int W, int CT, int nbB,
-                                                         const float2* __restrict__ X, const float* __restrict__ radial,
-                                                         AngParams A, float2* __restrict__ T) {
+__global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_gather(const LevelJob* __restrict__ jobs, int job, const GatherArgs G,
+                                                                    float inv_hh, float inv_hw, float2* __restrict__ regionB) {
     extern __shared__ float2 smem[];
-    const int E = h * CT;
-    float2* a = smem;
-    float2* bq = smem + E;
-    const int x0 = blockIdx.x * CT, n = blockIdx.y;
-    const int cols = min(CT, w - x0);
-    const float2* Xn = X + (size_t)n * H * W;
-    for (int b = 0; b < nbB; ++b) {
-        for (int q = threadIdx.x; q < E; q += blockDim.x) {
-            const int ky = q / CT, c = q - ky * CT;
-            float2 v = make_float2(0.f, 0.f);
-            if (c < cols) {
-                const int kx = x0 + c;
-                const int fy = sfreq(ky, h), fx = sfreq(kx, w);
-                float m = __ldg(radial + (size_t)ky * w + kx);
-                if (ANG && m != 0.f) m *= ang_factor(A, b, fy, fx);
-                if (m != 0.f) {
-                    const float2 xv = __ldg(Xn + (size_t)wrapi(fy, H) * W + wrapi(fx, W));
-                    v = make_float2(xv.x * m, xv.y * m);
-                    if (ANG) v = cmul(v, A.fac);
-                }
-            }
-            a[q] = v;
-        }
-        __syncthreads();
-        float2* res = fft_smem<true>(P, a, bq, CT, 1, CT);
-        float2* dst = T + ((size_t)n * nbB + b) * h * w;
-        for (int q = threadIdx.x; q < E; q += blockDim.x) {
-            const int y = q / CT, c = q - y * CT;
-            if (c < cols) dst[(size_t)y * w + x0 + c] = res[q];
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(512) k_cols_inv_gather(Fft1D P, int H, int W, int CT, GatherArgs G, float inv_hh,
-                                                         float inv_hw, float2* __restrict__ T) {
-    extern __shared__ float2 smem[];
-    const int E = H * CT;
-    float2* a = smem;
-    float2* bq = smem + E;
-    const int x0 = blockIdx.x * CT, n = blockIdx.y;
+    const LevelJob& J = jobs[job];
+    const int H = J.h, W = J.w, cs = J.ct_shift, CT = 1 << cs;
+    const int x0 = blockIdx.x << cs, n = blockIdx.z, N = gridDim.z;
     const int cols = min(CT, W - x0);
-    for (int q = threadIdx.x; q < E; q += blockDim.x) {
-        const int ky = q / CT, c = q - ky * CT;
+    const int E_ = H << cs;
+    float2* a = smem;
+    for (int q = threadIdx.x; q < E_; q += blockDim.x) {
+        const int ky = q >> cs, c = q & (CT - 1);
         float2 v = make_float2(0.f, 0.f);
         if (c < cols) {
             const int kx = x0 + c;
@@ -419,7 +586,7 @@ __global__ void __launch_bounds__(512) k_cols_inv_gather(Fft1D P, int H, int W, 
             const float r2 = xv * xv + yv * yv;
             if (G.Yhigh) v = G.Yhigh[((size_t)n * H + ky) * W + kx];
             for (int l = 0; l < G.nlev; ++l) {
-                const LevelGeom g = G.lv[l];
+                const LevelGeom& g = G.lv[l];
                 // nested centred windows: once outside, outside of all coarser levels too
                 if (fy < -(g.h >> 1) || fy > g.h - 1 - (g.h >> 1) || fx < -(g.w >> 1) || fx > g.w - 1 - (g.w >> 1)) break;
                 if (!((G.active >> l) & 1ull)) continue;
@@ -428,136 +595,178 @@ __global__ void __launch_bounds__(512) k_cols_inv_gather(Fft1D P, int H, int W, 
                 const float2 y = G.Y[(size_t)n * G.plane_stride + g.off + (size_t)wrapi(fy, g.h) * g.w + wrapi(fx, g.w)];
                 v = cadd(v, y);
             }
+            v.y = -v.y;
         }
-        a[q] = v;
+        fft_put<true>(J.fy, a, c, ky, v, cs, 0);
     }
     __syncthreads();
-    float2* res = fft_smem<true>(P, a, bq, CT, 1, CT);
-    float2* dst = T + (size_t)n * H * W;
-    for (int q = threadIdx.x; q < E; q += blockDim.x) {
-        const int y = q / CT, c = q - y * CT;
-        if (c < cols) dst[(size_t)y * W + x0 + c] = res[q];
+    const FftResult R = fft_forward<true>(J.fy, a, nullptr, CT, cs, 0, true, FftCtx{(int)threadIdx.x, (int)blockDim.x});
+    float2* dst = regionB + (size_t)N * J.t_off + (size_t)n * H * W;
+    for (int q = threadIdx.x; q < E_; q += blockDim.x) {
+        const int pos = q >> cs, c = q & (CT - 1);
+        if (c >= cols) continue;
+        const int y = R.perm ? (int)__ldg(R.perm + pos) : pos;
+        dst[(size_t)y * W + x0 + c] = fft_get<true>(J.fy, R, c, pos, cs, 0);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: row pass, inverse, with output epilogue.  T[n][b][y][:] -> IFFT along x -> * scale ->
-//   EPI 0: real part -> out0[n][y][x]
-//   EPI 1: polar: phase -> out0, amplitude -> out1 at channel n*nbB + b; per-plane max amplitude
-//          (pyramid.py:63-69, phase_net.py:47-59)
-//   EPI 2: complex interleaved -> tab.p[b][n][y][x][2]
-// grid: (ceil(h/RB), nbB, N)
+// K5: row pass of an IFFT with output epilogue.  T[n][b][y][:] -> forward FFT along x -> conj, scale 1/(h*w) ->
+//   mode 0: real part -> q0[n][y][x]
+//   mode 1: polar: phase -> q0, amplitude -> q1 at channel n*nb + b; per-plane max amplitude -> aux[n]
+//           (pyramid.py:63-69, phase_net.py:47-59)
+//   mode 2: complex interleaved -> tab.p[b][n][y][x][2]
+// grid: (row tiles of all jobs, nb, N)
 // ------------------------------------------------------------------------------------------------
-struct MutPtrTable { float* p[MAX_BANDS]; };
-
-template <int EPI>
-__global__ void __launch_bounds__(256) k_rows_inv(Fft1D P, int h, int w, int RB, int nbB, const float2* __restrict__ T,
-                                                  float scale, float* __restrict__ out0, float* __restrict__ out1,
-                                                  MutPtrTable tab, float* __restrict__ amp_max) {
+__global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_inv(const LevelJob* __restrict__ jobs, const LaunchSet S, MutPtrTable tab,
+                                                             const float2* __restrict__ regionB) {
     extern __shared__ float2 smem[];
+    const SetEntry& E = find_entry(S, blockIdx.x);
+    const LevelJob& J = jobs[E.job];
+    const int mode = E.mode;
+    const int nbB = (mode == 0) ? 1 : J.nb;
+    const int b = blockIdx.y, n = blockIdx.z, N = gridDim.z;
+    if (b >= nbB) return;
+    const int h = J.h, w = J.w, rb = J.rb;
+    const int y0 = (blockIdx.x - E.start) * rb;
+    const int rows = min(rb, h - y0);
+    const int pitch = fft_row_pitch(J.fx.M, J.fx.pad);
     float2* a = smem;
-    float2* bq = smem + RB * w;
-    const int y0 = blockIdx.x * RB, b = blockIdx.y, n = blockIdx.z;
-    const int rows = min(RB, h - y0);
-    const float2* src = T + (((size_t)n * nbB + b) * h + y0) * w;
-    for (int q = threadIdx.x; q < rows * w; q += blockDim.x) a[q] = src[q];
-    __syncthreads();
-    float2* res = fft_smem<true>(P, a, bq, rows, w, 1);
-    float mx = 0.f;
-    for (int q = threadIdx.x; q < rows * w; q += blockDim.x) {
-        const float2 z = make_float2(res[q].x * scale, res[q].y * scale);
-        const size_t pix = (size_t)y0 * w + q;
-        if (EPI == 0) {
-            out0[(size_t)n * h * w + pix] = z.x;
-        } else if (EPI == 1) {
-            const size_t o = ((size_t)n * nbB + b) * h * w + pix;
-            const float am = sqrtf(z.x * z.x + z.y * z.y);       // torch.abs            (pyramid.py:67)
-            out0[o] = atan2f(z.y, z.x);                          // imag(log z)          (pyramid.py:63)
-            out1[o] = am;
-            mx = fmaxf(mx, am);
-        } else {
-            ((float2*)tab.p[b])[(size_t)n * h * w + pix] = z;
+    float2* bq = smem + (size_t)rb * pitch;
+    const unsigned mag_w = J.mag_w;
+    const size_t plane = (size_t)h * w;
+    const float2* src = regionB + (size_t)N * J.t_off + ((size_t)n * nbB + b) * plane + (size_t)y0 * w;
+    {
+        constexpr int U = 8;                  // independent global loads in flight per thread
+        const int total = rows * w;
+        for (int q0 = threadIdx.x; q0 < total; q0 += U * blockDim.x) {
+            float2 z[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u * blockDim.x;
+                if (q < total) z[u] = __ldcs(src + q);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u * blockDim.x;
+                if (q < total) {
+                    const int r = (int)fast_div((unsigned)q, (unsigned)w, mag_w), x = q - r * w;
+                    fft_put<false>(J.fx, a, r, x, z[u], 0, pitch);
+                }
+            }
         }
     }
-    if (EPI == 1 && amp_max) {
+    __syncthreads();
+    const FftResult R = fft_forward<false>(J.fx, a, bq, rows, 0, pitch, false, FftCtx{(int)threadIdx.x, (int)blockDim.x});
+    const float scale = 1.f / ((float)h * (float)w);
+    float mx = 0.f;
+    for (int q = threadIdx.x; q < rows * w; q += blockDim.x) {
+        const int r = (int)fast_div((unsigned)q, (unsigned)w, mag_w), x = q - r * w;
+        const float2 t = fft_get<false>(J.fx, R, r, x, 0, pitch);
+        const float2 z = make_float2(t.x * scale, -t.y * scale);
+        const size_t pix = (size_t)y0 * w + q;
+        if (mode == 0) {
+            E.q0[(size_t)n * plane + pix] = z.x;
+        } else if (mode == 1) {
+            const size_t o = ((size_t)n * nbB + b) * plane + pix;
+            const float am = sqrtf(z.x * z.x + z.y * z.y);       // torch.abs            (pyramid.py:67)
+            E.q0[o] = fast_atan2f(z.y, z.x);                     // imag(log z)          (pyramid.py:63)
+            E.q1[o] = am;
+            mx = fmaxf(mx, am);
+        } else {
+            ((float2*)tab.p[b])[(size_t)n * plane + pix] = z;
+        }
+    }
+    if (mode == 1 && E.aux) {
         for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if ((threadIdx.x & 31) == 0) atomicMax((int*)(amp_max + n), __float_as_int(mx));  // amplitudes are >= 0
+        if ((threadIdx.x & 31) == 0) atomicMax((int*)(E.aux + n), __float_as_int(mx));  // amplitudes are >= 0
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host: launch helpers
 // ------------------------------------------------------------------------------------------------
-static int pick_rb(int h, int w) { return std::max(1, std::min(std::min(h, 32), ROW_ELEMS / w)); }
-static int pick_ct(int h, int w, int nbuf_elems) {
-    int ct = 32;
-    while (ct > 1 && (size_t)ct * h > (size_t)nbuf_elems) ct >>= 1;
-    while (ct > 1 && ct >= 2 * w) ct >>= 1;
-    return ct;
-}
-
 template <typename K>
 static int ensure_smem(K kernel, size_t bytes) {
     if (bytes > 227 * 1024) { set_error("pyramid: tile needs %zu B of shared memory (> 227 KB)", bytes); return FVFI_EINVAL; }
-    if (bytes > 48 * 1024) FVFI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    FVFI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 48 * 1024)));
     return FVFI_OK;
 }
 
-template <int MODE>
-static int launch_rows_fwd(const Fft1D& P, int h, int w, int nbB, int N, const float* in0, const float* in1,
-                           const PtrTable& tab, float2* T, cudaStream_t s) {
-    const int RB = pick_rb(h, w);
-    const size_t smem = (size_t)2 * RB * w * sizeof(float2);
-    if (int rc = ensure_smem(k_rows_fwd<MODE>, smem)) return rc;
-    dim3 grid(ceil_div(h, RB), nbB, N);
-    k_rows_fwd<MODE><<<grid, 256, smem, s>>>(P, h, w, RB, nbB, in0, in1, tab, T);
+static size_t row_smem(const LevelJob& J) { return (size_t)J.rb * row_bytes_per_row(J.fx); }
+static size_t col_smem(const LevelJob& J, bool combine) {
+    return (((size_t)J.fy.M << J.ct_shift) + (combine ? ((size_t)J.h << J.ct_shift) : 0)) * sizeof(float2);
+}
+
+struct SetBuilder {
+    const fvfi_pyr_plan* p;
+    LaunchSet rows{}, cols{};
+    size_t rows_smem = 0, cols_smem = 0;
+    int max_nb = 1;
+    bool has_combine = false;
+    explicit SetBuilder(const fvfi_pyr_plan* plan) : p(plan) {}
+    bool full() const { return rows.n >= MAX_SET; }
+    bool empty() const { return rows.n == 0; }
+    void add(int job, int mode, const float* p0, const float* p1, float* q0, float* q1, float* aux, bool combine_cols) {
+        const LevelJob& J = p->jobs[job];
+        SetEntry e{};
+        e.job = job; e.mode = mode; e.p0 = p0; e.p1 = p1; e.q0 = q0; e.q1 = q1; e.aux = aux;
+        e.start = rows.total;
+        rows.e[rows.n++] = e;
+        rows.total += J.row_tiles;
+        e.start = cols.total;
+        e.mode = combine_cols ? 1 : 0;
+        cols.e[cols.n++] = e;
+        cols.total += J.col_tiles;
+        rows_smem = std::max(rows_smem, row_smem(J));
+        cols_smem = std::max(cols_smem, col_smem(J, combine_cols));
+        if (mode != 0) max_nb = std::max(max_nb, J.nb);
+        has_combine |= combine_cols;
+    }
+};
+
+static int launch_rows_fwd(const fvfi_pyr_plan* p, const SetBuilder& sb, const PtrTable& tab, int N, float2* regionB, cudaStream_t s) {
+    if (int rc = ensure_smem(k_rows_fwd, sb.rows_smem)) return rc;
+    dim3 grid(sb.rows.total, sb.max_nb, N);
+    k_rows_fwd<<<grid, PYR_THREADS, sb.rows_smem, s>>>(p->d_jobs, sb.rows, tab, regionB);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }
 
-template <bool ANG>
-static int launch_cols_fwd(const Fft1D& P, int h, int w, int nbB, int N, const float2* T, const float* radial,
-                           const AngParams& A, float2* out, size_t stride, cudaStream_t s) {
-    const int CT = pick_ct(h, w, COL_ELEMS);
-    const size_t smem = (size_t)3 * h * CT * sizeof(float2);
-    if (int rc = ensure_smem(k_cols_fwd<ANG>, smem)) return rc;
-    dim3 grid(ceil_div(w, CT), N);
-    k_cols_fwd<ANG><<<grid, (h * CT > 2048) ? 512 : 256, smem, s>>>(P, h, w, CT, nbB, T, radial, A, out, stride);
+static int launch_cols_fwd(const fvfi_pyr_plan* p, const SetBuilder& sb, int N, const float2* regionB, float2* out, size_t stride,
+                           int add_c_off, int use_radial, cudaStream_t s) {
+    if (int rc = ensure_smem(k_cols_fwd, sb.cols_smem)) return rc;
+    dim3 grid(sb.cols.total, 1, N);
+    k_cols_fwd<<<grid, PYR_THREADS, sb.cols_smem, s>>>(p->d_jobs, sb.cols, p->ang_rec, regionB, out, stride, add_c_off, use_radial);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }
 
-template <bool ANG>
-static int launch_cols_inv_decomp(const Fft1D& P, int h, int w, int H, int W, int nbB, int N, const float2* X,
-                                  const float* radial, const AngParams& A, float2* T, cudaStream_t s) {
-    const int CT = pick_ct(h, w, COL_ELEMS);
-    const size_t smem = (size_t)2 * h * CT * sizeof(float2);
-    if (int rc = ensure_smem(k_cols_inv_decomp<ANG>, smem)) return rc;
-    dim3 grid(ceil_div(w, CT), N);
-    k_cols_inv_decomp<ANG><<<grid, (h * CT > 2048) ? 512 : 256, smem, s>>>(P, h, w, H, W, CT, nbB, X, radial, A, T);
+static int launch_cols_inv_decomp(const fvfi_pyr_plan* p, const SetBuilder& sb, int N, const float2* X, float2* regionB, cudaStream_t s) {
+    if (int rc = ensure_smem(k_cols_inv_decomp, sb.cols_smem)) return rc;
+    int nbmax = 1;
+    for (int i = 0; i < sb.cols.n; ++i) nbmax = std::max(nbmax, p->jobs[sb.cols.e[i].job].nb);
+    dim3 grid(sb.cols.total, nbmax, N);
+    k_cols_inv_decomp<<<grid, PYR_THREADS, sb.cols_smem, s>>>(p->d_jobs, sb.cols, p->ang_build, p->H, p->W, X, regionB);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }
 
-template <int EPI>
-static int launch_rows_inv(const Fft1D& P, int h, int w, int nbB, int N, const float2* T, float scale, float* out0,
-                           float* out1, const MutPtrTable& tab, float* amp_max, cudaStream_t s) {
-    const int RB = pick_rb(h, w);
-    const size_t smem = (size_t)2 * RB * w * sizeof(float2);
-    if (int rc = ensure_smem(k_rows_inv<EPI>, smem)) return rc;
-    dim3 grid(ceil_div(h, RB), nbB, N);
-    k_rows_inv<EPI><<<grid, 256, smem, s>>>(P, h, w, RB, nbB, T, scale, out0, out1, tab, amp_max);
+static int launch_rows_inv(const fvfi_pyr_plan* p, const SetBuilder& sb, const MutPtrTable& tab, int N, const float2* regionB, cudaStream_t s) {
+    if (int rc = ensure_smem(k_rows_inv, sb.rows_smem)) return rc;
+    dim3 grid(sb.rows.total, sb.max_nb, N);
+    k_rows_inv<<<grid, PYR_THREADS, sb.rows_smem, s>>>(p->d_jobs, sb.rows, tab, regionB);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }
 
 struct Workspace {
-    float2 *A, *B, *C;  // A: N*H*W ; B: N*nb*H*W ; C: N*level_elems
+    float2 *A, *B, *C;  // A: N*H*W (X / high spectrum) ; B: N*(nb*level_elems + H*W) (intermediates) ; C: N*level_elems
 };
 
 static size_t ws_elems(const fvfi_pyr_plan* p, int N) {
     const size_t HW = (size_t)p->H * p->W;
-    return (size_t)N * (HW + (size_t)p->nbands * HW + p->level_elems) + 64;
+    return (size_t)N * (HW + ((size_t)p->nbands * p->level_elems + HW) + p->level_elems) + 64;
 }
 
 static Workspace carve(const fvfi_pyr_plan* p, int N, void* ws) {
@@ -566,109 +775,135 @@ static Workspace carve(const fvfi_pyr_plan* p, int N, void* ws) {
     uintptr_t base = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
     w.A = (float2*)base;
     w.B = w.A + (size_t)N * HW;
-    w.C = w.B + (size_t)N * p->nbands * HW;
+    w.C = w.B + (size_t)N * ((size_t)p->nbands * p->level_elems + HW);
     return w;
 }
+
+static bool is_small(const LevelJob& J) { return (long long)J.h * J.w <= SMALL_LEVEL_ELEMS; }
 
 // decomposition shared by the polar and complex front ends
 static int decompose(const fvfi_pyr_plan* p, const float* img, int N, float* high, float* const* phase,
                      float* const* amp, float* const* bands, float* low, float* amp_max, void* workspace,
                      cudaStream_t s) {
     const int H = p->H, W = p->W, L = p->L, nb = p->nbands;
+    const int FULL = L + 1;
     Workspace ws = carve(p, N, workspace);
     PtrTable none{};
     MutPtrTable mnone{};
-    AngParams noang{};
-    // X = FFT2(img): rows then columns (in place in region A)
-    if (int rc = launch_rows_fwd<0>(p->fx[0], H, W, 1, N, img, nullptr, none, ws.B, s)) return rc;
-    if (int rc = launch_cols_fwd<false>(p->fy[0], H, W, 1, N, ws.B, nullptr, noang, ws.A, (size_t)H * W, s)) return rc;
-    if (amp_max) FVFI_CUDA(cudaMemsetAsync(amp_max, 0, (size_t)L * N * sizeof(float), s));
-    // high-pass residual
-    if (high) {
-        if (int rc = launch_cols_inv_decomp<false>(p->fy[0], H, W, H, W, 1, N, ws.A, p->hi0, noang, ws.B, s)) return rc;
-        if (int rc = launch_rows_inv<0>(p->fx[0], H, W, 1, N, ws.B, 1.f / ((float)H * W), high, nullptr, mnone, nullptr, s))
-            return rc;
+    // X = FFT2(img): rows (into the full-size intermediate) then columns (into region A)
+    {
+        SetBuilder sb(p);
+        sb.add(FULL, 0, img, nullptr, nullptr, nullptr, nullptr, false);
+        if (int rc = launch_rows_fwd(p, sb, none, N, ws.B, s)) return rc;
+        if (int rc = launch_cols_fwd(p, sb, N, ws.B, ws.A, (size_t)H * W, 0, 0, s)) return rc;
     }
-    // oriented band-pass levels
+    if (amp_max) FVFI_CUDA(cudaMemsetAsync(amp_max, 0, (size_t)L * N * sizeof(float), s));
+    // every output component is an independent job: big ones get their own launch pair, small ones share one
+    SetBuilder small(p);
+    auto flush = [&](SetBuilder& sb, const MutPtrTable& tab) -> int {
+        if (sb.empty()) return FVFI_OK;
+        if (int rc = launch_cols_inv_decomp(p, sb, N, ws.A, ws.B, s)) return rc;
+        if (int rc = launch_rows_inv(p, sb, tab, N, ws.B, s)) return rc;
+        sb = SetBuilder(p);
+        return FVFI_OK;
+    };
+    auto submit = [&](int job, int mode, float* q0, float* q1, float* aux) -> int {
+        if (is_small(p->jobs[job])) {
+            small.add(job, mode, nullptr, nullptr, q0, q1, aux, false);
+            if (small.full()) return flush(small, mnone);
+            return FVFI_OK;
+        }
+        SetBuilder one(p);
+        one.add(job, mode, nullptr, nullptr, q0, q1, aux, false);
+        return flush(one, mnone);
+    };
+    if (high)
+        if (int rc = submit(FULL, 0, high, nullptr, nullptr)) return rc;
     for (int l = 0; l < L; ++l) {
-        const int h = p->lv[l].h, w = p->lv[l].w;
         if (phase ? (phase[l] == nullptr) : (bands[l * nb] == nullptr)) continue;
-        if (int rc = launch_cols_inv_decomp<true>(p->fy[l], h, w, H, W, nb, N, ws.A, p->radial[l], p->ang_build, ws.B, s))
-            return rc;
-        const float scale = 1.f / ((float)h * w);
         if (phase) {
-            if (int rc = launch_rows_inv<1>(p->fx[l], h, w, nb, N, ws.B, scale, phase[l], amp[l], mnone,
-                                            amp_max ? amp_max + (size_t)l * N : nullptr, s))
-                return rc;
+            if (int rc = submit(l, 1, phase[l], amp[l], amp_max ? amp_max + (size_t)l * N : nullptr)) return rc;
         } else {
             MutPtrTable t{};
             for (int b = 0; b < nb; ++b) t.p[b] = bands[l * nb + b];
-            if (int rc = launch_rows_inv<2>(p->fx[l], h, w, nb, N, ws.B, scale, nullptr, nullptr, t, nullptr, s)) return rc;
+            SetBuilder one(p);
+            one.add(l, 2, nullptr, nullptr, nullptr, nullptr, nullptr, false);
+            if (int rc = flush(one, t)) return rc;
         }
     }
-    // low-pass residual
-    if (low) {
-        const int h = p->lv[L].h, w = p->lv[L].w;
-        if (int rc = launch_cols_inv_decomp<false>(p->fy[L], h, w, H, W, 1, N, ws.A, p->radial[L], noang, ws.B, s)) return rc;
-        if (int rc = launch_rows_inv<0>(p->fx[L], h, w, 1, N, ws.B, 1.f / ((float)h * w), low, nullptr, mnone, nullptr, s))
-            return rc;
-    }
-    return FVFI_OK;
+    if (low)
+        if (int rc = submit(L, 0, low, nullptr, nullptr)) return rc;
+    return flush(small, mnone);
 }
 
 static int reconstruct(const fvfi_pyr_plan* p, const float* high, const float* const* phase, const float* const* amp,
                        const float* const* bands, const float* low, int N, float* img, void* workspace,
                        cudaStream_t s) {
     const int H = p->H, W = p->W, L = p->L, nb = p->nbands;
+    const int FULL = L + 1;
     Workspace ws = carve(p, N, workspace);
     PtrTable none{};
     MutPtrTable mnone{};
-    AngParams noang{};
     GatherArgs G{};
     G.nlev = L + 1;
     G.Y = ws.C;
     G.plane_stride = p->level_elems;
     G.active = 0;
     for (int l = 0; l <= L; ++l) G.lv[l] = p->lv[l];
+    SetBuilder small(p);
+    auto flush = [&](SetBuilder& sb, const PtrTable& tab) -> int {
+        if (sb.empty()) return FVFI_OK;
+        if (int rc = launch_rows_fwd(p, sb, tab, N, ws.B, s)) return rc;
+        if (int rc = launch_cols_fwd(p, sb, N, ws.B, ws.C, p->level_elems, 1, 1, s)) return rc;
+        sb = SetBuilder(p);
+        return FVFI_OK;
+    };
     for (int l = 0; l < L; ++l) {
-        const int h = p->lv[l].h, w = p->lv[l].w;
         const bool have = phase ? (phase[l] != nullptr && amp[l] != nullptr) : (bands[l * nb] != nullptr);
         if (!have) continue;
+        G.active |= 1ull << l;
         if (phase) {
-            if (int rc = launch_rows_fwd<1>(p->fx[l], h, w, nb, N, phase[l], amp[l], none, ws.B, s)) return rc;
+            if (is_small(p->jobs[l])) {
+                small.add(l, 1, phase[l], amp[l], nullptr, nullptr, nullptr, true);
+                if (small.full())
+                    if (int rc = flush(small, none)) return rc;
+            } else {
+                SetBuilder one(p);
+                one.add(l, 1, phase[l], amp[l], nullptr, nullptr, nullptr, true);
+                if (int rc = flush(one, none)) return rc;
+            }
         } else {
             PtrTable t{};
             for (int b = 0; b < nb; ++b) t.p[b] = bands[l * nb + b];
-            if (int rc = launch_rows_fwd<2>(p->fx[l], h, w, nb, N, nullptr, nullptr, t, ws.B, s)) return rc;
+            SetBuilder one(p);
+            one.add(l, 2, nullptr, nullptr, nullptr, nullptr, nullptr, true);
+            if (int rc = flush(one, t)) return rc;
         }
-        if (int rc = launch_cols_fwd<true>(p->fy[l], h, w, nb, N, ws.B, p->radial[l], p->ang_rec, ws.C + p->lv[l].off,
-                                           p->level_elems, s))
-            return rc;
-        G.active |= 1ull << l;
     }
     if (low) {
-        const int h = p->lv[L].h, w = p->lv[L].w;
-        if (int rc = launch_rows_fwd<0>(p->fx[L], h, w, 1, N, low, nullptr, none, ws.B, s)) return rc;
-        if (int rc = launch_cols_fwd<false>(p->fy[L], h, w, 1, N, ws.B, p->radial[L], noang, ws.C + p->lv[L].off,
-                                            p->level_elems, s))
-            return rc;
+        small.add(L, 0, low, nullptr, nullptr, nullptr, nullptr, false);
         G.active |= 1ull << L;
     }
+    if (int rc = flush(small, none)) return rc;
     if (high) {
-        if (int rc = launch_rows_fwd<0>(p->fx[0], H, W, 1, N, high, nullptr, none, ws.B, s)) return rc;
-        if (int rc = launch_cols_fwd<false>(p->fy[0], H, W, 1, N, ws.B, p->hi0, noang, ws.A, (size_t)H * W, s)) return rc;
+        SetBuilder one(p);
+        one.add(FULL, 0, high, nullptr, nullptr, nullptr, nullptr, false);
+        if (int rc = launch_rows_fwd(p, one, none, N, ws.B, s)) return rc;
+        if (int rc = launch_cols_fwd(p, one, N, ws.B, ws.A, (size_t)H * W, 0, 1, s)) return rc;
         G.Yhigh = ws.A;
     }
     // gather all level spectra + inverse FFT2
     {
-        const int CT = pick_ct(H, W, COL_ELEMS);
-        const size_t smem = (size_t)2 * H * CT * sizeof(float2);
+        const LevelJob& J = p->jobs[FULL];
+        const size_t smem = col_smem(J, false);
         if (int rc = ensure_smem(k_cols_inv_gather, smem)) return rc;
-        dim3 grid(ceil_div(W, CT), N);
-        k_cols_inv_gather<<<grid, 512, smem, s>>>(p->fy[0], H, W, CT, G, p->ang_rec.inv_hh, p->ang_rec.inv_hw, ws.B);
+        dim3 grid(J.col_tiles, 1, N);
+        k_cols_inv_gather<<<grid, PYR_THREADS, smem, s>>>(p->d_jobs, FULL, G, p->ang_rec.inv_hh, p->ang_rec.inv_hw, ws.B);
         FVFI_LAUNCH_CHECK();
     }
-    return launch_rows_inv<0>(p->fx[0], H, W, 1, N, ws.B, 1.f / ((float)H * W), img, nullptr, mnone, nullptr, s);
+    SetBuilder fin(p);
+    fin.add(FULL, 0, nullptr, nullptr, img, nullptr, nullptr, false);
+    return launch_rows_inv(p, fin, mnone, N, ws.B, s);
 }
 
 }  // namespace fvfi

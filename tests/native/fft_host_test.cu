@@ -1,0 +1,49 @@
+// Host-side harness for csrc/fft_engine.cuh: runs the SAME stage code (index math, butterflies, Bluestein
+// driver) on the CPU with one "thread", so tests/test_fft_engine_host.py can check every length against numpy.fft.
+#include <string.h>
+
+#include <vector>
+
+#include "fft_plan.hpp"
+
+using namespace fvfi;
+
+// mode 0: rows layout, out-of-place (Stockham) for direct lengths; mode 1: columns layout, in-place DIF (+perm)
+// in/out: [batch][n][2] floats.  Returns 0, or -1 if no plan.
+extern "C" int fft_host_run(int n, int mode, int batch, const float* in, float* out, int* info) {
+    HostFftPlan H;
+    const bool col = mode == 1;
+    if (!fft_make_plan(n, !col, H)) return -1;
+    H.p.tw = H.tw.data();
+    H.p.perm = H.p.bluestein ? nullptr : H.perm.data();
+    H.p.chirp = H.chirp.data();
+    H.p.bhat = H.bhat.data();
+    const int M = H.p.M;
+    int ctshift = 0;
+    while ((1 << ctshift) < batch) ++ctshift;
+    const int pitch = fft_row_pitch(M, H.p.pad);
+    const size_t elems = col ? ((size_t)M << ctshift) : (size_t)batch * pitch;
+    std::vector<float2> a(elems, make_float2(7.f, 7.f)), b(elems, make_float2(9.f, 9.f));   // garbage-filled on purpose
+    for (int bb = 0; bb < batch; ++bb)
+        for (int i = 0; i < n; ++i) {
+            const float2 v = make_float2(in[((size_t)bb * n + i) * 2], in[((size_t)bb * n + i) * 2 + 1]);
+            if (col) fft_put<true>(H.p, a.data(), bb, i, v, ctshift, pitch);
+            else fft_put<false>(H.p, a.data(), bb, i, v, ctshift, pitch);
+        }
+    FftResult r = col ? fft_forward<true>(H.p, a.data(), b.data(), batch, ctshift, pitch, true, FftCtx{0, 1})
+                      : fft_forward<false>(H.p, a.data(), b.data(), batch, ctshift, pitch, false, FftCtx{0, 1});
+    for (int bb = 0; bb < batch; ++bb)
+        for (int pos = 0; pos < n; ++pos) {
+            const float2 v = col ? fft_get<true>(H.p, r, bb, pos, ctshift, pitch) : fft_get<false>(H.p, r, bb, pos, ctshift, pitch);
+            const int k = r.perm ? r.perm[pos] : pos;
+            out[((size_t)bb * n + k) * 2] = v.x;
+            out[((size_t)bb * n + k) * 2 + 1] = v.y;
+        }
+    if (info) {
+        info[0] = M;
+        info[1] = H.p.bluestein;
+        info[2] = H.p.nfac;
+        for (int s = 0; s < H.p.nfac; ++s) info[3 + s] = H.p.fac[s];
+    }
+    return 0;
+}
