@@ -37,7 +37,7 @@ class PipelineWorkload:
         self.launches_per_step = None
         self.stage_ms = {}
         self.nsteps = 0
-        self.config_extra = {"tf32_convs": self.tf32, "convs": "cuDNN via torch.nn.Conv2d (scaffolding)",
+        self.config_extra = {"tf32_convs": self.tf32, "convs": "tcgen05 3xTF32 implicit GEMM (csrc/conv_tc.cu)",
                              "phase_plane_chunk": self.pipe.phase_net.plane_chunk,
                              "sub_batch": self.pipe.max_batch}
 

@@ -67,6 +67,7 @@ struct LevelJob {
     int h, w, nb, is_band;
     int ct_shift, rb;            // column tile = 1 << ct_shift columns; rows per CTA in a row pass
     int col_tiles, row_tiles;
+    int ct_shift_c, col_tiles_c; // column tile of the band-combining pass (two buffers per tile)
     unsigned mag_w;              // ceil(2^32 / w)
     long long t_off;             // intermediate T of this level starts at regionB + N * t_off (complex elements)
     long long c_off;             // per-plane offset of the level spectrum in region C
@@ -190,6 +191,10 @@ static int build_jobs(fvfi_pyr_plan* p) {
         rb = std::max(1, std::min(std::min(rb, 16), J.h));
         J.rb = rb;
         J.col_tiles = ceil_div(J.w, 1 << cs);
+        int cc = cs;                 // combine pass: transform buffer + accumulator, aim for three CTAs per SM
+        while (cc > 2 && (((size_t)J.fy.M + J.h) << cc) * sizeof(float2) > 75 * 1024) --cc;
+        J.ct_shift_c = cc;
+        J.col_tiles_c = ceil_div(J.w, 1 << cc);
         J.row_tiles = ceil_div(J.h, rb);
     }
     const LevelJob* d = nullptr;
@@ -433,7 +438,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_fwd(const Le
     const bool combine = E.mode == 1;
     const int nbB = combine ? J.nb : 1;
     const int n = blockIdx.z, N = gridDim.z;
-    const int h = J.h, w = J.w, cs = J.ct_shift, CT = 1 << cs;
+    const int h = J.h, w = J.w, cs = combine ? J.ct_shift_c : J.ct_shift, CT = 1 << cs;
     const int x0 = (blockIdx.x - E.start) << cs;
     const int cols = min(CT, w - x0);
     const int E_ = h << cs;
@@ -695,7 +700,7 @@ static int ensure_smem(K kernel, size_t bytes) {
 
 static size_t row_smem(const LevelJob& J) { return (size_t)J.rb * row_bytes_per_row(J.fx); }
 static size_t col_smem(const LevelJob& J, bool combine) {
-    return (((size_t)J.fy.M << J.ct_shift) + (combine ? ((size_t)J.h << J.ct_shift) : 0)) * sizeof(float2);
+    return combine ? ((((size_t)J.fy.M + J.h) << J.ct_shift_c) * sizeof(float2)) : (((size_t)J.fy.M << J.ct_shift) * sizeof(float2));
 }
 
 struct SetBuilder {
@@ -717,7 +722,7 @@ struct SetBuilder {
         e.start = cols.total;
         e.mode = combine_cols ? 1 : 0;
         cols.e[cols.n++] = e;
-        cols.total += J.col_tiles;
+        cols.total += combine_cols ? J.col_tiles_c : J.col_tiles;
         rows_smem = std::max(rows_smem, row_smem(J));
         cols_smem = std::max(cols_smem, col_smem(J, combine_cols));
         if (mode != 0) max_nb = std::max(max_nb, J.nb);
