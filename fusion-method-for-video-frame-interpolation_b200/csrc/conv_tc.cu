@@ -1,5 +1,14 @@
 // conv_tc.cu -- implicit-GEMM 2-D convolution on the 5th-gen tensor cores (tcgen05 + TMEM), fp32 in / fp32 out,
-// 3xTF32 error-compensated so the result matches an fp32 FFMA convolution to ~1e-6 relative.
+// split-operand error-compensated so the result matches an fp32 FFMA convolution to ~1e-6 relative.
+//
+// Two operand splits (same kernel, template PREC; same shared-memory bytes per MMA, so the descriptors are identical):
+//   PREC_F16X3  (default)  a = a_hi + a_lo with a_hi = fp16(a * 2^s), a_lo = fp16(a * 2^s - a_hi): 11 + 11 mantissa
+//                          bits, products exact in the fp32 accumulator; tcgen05.mma.kind::f16 runs at TWICE the
+//                          kind::tf32 rate and moves 16 instead of 8 channels per 32-byte K step.  Power-of-two scales
+//                          (activations 2^4, weights per layer so that max|w| lands in [2^14, 2^15)) keep both halves
+//                          in fp16's normal range; the epilogue multiplies by the exact inverse.  |a| * 2^4 > 65504 sets
+//                          an overflow flag the host checks (fvfi_conv2d_overflow_count) -- no silent saturation.
+//   PREC_TF32X3            a_hi = rna_tf32(a), a_lo = a - a_hi: the same 11 + 11 bits without any range limit.
 //
 // Used for the PhaseNet / KernelEstimation / FusionNet convolutions (the only dense contractions on the path;
 // reference: torch.nn.Conv2d -> cuDNN, src/phase_net/phase_net.py:190-199, src/fusion_net/fusion_adacofnet.py:19-83,
@@ -17,31 +26,42 @@
 //   (hi|lo, canonical layout) and streamed per (chunk, tap) with cp.async.bulk + mbarrier.
 //   Warp roles: warps 0-3 activation loaders + epilogue (TMEM -> regs -> bias/activation -> NHWC), warp 4 weight
 //   producer, warp 5 TMEM allocator + single-thread MMA issuer.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace fvfi {
 
-constexpr int CV_CHUNK = 16;            // input channels per K chunk (2 MMAs of K=8)
+constexpr int CV_KCHUNKS = 4;           // 16-byte K chunks per stage = two MMA K steps of 32 bytes
+constexpr int CV_HDR = 32;              // floats of header in front of the packed weights (scales, precision)
+constexpr int CV_X_SHIFT = 4;           // PREC_F16X3: activations are scaled by 2^4 before the fp16 split
 constexpr int CV_ROWS = 16;             // output rows per CTA
 constexpr int CV_LOADERS = 128;         // warps 0-3
 constexpr int CV_THREADS = 192;
-constexpr int CV_ASTAGES = 2;
+constexpr int CV_MAX_ASTAGES = 2;
 constexpr int CV_MAX_BSTAGES = 4;
 constexpr unsigned CV_SPIN_LIMIT = 200u * 1000u * 1000u;   // bounded waits: trap instead of hanging the GPU
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4, ACT_SOFTMAX = 5 };   // softmax over channels
 enum { PAD_ZERO = 0, PAD_REFLECT = 1 };
+enum { PREC_TF32X3 = 0, PREC_F16X3 = 1 };
+__host__ __device__ constexpr int cv_cpk(int prec) { return prec == PREC_F16X3 ? 8 : 4; }        // channels per 16-byte K chunk
+__host__ __device__ constexpr int cv_chunk(int prec) { return CV_KCHUNKS * cv_cpk(prec); }        // channels per stage
 
 struct ConvArgs {
     const float* x;        // [B,H,W,Cin] NHWC
-    const float* wpack;    // packed weights (see pack kernel)
+    const float* wpack;    // packed weights (see pack kernel), behind the CV_HDR-float header
+    const float* hdr;      // header of the packed weights: [0] = output scale (exact inverse of the operand scales)
+    int* overflow;         // PREC_F16X3: set to 1 when a scaled activation leaves fp16's range
     const float* bias;     // [Npad] or null
     float* y;              // [B,H,W,Cout] NHWC
     int B, H, W, Cin, Cout, Npad, KH, KW, pad_mode, act;
     int ldx, ldy;          // floats per pixel in the input / output storage (channel-slice views)
     int out_nchw;          // 1: y is planar [B,Cout,H,W] (coefficient maps for the warp kernel)
     int MT, RW, RH, NPIX;  // tiles per CTA, staged region geometry
-    int nchunks, bstages, tmem_cols;
+    int nchunks, last_ksteps, astages, bstages, tmem_cols;
     unsigned a_stage_bytes, b_stage_bytes;
 };
 
@@ -103,38 +123,44 @@ __device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, unsigned long long 
 // A single asm block: the tensor core consumes an MMA of N <= 128 every 40-64 cycles, which one warp can only sustain
 // if the issue stream is ~3 instructions per MMA (measured: a C++ loop with per-MMA descriptor arithmetic and elect
 // costs ~120 cycles per MMA).  Tile t: A descriptor + 8*t (eight pixels = 8 x 16 B), TMEM columns + t*Npad.
-#define FVFI_MMA3(D, AL, AH)                                                              \
-    "@pe tcgen05.mma.cta_group::1.kind::tf32 [" D "], " AL ", %4, %6, pa;\n\t"            \
-    "@pe tcgen05.mma.cta_group::1.kind::tf32 [" D "], " AH ", %5, %6, pt;\n\t"            \
-    "@pe tcgen05.mma.cta_group::1.kind::tf32 [" D "], " AH ", %4, %6, pt;\n\t"
-template <int MT>
+#define FVFI_MMA3(KIND, D, AL, AH)                                                        \
+    "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AL ", %4, %6, pa;\n\t"        \
+    "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AH ", %5, %6, pt;\n\t"        \
+    "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AH ", %4, %6, pt;\n\t"
+#define FVFI_KSTEP_BODY(KIND)                                                                                          \
+    if (MT == 1) {                                                                                                     \
+        asm volatile(                                                                                                  \
+            "{\n\t.reg .pred pe, pa, pt;\n\t"                                                                          \
+            "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"                       \
+            FVFI_MMA3(KIND, "%0", "%2", "%3") "}"                                                                      \
+            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc) : "memory");                  \
+    } else if (MT == 2) {                                                                                              \
+        asm volatile(                                                                                                  \
+            "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 al1, ah1;\n\t.reg .b32 d1;\n\t"                                  \
+            "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"                       \
+            "add.u64 al1, %2, 8;\n\tadd.u64 ah1, %3, 8;\n\tadd.u32 d1, %0, %1;\n\t"                                    \
+            FVFI_MMA3(KIND, "%0", "%2", "%3") FVFI_MMA3(KIND, "d1", "al1", "ah1") "}"                                  \
+            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc) : "memory");                  \
+    } else {                                                                                                           \
+        asm volatile(                                                                                                  \
+            "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 al1, ah1, al2, ah2, al3, ah3;\n\t.reg .b32 d1, d2, d3;\n\t"      \
+            "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"                       \
+            "add.u64 al1, %2, 8;\n\tadd.u64 ah1, %3, 8;\n\tadd.u32 d1, %0, %1;\n\t"                                    \
+            "add.u64 al2, %2, 16;\n\tadd.u64 ah2, %3, 16;\n\tadd.u32 d2, d1, %1;\n\t"                                  \
+            "add.u64 al3, %2, 24;\n\tadd.u64 ah3, %3, 24;\n\tadd.u32 d3, d2, %1;\n\t"                                  \
+            FVFI_MMA3(KIND, "%0", "%2", "%3") FVFI_MMA3(KIND, "d1", "al1", "ah1") FVFI_MMA3(KIND, "d2", "al2", "ah2")   \
+            FVFI_MMA3(KIND, "d3", "al3", "ah3") "}"                                                                    \
+            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc) : "memory");                  \
+    }
+template <int MT, int PREC>
 __device__ __forceinline__ void tc_mma_kstep(unsigned d, unsigned np, unsigned long long al, unsigned long long ah,
                                              unsigned long long bh, unsigned long long bl, unsigned idesc, unsigned acc) {
-    if (MT == 1) {
-        asm volatile(
-            "{\n\t.reg .pred pe, pa, pt;\n\t"
-            "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
-            FVFI_MMA3("%0", "%2", "%3") "}"
-            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc) : "memory");
-    } else if (MT == 2) {
-        asm volatile(
-            "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 al1, ah1;\n\t.reg .b32 d1;\n\t"
-            "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
-            "add.u64 al1, %2, 8;\n\tadd.u64 ah1, %3, 8;\n\tadd.u32 d1, %0, %1;\n\t"
-            FVFI_MMA3("%0", "%2", "%3") FVFI_MMA3("d1", "al1", "ah1") "}"
-            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc) : "memory");
+    if (PREC == PREC_F16X3) {
+        FVFI_KSTEP_BODY("f16")
     } else {
-        asm volatile(
-            "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 al1, ah1, al2, ah2, al3, ah3;\n\t.reg .b32 d1, d2, d3;\n\t"
-            "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
-            "add.u64 al1, %2, 8;\n\tadd.u64 ah1, %3, 8;\n\tadd.u32 d1, %0, %1;\n\t"
-            "add.u64 al2, %2, 16;\n\tadd.u64 ah2, %3, 16;\n\tadd.u32 d2, d1, %1;\n\t"
-            "add.u64 al3, %2, 24;\n\tadd.u64 ah3, %3, 24;\n\tadd.u32 d3, d2, %1;\n\t"
-            FVFI_MMA3("%0", "%2", "%3") FVFI_MMA3("d1", "al1", "ah1") FVFI_MMA3("d2", "al2", "ah2") FVFI_MMA3("d3", "al3", "ah3") "}"
-            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc) : "memory");
+        FVFI_KSTEP_BODY("tf32")
     }
 }
-
 __device__ __forceinline__ void tc_ld16(unsigned taddr, float* v) {
     unsigned r[16];
     asm volatile(
@@ -184,36 +210,71 @@ __device__ __forceinline__ int reflect101(int i, int n) {   // torch 'reflect': 
     return m < n ? m : period - m;
 }
 
-// ---- weight packing: OIHW fp32 -> [chunk][tap][hi|lo][kc(4)][n(Npad)][4] --------------------------------------
-__global__ void conv_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int KH,
+// ---- weight packing: OIHW fp32 -> header + [chunk][tap][hi|lo][kc(4)][n(Npad)][16 bytes] --------------------------
+// header[0] = output scale (exact inverse of the operand scales), [1] = weight scale, [2] = precision.
+__global__ void conv_weight_scale_kernel(const float* __restrict__ w, size_t count, float* __restrict__ hdr, int prec) {
+    __shared__ float red[32];
+    float m = 0.f;
+    for (size_t i = threadIdx.x; i < count; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+        float wscale = 1.f, oscale = 1.f;
+        if (prec == PREC_F16X3) {
+            int e = 0;                                  // 2^e: max|w| * 2^e in [2^14, 2^15)
+            if (m > 0.f && isfinite(m)) { int ex; frexpf(m, &ex); e = 15 - ex; }
+            e = max(-40, min(40, e));
+            wscale = ldexpf(1.f, e);
+            oscale = ldexpf(1.f, -e - CV_X_SHIFT);
+        }
+        hdr[0] = oscale;
+        hdr[1] = wscale;
+        hdr[2] = (float)prec;
+    }
+}
+
+template <int PREC>
+__global__ void conv_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ packed, int Cout, int Cin, int KH,
                                          int KW, int Npad, int nchunks) {
+    constexpr int CPK = cv_cpk(PREC);
     const int taps = KH * KW;
-    const size_t total = (size_t)nchunks * taps * 2 * 4 * Npad * 4;
+    const float wscale = packed[1];
+    float* out32 = packed + CV_HDR;
+    __half* out16 = (__half*)(packed + CV_HDR);
+    const size_t total = (size_t)nchunks * taps * 2 * CV_KCHUNKS * Npad * CPK;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
         size_t t = q;
-        const int e = (int)(t % 4); t /= 4;
+        const int e = (int)(t % CPK); t /= CPK;
         const int n = (int)(t % Npad); t /= Npad;
-        const int kc = (int)(t % 4); t /= 4;
+        const int kc = (int)(t % CV_KCHUNKS); t /= CV_KCHUNKS;
         const int lo = (int)(t % 2); t /= 2;
         const int tap = (int)(t % taps); t /= taps;
         const int chunk = (int)t;
-        const int c = chunk * CV_CHUNK + kc * 4 + e;
+        const int c = chunk * (CV_KCHUNKS * CPK) + kc * CPK + e;
         float v = 0.f;
         if (n < Cout && c < Cin) v = w[(((size_t)n * Cin + c) * KH + tap / KW) * KW + tap % KW];
-        unsigned hb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-        const float hi = __uint_as_float(hb);
-        out[q] = lo ? (v - hi) : hi;
+        if (PREC == PREC_F16X3) {
+            v *= wscale;
+            const __half hi = __float2half_rn(v);
+            out16[q] = lo ? __float2half_rn(v - __half2float(hi)) : hi;
+        } else {
+            unsigned hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+            const float hi = __uint_as_float(hb);
+            out32[q] = lo ? (v - hi) : hi;
+        }
     }
 }
 
 // ---- the convolution ---------------------------------------------------------------------------------
-template <int ACT>
-__global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvArgs A) {
+template <int ACT, int PREC>
+__global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [A stages: hi, lo] [B stages] [barriers] [tmem ptr]
     unsigned char* a_base = smem_raw;
-    unsigned char* b_base = a_base + (size_t)CV_ASTAGES * A.a_stage_bytes;
+    unsigned char* b_base = a_base + (size_t)A.astages * A.a_stage_bytes;
     unsigned long long* bars = (unsigned long long*)(b_base + (size_t)A.bstages * A.b_stage_bytes);
     unsigned long long* a_full = bars;                       // [2]  count 128
     unsigned long long* a_empty = bars + 2;                  // [2]  count 1 (tcgen05.commit)
@@ -230,7 +291,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
     const unsigned a_half = A.a_stage_bytes / 2;             // hi | lo halves of an A stage
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < CV_ASTAGES; ++s) { mbar_init(&a_full[s], CV_LOADERS); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < CV_MAX_ASTAGES; ++s) { mbar_init(&a_full[s], CV_LOADERS); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < A.bstages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -264,32 +325,45 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
         }
         for (int n = threadIdx.x; n < A.Npad; n += CV_LOADERS) bias_s[n] = (A.bias && n < A.Cout) ? __ldg(A.bias + n) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(CV_LOADERS) : "memory");
-        const int total = A.NPIX * 4;
-        constexpr int U = 5;                                       // loads in flight per thread
+        constexpr int CPK = cv_cpk(PREC);
+        constexpr int CHUNK = cv_chunk(PREC);
+        constexpr int U = (PREC == PREC_F16X3) ? 3 : 5;            // loads in flight per thread
+        const float xs = (float)(1 << CV_X_SHIFT);
+        float amax = 0.f;
         for (int c = 0; c < A.nchunks; ++c) {
-            const int s = c % CV_ASTAGES;
-            if (c >= CV_ASTAGES) mbar_wait(&a_empty[s], ((c / CV_ASTAGES) - 1) & 1);
+            const int s = c % A.astages;
+            if (c >= A.astages) mbar_wait(&a_empty[s], ((c / A.astages) - 1) & 1);
             float4* hi = (float4*)(a_base + (size_t)s * A.a_stage_bytes);
             float4* lo = (float4*)(a_base + (size_t)s * A.a_stage_bytes + a_half);
-            const int cbase = c * CV_CHUNK;
+            const int cbase = c * CHUNK;
+            // the last chunk may need only the first MMA K step: K chunks 0,1 are stored first, so just stop early
+            const int ksh = (c == A.nchunks - 1 && A.last_ksteps == 1) ? 1 : 2;   // log2(K chunks to fill)
+            const int kmask = (1 << ksh) - 1;
+            const int total = A.NPIX << ksh;
             for (int q0 = threadIdx.x; q0 < total; q0 += CV_LOADERS * U) {
-                float4 v[U];
+                float v[U][CPK];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int q = q0 + u * CV_LOADERS;
-                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int e = 0; e < CPK; ++e) v[u][e] = 0.f;
                     if (q < total) {
-                        const int pix = q >> 2, ch = cbase + (q & 3) * 4;   // 4 consecutive threads read one pixel's 64 B
+                        const int pix = q >> ksh, ch = cbase + (q & kmask) * CPK;   // consecutive threads read one pixel's chunk
                         const int off = pixoff[pix];
                         if (off >= 0 && ch < A.Cin) {
                             const float* p = X + (size_t)off * A.ldx + ch;
                             if (vec) {
-                                v[u] = __ldg((const float4*)p);
+#pragma unroll
+                                for (int e = 0; e < CPK; e += 4) {
+                                    if (ch + e < A.Cin) {
+                                        const float4 t = __ldg((const float4*)(p + e));
+                                        v[u][e] = t.x; v[u][e + 1] = t.y; v[u][e + 2] = t.z; v[u][e + 3] = t.w;
+                                    }
+                                }
                             } else {
-                                v[u].x = __ldg(p);
-                                if (ch + 1 < A.Cin) v[u].y = __ldg(p + 1);
-                                if (ch + 2 < A.Cin) v[u].z = __ldg(p + 2);
-                                if (ch + 3 < A.Cin) v[u].w = __ldg(p + 3);
+#pragma unroll
+                                for (int e = 0; e < CPK; ++e)
+                                    if (ch + e < A.Cin) v[u][e] = __ldg(p + e);
                             }
                         }
                     }
@@ -298,17 +372,34 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
                 for (int u = 0; u < U; ++u) {
                     const int q = q0 + u * CV_LOADERS;
                     if (q < total) {
-                        float4 h;
-                        h.x = to_tf32_rna(v[u].x); h.y = to_tf32_rna(v[u].y); h.z = to_tf32_rna(v[u].z); h.w = to_tf32_rna(v[u].w);
-                        const int o = (q & 3) * A.NPIX + (q >> 2);
-                        hi[o] = h;
-                        lo[o] = make_float4(v[u].x - h.x, v[u].y - h.y, v[u].z - h.z, v[u].w - h.w);
+                        const int o = (q & kmask) * A.NPIX + (q >> ksh);
+                        if (PREC == PREC_F16X3) {
+                            unsigned hw[4], lw[4];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                const float x0 = v[u][e] * xs, x1 = v[u][e + 1] * xs;
+                                amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+                                const __half2 h = __floats2half2_rn(x0, x1);
+                                const float2 hf = __half22float2(h);
+                                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                                hw[e >> 1] = *(const unsigned*)&h;
+                                lw[e >> 1] = *(const unsigned*)&l;
+                            }
+                            hi[o] = make_float4(__uint_as_float(hw[0]), __uint_as_float(hw[1]), __uint_as_float(hw[2]), __uint_as_float(hw[3]));
+                            lo[o] = make_float4(__uint_as_float(lw[0]), __uint_as_float(lw[1]), __uint_as_float(lw[2]), __uint_as_float(lw[3]));
+                        } else {
+                            float4 h;
+                            h.x = to_tf32_rna(v[u][0]); h.y = to_tf32_rna(v[u][1]); h.z = to_tf32_rna(v[u][2]); h.w = to_tf32_rna(v[u][3]);
+                            hi[o] = h;
+                            lo[o] = make_float4(v[u][0] - h.x, v[u][1] - h.y, v[u][2] - h.z, v[u][3] - h.w);
+                        }
                     }
                 }
             }
             fence_async_smem();          // generic-proxy stores -> visible to the tensor-core (async) proxy
             mbar_arrive(&a_full[s]);
         }
+        if (PREC == PREC_F16X3 && !(amax <= 65504.f) && A.overflow) atomicOr(A.overflow, 1);
         // ================= epilogue =================
         mbar_wait(acc_full, 0);
         tc_fence_after();
@@ -316,6 +407,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
         const int orow = y0 + (m >> 3);
         const bool vec_out = (A.Cout & 3) == 0 && (A.ldy & 3) == 0 && ((((size_t)A.y) & 15) == 0);
         const size_t plane = (size_t)A.H * A.W;
+        const float oscale = __ldg(A.hdr);                       // exact power of two (1 for PREC_TF32X3)
         for (int t = 0; t < A.MT; ++t) {
             const int ocol = x0 + t * 8 + (m & 7);
             const bool inb = (orow < A.H && ocol < A.W);
@@ -331,7 +423,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (n0 + i < A.Cout) {
-                            const float z = v[i] + bias_s[n0 + i];
+                            const float z = fmaf(v[i], oscale, bias_s[n0 + i]);
                             if (z > smax) { ssum = ssum * expf(smax - z); smax = z; }
                             ssum += expf(z - smax);
                         }
@@ -346,15 +438,15 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
                 for (int i = 0; i < 16; i += 4) {
                     const float4 b4 = *(const float4*)(bias_s + n0 + i);        // smem broadcast
                     if (ACT == ACT_SOFTMAX) {
-                        v[i] = expf(v[i] + b4.x - smax) * sinv;
-                        v[i + 1] = expf(v[i + 1] + b4.y - smax) * sinv;
-                        v[i + 2] = expf(v[i + 2] + b4.z - smax) * sinv;
-                        v[i + 3] = expf(v[i + 3] + b4.w - smax) * sinv;
+                        v[i] = expf(fmaf(v[i], oscale, b4.x) - smax) * sinv;
+                        v[i + 1] = expf(fmaf(v[i + 1], oscale, b4.y) - smax) * sinv;
+                        v[i + 2] = expf(fmaf(v[i + 2], oscale, b4.z) - smax) * sinv;
+                        v[i + 3] = expf(fmaf(v[i + 3], oscale, b4.w) - smax) * sinv;
                     } else {
-                        v[i] = apply_act<ACT>(v[i] + b4.x);
-                        v[i + 1] = apply_act<ACT>(v[i + 1] + b4.y);
-                        v[i + 2] = apply_act<ACT>(v[i + 2] + b4.z);
-                        v[i + 3] = apply_act<ACT>(v[i + 3] + b4.w);
+                        v[i] = apply_act<ACT>(fmaf(v[i], oscale, b4.x));
+                        v[i + 1] = apply_act<ACT>(fmaf(v[i + 1], oscale, b4.y));
+                        v[i + 2] = apply_act<ACT>(fmaf(v[i + 2], oscale, b4.z));
+                        v[i + 3] = apply_act<ACT>(fmaf(v[i + 3], oscale, b4.w));
                     }
                 }
                 if (A.out_nchw) {
@@ -389,8 +481,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
     } else {
         // ================= MMA issuer: whole warp runs the (uniform) loops, one elected lane issues =================
         {
-            // instruction descriptor: D=F32, A=B=TF32, K-major both, N = Npad, M = 128
-            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(A.Npad >> 3) << 17) | ((128u >> 4) << 24);
+            // instruction descriptor: D=F32, A=B=TF32 (format 2) or F16 (format 0), K-major both, N = Npad, M = 128
+            const unsigned fmt = (PREC == PREC_F16X3) ? 0u : 2u;
+            const unsigned idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(A.Npad >> 3) << 17) | ((128u >> 4) << 24);
             const unsigned a_lbo = (unsigned)A.NPIX * 16u, a_sbo = (unsigned)A.RW * 16u;
             const unsigned b_lbo = (unsigned)A.Npad * 16u, b_sbo = 128u;
             const unsigned b_half = A.b_stage_bytes / 2;
@@ -400,11 +493,12 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
             const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
             int it = 0;
             for (int c = 0; c < A.nchunks; ++c) {
-                const int sa = c % CV_ASTAGES;
-                mbar_wait(&a_full[sa], (c / CV_ASTAGES) & 1);
+                const int sa = c % A.astages;
+                mbar_wait(&a_full[sa], (c / A.astages) & 1);
                 const unsigned a_st = smem_u32(a_base + (size_t)sa * A.a_stage_bytes) >> 4;
                 const unsigned long long a_hi0 = a_desc0 + a_st, a_lo0 = a_hi0 + (a_half >> 4);
                 int dy = 0, dx = 0;
+                const bool two = (c < A.nchunks - 1) || A.last_ksteps == 2;   // warp-uniform
                 for (int tp = 0; tp < taps; ++tp, ++it) {
                     const int sb = it % A.bstages;
                     mbar_wait(&b_full[sb], (it / A.bstages) & 1);
@@ -417,14 +511,14 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
                     const unsigned long long dah = a_hi0 + tap_off, dal = a_lo0 + tap_off;
                     const unsigned np = (unsigned)A.Npad;
                     if (A.MT == 4) {
-                        tc_mma_kstep<4>(tmem_u, np, dal, dah, dbh0, dbl0, idesc, acc_first);
-                        tc_mma_kstep<4>(tmem_u, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
+                        tc_mma_kstep<4, PREC>(tmem_u, np, dal, dah, dbh0, dbl0, idesc, acc_first);
+                        if (two) tc_mma_kstep<4, PREC>(tmem_u, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
                     } else if (A.MT == 2) {
-                        tc_mma_kstep<2>(tmem_u, np, dal, dah, dbh0, dbl0, idesc, acc_first);
-                        tc_mma_kstep<2>(tmem_u, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
+                        tc_mma_kstep<2, PREC>(tmem_u, np, dal, dah, dbh0, dbl0, idesc, acc_first);
+                        if (two) tc_mma_kstep<2, PREC>(tmem_u, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
                     } else {
-                        tc_mma_kstep<1>(tmem_u, np, dal, dah, dbh0, dbl0, idesc, acc_first);
-                        tc_mma_kstep<1>(tmem_u, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
+                        tc_mma_kstep<1, PREC>(tmem_u, np, dal, dah, dbh0, dbl0, idesc, acc_first);
+                        if (two) tc_mma_kstep<1, PREC>(tmem_u, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
                     }
                     tc_commit(&b_empty[sb]);           // weights of this (chunk, tap) consumed
                     if (++dx == A.KW) { dx = 0; ++dy; }
@@ -443,59 +537,112 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tf32x3_kernel(const ConvAr
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-static int conv_geometry(ConvArgs& a, size_t* smem_bytes) {
+static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
+    const int chunk = cv_chunk(prec);
     a.Npad = (a.Cout + 15) & ~15;
     FVFI_CHECK_ARG(a.Npad >= 16 && a.Npad <= 256, "conv: Cout %d not supported (1..256 per launch)", a.Cout);
-    a.nchunks = (a.Cin + CV_CHUNK - 1) / CV_CHUNK;
-    a.b_stage_bytes = (unsigned)a.Npad * CV_CHUNK * 4u * 2u;           // hi + lo
-    const size_t budget = 220 * 1024;
-    for (int mt = 4; mt >= 1; mt >>= 1) {
-        if (mt * a.Npad > 512) continue;
-        if (mt > 1 && 8 * (mt / 2) >= a.W) continue;                   // do not over-tile narrow images
-        a.MT = mt;
-        a.RW = 8 * mt + a.KW - 1;
-        a.RH = CV_ROWS + a.KH - 1;
-        a.NPIX = a.RW * a.RH;
-        a.a_stage_bytes = (unsigned)a.NPIX * CV_CHUNK * 4u * 2u;       // hi + lo
-        const size_t fixed = (size_t)CV_ASTAGES * a.a_stage_bytes + 256 + (size_t)a.NPIX * 4 + 1024 + 16;
-        if (fixed + 2 * (size_t)a.b_stage_bytes > budget) continue;
-        int bs = (int)((budget - fixed) / a.b_stage_bytes);
-        a.bstages = bs > CV_MAX_BSTAGES ? CV_MAX_BSTAGES : bs;
-        int cols = 32;
-        while (cols < mt * a.Npad) cols <<= 1;
-        a.tmem_cols = cols;
-        *smem_bytes = fixed + (size_t)a.bstages * a.b_stage_bytes;
-        return FVFI_OK;
+    a.nchunks = (a.Cin + chunk - 1) / chunk;
+    a.last_ksteps = (a.Cin - (a.nchunks - 1) * chunk) > chunk / 2 ? 2 : 1;
+    a.b_stage_bytes = (unsigned)a.Npad * CV_KCHUNKS * 16u * 2u;        // hi + lo
+    // Shallow layers (few K stages per tile) cannot hide their prologue / first load / epilogue behind their own main
+    // loop: give them half the shared memory so that two CTAs share an SM and overlap each other.
+    a.astages = a.nchunks > 1 ? CV_MAX_ASTAGES : 1;
+    const int taps = a.KH * a.KW;
+    const bool shallow = a.nchunks * taps <= 64;
+    for (int pass = shallow ? 0 : 1; pass < 2; ++pass) {
+        const size_t budget = (pass == 0 ? 110 : 220) * 1024;
+        for (int mt = 4; mt >= 1; mt >>= 1) {
+            if (mt * a.Npad > (pass == 0 ? 256 : 512)) continue;           // TMEM columns are shared by the resident CTAs
+            if (mt > 1 && 8 * (mt / 2) >= a.W) continue;                   // do not over-tile narrow images
+            a.MT = mt;
+            a.RW = 8 * mt + a.KW - 1;
+            a.RH = CV_ROWS + a.KH - 1;
+            a.NPIX = a.RW * a.RH;
+            a.a_stage_bytes = (unsigned)a.NPIX * CV_KCHUNKS * 16u * 2u;    // hi + lo
+            const size_t fixed = (size_t)a.astages * a.a_stage_bytes + 256 + (size_t)a.NPIX * 4 + 1024 + 16;
+            const int min_b = std::min(2, a.nchunks * taps);
+            if (fixed + (size_t)min_b * a.b_stage_bytes > budget) continue;
+            int bs = (int)((budget - fixed) / a.b_stage_bytes);
+            a.bstages = bs > CV_MAX_BSTAGES ? CV_MAX_BSTAGES : bs;
+            int cols = 32;
+            while (cols < mt * a.Npad) cols <<= 1;
+            a.tmem_cols = cols;
+            *smem_bytes = fixed + (size_t)a.bstages * a.b_stage_bytes;
+            return FVFI_OK;
+        }
     }
     set_error("conv: no tile configuration fits (Cout %d, kernel %dx%d)", a.Cout, a.KH, a.KW);
     return FVFI_EINVAL;
+}
+
+static int* overflow_flag() {      // one device word per device, zero-initialised
+    static int* flags[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!flags[dev]) {
+        int* p = nullptr;
+        if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, sizeof(int));
+        flags[dev] = p;
+    }
+    return flags[dev];
+}
+
+template <int PREC>
+static void (*pick_kernel(int activation))(const ConvArgs) {
+    switch (activation) {
+        case ACT_RELU: return conv_split_kernel<ACT_RELU, PREC>;
+        case ACT_ELU: return conv_split_kernel<ACT_ELU, PREC>;
+        case ACT_TANH: return conv_split_kernel<ACT_TANH, PREC>;
+        case ACT_SIGMOID: return conv_split_kernel<ACT_SIGMOID, PREC>;
+        case ACT_SOFTMAX: return conv_split_kernel<ACT_SOFTMAX, PREC>;
+        default: return conv_split_kernel<ACT_NONE, PREC>;
+    }
 }
 
 }  // namespace fvfi
 
 using namespace fvfi;
 
-extern "C" size_t fvfi_conv2d_packed_weight_floats(int Cout, int Cin, int KH, int KW) {
+extern "C" size_t fvfi_conv2d_packed_weight_floats(int Cout, int Cin, int KH, int KW, int precision) {
     const int Npad = (Cout + 15) & ~15;
-    const int nchunks = (Cin + CV_CHUNK - 1) / CV_CHUNK;
-    return (size_t)nchunks * KH * KW * 2 * 4 * Npad * 4;
+    const int chunk = cv_chunk(precision);
+    const int nchunks = (Cin + chunk - 1) / chunk;
+    return (size_t)CV_HDR + (size_t)nchunks * KH * KW * 2 * CV_KCHUNKS * Npad * 4;   // 16 bytes per (K chunk, n)
 }
 
 extern "C" int fvfi_conv2d_pack_weights(const float* weight_oihw, float* packed, int Cout, int Cin, int KH, int KW,
-                                        void* stream) {
+                                        int precision, void* stream) {
     FVFI_CHECK_ARG(weight_oihw && packed && Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "conv_pack_weights: bad argument");
+    FVFI_CHECK_ARG(precision == PREC_TF32X3 || precision == PREC_F16X3, "conv_pack_weights: precision must be 0 (3xTF32) or 1 (3xFP16)");
     const int Npad = (Cout + 15) & ~15;
-    const int nchunks = (Cin + CV_CHUNK - 1) / CV_CHUNK;
-    const size_t total = fvfi_conv2d_packed_weight_floats(Cout, Cin, KH, KW);
+    const int chunk = cv_chunk(precision);
+    const int nchunks = (Cin + chunk - 1) / chunk;
+    const size_t total = (size_t)nchunks * KH * KW * 2 * CV_KCHUNKS * Npad * cv_cpk(precision);
     const unsigned blocks = (unsigned)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
-    conv_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(weight_oihw, packed, Cout, Cin, KH, KW, Npad, nchunks);
+    cudaStream_t s = (cudaStream_t)stream;
+    conv_weight_scale_kernel<<<1, 1024, 0, s>>>(weight_oihw, (size_t)Cout * Cin * KH * KW, packed, precision);
+    FVFI_LAUNCH_CHECK();
+    if (precision == PREC_F16X3)
+        conv_pack_weights_kernel<PREC_F16X3><<<blocks, 256, 0, s>>>(weight_oihw, packed, Cout, Cin, KH, KW, Npad, nchunks);
+    else
+        conv_pack_weights_kernel<PREC_TF32X3><<<blocks, 256, 0, s>>>(weight_oihw, packed, Cout, Cin, KH, KW, Npad, nchunks);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }
 
+extern "C" int fvfi_conv2d_overflow_count(void) {
+    int* f = overflow_flag();
+    if (!f) return -1;
+    int v = 0;
+    if (cudaMemcpy(&v, f, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (v) cudaMemset(f, 0, sizeof(int));
+    return v;
+}
+
 extern "C" int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias, float* y,
                                 int y_pixel_stride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad_mode,
-                                int activation, int out_nchw, void* stream) {
+                                int activation, int out_nchw, int precision, void* stream) {
     FVFI_CHECK_ARG(x && packed_weight && y, "conv2d: null pointer");
     FVFI_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && B <= 65535, "conv2d: bad dimension");
     FVFI_CHECK_ARG((KH == 1 || KH == 3 || KH == 5) && KW == KH, "conv2d: kernel must be 1x1, 3x3 or 5x5");
@@ -503,22 +650,17 @@ extern "C" int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float*
     FVFI_CHECK_ARG(pad_mode != PAD_REFLECT || (H > KH / 2 && W > KW / 2), "conv2d: reflect padding needs H,W > pad");
     FVFI_CHECK_ARG(activation >= 0 && activation <= 5, "conv2d: bad activation");
     FVFI_CHECK_ARG(activation != ACT_SOFTMAX || Cout <= 256, "conv2d: softmax needs all channels in one call");
+    FVFI_CHECK_ARG(precision == PREC_TF32X3 || precision == PREC_F16X3, "conv2d: precision must be 0 (3xTF32) or 1 (3xFP16)");
     ConvArgs a{};
-    a.x = x; a.wpack = packed_weight; a.bias = bias; a.y = y; a.ldx = x_pixel_stride; a.ldy = y_pixel_stride; a.out_nchw = out_nchw ? 1 : 0;
+    a.x = x; a.hdr = packed_weight; a.wpack = packed_weight + CV_HDR; a.bias = bias; a.y = y;
+    a.ldx = x_pixel_stride; a.ldy = y_pixel_stride; a.out_nchw = out_nchw ? 1 : 0;
+    a.overflow = (precision == PREC_F16X3) ? overflow_flag() : nullptr;
     FVFI_CHECK_ARG(x_pixel_stride >= Cin && (out_nchw || y_pixel_stride >= Cout), "conv2d: pixel stride smaller than channel count");
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.KH = KH; a.KW = KW; a.pad_mode = pad_mode; a.act = activation;
     size_t smem = 0;
-    if (int rc = conv_geometry(a, &smem)) return rc;
+    if (int rc = conv_geometry(a, precision, &smem)) return rc;
     dim3 grid(ceil_div(W, 8 * a.MT), ceil_div(H, CV_ROWS), B);
-    void (*kern)(const ConvArgs) = nullptr;
-    switch (activation) {
-        case ACT_RELU: kern = conv_tf32x3_kernel<ACT_RELU>; break;
-        case ACT_ELU: kern = conv_tf32x3_kernel<ACT_ELU>; break;
-        case ACT_TANH: kern = conv_tf32x3_kernel<ACT_TANH>; break;
-        case ACT_SIGMOID: kern = conv_tf32x3_kernel<ACT_SIGMOID>; break;
-        case ACT_SOFTMAX: kern = conv_tf32x3_kernel<ACT_SOFTMAX>; break;
-        default: kern = conv_tf32x3_kernel<ACT_NONE>; break;
-    }
+    void (*kern)(const ConvArgs) = (precision == PREC_F16X3) ? pick_kernel<PREC_F16X3>(activation) : pick_kernel<PREC_TF32X3>(activation);
     FVFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, CV_THREADS, smem, (cudaStream_t)stream>>>(a);
     FVFI_LAUNCH_CHECK();

@@ -9,7 +9,18 @@ import torch
 
 from . import _lib
 
+import os
+
 enabled = True   # use the tcgen05 kernels for inference convolutions (False -> torch/cuDNN scaffolding)
+PRECISIONS = {"tf32x3": 0, "f16x3": 1}
+precision = PRECISIONS[os.environ.get("FVFI_CONV_PREC", "f16x3")]   # operand split (include/fvfi.h: FVFI_CONV_*)
+
+
+def check_overflow():
+    """Raise if a convolution since the last check saw an activation outside the 3xFP16 range (|x| > 4094).
+    Synchronises; call it where the caller synchronises anyway (end of an inference call)."""
+    if precision == PRECISIONS["f16x3"] and _lib.lib().fvfi_conv2d_overflow_count() > 0:
+        raise FloatingPointError("fvfi.conv: activation beyond the 3xFP16 range (|x| > 4094); set FVFI_CONV_PREC=tf32x3")
 
 
 def use_tc(x):
@@ -23,7 +34,7 @@ _pack_cache = {}
 
 
 def _packed(weight):
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device))
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device), precision)
     hit = _pack_cache.get(id(weight))
     if hit is not None and hit[0] == key:
         return hit[1]
@@ -33,10 +44,11 @@ def _packed(weight):
     w = weight.detach().contiguous().float()
     for o in range(0, Cout, 256):
         wo = w[o:o + 256].contiguous()
-        n = L.fvfi_conv2d_packed_weight_floats(wo.shape[0], Cin, KH, KW)
+        n = L.fvfi_conv2d_packed_weight_floats(wo.shape[0], Cin, KH, KW, precision)
         buf = torch.empty(n, dtype=torch.float32, device=weight.device)
         with torch.cuda.device(weight.device):
-            _lib.check(L.fvfi_conv2d_pack_weights(wo.data_ptr(), buf.data_ptr(), wo.shape[0], Cin, KH, KW, _lib.stream_ptr()))
+            _lib.check(L.fvfi_conv2d_pack_weights(wo.data_ptr(), buf.data_ptr(), wo.shape[0], Cin, KH, KW, precision,
+                                                  _lib.stream_ptr()))
         parts.append((o, wo.shape[0], buf, wo))
     _pack_cache[id(weight)] = (key, parts)
     return parts
@@ -72,7 +84,7 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
         for (o, n, buf, _) in _packed(weight):
             _lib.check(L.fvfi_conv2d_nhwc(xc.data_ptr(), ldx, buf.data_ptr(), None if b is None else b.data_ptr() + 4 * o,
                                           out.data_ptr() + 4 * o, ldy, B, H, W, Cin, n, KH, KW, pad_mode, ACT[act],
-                                          1 if nchw_out else 0, _lib.stream_ptr()))
+                                          1 if nchw_out else 0, precision, _lib.stream_ptr()))
     return out
 
 

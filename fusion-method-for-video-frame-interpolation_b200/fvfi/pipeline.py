@@ -14,6 +14,7 @@ import types
 
 import torch
 
+from . import conv as tc
 from . import filters, transform, utils
 from .adacofnet import AdaCoFNet
 from .fusion_net import FusionNet
@@ -135,4 +136,5 @@ class FusionPipeline(torch.nn.Module):
             out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
         out_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        tc.check_overflow()     # 3xFP16 convolutions report out-of-range activations instead of saturating silently
         return out_host

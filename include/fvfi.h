@@ -35,6 +35,9 @@ enum {
     FVFI_ENOMEM = 3
 };
 
+/* operand split of fvfi_conv2d_* */
+enum { FVFI_CONV_TF32X3 = 0, FVFI_CONV_F16X3 = 1 };
+
 /* gradInput modes of fvfi_adacof_backward */
 enum {
     FVFI_GIN_NONE = 0,  /* gin pointer ignored */
@@ -101,7 +104,10 @@ int fvfi_gaussian_filter(const float* in, float* out, float* tmp, int N, int H, 
 int fvfi_median_filter(const float* in, float* out, int N, int H, int W, int size, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * Convolution on the tcgen05 tensor cores (3xTF32 error-compensated, fp32 in/out), NHWC activations.
+ * Convolution on the tcgen05 tensor cores (split-operand error-compensated, fp32 in/out), NHWC activations.
+ * precision: FVFI_CONV_F16X3 (default of the Python mirror: three kind::f16 products of fp16 hi/lo halves, 22 mantissa
+ * bits, twice the TF32 rate) or FVFI_CONV_TF32X3 (three kind::tf32 products, no range limit).  Packed weights are
+ * specific to the precision they were packed for.
  * Replaces torch.nn.Conv2d -> cuDNN for the stride-1 "same" convolutions of PhaseNetBlock
  * (src/phase_net/phase_net.py:190-199), KernelEstimation (src/fusion_net/fusion_adacofnet.py:19-83) and
  * FusionNet (src/fusion_net/fusion_net.py:24-36).
@@ -110,11 +116,16 @@ int fvfi_median_filter(const float* in, float* out, int N, int H, int W, int siz
  *   KH == KW in {1,3,5}; pad_mode 0 = zeros, 1 = reflect (torch 'reflect'); activation 0 none, 1 ReLU, 2 ELU,
  *   3 tanh, 4 sigmoid, 5 softmax over the Cout channels; bias [Cout] or NULL.
  *   out_nchw != 0: y is planar [B,Cout,H,W] (the layout the AdaCoF warp streams its coefficient maps in). */
-size_t fvfi_conv2d_packed_weight_floats(int Cout, int Cin, int KH, int KW);
-int fvfi_conv2d_pack_weights(const float* weight_oihw, float* packed, int Cout, int Cin, int KH, int KW, void* stream);
+size_t fvfi_conv2d_packed_weight_floats(int Cout, int Cin, int KH, int KW, int precision);
+int fvfi_conv2d_pack_weights(const float* weight_oihw, float* packed, int Cout, int Cin, int KH, int KW, int precision,
+                             void* stream);
 int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias, float* y,
                      int y_pixel_stride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad_mode,
-                     int activation, int out_nchw, void* stream);
+                     int activation, int out_nchw, int precision, void* stream);
+/* FVFI_CONV_F16X3 scales activations by 2^4 before the fp16 split; |x| > 4094 would leave fp16's range.  Returns 1
+ * (and clears the flag) if any convolution since the last call saw such a value, 0 if not, -1 on error.
+ * Synchronises the device. */
+int fvfi_conv2d_overflow_count(void);
 
 /* Bilinear resize of NHWC tensors (torch.nn.Upsample / F.interpolate 'bilinear' semantics, both align_corners
  * modes; src/fusion_net/fusion_adacofnet.py:31, src/fusion_net/fusion_net.py:41, src/phase_net/phase_net.py:138-139).

@@ -1,4 +1,4 @@
-"""GPU parity of the tcgen05 3xTF32 convolution against torch's fp32 convolution (TF32 off)."""
+"""GPU parity of the tcgen05 split-operand convolution (3xFP16 default, 3xTF32) against an fp64 convolution."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -21,8 +21,15 @@ CASES = [
 ]
 
 
+@pytest.fixture(params=["f16x3", "tf32x3"])
+def prec(request, monkeypatch):
+    from fvfi import conv
+    monkeypatch.setattr(conv, "precision", conv.PRECISIONS[request.param])
+    return request.param
+
+
 @pytest.mark.parametrize("B,Cin,Cout,K,H,W,mode,act", CASES)
-def test_conv_matches_fp32(B, Cin, Cout, K, H, W, mode, act):
+def test_conv_matches_fp32(B, Cin, Cout, K, H, W, mode, act, prec):
     from fvfi import conv
     torch.backends.cudnn.allow_tf32 = False
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -40,6 +47,27 @@ def test_conv_matches_fp32(B, Cin, Cout, K, H, W, mode, act):
     assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
     print('max abs err %.2e (max |ref| %.2f)' % (err, float(ref.abs().max())))
     assert err <= 2e-5 * max(1.0, float(ref.abs().max())), err
+    conv.check_overflow()
+
+
+def test_conv_f16x3_range_and_small_values(monkeypatch):
+    """3xFP16 keeps fp32-grade accuracy for small activations / weights (power-of-two scaling keeps both halves in
+    fp16's normal range) and reports -- instead of hiding -- activations beyond its range."""
+    from fvfi import conv
+    monkeypatch.setattr(conv, "precision", conv.PRECISIONS["f16x3"])
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for xs, ws in ((1e-3, 1.0), (1.0, 1e-4), (100.0, 30.0), (3e-4, 2e-3)):
+        x = xs * torch.randn((1, 48, 24, 40), device="cuda", generator=g)
+        w = ws * torch.randn((40, 48, 3, 3), device="cuda", generator=g) / 20
+        y = conv.conv2d(x, w, None, "zeros", None)
+        ref = F.conv2d(x.double(), w.double(), padding=1)
+        assert float((y.double() - ref).abs().max()) <= 3e-6 * float(ref.abs().max()) + 1e-9, (xs, ws)
+    conv.check_overflow()
+    x = torch.full((1, 16, 16, 16), 5000.0, device="cuda")
+    conv.conv2d(x, torch.ones((16, 16, 1, 1), device="cuda"), None, "zeros", None)
+    with pytest.raises(FloatingPointError):
+        conv.check_overflow()
+    conv.check_overflow()   # the flag is cleared by the read
 
 
 @pytest.mark.parametrize("align", [True, False])
@@ -59,7 +87,7 @@ def test_resize_bilinear_nhwc_matches_torch(align):
     assert float(buf[:, :8].abs().max()) == 0.0 and float(buf[:, 72:].abs().max()) == 0.0
 
 
-def test_conv_softmax_and_nchw_epilogues():
+def test_conv_softmax_and_nchw_epilogues(prec):
     from fvfi import conv
     g = torch.Generator(device="cuda").manual_seed(2)
     x = torch.randn((2, 25, 40, 72), device="cuda", generator=g)

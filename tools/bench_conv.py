@@ -45,6 +45,9 @@ for name, ci, co, k, h, w, mode in LAYERS:
     wt = torch.randn((co, ci, k, k), device="cuda") / (ci * k * k) ** 0.5
     bias = torch.randn((co,), device="cuda")
     flops = 2.0 * b * h * w * ci * co * k * k
+    conv.precision = conv.PRECISIONS["tf32x3"]
+    t_t3 = timeit(lambda: conv.conv2d(x, wt, bias, mode, "relu"))
+    conv.precision = conv.PRECISIONS["f16x3"]
     t_tc = timeit(lambda: conv.conv2d(x, wt, bias, mode, "relu"))
     p = k // 2
     def cudnn():
@@ -54,5 +57,5 @@ for name, ci, co, k, h, w, mode in LAYERS:
     t_f32 = timeit(cudnn)
     torch.backends.cudnn.allow_tf32 = True
     t_tf32 = timeit(cudnn)
-    print("%-26s B=%d  tcgen05-3xTF32 %7.3f ms %6.1f TF/s | cuDNN fp32 %7.3f ms %6.1f | cuDNN tf32 %7.3f ms %6.1f" %
-          (name, b, t_tc, flops / t_tc / 1e9, t_f32, flops / t_f32 / 1e9, t_tf32, flops / t_tf32 / 1e9))
+    print("%-26s B=%d  tcgen05 3xFP16 %7.3f ms %6.1f TF/s | 3xTF32 %7.3f ms %6.1f | cuDNN fp32 %7.3f ms %6.1f | cuDNN tf32 %7.3f ms %6.1f" %
+          (name, b, t_tc, flops / t_tc / 1e9, t_t3, flops / t_t3 / 1e9, t_f32, flops / t_f32 / 1e9, t_tf32, flops / t_tf32 / 1e9))
