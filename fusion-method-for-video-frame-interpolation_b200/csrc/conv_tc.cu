@@ -38,9 +38,10 @@ constexpr int CV_KCHUNKS = 4;           // 16-byte K chunks per stage = two MMA 
 constexpr int CV_HDR = 32;              // floats of header in front of the packed weights (scales, precision)
 constexpr int CV_X_SHIFT = 4;           // PREC_F16X3: activations are scaled by 2^4 before the fp16 split
 constexpr int CV_ROWS = 16;             // output rows per CTA
-constexpr int CV_LOADERS = 128;         // warps 0-3
-constexpr int CV_THREADS = 192;
-constexpr int CV_MAX_ASTAGES = 2;
+constexpr int CV_LOADER_WARPS = 8;      // warps 0-7: activation loaders + epilogue (two warps per TMEM lane quarter)
+constexpr int CV_LOADERS = 32 * CV_LOADER_WARPS;
+constexpr int CV_THREADS = CV_LOADERS + 64;   // + weight producer warp + MMA warp
+constexpr int CV_MAX_ASTAGES = 4;
 constexpr int CV_MAX_BSTAGES = 4;
 constexpr unsigned CV_SPIN_LIMIT = 200u * 1000u * 1000u;   // bounded waits: trap instead of hanging the GPU
 
@@ -62,6 +63,8 @@ struct ConvArgs {
     int out_nchw;          // 1: y is planar [B,Cout,H,W] (coefficient maps for the warp kernel)
     int MT, RW, RH, NPIX;  // tiles per CTA, staged region geometry
     int nchunks, last_ksteps, astages, bstages, tmem_cols;
+    int nacc;              // TMEM accumulator buffers (2 when they fit: epilogue of tile j-1 overlaps the MMAs of tile j)
+    int tiles_x, tiles_y, ntiles;
     unsigned a_stage_bytes, b_stage_bytes;
 };
 
@@ -269,34 +272,49 @@ __global__ void conv_pack_weights_kernel(const float* __restrict__ w, float* __r
 }
 
 // ---- the convolution ---------------------------------------------------------------------------------
+// Persistent, warp-specialised: one CTA per SM walks the output tiles (tile = blockIdx.x + j * gridDim.x).  The A / B
+// shared-memory rings and the (double-buffered) TMEM accumulator keep running across tile boundaries, so the loaders
+// fetch tile j+1 while the tensor core works on tile j and the epilogue drains tile j-1.
+struct TileCoord { int img, y0, x0; };
+__device__ __forceinline__ TileCoord tile_coord(const ConvArgs& A, int tile) {
+    TileCoord t;
+    const int bx = tile % A.tiles_x, r = tile / A.tiles_x;
+    t.x0 = bx * 8 * A.MT;
+    t.y0 = (r % A.tiles_y) * CV_ROWS;
+    t.img = r / A.tiles_y;
+    return t;
+}
+
 template <int ACT, int PREC>
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [A stages: hi, lo] [B stages] [barriers] [tmem ptr]
+    // layout: [A stages: hi, lo] [B stages] [barriers] [tmem ptr] [pixoff] [bias]
     unsigned char* a_base = smem_raw;
     unsigned char* b_base = a_base + (size_t)A.astages * A.a_stage_bytes;
     unsigned long long* bars = (unsigned long long*)(b_base + (size_t)A.bstages * A.b_stage_bytes);
-    unsigned long long* a_full = bars;                       // [2]  count 128
-    unsigned long long* a_empty = bars + 2;                  // [2]  count 1 (tcgen05.commit)
-    unsigned long long* b_full = bars + 4;                   // [bstages] count 1 + tx
-    unsigned long long* b_empty = bars + 4 + CV_MAX_BSTAGES; // [bstages] count 1 (tcgen05.commit)
-    unsigned long long* acc_full = bars + 4 + 2 * CV_MAX_BSTAGES;
-    unsigned* tmem_ptr = (unsigned*)(acc_full + 1);
+    unsigned long long* a_full = bars;                                          // [astages] count CV_LOADERS
+    unsigned long long* a_empty = bars + CV_MAX_ASTAGES;                        // [astages] count 1 (tcgen05.commit)
+    unsigned long long* b_full = bars + 2 * CV_MAX_ASTAGES;                     // [bstages] count 1 + tx
+    unsigned long long* b_empty = b_full + CV_MAX_BSTAGES;                      // [bstages] count 1 (tcgen05.commit)
+    unsigned long long* acc_full = b_empty + CV_MAX_BSTAGES;                    // [2] count 1 (tcgen05.commit)
+    unsigned long long* acc_empty = acc_full + 2;                               // [2] count CV_LOADERS
+    unsigned* tmem_ptr = (unsigned*)(acc_empty + 2);
     int* pixoff = (int*)(tmem_ptr + 2);                      // [NPIX] global pixel index of every region pixel, -1 = zero pad
     float* bias_s = (float*)(((size_t)(pixoff + A.NPIX) + 15) & ~(size_t)15);   // [Npad], 16 B aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int taps = A.KH * A.KW;
-    const int x0 = blockIdx.x * 8 * A.MT, y0 = blockIdx.y * CV_ROWS, img = blockIdx.z;
     const unsigned a_half = A.a_stage_bytes / 2;             // hi | lo halves of an A stage
+    const int nacc = A.nacc;
+    const unsigned acc_cols = (unsigned)(A.MT * A.Npad);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < CV_MAX_ASTAGES; ++s) { mbar_init(&a_full[s], CV_LOADERS); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < A.astages; ++s) { mbar_init(&a_full[s], CV_LOADERS); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < A.bstages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        mbar_init(acc_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], CV_LOADERS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {   // TMEM allocation by one warp
+    if (warp == CV_LOADER_WARPS + 1) {   // TMEM allocation by one warp
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(A.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -305,34 +323,98 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
     tc_fence_after();
     const unsigned tmem = *tmem_ptr;
 
-    if (warp < 4) {
-        // ================= activation loaders: region -> (hi, lo) canonical tiles =================
+    if (warp < CV_LOADER_WARPS) {
+        // ================= activation loaders (region -> hi/lo canonical tiles) + epilogue =================
         const int padT = A.KH / 2, padL = A.KW / 2;
-        const float* X = A.x + (size_t)img * A.H * A.W * A.ldx;
         const bool vec = ((A.ldx & 3) == 0) && ((A.Cin & 3) == 0) && ((((size_t)A.x) & 15) == 0);
-        // the region -> image mapping does not depend on the channel chunk: compute it once
-        for (int pix = threadIdx.x; pix < A.NPIX; pix += CV_LOADERS) {
-            const int r = pix / A.RW, cc = pix - r * A.RW;
-            int gy = y0 + r - padT, gx = x0 + cc - padL;
-            bool ok = true;
-            if (A.pad_mode == PAD_REFLECT) {
-                gy = reflect101(gy, A.H);
-                gx = reflect101(gx, A.W);
-            } else {
-                ok = (gy >= 0 && gy < A.H && gx >= 0 && gx < A.W);
-            }
-            pixoff[pix] = ok ? gy * A.W + gx : -1;
-        }
         for (int n = threadIdx.x; n < A.Npad; n += CV_LOADERS) bias_s[n] = (A.bias && n < A.Cout) ? __ldg(A.bias + n) : 0.f;
-        asm volatile("bar.sync 1, %0;" ::"n"(CV_LOADERS) : "memory");
         constexpr int CPK = cv_cpk(PREC);
         constexpr int CHUNK = cv_chunk(PREC);
-        constexpr int U = (PREC == PREC_F16X3) ? 3 : 5;            // loads in flight per thread
+        constexpr int U = (PREC == PREC_F16X3) ? 4 : 6;            // loads in flight per thread
         const float xs = (float)(1 << CV_X_SHIFT);
+        const float oscale = __ldg(A.hdr);                         // exact power of two (1 for PREC_TF32X3)
+        const bool vec_out = (A.Cout & 3) == 0 && (A.ldy & 3) == 0 && ((((size_t)A.y) & 15) == 0);
+        const size_t plane = (size_t)A.H * A.W;
+        const int quarter = warp & 3, half = warp >> 2;            // a warp reads TMEM lanes 32*(warp % 4) .. +31
+        const int m = quarter * 32 + lane;                         // accumulator row = TMEM lane
         float amax = 0.f;
-        for (int c = 0; c < A.nchunks; ++c) {
-            const int s = c % A.astages;
-            if (c >= A.astages) mbar_wait(&a_empty[s], ((c / A.astages) - 1) & 1);
+        int g = 0;                                                 // running chunk counter of the A ring
+
+        // ---- epilogue of tile number jt (coordinates T): TMEM -> registers -> bias/activation -> global
+        auto epilogue = [&](int jt, const TileCoord& T) {
+            const int buf = jt % nacc, use = jt / nacc;
+            mbar_wait(&acc_full[buf], use & 1);
+            tc_fence_after();
+            const int orow = T.y0 + (m >> 3);
+            for (int t = 0; t < A.MT; ++t) {
+                const int ocol = T.x0 + t * 8 + (m & 7);
+                const bool inb = (orow < A.H && ocol < A.W);
+                const unsigned tbase = tmem + ((unsigned)(quarter * 32) << 16) + (unsigned)buf * acc_cols + (unsigned)(t * A.Npad);
+                // the two warps of a lane quarter split the work: whole tiles for softmax (needs every channel), else column blocks
+                if (ACT == ACT_SOFTMAX && A.MT > 1 && (t & 1) != half) continue;
+                if (ACT == ACT_SOFTMAX && A.MT == 1 && half) continue;
+                float* dst = A.out_nchw ? A.y + (size_t)T.img * A.Cout * plane + (size_t)orow * A.W + ocol
+                                        : A.y + (((size_t)T.img * A.H + orow) * A.W + ocol) * A.ldy;
+                float smax = -INFINITY, sinv = 1.f;
+                if (ACT == ACT_SOFTMAX) {          // pass 1 over TMEM: channel max and sum(exp)
+                    float ssum = 0.f;
+                    for (int n0 = 0; n0 < A.Npad; n0 += 16) {
+                        float v[16];
+                        tc_ld16(tbase + n0, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (n0 + i < A.Cout) {
+                                const float z = fmaf(v[i], oscale, bias_s[n0 + i]);
+                                if (z > smax) { ssum = ssum * expf(smax - z); smax = z; }
+                                ssum += expf(z - smax);
+                            }
+                    }
+                    sinv = 1.f / ssum;
+                }
+                for (int n0 = 0; n0 < A.Npad; n0 += 16) {
+                    if (ACT != ACT_SOFTMAX && (((n0 >> 4) + t) & 1) != half) continue;
+                    float v[16];
+                    tc_ld16(tbase + n0, v);
+                    if (!inb) continue;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const float4 b4 = *(const float4*)(bias_s + n0 + i);        // smem broadcast
+                        if (ACT == ACT_SOFTMAX) {
+                            v[i] = expf(fmaf(v[i], oscale, b4.x) - smax) * sinv;
+                            v[i + 1] = expf(fmaf(v[i + 1], oscale, b4.y) - smax) * sinv;
+                            v[i + 2] = expf(fmaf(v[i + 2], oscale, b4.z) - smax) * sinv;
+                            v[i + 3] = expf(fmaf(v[i + 3], oscale, b4.w) - smax) * sinv;
+                        } else {
+                            v[i] = apply_act<ACT>(fmaf(v[i], oscale, b4.x));
+                            v[i + 1] = apply_act<ACT>(fmaf(v[i + 1], oscale, b4.y));
+                            v[i + 2] = apply_act<ACT>(fmaf(v[i + 2], oscale, b4.z));
+                            v[i + 3] = apply_act<ACT>(fmaf(v[i + 3], oscale, b4.w));
+                        }
+                    }
+                    if (A.out_nchw) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (n0 + i < A.Cout) dst[(size_t)(n0 + i) * plane] = v[i];   // 8 consecutive px per row: full 32 B sectors
+                    } else if (vec_out) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            if (n0 + i < A.Cout) *(float4*)(dst + n0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (n0 + i < A.Cout) dst[n0 + i] = v[i];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);          // this thread's TMEM reads of the buffer are done
+        };
+
+        // ---- one K chunk of the current tile: global (via pixoff) -> hi/lo stage of the A ring
+        auto load_chunk = [&](int c, const float* X) {
+            const int s = g % A.astages;
+            if (g >= A.astages) mbar_wait(&a_empty[s], ((g / A.astages) - 1) & 1);
+            ++g;
             float4* hi = (float4*)(a_base + (size_t)s * A.a_stage_bytes);
             float4* lo = (float4*)(a_base + (size_t)s * A.a_stage_bytes + a_half);
             const int cbase = c * CHUNK;
@@ -398,85 +480,51 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             }
             fence_async_smem();          // generic-proxy stores -> visible to the tensor-core (async) proxy
             mbar_arrive(&a_full[s]);
-        }
-        if (PREC == PREC_F16X3 && !(amax <= 65504.f) && A.overflow) atomicOr(A.overflow, 1);
-        // ================= epilogue =================
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int m = warp * 32 + lane;                          // accumulator row = TMEM lane
-        const int orow = y0 + (m >> 3);
-        const bool vec_out = (A.Cout & 3) == 0 && (A.ldy & 3) == 0 && ((((size_t)A.y) & 15) == 0);
-        const size_t plane = (size_t)A.H * A.W;
-        const float oscale = __ldg(A.hdr);                       // exact power of two (1 for PREC_TF32X3)
-        for (int t = 0; t < A.MT; ++t) {
-            const int ocol = x0 + t * 8 + (m & 7);
-            const bool inb = (orow < A.H && ocol < A.W);
-            const unsigned tbase = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(t * A.Npad);
-            float* dst = A.out_nchw ? A.y + (size_t)img * A.Cout * plane + (size_t)orow * A.W + ocol
-                                    : A.y + (((size_t)img * A.H + orow) * A.W + ocol) * A.ldy;
-            float smax = -INFINITY, sinv = 1.f;
-            if (ACT == ACT_SOFTMAX) {          // pass 1 over TMEM: channel max and sum(exp)
-                float ssum = 0.f;
-                for (int n0 = 0; n0 < A.Npad; n0 += 16) {
-                    float v[16];
-                    tc_ld16(tbase + n0, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (n0 + i < A.Cout) {
-                            const float z = fmaf(v[i], oscale, bias_s[n0 + i]);
-                            if (z > smax) { ssum = ssum * expf(smax - z); smax = z; }
-                            ssum += expf(z - smax);
-                        }
-                }
-                sinv = 1.f / ssum;
-            }
-            for (int n0 = 0; n0 < A.Npad; n0 += 16) {
-                float v[16];
-                tc_ld16(tbase + n0, v);
-                if (!inb) continue;
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 b4 = *(const float4*)(bias_s + n0 + i);        // smem broadcast
-                    if (ACT == ACT_SOFTMAX) {
-                        v[i] = expf(fmaf(v[i], oscale, b4.x) - smax) * sinv;
-                        v[i + 1] = expf(fmaf(v[i + 1], oscale, b4.y) - smax) * sinv;
-                        v[i + 2] = expf(fmaf(v[i + 2], oscale, b4.z) - smax) * sinv;
-                        v[i + 3] = expf(fmaf(v[i + 3], oscale, b4.w) - smax) * sinv;
-                    } else {
-                        v[i] = apply_act<ACT>(fmaf(v[i], oscale, b4.x));
-                        v[i + 1] = apply_act<ACT>(fmaf(v[i + 1], oscale, b4.y));
-                        v[i + 2] = apply_act<ACT>(fmaf(v[i + 2], oscale, b4.z));
-                        v[i + 3] = apply_act<ACT>(fmaf(v[i + 3], oscale, b4.w));
-                    }
-                }
-                if (A.out_nchw) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (n0 + i < A.Cout) dst[(size_t)(n0 + i) * plane] = v[i];   // 8 consecutive px per row: full 32 B sectors
-                } else if (vec_out) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        if (n0 + i < A.Cout) *(float4*)(dst + n0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        };
+
+        TileCoord prev{0, 0, 0};
+        int j = 0;
+        for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, ++j) {
+            const TileCoord T = tile_coord(A, tile);
+            // region -> image mapping of this tile (all loaders are done with the previous table)
+            asm volatile("bar.sync 1, %0;" ::"n"(CV_LOADERS) : "memory");
+            for (int pix = threadIdx.x; pix < A.NPIX; pix += CV_LOADERS) {
+                const int r = pix / A.RW, cc = pix - r * A.RW;
+                int gy = T.y0 + r - padT, gx = T.x0 + cc - padL;
+                bool ok = true;
+                if (A.pad_mode == PAD_REFLECT) {
+                    gy = reflect101(gy, A.H);
+                    gx = reflect101(gx, A.W);
                 } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (n0 + i < A.Cout) dst[n0 + i] = v[i];
+                    ok = (gy >= 0 && gy < A.H && gx >= 0 && gx < A.W);
                 }
+                pixoff[pix] = ok ? gy * A.W + gx : -1;
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(CV_LOADERS) : "memory");
+            const float* X = A.x + (size_t)T.img * A.H * A.W * A.ldx;
+            // chunks that fit the ring first (never blocks on this tile's own MMA), then the previous tile's epilogue
+            // (which frees the accumulator this tile's MMA may be waiting for), then the rest
+            const int ahead = min(A.nchunks, A.astages);
+            for (int c = 0; c < ahead; ++c) load_chunk(c, X);
+            if (j > 0) epilogue(j - 1, prev);
+            for (int c = ahead; c < A.nchunks; ++c) load_chunk(c, X);
+            prev = T;
         }
-        tc_fence_before();
-    } else if (warp == 4) {
+        if (j > 0) epilogue(j - 1, prev);
+        if (PREC == PREC_F16X3 && !(amax <= 65504.f) && A.overflow) atomicOr(A.overflow, 1);
+    } else if (warp == CV_LOADER_WARPS) {
         // ================= weight producer =================
         if (lane == 0) {
             int it = 0;
-            for (int c = 0; c < A.nchunks; ++c)
-                for (int tp = 0; tp < taps; ++tp, ++it) {
-                    const int s = it % A.bstages;
-                    if (it >= A.bstages) mbar_wait(&b_empty[s], ((it / A.bstages) - 1) & 1);
-                    mbar_expect_tx(&b_full[s], A.b_stage_bytes);
-                    bulk_g2s(b_base + (size_t)s * A.b_stage_bytes,
-                             A.wpack + ((size_t)c * taps + tp) * (A.b_stage_bytes / 4), A.b_stage_bytes, &b_full[s]);
-                }
+            for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x)
+                for (int c = 0; c < A.nchunks; ++c)
+                    for (int tp = 0; tp < taps; ++tp, ++it) {
+                        const int s = it % A.bstages;
+                        if (it >= A.bstages) mbar_wait(&b_empty[s], ((it / A.bstages) - 1) & 1);
+                        mbar_expect_tx(&b_full[s], A.b_stage_bytes);
+                        bulk_g2s(b_base + (size_t)s * A.b_stage_bytes,
+                                 A.wpack + ((size_t)c * taps + tp) * (A.b_stage_bytes / 4), A.b_stage_bytes, &b_full[s]);
+                    }
         }
     } else {
         // ================= MMA issuer: whole warp runs the (uniform) loops, one elected lane issues =================
@@ -491,46 +539,52 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             const unsigned long long a_desc0 = make_desc(0, a_lbo, a_sbo), b_desc0 = make_desc(0, b_lbo, b_sbo);
             const unsigned long long a_kstep = (2u * a_lbo) >> 4, b_kstep = (2u * b_lbo) >> 4;
             const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-            int it = 0;
-            for (int c = 0; c < A.nchunks; ++c) {
-                const int sa = c % A.astages;
-                mbar_wait(&a_full[sa], (c / A.astages) & 1);
-                const unsigned a_st = smem_u32(a_base + (size_t)sa * A.a_stage_bytes) >> 4;
-                const unsigned long long a_hi0 = a_desc0 + a_st, a_lo0 = a_hi0 + (a_half >> 4);
-                int dy = 0, dx = 0;
-                const bool two = (c < A.nchunks - 1) || A.last_ksteps == 2;   // warp-uniform
-                for (int tp = 0; tp < taps; ++tp, ++it) {
-                    const int sb = it % A.bstages;
-                    mbar_wait(&b_full[sb], (it / A.bstages) & 1);
-                    tc_fence_after();
-                    const unsigned b_st = smem_u32(b_base + (size_t)sb * A.b_stage_bytes) >> 4;
-                    const unsigned long long dbh0 = b_desc0 + b_st, dbl0 = dbh0 + (b_half >> 4);
-                    const unsigned long long dbh1 = dbh0 + b_kstep, dbl1 = dbl0 + b_kstep;
-                    const unsigned tap_off = (unsigned)(dy * A.RW + dx);             // in 16 B units (one pixel)
-                    const unsigned acc_first = (c == 0 && tp == 0) ? 0u : 1u;
-                    const unsigned long long dah = a_hi0 + tap_off, dal = a_lo0 + tap_off;
-                    const unsigned np = (unsigned)A.Npad;
-                    if (A.MT == 4) {
-                        tc_mma_kstep<4, PREC>(tmem_u, np, dal, dah, dbh0, dbl0, idesc, acc_first);
-                        if (two) tc_mma_kstep<4, PREC>(tmem_u, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
-                    } else if (A.MT == 2) {
-                        tc_mma_kstep<2, PREC>(tmem_u, np, dal, dah, dbh0, dbl0, idesc, acc_first);
-                        if (two) tc_mma_kstep<2, PREC>(tmem_u, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
-                    } else {
-                        tc_mma_kstep<1, PREC>(tmem_u, np, dal, dah, dbh0, dbl0, idesc, acc_first);
-                        if (two) tc_mma_kstep<1, PREC>(tmem_u, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
+            int it = 0, g = 0, j = 0;
+            for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, ++j) {
+                const int buf = j % nacc, use = j / nacc;
+                if (use > 0) mbar_wait(&acc_empty[buf], (use - 1) & 1);     // epilogue drained this accumulator
+                tc_fence_after();
+                const unsigned tacc = tmem_u + (unsigned)buf * acc_cols;
+                for (int c = 0; c < A.nchunks; ++c, ++g) {
+                    const int sa = g % A.astages;
+                    mbar_wait(&a_full[sa], (g / A.astages) & 1);
+                    const unsigned a_st = smem_u32(a_base + (size_t)sa * A.a_stage_bytes) >> 4;
+                    const unsigned long long a_hi0 = a_desc0 + a_st, a_lo0 = a_hi0 + (a_half >> 4);
+                    int dy = 0, dx = 0;
+                    const bool two = (c < A.nchunks - 1) || A.last_ksteps == 2;   // warp-uniform
+                    for (int tp = 0; tp < taps; ++tp, ++it) {
+                        const int sb = it % A.bstages;
+                        mbar_wait(&b_full[sb], (it / A.bstages) & 1);
+                        tc_fence_after();
+                        const unsigned b_st = smem_u32(b_base + (size_t)sb * A.b_stage_bytes) >> 4;
+                        const unsigned long long dbh0 = b_desc0 + b_st, dbl0 = dbh0 + (b_half >> 4);
+                        const unsigned long long dbh1 = dbh0 + b_kstep, dbl1 = dbl0 + b_kstep;
+                        const unsigned tap_off = (unsigned)(dy * A.RW + dx);             // in 16 B units (one pixel)
+                        const unsigned acc_first = (c == 0 && tp == 0) ? 0u : 1u;
+                        const unsigned long long dah = a_hi0 + tap_off, dal = a_lo0 + tap_off;
+                        const unsigned np = (unsigned)A.Npad;
+                        if (A.MT == 4) {
+                            tc_mma_kstep<4, PREC>(tacc, np, dal, dah, dbh0, dbl0, idesc, acc_first);
+                            if (two) tc_mma_kstep<4, PREC>(tacc, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
+                        } else if (A.MT == 2) {
+                            tc_mma_kstep<2, PREC>(tacc, np, dal, dah, dbh0, dbl0, idesc, acc_first);
+                            if (two) tc_mma_kstep<2, PREC>(tacc, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
+                        } else {
+                            tc_mma_kstep<1, PREC>(tacc, np, dal, dah, dbh0, dbl0, idesc, acc_first);
+                            if (two) tc_mma_kstep<1, PREC>(tacc, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
+                        }
+                        tc_commit(&b_empty[sb]);           // weights of this (chunk, tap) consumed
+                        if (++dx == A.KW) { dx = 0; ++dy; }
                     }
-                    tc_commit(&b_empty[sb]);           // weights of this (chunk, tap) consumed
-                    if (++dx == A.KW) { dx = 0; ++dy; }
+                    tc_commit(&a_empty[sa]);               // region of this chunk consumed
                 }
-                tc_commit(&a_empty[sa]);               // region of this chunk consumed
+                tc_commit(&acc_full[buf]);
             }
-            tc_commit(acc_full);
         }
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 5) {
+    if (warp == CV_LOADER_WARPS + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(A.tmem_cols));
     }
@@ -544,32 +598,34 @@ static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
     a.nchunks = (a.Cin + chunk - 1) / chunk;
     a.last_ksteps = (a.Cin - (a.nchunks - 1) * chunk) > chunk / 2 ? 2 : 1;
     a.b_stage_bytes = (unsigned)a.Npad * CV_KCHUNKS * 16u * 2u;        // hi + lo
-    // Shallow layers (few K stages per tile) cannot hide their prologue / first load / epilogue behind their own main
-    // loop: give them half the shared memory so that two CTAs share an SM and overlap each other.
-    a.astages = a.nchunks > 1 ? CV_MAX_ASTAGES : 1;
+    // one persistent CTA per SM: as many A stages as fit (the loaders run that far ahead of the tensor core)
     const int taps = a.KH * a.KW;
-    const bool shallow = a.nchunks * taps <= 64;
-    for (int pass = shallow ? 0 : 1; pass < 2; ++pass) {
-        const size_t budget = (pass == 0 ? 110 : 220) * 1024;
-        for (int mt = 4; mt >= 1; mt >>= 1) {
-            if (mt * a.Npad > (pass == 0 ? 256 : 512)) continue;           // TMEM columns are shared by the resident CTAs
-            if (mt > 1 && 8 * (mt / 2) >= a.W) continue;                   // do not over-tile narrow images
-            a.MT = mt;
-            a.RW = 8 * mt + a.KW - 1;
-            a.RH = CV_ROWS + a.KH - 1;
-            a.NPIX = a.RW * a.RH;
-            a.a_stage_bytes = (unsigned)a.NPIX * CV_KCHUNKS * 16u * 2u;    // hi + lo
-            const size_t fixed = (size_t)a.astages * a.a_stage_bytes + 256 + (size_t)a.NPIX * 4 + 1024 + 16;
-            const int min_b = std::min(2, a.nchunks * taps);
-            if (fixed + (size_t)min_b * a.b_stage_bytes > budget) continue;
-            int bs = (int)((budget - fixed) / a.b_stage_bytes);
-            a.bstages = bs > CV_MAX_BSTAGES ? CV_MAX_BSTAGES : bs;
-            int cols = 32;
-            while (cols < mt * a.Npad) cols <<= 1;
-            a.tmem_cols = cols;
-            *smem_bytes = fixed + (size_t)a.bstages * a.b_stage_bytes;
-            return FVFI_OK;
-        }
+    const size_t budget = 222 * 1024;
+    for (int mt = 4; mt >= 1; mt >>= 1) {
+        if (mt * a.Npad > 512) continue;
+        if (mt > 1 && 8 * (mt / 2) >= a.W) continue;                   // do not over-tile narrow images
+        a.MT = mt;
+        a.nacc = (2 * mt * a.Npad <= 512) ? 2 : 1;
+        a.RW = 8 * mt + a.KW - 1;
+        a.RH = CV_ROWS + a.KH - 1;
+        a.NPIX = a.RW * a.RH;
+        a.a_stage_bytes = (unsigned)a.NPIX * CV_KCHUNKS * 16u * 2u;    // hi + lo
+        const size_t misc = 512 + (size_t)a.NPIX * 4 + 1024 + 16;
+        const int min_b = std::min(2, a.nchunks * taps);
+        if (misc + 2 * (size_t)a.a_stage_bytes + (size_t)min_b * a.b_stage_bytes > budget) continue;
+        // weights first (up to 4 stages of a few KB), the rest goes to activation stages
+        int bs = std::min(CV_MAX_BSTAGES, std::max(min_b, (int)((budget - misc - 2 * (size_t)a.a_stage_bytes) / a.b_stage_bytes)));
+        int as = (int)((budget - misc - (size_t)bs * a.b_stage_bytes) / a.a_stage_bytes);
+        a.bstages = bs;
+        a.astages = std::max(2, std::min(CV_MAX_ASTAGES, as));
+        int cols = 32;
+        while (cols < a.nacc * mt * a.Npad) cols <<= 1;
+        a.tmem_cols = cols;
+        *smem_bytes = misc + (size_t)a.astages * a.a_stage_bytes + (size_t)a.bstages * a.b_stage_bytes;
+        a.tiles_x = ceil_div(a.W, 8 * mt);
+        a.tiles_y = ceil_div(a.H, CV_ROWS);
+        a.ntiles = a.tiles_x * a.tiles_y * a.B;
+        return FVFI_OK;
     }
     set_error("conv: no tile configuration fits (Cout %d, kernel %dx%d)", a.Cout, a.KH, a.KW);
     return FVFI_EINVAL;
@@ -659,7 +715,8 @@ extern "C" int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float*
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.KH = KH; a.KW = KW; a.pad_mode = pad_mode; a.act = activation;
     size_t smem = 0;
     if (int rc = conv_geometry(a, precision, &smem)) return rc;
-    dim3 grid(ceil_div(W, 8 * a.MT), ceil_div(H, CV_ROWS), B);
+    const int nsm = sm_count();
+    dim3 grid((unsigned)std::min(a.ntiles, nsm > 0 ? nsm : 148), 1, 1);
     void (*kern)(const ConvArgs) = (precision == PREC_F16X3) ? pick_kernel<PREC_F16X3>(activation) : pick_kernel<PREC_TF32X3>(activation);
     FVFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, CV_THREADS, smem, (cudaStream_t)stream>>>(a);
