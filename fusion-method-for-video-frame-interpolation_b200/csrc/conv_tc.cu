@@ -61,6 +61,7 @@ struct ConvArgs {
     int B, H, W, Cin, Cout, Npad, KH, KW, pad_mode, act;
     int ldx, ldy;          // floats per pixel in the input / output storage (channel-slice views)
     int out_nchw;          // 1: y is planar [B,Cout,H,W] (coefficient maps for the warp kernel)
+    int cout_store;        // NHWC channels written per pixel: Cout, or round16(Cout) with the padding zero-filled
     int MT, RW, RH, NPIX;  // tiles per CTA, staged region geometry
     int nchunks, last_ksteps, astages, bstages, tmem_cols;
     int nacc;              // TMEM accumulator buffers (2 when they fit: epilogue of tile j-1 overlaps the MMAs of tile j)
@@ -326,14 +327,17 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
     if (warp < CV_LOADER_WARPS) {
         // ================= activation loaders (region -> hi/lo canonical tiles) + epilogue =================
         const int padT = A.KH / 2, padL = A.KW / 2;
-        const bool vec = ((A.ldx & 3) == 0) && ((A.Cin & 3) == 0) && ((((size_t)A.x) & 15) == 0);
+        // 16-byte loads need aligned pixels; a channel count that is not a multiple of 4 is fine when the pixel stride
+        // leaves room for the rounded-up group (the producer zero-fills the padding channels, see out layout 2)
+        const int cin4 = (A.Cin + 3) & ~3;
+        const bool vec = ((A.ldx & 3) == 0) && (A.ldx >= cin4) && ((((size_t)A.x) & 15) == 0);
         for (int n = threadIdx.x; n < A.Npad; n += CV_LOADERS) bias_s[n] = (A.bias && n < A.Cout) ? __ldg(A.bias + n) : 0.f;
         constexpr int CPK = cv_cpk(PREC);
         constexpr int CHUNK = cv_chunk(PREC);
         constexpr int U = (PREC == PREC_F16X3) ? 4 : 6;            // loads in flight per thread
         const float xs = (float)(1 << CV_X_SHIFT);
         const float oscale = __ldg(A.hdr);                         // exact power of two (1 for PREC_TF32X3)
-        const bool vec_out = (A.Cout & 3) == 0 && (A.ldy & 3) == 0 && ((((size_t)A.y) & 15) == 0);
+        const bool vec_out = (A.cout_store & 3) == 0 && (A.ldy & 3) == 0 && ((((size_t)A.y) & 15) == 0);
         const size_t plane = (size_t)A.H * A.W;
         const int quarter = warp & 3, half = warp >> 2;            // a warp reads TMEM lanes 32*(warp % 4) .. +31
         const int m = quarter * 32 + lane;                         // accumulator row = TMEM lane
@@ -398,11 +402,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     } else if (vec_out) {
 #pragma unroll
                         for (int i = 0; i < 16; i += 4)
-                            if (n0 + i < A.Cout) *(float4*)(dst + n0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            if (n0 + i < A.cout_store) *(float4*)(dst + n0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (n0 + i < A.Cout) dst[n0 + i] = v[i];
+                            if (n0 + i < A.cout_store) dst[n0 + i] = v[i];
                     }
                 }
             }
@@ -432,12 +436,12 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     if (q < total) {
                         const int pix = q >> ksh, ch = cbase + (q & kmask) * CPK;   // consecutive threads read one pixel's chunk
                         const int off = pixoff[pix];
-                        if (off >= 0 && ch < A.Cin) {
+                        if (off >= 0 && ch < cin4) {
                             const float* p = X + (size_t)off * A.ldx + ch;
                             if (vec) {
 #pragma unroll
                                 for (int e = 0; e < CPK; e += 4) {
-                                    if (ch + e < A.Cin) {
+                                    if (ch + e < cin4) {
                                         const float4 t = __ldg((const float4*)(p + e));
                                         v[u][e] = t.x; v[u][e + 1] = t.y; v[u][e + 2] = t.z; v[u][e + 3] = t.w;
                                     }
@@ -709,7 +713,10 @@ extern "C" int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float*
     FVFI_CHECK_ARG(precision == PREC_TF32X3 || precision == PREC_F16X3, "conv2d: precision must be 0 (3xTF32) or 1 (3xFP16)");
     ConvArgs a{};
     a.x = x; a.hdr = packed_weight; a.wpack = packed_weight + CV_HDR; a.bias = bias; a.y = y;
-    a.ldx = x_pixel_stride; a.ldy = y_pixel_stride; a.out_nchw = out_nchw ? 1 : 0;
+    a.ldx = x_pixel_stride; a.ldy = y_pixel_stride; a.out_nchw = (out_nchw == 1) ? 1 : 0;
+    a.cout_store = (out_nchw == 2) ? ((Cout + 15) & ~15) : Cout;
+    FVFI_CHECK_ARG(out_nchw >= 0 && out_nchw <= 2, "conv2d: output layout must be 0 (NHWC), 1 (NCHW) or 2 (NHWC, zero-padded channels)");
+    FVFI_CHECK_ARG(out_nchw != 2 || y_pixel_stride >= a.cout_store, "conv2d: padded NHWC output needs a pixel stride >= round16(Cout)");
     a.overflow = (precision == PREC_F16X3) ? overflow_flag() : nullptr;
     FVFI_CHECK_ARG(x_pixel_stride >= Cin && (out_nchw || y_pixel_stride >= Cout), "conv2d: pixel stride smaller than channel count");
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.KH = KH; a.KW = KW; a.pad_mode = pad_mode; a.act = activation;

@@ -312,13 +312,13 @@ namespace fvfi {
 __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi,
                                                                    int Wi, int Ho, int Wo, int C, int ldx, int ldy,
                                                                    float sy, float sx, int align_corners) {
-    const int c4 = (C + 3) >> 2;
-    const size_t total = (size_t)Ho * Wo * c4;
-    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned c4 = (unsigned)(C + 3) >> 2;
+    const unsigned total = (unsigned)Ho * (unsigned)Wo * c4;      // per image; < 2^32 checked by the launcher
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= total) return;
-    const int cg = (int)(q % c4);
-    const size_t p = q / c4;
-    const int ox = (int)(p % Wo), oy = (int)(p / Wo);
+    const unsigned p = q / c4;
+    const int cg = (int)(q - p * c4);
+    const int oy = (int)(p / (unsigned)Wo), ox = (int)(p - (unsigned)oy * (unsigned)Wo);
     const int n = blockIdx.y;
     // source coordinates exactly as ATen's area_pixel_compute_source_index
     float fy, fx;
@@ -370,6 +370,7 @@ extern "C" int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, flo
         sx = (float)Wi / (float)Wo;
     }
     const size_t total = (size_t)Ho * Wo * ((C + 3) / 4);
+    FVFI_CHECK_ARG(total < (1ull << 32) - 256, "resize_bilinear: image too large");
     dim3 grid((unsigned)((total + 255) / 256), B);
     fvfi::resize_bilinear_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride,
                                                                               sy, sx, align_corners);

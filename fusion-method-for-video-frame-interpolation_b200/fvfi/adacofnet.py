@@ -96,7 +96,10 @@ class KernelEstimation(torch.nn.Module):
             if isinstance(m, torch.nn.Conv2d):
                 nxt = mods[i + 1] if i + 1 < len(mods) else None
                 act = {torch.nn.ReLU: "relu", torch.nn.Sigmoid: "sigmoid", torch.nn.Softmax: "softmax"}.get(type(nxt))
-                x = tc.conv_module(m, x, act, nchw_out=nchw_last and i == last_conv)
+                # a conv feeding an Upsample keeps its channels padded to 16 (zeros): resize and the next conv then
+                # use 16-byte accesses even for the 25-channel heads
+                pad = (i + 2 < len(mods) and isinstance(mods[i + 2], torch.nn.Upsample) and m.out_channels % 4 != 0)
+                x = tc.conv_module(m, x, act, nchw_out=nchw_last and i == last_conv, pad_out=pad)
                 i += 2 if act else 1
             elif isinstance(m, torch.nn.Upsample):
                 x = tc.resize_bilinear(x, (x.shape[2] * 2, x.shape[3] * 2), bool(m.align_corners))

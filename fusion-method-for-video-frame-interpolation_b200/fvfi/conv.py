@@ -58,25 +58,30 @@ def to_nhwc(x):
     return x.contiguous(memory_format=torch.channels_last)
 
 
-def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_out=False):
+def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_out=False, pad_out=False):
     """x [B,Cin,H,W] (any memory format; channels_last avoids a copy) -> [B,Cout,H,W] channels_last
     (``nchw_out=True``: plain contiguous NCHW, written directly by the epilogue).
     Equivalent to act(F.conv2d(pad(x), weight, bias)) with 'same' padding (K//2) in zeros or reflect mode;
-    act 'softmax' is over the channel dimension."""
+    act 'softmax' is over the channel dimension.
+    ``pad_out=True``: the result has round16(Cout) channels, the extra ones zero (keeps 16-byte accesses for channel
+    counts such as 25).  ``x`` may carry such zero padding channels beyond the weight's Cin."""
     if not x.is_cuda:
         raise NotImplementedError("fvfi.conv.conv2d: CUDA tensors only")
     B, Cin, H, W = x.shape
     Cout, Cin_w, KH, KW = weight.shape
-    assert Cin == Cin_w and KH == KW and KH in (1, 3, 5)
+    assert Cin >= Cin_w and KH == KW and KH in (1, 3, 5)
+    Cin = Cin_w
     xc = to_nhwc(x.float())
     assert xc.stride(1) == 1
     ldx = xc.stride(3)                       # floats per pixel
     if out is None:
-        out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device,
+        out = torch.empty((B, (Cout + 15) // 16 * 16 if pad_out else Cout, H, W), dtype=torch.float32, device=x.device,
                           memory_format=torch.contiguous_format if nchw_out else torch.channels_last)
     ldy = Cout if nchw_out else out.stride(3)
     if nchw_out:
-        assert out.is_contiguous() and Cout <= 256
+        assert out.is_contiguous() and Cout <= 256 and not pad_out
+    if pad_out:
+        assert Cout <= 256
     L = _lib.lib()
     pad_mode = {"zeros": 0, "reflect": 1}[padding_mode]
     b = None if bias is None else bias.detach().contiguous().float()
@@ -84,7 +89,7 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
         for (o, n, buf, _) in _packed(weight):
             _lib.check(L.fvfi_conv2d_nhwc(xc.data_ptr(), ldx, buf.data_ptr(), None if b is None else b.data_ptr() + 4 * o,
                                           out.data_ptr() + 4 * o, ldy, B, H, W, Cin, n, KH, KW, pad_mode, ACT[act],
-                                          1 if nchw_out else 0, precision, _lib.stream_ptr()))
+                                          1 if nchw_out else (2 if pad_out else 0), precision, _lib.stream_ptr()))
     return out
 
 
@@ -104,13 +109,13 @@ def resize_bilinear(x, size, align_corners, out=None, out_channel_offset=0):
     return out
 
 
-def conv_module(conv, x, act=None, nchw_out=False):
+def conv_module(conv, x, act=None, nchw_out=False, pad_out=False):
     """Run an nn.Conv2d (stride 1, dilation 1, padding == K//2) through the tensor-core kernel."""
     k = conv.kernel_size[0]
     assert conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
     assert conv.padding == (k // 2, k // 2) or (k == 1 and conv.padding == (0, 0))
     mode = "zeros" if k == 1 else conv.padding_mode
-    return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out)
+    return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out, pad_out=pad_out)
 
 
 _fold_cache = {}

@@ -115,7 +115,9 @@ int fvfi_median_filter(const float* in, float* out, int N, int H, int W, int siz
  *   x: NHWC, x_pixel_stride floats between pixels (>= Cin); y likewise.  Cout <= 256 per call.
  *   KH == KW in {1,3,5}; pad_mode 0 = zeros, 1 = reflect (torch 'reflect'); activation 0 none, 1 ReLU, 2 ELU,
  *   3 tanh, 4 sigmoid, 5 softmax over the Cout channels; bias [Cout] or NULL.
- *   out_nchw != 0: y is planar [B,Cout,H,W] (the layout the AdaCoF warp streams its coefficient maps in). */
+ *   out_nchw: 0 = NHWC; 1 = planar [B,Cout,H,W] (the layout the AdaCoF warp streams its coefficient maps in);
+ *   2 = NHWC with round16(Cout) channels written per pixel, the padding zero-filled (so that a consumer with a channel
+ *   count that is not a multiple of 4 can still use 16-byte loads: x_pixel_stride >= roundup4(Cin) enables them). */
 size_t fvfi_conv2d_packed_weight_floats(int Cout, int Cin, int KH, int KW, int precision);
 int fvfi_conv2d_pack_weights(const float* weight_oihw, float* packed, int Cout, int Cin, int KH, int KW, int precision,
                              void* stream);

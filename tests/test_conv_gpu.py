@@ -101,3 +101,23 @@ def test_conv_softmax_and_nchw_epilogues(prec):
     w1 = torch.randn((1, 25, 3, 3), device="cuda", generator=g) / 15
     y = conv.conv2d(x, w1, b[:1], "zeros", "sigmoid", nchw_out=True)
     assert float((y.double() - torch.sigmoid(F.conv2d(x.double(), w1.double(), b[:1].double(), padding=1))).abs().max()) <= 2e-6
+
+
+def test_conv_padded_channel_chain(prec):
+    """64 -> 25 conv with zero-padded NHWC output (32 channels), bilinear x2, 25 -> 25 conv reading the padded tensor
+    with 16-byte loads: the KernelEstimation head tail (fusion_adacofnet.py:36-59)."""
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn((2, 64, 20, 36), device="cuda", generator=g)
+    w1 = torch.randn((25, 64, 3, 3), device="cuda", generator=g) / 24
+    b1 = torch.randn((25,), device="cuda", generator=g)
+    w2 = torch.randn((25, 25, 3, 3), device="cuda", generator=g) / 15
+    b2 = torch.randn((25,), device="cuda", generator=g)
+    y1 = conv.conv2d(x, w1, b1, "zeros", "relu", pad_out=True)
+    assert y1.shape == (2, 32, 20, 36) and float(y1[:, 25:].abs().max()) == 0.0
+    up = conv.resize_bilinear(y1, (40, 72), True)
+    assert float(up[:, 25:].abs().max()) == 0.0
+    y2 = conv.conv2d(up, w2, b2, "zeros", "softmax", nchw_out=True)
+    r1 = F.relu(F.conv2d(x.double(), w1.double(), b1.double(), padding=1))
+    r2 = F.conv2d(F.interpolate(r1, size=(40, 72), mode="bilinear", align_corners=True), w2.double(), b2.double(), padding=1)
+    assert y2.shape == (2, 25, 40, 72) and float((y2.double() - torch.softmax(r2, 1)).abs().max()) <= 5e-6
