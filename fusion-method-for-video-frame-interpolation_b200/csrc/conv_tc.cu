@@ -35,6 +35,7 @@
 namespace fvfi {
 
 constexpr int CV_KCHUNKS = 4;           // 16-byte K chunks per stage = two MMA K steps of 32 bytes
+constexpr int CV_UMAX = 12;             // (pixel, K chunk) items a loader thread keeps in flight: a whole K chunk of the tile
 constexpr int CV_HDR = 32;              // floats of header in front of the packed weights (scales, precision)
 constexpr int CV_X_SHIFT = 4;           // PREC_F16X3: activations are scaled by 2^4 before the fp16 split
 constexpr int CV_ROWS = 16;             // output rows per CTA
@@ -165,6 +166,14 @@ __device__ __forceinline__ void tc_mma_kstep(unsigned d, unsigned np, unsigned l
         FVFI_KSTEP_BODY("tf32")
     }
 }
+__device__ __forceinline__ void tc_ld16_issue(unsigned taddr, unsigned* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld16(unsigned taddr, float* v) {
     unsigned r[16];
     asm volatile(
@@ -350,19 +359,48 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after();
             const int orow = T.y0 + (m >> 3);
-            for (int t = 0; t < A.MT; ++t) {
+            const unsigned tq = tmem + ((unsigned)(quarter * 32) << 16) + (unsigned)buf * acc_cols;
+            // bias + activation + store of one 16-column block of accumulator tile t (smax / sinv: softmax only)
+            auto emit = [&](int t, int n0, const unsigned* r, float smax, float sinv) {
                 const int ocol = T.x0 + t * 8 + (m & 7);
-                const bool inb = (orow < A.H && ocol < A.W);
-                const unsigned tbase = tmem + ((unsigned)(quarter * 32) << 16) + (unsigned)buf * acc_cols + (unsigned)(t * A.Npad);
-                // the two warps of a lane quarter split the work: whole tiles for softmax (needs every channel), else column blocks
-                if (ACT == ACT_SOFTMAX && A.MT > 1 && (t & 1) != half) continue;
-                if (ACT == ACT_SOFTMAX && A.MT == 1 && half) continue;
+                if (!(orow < A.H && ocol < A.W)) return;
                 float* dst = A.out_nchw ? A.y + (size_t)T.img * A.Cout * plane + (size_t)orow * A.W + ocol
                                         : A.y + (((size_t)T.img * A.H + orow) * A.W + ocol) * A.ldy;
-                float smax = -INFINITY, sinv = 1.f;
-                if (ACT == ACT_SOFTMAX) {          // pass 1 over TMEM: channel max and sum(exp)
-                    float ssum = 0.f;
-                    for (int n0 = 0; n0 < A.Npad; n0 += 16) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 b4 = *(const float4*)(bias_s + n0 + i);        // smem broadcast
+                    const float z0 = fmaf(__uint_as_float(r[i]), oscale, b4.x), z1 = fmaf(__uint_as_float(r[i + 1]), oscale, b4.y);
+                    const float z2 = fmaf(__uint_as_float(r[i + 2]), oscale, b4.z), z3 = fmaf(__uint_as_float(r[i + 3]), oscale, b4.w);
+                    if (ACT == ACT_SOFTMAX) {
+                        v[i] = expf(z0 - smax) * sinv; v[i + 1] = expf(z1 - smax) * sinv;
+                        v[i + 2] = expf(z2 - smax) * sinv; v[i + 3] = expf(z3 - smax) * sinv;
+                    } else {
+                        v[i] = apply_act<ACT>(z0); v[i + 1] = apply_act<ACT>(z1);
+                        v[i + 2] = apply_act<ACT>(z2); v[i + 3] = apply_act<ACT>(z3);
+                    }
+                }
+                if (A.out_nchw) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < A.Cout) dst[(size_t)(n0 + i) * plane] = v[i];   // 8 consecutive px per row: full 32 B sectors
+                } else if (vec_out) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        if (n0 + i < A.cout_store) *(float4*)(dst + n0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < A.cout_store) dst[n0 + i] = v[i];
+                }
+            };
+            if (ACT == ACT_SOFTMAX) {
+                // the two warps of a lane quarter take whole tiles (a pixel's softmax needs every channel)
+                for (int t = 0; t < A.MT; ++t) {
+                    if (A.MT > 1 ? ((t & 1) != half) : (half != 0)) continue;
+                    const unsigned tbase = tq + (unsigned)(t * A.Npad);
+                    float smax = -INFINITY, ssum = 0.f;
+                    for (int n0 = 0; n0 < A.Npad; n0 += 16) {          // pass 1 over TMEM: channel max and sum(exp)
                         float v[16];
                         tc_ld16(tbase + n0, v);
 #pragma unroll
@@ -373,124 +411,110 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                                 ssum += expf(z - smax);
                             }
                     }
-                    sinv = 1.f / ssum;
-                }
-                for (int n0 = 0; n0 < A.Npad; n0 += 16) {
-                    if (ACT != ACT_SOFTMAX && (((n0 >> 4) + t) & 1) != half) continue;
-                    float v[16];
-                    tc_ld16(tbase + n0, v);
-                    if (!inb) continue;
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const float4 b4 = *(const float4*)(bias_s + n0 + i);        // smem broadcast
-                        if (ACT == ACT_SOFTMAX) {
-                            v[i] = expf(fmaf(v[i], oscale, b4.x) - smax) * sinv;
-                            v[i + 1] = expf(fmaf(v[i + 1], oscale, b4.y) - smax) * sinv;
-                            v[i + 2] = expf(fmaf(v[i + 2], oscale, b4.z) - smax) * sinv;
-                            v[i + 3] = expf(fmaf(v[i + 3], oscale, b4.w) - smax) * sinv;
-                        } else {
-                            v[i] = apply_act<ACT>(fmaf(v[i], oscale, b4.x));
-                            v[i + 1] = apply_act<ACT>(fmaf(v[i + 1], oscale, b4.y));
-                            v[i + 2] = apply_act<ACT>(fmaf(v[i + 2], oscale, b4.z));
-                            v[i + 3] = apply_act<ACT>(fmaf(v[i + 3], oscale, b4.w));
-                        }
-                    }
-                    if (A.out_nchw) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (n0 + i < A.Cout) dst[(size_t)(n0 + i) * plane] = v[i];   // 8 consecutive px per row: full 32 B sectors
-                    } else if (vec_out) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            if (n0 + i < A.cout_store) *(float4*)(dst + n0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (n0 + i < A.cout_store) dst[n0 + i] = v[i];
+                    const float sinv = 1.f / ssum;
+                    for (int n0 = 0; n0 < A.Npad; n0 += 16) {
+                        unsigned r[16];
+                        tc_ld16_issue(tbase + n0, r);
+                        tc_ld_wait();
+                        emit(t, n0, r, smax, sinv);
                     }
                 }
+            } else {
+                // the two warps of a lane quarter take alternate 16-column blocks
+                for (int t = 0; t < A.MT; ++t)
+                    for (int n0 = ((t & 1) != half) ? 16 : 0; n0 < A.Npad; n0 += 32) {
+                        unsigned r[16];
+                        tc_ld16_issue(tq + (unsigned)(t * A.Npad + n0), r);
+                        tc_ld_wait();
+                        emit(t, n0, r, 0.f, 1.f);
+                    }
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);          // this thread's TMEM reads of the buffer are done
         };
 
-        // ---- one K chunk of the current tile: global (via pixoff) -> hi/lo stage of the A ring
-        auto load_chunk = [&](int c, const float* X) {
+        // ---- one K chunk = two phases.  issue(): ALL of this thread's 16-byte global loads of the chunk go out at once
+        // (up to UMAX items of CPK channels stay in registers), so the whole chunk is in flight while the thread does
+        // something else (the previous tile's epilogue); finish(): split into hi/lo, store into the A ring.
+        constexpr int UMAX = CV_UMAX;                              // NPIX * 4 <= CV_LOADERS * UMAX (checked on the host)
+        float v[UMAX][CPK];
+        auto chunk_shape = [&](int c, int& ksh) {
+            // the last chunk may need only the first MMA K step: K chunks 0,1 are stored first, so just stop early
+            ksh = (c == A.nchunks - 1 && A.last_ksteps == 1) ? 1 : 2;            // log2(K chunks to fill)
+            return A.NPIX << ksh;
+        };
+        auto issue = [&](int c, const float* X) {
+            int ksh;
+            const int total = chunk_shape(c, ksh);
+            const int kmask = (1 << ksh) - 1, cbase = c * CHUNK;
+#pragma unroll
+            for (int u = 0; u < UMAX; ++u) {
+                const int q = threadIdx.x + u * CV_LOADERS;
+#pragma unroll
+                for (int e = 0; e < CPK; ++e) v[u][e] = 0.f;
+                if (q < total) {
+                    const int pix = q >> ksh, ch = cbase + (q & kmask) * CPK;   // consecutive threads read one pixel's chunk
+                    const int off = pixoff[pix];
+                    if (off >= 0 && ch < cin4) {
+                        const float* p = X + (size_t)off * A.ldx + ch;
+                        if (vec) {
+#pragma unroll
+                            for (int e = 0; e < CPK; e += 4) {
+                                if (ch + e < cin4) {
+                                    const float4 t = __ldg((const float4*)(p + e));
+                                    v[u][e] = t.x; v[u][e + 1] = t.y; v[u][e + 2] = t.z; v[u][e + 3] = t.w;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < CPK; ++e)
+                                if (ch + e < A.Cin) v[u][e] = __ldg(p + e);
+                        }
+                    }
+                }
+            }
+        };
+        auto finish = [&](int c) {
             const int s = g % A.astages;
             if (g >= A.astages) mbar_wait(&a_empty[s], ((g / A.astages) - 1) & 1);
             ++g;
             float4* hi = (float4*)(a_base + (size_t)s * A.a_stage_bytes);
             float4* lo = (float4*)(a_base + (size_t)s * A.a_stage_bytes + a_half);
-            const int cbase = c * CHUNK;
-            // the last chunk may need only the first MMA K step: K chunks 0,1 are stored first, so just stop early
-            const int ksh = (c == A.nchunks - 1 && A.last_ksteps == 1) ? 1 : 2;   // log2(K chunks to fill)
+            int ksh;
+            const int total = chunk_shape(c, ksh);
             const int kmask = (1 << ksh) - 1;
-            const int total = A.NPIX << ksh;
-            for (int q0 = threadIdx.x; q0 < total; q0 += CV_LOADERS * U) {
-                float v[U][CPK];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int q = q0 + u * CV_LOADERS;
+            for (int u = 0; u < UMAX; ++u) {
+                const int q = threadIdx.x + u * CV_LOADERS;
+                if (q < total) {
+                    const int o = (q & kmask) * A.NPIX + (q >> ksh);
+                    if (PREC == PREC_F16X3) {
+                        unsigned hw[4], lw[4];
 #pragma unroll
-                    for (int e = 0; e < CPK; ++e) v[u][e] = 0.f;
-                    if (q < total) {
-                        const int pix = q >> ksh, ch = cbase + (q & kmask) * CPK;   // consecutive threads read one pixel's chunk
-                        const int off = pixoff[pix];
-                        if (off >= 0 && ch < cin4) {
-                            const float* p = X + (size_t)off * A.ldx + ch;
-                            if (vec) {
-#pragma unroll
-                                for (int e = 0; e < CPK; e += 4) {
-                                    if (ch + e < cin4) {
-                                        const float4 t = __ldg((const float4*)(p + e));
-                                        v[u][e] = t.x; v[u][e + 1] = t.y; v[u][e + 2] = t.z; v[u][e + 3] = t.w;
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < CPK; ++e)
-                                    if (ch + e < A.Cin) v[u][e] = __ldg(p + e);
-                            }
+                        for (int e = 0; e < 8; e += 2) {
+                            const float x0 = v[u][e] * xs, x1 = v[u][e + 1] * xs;
+                            amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+                            const __half2 h = __floats2half2_rn(x0, x1);
+                            const float2 hf = __half22float2(h);
+                            const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                            hw[e >> 1] = *(const unsigned*)&h;
+                            lw[e >> 1] = *(const unsigned*)&l;
                         }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int q = q0 + u * CV_LOADERS;
-                    if (q < total) {
-                        const int o = (q & kmask) * A.NPIX + (q >> ksh);
-                        if (PREC == PREC_F16X3) {
-                            unsigned hw[4], lw[4];
-#pragma unroll
-                            for (int e = 0; e < 8; e += 2) {
-                                const float x0 = v[u][e] * xs, x1 = v[u][e + 1] * xs;
-                                amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
-                                const __half2 h = __floats2half2_rn(x0, x1);
-                                const float2 hf = __half22float2(h);
-                                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                                hw[e >> 1] = *(const unsigned*)&h;
-                                lw[e >> 1] = *(const unsigned*)&l;
-                            }
-                            hi[o] = make_float4(__uint_as_float(hw[0]), __uint_as_float(hw[1]), __uint_as_float(hw[2]), __uint_as_float(hw[3]));
-                            lo[o] = make_float4(__uint_as_float(lw[0]), __uint_as_float(lw[1]), __uint_as_float(lw[2]), __uint_as_float(lw[3]));
-                        } else {
-                            float4 h;
-                            h.x = to_tf32_rna(v[u][0]); h.y = to_tf32_rna(v[u][1]); h.z = to_tf32_rna(v[u][2]); h.w = to_tf32_rna(v[u][3]);
-                            hi[o] = h;
-                            lo[o] = make_float4(v[u][0] - h.x, v[u][1] - h.y, v[u][2] - h.z, v[u][3] - h.w);
-                        }
+                        hi[o] = make_float4(__uint_as_float(hw[0]), __uint_as_float(hw[1]), __uint_as_float(hw[2]), __uint_as_float(hw[3]));
+                        lo[o] = make_float4(__uint_as_float(lw[0]), __uint_as_float(lw[1]), __uint_as_float(lw[2]), __uint_as_float(lw[3]));
+                    } else {
+                        float4 h;
+                        h.x = to_tf32_rna(v[u][0]); h.y = to_tf32_rna(v[u][1]); h.z = to_tf32_rna(v[u][2]); h.w = to_tf32_rna(v[u][3]);
+                        hi[o] = h;
+                        lo[o] = make_float4(v[u][0] - h.x, v[u][1] - h.y, v[u][2] - h.z, v[u][3] - h.w);
                     }
                 }
             }
             fence_async_smem();          // generic-proxy stores -> visible to the tensor-core (async) proxy
             mbar_arrive(&a_full[s]);
         };
-
-        TileCoord prev{0, 0, 0};
-        int j = 0;
-        for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, ++j) {
-            const TileCoord T = tile_coord(A, tile);
-            // region -> image mapping of this tile (all loaders are done with the previous table)
+        // region -> image mapping of a tile (the table is shared by the loaders: barrier before and after the rewrite)
+        auto map_tile = [&](const TileCoord& T) {
             asm volatile("bar.sync 1, %0;" ::"n"(CV_LOADERS) : "memory");
             for (int pix = threadIdx.x; pix < A.NPIX; pix += CV_LOADERS) {
                 const int r = pix / A.RW, cc = pix - r * A.RW;
@@ -505,16 +529,37 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                 pixoff[pix] = ok ? gy * A.W + gx : -1;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(CV_LOADERS) : "memory");
-            const float* X = A.x + (size_t)T.img * A.H * A.W * A.ldx;
-            // chunks that fit the ring first (never blocks on this tile's own MMA), then the previous tile's epilogue
-            // (which frees the accumulator this tile's MMA may be waiting for), then the rest
-            const int ahead = min(A.nchunks, A.astages);
-            for (int c = 0; c < ahead; ++c) load_chunk(c, X);
-            if (j > 0) epilogue(j - 1, prev);
-            for (int c = ahead; c < A.nchunks; ++c) load_chunk(c, X);
-            prev = T;
+        };
+
+        // Software pipeline over the (tile, chunk) stream: store chunk k, put chunk k+1's loads in flight, and run the
+        // previous tile's epilogue under them.  The epilogue of tile j-1 comes after chunk e_at of tile j is stored: late
+        // enough that the loads are in flight, early enough that tile j's MMAs never wait for it while the loaders wait
+        // for those MMAs to free a ring stage.
+        const int e_at = min(A.nchunks, A.astages) - 1;
+        TileCoord curT = tile_coord(A, blockIdx.x), prevT = curT, nextT = curT;
+        const float* X = A.x + (size_t)curT.img * A.H * A.W * A.ldx;
+        int j = 0;
+        if ((int)blockIdx.x < A.ntiles) {
+            map_tile(curT);
+            issue(0, X);
         }
-        if (j > 0) epilogue(j - 1, prev);
+        for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, ++j) {
+            for (int c = 0; c < A.nchunks; ++c) {
+                finish(c);
+                if (c + 1 < A.nchunks) {
+                    issue(c + 1, X);
+                } else if (tile + (int)gridDim.x < A.ntiles) {
+                    nextT = tile_coord(A, tile + gridDim.x);
+                    X = A.x + (size_t)nextT.img * A.H * A.W * A.ldx;
+                    map_tile(nextT);
+                    issue(0, X);
+                }
+                if (c == e_at && j > 0) epilogue(j - 1, prevT);
+            }
+            prevT = curT;
+            curT = nextT;
+        }
+        if (j > 0) epilogue(j - 1, prevT);
         if (PREC == PREC_F16X3 && !(amax <= 65504.f) && A.overflow) atomicOr(A.overflow, 1);
     } else if (warp == CV_LOADER_WARPS) {
         // ================= weight producer =================
@@ -614,6 +659,7 @@ static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
         a.RH = CV_ROWS + a.KH - 1;
         a.NPIX = a.RW * a.RH;
         a.a_stage_bytes = (unsigned)a.NPIX * CV_KCHUNKS * 16u * 2u;    // hi + lo
+        if (a.NPIX * CV_KCHUNKS > CV_LOADERS * CV_UMAX) continue;          // the loaders keep a whole K chunk in registers (UMAX)
         const size_t misc = 512 + (size_t)a.NPIX * 4 + 1024 + 16;
         const int min_b = std::min(2, a.nchunks * taps);
         if (misc + 2 * (size_t)a.a_stage_bytes + (size_t)min_b * a.b_stage_bytes > budget) continue;
