@@ -221,7 +221,7 @@ except ImportError:
 DEFAULT_WORKLOAD = os.environ.get("FVFI_BENCH_WORKLOAD", "pipeline" if "pipeline" in WORKLOADS else "adacof")
 
 
-def run_reference(args):
+def run_reference(args, emit=print):
     """Reference arm: the path on the host CPU, all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -248,11 +248,20 @@ def run_reference(args):
                          "kind": getattr(wl, "cpu_kind", "port"), "sample": sample},
         "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
+def _quiet_stdout():
+    """Only the JSON line may reach stdout (NCCL / library banners go to stderr): returns a writer for the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return lambda text: os.write(real, (text + "\n").encode())
+
+
 def main():
+    emit = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -266,7 +275,7 @@ def main():
     args.warmup = max(args.warmup, 0)
 
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -343,7 +352,7 @@ def main():
                                 "kind": getattr(wl, "cpu_kind", "port"), "sample": sample,
                                 "seconds": round(dt, 2)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()

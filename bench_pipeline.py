@@ -37,7 +37,7 @@ class PipelineWorkload:
         self.launches_per_step = None
         self.stage_ms = {}
         self.nsteps = 0
-        self.config_extra = {"tf32_convs": self.tf32, "convs": "tcgen05 3xTF32 implicit GEMM (csrc/conv_tc.cu)",
+        self.config_extra = {"tf32_convs": self.tf32, "convs": "tcgen05 implicit GEMM, %s operand split, persistent (csrc/conv_tc.cu)" % os.environ.get("FVFI_CONV_PREC", "f16x3"),
                              "phase_plane_chunk": self.pipe.phase_net.plane_chunk,
                              "sub_batch": self.pipe.max_batch}
 
@@ -58,37 +58,89 @@ class PipelineWorkload:
             self.nsteps += 1
         self._pending = []
 
-    def roofline(self, peak, peak_src):
-        """Dominant hand-written HBM-bound kernel inside the step: the fused AdaCoFNet synthesis kernel
-        (two warps + blend + mask), timed alone with CUDA events on the same inputs."""
+    def _peaks(self):
+        import json
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")
+        if os.path.exists(path):
+            d = json.load(open(path))
+            return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1399.0))), "measured sustained bf16 (MEASURED_PEAKS.json)"
+        return 1400.0, "fallback (B200_PROFILING.md, sustained)"
+
+    def _time_conv(self):
+        """Per-launch CUDA events around every tcgen05 convolution of ONE extra pipeline step: the step's dominant
+        kernel (conv_split_kernel, ~60 % of the step).  achieved = algorithmic FLOPs (2*B*H*W*Cin*Cout*K*K) / time."""
+        from fvfi import conv as tc
         torch = self.torch
-        self._collect()
+        tc.timing = []
+        self.pipe.timing = None
+        self.pipe(self.d1, self.d2)
+        torch.cuda.synchronize()
+        rec, tc.timing = tc.timing, None
+        flops = sum(r[0] for r in rec)
+        ms = sum(r[1].elapsed_time(r[2]) for r in rec)
+        return flops, ms, sum(r[3] for r in rec)
+
+    def _time_hbm_kernels(self, peak):
+        """The hand-written HBM-bound kernels of the step, each timed alone with CUDA events on the step's shapes."""
+        torch = self.torch
         from fvfi import adacof
-        B, H, W, F = self.B, 1088, 1920, 5
+        B, H, W = min(self.B, self.pipe.max_batch), 1088, 1920
         g = torch.Generator(device=self.device).manual_seed(0)
         mk = lambda *s: torch.rand(s, device=self.device, generator=g)
         i1, i2 = mk(B, 3, H + 4, W + 4), mk(B, 3, H + 4, W + 4)
         w1 = torch.softmax(mk(B, 25, H, W), 1)
         a1, b1 = mk(B, 25, H, W) - 0.5, mk(B, 25, H, W) - 0.5
         occ = mk(B, 1, H, W)
-        for _ in range(2):
-            adacof.adacofnet_warp_blend(i1, i2, w1, a1, b1, w1, b1, a1, occ, 1, want_t=False)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        reps = 5
-        for _ in range(reps):
-            adacof.adacofnet_warp_blend(i1, i2, w1, a1, b1, w1, b1, a1, occ, 1, want_t=False)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
+
+        def timeit(fn, reps=5):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        out = []
+        ms = timeit(lambda: adacof.adacofnet_warp_blend(i1, i2, w1, a1, b1, w1, b1, a1, occ, 1, want_t=False))
         px = B * H * W
         nbytes = 4 * (6 * 25 * px + 2 * 3 * B * (H + 4) * (W + 4) + px + 3 * px + px)
-        ach = nbytes / (ms * 1e-3) / 1e9
+        out.append({"kernel": "adacof_fwd_tiled<5,4,2> (two warps + blend + uncertainty, smooth offsets)", "bound": "hbm",
+                    "achieved": round(nbytes / ms / 1e6, 1), "unit": "GB/s", "frac": round(nbytes / ms / 1e6 / peak, 4),
+                    "ms_per_launch": round(ms, 4), "algorithmic_bytes_per_launch": nbytes})
+        del i1, i2, w1, a1, b1, occ
+        N = 12 * B
+        x = mk(N, self.H, self.W)
+        pyr = self.pipe.pyr
+        vals = pyr.filter(x, want_high=False)
+        msd = timeit(lambda: pyr.filter(x, want_high=False), 3)
+        msr = timeit(lambda: pyr.inv_filter_sparse(vals, use_high=False), 3)
+        pb = 72 * self.H * self.W * N - 4 * self.H * self.W * N      # 72 HW per plane-op minus the skipped high residual
+        for name, t in (("pyramid decompose (k_rows_fwd/k_cols_fwd + per level k_cols_inv_decomp/k_rows_inv)", msd),
+                        ("pyramid reconstruct (per level k_rows_fwd/k_cols_fwd + k_cols_inv_gather/k_rows_inv)", msr)):
+            out.append({"kernel": name, "bound": "hbm", "achieved": round(pb / t / 1e6, 1), "unit": "GB/s",
+                        "frac": round(pb / t / 1e6 / peak, 4), "ms_per_call": round(t, 4), "planes": N,
+                        "algorithmic_bytes_per_call": pb})
+        return out
+
+    def roofline(self, peak, peak_src):
+        """Dominant kernel of the step = the tcgen05 convolution (tensor-bound).  `achieved` counts ALGORITHMIC FLOPs
+        (one multiply-add per tap, channel pair and pixel); every one of them is executed as three fp16 tensor-core
+        products (3xFP16 split), so the tensor pipe runs 3x that rate (`mma_frac`).  The hand-written HBM-bound kernels
+        of the step (fused AdaCoF synthesis, pyramid) follow in `other_kernels`."""
+        self._collect()
+        tpeak, tsrc = self._peaks()
+        flops, ms, launches = self._time_conv()
+        ach = flops / (ms * 1e-3) / 1e12
         stages = {k: round(v / max(self.nsteps, 1), 3) for k, v in self.stage_ms.items()}
-        return {"bound": "hbm", "kernel": "adacof_fwd_tiled<5,4,2> (fused two-warp + blend + uncertainty)",
-                "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
-                "peak_source": peak_src, "ms_per_launch": round(ms, 4), "algorithmic_bytes_per_launch": nbytes,
-                "offsets": "smooth (|offset| < 0.5), as a random-init KernelEstimation produces",
+        step_ms = sum(stages.values())
+        return {"bound": "tensor", "kernel": "conv_split_kernel<ACT, PREC_F16X3> (all %d launches of one step)" % launches,
+                "achieved": round(ach, 1), "peak": tpeak, "unit": "TFLOP/s", "frac": round(ach / tpeak, 4),
+                "mma_frac": round(3 * ach / tpeak, 4), "traffic": None, "peak_source": tsrc,
+                "ms_per_step_in_kernel": round(ms, 2), "share_of_step": round(ms / max(step_ms, 1e-9), 3),
+                "algorithmic_flops_per_step": flops,
+                "other_kernels": self._time_hbm_kernels(peak), "hbm_peak": peak, "hbm_peak_source": peak_src,
                 "stage_ms_per_step": stages}
 
     def e2e(self, steps):

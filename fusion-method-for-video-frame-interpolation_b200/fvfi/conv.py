@@ -1,5 +1,5 @@
 """Tensor-core convolution op (C-ABI: fvfi_conv2d_* in include/fvfi.h): stride-1 "same" convolutions of
-the three networks on tcgen05 with 3xTF32 error compensation (fp32-grade results), NHWC activations
+the three networks on tcgen05 with split-operand error compensation (3xFP16 default / 3xTF32; fp32-grade results), NHWC activations
 (torch ``channels_last``), fused bias + activation.
 
 ``Conv2dTC.apply_module(conv, x, act)`` runs an ``nn.Conv2d`` (weights stay in the module, so reference
@@ -31,6 +31,7 @@ def use_tc(x):
 
 ACT = {None: 0, "none": 0, "relu": 1, "elu": 2, "tanh": 3, "sigmoid": 4, "softmax": 5}
 _pack_cache = {}
+timing = None    # set to a list to collect (flops, start_event, end_event) per convolution launch (bench.py roofline)
 
 
 def _packed(weight):
@@ -86,10 +87,17 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
     pad_mode = {"zeros": 0, "reflect": 1}[padding_mode]
     b = None if bias is None else bias.detach().contiguous().float()
     with torch.cuda.device(x.device):
-        for (o, n, buf, _) in _packed(weight):
+        parts = _packed(weight)
+        if timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        for (o, n, buf, _) in parts:
             _lib.check(L.fvfi_conv2d_nhwc(xc.data_ptr(), ldx, buf.data_ptr(), None if b is None else b.data_ptr() + 4 * o,
                                           out.data_ptr() + 4 * o, ldy, B, H, W, Cin, n, KH, KW, pad_mode, ACT[act],
                                           1 if nchw_out else (2 if pad_out else 0), precision, _lib.stream_ptr()))
+        if timing is not None:
+            e1.record()
+            timing.append((2.0 * B * H * W * Cin * Cout * KH * KW, e0, e1, len(parts), (B, Cin, Cout, KH, H, W, act)))
     return out
 
 

@@ -170,6 +170,26 @@ def test_phase_epilogue_accuracy():
         assert float(vals.phase[l].abs().max()) <= np.pi + 1e-6
 
 
+def test_4k_plan_round_trip():
+    """BASELINE.json configs[3]: 3840x2160, height 19.  Properties that do not need the (slow) oracle at this size:
+    perfect reconstruction, linearity, level shapes of the ceil((n - 0.5)/sqrt 2) rule."""
+    from fvfi.pyramid import Pyramid
+    from fvfi.utils import calc_pyr_height
+    H, W = 2160, 3840
+    img = _img(1, H, W, seed=11).cuda()
+    height = calc_pyr_height(img)
+    assert height == 19
+    pyr = Pyramid(height=height, nbands=4, scale_factor=S2, device=torch.device("cuda"))
+    vals = pyr.filter(img)
+    sizes = ss.level_sizes(H, W, height, S2)
+    assert [tuple(p.shape[2:]) for p in vals.phase] == [tuple(s) for s in sizes[:-1]]
+    rec = pyr.inv_filter(vals)
+    assert float((rec - img).abs().max()) <= 6e-5
+    v3 = pyr.filter(3 * img)
+    for l in (0, 1, 2, 7):
+        assert float((v3.amplitude[l] - 3 * vals.amplitude[l]).abs().max()) <= 2e-4 * float(vals.amplitude[l].max())
+
+
 def test_errors():
     from fvfi import FvfiError
     from fvfi.pyramid import Pyramid
