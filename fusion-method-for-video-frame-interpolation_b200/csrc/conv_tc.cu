@@ -198,19 +198,38 @@ __device__ __forceinline__ unsigned long long make_desc(unsigned saddr, unsigned
     return d;
 }
 
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): one full 32-byte sector per lane and instruction
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
 __device__ __forceinline__ float to_tf32_rna(float x) {
     unsigned r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
 
+// Activations of the epilogue.  exp is the hardware ex2 path (__expf, relative error 2^-21): the absolute error of the
+// results below is <= 1e-6, an order below the convolution's own rounding; inputs are clamped where exp would overflow.
+__device__ __forceinline__ float fast_tanh(float v) {
+    const float t = __expf(2.f * fminf(fmaxf(v, -15.f), 15.f));
+    return __fdividef(t - 1.f, t + 1.f);
+}
+__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.f, 1.f + __expf(-fmaxf(v, -80.f))); }
 template <int ACT>
 __device__ __forceinline__ float apply_act(float v) {
     switch (ACT) {
         case ACT_RELU: return fmaxf(v, 0.f);
-        case ACT_ELU: return v > 0.f ? v : expm1f(v);
-        case ACT_TANH: return tanhf(v);
-        case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        case ACT_ELU: return v > 0.f ? v : __expf(v) - 1.f;
+        case ACT_TANH: return fast_tanh(v);
+        case ACT_SIGMOID: return fast_sigmoid(v);
         default: return v;
     }
 }
@@ -340,6 +359,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
         // leaves room for the rounded-up group (the producer zero-fills the padding channels, see out layout 2)
         const int cin4 = (A.Cin + 3) & ~3;
         const bool vec = ((A.ldx & 3) == 0) && (A.ldx >= cin4) && ((((size_t)A.x) & 15) == 0);
+        const int cin8 = (A.Cin + 7) & ~7;
+        const bool vec8 = ((A.ldx & 7) == 0) && (A.ldx >= cin8) && ((((size_t)A.x) & 31) == 0);
         for (int n = threadIdx.x; n < A.Npad; n += CV_LOADERS) bias_s[n] = (A.bias && n < A.Cout) ? __ldg(A.bias + n) : 0.f;
         constexpr int CPK = cv_cpk(PREC);
         constexpr int CHUNK = cv_chunk(PREC);
@@ -347,6 +368,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
         const float xs = (float)(1 << CV_X_SHIFT);
         const float oscale = __ldg(A.hdr);                         // exact power of two (1 for PREC_TF32X3)
         const bool vec_out = (A.cout_store & 3) == 0 && (A.ldy & 3) == 0 && ((((size_t)A.y) & 15) == 0);
+        const bool vec_out8 = (A.cout_store & 7) == 0 && (A.ldy & 7) == 0 && ((((size_t)A.y) & 31) == 0);
         const size_t plane = (size_t)A.H * A.W;
         const int quarter = warp & 3, half = warp >> 2;            // a warp reads TMEM lanes 32*(warp % 4) .. +31
         const int m = quarter * 32 + lane;                         // accumulator row = TMEM lane
@@ -373,8 +395,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     const float z0 = fmaf(__uint_as_float(r[i]), oscale, b4.x), z1 = fmaf(__uint_as_float(r[i + 1]), oscale, b4.y);
                     const float z2 = fmaf(__uint_as_float(r[i + 2]), oscale, b4.z), z3 = fmaf(__uint_as_float(r[i + 3]), oscale, b4.w);
                     if (ACT == ACT_SOFTMAX) {
-                        v[i] = expf(z0 - smax) * sinv; v[i + 1] = expf(z1 - smax) * sinv;
-                        v[i + 2] = expf(z2 - smax) * sinv; v[i + 3] = expf(z3 - smax) * sinv;
+                        v[i] = __expf(z0 - smax) * sinv; v[i + 1] = __expf(z1 - smax) * sinv;
+                        v[i + 2] = __expf(z2 - smax) * sinv; v[i + 3] = __expf(z3 - smax) * sinv;
                     } else {
                         v[i] = apply_act<ACT>(z0); v[i + 1] = apply_act<ACT>(z1);
                         v[i + 2] = apply_act<ACT>(z2); v[i + 3] = apply_act<ACT>(z3);
@@ -384,6 +406,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (n0 + i < A.Cout) dst[(size_t)(n0 + i) * plane] = v[i];   // 8 consecutive px per row: full 32 B sectors
+                } else if (vec_out8) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 8)
+                        if (n0 + i < A.cout_store) stg256(dst + n0 + i, v + i);
                 } else if (vec_out) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4)
@@ -407,8 +433,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                         for (int i = 0; i < 16; ++i)
                             if (n0 + i < A.Cout) {
                                 const float z = fmaf(v[i], oscale, bias_s[n0 + i]);
-                                if (z > smax) { ssum = ssum * expf(smax - z); smax = z; }
-                                ssum += expf(z - smax);
+                                if (z > smax) { ssum = ssum * __expf(smax - z); smax = z; }
+                                ssum += __expf(z - smax);
                             }
                     }
                     const float sinv = 1.f / ssum;
@@ -457,7 +483,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     const int off = pixoff[pix];
                     if (off >= 0 && ch < cin4) {
                         const float* p = X + (size_t)off * A.ldx + ch;
-                        if (vec) {
+                        if (vec8 && CPK == 8 && ch + 8 <= cin8) {
+                            ldg256(p, v[u]);
+                        } else if (vec) {
 #pragma unroll
                             for (int e = 0; e < CPK; e += 4) {
                                 if (ch + e < cin4) {

@@ -114,7 +114,8 @@ class KernelEstimation(torch.nn.Module):
         pooling / bilinear upsampling / softmax run on NHWC tensors, the seven heads are returned NCHW-contiguous
         (the warp kernel streams each coefficient plane)."""
         run = self._seq_tc
-        x = tc.to_nhwc(torch.cat([rfield0, rfield2], 1))
+        # 6 input channels padded to 8 (zeros): 16-byte loads in the first convolution
+        x = tc.to_nhwc(torch.cat([rfield0, rfield2, rfield0.new_zeros((rfield0.shape[0], 2) + tuple(rfield0.shape[2:]))], 1))
         c1 = run(self.moduleConv1, x)
         c2 = run(self.moduleConv2, self.modulePool1(c1))
         del c1

@@ -18,6 +18,9 @@ CASES = [
     (1, 128, 256, 3, 20, 28, "zeros", "relu"),
     (1, 512, 512, 3, 17, 30, "zeros", "relu"),
     (2, 32, 64, 5, 70, 130, "reflect", "relu"),
+    (2, 32, 3, 1, 40, 56, "zeros", None),
+    (1, 24, 5, 3, 31, 45, "reflect", "elu"),
+    (1, 6, 2, 3, 20, 20, "zeros", "relu"),
 ]
 
 
