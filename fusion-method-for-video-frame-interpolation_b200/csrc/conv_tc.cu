@@ -65,6 +65,7 @@ struct ConvArgs {
     int cout_store;        // NHWC channels written per pixel: Cout, or round16(Cout) with the padding zero-filled
     int MT, RW, RH, NPIX;  // tiles per CTA, staged region geometry
     int nchunks, last_ksteps, astages, bstages, tmem_cols;
+    int wide, tcols;       // WIDE MMA pairing (Npad <= 32); TMEM columns per accumulator tile (Npad or 2*Npad)
     int nacc;              // TMEM accumulator buffers (2 when they fit: epilogue of tile j-1 overlaps the MMAs of tile j)
     int tiles_x, tiles_y, ntiles;
     unsigned a_stage_bytes, b_stage_bytes;
@@ -128,24 +129,31 @@ __device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, unsigned long long 
 // A single asm block: the tensor core consumes an MMA of N <= 128 every 40-64 cycles, which one warp can only sustain
 // if the issue stream is ~3 instructions per MMA (measured: a C++ loop with per-MMA descriptor arithmetic and elect
 // costs ~120 cycles per MMA).  Tile t: A descriptor + 8*t (eight pixels = 8 x 16 B), TMEM columns + t*Npad.
+// %4 = B_hi descriptor, %5 = B_lo descriptor, %6 = instruction descriptor (N = Npad), %8 = instruction descriptor with
+// N = 2*Npad.  WIDE (Npad <= 32): the packed weights hold [B_hi; B_lo] as one 2*Npad-row operand, so  A_hi x [B_hi; B_lo]
+// is ONE MMA writing two accumulators (columns [0,Npad) and [Npad,2Npad), summed by the epilogue) and A_lo x B_hi a second
+// one: two instead of three reads of the 4 KB A tile, which is what bounds an SS-mode MMA with N <= 64.
 #define FVFI_MMA3(KIND, D, AL, AH)                                                        \
     "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AL ", %4, %6, pa;\n\t"        \
     "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AH ", %5, %6, pt;\n\t"        \
     "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AH ", %4, %6, pt;\n\t"
-#define FVFI_KSTEP_BODY(KIND)                                                                                          \
+#define FVFI_MMA2W(KIND, D, AL, AH)                                                       \
+    "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AH ", %4, %8, pa;\n\t"        \
+    "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AL ", %4, %6, pt;\n\t"
+#define FVFI_KSTEP_BODY(KIND, MM)                                                                                      \
     if (MT == 1) {                                                                                                     \
         asm volatile(                                                                                                  \
             "{\n\t.reg .pred pe, pa, pt;\n\t"                                                                          \
             "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"                       \
-            FVFI_MMA3(KIND, "%0", "%2", "%3") "}"                                                                      \
-            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc) : "memory");                  \
+            MM(KIND, "%0", "%2", "%3") "}"                                                                             \
+            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc), "r"(idesc2) : "memory");     \
     } else if (MT == 2) {                                                                                              \
         asm volatile(                                                                                                  \
             "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 al1, ah1;\n\t.reg .b32 d1;\n\t"                                  \
             "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"                       \
             "add.u64 al1, %2, 8;\n\tadd.u64 ah1, %3, 8;\n\tadd.u32 d1, %0, %1;\n\t"                                    \
-            FVFI_MMA3(KIND, "%0", "%2", "%3") FVFI_MMA3(KIND, "d1", "al1", "ah1") "}"                                  \
-            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc) : "memory");                  \
+            MM(KIND, "%0", "%2", "%3") MM(KIND, "d1", "al1", "ah1") "}"                                                \
+            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc), "r"(idesc2) : "memory");     \
     } else {                                                                                                           \
         asm volatile(                                                                                                  \
             "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 al1, ah1, al2, ah2, al3, ah3;\n\t.reg .b32 d1, d2, d3;\n\t"      \
@@ -153,17 +161,19 @@ __device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, unsigned long long 
             "add.u64 al1, %2, 8;\n\tadd.u64 ah1, %3, 8;\n\tadd.u32 d1, %0, %1;\n\t"                                    \
             "add.u64 al2, %2, 16;\n\tadd.u64 ah2, %3, 16;\n\tadd.u32 d2, d1, %1;\n\t"                                  \
             "add.u64 al3, %2, 24;\n\tadd.u64 ah3, %3, 24;\n\tadd.u32 d3, d2, %1;\n\t"                                  \
-            FVFI_MMA3(KIND, "%0", "%2", "%3") FVFI_MMA3(KIND, "d1", "al1", "ah1") FVFI_MMA3(KIND, "d2", "al2", "ah2")   \
-            FVFI_MMA3(KIND, "d3", "al3", "ah3") "}"                                                                    \
-            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc) : "memory");                  \
+            MM(KIND, "%0", "%2", "%3") MM(KIND, "d1", "al1", "ah1") MM(KIND, "d2", "al2", "ah2")                       \
+            MM(KIND, "d3", "al3", "ah3") "}"                                                                           \
+            ::"r"(d), "r"(np), "l"(al), "l"(ah), "l"(bh), "l"(bl), "r"(idesc), "r"(acc), "r"(idesc2) : "memory");     \
     }
-template <int MT, int PREC>
+// np = TMEM columns per accumulator tile (Npad, or 2*Npad when WIDE)
+template <int MT, int PREC, bool WIDE>
 __device__ __forceinline__ void tc_mma_kstep(unsigned d, unsigned np, unsigned long long al, unsigned long long ah,
-                                             unsigned long long bh, unsigned long long bl, unsigned idesc, unsigned acc) {
+                                             unsigned long long bh, unsigned long long bl, unsigned idesc, unsigned acc,
+                                             unsigned idesc2) {
     if (PREC == PREC_F16X3) {
-        FVFI_KSTEP_BODY("f16")
+        if (WIDE) { FVFI_KSTEP_BODY("f16", FVFI_MMA2W) } else { FVFI_KSTEP_BODY("f16", FVFI_MMA3) }
     } else {
-        FVFI_KSTEP_BODY("tf32")
+        if (WIDE) { FVFI_KSTEP_BODY("tf32", FVFI_MMA2W) } else { FVFI_KSTEP_BODY("tf32", FVFI_MMA3) }
     }
 }
 __device__ __forceinline__ void tc_ld16_issue(unsigned taddr, unsigned* r) {
@@ -242,7 +252,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {   // torch 'reflect': 
     return m < n ? m : period - m;
 }
 
-// ---- weight packing: OIHW fp32 -> header + [chunk][tap][hi|lo][kc(4)][n(Npad)][16 bytes] --------------------------
+// ---- weight packing: OIHW fp32 -> header + [chunk][tap][kc(4)][hi|lo][n(Npad)][16 bytes] --------------------------
 // header[0] = output scale (exact inverse of the operand scales), [1] = weight scale, [2] = precision.
 __global__ void conv_weight_scale_kernel(const float* __restrict__ w, size_t count, float* __restrict__ hdr, int prec) {
     __shared__ float red[32];
@@ -280,8 +290,8 @@ __global__ void conv_pack_weights_kernel(const float* __restrict__ w, float* __r
         size_t t = q;
         const int e = (int)(t % CPK); t /= CPK;
         const int n = (int)(t % Npad); t /= Npad;
+        const int lo = (int)(t % 2); t /= 2;                  // [B_hi rows; B_lo rows] form one 2*Npad-row operand per K chunk
         const int kc = (int)(t % CV_KCHUNKS); t /= CV_KCHUNKS;
-        const int lo = (int)(t % 2); t /= 2;
         const int tap = (int)(t % taps); t /= taps;
         const int chunk = (int)t;
         const int c = chunk * (CV_KCHUNKS * CPK) + kc * CPK + e;
@@ -335,7 +345,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
     const int taps = A.KH * A.KW;
     const unsigned a_half = A.a_stage_bytes / 2;             // hi | lo halves of an A stage
     const int nacc = A.nacc;
-    const unsigned acc_cols = (unsigned)(A.MT * A.Npad);
+    const unsigned acc_cols = (unsigned)(A.MT * A.tcols);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < A.astages; ++s) { mbar_init(&a_full[s], CV_LOADERS); mbar_init(&a_empty[s], 1); }
@@ -383,7 +393,16 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             const int orow = T.y0 + (m >> 3);
             const unsigned tq = tmem + ((unsigned)(quarter * 32) << 16) + (unsigned)buf * acc_cols;
             // bias + activation + store of one 16-column block of accumulator tile t (smax / sinv: softmax only)
-            auto emit = [&](int t, int n0, const unsigned* r, float smax, float sinv) {
+            // 16 accumulator columns of this thread's row; WIDE: the two partial accumulators (A_hi B_hi + A_lo B_hi, A_hi B_lo)
+            auto ld_acc16 = [&](unsigned taddr, float* v) {
+                unsigned r0[16], r1[16];
+                tc_ld16_issue(taddr, r0);
+                if (A.wide) tc_ld16_issue(taddr + (unsigned)A.Npad, r1);
+                tc_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]) + (A.wide ? __uint_as_float(r1[i]) : 0.f);
+            };
+            auto emit = [&](int t, int n0, const float* r, float smax, float sinv) {
                 const int ocol = T.x0 + t * 8 + (m & 7);
                 if (!(orow < A.H && ocol < A.W)) return;
                 float* dst = A.out_nchw ? A.y + (size_t)T.img * A.Cout * plane + (size_t)orow * A.W + ocol
@@ -392,8 +411,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
                     const float4 b4 = *(const float4*)(bias_s + n0 + i);        // smem broadcast
-                    const float z0 = fmaf(__uint_as_float(r[i]), oscale, b4.x), z1 = fmaf(__uint_as_float(r[i + 1]), oscale, b4.y);
-                    const float z2 = fmaf(__uint_as_float(r[i + 2]), oscale, b4.z), z3 = fmaf(__uint_as_float(r[i + 3]), oscale, b4.w);
+                    const float z0 = fmaf(r[i], oscale, b4.x), z1 = fmaf(r[i + 1], oscale, b4.y);
+                    const float z2 = fmaf(r[i + 2], oscale, b4.z), z3 = fmaf(r[i + 3], oscale, b4.w);
                     if (ACT == ACT_SOFTMAX) {
                         v[i] = __expf(z0 - smax) * sinv; v[i + 1] = __expf(z1 - smax) * sinv;
                         v[i + 2] = __expf(z2 - smax) * sinv; v[i + 3] = __expf(z3 - smax) * sinv;
@@ -424,11 +443,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                 // the two warps of a lane quarter take whole tiles (a pixel's softmax needs every channel)
                 for (int t = 0; t < A.MT; ++t) {
                     if (A.MT > 1 ? ((t & 1) != half) : (half != 0)) continue;
-                    const unsigned tbase = tq + (unsigned)(t * A.Npad);
+                    const unsigned tbase = tq + (unsigned)(t * A.tcols);
                     float smax = -INFINITY, ssum = 0.f;
                     for (int n0 = 0; n0 < A.Npad; n0 += 16) {          // pass 1 over TMEM: channel max and sum(exp)
                         float v[16];
-                        tc_ld16(tbase + n0, v);
+                        tc_ld16(tbase + n0, v);          // softmax layers never use the WIDE pairing
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
                             if (n0 + i < A.Cout) {
@@ -439,9 +458,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     }
                     const float sinv = 1.f / ssum;
                     for (int n0 = 0; n0 < A.Npad; n0 += 16) {
-                        unsigned r[16];
-                        tc_ld16_issue(tbase + n0, r);
-                        tc_ld_wait();
+                        float r[16];
+                        tc_ld16(tbase + n0, r);
                         emit(t, n0, r, smax, sinv);
                     }
                 }
@@ -449,9 +467,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                 // the two warps of a lane quarter take alternate 16-column blocks
                 for (int t = 0; t < A.MT; ++t)
                     for (int n0 = ((t & 1) != half) ? 16 : 0; n0 < A.Npad; n0 += 32) {
-                        unsigned r[16];
-                        tc_ld16_issue(tq + (unsigned)(t * A.Npad + n0), r);
-                        tc_ld_wait();
+                        float r[16];
+                        ld_acc16(tq + (unsigned)(t * A.tcols + n0), r);
                         emit(t, n0, r, 0.f, 1.f);
                     }
             }
@@ -610,8 +627,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             const unsigned fmt = (PREC == PREC_F16X3) ? 0u : 2u;
             const unsigned idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(A.Npad >> 3) << 17) | ((128u >> 4) << 24);
             const unsigned a_lbo = (unsigned)A.NPIX * 16u, a_sbo = (unsigned)A.RW * 16u;
-            const unsigned b_lbo = (unsigned)A.Npad * 16u, b_sbo = 128u;
-            const unsigned b_half = A.b_stage_bytes / 2;
+            const unsigned b_lbo = 2u * (unsigned)A.Npad * 16u, b_sbo = 128u;     // K chunks are [hi rows; lo rows] apart
+            const unsigned b_half = (unsigned)A.Npad * 16u;                        // B_lo rows follow the B_hi rows
+            const unsigned idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(A.Npad >> 2) << 17) | ((128u >> 4) << 24);
             // descriptors = constant part + (byte offset >> 4) in the 14-bit start-address field (smem < 256 KB: no carry)
             const unsigned long long a_desc0 = make_desc(0, a_lbo, a_sbo), b_desc0 = make_desc(0, b_lbo, b_sbo);
             const unsigned long long a_kstep = (2u * a_lbo) >> 4, b_kstep = (2u * b_lbo) >> 4;
@@ -639,17 +657,16 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                         const unsigned tap_off = (unsigned)(dy * A.RW + dx);             // in 16 B units (one pixel)
                         const unsigned acc_first = (c == 0 && tp == 0) ? 0u : 1u;
                         const unsigned long long dah = a_hi0 + tap_off, dal = a_lo0 + tap_off;
-                        const unsigned np = (unsigned)A.Npad;
-                        if (A.MT == 4) {
-                            tc_mma_kstep<4, PREC>(tacc, np, dal, dah, dbh0, dbl0, idesc, acc_first);
-                            if (two) tc_mma_kstep<4, PREC>(tacc, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
-                        } else if (A.MT == 2) {
-                            tc_mma_kstep<2, PREC>(tacc, np, dal, dah, dbh0, dbl0, idesc, acc_first);
-                            if (two) tc_mma_kstep<2, PREC>(tacc, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
+                        const unsigned np = (unsigned)A.tcols;
+#define FVFI_ISSUE(MTV, W)                                                                                          \
+    tc_mma_kstep<MTV, PREC, W>(tacc, np, dal, dah, dbh0, dbl0, idesc, acc_first, idesc2);                              \
+    if (two) tc_mma_kstep<MTV, PREC, W>(tacc, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u, idesc2);
+                        if (A.wide) {
+                            if (A.MT == 4) { FVFI_ISSUE(4, true) } else if (A.MT == 2) { FVFI_ISSUE(2, true) } else { FVFI_ISSUE(1, true) }
                         } else {
-                            tc_mma_kstep<1, PREC>(tacc, np, dal, dah, dbh0, dbl0, idesc, acc_first);
-                            if (two) tc_mma_kstep<1, PREC>(tacc, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u);
+                            if (A.MT == 4) { FVFI_ISSUE(4, false) } else if (A.MT == 2) { FVFI_ISSUE(2, false) } else { FVFI_ISSUE(1, false) }
                         }
+#undef FVFI_ISSUE
                         tc_commit(&b_empty[sb]);           // weights of this (chunk, tap) consumed
                         if (++dx == A.KW) { dx = 0; ++dy; }
                     }
@@ -679,10 +696,13 @@ static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
     const int taps = a.KH * a.KW;
     const size_t budget = 222 * 1024;
     for (int mt = 4; mt >= 1; mt >>= 1) {
-        if (mt * a.Npad > 512) continue;
+        a.wide = (a.Npad <= 32 && a.act != ACT_SOFTMAX) ? 1 : 0;     // measured: pays for N <= 32 (two A reads instead of three), not for N = 64 (smaller tiles)
+        a.tcols = a.wide ? 2 * a.Npad : a.Npad;
+        if (mt * a.tcols > 512) continue;
+        if (a.wide && mt > 1 && 2 * mt * a.tcols > 512) continue;      // small-N layers: keep the accumulator double-buffered
         if (mt > 1 && 8 * (mt / 2) >= a.W) continue;                   // do not over-tile narrow images
         a.MT = mt;
-        a.nacc = (2 * mt * a.Npad <= 512) ? 2 : 1;
+        a.nacc = (2 * mt * a.tcols <= 512) ? 2 : 1;
         a.RW = 8 * mt + a.KW - 1;
         a.RH = CV_ROWS + a.KH - 1;
         a.NPIX = a.RW * a.RH;
@@ -697,7 +717,7 @@ static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
         a.bstages = bs;
         a.astages = std::max(2, std::min(CV_MAX_ASTAGES, as));
         int cols = 32;
-        while (cols < a.nacc * mt * a.Npad) cols <<= 1;
+        while (cols < a.nacc * mt * a.tcols) cols <<= 1;
         a.tmem_cols = cols;
         *smem_bytes = misc + (size_t)a.astages * a.a_stage_bytes + (size_t)a.bstages * a.b_stage_bytes;
         a.tiles_x = ceil_div(a.W, 8 * mt);
