@@ -35,7 +35,7 @@ class FusionPipeline(torch.nn.Module):
                                 ).to(self.device).eval()                                       # :99-103
         self.phase_net.plane_chunk = phase_plane_chunk
         self.stages = None  # set to a dict to capture intermediates (tests)
-        self.max_batch = 4  # frame pairs per sub-batch at full HD (see forward)
+        self.max_batch = 8  # frame pairs per sub-batch at full HD (see forward)
         self.timing = None  # set to a list to collect (stage, start_event, end_event) (bench)
 
     def _tick(self, name):
