@@ -92,8 +92,11 @@ class FusionPipeline(torch.nn.Module):
         self._tick('pyr.inv_filter(3 planes/frame)')
         phase_pred = transform.lab2rgb(lab_pred)                                                # :192
         # uncertainty maps (:197-225)
+        # only level 0 (h_freq) and the six coarsest levels + low pass (freq_diff) of these pyramids are ever read
+        L = pyr.height - 2
+        used = sorted(set([0]) | set(range(L - 6, L)))
         vals_ada, vals_ph = utils.separate_vals(
-            pyr.filter(torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0)), 2)
+            pyr.filter(torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), levels=used), 2)
         self._tick('lab2rgb+pyr.filter(6 planes/frame)')
         h_freq = pyr.inv_filter_sparse(vals_ada, use_low=False, levels=[0]).reshape(r_shape).mean(1)     # get_last_value_levels(.,1)
         h_freq_ph = pyr.inv_filter_sparse(vals_ph, use_low=False, levels=[0]).reshape(r_shape).mean(1)

@@ -38,8 +38,10 @@ class Pyramid:
     def _plan(self, H, W, device):
         return PyrPlan.get(H, W, self.height, self.nbands, self.scale_factor, device)
 
-    def filter(self, img, want_high=True):
-        """ Psi filter: img [N,H,W] -> DecompValues (layouts of src/train/pyramid.py:48-78). """
+    def filter(self, img, want_high=True, levels=None):
+        """ Psi filter: img [N,H,W] -> DecompValues (layouts of src/train/pyramid.py:48-78).
+        ``levels`` (optional): only these band levels are computed, the others are ``None`` in the result (the
+        uncertainty branch of the recipe reads level 0 and the six coarsest levels only). """
         if not img.is_cuda:
             raise NotImplementedError("fvfi pyramid: CUDA tensors only")
         img = img.contiguous().float()
@@ -48,8 +50,9 @@ class Pyramid:
         nb = self.nbands
         new = lambda *s: torch.empty(s, dtype=torch.float32, device=img.device)
         high = new(N, 1, H, W) if want_high else None
-        phase = [new(N * nb, 1, h, w) for (h, w) in plan.shapes[:-1]]
-        amp = [new(N * nb, 1, h, w) for (h, w) in plan.shapes[:-1]]
+        keep = set(range(plan.L)) if levels is None else set(levels)
+        phase = [new(N * nb, 1, h, w) if l in keep else None for l, (h, w) in enumerate(plan.shapes[:-1])]
+        amp = [new(N * nb, 1, h, w) if l in keep else None for l, (h, w) in enumerate(plan.shapes[:-1])]
         low = new(N, 1, *plan.shapes[-1])
         amp_max = new(plan.L, N)
         with torch.cuda.device(img.device):

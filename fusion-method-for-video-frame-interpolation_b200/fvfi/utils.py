@@ -26,14 +26,15 @@ def get_concat_layers(pyr, vals1, vals2):
 def separate_vals(vals, num_input):
     """utils.py:83-127.  Splits the batch dimension into ``num_input`` per-frame DecompValues (views)."""
     def split(t):
-        return t.reshape(num_input, -1, t.shape[2], t.shape[3])
+        return None if t is None else t.reshape(num_input, -1, t.shape[2], t.shape[3])   # None: level not computed
     low, high = split(vals.low_level), split(vals.high_level)
     ph = [split(p) for p in vals.phase]
     am = [split(a) for a in vals.amplitude]
     out = []
     for i in range(num_input):
         out.append(DecompValues(high_level=high[i].unsqueeze(1), low_level=low[i].unsqueeze(1),
-                                phase=[p[i].unsqueeze(1) for p in ph], amplitude=[a[i].unsqueeze(1) for a in am]))
+                                phase=[None if p is None else p[i].unsqueeze(1) for p in ph],
+                                amplitude=[None if a is None else a[i].unsqueeze(1) for a in am]))
     return out
 
 

@@ -124,3 +124,18 @@ def test_conv_padded_channel_chain(prec):
     r1 = F.relu(F.conv2d(x.double(), w1.double(), b1.double(), padding=1))
     r2 = F.conv2d(F.interpolate(r1, size=(40, 72), mode="bilinear", align_corners=True), w2.double(), b2.double(), padding=1)
     assert y2.shape == (2, 25, 40, 72) and float((y2.double() - torch.softmax(r2, 1)).abs().max()) <= 5e-6
+
+
+def test_conv_full_size_layer_vs_cudnn_fp32():
+    """One KernelEstimation layer at its real size (64 -> 64, 3x3, 544x960, batch 2) against cuDNN's fp32 path
+    (TF32 off): the two fp32-grade implementations agree to 2e-5 of the output range."""
+    from fvfi import conv
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn((2, 64, 544, 960), device="cuda", generator=g).relu_()
+    w = torch.randn((64, 64, 3, 3), device="cuda", generator=g) / 24
+    b = torch.randn((64,), device="cuda", generator=g)
+    y = conv.conv2d(x, w, b, "zeros", "relu")
+    ref = F.relu(F.conv2d(x, w, b, padding=1))
+    assert float((y - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    conv.check_overflow()
