@@ -309,15 +309,28 @@ extern "C" int fvfi_median_filter(const float* in, float* out, int N, int H, int
 // One thread = one output pixel x 4 channels (float4); the output may be a channel slice of a wider NHWC
 // buffer (y_pixel_stride), which is how PhaseNet's 88-channel concat is assembled without torch.cat.
 namespace fvfi {
+__device__ __forceinline__ void ldg256f(const float* p, float* v) {      // sm_100 256-bit global load (one sector per lane)
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256f(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
+// VEC = channels per thread: 8 (256-bit accesses), 4 (128-bit) or 1 (any stride / alignment)
+template <int VEC>
 __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi,
                                                                    int Wi, int Ho, int Wo, int C, int ldx, int ldy,
                                                                    float sy, float sx, int align_corners) {
-    const unsigned c4 = (unsigned)(C + 3) >> 2;
-    const unsigned total = (unsigned)Ho * (unsigned)Wo * c4;      // per image; < 2^32 checked by the launcher
+    const unsigned cg_n = (unsigned)(C + VEC - 1) / VEC;
+    const unsigned total = (unsigned)Ho * (unsigned)Wo * cg_n;      // per image; < 2^32 checked by the launcher
     const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= total) return;
-    const unsigned p = q / c4;
-    const int cg = (int)(q - p * c4);
+    const unsigned p = q / cg_n;
+    const int ch = (int)(q - p * cg_n) * VEC;
     const int oy = (int)(p / (unsigned)Wo), ox = (int)(p - (unsigned)oy * (unsigned)Wo);
     const int n = blockIdx.y;
     // source coordinates exactly as ATen's area_pixel_compute_source_index
@@ -334,26 +347,57 @@ __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* 
     const float ly = fy - (float)y0, lx = fx - (float)x0;
     const float hy = 1.f - ly, hx = 1.f - lx;
     const float* X = x + (size_t)n * Hi * Wi * ldx;
-    const int ch = cg * 4;
     const float* p00 = X + ((size_t)y0 * Wi + x0) * ldx + ch;
     const float* p01 = X + ((size_t)y0 * Wi + x1) * ldx + ch;
     const float* p10 = X + ((size_t)y1 * Wi + x0) * ldx + ch;
     const float* p11 = X + ((size_t)y1 * Wi + x1) * ldx + ch;
     float* dst = y + ((size_t)n * Ho * Wo + p) * ldy + ch;
-    const bool vec = (ch + 3 < C) && ((ldx & 3) == 0) && ((ldy & 3) == 0) && ((((size_t)x) & 15) == 0) && ((((size_t)y) & 15) == 0);
-    if (vec) {
-        const float4 a = __ldg((const float4*)p00), b = __ldg((const float4*)p01), c = __ldg((const float4*)p10),
-                     d = __ldg((const float4*)p11);
-        float4 o;
-        o.x = hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x);
-        o.y = hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y);
-        o.z = hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z);
-        o.w = hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w);
-        *(float4*)dst = o;
+    float a[VEC], b[VEC], c[VEC], d[VEC], o[VEC];
+    if (VEC == 8) {
+        ldg256f(p00, a); ldg256f(p01, b); ldg256f(p10, c); ldg256f(p11, d);
+    } else if (VEC == 4) {
+        const float4 a4 = __ldg((const float4*)p00), b4 = __ldg((const float4*)p01), c4 = __ldg((const float4*)p10),
+                     d4 = __ldg((const float4*)p11);
+        a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+        b[0] = b4.x; b[1] = b4.y; b[2] = b4.z; b[3] = b4.w;
+        c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
+        d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
     } else {
-        for (int i = 0; i < 4 && ch + i < C; ++i)
-            dst[i] = hy * (hx * __ldg(p00 + i) + lx * __ldg(p01 + i)) + ly * (hx * __ldg(p10 + i) + lx * __ldg(p11 + i));
+        a[0] = __ldg(p00); b[0] = __ldg(p01); c[0] = __ldg(p10); d[0] = __ldg(p11);
     }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+    if (VEC == 8) stg256f(dst, o);
+    else if (VEC == 4) *(float4*)dst = make_float4(o[0], o[1], o[2], o[3]);
+    else dst[0] = o[0];
+}
+
+// nn.AvgPool2d(2, 2) on NHWC storage (src/fusion_net/fusion_adacofnet.py:62-70): one thread = one output pixel x VEC channels
+template <int VEC>
+__global__ void __launch_bounds__(256) avg_pool2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi, int Wi,
+                                                             int C, int ldx, int ldy) {
+    const int Ho = Hi >> 1, Wo = Wi >> 1;
+    const unsigned cg_n = (unsigned)(C + VEC - 1) / VEC;
+    const unsigned total = (unsigned)Ho * (unsigned)Wo * cg_n;
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    const unsigned p = q / cg_n;
+    const int ch = (int)(q - p * cg_n) * VEC;
+    const int oy = (int)(p / (unsigned)Wo), ox = (int)(p - (unsigned)oy * (unsigned)Wo);
+    const int n = blockIdx.y;
+    const float* p00 = x + (((size_t)n * Hi + 2 * oy) * Wi + 2 * ox) * ldx + ch;
+    const float* p10 = p00 + (size_t)Wi * ldx;
+    float* dst = y + ((size_t)n * Ho * Wo + p) * ldy + ch;
+    float a[VEC], b[VEC], c[VEC], d[VEC], o[VEC];
+    if (VEC == 8) {
+        ldg256f(p00, a); ldg256f(p00 + ldx, b); ldg256f(p10, c); ldg256f(p10 + ldx, d);
+    } else {
+        a[0] = __ldg(p00); b[0] = __ldg(p00 + ldx); c[0] = __ldg(p10); d[0] = __ldg(p10 + ldx);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = ((a[i] + b[i]) + (c[i] + d[i])) * 0.25f;
+    if (VEC == 8) stg256f(dst, o);
+    else dst[0] = o[0];
 }
 }  // namespace fvfi
 
@@ -369,11 +413,34 @@ extern "C" int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, flo
         sy = (float)Hi / (float)Ho;
         sx = (float)Wi / (float)Wo;
     }
-    const size_t total = (size_t)Ho * Wo * ((C + 3) / 4);
+    const bool a32 = ((((size_t)x) | ((size_t)y)) & 31) == 0, a16 = ((((size_t)x) | ((size_t)y)) & 15) == 0;
+    const int vec = (a32 && (C & 7) == 0 && (x_pixel_stride & 7) == 0 && (y_pixel_stride & 7) == 0) ? 8
+                  : (a16 && (C & 3) == 0 && (x_pixel_stride & 3) == 0 && (y_pixel_stride & 3) == 0) ? 4 : 1;
+    const size_t total = (size_t)Ho * Wo * ((C + vec - 1) / vec);
     FVFI_CHECK_ARG(total < (1ull << 32) - 256, "resize_bilinear: image too large");
     dim3 grid((unsigned)((total + 255) / 256), B);
-    fvfi::resize_bilinear_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride,
-                                                                              sy, sx, align_corners);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (vec == 8)
+        fvfi::resize_bilinear_nhwc_kernel<8><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners);
+    else if (vec == 4)
+        fvfi::resize_bilinear_nhwc_kernel<4><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners);
+    else
+        fvfi::resize_bilinear_nhwc_kernel<1><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
+
+extern "C" int fvfi_avg_pool2_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi, int C,
+                                   void* stream) {
+    FVFI_CHECK_ARG(x && y && B > 0 && Hi > 1 && Wi > 1 && C > 0 && B <= 65535, "avg_pool2: bad argument");
+    FVFI_CHECK_ARG(x_pixel_stride >= C && y_pixel_stride >= C, "avg_pool2: pixel stride smaller than channel count");
+    const bool a32 = ((((size_t)x) | ((size_t)y)) & 31) == 0;
+    const int vec = (a32 && (C & 7) == 0 && (x_pixel_stride & 7) == 0 && (y_pixel_stride & 7) == 0) ? 8 : 1;
+    const size_t total = (size_t)(Hi / 2) * (Wi / 2) * ((C + vec - 1) / vec);
+    FVFI_CHECK_ARG(total < (1ull << 32) - 256, "avg_pool2: image too large");
+    dim3 grid((unsigned)((total + 255) / 256), B);
+    if (vec == 8) fvfi::avg_pool2_nhwc_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, Hi, Wi, C, x_pixel_stride, y_pixel_stride);
+    else fvfi::avg_pool2_nhwc_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, Hi, Wi, C, x_pixel_stride, y_pixel_stride);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }

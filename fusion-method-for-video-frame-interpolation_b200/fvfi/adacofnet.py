@@ -116,13 +116,14 @@ class KernelEstimation(torch.nn.Module):
         run = self._seq_tc
         # 6 input channels padded to 8 (zeros): 16-byte loads in the first convolution
         x = tc.to_nhwc(torch.cat([rfield0, rfield2, rfield0.new_zeros((rfield0.shape[0], 2) + tuple(rfield0.shape[2:]))], 1))
+        pool = tc.avg_pool2                    # modulePool1..5 = AvgPool2d(2, 2), on NHWC with 256-bit accesses
         c1 = run(self.moduleConv1, x)
-        c2 = run(self.moduleConv2, self.modulePool1(c1))
+        c2 = run(self.moduleConv2, pool(c1))
         del c1
-        c3 = run(self.moduleConv3, self.modulePool2(c2))
-        c4 = run(self.moduleConv4, self.modulePool3(c3))
-        c5 = run(self.moduleConv5, self.modulePool4(c4))
-        d5 = run(self.moduleUpsample5, run(self.moduleDeconv5, self.modulePool5(c5)))
+        c3 = run(self.moduleConv3, pool(c2))
+        c4 = run(self.moduleConv4, pool(c3))
+        c5 = run(self.moduleConv5, pool(c4))
+        d5 = run(self.moduleUpsample5, run(self.moduleDeconv5, pool(c5)))
         d4 = run(self.moduleUpsample4, run(self.moduleDeconv4, d5 + c5))
         d3 = run(self.moduleUpsample3, run(self.moduleDeconv3, d4 + c4))
         d2 = run(self.moduleUpsample2, run(self.moduleDeconv2, d3 + c3))

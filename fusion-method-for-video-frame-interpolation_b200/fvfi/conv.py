@@ -117,6 +117,17 @@ def resize_bilinear(x, size, align_corners, out=None, out_channel_offset=0):
     return out
 
 
+def avg_pool2(x):
+    """nn.AvgPool2d(kernel_size=2, stride=2) on NHWC storage."""
+    B, C, H, W = x.shape
+    xc = to_nhwc(x.float())
+    out = torch.empty((B, C, H // 2, W // 2), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().fvfi_avg_pool2_nhwc(xc.data_ptr(), xc.stride(3), out.data_ptr(), out.stride(3), B, H, W, C,
+                                                  _lib.stream_ptr()))
+    return out
+
+
 def conv_module(conv, x, act=None, nchw_out=False, pad_out=False):
     """Run an nn.Conv2d (stride 1, dilation 1, padding == K//2) through the tensor-core kernel."""
     k = conv.kernel_size[0]

@@ -135,6 +135,11 @@ int fvfi_conv2d_overflow_count(void);
 int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi,
                               int Ho, int Wo, int C, int align_corners, void* stream);
 
+/* nn.AvgPool2d(kernel_size=2, stride=2) on NHWC tensors (KernelEstimation's encoder, src/fusion_net/fusion_adacofnet.py:62-70,
+ * 111-123): x [B,Hi,Wi,C] -> y [B,Hi/2,Wi/2,C]. */
+int fvfi_avg_pool2_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi, int C,
+                        void* stream);
+
 /* Host-buffer variants for end-to-end timing: pointers are HOST memory (pinned preferred);
  * the call does H2D, the kernel(s), D2H and synchronises. */
 int fvfi_adacof_forward_host(const float* input, const float* weight, const float* off_i, const float* off_j,

@@ -139,3 +139,13 @@ def test_conv_full_size_layer_vs_cudnn_fp32():
     ref = F.relu(F.conv2d(x, w, b, padding=1))
     assert float((y - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
     conv.check_overflow()
+
+
+def test_avg_pool2_nhwc_matches_torch():
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(8)
+    for (B, C, H, W) in [(2, 32, 32, 64), (1, 64, 34, 60), (1, 5, 9, 7), (2, 512, 68, 120)]:
+        x = torch.randn((B, C, H, W), device="cuda", generator=g)
+        y = conv.avg_pool2(x)
+        ref = F.avg_pool2d(x, 2, 2)
+        assert y.shape == ref.shape and float((y - ref).abs().max()) <= 1e-6

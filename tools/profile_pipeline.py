@@ -7,7 +7,7 @@ from fvfi.pipeline import FusionPipeline
 from oracle import fusion_pipeline as fp
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 torch.backends.cudnn.allow_tf32 = False
-pipe = FusionPipeline(1080, 1920, "cuda", phase_plane_chunk=6)
+pipe = FusionPipeline(1080, 1920, "cuda", phase_plane_chunk=12)
 pipe.load_state(fp.seeded_state(0))
 r1, r2 = fp.seeded_frames(1, 1080, 1920, 0)
 d1, d2 = r1.expand(B, -1, -1, -1).contiguous().cuda(), r2.expand(B, -1, -1, -1).contiguous().cuda()
