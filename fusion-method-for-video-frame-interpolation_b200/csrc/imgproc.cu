@@ -399,7 +399,34 @@ __global__ void __launch_bounds__(256) avg_pool2_nhwc_kernel(const float* __rest
     if (VEC == 8) stg256f(dst, o);
     else dst[0] = o[0];
 }
+// planar [B,C,H,W] -> channel slice of an NHWC buffer (PhaseNet's concat assembly, src/phase_net/phase_net.py:141):
+// coalesced plane reads, one contiguous C-float store per pixel (256-bit when C == 8)
+__global__ void __launch_bounds__(256) nchw_to_nhwc_slice_kernel(const float* __restrict__ x, float* __restrict__ y, int C,
+                                                                 size_t plane, int ldy) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= plane) return;
+    const int n = blockIdx.y;
+    const float* src = x + (size_t)n * C * plane + p;
+    float* dst = y + ((size_t)n * plane + p) * ldy;
+    if (C == 8 && (ldy & 7) == 0 && ((((size_t)y) & 31) == 0)) {
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = __ldg(src + (size_t)c * plane);
+        stg256f(dst, v);
+    } else {
+        for (int c = 0; c < C; ++c) dst[c] = __ldg(src + (size_t)c * plane);
+    }
+}
 }  // namespace fvfi
+
+extern "C" int fvfi_nchw_to_nhwc_slice(const float* x, float* y, int y_pixel_stride, int B, int C, int H, int W, void* stream) {
+    FVFI_CHECK_ARG(x && y && B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535 && y_pixel_stride >= C, "nchw_to_nhwc_slice: bad argument");
+    const size_t plane = (size_t)H * W;
+    dim3 grid((unsigned)((plane + 255) / 256), B);
+    fvfi::nchw_to_nhwc_slice_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, C, plane, y_pixel_stride);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
 
 extern "C" int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi,
                                          int Ho, int Wo, int C, int align_corners, void* stream) {

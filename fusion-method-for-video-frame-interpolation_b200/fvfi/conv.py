@@ -117,6 +117,17 @@ def resize_bilinear(x, size, align_corners, out=None, out_channel_offset=0):
     return out
 
 
+def put_planar(x, out, out_channel_offset):
+    """out[:, off:off+C] = x for a contiguous planar x [B,C,H,W] and a channels_last ``out`` (one kernel, no temporaries)."""
+    B, C, H, W = x.shape
+    x = x.contiguous().float()
+    assert out.stride(1) == 1 and out.shape[2] == H and out.shape[3] == W
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().fvfi_nchw_to_nhwc_slice(x.data_ptr(), out.data_ptr() + 4 * out_channel_offset, out.stride(3),
+                                                      B, C, H, W, _lib.stream_ptr()))
+    return out
+
+
 def avg_pool2(x):
     """nn.AvgPool2d(kernel_size=2, stride=2) on NHWC storage."""
     B, C, H, W = x.shape

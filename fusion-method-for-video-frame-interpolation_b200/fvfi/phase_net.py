@@ -128,8 +128,8 @@ class PhaseNet(nn.Module):
                 concat = torch.empty((feature.shape[0], cf + 2 * cv + cp, res[0], res[1]), dtype=torch.float32,
                                      device=feature.device, memory_format=torch.channels_last)
                 tc.resize_bilinear(feature, res, False, out=concat, out_channel_offset=0)
-                concat[:, cf:cf + cv] = phase[idx]
-                concat[:, cf + cv:cf + 2 * cv] = amplitude[idx]
+                tc.put_planar(phase[idx], concat, cf)
+                tc.put_planar(amplitude[idx], concat, cf + cv)
                 tc.resize_bilinear(prediction, res, False, out=concat, out_channel_offset=cf + 2 * cv)
             else:
                 feature_r = F.interpolate(feature, size=tuple(res), mode='bilinear', align_corners=False)

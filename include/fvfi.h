@@ -140,6 +140,10 @@ int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, float* y, int 
 int fvfi_avg_pool2_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi, int C,
                         void* stream);
 
+/* Planar [B,C,H,W] -> channels [0,C) of an NHWC buffer whose pixels are y_pixel_stride floats apart (pass y + offset for a
+ * channel slice): PhaseNet's concat of phase / amplitude planes with NHWC features (src/phase_net/phase_net.py:141). */
+int fvfi_nchw_to_nhwc_slice(const float* x, float* y, int y_pixel_stride, int B, int C, int H, int W, void* stream);
+
 /* Host-buffer variants for end-to-end timing: pointers are HOST memory (pinned preferred);
  * the call does H2D, the kernel(s), D2H and synchronises. */
 int fvfi_adacof_forward_host(const float* input, const float* weight, const float* off_i, const float* off_j,

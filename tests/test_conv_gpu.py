@@ -149,3 +149,13 @@ def test_avg_pool2_nhwc_matches_torch():
         y = conv.avg_pool2(x)
         ref = F.avg_pool2d(x, 2, 2)
         assert y.shape == ref.shape and float((y - ref).abs().max()) <= 1e-6
+
+
+def test_put_planar_slice():
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for C, off in ((8, 64), (8, 72), (5, 3)):
+        x = torch.randn((3, C, 23, 31), device="cuda", generator=g)
+        buf = torch.zeros((3, 88, 23, 31), device="cuda").contiguous(memory_format=torch.channels_last)
+        conv.put_planar(x, buf, off)
+        assert torch.equal(buf[:, off:off + C], x) and float(buf[:, :off].abs().max()) == 0 and float(buf[:, off + C:].abs().max()) == 0
