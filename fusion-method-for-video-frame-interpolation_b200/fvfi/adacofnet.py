@@ -130,7 +130,24 @@ class KernelEstimation(torch.nn.Module):
         comb = d2 + c2
         heads = (self.moduleWeight1, self.moduleAlpha1, self.moduleBeta1, self.moduleWeight2, self.moduleAlpha2,
                  self.moduleBeta2, self.moduleOcclusion)
-        return tuple(run(h, comb, nchw_last=True) for h in heads)
+        # the seven heads start with a 64 -> 64 convolution of the SAME tensor: one 64 -> 448 convolution (N = 256 + 192
+        # per tensor-core tile instead of 64, the input staged once instead of seven times); each head continues on its
+        # 64-channel slice of the result
+        first = self._fused_first(heads)
+        y = tc.conv2d(comb, first[0], first[1], "zeros", "relu")
+        return tuple(run(torch.nn.Sequential(*list(h)[2:]), y[:, 64 * i:64 * (i + 1)], nchw_last=True)
+                     for i, h in enumerate(heads))
+
+    def _fused_first(self, heads):
+        """Concatenated weights / biases of the heads' first convolutions, rebuilt when any of them changes."""
+        key = tuple((h[0].weight.data_ptr(), h[0].weight._version, h[0].bias._version) for h in heads)
+        hit = getattr(self, "_first_cache", None)
+        if hit is None or hit[0] != key:
+            w = torch.cat([h[0].weight.detach() for h in heads], 0).contiguous()
+            b = torch.cat([h[0].bias.detach() for h in heads], 0).contiguous()
+            hit = (key, (w, b))
+            self._first_cache = hit
+        return hit[1]
 
     def forward(self, rfield0, rfield2):
         if tc.use_tc(rfield0) and not self.training:

@@ -56,6 +56,12 @@ def _packed(weight):
 
 
 def to_nhwc(x):
+    """NHWC storage of x; a channel slice of an NHWC tensor is used in place (pixel stride > C), anything else is copied."""
+    if x.dim() == 4 and x.stride(1) == 1:
+        B, C, H, W = x.shape
+        ld = x.stride(3)
+        if ld >= C and x.stride(2) == W * ld and (B == 1 or x.stride(0) == H * W * ld):
+            return x
     return x.contiguous(memory_format=torch.channels_last)
 
 
