@@ -214,8 +214,9 @@ class AdaCoFWorkload:
 
 WORKLOADS = {"adacof": AdaCoFWorkload}
 try:
-    from bench_pipeline import PipelineWorkload  # added when the full fusion pipeline exists
+    from bench_pipeline import Pipeline4KWorkload, PipelineWorkload
     WORKLOADS["pipeline"] = PipelineWorkload
+    WORKLOADS["pipeline4k"] = Pipeline4KWorkload
 except ImportError:
     pass
 DEFAULT_WORKLOAD = os.environ.get("FVFI_BENCH_WORKLOAD", "pipeline" if "pipeline" in WORKLOADS else "adacof")

@@ -23,7 +23,7 @@ class PipelineWorkload:
         torch.backends.cuda.matmul.allow_tf32 = self.tf32
         torch.backends.cudnn.benchmark = True
         self.pipe = FusionPipeline(self.H, self.W, device, phase_plane_chunk=int(os.environ.get("FVFI_PLANE_CHUNK", "12")))
-        self.pipe.max_batch = int(os.environ.get("FVFI_MAX_BATCH", "8"))
+        self.pipe.max_batch = int(os.environ.get("FVFI_MAX_BATCH", "8" if self.H <= 1080 else "2"))
         self.pipe.load_state(fp.seeded_state(0))
         r1, r2 = fp.seeded_frames(1, self.H, self.W, seed)
         g = torch.Generator().manual_seed(seed)
@@ -173,3 +173,16 @@ class PipelineWorkload:
         scale = (H * W) / float(cls.H * cls.W)
         return scale / dt, dt, ("1 frame pair at %dx%d (%.4f of 1080p area), frames/s scaled by the pixel ratio; "
                                 "oracle port of the reference recipe, torch CPU + scipy + C warp" % (H, W, scale))
+
+
+class Pipeline4KWorkload(PipelineWorkload):
+    """BASELINE.json configs[3]: the same recipe at 3840x2160 (pyramid height 19, AdaCoFNet pads to 2176 rows); frame pairs
+    shard across ranks exactly like the 1080p workload.  Not the default bench line (the metric is quoted at 1080p)."""
+    H, W = 2160, 3840
+    B = int(os.environ.get("FVFI_BENCH_BATCH_4K", "4"))
+    name = "fusion_pipeline_4k_batch%d (BASELINE.json configs[3])" % B
+
+    @classmethod
+    def cpu_sample(cls, threads, seed=0):
+        fps, dt, sample = PipelineWorkload.cpu_sample(threads, seed)
+        return fps * (PipelineWorkload.H * PipelineWorkload.W) / float(cls.H * cls.W), dt, sample.replace("1080p", "4K-scaled 1080p")

@@ -192,3 +192,18 @@ def test_pipeline_1080p_properties():
     host = pipe.interpolate_host(f1.cpu().pin_memory(), f2.cpu().pin_memory())
     assert float((host - out2.cpu()).abs().max()) <= 2e-6
     tc.check_overflow()
+
+
+def test_pipeline_4k_runs():
+    """BASELINE.json configs[3] size (3840x2160, one pair): the whole recipe runs at 4K (pyramid height 19, AdaCoFNet
+    padding to 2176 rows, every convolution / resize / filter kernel at that size) and stays finite in [0,1]."""
+    from fvfi import conv as tc
+    from fvfi.pipeline import FusionPipeline
+    H, W = 2160, 3840
+    pipe = FusionPipeline(H, W, "cuda", phase_plane_chunk=3)
+    pipe.load_state(fp.seeded_state(0))
+    r1, r2 = fp.seeded_frames(1, H, W, 4)
+    out = pipe(r1.cuda(), r2.cuda())
+    assert out.shape == (1, 3, H, W) and bool(torch.isfinite(out).all())
+    assert float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    tc.check_overflow()
