@@ -135,7 +135,10 @@ class AdaCoFWorkload:
         ach_b = self.bytes_bwd / (bwd * 1e-3) / 1e9
         return {
             "bound": "hbm", "kernel": "adacof_fwd_tiled<5,4,1>", "achieved": round(ach_f, 1), "peak": peak,
-            "unit": "GB/s", "frac": round(ach_f / peak, 4), "traffic": None, "peak_source": peak_src,
+            "unit": "GB/s", "frac": round(ach_f / peak, 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, ncu --set full (profiles/r01_adacof_*):
+            # 5.39 GB per launch = the algorithmic bytes, i.e. every coefficient map is read from HBM exactly once
+            "traffic": 5.39e9, "peak_source": peak_src,
             "ms_per_launch": round(fwd, 4), "algorithmic_bytes_per_launch": self.bytes_fwd,
             "other_kernels": [{"kernel": "adacof_bwd_tiled<5,4>", "achieved": round(ach_b, 1),
                                "frac": round(ach_b / peak, 4), "ms_per_launch": round(bwd, 4),
