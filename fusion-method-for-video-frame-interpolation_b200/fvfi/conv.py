@@ -2,14 +2,15 @@
 the three networks on tcgen05 with split-operand error compensation (3xFP16 default / 3xTF32; fp32-grade results), NHWC activations
 (torch ``channels_last``), fused bias + activation.
 
-``Conv2dTC.apply_module(conv, x, act)`` runs an ``nn.Conv2d`` (weights stay in the module, so reference
-checkpoints load unchanged) through the kernel; packed weights are cached per weight version.
+``conv_module(conv, x, act)`` runs an ``nn.Conv2d`` (weights stay in the module, so reference checkpoints load
+unchanged) through the kernel; packed weights are cached per weight version.  Also here: the NHWC helpers around
+the convolutions (bilinear resize, 2x2 average pool, planar -> NHWC slice).
 """
+import os
+
 import torch
 
 from . import _lib
-
-import os
 
 enabled = True   # use the tcgen05 kernels for inference convolutions (False -> torch/cuDNN scaffolding)
 PRECISIONS = {"tf32x3": 0, "f16x3": 1}
