@@ -323,6 +323,11 @@ int adacofnet_warp_blend_tiled(const float* in1, const float* in2, const float* 
                                const float* b1, const float* w2, const float* a2, const float* b2,
                                const float* occ, float* t1, float* t2, float* frame, float* mask, int B, int Hin,
                                int Win, int H, int W, int F, int dil, cudaStream_t s, int* handled);
+// implemented in adacof_tma.cu (F = 5, dilation 1, W % 4 == 0): TMA-streamed coefficient maps, persistent CTAs
+int adacof_tma_launch(const float* in1, const float* in2, const float* w1, const float* a1, const float* b1,
+                      const float* w2, const float* a2, const float* b2, const float* occ, float* t1, float* t2,
+                      float* frame, float* mask, int nframes, int B, int Hin, int Win, int H, int W, int F, int dil,
+                      cudaStream_t s, int* handled);
 
 }  // namespace fvfi
 
@@ -333,8 +338,16 @@ extern "C" int fvfi_adacof_forward(const float* input, const float* weight, cons
                                    int W, int F, int dilation, int algo, void* stream) {
     if (int rc = check_dims(B, C, Hin, Win, H, W, F, dilation)) return rc;
     FVFI_CHECK_ARG(input && weight && off_i && off_j && output, "adacof_forward: null pointer");
-    FVFI_CHECK_ARG(algo >= 0 && algo <= 2, "adacof_forward: algo must be 0..2");
+    FVFI_CHECK_ARG(algo >= 0 && algo <= 3, "adacof_forward: algo must be 0..3");
     cudaStream_t s = (cudaStream_t)stream;
+    if (C == 3 && (algo == 0 || algo == 3)) {
+        int handled = 0;
+        if (int rc = adacof_tma_launch(input, nullptr, weight, off_i, off_j, nullptr, nullptr, nullptr, nullptr, output,
+                                       nullptr, nullptr, nullptr, 1, B, Hin, Win, H, W, F, dilation, s, &handled))
+            return rc;
+        if (handled) return FVFI_OK;
+        FVFI_CHECK_ARG(algo != 3, "adacof_forward: TMA algorithm needs F = 5, dilation 1, W %% 4 == 0 and 16-byte aligned maps");
+    }
     if (C == 3 && algo != 1) {
         int handled = 0;
         if (int rc = adacof_forward_tiled(input, weight, off_i, off_j, output, B, Hin, Win, H, W, F, dilation, s,
@@ -412,6 +425,10 @@ extern "C" int fvfi_adacofnet_warp_blend(const float* in1, const float* in2, con
     if (int rc = check_dims(B, 3, Hin, Win, H, W, F, dilation)) return rc;
     FVFI_CHECK_ARG(in1 && in2 && w1 && a1 && b1 && w2 && a2 && b2 && occ, "adacofnet_warp_blend: null input");
     int handled = 0;
+    if (int rc = adacof_tma_launch(in1, in2, w1, a1, b1, w2, a2, b2, occ, t1, t2, frame, mask, 2, B, Hin, Win, H, W, F,
+                                   dilation, (cudaStream_t)stream, &handled))
+        return rc;
+    if (handled) return FVFI_OK;
     if (int rc = adacofnet_warp_blend_tiled(in1, in2, w1, a1, b1, w2, a2, b2, occ, t1, t2, frame, mask, B, Hin, Win,
                                             H, W, F, dilation, (cudaStream_t)stream, &handled))
         return rc;

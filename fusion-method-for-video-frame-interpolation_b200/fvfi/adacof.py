@@ -17,7 +17,7 @@ import torch
 from . import _lib
 
 gin_mode = "zeros"
-algo = 0  # 0 auto, 1 direct, 2 tiled (see include/fvfi.h)
+algo = 0  # 0 auto, 1 direct, 2 tiled, 3 TMA-streamed (forward only; see include/fvfi.h)
 
 _GIN = {"none": 0, "zeros": 1, "true": 2}
 

@@ -57,7 +57,8 @@ unsigned long long fvfi_launch_count(void);
  * (src/adacof/cupy_module/adacof.py:313-361, :6-65).
  *   input  [B,C,Hin,Win]   weight/off_i/off_j [B,F*F,H,W]   output [B,C,H,W]
  *   requires Hin == H + (F-1)*dilation, Win == W + (F-1)*dilation  (adacof.py:326-327)
- * algo: 0 = auto, 1 = direct (global gathers), 2 = tiled (smem-staged frame tile)
+ * algo: 0 = auto, 1 = direct (global gathers), 2 = tiled (smem-staged frame tile, register-prefetched coefficients),
+ *       3 = TMA (persistent CTAs, coefficient planes streamed by cp.async.bulk.tensor; F = 5, dilation 1, W % 4 == 0)
  */
 int fvfi_adacof_forward(const float* input, const float* weight, const float* off_i, const float* off_j,
                         float* output, int B, int C, int Hin, int Win, int H, int W, int F, int dilation,

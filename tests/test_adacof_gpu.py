@@ -43,6 +43,25 @@ def test_forward_backward_vs_oracle(shape, algo):
     assert np.abs(gj.cpu().numpy() - rgj).max() <= TOL_BWD
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 40, 56, 5, 1), (2, 3, 96, 160, 5, 1), (3, 3, 37, 52, 5, 1), (1, 3, 9, 36, 5, 1)])
+def test_forward_algorithms_agree(shape):
+    """The TMA-streamed forward (algo 3; what `auto` picks for F = 5, dilation 1, W % 4 == 0) equals the tiled kernel
+    (algo 2) BIT FOR BIT -- same tap order and contractions -- and both match the oracle, including ragged tile edges
+    and offsets far outside the staged halo (clamp-to-edge fallback)."""
+    from fvfi import adacof
+    B, C, H, W, F, d = shape
+    inp, w, oi, oj, _ = oa.synth(B, C, H, W, F, d, seed=17)
+    oi = (oi * 2.5).astype(np.float32)          # pushes many taps beyond the +-8 halo
+    t = _dev(inp, w, oi, oj)
+    o3 = adacof.adacof_forward(*t, d, algo_=3)
+    o2 = adacof.adacof_forward(*t, d, algo_=2)
+    o0 = adacof.adacof_forward(*t, d, algo_=0)
+    assert torch.equal(o3, o2) and torch.equal(o0, o3)
+    assert np.abs(o3.cpu().numpy() - oa.forward(inp, w, oi, oj, d, threads=4)).max() <= TOL_FWD
+    with pytest.raises(Exception):
+        adacof.adacof_forward(*_dev(*oa.synth(1, 3, 24, 40, 3, 1, seed=1)[:4]), 1, algo_=3)   # F = 3: not applicable
+
+
 def test_golden_vectors(golden_dir):
     from fvfi import adacof
     files = sorted(glob.glob(os.path.join(golden_dir, "adacof_ref_*.npz")))
