@@ -134,7 +134,7 @@ class AdaCoFWorkload:
         ach_f = self.bytes_fwd / (fwd * 1e-3) / 1e9
         ach_b = self.bytes_bwd / (bwd * 1e-3) / 1e9
         return {
-            "bound": "hbm", "kernel": "adacof_fwd_tiled<5,4,1>", "achieved": round(ach_f, 1), "peak": peak,
+            "bound": "hbm", "kernel": "adacof_fwd_tma<1,3,2> (TMA-streamed coefficients; offsets ~ N(0, 3^2): the adversarial gather)", "achieved": round(ach_f, 1), "peak": peak,
             "unit": "GB/s", "frac": round(ach_f / peak, 4),
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, ncu --set full (profiles/r01_adacof_*):
             # 5.39 GB per launch = the algorithmic bytes, i.e. every coefficient map is read from HBM exactly once

@@ -106,7 +106,7 @@ class PipelineWorkload:
         ms = timeit(lambda: adacof.adacofnet_warp_blend(i1, i2, w1, a1, b1, w1, b1, a1, occ, 1, want_t=False))
         px = B * H * W
         nbytes = 4 * (6 * 25 * px + 2 * 3 * B * (H + 4) * (W + 4) + px + 3 * px + px)
-        out.append({"kernel": "adacof_fwd_tiled<5,4,2> (two warps + blend + uncertainty, smooth offsets)", "bound": "hbm",
+        out.append({"kernel": "adacof_fwd_tma<2,2,3> (two warps + blend + uncertainty, TMA-streamed coefficients, smooth offsets)", "bound": "hbm",
                     "achieved": round(nbytes / ms / 1e6, 1), "unit": "GB/s", "frac": round(nbytes / ms / 1e6 / peak, 4),
                     "ms_per_launch": round(ms, 4), "algorithmic_bytes_per_launch": nbytes})
         del i1, i2, w1, a1, b1, occ

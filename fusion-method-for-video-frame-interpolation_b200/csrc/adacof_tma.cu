@@ -8,13 +8,16 @@
 //     planes of the tile with three cp.async.bulk.tensor (TMA, 3-D boxes 32 x 8 x 5, out-of-image elements zero-filled) into a
 //     ring of shared-memory stages guarded by full/empty mbarriers -- bytes in flight no longer cost registers or warps;
 //   * the 8 CONSUMER warps (one pixel per thread) read their coefficients from the stage (conflict-free LDS.32: a lane is a
-//     column), gather the frame from the staged region exactly like the tiled kernel (float4 {R,G,B,-} pixels, clamped fill,
-//     global fallback for offsets beyond the halo), and release the stage;
+//     column), gather the frame from the staged region (PLANAR here: the shared-memory pipe is the limiter once HBM latency
+//     is hidden, and 12 LDS.32 cost 12 wavefronts where 4 LDS.128 of padded {R,G,B,-} pixels cost 16; clamped fill, global
+//     fallback for offsets beyond the halo as in the tiled kernel), and release the stage;
 //   * the frame region of the NEXT work item is fetched with 4-byte cp.async into the second region buffer while the current
 //     item is processed, so tiles (and the two frames of the fused synthesis) follow each other without a staging bubble.
 // Arithmetic (tap order, truncation toward zero, clamp-to-edge, fmaf contraction) is identical to adacof_tiled.cu, which stays
 // the path for other filter sizes / dilations / unaligned widths.
 #include <cuda.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -23,14 +26,12 @@ namespace fvfi {
 constexpr int XW = 32, XH = 8;                 // output tile
 constexpr int XCONS = XW * XH;                 // consumer threads (one pixel each)
 constexpr int XTHREADS = XCONS + 32;           // + producer warp
-constexpr int XSTAGES = 3;                     // coefficient ring
 constexpr int XF = 5, XPADF = XF - 1, XHALO = 8;
 constexpr int XSH = XH + XPADF + 2 * XHALO + 1;    // staged region rows / columns (tile + taps + halo + 1 for the +1 neighbour)
 constexpr int XSW = XW + XPADF + 2 * XHALO + 1;
 constexpr int XSTAGE_FLOATS = 3 * XF * XH * XW;    // one tap-row of the three maps
-constexpr size_t XRING_BYTES = (size_t)XSTAGES * XSTAGE_FLOATS * sizeof(float);
-constexpr size_t XREGION_BYTES = (size_t)XSH * XSW * sizeof(float4);
-constexpr size_t XSMEM_BYTES = XRING_BYTES + 2 * XREGION_BYTES + 128;
+constexpr int XRPLANE = XSH * XSW;                 // one colour plane of the staged region
+constexpr size_t XREGION_BYTES = ((size_t)3 * XRPLANE * sizeof(float) + 127) & ~(size_t)127;
 constexpr unsigned XSPIN_LIMIT = 400u * 1000u * 1000u;
 
 struct TmaArgs {
@@ -90,15 +91,16 @@ __device__ __forceinline__ XTile x_tile(const TmaArgs& A, int tile) {
     return t;
 }
 
-template <int NFRAMES>
-__global__ void __launch_bounds__(XTHREADS, 2)
+template <int NFRAMES, int XSTAGES, int MINB>
+__global__ void __launch_bounds__(XTHREADS, MINB)
 adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ CUtensorMap ma0,
                const __grid_constant__ CUtensorMap mb0, const __grid_constant__ CUtensorMap mw1,
                const __grid_constant__ CUtensorMap ma1, const __grid_constant__ CUtensorMap mb1, const TmaArgs A) {
     extern __shared__ __align__(128) unsigned char xsm[];
+    constexpr size_t XRING_BYTES = (size_t)XSTAGES * XSTAGE_FLOATS * sizeof(float);
     float* ring = (float*)xsm;
-    float4* region0 = (float4*)(xsm + XRING_BYTES);
-    float4* region1 = (float4*)(xsm + XRING_BYTES + XREGION_BYTES);
+    float* region0 = (float*)(xsm + XRING_BYTES);
+    float* region1 = (float*)(xsm + XRING_BYTES + XREGION_BYTES);
     unsigned long long* full = (unsigned long long*)(xsm + XRING_BYTES + 2 * XREGION_BYTES);
     unsigned long long* empty = full + XSTAGES;
 
@@ -139,17 +141,16 @@ adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ 
     }
 
     // ================= consumers: thread = pixel (row = warp, column = lane) of the tile =================
-    auto issue_region = [&](float4* R, const XTile& T, int f) {
+    auto issue_region = [&](float* R, const XTile& T, int f) {
         const float* I = A.in[f] + (size_t)T.n * 3 * plane_in;
-        for (int p = threadIdx.x; p < XSH * XSW; p += XCONS) {
+        for (int p = threadIdx.x; p < XRPLANE; p += XCONS) {
             const int r = p / XSW, c = p - r * XSW;
             const int gr = min(max(T.i0 - XHALO + r, 0), A.Hin - 1);
             const int gc = min(max(T.j0 - XHALO + c, 0), A.Win - 1);
             const float* src = I + (size_t)gr * A.Win + gc;
-            float* d = (float*)(R + p);
-            cp_async4(d, src);
-            cp_async4(d + 1, src + plane_in);
-            cp_async4(d + 2, src + 2 * plane_in);
+            cp_async4(R + p, src);                                   // planar: consecutive lanes, consecutive words
+            cp_async4(R + XRPLANE + p, src + plane_in);
+            cp_async4(R + 2 * XRPLANE + p, src + 2 * plane_in);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -174,7 +175,7 @@ adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ 
                 const int ntile = more_f ? tile : tile + (int)gridDim.x;
                 if (ntile < A.ntiles) issue_region((item & 1) ? region0 : region1, x_tile(A, ntile), more_f ? f + 1 : 0);
             }
-            const float4* R = (item & 1) ? region1 : region0;
+            const float* R = (item & 1) ? region1 : region0;
             const float* I = A.in[f] + (size_t)T.n * 3 * plane_in;
             float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
             float s0 = 0.f, s1i = 0.f, s2i = 0.f, s1j = 0.f, s2j = 0.f;
@@ -194,11 +195,12 @@ adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ 
                     const int rr = warp + k + Ai + XHALO, cc = lane + l + Bj + XHALO;
                     float4 v00, v01, v10, v11;
                     if ((unsigned)rr < (unsigned)(XSH - 1) && (unsigned)cc < (unsigned)(XSW - 1)) {
-                        const float4* q = R + rr * XSW + cc;
-                        v00 = q[0];
-                        v01 = q[1];
-                        v10 = q[XSW];
-                        v11 = q[XSW + 1];
+                        // planar region: 12 LDS.32 (one wavefront each for smooth offsets) instead of 4 LDS.128 (four each)
+                        const float* q = R + rr * XSW + cc;
+                        v00 = make_float4(q[0], q[XRPLANE], q[2 * XRPLANE], 0.f);
+                        v01 = make_float4(q[1], q[XRPLANE + 1], q[2 * XRPLANE + 1], 0.f);
+                        v10 = make_float4(q[XSW], q[XRPLANE + XSW], q[2 * XRPLANE + XSW], 0.f);
+                        v11 = make_float4(q[XSW + 1], q[XRPLANE + XSW + 1], q[2 * XRPLANE + XSW + 1], 0.f);
                     } else {                                              // offset beyond the halo: global, explicit clamps
                         const int gr = gi + k + Ai, gc = gj + l + Bj;
                         const int r0 = min(max(gr, 0), A.Hin - 1), r1 = min(max(gr + 1, 0), A.Hin - 1);
@@ -309,14 +311,17 @@ int adacof_tma_launch(const float* in1, const float* in2, const float* w1, const
     if (nt > 0x7fffffffLL) return FVFI_OK;
     A.ntiles = (int)nt;
     const int nsm = sm_count() > 0 ? sm_count() : 148;
-    const unsigned grid = (unsigned)std::min<long long>(nt, 2LL * nsm);
-    if (nframes == 2) {
-        FVFI_CUDA(cudaFuncSetAttribute(adacof_fwd_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XSMEM_BYTES));
-        adacof_fwd_tma<2><<<grid, XTHREADS, XSMEM_BYTES, s>>>(mw0, ma0, mb0, mw1, ma1, mb1, A);
-    } else {
-        FVFI_CUDA(cudaFuncSetAttribute(adacof_fwd_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XSMEM_BYTES));
-        adacof_fwd_tma<1><<<grid, XTHREADS, XSMEM_BYTES, s>>>(mw0, ma0, mb0, mw1, ma1, mb1, A);
+#define FVFI_TMA_LAUNCH(NF, ST, MB)                                                                                       \
+    {                                                                                                                     \
+        const size_t smem = (size_t)ST * XSTAGE_FLOATS * sizeof(float) + 2 * XREGION_BYTES + 128;                        \
+        const unsigned grid = (unsigned)std::min<long long>(nt, (long long)MB * nsm);                                    \
+        FVFI_CUDA(cudaFuncSetAttribute(adacof_fwd_tma<NF, ST, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        adacof_fwd_tma<NF, ST, MB><<<grid, XTHREADS, smem, s>>>(mw0, ma0, mb0, mw1, ma1, mb1, A);                       \
     }
+    // measured (tools/prof_adacof.py): the single warp is fastest with a 3-deep ring and 2 CTAs/SM, the fused synthesis (more
+    // arithmetic per byte: moments, blend) with a 2-deep ring and 3 CTAs/SM (67 KB each, 72 registers)
+    if (nframes == 2) FVFI_TMA_LAUNCH(2, 2, 3) else FVFI_TMA_LAUNCH(1, 3, 2)
+#undef FVFI_TMA_LAUNCH
     FVFI_LAUNCH_CHECK();
     *handled = 1;
     return FVFI_OK;
