@@ -327,7 +327,8 @@ int adacofnet_warp_blend_tiled(const float* in1, const float* in2, const float* 
 int adacof_tma_launch(const float* in1, const float* in2, const float* w1, const float* a1, const float* b1,
                       const float* w2, const float* a2, const float* b2, const float* occ, float* t1, float* t2,
                       float* frame, float* mask, int nframes, int B, int Hin, int Win, int H, int W, int F, int dil,
-                      cudaStream_t s, int* handled);
+                      cudaStream_t s, int* handled, const float* bwd_gout = nullptr, float* bwd_gw = nullptr,
+                      float* bwd_goi = nullptr, float* bwd_goj = nullptr);
 
 }  // namespace fvfi
 
@@ -379,11 +380,20 @@ extern "C" int fvfi_adacof_backward(const float* gout, const float* input, const
     FVFI_CHECK_ARG(gout && input && weight && off_i && off_j && gw && goi && goj, "adacof_backward: null pointer");
     FVFI_CHECK_ARG(gin_mode >= 0 && gin_mode <= 2, "adacof_backward: bad gin_mode");
     FVFI_CHECK_ARG(gin_mode == FVFI_GIN_NONE || gin, "adacof_backward: gin is null");
-    FVFI_CHECK_ARG(algo >= 0 && algo <= 2, "adacof_backward: algo must be 0..2");
+    FVFI_CHECK_ARG(algo >= 0 && algo <= 3, "adacof_backward: algo must be 0..3");
     cudaStream_t s = (cudaStream_t)stream;
     if (gin_mode != FVFI_GIN_NONE)
         FVFI_CUDA(cudaMemsetAsync(gin, 0, (size_t)B * C * Hin * Win * sizeof(float), s));
-    if (gin_mode != FVFI_GIN_TRUE && algo != 1) {
+    if (C == 3 && gin_mode != FVFI_GIN_TRUE && (algo == 0 || algo == 3)) {
+        int handled = 0;
+        if (int rc = adacof_tma_launch(input, nullptr, weight, off_i, off_j, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                       nullptr, nullptr, nullptr, 0, B, Hin, Win, H, W, F, dilation, s, &handled, gout, gw,
+                                       goi, goj))
+            return rc;
+        if (handled) return FVFI_OK;
+        FVFI_CHECK_ARG(algo != 3, "adacof_backward: TMA algorithm needs F = 5, dilation 1, W %% 4 == 0 and 16-byte aligned maps");
+    }
+    if (gin_mode != FVFI_GIN_TRUE && algo != 1 && algo != 3) {
         int handled = 0;
         if (int rc = adacof_backward_tiled(gout, input, weight, off_i, off_j, gw, goi, goj, B, Hin, Win, H, W, F,
                                            dilation, s, &handled))

@@ -40,6 +40,10 @@ struct TmaArgs {
     float* t[2];
     float* frame;
     float* mask;
+    const float* gout;         // backward (NFRAMES == 0): gradOutput and the three gradient maps
+    float* gw;
+    float* goi;
+    float* goj;
     int Hin, Win, H, W;
     int tiles_x, tiles_y, ntiles;
 };
@@ -91,11 +95,14 @@ __device__ __forceinline__ XTile x_tile(const TmaArgs& A, int tile) {
     return t;
 }
 
+// NFRAMES: 1 = forward, 2 = fused two-frame synthesis, 0 = fused backward (gW, g_alpha, g_beta from one gather; algebra in adacof.cu)
 template <int NFRAMES, int XSTAGES, int MINB>
 __global__ void __launch_bounds__(XTHREADS, MINB)
 adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ CUtensorMap ma0,
                const __grid_constant__ CUtensorMap mb0, const __grid_constant__ CUtensorMap mw1,
                const __grid_constant__ CUtensorMap ma1, const __grid_constant__ CUtensorMap mb1, const TmaArgs A) {
+    constexpr bool BWD = NFRAMES == 0;
+    constexpr int NF = BWD ? 1 : NFRAMES;
     extern __shared__ __align__(128) unsigned char xsm[];
     constexpr size_t XRING_BYTES = (size_t)XSTAGES * XSTAGE_FLOATS * sizeof(float);
     float* ring = (float*)xsm;
@@ -119,7 +126,7 @@ adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
                 const XTile T = x_tile(A, tile);
 #pragma unroll 1
-                for (int f = 0; f < NFRAMES; ++f) {
+                for (int f = 0; f < NF; ++f) {
                     const CUtensorMap* pw = f ? &mw1 : &mw0;
                     const CUtensorMap* pa = f ? &ma1 : &ma0;
                     const CUtensorMap* pb = f ? &mb1 : &mb0;
@@ -165,18 +172,25 @@ adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ 
         const bool live = gi < A.H && gj < A.W;
         const size_t p = (size_t)gi * A.W + gj;
 #pragma unroll 1
-        for (int f = 0; f < NFRAMES; ++f, ++item) {
+        for (int f = 0; f < NF; ++f, ++item) {
             // this item's region has landed (own copies), everybody's copies have landed and everybody is done with the
             // previous item -> its region buffer may be refilled with the NEXT item's region
             asm volatile("cp.async.wait_all;" ::: "memory");
             asm volatile("bar.sync 1, %0;" ::"n"(XCONS) : "memory");
             {
-                const bool more_f = f + 1 < NFRAMES;
+                const bool more_f = f + 1 < NF;
                 const int ntile = more_f ? tile : tile + (int)gridDim.x;
                 if (ntile < A.ntiles) issue_region((item & 1) ? region0 : region1, x_tile(A, ntile), more_f ? f + 1 : 0);
             }
             const float* R = (item & 1) ? region1 : region0;
             const float* I = A.in[f] + (size_t)T.n * 3 * plane_in;
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+            if (BWD && live) {
+                g0 = ld_stream(A.gout + ((size_t)T.n * 3 + 0) * plane + p);
+                g1 = ld_stream(A.gout + ((size_t)T.n * 3 + 1) * plane + p);
+                g2 = ld_stream(A.gout + ((size_t)T.n * 3 + 2) * plane + p);
+            }
+            const size_t gq = (size_t)T.n * XF * XF * plane + p;      // this pixel in the [B,25,H,W] gradient maps
             float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
             float s0 = 0.f, s1i = 0.f, s2i = 0.f, s1j = 0.f, s2j = 0.f;
 #pragma unroll 1
@@ -214,10 +228,23 @@ adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ 
                         v01 = make_float4(__ldg(p01), __ldg(p01 + plane_in), __ldg(p01 + 2 * plane_in), 0.f);
                         v11 = make_float4(__ldg(p11), __ldg(p11 + plane_in), __ldg(p11 + 2 * plane_in), 0.f);
                     }
-                    const float w00 = na * nb, w10 = a * nb, w01 = na * b, w11 = a * b;
-                    acc0 = fmaf(w, v00.x * w00 + v10.x * w10 + v01.x * w01 + v11.x * w11, acc0);
-                    acc1 = fmaf(w, v00.y * w00 + v10.y * w10 + v01.y * w01 + v11.y * w11, acc1);
-                    acc2 = fmaf(w, v00.z * w00 + v10.z * w10 + v01.z * w01 + v11.z * w11, acc2);
+                    if (BWD) {
+                        const float s00 = fmaf(g2, v00.z, fmaf(g1, v00.y, g0 * v00.x));
+                        const float s10 = fmaf(g2, v10.z, fmaf(g1, v10.y, g0 * v10.x));
+                        const float s01 = fmaf(g2, v01.z, fmaf(g1, v01.y, g0 * v01.x));
+                        const float s11 = fmaf(g2, v11.z, fmaf(g1, v11.y, g0 * v11.x));
+                        if (live) {
+                            const size_t o = gq + (size_t)(k * XF + l) * plane;
+                            st_stream(A.gw + o, s00 * (na * nb) + s10 * (a * nb) + s01 * (na * b) + s11 * (a * b));
+                            st_stream(A.goi + o, w * ((s10 - s00) * nb + (s11 - s01) * b));
+                            st_stream(A.goj + o, w * ((s01 - s00) * na + (s11 - s10) * a));
+                        }
+                    } else {
+                        const float w00 = na * nb, w10 = a * nb, w01 = na * b, w11 = a * b;
+                        acc0 = fmaf(w, v00.x * w00 + v10.x * w10 + v01.x * w01 + v11.x * w11, acc0);
+                        acc1 = fmaf(w, v00.y * w00 + v10.y * w10 + v01.y * w01 + v11.y * w11, acc1);
+                        acc2 = fmaf(w, v00.z * w00 + v10.z * w10 + v01.z * w01 + v11.z * w11, acc2);
+                    }
                     if (NFRAMES == 2) {
                         s0 += w;
                         s1i = fmaf(w, al, s1i);
@@ -229,7 +256,7 @@ adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) xbar_arrive(&empty[s]);          // this warp is done with the stage
             }
-            if (live) {
+            if (!BWD && live) {
                 float* const t = A.t[f];
                 if (t) {
                     st_stream(t + ((size_t)T.n * 3 + 0) * plane + p, acc0);
@@ -288,10 +315,12 @@ static bool make_map(CUtensorMap* m, const float* base, int B, int H, int W) {
 static bool aligned16(const void* p) { return (((size_t)p) & 15) == 0; }
 
 // Returns FVFI_OK with *handled = 1 if the TMA path ran, *handled = 0 if it does not apply (caller falls back).
+// nframes: 1 forward, 2 fused synthesis, 0 backward (gout, gw/goi/goj via the bwd_* arguments)
 int adacof_tma_launch(const float* in1, const float* in2, const float* w1, const float* a1, const float* b1,
                       const float* w2, const float* a2, const float* b2, const float* occ, float* t1, float* t2,
                       float* frame, float* mask, int nframes, int B, int Hin, int Win, int H, int W, int F, int dil,
-                      cudaStream_t s, int* handled) {
+                      cudaStream_t s, int* handled, const float* bwd_gout = nullptr, float* bwd_gw = nullptr,
+                      float* bwd_goi = nullptr, float* bwd_goj = nullptr) {
     *handled = 0;
     if (F != XF || dil != 1 || (W & 3) || !aligned16(w1) || !aligned16(a1) || !aligned16(b1)) return FVFI_OK;
     if (nframes == 2 && (!aligned16(w2) || !aligned16(a2) || !aligned16(b2))) return FVFI_OK;
@@ -304,6 +333,7 @@ int adacof_tma_launch(const float* in1, const float* in2, const float* w1, const
     }
     TmaArgs A{};
     A.in[0] = in1; A.in[1] = in2; A.occ = occ; A.t[0] = t1; A.t[1] = t2; A.frame = frame; A.mask = mask;
+    A.gout = bwd_gout; A.gw = bwd_gw; A.goi = bwd_goi; A.goj = bwd_goj;
     A.Hin = Hin; A.Win = Win; A.H = H; A.W = W;
     A.tiles_x = ceil_div(W, XW);
     A.tiles_y = ceil_div(H, XH);
@@ -318,6 +348,7 @@ int adacof_tma_launch(const float* in1, const float* in2, const float* w1, const
         FVFI_CUDA(cudaFuncSetAttribute(adacof_fwd_tma<NF, ST, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         adacof_fwd_tma<NF, ST, MB><<<grid, XTHREADS, smem, s>>>(mw0, ma0, mb0, mw1, ma1, mb1, A);                       \
     }
+    if (nframes == 0) FVFI_TMA_LAUNCH(0, 3, 2) else
     // measured (tools/prof_adacof.py): the single warp is fastest with a 3-deep ring and 2 CTAs/SM, the fused synthesis (more
     // arithmetic per byte: moments, blend) with a 2-deep ring and 3 CTAs/SM (67 KB each, 72 registers)
     if (nframes == 2) FVFI_TMA_LAUNCH(2, 2, 3) else FVFI_TMA_LAUNCH(1, 3, 2)

@@ -66,7 +66,7 @@ int fvfi_adacof_forward(const float* input, const float* weight, const float* of
 
 /* Replaces FunctionAdaCoF.backward + kernel_AdaCoF_updateGradWeight/-Alpha/-Beta
  * (adacof.py:364-445, :67-258) with ONE fused kernel.  C must be 3 (the reference hard-codes
- * three channels, adacof.py:86,150,215).  gw/goi/goj [B,F*F,H,W] are fully overwritten
+ * three channels, adacof.py:86,150,215; algo as in fvfi_adacof_forward).  gw/goi/goj [B,F*F,H,W] are fully overwritten
  * (no pre-zeroing needed).  gin [B,C,Hin,Win] per gin_mode. */
 int fvfi_adacof_backward(const float* gout, const float* input, const float* weight, const float* off_i,
                          const float* off_j, float* gin, float* gw, float* goi, float* goj, int B, int C,

@@ -45,7 +45,7 @@ def test_forward_backward_vs_oracle(shape, algo):
 
 @pytest.mark.parametrize("shape", [(2, 3, 40, 56, 5, 1), (2, 3, 96, 160, 5, 1), (3, 3, 37, 52, 5, 1), (1, 3, 9, 36, 5, 1)])
 def test_forward_algorithms_agree(shape):
-    """The TMA-streamed forward (algo 3; what `auto` picks for F = 5, dilation 1, W % 4 == 0) equals the tiled kernel
+    """The TMA-streamed forward and backward (algo 3; what `auto` picks for F = 5, dilation 1, W % 4 == 0) equals the tiled kernel
     (algo 2) BIT FOR BIT -- same tap order and contractions -- and both match the oracle, including ragged tile edges
     and offsets far outside the staged halo (clamp-to-edge fallback)."""
     from fvfi import adacof
@@ -58,6 +58,14 @@ def test_forward_algorithms_agree(shape):
     o0 = adacof.adacof_forward(*t, d, algo_=0)
     assert torch.equal(o3, o2) and torch.equal(o0, o3)
     assert np.abs(o3.cpu().numpy() - oa.forward(inp, w, oi, oj, d, threads=4)).max() <= TOL_FWD
+    g = torch.randn(o3.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    b3 = adacof.adacof_backward(g, *t, d, "none", algo_=3)
+    b2 = adacof.adacof_backward(g, *t, d, "none", algo_=2)
+    for x3, x2 in zip(b3[1:], b2[1:]):
+        assert torch.equal(x3, x2)
+    rg = oa.backward(g.cpu().numpy(), inp, w, oi, oj, d, threads=4)
+    for x3, r in zip(b3[1:], rg):
+        assert np.abs(x3.cpu().numpy() - r).max() <= TOL_BWD
     with pytest.raises(Exception):
         adacof.adacof_forward(*_dev(*oa.synth(1, 3, 24, 40, 3, 1, seed=1)[:4]), 1, algo_=3)   # F = 3: not applicable
 
