@@ -263,6 +263,7 @@ FVFI_HD void fft_stage_impl(const FftPlan& P, int s, const float2* in, float2* o
     const int M = P.M, items = M / R, total = batch * items;
     const int sub = P.sub[s];
     const unsigned mag_sub = P.mag_sub[s], mag_items = P.mag_items[s];
+    const float2* tw = P.tw;             // hoisted: the plan is in global memory and the stage stores could alias it
     constexpr bool LINEAR = COL || !PAD;
     for (int q = cx.tid; q < total; q += cx.nthr) {
         int b, t;
@@ -287,7 +288,7 @@ FVFI_HD void fft_stage_impl(const FftPlan& P, int s, const float2* in, float2* o
 #pragma unroll
                 for (int u = 0; u < R; ++u) v[u] = in[fft_addr<COL>(b, t + u * items, ctshift, pitch, 1)];
             }
-            if (Ns > 1) twiddle_powers<R>(v, ldg_(P.tw + k * (M / (Ns * R))));
+            if (Ns > 1) twiddle_powers<R>(v, ldg_(tw + k * (M / (Ns * R))));
             dft(v, Radix<R>());
             const int o = hi * Ns * R + k;
             if (LINEAR) {
@@ -309,9 +310,9 @@ FVFI_HD void fft_stage_impl(const FftPlan& P, int s, const float2* in, float2* o
 #pragma unroll
             for (int u = 0; u < R; ++u)
                 v[u] = LINEAR ? in[a0 + u * st] : in[fft_addr<COL>(b, base + u * m, ctshift, pitch, 1)];
-            if (KIND == FFT_DIT && m > 1) twiddle_powers<R>(v, ldg_(P.tw + j * (M / (R * m))));
+            if (KIND == FFT_DIT && m > 1) twiddle_powers<R>(v, ldg_(tw + j * (M / (R * m))));
             dft(v, Radix<R>());
-            if (KIND == FFT_DIF && m > 1) twiddle_powers<R>(v, ldg_(P.tw + j * (M / (R * m))));
+            if (KIND == FFT_DIF && m > 1) twiddle_powers<R>(v, ldg_(tw + j * (M / (R * m))));
             if (KIND == FFT_DIF && post) {                        // Bluestein: spectrum of the chirp filter, then conj
 #pragma unroll
                 for (int u = 0; u < R; ++u) v[u] = cconj(cmul(v[u], ldg_(post + base + u * m)));
@@ -365,18 +366,26 @@ struct FftResult {
     const unsigned short* perm;  // non-null: position p holds natural index perm[p]
 };
 
+// What fft_put / fft_get need from a plan, read ONCE per kernel (the plan lives in global memory: re-reading `bluestein` / `pad`
+// per element put an L1 round trip on every load and store of the prologue / epilogue loops).
+struct FftIO {
+    int bluestein, pad;
+    const float2* chirp;
+};
+FVFI_HD FftIO fft_io(const FftPlan& P) { return FftIO{P.bluestein, P.pad, P.chirp}; }
+
 // Callers WRITE their input through fft_put (Bluestein: the chirp is applied on the way in) ...
 template <bool COL>
-FVFI_HD void fft_put(const FftPlan& P, float2* buf, int b, int i, float2 v, int ctshift, int pitch) {
-    if (P.bluestein) v = cmul(v, ldg_(P.chirp + i));
-    buf[fft_addr<COL>(b, i, ctshift, pitch, P.pad)] = v;
+FVFI_HD void fft_put(const FftIO& io, float2* buf, int b, int i, float2 v, int ctshift, int pitch) {
+    if (io.bluestein) v = cmul(v, ldg_(io.chirp + i));
+    buf[fft_addr<COL>(b, i, ctshift, pitch, io.pad)] = v;
 }
 // ... and READ the result through fft_get (Bluestein: conj + chirp on the way out).  pos < n; the natural index
 // of the value is R.perm ? R.perm[pos] : pos.
 template <bool COL>
-FVFI_HD float2 fft_get(const FftPlan& P, const FftResult& R, int b, int pos, int ctshift, int pitch) {
-    const float2 v = R.buf[fft_addr<COL>(b, pos, ctshift, pitch, P.pad)];
-    return P.bluestein ? cmul(cconj(v), ldg_(P.chirp + pos)) : v;
+FVFI_HD float2 fft_get(const FftIO& io, const FftResult& R, int b, int pos, int ctshift, int pitch) {
+    const float2 v = R.buf[fft_addr<COL>(b, pos, ctshift, pitch, io.pad)];
+    return io.bluestein ? cmul(cconj(v), ldg_(io.chirp + pos)) : v;
 }
 
 // Forward DFT of `batch` sequences of logical length P.n, written with fft_put at positions [0, n) of `a`

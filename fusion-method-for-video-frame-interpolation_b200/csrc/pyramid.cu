@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_fwd(const Le
     const int y0 = (blockIdx.x - E.start) * rb;
     const int rows = min(rb, h - y0);
     const int pitch = fft_row_pitch(J.fx.M, J.fx.pad);
+    const FftIO iox = fft_io(J.fx);
     float2* a = smem;
     float2* bq = smem + (size_t)rb * pitch;
     const unsigned mag_w = J.mag_w;
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_fwd(const Le
                     sincosf(z[u].x, &sn, &cs);
                     v = make_float2(cs * z[u].y, sn * z[u].y);  // pyramid.py:105-106
                 }
-                fft_put<false>(J.fx, a, r, x, v, 0, pitch);
+                fft_put<false>(iox, a, r, x, v, 0, pitch);
             }
         }
     }
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_fwd(const Le
     float2* dst = regionB + (size_t)N * J.t_off + ((size_t)n * nbB + b) * plane + (size_t)y0 * w;
     for (int q = threadIdx.x; q < rows * w; q += blockDim.x) {
         const int r = (int)fast_div((unsigned)q, (unsigned)w, mag_w), x = q - r * w;
-        dst[q] = fft_get<false>(J.fx, R, r, x, 0, pitch);
+        dst[q] = fft_get<false>(iox, R, r, x, 0, pitch);
     }
 }
 
@@ -442,6 +443,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_fwd(const Le
     const int x0 = (blockIdx.x - E.start) << cs;
     const int cols = min(CT, w - x0);
     const int E_ = h << cs;
+    const FftIO ioy = fft_io(J.fy);
     float2* a = smem;
     float2* acc = smem + ((size_t)J.fy.M << cs);
     const size_t plane = (size_t)h * w;
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_fwd(const Le
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int q = q0 + u * blockDim.x;
-                    if (q < E_) fft_put<true>(J.fy, a, q & (CT - 1), q >> cs, z[u], cs, 0);
+                    if (q < E_) fft_put<true>(ioy, a, q & (CT - 1), q >> cs, z[u], cs, 0);
                 }
             }
         }
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_fwd(const Le
                 const int pos = q >> cs, c = q & (CT - 1);
                 const int ky = R.perm ? (int)__ldg(R.perm + pos) : pos;
                 const float g = ang_factor(A, b, sfreq(ky, h), sfreq(min(x0 + c, w - 1), w));
-                const float2 rv = fft_get<true>(J.fy, R, c, pos, cs, 0);
+                const float2 rv = fft_get<true>(ioy, R, c, pos, cs, 0);
                 const float2 v = cmul(make_float2(rv.x * g, rv.y * g), A.fac);
                 acc[q] = (b == 0) ? v : cadd(acc[q], v);
             }
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_fwd(const Le
         const int ky = R.perm ? (int)__ldg(R.perm + pos) : pos;
         const size_t o = (size_t)ky * w + x0 + c;
         const float m = radial ? __ldg(radial + o) : 1.f;
-        const float2 rv = combine ? acc[q] : fft_get<true>(J.fy, R, c, pos, cs, 0);
+        const float2 rv = combine ? acc[q] : fft_get<true>(ioy, R, c, pos, cs, 0);
         dst[o] = make_float2(rv.x * m, rv.y * m);
     }
 }
@@ -512,6 +514,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_decomp(c
     const int x0 = (blockIdx.x - E.start) << cs;
     const int cols = min(CT, w - x0);
     const int E_ = h << cs;
+    const FftIO ioy = fft_io(J.fy);
     const bool band = J.is_band != 0;
     float2* a = smem;
     const float2* Xn = X + (size_t)n * H * W;
@@ -543,7 +546,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_decomp(c
                     float2 v = make_float2(xv[u].x * m[u], xv[u].y * m[u]);
                     if (band) v = cmul(v, A.fac);
                     v.y = -v.y;
-                    fft_put<true>(J.fy, a, q & (CT - 1), q >> cs, v, cs, 0);
+                    fft_put<true>(ioy, a, q & (CT - 1), q >> cs, v, cs, 0);
                 }
             }
         }
@@ -555,7 +558,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_decomp(c
         const int pos = q >> cs, c = q & (CT - 1);
         if (c >= cols) continue;
         const int y = R.perm ? (int)__ldg(R.perm + pos) : pos;
-        dst[(size_t)y * w + x0 + c] = fft_get<true>(J.fy, R, c, pos, cs, 0);
+        dst[(size_t)y * w + x0 + c] = fft_get<true>(ioy, R, c, pos, cs, 0);
     }
 }
 
@@ -580,6 +583,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_gather(c
     const int x0 = blockIdx.x << cs, n = blockIdx.z, N = gridDim.z;
     const int cols = min(CT, W - x0);
     const int E_ = H << cs;
+    const FftIO ioy = fft_io(J.fy);
     float2* a = smem;
     for (int q = threadIdx.x; q < E_; q += blockDim.x) {
         const int ky = q >> cs, c = q & (CT - 1);
@@ -602,7 +606,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_gather(c
             }
             v.y = -v.y;
         }
-        fft_put<true>(J.fy, a, c, ky, v, cs, 0);
+        fft_put<true>(ioy, a, c, ky, v, cs, 0);
     }
     __syncthreads();
     const FftResult R = fft_forward<true>(J.fy, a, nullptr, CT, cs, 0, true, FftCtx{(int)threadIdx.x, (int)blockDim.x});
@@ -611,7 +615,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_gather(c
         const int pos = q >> cs, c = q & (CT - 1);
         if (c >= cols) continue;
         const int y = R.perm ? (int)__ldg(R.perm + pos) : pos;
-        dst[(size_t)y * W + x0 + c] = fft_get<true>(J.fy, R, c, pos, cs, 0);
+        dst[(size_t)y * W + x0 + c] = fft_get<true>(ioy, R, c, pos, cs, 0);
     }
 }
 
@@ -636,6 +640,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_inv(const Le
     const int y0 = (blockIdx.x - E.start) * rb;
     const int rows = min(rb, h - y0);
     const int pitch = fft_row_pitch(J.fx.M, J.fx.pad);
+    const FftIO iox = fft_io(J.fx);
     float2* a = smem;
     float2* bq = smem + (size_t)rb * pitch;
     const unsigned mag_w = J.mag_w;
@@ -656,7 +661,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_inv(const Le
                 const int q = q0 + u * blockDim.x;
                 if (q < total) {
                     const int r = (int)fast_div((unsigned)q, (unsigned)w, mag_w), x = q - r * w;
-                    fft_put<false>(J.fx, a, r, x, z[u], 0, pitch);
+                    fft_put<false>(iox, a, r, x, z[u], 0, pitch);
                 }
             }
         }
@@ -667,14 +672,15 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_inv(const Le
     float mx = 0.f;
     for (int q = threadIdx.x; q < rows * w; q += blockDim.x) {
         const int r = (int)fast_div((unsigned)q, (unsigned)w, mag_w), x = q - r * w;
-        const float2 t = fft_get<false>(J.fx, R, r, x, 0, pitch);
+        const float2 t = fft_get<false>(iox, R, r, x, 0, pitch);
         const float2 z = make_float2(t.x * scale, -t.y * scale);
         const size_t pix = (size_t)y0 * w + q;
         if (mode == 0) {
             E.q0[(size_t)n * plane + pix] = z.x;
         } else if (mode == 1) {
             const size_t o = ((size_t)n * nbB + b) * plane + pix;
-            const float am = sqrtf(z.x * z.x + z.y * z.y);       // torch.abs            (pyramid.py:67)
+            const float ss = fmaf(z.x, z.x, z.y * z.y);
+            const float am = ss > 0.f ? ss * rsqrtf(ss) : 0.f;   // torch.abs (pyramid.py:67); rsqrt form: 2 ulp, 3 instructions
             E.q0[o] = fast_atan2f(z.y, z.x);                     // imag(log z)          (pyramid.py:63)
             E.q1[o] = am;
             mx = fmaxf(mx, am);

@@ -27,14 +27,14 @@ extern "C" int fft_host_run(int n, int mode, int batch, const float* in, float* 
     for (int bb = 0; bb < batch; ++bb)
         for (int i = 0; i < n; ++i) {
             const float2 v = make_float2(in[((size_t)bb * n + i) * 2], in[((size_t)bb * n + i) * 2 + 1]);
-            if (col) fft_put<true>(H.p, a.data(), bb, i, v, ctshift, pitch);
-            else fft_put<false>(H.p, a.data(), bb, i, v, ctshift, pitch);
+            if (col) fft_put<true>(fft_io(H.p), a.data(), bb, i, v, ctshift, pitch);
+            else fft_put<false>(fft_io(H.p), a.data(), bb, i, v, ctshift, pitch);
         }
     FftResult r = col ? fft_forward<true>(H.p, a.data(), b.data(), batch, ctshift, pitch, true, FftCtx{0, 1})
                       : fft_forward<false>(H.p, a.data(), b.data(), batch, ctshift, pitch, false, FftCtx{0, 1});
     for (int bb = 0; bb < batch; ++bb)
         for (int pos = 0; pos < n; ++pos) {
-            const float2 v = col ? fft_get<true>(H.p, r, bb, pos, ctshift, pitch) : fft_get<false>(H.p, r, bb, pos, ctshift, pitch);
+            const float2 v = col ? fft_get<true>(fft_io(H.p), r, bb, pos, ctshift, pitch) : fft_get<false>(fft_io(H.p), r, bb, pos, ctshift, pitch);
             const int k = r.perm ? r.perm[pos] : pos;
             out[((size_t)bb * n + k) * 2] = v.x;
             out[((size_t)bb * n + k) * 2 + 1] = v.y;
