@@ -76,7 +76,8 @@ struct LevelJob {
 };
 
 struct SetEntry {
-    int job, start, mode, pad_;
+    int job, start, mode;
+    float scale;             // row-pass output scale; 0 = the IFFT normalisation 1/(h*w)
     const float* p0;
     const float* p1;
     float* q0;
@@ -625,6 +626,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_gather(c
 //   mode 1: polar: phase -> q0, amplitude -> q1 at channel n*nb + b; per-plane max amplitude -> aux[n]
 //           (pyramid.py:63-69, phase_net.py:47-59)
 //   mode 2: complex interleaved -> tab.p[b][n][y][x][2]
+//   mode 3: backward of the reconstruction: z is dL/d(band); with phase = p0, amplitude = p1 -> dL/dphase -> q0, dL/damp -> q1
 // grid: (row tiles of all jobs, nb, N)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_inv(const LevelJob* __restrict__ jobs, const LaunchSet S, MutPtrTable tab,
@@ -668,7 +670,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_inv(const Le
     }
     __syncthreads();
     const FftResult R = fft_forward<false>(J.fx, a, bq, rows, 0, pitch, false, FftCtx{(int)threadIdx.x, (int)blockDim.x});
-    const float scale = 1.f / ((float)h * (float)w);
+    const float scale = E.scale > 0.f ? E.scale : 1.f / ((float)h * (float)w);
     float mx = 0.f;
     for (int q = threadIdx.x; q < rows * w; q += blockDim.x) {
         const int r = (int)fast_div((unsigned)q, (unsigned)w, mag_w), x = q - r * w;
@@ -684,6 +686,13 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_inv(const Le
             E.q0[o] = fast_atan2f(z.y, z.x);                     // imag(log z)          (pyramid.py:63)
             E.q1[o] = am;
             mx = fmaxf(mx, am);
+        } else if (mode == 3) {
+            // adjoint of values_to_coeff (pyramid.py:103-108): z = A (cos phi, sin phi), z_bar = dL/d(re, im)
+            const size_t o = ((size_t)n * nbB + b) * plane + pix;
+            float sn, cs;
+            sincosf(__ldg(E.p0 + o), &sn, &cs);
+            E.q0[o] = __ldg(E.p1 + o) * (z.y * cs - z.x * sn);     // dL/dphi
+            E.q1[o] = z.x * cs + z.y * sn;                         // dL/dA
         } else {
             ((float2*)tab.p[b])[(size_t)n * plane + pix] = z;
         }
@@ -718,9 +727,11 @@ struct SetBuilder {
     explicit SetBuilder(const fvfi_pyr_plan* plan) : p(plan) {}
     bool full() const { return rows.n >= MAX_SET; }
     bool empty() const { return rows.n == 0; }
-    void add(int job, int mode, const float* p0, const float* p1, float* q0, float* q1, float* aux, bool combine_cols) {
+    void add(int job, int mode, const float* p0, const float* p1, float* q0, float* q1, float* aux, bool combine_cols,
+             float scale = 0.f) {
         const LevelJob& J = p->jobs[job];
         SetEntry e{};
+        e.scale = scale;
         e.job = job; e.mode = mode; e.p0 = p0; e.p1 = p1; e.q0 = q0; e.q1 = q1; e.aux = aux;
         e.start = rows.total;
         rows.e[rows.n++] = e;
@@ -753,12 +764,13 @@ static int launch_cols_fwd(const fvfi_pyr_plan* p, const SetBuilder& sb, int N, 
     return FVFI_OK;
 }
 
-static int launch_cols_inv_decomp(const fvfi_pyr_plan* p, const SetBuilder& sb, int N, const float2* X, float2* regionB, cudaStream_t s) {
+static int launch_cols_inv_decomp(const fvfi_pyr_plan* p, const SetBuilder& sb, int N, const float2* X, float2* regionB, cudaStream_t s,
+                                  const AngParams* ang = nullptr) {
     if (int rc = ensure_smem(k_cols_inv_decomp, sb.cols_smem)) return rc;
     int nbmax = 1;
     for (int i = 0; i < sb.cols.n; ++i) nbmax = std::max(nbmax, p->jobs[sb.cols.e[i].job].nb);
     dim3 grid(sb.cols.total, nbmax, N);
-    k_cols_inv_decomp<<<grid, PYR_THREADS, sb.cols_smem, s>>>(p->d_jobs, sb.cols, p->ang_build, p->H, p->W, X, regionB);
+    k_cols_inv_decomp<<<grid, PYR_THREADS, sb.cols_smem, s>>>(p->d_jobs, sb.cols, ang ? *ang : p->ang_build, p->H, p->W, X, regionB);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }
@@ -917,6 +929,57 @@ static int reconstruct(const fvfi_pyr_plan* p, const float* high, const float* c
     return launch_rows_inv(p, fin, mnone, N, ws.B, s);
 }
 
+// Backward of reconstruct(): img = Re M(high, bands, low) is real-linear in the complex bands, so dL/d(band) = M^H dL/d(img):
+//   FFT2 of the image gradient, then per level the SAME crop / radial mask as the forward, the conjugated two-sided angular
+//   factor, an unnormalised IFFT2 at the level size and 1/(H*W) -- i.e. the decomposition machinery with the reconstruction's
+//   masks.  The row-pass epilogue chains through z = A e^{i phi} (mode 3) or takes the real part (high / low).
+static int reconstruct_backward(const fvfi_pyr_plan* p, const float* gimg, int N, const float* const* phase,
+                                const float* const* amp, float* ghigh, float* const* gphase, float* const* gamp, float* glow,
+                                void* workspace, cudaStream_t s) {
+    const int H = p->H, W = p->W, L = p->L;
+    const int FULL = L + 1;
+    Workspace ws = carve(p, N, workspace);
+    PtrTable none{};
+    MutPtrTable mnone{};
+    {
+        SetBuilder sb(p);
+        sb.add(FULL, 0, gimg, nullptr, nullptr, nullptr, nullptr, false);
+        if (int rc = launch_rows_fwd(p, sb, none, N, ws.B, s)) return rc;
+        if (int rc = launch_cols_fwd(p, sb, N, ws.B, ws.A, (size_t)H * W, 0, 0, s)) return rc;
+    }
+    AngParams adj = p->ang_rec;
+    adj.fac.y = -adj.fac.y;                      // conj((i)^(nb-1))
+    const float scale = 1.f / ((float)H * (float)W);
+    SetBuilder small(p);
+    auto flush = [&](SetBuilder& sb) -> int {
+        if (sb.empty()) return FVFI_OK;
+        if (int rc = launch_cols_inv_decomp(p, sb, N, ws.A, ws.B, s, &adj)) return rc;
+        if (int rc = launch_rows_inv(p, sb, mnone, N, ws.B, s)) return rc;
+        sb = SetBuilder(p);
+        return FVFI_OK;
+    };
+    auto submit = [&](int job, int mode, const float* p0, const float* p1, float* q0, float* q1) -> int {
+        if (is_small(p->jobs[job])) {
+            small.add(job, mode, p0, p1, q0, q1, nullptr, false, scale);
+            if (small.full()) return flush(small);
+            return FVFI_OK;
+        }
+        SetBuilder one(p);
+        one.add(job, mode, p0, p1, q0, q1, nullptr, false, scale);
+        return flush(one);
+    };
+    if (ghigh)
+        if (int rc = submit(FULL, 0, nullptr, nullptr, ghigh, nullptr)) return rc;
+    for (int l = 0; l < L; ++l) {
+        if (!gphase[l] || !gamp[l]) continue;
+        if (!phase[l] || !amp[l]) { set_error("pyr_reconstruct_backward: level %d gradient requested without its values", l); return FVFI_EINVAL; }
+        if (int rc = submit(l, 3, phase[l], amp[l], gphase[l], gamp[l])) return rc;
+    }
+    if (glow)
+        if (int rc = submit(L, 0, nullptr, nullptr, glow, nullptr)) return rc;
+    return flush(small);
+}
+
 }  // namespace fvfi
 
 using namespace fvfi;
@@ -982,6 +1045,15 @@ int fvfi_pyr_reconstruct_complex(const fvfi_pyr_plan* p, const float* high, cons
                                  const float* low, int N, float* img, void* workspace, void* stream) {
     FVFI_CHECK_ARG(p && bands && img && workspace && N > 0 && N <= 65535, "pyr_reconstruct_complex: bad argument");
     return reconstruct(p, high, nullptr, nullptr, bands, low, N, img, workspace, (cudaStream_t)stream);
+}
+
+int fvfi_pyr_reconstruct_backward(const fvfi_pyr_plan* p, const float* grad_img, int N, const float* const* phase,
+                                  const float* const* amp, float* grad_high, float* const* grad_phase,
+                                  float* const* grad_amp, float* grad_low, void* workspace, void* stream) {
+    FVFI_CHECK_ARG(p && grad_img && phase && amp && grad_phase && grad_amp && workspace && N > 0 && N <= 65535,
+                   "pyr_reconstruct_backward: bad argument");
+    return reconstruct_backward(p, grad_img, N, phase, amp, grad_high, grad_phase, grad_amp, grad_low, workspace,
+                                (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -23,6 +23,53 @@ DecompValues = namedtuple(
 )
 
 
+class _InvFilterFn(torch.autograd.Function):
+    """Pyramid.inv_filter with a backward (fvfi_pyr_reconstruct_backward): what PhaseNet training needs to push the L1 image
+    loss through the reconstruction (src/train/trainer.py:139-147).  Inputs: plan, L, high-or-None, low-or-None, then the L
+    phase tensors and the L amplitude tensors (None = level absent)."""
+
+    @staticmethod
+    def forward(ctx, plan, L, high, low, *levels):
+        phase, amp = list(levels[:L]), list(levels[L:])
+        ref = next(t for t in [high, low] + phase + amp if t is not None)
+        N = (high if high is not None else low).shape[0]
+        H, W = plan.H, plan.W
+        out = torch.empty((N, H, W), dtype=torch.float32, device=ref.device)
+        with torch.cuda.device(ref.device):
+            _lib.check(_lib.lib().fvfi_pyr_reconstruct(plan.handle, _lib.ptr(high), ptr_array(phase), ptr_array(amp),
+                                                       _lib.ptr(low), N, out.data_ptr(), plan.workspace(N).data_ptr(),
+                                                       _lib.stream_ptr()))
+        ctx.plan, ctx.L, ctx.N = plan, L, N
+        ctx.has = (high is not None, low is not None)
+        ctx.save_for_backward(*[t for t in phase + amp if t is not None])
+        ctx.present = [t is not None for t in phase]
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        plan, L, N = ctx.plan, ctx.L, ctx.N
+        saved = list(ctx.saved_tensors)
+        npres = sum(ctx.present)
+        ph_s, am_s = saved[:npres], saved[npres:]
+        phase, amp, gph, gam = [None] * L, [None] * L, [None] * L, [None] * L
+        it = 0
+        for l in range(L):
+            if ctx.present[l]:
+                phase[l], amp[l] = ph_s[it], am_s[it]
+                gph[l], gam[l] = torch.empty_like(ph_s[it]), torch.empty_like(am_s[it])
+                it += 1
+        g = gout.contiguous().float()
+        new = lambda *s: torch.empty(s, dtype=torch.float32, device=g.device)
+        ghigh = new(N, 1, plan.H, plan.W) if ctx.has[0] else None
+        glow = new(N, 1, *plan.shapes[-1]) if ctx.has[1] else None
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().fvfi_pyr_reconstruct_backward(plan.handle, g.data_ptr(), N, ptr_array(phase), ptr_array(amp),
+                                                                _lib.ptr(ghigh), ptr_array(gph), ptr_array(gam),
+                                                                _lib.ptr(glow), plan.workspace(N).data_ptr(),
+                                                                _lib.stream_ptr()))
+        return (None, None, ghigh, glow) + tuple(gph) + tuple(gam)
+
+
 class Pyramid:
     """ Steerable Pyramid Decomposition (B200-native). """
 
@@ -81,6 +128,11 @@ class Pyramid:
         phase = [prep(t) for t in vals.phase]
         amp = [prep(t) for t in vals.amplitude]
         high_c, low_c = prep(high), prep(vals.low_level)
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in phase + amp + [high_c, low_c]):
+            for l in range(len(phase)):            # a level is used only if both of its tensors are present
+                if phase[l] is None or amp[l] is None:
+                    phase[l] = amp[l] = None
+            return _InvFilterFn.apply(plan, plan.L, high_c, low_c, *(phase + amp))
         out = torch.empty((N, H, W), dtype=torch.float32, device=high.device)
         with torch.cuda.device(high.device):
             _lib.check(_lib.lib().fvfi_pyr_reconstruct(plan.handle, high_c.data_ptr(), ptr_array(phase), ptr_array(amp),

@@ -184,6 +184,13 @@ int fvfi_pyr_reconstruct(const fvfi_pyr_plan* plan, const float* high, const flo
                          const float* const* amp, const float* low, int N, float* img, void* workspace,
                          void* stream);
 
+/* Backward of fvfi_pyr_reconstruct for PhaseNet training (src/train/trainer.py:139-147 back-propagates the L1 image loss through
+ * Pyramid.inv_filter): grad_img [N,H,W] -> gradients w.r.t. high [N,1,H,W], phase[l] / amp[l] [N*nb,1,h_l,w_l] and low.  A level
+ * whose grad_phase[l] / grad_amp[l] is NULL is skipped; grad_high / grad_low may be NULL.  phase / amp are the forward's inputs. */
+int fvfi_pyr_reconstruct_backward(const fvfi_pyr_plan* plan, const float* grad_img, int N, const float* const* phase,
+                                  const float* const* amp, float* grad_high, float* const* grad_phase,
+                                  float* const* grad_amp, float* grad_low, void* workspace, void* stream);
+
 /* Complex coefficient interface (the SCFpyr_PyTorch.build/reconstruct layout, band tensors
  * [N,h_l,w_l,2], src/train/pyramid.py:58): bands[l*nb + b]. */
 int fvfi_pyr_build_complex(const fvfi_pyr_plan* plan, const float* img, int N, float* high,

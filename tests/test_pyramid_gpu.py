@@ -170,6 +170,54 @@ def test_phase_epilogue_accuracy():
         assert float(vals.phase[l].abs().max()) <= np.pi + 1e-6
 
 
+def test_reconstruct_backward_is_the_adjoint():
+    """fvfi_pyr_reconstruct_backward (autograd of Pyramid.inv_filter, PhaseNet training): (a) exact adjoint identity
+    <g, R(low, high)> = <R^H g, (low, high)> on the linear inputs; (b) the polar inputs against a central difference of the
+    (oracle-verified) forward along a random direction; (c) gradients reach PhaseNet-style leaves and the reference loss."""
+    from fvfi.loss import get_loss
+    from fvfi.pyramid import DecompValues, Pyramid
+    torch.manual_seed(5)
+    N, H, W, height = 2, 90, 150, 8
+    pyr = Pyramid(height=height, nbands=4, scale_factor=S2, device=torch.device("cuda"))
+    vals = pyr.filter(_img(N, H, W, seed=9).cuda())
+    g = torch.randn((N, H, W), device="cuda")
+
+    def leaf(t):
+        return t.clone().requires_grad_(True)
+    ph, am = [leaf(t) for t in vals.phase], [leaf(t) for t in vals.amplitude]
+    lo, hi = leaf(vals.low_level), leaf(vals.high_level)
+    v = DecompValues(high_level=hi, low_level=lo, phase=ph, amplitude=am)
+    rec = pyr.inv_filter(v)
+    assert rec.requires_grad
+    (rec * g).sum().backward()
+    # (a) linear parts: R is linear in (low, high) -> <g, R(0,..,low,high)> == <grad, (low, high)>
+    zero = DecompValues(high_level=vals.high_level, low_level=vals.low_level, phase=[0] * len(ph), amplitude=[0] * len(am))
+    lhs = float((pyr.inv_filter(zero) * g).sum())
+    rhs = float((lo.grad * vals.low_level).sum() + (hi.grad * vals.high_level).sum())
+    assert abs(lhs - rhs) <= 2e-4 * max(abs(lhs), 1.0), (lhs, rhs)
+    # (b) polar parts: directional derivative by central differences of the forward
+    dph, dam = [torch.randn_like(t) for t in vals.phase], [torch.randn_like(t) for t in vals.amplitude]
+    eps = 1e-2
+
+    def fwd(sign):
+        vv = DecompValues(high_level=vals.high_level, low_level=vals.low_level,
+                          phase=[p_ + sign * eps * d for p_, d in zip(vals.phase, dph)],
+                          amplitude=[a_ + sign * eps * d for a_, d in zip(vals.amplitude, dam)])
+        return pyr.inv_filter(vv)
+    num = float(((fwd(+1) - fwd(-1)) * g).sum()) / (2 * eps)
+    ana = float(sum((p_.grad * d).sum() for p_, d in zip(ph, dph)) + sum((a_.grad * d).sum() for a_, d in zip(am, dam)))
+    assert abs(num - ana) <= 5e-3 * max(abs(ana), 1.0), (num, ana)
+    # (c) the reference loss (src/train/loss.py) back-propagates through inv_filter
+    for t in ph + am + [lo, hi]:
+        t.grad = None
+    out = pyr.inv_filter(v)
+    target = torch.rand_like(out)
+    total, p1, p2 = get_loss(v, vals, out, target, pyr)
+    total.backward()
+    assert all(t.grad is not None and bool(torch.isfinite(t.grad).all()) for t in ph + am + [lo])
+    assert float(ph[0].grad.abs().max()) > 0 and float(am[0].grad.abs().max()) > 0
+
+
 def test_4k_plan_round_trip():
     """BASELINE.json configs[3]: 3840x2160, height 19.  Properties that do not need the (slow) oracle at this size:
     perfect reconstruction, linearity, level shapes of the ceil((n - 0.5)/sqrt 2) rule."""
