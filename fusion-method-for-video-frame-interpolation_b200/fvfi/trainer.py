@@ -28,3 +28,41 @@ class FusionTrainer:
         self.bucket.all_reduce_mean(self.group)
         self.optimizer.step()                                    # trainer.py:257-259
         return loss.detach()
+
+
+class PhaseNetTrainer:
+    """PhaseNet training step -- mirror of ``Trainer.predict`` + ``Trainer.train`` of the reference's ``src/train/trainer.py``
+    in ``mode == 'phase'`` (:65-165): decompose frame 1, frame 2 and the target (Lab planes), PhaseNet on the two input
+    pyramids, reconstruct, PhaseNet loss (src/train/loss.py) = L1 on the image + wrapped phase difference per level, Adam.
+    The decomposition needs no gradient; the reconstruction back-propagates through fvfi_pyr_reconstruct_backward; the network
+    runs on torch's autograd convolutions.  Data parallel like FusionTrainer (one flat gradient bucket)."""
+
+    def __init__(self, pyr, phase_net, lr=1e-3, weight_decay=0.0, group=None):
+        from .dist import FlatGradBucket
+        self.pyr, self.net, self.group = pyr, phase_net, group
+        self.net.train()
+        params = [p for p in self.net.parameters() if p.requires_grad]
+        self.bucket = FlatGradBucket(params)
+        self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay)       # trainer.py:40-42
+
+    def predict(self, lab1, lab2, target, m=None):
+        """lab1 / lab2 / target: [P,H,W] Lab planes.  Returns (prediction [P,H,W], vals_pred, vals_target)."""
+        from . import utils
+        P = lab1.shape[0]
+        with torch.no_grad():                                                            # inputs carry no gradient
+            vals = self.pyr.filter(torch.cat((lab1, lab2, target), 0))
+            v1, v2, vt = utils.separate_vals(vals, 3)
+            vals_in = self.net.normalize_vals(utils.get_concat_layers_inf(self.pyr, [v1, v2]))
+        vals_pred = self.net(vals_in, m)
+        prediction = self.pyr.inv_filter(vals_pred)
+        return prediction, vals_pred, vt
+
+    def step(self, lab1, lab2, target, m=None):
+        from .loss import get_loss
+        self.bucket.zero()
+        prediction, vals_pred, vals_target = self.predict(lab1, lab2, target, m)
+        loss, p1, p2 = get_loss(vals_pred, vals_target, prediction, target, self.pyr)      # trainer.py:127-128
+        loss.backward()
+        self.bucket.all_reduce_mean(self.group)
+        self.optimizer.step()
+        return loss.detach()

@@ -207,3 +207,29 @@ def test_pipeline_4k_runs():
     assert out.shape == (1, 3, H, W) and bool(torch.isfinite(out).all())
     assert float(out.min()) >= 0.0 and float(out.max()) <= 1.0
     tc.check_overflow()
+
+
+def test_phasenet_training_step():
+    """PhaseNet training on the new path: loss = L1(image) + wrapped-phase term back-propagates through
+    Pyramid.inv_filter (fvfi_pyr_reconstruct_backward) into every PhaseNet layer; a few Adam steps on a fixed batch lower it."""
+    import math
+    from fvfi.phase_net import PhaseNet
+    from fvfi.pyramid import Pyramid
+    from fvfi.trainer import PhaseNetTrainer
+    from fvfi.utils import calc_pyr_height
+    torch.manual_seed(0)
+    H = W = 64
+    planes = torch.rand((6, H, W), device="cuda")
+    height = calc_pyr_height(planes)
+    pyr = Pyramid(height=height, nbands=4, scale_factor=math.sqrt(2), device=torch.device("cuda"))
+    net = PhaseNet(pyr, torch.device("cuda"), num_img=2)
+    tr = PhaseNetTrainer(pyr, net, lr=1e-3)
+    l1, l2 = planes[:3], planes[3:]
+    target = 0.5 * (l1 + l2)
+    losses = [float(tr.step(l1, l2, target)) for _ in range(6)]
+    assert all(math.isfinite(v) for v in losses)
+    grads = [p.grad for p in net.parameters() if p.requires_grad]
+    assert all(g is not None and bool(torch.isfinite(g).all()) for g in grads)
+    # 64x64 -> 6 pyramid levels -> layers[0..6] are exercised; layers[7] (8 tensors) only exists for deeper pyramids
+    assert sum(float(g.abs().sum()) > 0 for g in grads) >= len(grads) - 8
+    assert losses[-1] < losses[0]
