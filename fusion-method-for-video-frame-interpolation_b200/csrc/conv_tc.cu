@@ -29,6 +29,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -402,29 +403,32 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]) + (A.wide ? __uint_as_float(r1[i]) : 0.f);
             };
-            auto emit = [&](int t, int n0, const float* r, float smax, float sinv) {
+            // softmax epilogue: same, sequential loads (32 instead of 48 live registers next to the loads in flight)
+            auto ld_acc16s = [&](unsigned taddr, float* v) {
+                tc_ld16(taddr, v);
+                if (A.wide) {
+                    float w[16];
+                    tc_ld16(taddr + (unsigned)A.Npad, w);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += w[i];
+                }
+            };
+            // store of one 16-column block of finished values of accumulator tile t
+            auto store16 = [&](int t, int n0, const float* v) {
                 const int ocol = T.x0 + t * 8 + (m & 7);
                 if (!(orow < A.H && ocol < A.W)) return;
                 float* dst = A.out_nchw ? A.y + (size_t)T.img * A.Cout * plane + (size_t)orow * A.W + ocol
                                         : A.y + (((size_t)T.img * A.H + orow) * A.W + ocol) * A.ldy;
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 b4 = *(const float4*)(bias_s + n0 + i);        // smem broadcast
-                    const float z0 = fmaf(r[i], oscale, b4.x), z1 = fmaf(r[i + 1], oscale, b4.y);
-                    const float z2 = fmaf(r[i + 2], oscale, b4.z), z3 = fmaf(r[i + 3], oscale, b4.w);
-                    if (ACT == ACT_SOFTMAX) {
-                        v[i] = __expf(z0 - smax) * sinv; v[i + 1] = __expf(z1 - smax) * sinv;
-                        v[i + 2] = __expf(z2 - smax) * sinv; v[i + 3] = __expf(z3 - smax) * sinv;
-                    } else {
-                        v[i] = apply_act<ACT>(z0); v[i + 1] = apply_act<ACT>(z1);
-                        v[i + 2] = apply_act<ACT>(z2); v[i + 3] = apply_act<ACT>(z3);
-                    }
-                }
                 if (A.out_nchw) {
+                    // 8 consecutive px per row: full 32 B sectors.  Running pointer + one compare per plane (the indexed form
+                    // cost a 64-bit multiply-add per store: 12 instructions per STG, 15 % of the head layers' stall samples)
+                    float* d = dst + (size_t)n0 * plane;
+                    const int nv = A.Cout - n0;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (n0 + i < A.Cout) dst[(size_t)(n0 + i) * plane] = v[i];   // 8 consecutive px per row: full 32 B sectors
+                    for (int i = 0; i < 16; ++i) {
+                        if (i < nv) *d = v[i];
+                        d += plane;
+                    }
                 } else if (vec_out8) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 8)
@@ -439,15 +443,68 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                         if (n0 + i < A.cout_store) dst[n0 + i] = v[i];
                 }
             };
+            auto emit = [&](int t, int n0, const float* r, float smax, float sinv) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 b4 = *(const float4*)(bias_s + n0 + i);        // smem broadcast
+                    const float z0 = fmaf(r[i], oscale, b4.x), z1 = fmaf(r[i + 1], oscale, b4.y);
+                    const float z2 = fmaf(r[i + 2], oscale, b4.z), z3 = fmaf(r[i + 3], oscale, b4.w);
+                    if (ACT == ACT_SOFTMAX) {
+                        v[i] = __expf(z0 - smax) * sinv; v[i + 1] = __expf(z1 - smax) * sinv;
+                        v[i + 2] = __expf(z2 - smax) * sinv; v[i + 3] = __expf(z3 - smax) * sinv;
+                    } else {
+                        v[i] = apply_act<ACT>(z0); v[i + 1] = apply_act<ACT>(z1);
+                        v[i + 2] = apply_act<ACT>(z2); v[i + 3] = apply_act<ACT>(z3);
+                    }
+                }
+                store16(t, n0, v);
+            };
             if (ACT == ACT_SOFTMAX) {
                 // the two warps of a lane quarter take whole tiles (a pixel's softmax needs every channel)
                 for (int t = 0; t < A.MT; ++t) {
                     if (A.MT > 1 ? ((t & 1) != half) : (half != 0)) continue;
                     const unsigned tbase = tq + (unsigned)(t * A.tcols);
+                    if (A.Npad <= 32) {
+                        // the AdaCoF weight heads (25 channels), 16 live values at a time: statistics of columns 16.., then
+                        // columns 0..15 finished and stored, then columns 16.. again -- three TMEM reads and two exps per
+                        // channel pair instead of four reads and three exps per channel of the general two-pass form
+                        float z[16];
+                        float m2 = -INFINITY, s2 = 0.f;
+                        if (A.Npad > 16) {
+                            ld_acc16s(tbase + 16, z);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                z[i] = (16 + i < A.Cout) ? fmaf(z[i], oscale, bias_s[16 + i]) : -INFINITY;
+                                m2 = fmaxf(m2, z[i]);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) s2 += __expf(z[i] - m2);     // exp(-inf) = 0 for the padding
+                        }
+                        ld_acc16s(tbase, z);
+                        float m1 = -INFINITY, s1 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            z[i] = (i < A.Cout) ? fmaf(z[i], oscale, bias_s[i]) : -INFINITY;
+                            m1 = fmaxf(m1, z[i]);
+                        }
+                        const float smax = fmaxf(m1, m2);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { z[i] = __expf(z[i] - smax); s1 += z[i]; }
+                        const float sinv = 1.f / (s1 + (A.Npad > 16 ? s2 * __expf(m2 - smax) : 0.f));
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) z[i] *= sinv;
+                        store16(t, 0, z);
+                        if (A.Npad > 16) {
+                            ld_acc16s(tbase + 16, z);
+                            emit(t, 16, z, smax, sinv);
+                        }
+                        continue;
+                    }
                     float smax = -INFINITY, ssum = 0.f;
                     for (int n0 = 0; n0 < A.Npad; n0 += 16) {          // pass 1 over TMEM: channel max and sum(exp)
                         float v[16];
-                        tc_ld16(tbase + n0, v);          // softmax layers never use the WIDE pairing
+                        ld_acc16s(tbase + n0, v);
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
                             if (n0 + i < A.Cout) {
@@ -459,7 +516,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     const float sinv = 1.f / ssum;
                     for (int n0 = 0; n0 < A.Npad; n0 += 16) {
                         float r[16];
-                        tc_ld16(tbase + n0, r);
+                        ld_acc16s(tbase + n0, r);
                         emit(t, n0, r, smax, sinv);
                     }
                 }
@@ -685,6 +742,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
 }
 
 // ---- host side -----------------------------------------------------------------------------------
+static bool softmax_wide() {      // experiment switch: WIDE pairing for the softmax heads too (FVFI_CONV_SOFTMAX_WIDE=1)
+    static const bool on = [] { const char* e = getenv("FVFI_CONV_SOFTMAX_WIDE"); return e && e[0] == '1'; }();
+    return on;
+}
 static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
     const int chunk = cv_chunk(prec);
     a.Npad = (a.Cout + 15) & ~15;
@@ -696,7 +757,7 @@ static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
     const int taps = a.KH * a.KW;
     const size_t budget = 222 * 1024;
     for (int mt = 4; mt >= 1; mt >>= 1) {
-        a.wide = (a.Npad <= 32 && a.act != ACT_SOFTMAX) ? 1 : 0;     // measured: pays for N <= 32 (two A reads instead of three), not for N = 64 (smaller tiles)
+        a.wide = (a.Npad <= 32 && (a.act != ACT_SOFTMAX || softmax_wide())) ? 1 : 0;     // measured: pays for N <= 32 (two A reads instead of three), not for N = 64 (smaller tiles)
         a.tcols = a.wide ? 2 * a.Npad : a.Npad;
         if (mt * a.tcols > 512) continue;
         if (a.wide && mt > 1 && 2 * mt * a.tcols > 512) continue;      // small-N layers: keep the accumulator double-buffered

@@ -101,6 +101,13 @@ class KernelEstimation(torch.nn.Module):
                 pad = (i + 2 < len(mods) and isinstance(mods[i + 2], torch.nn.Upsample) and m.out_channels % 4 != 0)
                 x = tc.conv_module(m, x, act, nchw_out=nchw_last and i == last_conv, pad_out=pad)
                 i += 2 if act else 1
+            elif (isinstance(m, torch.nn.Upsample) and i + 1 == last_conv and mods[last_conv].out_channels == 1
+                  and m.scale_factor == 2 and m.mode == 'bilinear' and m.align_corners):
+                # occlusion head: Upsample -> Conv2d(64, 1, 3) -> Sigmoid with the channels contracted before upsampling
+                nxt = mods[i + 2] if i + 2 < len(mods) else None
+                act = {torch.nn.ReLU: "relu", torch.nn.Sigmoid: "sigmoid"}.get(type(nxt))
+                x = tc.upsample2_conv3x3_single(mods[last_conv], x, act)
+                i += 3 if act else 2
             elif isinstance(m, torch.nn.Upsample):
                 x = tc.resize_bilinear(x, (x.shape[2] * 2, x.shape[3] * 2), bool(m.align_corners))
                 i += 1

@@ -82,6 +82,9 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
     xc = to_nhwc(x.float())
     assert xc.stride(1) == 1
     ldx = xc.stride(3)                       # floats per pixel
+    if (KH == 1 and Cout <= 8 and Cin % 8 == 0 and Cin <= 128 and ldx % 8 == 0 and xc.data_ptr() % 32 == 0
+            and act != "softmax" and out is None and not nchw_out and not pad_out):
+        return _conv1x1_direct(xc, weight, bias, act)
     if out is None:
         out = torch.empty((B, (Cout + 15) // 16 * 16 if pad_out else Cout, H, W), dtype=torch.float32, device=x.device,
                           memory_format=torch.contiguous_format if nchw_out else torch.channels_last)
@@ -105,6 +108,48 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
         if timing is not None:
             e1.record()
             timing.append((2.0 * B * H * W * Cin * Cout * KH * KW, e0, e1, len(parts), (B, Cin, Cout, KH, H, W, act)))
+    return out
+
+
+def _conv1x1_direct(xc, weight, bias, act):
+    """1x1 convolution with Cout <= 8 as one pass over the NHWC activation (fvfi_conv1x1_nhwc, fp32 FFMA): PhaseNet's
+    per-level prediction (phase_net.py:197-200), FusionNet's last layer (fusion_net.py:36)."""
+    B, _, H, W = xc.shape
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    assert B == 1 or xc.stride(0) == H * W * xc.stride(3)
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=xc.device, memory_format=torch.channels_last)
+    w = weight.detach().reshape(Cout, Cin).contiguous().float()
+    b = None if bias is None else bias.detach().contiguous().float()
+    with torch.cuda.device(xc.device):
+        _lib.check(_lib.lib().fvfi_conv1x1_nhwc(xc.data_ptr(), xc.stride(3), w.data_ptr(), None if b is None else b.data_ptr(),
+                                                out.data_ptr(), out.stride(3), B * H * W, Cin, Cout, ACT[act],
+                                                _lib.stream_ptr()))
+    return out
+
+
+_tap_cache = {}
+
+
+def upsample2_conv3x3_single(conv, x, act=None):
+    """act(conv(Upsample(scale_factor=2, bilinear, align_corners=True)(x))) for a 3x3, zero-padded ``conv`` with ONE output
+    channel (KernelEstimation's occlusion head, fusion_adacofnet.py:50-59,103-104) -> contiguous [B,1,2H,2W].
+    Upsampling and convolution are linear: the C input channels are contracted first, at half resolution, into the nine
+    tap maps (one C -> 9 tensor-core 1x1 convolution), and fvfi_upsample2_tapsum interpolates + sums the shifted taps."""
+    assert conv.out_channels == 1 and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.padding_mode == "zeros"
+    w = conv.weight
+    key = (w.data_ptr(), w._version)
+    hit = _tap_cache.get(id(conv))
+    if hit is None or hit[0] != key:
+        C = w.shape[1]
+        hit = (key, w.detach()[0].reshape(C, 9).t().reshape(9, C, 1, 1).contiguous())     # [tap = ky*3+kx, c]
+        _tap_cache[id(conv)] = hit
+    B, _, H, W = x.shape
+    z = conv2d(x, hit[1], None, "zeros", None, pad_out=True)                              # [B,16,H,W] NHWC, 9 used
+    out = torch.empty((B, 1, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+    b = None if conv.bias is None else conv.bias.detach().contiguous().float()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().fvfi_upsample2_tapsum(z.data_ptr(), z.stride(3), None if b is None else b.data_ptr(),
+                                                    out.data_ptr(), B, H, W, ACT[act], _lib.stream_ptr()))
     return out
 
 

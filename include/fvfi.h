@@ -130,6 +130,22 @@ int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float* packed_wei
  * Synchronises the device. */
 int fvfi_conv2d_overflow_count(void);
 
+/* Direct (CUDA-core, fp32 FFMA) 1x1 convolution for Cout <= 8 -- the layers that are a pure stream of the activation:
+ * PhaseNet's per-level prediction Conv2d(64, 8, 1) + tanh (src/phase_net/phase_net.py:197-200) and FusionNet's last
+ * Conv2d(32, 3, 1) (src/fusion_net/fusion_net.py:36).  x [npix, x_pixel_stride] NHWC pixels (32-byte aligned, Cin a multiple
+ * of 8, <= 128), weight [Cout, Cin] (the OIHW tensor of a 1x1 convolution), bias [Cout] or NULL, y [npix, y_pixel_stride].
+ * activation: 0 none, 1 ReLU, 2 ELU, 3 tanh, 4 sigmoid. */
+int fvfi_conv1x1_nhwc(const float* x, int x_pixel_stride, const float* weight, const float* bias, float* y,
+                      int y_pixel_stride, size_t npix, int Cin, int Cout, int activation, void* stream);
+
+/* Tail of KernelEstimation's occlusion head, Upsample(x2, bilinear, align_corners=True) -> Conv2d(C, 1, 3, padding 1) ->
+ * Sigmoid (src/fusion_net/fusion_adacofnet.py:50-59, 103-104), with the channel contraction done first at half resolution:
+ * z [B,Hi,Wi,z_pixel_stride] holds in channels 0..8 the nine tap maps z_t = sum_c w[0,c,t] x_c (t = ky*3 + kx; a 1x1
+ * convolution C -> 9 of the half-resolution feature), and  y[b,i,j] = act(bias[0] + sum_t [p_t inside] bilinear(z_t)(p_t)),
+ * p_t = (i + ky - 1, j + kx - 1), y [B, 2*Hi, 2*Wi].  Same real-number result as the reference's order of operations. */
+int fvfi_upsample2_tapsum(const float* z, int z_pixel_stride, const float* bias, float* y, int B, int Hi, int Wi,
+                          int activation, void* stream);
+
 /* Bilinear resize of NHWC tensors (torch.nn.Upsample / F.interpolate 'bilinear' semantics, both align_corners
  * modes; src/fusion_net/fusion_adacofnet.py:31, src/fusion_net/fusion_net.py:41, src/phase_net/phase_net.py:138-139).
  * x [B,Hi,Wi,C] with x_pixel_stride floats per pixel -> y [B,Ho,Wo,C] (may be a channel slice: y_pixel_stride). */

@@ -159,3 +159,41 @@ def test_put_planar_slice():
         buf = torch.zeros((3, 88, 23, 31), device="cuda").contiguous(memory_format=torch.channels_last)
         conv.put_planar(x, buf, off)
         assert torch.equal(buf[:, off:off + C], x) and float(buf[:, :off].abs().max()) == 0 and float(buf[:, off + C:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("Cin,Cout,act,shape", [(64, 8, "tanh", (3, 37, 53)), (128, 8, None, (1, 9, 301)), (32, 3, None, (2, 40, 56)),
+                                                (8, 1, "sigmoid", (1, 5, 7)), (24, 5, "elu", (2, 31, 17))])
+def test_conv1x1_direct_kernel(Cin, Cout, act, shape):
+    """Cout <= 8 1x1 convolutions take the direct fp32 kernel (fvfi_conv1x1_nhwc): PhaseNet prediction 64 -> 8 + tanh
+    (phase_net.py:197-200), FusionNet 32 -> 3 (fusion_net.py:36); also on a channel slice of a wider NHWC tensor."""
+    from fvfi import conv
+    B, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(1)
+    wide = torch.randn((B, Cin + 8, H, W), device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    w = torch.randn((Cout, Cin, 1, 1), device="cuda", generator=g) / Cin ** 0.5
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    fn = {None: lambda t: t, "elu": F.elu, "tanh": torch.tanh, "sigmoid": torch.sigmoid}[act]
+    for x in (wide[:, :Cin].contiguous(memory_format=torch.channels_last), wide[:, :Cin]):
+        n0 = conv._lib.lib().fvfi_launch_count()
+        y = conv.conv2d(x, w, b, "zeros", act)
+        assert conv._lib.lib().fvfi_launch_count() == n0 + 1          # one direct kernel, no tensor-core launch
+        ref = fn(F.conv2d(x.double(), w.double(), b.double()))
+        assert y.shape == ref.shape
+        assert float((y.double() - ref).abs().max()) <= 2e-6 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 17, 23), (1, 64, 34, 60), (1, 16, 1, 9)])
+def test_upsample2_conv_single_channel(B, C, H, W, prec):
+    """Occlusion-head tail (fusion_adacofnet.py:50-59,103-104): Upsample(x2, align_corners=True) -> Conv2d(C, 1, 3) -> Sigmoid with
+    the channels contracted at half resolution (fvfi_upsample2_tapsum) == the reference's order of operations."""
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn((B, C, H, W), device="cuda", generator=g)
+    m = torch.nn.Conv2d(C, 1, 3, 1, 1).cuda()
+    with torch.no_grad():
+        y = conv.upsample2_conv3x3_single(m, x, "sigmoid")
+        up = F.interpolate(x.double(), scale_factor=2, mode="bilinear", align_corners=True)
+        ref = torch.sigmoid(F.conv2d(up, m.weight.double(), m.bias.double(), padding=1))
+    assert y.shape == ref.shape and y.is_contiguous()
+    assert float((y.double() - ref).abs().max()) <= 3e-6
+    conv.check_overflow()
