@@ -100,7 +100,9 @@ __global__ void __launch_bounds__(256) gauss1d_kernel(const float* __restrict__ 
 // ---- exact k x k median (rank k*k/2, window [i - k/2, i + k - k/2 - 1], reflect) -------------------------
 // Order statistics must be exact (scipy's rank filter), so no histogram approximation.
 //
-// Fast path (median_rank_kernel): a CTA owns a 32x16 output tile.  It stages the (32+k-1)x(16+k-1)
+// Fast path (median_rank_kernel): a CTA owns a TW x 16 output tile, TW chosen by the launcher so that the region fills the
+// 8192-entry sorting network (k = 50: 77 x 16 outputs, 126 x 65 = 8190 samples; a 32-wide tile left 36 % of the network
+// sorting padding).  It stages the (TW+k-1)x(16+k-1)
 // neighbourhood as (order-preserving key, position) pairs, BITONIC-SORTS it once in shared memory, and
 // replaces every sample by its RANK in the region.  A window's median is then "the rank-th set bit" of a
 // window-membership bitmap over rank space: one warp per output row builds the bitmap of its first window
@@ -116,11 +118,11 @@ __device__ __forceinline__ float key2f(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-constexpr int MR_TW = 32, MR_TH = 16, MR_THREADS = MR_TH * 32;
+constexpr int MR_TH = 16, MR_THREADS = MR_TH * 32;
 constexpr int MR_MAX_N = 8192;
 
 __global__ void __launch_bounds__(MR_THREADS) median_rank_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                                 int H, int W, int k, int rank, int npad) {
+                                                                 int H, int W, int k, int rank, int npad, int MR_TW) {
     extern __shared__ unsigned long long pairs[];                      // npad (key << 32 | pos)
     const int RW = MR_TW + k - 1, RH = MR_TH + k - 1, n = RW * RH;
     unsigned short* rank_of = (unsigned short*)(pairs + npad);         // n
@@ -143,12 +145,11 @@ __global__ void __launch_bounds__(MR_THREADS) median_rank_kernel(const float* __
     __syncthreads();
     for (int kk = 2; kk <= npad; kk <<= 1) {
         for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < npad; i += MR_THREADS) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = pairs[i], b = pairs[ixj];
-                    if ((a > b) == ((i & kk) == 0)) { pairs[i] = b; pairs[ixj] = a; }
-                }
+            for (int p = threadIdx.x; p < (npad >> 1); p += MR_THREADS) {      // one thread per compare-exchange pair
+                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));           // p with a zero inserted at bit log2(j)
+                const int ixj = i | j;
+                const unsigned long long a = pairs[i], b = pairs[ixj];
+                if ((a > b) == ((i & kk) == 0)) { pairs[i] = b; pairs[ixj] = a; }
             }
             __syncthreads();
         }
@@ -279,8 +280,13 @@ extern "C" int fvfi_median_filter(const float* in, float* out, int N, int H, int
     FVFI_CHECK_ARG(in && out && N > 0 && H > 0 && W > 0 && N <= 65535, "median_filter: bad argument");
     FVFI_CHECK_ARG(size >= 1 && size <= 96, "median_filter: size must be 1..96");
     const int rank = (size * size) / 2;
+    // widest tile whose region fits the sorting network, evened out over the row of tiles
+    int tw = MR_MAX_N / (MR_TH + size - 1) - (size - 1);
+    if (tw > W) tw = W;
+    if (tw >= 1) tw = ceil_div(W, ceil_div(W, tw));
+    const int MR_TW = tw;
     const int n = (MR_TW + size - 1) * (MR_TH + size - 1);
-    if (n <= MR_MAX_N) {
+    if (MR_TW >= 8 && n <= MR_MAX_N) {
         int npad = 1;
         while (npad < n) npad <<= 1;
         const int nwords = (n + 31) / 32, wpl = (nwords + 31) / 32;
@@ -288,7 +294,7 @@ extern "C" int fvfi_median_filter(const float* in, float* out, int N, int H, int
         if (smem > 48 * 1024)
             FVFI_CUDA(cudaFuncSetAttribute(median_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(ceil_div(W, MR_TW), ceil_div(H, MR_TH), N);
-        median_rank_kernel<<<grid, MR_THREADS, smem, (cudaStream_t)stream>>>(in, out, H, W, size, rank, npad);
+        median_rank_kernel<<<grid, MR_THREADS, smem, (cudaStream_t)stream>>>(in, out, H, W, size, rank, npad, MR_TW);
         FVFI_LAUNCH_CHECK();
         return FVFI_OK;
     }
