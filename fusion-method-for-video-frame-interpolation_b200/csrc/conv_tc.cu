@@ -30,6 +30,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -40,9 +41,17 @@ constexpr int CV_UMAX = 12;             // (pixel, K chunk) items a loader threa
 constexpr int CV_HDR = 32;              // floats of header in front of the packed weights (scales, precision)
 constexpr int CV_X_SHIFT = 4;           // PREC_F16X3: activations are scaled by 2^4 before the fp16 split
 constexpr int CV_ROWS = 16;             // output rows per CTA
-constexpr int CV_LOADER_WARPS = 8;      // warps 0-7: activation loaders + epilogue (two warps per TMEM lane quarter)
+constexpr int CV_LOADER_WARPS = 8;      // warps 0-7 (two warpgroups): activation loaders
 constexpr int CV_LOADERS = 32 * CV_LOADER_WARPS;
-constexpr int CV_THREADS = CV_LOADERS + 64;   // + weight producer warp + MMA warp
+constexpr int CV_EPI_WARPS = 4;         // warps 8-11 (one warpgroup): epilogue, warp w owns TMEM lanes 32*(w % 4) .. +31
+constexpr int CV_EPI_THREADS = 32 * CV_EPI_WARPS;
+constexpr int CV_PRODUCER_WARP = CV_LOADER_WARPS + CV_EPI_WARPS;      // warp 12: weight producer
+constexpr int CV_MMA_WARP = CV_PRODUCER_WARP + 1;                     // warp 13: TMEM allocator + MMA issuer; 14, 15 fill the warpgroup
+constexpr int CV_THREADS = CV_LOADERS + CV_EPI_THREADS + 128;
+// Register budget per role (setmaxnreg, per warpgroup): the launch gives every thread 65536 / 512 = 128; the epilogue and
+// producer/MMA warpgroups hand most of theirs to the loaders, which keep a whole K chunk of a tile in flight in registers.
+constexpr int CV_REGS_LOADER = 184, CV_REGS_EPI = 80, CV_REGS_MISC = 56;
+static_assert(CV_LOADERS * CV_REGS_LOADER + CV_EPI_THREADS * CV_REGS_EPI + 128 * CV_REGS_MISC <= 65536, "register pool");
 constexpr int CV_MAX_ASTAGES = 4;
 constexpr int CV_MAX_BSTAGES = 4;
 constexpr unsigned CV_SPIN_LIMIT = 200u * 1000u * 1000u;   // bounded waits: trap instead of hanging the GPU
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
     unsigned long long* b_full = bars + 2 * CV_MAX_ASTAGES;                     // [bstages] count 1 + tx
     unsigned long long* b_empty = b_full + CV_MAX_BSTAGES;                      // [bstages] count 1 (tcgen05.commit)
     unsigned long long* acc_full = b_empty + CV_MAX_BSTAGES;                    // [2] count 1 (tcgen05.commit)
-    unsigned long long* acc_empty = acc_full + 2;                               // [2] count CV_LOADERS
+    unsigned long long* acc_empty = acc_full + 2;                               // [2] count CV_EPI_THREADS
     unsigned* tmem_ptr = (unsigned*)(acc_empty + 2);
     int* pixoff = (int*)(tmem_ptr + 2);                      // [NPIX] global pixel index of every region pixel, -1 = zero pad
     float* bias_s = (float*)(((size_t)(pixoff + A.NPIX) + 15) & ~(size_t)15);   // [Npad], 16 B aligned
@@ -351,10 +360,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
     if (threadIdx.x == 0) {
         for (int s = 0; s < A.astages; ++s) { mbar_init(&a_full[s], CV_LOADERS); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < A.bstages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], CV_LOADERS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], CV_EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == CV_LOADER_WARPS + 1) {   // TMEM allocation by one warp
+    for (int n = threadIdx.x; n < A.Npad; n += CV_THREADS) bias_s[n] = (A.bias && n < A.Cout) ? __ldg(A.bias + n) : 0.f;
+    if (warp == CV_MMA_WARP) {   // TMEM allocation by one warp
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(A.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -363,28 +373,18 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
     tc_fence_after();
     const unsigned tmem = *tmem_ptr;
 
-    if (warp < CV_LOADER_WARPS) {
-        // ================= activation loaders (region -> hi/lo canonical tiles) + epilogue =================
-        const int padT = A.KH / 2, padL = A.KW / 2;
-        // 16-byte loads need aligned pixels; a channel count that is not a multiple of 4 is fine when the pixel stride
-        // leaves room for the rounded-up group (the producer zero-fills the padding channels, see out layout 2)
-        const int cin4 = (A.Cin + 3) & ~3;
-        const bool vec = ((A.ldx & 3) == 0) && (A.ldx >= cin4) && ((((size_t)A.x) & 15) == 0);
-        const int cin8 = (A.Cin + 7) & ~7;
-        const bool vec8 = ((A.ldx & 7) == 0) && (A.ldx >= cin8) && ((((size_t)A.x) & 31) == 0);
-        for (int n = threadIdx.x; n < A.Npad; n += CV_LOADERS) bias_s[n] = (A.bias && n < A.Cout) ? __ldg(A.bias + n) : 0.f;
-        constexpr int CPK = cv_cpk(PREC);
-        constexpr int CHUNK = cv_chunk(PREC);
-        constexpr int U = (PREC == PREC_F16X3) ? 4 : 6;            // loads in flight per thread
-        const float xs = (float)(1 << CV_X_SHIFT);
+    if (warp >= CV_LOADER_WARPS && warp < CV_PRODUCER_WARP) {
+        // ================= epilogue warpgroup: TMEM -> registers -> bias/activation -> global =================
+        // Dedicated warps (the loaders used to run the epilogue between their two load phases: on the small-N full-resolution
+        // layers, where a tile's MMAs take ~6k cycles, the loader path -- epilogue included -- took ~14k and the tensor
+        // pipe idled 54 % of the time, profiles/r01_conv_head_summary.txt).
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CV_REGS_EPI));
         const float oscale = __ldg(A.hdr);                         // exact power of two (1 for PREC_TF32X3)
         const bool vec_out = (A.cout_store & 3) == 0 && (A.ldy & 3) == 0 && ((((size_t)A.y) & 15) == 0);
         const bool vec_out8 = (A.cout_store & 7) == 0 && (A.ldy & 7) == 0 && ((((size_t)A.y) & 31) == 0);
         const size_t plane = (size_t)A.H * A.W;
-        const int quarter = warp & 3, half = warp >> 2;            // a warp reads TMEM lanes 32*(warp % 4) .. +31
+        const int quarter = warp & 3;                              // a warp reads TMEM lanes 32*(warp % 4) .. +31
         const int m = quarter * 32 + lane;                         // accumulator row = TMEM lane
-        float amax = 0.f;
-        int g = 0;                                                 // running chunk counter of the A ring
 
         // ---- epilogue of tile number jt (coordinates T): TMEM -> registers -> bias/activation -> global
         auto epilogue = [&](int jt, const TileCoord& T) {
@@ -461,9 +461,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                 store16(t, n0, v);
             };
             if (ACT == ACT_SOFTMAX) {
-                // the two warps of a lane quarter take whole tiles (a pixel's softmax needs every channel)
                 for (int t = 0; t < A.MT; ++t) {
-                    if (A.MT > 1 ? ((t & 1) != half) : (half != 0)) continue;
                     const unsigned tbase = tq + (unsigned)(t * A.tcols);
                     if (A.Npad <= 32) {
                         // the AdaCoF weight heads (25 channels), 16 live values at a time: statistics of columns 16.., then
@@ -521,9 +519,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     }
                 }
             } else {
-                // the two warps of a lane quarter take alternate 16-column blocks
                 for (int t = 0; t < A.MT; ++t)
-                    for (int n0 = ((t & 1) != half) ? 16 : 0; n0 < A.Npad; n0 += 32) {
+                    for (int n0 = 0; n0 < A.Npad; n0 += 16) {
                         float r[16];
                         ld_acc16(tq + (unsigned)(t * A.tcols + n0), r);
                         emit(t, n0, r, 0.f, 1.f);
@@ -533,9 +530,29 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             mbar_arrive(&acc_empty[buf]);          // this thread's TMEM reads of the buffer are done
         };
 
+        {
+            int j = 0;
+            for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, ++j) epilogue(j, tile_coord(A, tile));
+        }
+    } else if (warp < CV_LOADER_WARPS) {
+        // ================= activation loaders (region -> hi/lo canonical tiles) =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CV_REGS_LOADER));
+        const int padT = A.KH / 2, padL = A.KW / 2;
+        // 16-byte loads need aligned pixels; a channel count that is not a multiple of 4 is fine when the pixel stride
+        // leaves room for the rounded-up group (the producer zero-fills the padding channels, see out layout 2)
+        const int cin4 = (A.Cin + 3) & ~3;
+        const bool vec = ((A.ldx & 3) == 0) && (A.ldx >= cin4) && ((((size_t)A.x) & 15) == 0);
+        const int cin8 = (A.Cin + 7) & ~7;
+        const bool vec8 = ((A.ldx & 7) == 0) && (A.ldx >= cin8) && ((((size_t)A.x) & 31) == 0);
+        constexpr int CPK = cv_cpk(PREC);
+        constexpr int CHUNK = cv_chunk(PREC);
+        constexpr int U = (PREC == PREC_F16X3) ? 4 : 6;            // loads in flight per thread
+        const float xs = (float)(1 << CV_X_SHIFT);
+        float amax = 0.f;
+        int g = 0;                                                 // running chunk counter of the A ring
+
         // ---- one K chunk = two phases.  issue(): ALL of this thread's 16-byte global loads of the chunk go out at once
-        // (up to UMAX items of CPK channels stay in registers), so the whole chunk is in flight while the thread does
-        // something else (the previous tile's epilogue); finish(): split into hi/lo, store into the A ring.
+        // (up to UMAX items of CPK channels stay in registers); finish(): split into hi/lo, store into the A ring.
         constexpr int UMAX = CV_UMAX;                              // NPIX * 4 <= CV_LOADERS * UMAX (checked on the host)
         float v[UMAX][CPK];
         auto chunk_shape = [&](int c, int& ksh) {
@@ -633,19 +650,15 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             asm volatile("bar.sync 1, %0;" ::"n"(CV_LOADERS) : "memory");
         };
 
-        // Software pipeline over the (tile, chunk) stream: store chunk k, put chunk k+1's loads in flight, and run the
-        // previous tile's epilogue under them.  The epilogue of tile j-1 comes after chunk e_at of tile j is stored: late
-        // enough that the loads are in flight, early enough that tile j's MMAs never wait for it while the loaders wait
-        // for those MMAs to free a ring stage.
-        const int e_at = min(A.nchunks, A.astages) - 1;
-        TileCoord curT = tile_coord(A, blockIdx.x), prevT = curT, nextT = curT;
+        // Stream of (tile, chunk): store chunk k, put chunk k+1's loads in flight.  The A ring (>= 2 stages) lets the
+        // loaders run a stage ahead of the tensor core, which is what hides the load latency of the next chunk.
+        TileCoord curT = tile_coord(A, blockIdx.x), nextT = curT;
         const float* X = A.x + (size_t)curT.img * A.H * A.W * A.ldx;
-        int j = 0;
         if ((int)blockIdx.x < A.ntiles) {
             map_tile(curT);
             issue(0, X);
         }
-        for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, ++j) {
+        for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
             for (int c = 0; c < A.nchunks; ++c) {
                 finish(c);
                 if (c + 1 < A.nchunks) {
@@ -656,14 +669,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     map_tile(nextT);
                     issue(0, X);
                 }
-                if (c == e_at && j > 0) epilogue(j - 1, prevT);
             }
-            prevT = curT;
             curT = nextT;
         }
-        if (j > 0) epilogue(j - 1, prevT);
         if (PREC == PREC_F16X3 && !(amax <= 65504.f) && A.overflow) atomicOr(A.overflow, 1);
-    } else if (warp == CV_LOADER_WARPS) {
+    } else {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CV_REGS_MISC));
+      if (warp == CV_PRODUCER_WARP) {
         // ================= weight producer =================
         if (lane == 0) {
             int it = 0;
@@ -677,7 +689,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                                  A.wpack + ((size_t)c * taps + tp) * (A.b_stage_bytes / 4), A.b_stage_bytes, &b_full[s]);
                     }
         }
-    } else {
+      } else if (warp == CV_MMA_WARP) {
         // ================= MMA issuer: whole warp runs the (uniform) loops, one elected lane issues =================
         {
             // instruction descriptor: D=F32, A=B=TF32 (format 2) or F16 (format 0), K-major both, N = Npad, M = 128
@@ -691,51 +703,68 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             const unsigned long long a_desc0 = make_desc(0, a_lbo, a_sbo), b_desc0 = make_desc(0, b_lbo, b_sbo);
             const unsigned long long a_kstep = (2u * a_lbo) >> 4, b_kstep = (2u * b_lbo) >> 4;
             const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-            int it = 0, g = 0, j = 0;
-            for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, ++j) {
-                const int buf = j % nacc, use = j / nacc;
-                if (use > 0) mbar_wait(&acc_empty[buf], (use - 1) & 1);     // epilogue drained this accumulator
-                tc_fence_after();
-                const unsigned tacc = tmem_u + (unsigned)buf * acc_cols;
-                for (int c = 0; c < A.nchunks; ++c, ++g) {
-                    const int sa = g % A.astages;
-                    mbar_wait(&a_full[sa], (g / A.astages) & 1);
-                    const unsigned a_st = smem_u32(a_base + (size_t)sa * A.a_stage_bytes) >> 4;
-                    const unsigned long long a_hi0 = a_desc0 + a_st, a_lo0 = a_hi0 + (a_half >> 4);
-                    int dy = 0, dx = 0;
-                    const bool two = (c < A.nchunks - 1) || A.last_ksteps == 2;   // warp-uniform
-                    for (int tp = 0; tp < taps; ++tp, ++it) {
-                        const int sb = it % A.bstages;
-                        mbar_wait(&b_full[sb], (it / A.bstages) & 1);
-                        tc_fence_after();
-                        const unsigned b_st = smem_u32(b_base + (size_t)sb * A.b_stage_bytes) >> 4;
-                        const unsigned long long dbh0 = b_desc0 + b_st, dbl0 = dbh0 + (b_half >> 4);
-                        const unsigned long long dbh1 = dbh0 + b_kstep, dbl1 = dbl0 + b_kstep;
-                        const unsigned tap_off = (unsigned)(dy * A.RW + dx);             // in 16 B units (one pixel)
-                        const unsigned acc_first = (c == 0 && tp == 0) ? 0u : 1u;
-                        const unsigned long long dah = a_hi0 + tap_off, dal = a_lo0 + tap_off;
-                        const unsigned np = (unsigned)A.tcols;
-#define FVFI_ISSUE(MTV, W)                                                                                          \
-    tc_mma_kstep<MTV, PREC, W>(tacc, np, dal, dah, dbh0, dbl0, idesc, acc_first, idesc2);                              \
-    if (two) tc_mma_kstep<MTV, PREC, W>(tacc, np, dal + a_kstep, dah + a_kstep, dbh1, dbl1, idesc, 1u, idesc2);
-                        if (A.wide) {
-                            if (A.MT == 4) { FVFI_ISSUE(4, true) } else if (A.MT == 2) { FVFI_ISSUE(2, true) } else { FVFI_ISSUE(1, true) }
-                        } else {
-                            if (A.MT == 4) { FVFI_ISSUE(4, false) } else if (A.MT == 2) { FVFI_ISSUE(2, false) } else { FVFI_ISSUE(1, false) }
+            // The issue loop is specialised on (tiles per CTA, WIDE) and keeps every ring position / phase / descriptor as a
+            // running value: on the small-N full-resolution layers a filter tap is only 16 MMAs (~700 tensor-pipe cycles), and
+            // the generic loop (runtime MT / WIDE branches, two integer divisions per tap for the ring slots, descriptors
+            // rebuilt from the arguments) took ~1300 cycles per tap -- the issuing warp, not the tensor pipe, set the pace
+            // (ncu: this warp never waited on a barrier, hmma pipe 29 % active).
+            auto mma_loop = [&](auto mt_c, auto wide_c) {
+                constexpr int MTV = decltype(mt_c)::value;
+                constexpr bool WV = decltype(wide_c)::value;
+                const int nchunks = A.nchunks, astages = A.astages, bstages = A.bstages, KW = A.KW, ntiles = A.ntiles;
+                const bool last_two = A.last_ksteps == 2;
+                const unsigned np = (unsigned)A.tcols, row_skip = (unsigned)(A.RW - A.KW);
+                const unsigned a_stage16 = A.a_stage_bytes >> 4, b_stage16 = A.b_stage_bytes >> 4;
+                const unsigned a_base16 = smem_u32(a_base) >> 4, b_base16 = smem_u32(b_base) >> 4;
+                const unsigned long long a_lo16 = a_half >> 4, b_lo16 = b_half >> 4;
+                int sa = 0, sb = 0, j = 0;
+                unsigned pha = 0, phb = 0, a_cur16 = a_base16, b_cur16 = b_base16;
+                for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
+                    const int buf = (nacc == 2) ? (j & 1) : 0, use = (nacc == 2) ? (j >> 1) : j;
+                    if (use > 0) mbar_wait(&acc_empty[buf], (use - 1) & 1);     // epilogue drained this accumulator
+                    tc_fence_after();
+                    const unsigned tacc = tmem_u + (unsigned)buf * acc_cols;
+                    for (int c = 0; c < nchunks; ++c) {
+                        mbar_wait(&a_full[sa], pha);
+                        const unsigned long long a_hi0 = a_desc0 + a_cur16, a_lo0 = a_hi0 + a_lo16;
+                        const bool two = (c < nchunks - 1) || last_two;              // warp-uniform
+                        unsigned tap_off = 0;                                        // in 16 B units (one pixel)
+                        int dx = 0;
+                        for (int tp = 0; tp < taps; ++tp) {
+                            mbar_wait(&b_full[sb], phb);
+                            tc_fence_after();
+                            const unsigned long long dbh0 = b_desc0 + b_cur16, dbl0 = dbh0 + b_lo16;
+                            const unsigned acc_first = (c == 0 && tp == 0) ? 0u : 1u;
+                            const unsigned long long dah = a_hi0 + tap_off, dal = a_lo0 + tap_off;
+                            tc_mma_kstep<MTV, PREC, WV>(tacc, np, dal, dah, dbh0, dbl0, idesc, acc_first, idesc2);
+                            if (two)
+                                tc_mma_kstep<MTV, PREC, WV>(tacc, np, dal + a_kstep, dah + a_kstep, dbh0 + b_kstep, dbl0 + b_kstep,
+                                                            idesc, 1u, idesc2);
+                            tc_commit(&b_empty[sb]);           // weights of this (chunk, tap) consumed
+                            if (++sb == bstages) { sb = 0; phb ^= 1u; b_cur16 = b_base16; } else { b_cur16 += b_stage16; }
+                            ++tap_off;
+                            if (++dx == KW) { dx = 0; tap_off += row_skip; }
                         }
-#undef FVFI_ISSUE
-                        tc_commit(&b_empty[sb]);           // weights of this (chunk, tap) consumed
-                        if (++dx == A.KW) { dx = 0; ++dy; }
+                        tc_commit(&a_empty[sa]);               // region of this chunk consumed
+                        if (++sa == astages) { sa = 0; pha ^= 1u; a_cur16 = a_base16; } else { a_cur16 += a_stage16; }
                     }
-                    tc_commit(&a_empty[sa]);               // region of this chunk consumed
+                    tc_commit(&acc_full[buf]);
                 }
-                tc_commit(&acc_full[buf]);
+            };
+            using I1 = std::integral_constant<int, 1>;
+            using I2 = std::integral_constant<int, 2>;
+            using I4 = std::integral_constant<int, 4>;
+            if (A.wide) {
+                if (A.MT == 4) mma_loop(I4{}, std::true_type{}); else if (A.MT == 2) mma_loop(I2{}, std::true_type{}); else mma_loop(I1{}, std::true_type{});
+            } else {
+                if (A.MT == 4) mma_loop(I4{}, std::false_type{}); else if (A.MT == 2) mma_loop(I2{}, std::false_type{}); else mma_loop(I1{}, std::false_type{});
             }
         }
         __syncwarp();
+      }
     }
     __syncthreads();
-    if (warp == CV_LOADER_WARPS + 1) {
+    if (warp == CV_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(A.tmem_cols));
     }
