@@ -50,7 +50,8 @@ constexpr int CV_MMA_WARP = CV_PRODUCER_WARP + 1;                     // warp 13
 constexpr int CV_THREADS = CV_LOADERS + CV_EPI_THREADS + 128;
 // Register budget per role (setmaxnreg, per warpgroup): the launch gives every thread 65536 / 512 = 128; the epilogue and
 // producer/MMA warpgroups hand most of theirs to the loaders, which keep a whole K chunk of a tile in flight in registers.
-constexpr int CV_REGS_LOADER = 184, CV_REGS_EPI = 80, CV_REGS_MISC = 56;
+constexpr int CV_REGS_LOADER = 152, CV_REGS_EPI = 144, CV_REGS_MISC = 56;
+constexpr int CV_REGS_LAUNCH = 65536 / CV_THREADS;      // what __launch_bounds__(CV_THREADS, 1) gives every thread
 static_assert(CV_LOADERS * CV_REGS_LOADER + CV_EPI_THREADS * CV_REGS_EPI + 128 * CV_REGS_MISC <= 65536, "register pool");
 constexpr int CV_MAX_ASTAGES = 4;
 constexpr int CV_MAX_BSTAGES = 4;
@@ -378,7 +379,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
         // Dedicated warps (the loaders used to run the epilogue between their two load phases: on the small-N full-resolution
         // layers, where a tile's MMAs take ~6k cycles, the loader path -- epilogue included -- took ~14k and the tensor
         // pipe idled 54 % of the time, profiles/r01_conv_head_summary.txt).
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CV_REGS_EPI));
+        if (CV_REGS_EPI > CV_REGS_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CV_REGS_EPI));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CV_REGS_EPI));
         const float oscale = __ldg(A.hdr);                         // exact power of two (1 for PREC_TF32X3)
         const bool vec_out = (A.cout_store & 3) == 0 && (A.ldy & 3) == 0 && ((((size_t)A.y) & 15) == 0);
         const bool vec_out8 = (A.cout_store & 7) == 0 && (A.ldy & 7) == 0 && ((((size_t)A.y) & 31) == 0);
@@ -519,12 +521,37 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     }
                 }
             } else {
-                for (int t = 0; t < A.MT; ++t)
-                    for (int n0 = 0; n0 < A.Npad; n0 += 16) {
-                        float r[16];
-                        ld_acc16(tq + (unsigned)(t * A.tcols + n0), r);
-                        emit(t, n0, r, 0.f, 1.f);
+                // 16-column blocks (t, n0) of the CTA tile in order, software-pipelined: the TMEM loads of block k+1 are in
+                // flight while block k is activated and stored (two register sets; tcgen05.wait::ld covers every load issued
+                // so far, hence wait -> issue next -> emit)
+                const int nblk = A.MT * (A.Npad >> 4);
+                int t_i = 0, n_i = 0, t_e = 0, n_e = 0;                                     // issue / emit cursors
+                auto adv = [&](int& t, int& n0) { n0 += 16; if (n0 >= A.Npad) { n0 = 0; ++t; } };
+                auto issue_at = [&](unsigned* x, unsigned* y) {
+                    const unsigned ta = tq + (unsigned)(t_i * A.tcols + n_i);
+                    tc_ld16_issue(ta, x);
+                    if (A.wide) tc_ld16_issue(ta + (unsigned)A.Npad, y);
+                    adv(t_i, n_i);
+                };
+                auto emit_at = [&](const unsigned* x, const unsigned* y) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(x[i]) + (A.wide ? __uint_as_float(y[i]) : 0.f);
+                    emit(t_e, n_e, v, 0.f, 1.f);
+                    adv(t_e, n_e);
+                };
+                unsigned a0[16], a1[16], b0[16], b1[16];
+                issue_at(a0, a1);
+                for (int k = 0; k < nblk; k += 2) {
+                    tc_ld_wait();
+                    if (k + 1 < nblk) issue_at(b0, b1);
+                    emit_at(a0, a1);
+                    if (k + 1 < nblk) {
+                        tc_ld_wait();
+                        if (k + 2 < nblk) issue_at(a0, a1);
+                        emit_at(b0, b1);
                     }
+                }
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);          // this thread's TMEM reads of the buffer are done
