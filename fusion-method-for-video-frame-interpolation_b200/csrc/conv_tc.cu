@@ -798,10 +798,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-static bool softmax_wide() {      // experiment switch: WIDE pairing for the softmax heads too (FVFI_CONV_SOFTMAX_WIDE=1)
-    static const bool on = [] { const char* e = getenv("FVFI_CONV_SOFTMAX_WIDE"); return e && e[0] == '1'; }();
-    return on;
-}
 static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
     const int chunk = cv_chunk(prec);
     a.Npad = (a.Cout + 15) & ~15;
@@ -813,7 +809,10 @@ static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
     const int taps = a.KH * a.KW;
     const size_t budget = 222 * 1024;
     for (int mt = 4; mt >= 1; mt >>= 1) {
-        a.wide = (a.Npad <= 32 && (a.act != ACT_SOFTMAX || softmax_wide())) ? 1 : 0;     // measured: pays for N <= 32 (two A reads instead of three), not for N = 64 (smaller tiles)
+        // WIDE pays for N <= 32 (two A reads instead of three).  Measured again with the dedicated epilogue warps and the lean
+        // issue loop: at N = 64 the halved tile (MT = 2: 340 vs 377 TF/s) or a single-buffered accumulator (MT = 4: 308) cost
+        // more than the saved A read; the softmax heads are epilogue-bound and keep the one-load-per-block form.
+        a.wide = (a.Npad <= 32 && a.act != ACT_SOFTMAX) ? 1 : 0;
         a.tcols = a.wide ? 2 * a.Npad : a.Npad;
         if (mt * a.tcols > 512) continue;
         if (a.wide && mt > 1 && 2 * mt * a.tcols > 512) continue;      // small-N layers: keep the accumulator double-buffered
