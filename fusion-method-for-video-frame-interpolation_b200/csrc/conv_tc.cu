@@ -24,8 +24,8 @@
 //   filter tap is then just a different descriptor start address into that region (SBO = region row pitch), so
 //   the activation is read from L2 once per chunk instead of once per tap.  Weights are pre-packed on the device
 //   (hi|lo, canonical layout) and streamed per (chunk, tap) with cp.async.bulk + mbarrier.
-//   Warp roles: warps 0-3 activation loaders + epilogue (TMEM -> regs -> bias/activation -> NHWC), warp 4 weight
-//   producer, warp 5 TMEM allocator + single-thread MMA issuer.
+//   Warp roles (one per warpgroup, registers split with setmaxnreg): warps 0-7 activation loaders, warps 8-11 epilogue
+//   (TMEM -> regs -> bias/activation -> NHWC / planar), warp 12 weight producer, warp 13 TMEM allocator + MMA issuer.
 #include <cuda_fp16.h>
 
 #include <algorithm>
