@@ -423,7 +423,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                                         : A.y + (((size_t)T.img * A.H + orow) * A.W + ocol) * A.ldy;
                 if (A.out_nchw) {
                     // 8 consecutive px per row: full 32 B sectors.  Running pointer + one compare per plane (the indexed form
-                    // cost a 64-bit multiply-add per store: 12 instructions per STG, 15 % of the head layers' stall samples)
+                    // cost a 64-bit multiply-add per store: 12 instructions per STG, 15 % of the head layers' stall samples).
+                    // Measured alternative: staging the tile in shared memory and leaving through TMA tensor stores (single- and
+                    // double-buffered) was SLOWER (1.20-1.24 vs 1.10 ms per head layer): with the stores removed altogether the
+                    // layer still takes 0.96 ms -- the operand reads of its MMAs (0.72 ms), not these stores, bound it.
                     float* d = dst + (size_t)n0 * plane;
                     const int nv = A.Cout - n0;
 #pragma unroll

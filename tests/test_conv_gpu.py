@@ -197,3 +197,24 @@ def test_upsample2_conv_single_channel(B, C, H, W, prec):
     assert y.shape == ref.shape and y.is_contiguous()
     assert float((y.double() - ref).abs().max()) <= 3e-6
     conv.check_overflow()
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,act", [(3, 25, 25, 50, 100, None), (2, 32, 25, 37, 52, "softmax"), (1, 64, 25, 19, 44, "relu"),
+                                                 (2, 25, 25, 33, 51, None), (1, 16, 40, 70, 36, None), (5, 8, 3, 64, 260, "sigmoid")])
+def test_conv_planar_output_tiles(B, Cin, Cout, H, W, act, prec):
+    """Planar [B,Cout,H,W] outputs (the coefficient maps the AdaCoF warp streams) at ragged sizes: several tiles per persistent CTA,
+    image edges inside a tile, nothing written outside the planes."""
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn((B, Cin, H, W), device="cuda", generator=g)
+    w = torch.randn((Cout, Cin, 3, 3), device="cuda", generator=g) / (3 * Cin ** 0.5)
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    canary = torch.full((B * Cout * H * W + 64,), 7.5, device="cuda")
+    out = canary[:B * Cout * H * W].view(B, Cout, H, W)
+    y = conv.conv2d(x, w, b, "zeros", act, out=out, nchw_out=True)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    ref = {None: lambda t: t, "relu": F.relu, "sigmoid": torch.sigmoid, "softmax": lambda t: torch.softmax(t, 1)}[act](ref)
+    assert float((y.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    assert float((canary[B * Cout * H * W:] - 7.5).abs().max()) == 0.0           # nothing written past the last plane
+    conv.check_overflow()
