@@ -423,7 +423,97 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_slice_kernel(const float* __
         for (int c = 0; c < C; ++c) dst[c] = __ldg(src + (size_t)c * plane);
     }
 }
+
+// ---- PhaseNet glue (src/train/utils.py:47-127, src/phase_net/phase_net.py:42-105,141,155-156) --------------------------------
+// Input side: the decomposition of [frame-1 planes | frame-2 planes] (N = 2*P planes, channel = plane*nb + band) goes straight
+// into the 4*nb value channels of the NHWC concat of planes [p0, p0+pc):  [phase_1 | phase_2] / pi,  [amp_1 | amp_2] / den[p]
+// (den = per-plane max over both frames + eps, from the decomposition's own epilogue) -- separate_vals, get_concat_layers_inf,
+// normalize_vals and the concat in ONE pass over the planes (the reference materialises each of them).
+template <int NB>
+__global__ void __launch_bounds__(256) phasenet_assemble_kernel(const float* __restrict__ phase, const float* __restrict__ amp,
+                                                                const float* __restrict__ den, float* __restrict__ y, size_t plane,
+                                                                int ldy, int P, int p0) {
+    const size_t px = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= plane) return;
+    const int p = p0 + blockIdx.y;
+    const float* ph1 = phase + (size_t)p * NB * plane + px;
+    const float* ph2 = phase + (size_t)(P + p) * NB * plane + px;
+    const float* am1 = amp + (size_t)p * NB * plane + px;
+    const float* am2 = amp + (size_t)(P + p) * NB * plane + px;
+    const float d = __ldg(den + p);
+    float v[4 * NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        v[c] = __ldcs(ph1 + (size_t)c * plane) / 3.14159265358979323846f;             // x / math.pi        (phase_net.py:64)
+        v[NB + c] = __ldcs(ph2 + (size_t)c * plane) / 3.14159265358979323846f;
+        v[2 * NB + c] = __ldg(am1 + (size_t)c * plane) / d;                           // amplitude / max    (phase_net.py:54-57)
+        v[3 * NB + c] = __ldg(am2 + (size_t)c * plane) / d;
+    }
+    float* dst = y + ((size_t)blockIdx.y * plane + px) * ldy;
+    if (NB == 4 && (ldy & 7) == 0 && ((((size_t)y) & 31) == 0)) {
+        stg256f(dst, v);
+        stg256f(dst + 8, v + 8);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4 * NB; ++c) dst[c] = v[c];
+    }
+}
+
+// Output side: prediction [pc, 2*nb, h, w] NHWC (tanh outputs) + the RAW amplitudes -> phase_out = pred[:nb] * pi,
+// amp_out = beta * amp_2 + (1 - beta) * amp_1 with beta = (pred[nb:] + 1) / 2, at channel (p0+p)*nb + b of the [P*nb,1,h,w]
+// outputs: the amplitude blend (phase_net.py:155-156) and reverse_normalize (:80-105) in one pass; normalising by the common
+// per-plane maximum and multiplying it back afterwards is the identity up to rounding, so the raw amplitudes are blended.
+template <int NB>
+__global__ void __launch_bounds__(256) phasenet_outputs_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ amp,
+                                                               float* __restrict__ phase_out, float* __restrict__ amp_out,
+                                                               size_t plane, int P, int p0) {
+    const size_t px = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= plane) return;
+    const int p = p0 + blockIdx.y;
+    const float* pr = pred + ((size_t)blockIdx.y * plane + px) * ldp;
+    float v[2 * NB];
+    if (NB == 4 && (ldp & 7) == 0 && ((((size_t)pred) & 31) == 0)) ldg256f(pr, v);
+    else {
+#pragma unroll
+        for (int c = 0; c < 2 * NB; ++c) v[c] = __ldg(pr + c);
+    }
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        const size_t o = ((size_t)p * NB + c) * plane + px;
+        const float a1 = __ldg(amp + o), a2 = __ldg(amp + ((size_t)(P + p) * NB + c) * plane + px);
+        const float beta = (v[NB + c] + 1.f) / 2.f;
+        __stcs(phase_out + o, v[c] * 3.14159265358979323846f);
+        __stcs(amp_out + o, beta * a2 + (1.f - beta) * a1);
+    }
+}
 }  // namespace fvfi
+
+extern "C" int fvfi_phasenet_assemble(const float* phase, const float* amp, const float* den, float* y, int y_pixel_stride, int P,
+                                      int p0, int pc, int nb, int H, int W, void* stream) {
+    FVFI_CHECK_ARG(phase && amp && den && y && P > 0 && p0 >= 0 && pc > 0 && p0 + pc <= P && pc <= 65535 && H > 0 && W > 0,
+                   "phasenet_assemble: bad argument");
+    FVFI_CHECK_ARG(nb == 4, "phasenet_assemble: nbands must be 4 (got %d)", nb);
+    FVFI_CHECK_ARG(y_pixel_stride >= 4 * nb, "phasenet_assemble: pixel stride smaller than 4*nbands");
+    const size_t plane = (size_t)H * W;
+    dim3 grid((unsigned)((plane + 255) / 256), pc);
+    fvfi::phasenet_assemble_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(phase, amp, den, y, plane, y_pixel_stride, P, p0);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
+
+extern "C" int fvfi_phasenet_outputs(const float* pred, int pred_pixel_stride, const float* amp, float* phase_out, float* amp_out,
+                                     int P, int p0, int pc, int nb, int H, int W, void* stream) {
+    FVFI_CHECK_ARG(pred && amp && phase_out && amp_out && P > 0 && p0 >= 0 && pc > 0 && p0 + pc <= P && pc <= 65535 && H > 0 && W > 0,
+                   "phasenet_outputs: bad argument");
+    FVFI_CHECK_ARG(nb == 4, "phasenet_outputs: nbands must be 4 (got %d)", nb);
+    FVFI_CHECK_ARG(pred_pixel_stride >= 2 * nb, "phasenet_outputs: pixel stride smaller than 2*nbands");
+    const size_t plane = (size_t)H * W;
+    dim3 grid((unsigned)((plane + 255) / 256), pc);
+    fvfi::phasenet_outputs_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(pred, pred_pixel_stride, amp, phase_out, amp_out, plane, P,
+                                                                             p0);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
 
 extern "C" int fvfi_nchw_to_nhwc_slice(const float* x, float* y, int y_pixel_stride, int B, int C, int H, int W, void* stream) {
     FVFI_CHECK_ARG(x && y && B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535 && y_pixel_stride >= C, "nchw_to_nhwc_slice: bad argument");

@@ -45,6 +45,8 @@ _PROTOS = {
     "fvfi_nchw_to_nhwc_slice": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "fvfi_conv1x1_nhwc": (c_int, [c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_size, c_int, c_int, c_int, c_fp]),
     "fvfi_upsample2_tapsum": (c_int, [c_fp, c_int, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
+    "fvfi_phasenet_assemble": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_fp]),
+    "fvfi_phasenet_outputs": (c_int, [c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "fvfi_avg_pool2_nhwc": (c_int, [c_fp, c_int, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "fvfi_resize_bilinear_nhwc": (c_int, [c_fp, c_int, c_fp, c_int] + [c_int] * 7 + [c_fp]),
     "fvfi_adacof_forward_host": (c_int, [c_fp] * 5 + [c_int] * 8),

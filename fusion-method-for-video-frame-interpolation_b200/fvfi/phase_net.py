@@ -148,6 +148,66 @@ class PhaseNet(nn.Module):
             amplitudes.append(amp.reshape(-1, 1, r1, r2))
         return low_level, phases, amplitudes
 
+    def forward_fused(self, vals, amp_max, m=None):
+        """Fused inference form of  separate_vals -> get_concat_layers_inf -> normalize_vals -> forward -> reverse_normalize
+        (src/train/utils.py:47-127, phase_net.py:42-177) for two input frames.
+
+        ``vals``: the RAW decomposition (``Pyramid.filter``) of ``cat(frame-1 planes, frame-2 planes)`` (N = 2*P planes, lists finest
+        first); ``amp_max`` [L, N]: the per-level per-plane amplitude maxima from the decomposition's epilogue
+        (``Pyramid.last_amp_max``).  Returns the DecompValues ``Pyramid.inv_filter`` consumes (P planes).  The value channels of
+        every level's concat are written by ONE kernel straight from the decomposition (fvfi_phasenet_assemble) and the amplitude
+        blend + de-normalisation by another (fvfi_phasenet_outputs): the regrouped / normalised / re-scaled copies of the whole
+        pyramid that the step-by-step form materialises (~80 GB per 8 frame pairs at 1080p) never exist."""
+        from . import _lib
+        assert self.num_img == 2 and vals.low_level.is_cuda and not self.training and not torch.is_grad_enabled()
+        L, nb = len(vals.phase), self.pyr.nbands
+        if m is None:
+            m = self.pyr.height - 2
+        N = vals.low_level.shape[0]
+        P = N // 2
+        dev = vals.low_level.device
+        low = torch.cat((vals.low_level[:P], vals.low_level[P:]), 1)                       # [P,2,hL,wL] (a few hundred values)
+        self.max_low_level = low.reshape(P, -1).max(1)[0] + self.eps                       # max, not max|.| (phase_net.py:70)
+        low = low / self.max_low_level.view(-1, 1, 1, 1)
+        den = (torch.maximum(amp_max[:, :P], amp_max[:, P:]) + self.eps).contiguous()      # [L,P]: max over both frames' bands + eps
+        self.max_amplitudes = [den[L - 1 - i] for i in range(m)]                           # coarsest first, as normalize_vals keeps them
+        new = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+        phase_out = [new(P * nb, 1, *vals.phase[l].shape[2:]) if l >= L - m else 0 for l in range(L)]
+        amp_out = [new(P * nb, 1, *vals.phase[l].shape[2:]) if l >= L - m else 0 for l in range(L)]
+        lows = []
+        lib = _lib.lib()
+        chunk = self.plane_chunk or P
+        for p0 in range(0, P, chunk):
+            pc = min(chunk, P - p0)
+            lo = low[p0:p0 + pc]
+            feature, prediction = self.layers[0](lo)
+            alpha = (prediction[:, 0] + 1) / 2
+            lows.append((alpha * lo[:, 0] + (1 - alpha) * lo[:, 1]).unsqueeze(1))          # phase_net.py:114-116
+            for idx in range(m):
+                l = L - 1 - idx                                                            # coarsest level first
+                ph, am = vals.phase[l], vals.amplitude[l]
+                h, w = int(ph.shape[2]), int(ph.shape[3])
+                cf, cp, cv = feature.shape[1], prediction.shape[1], 2 * nb
+                concat = torch.empty((pc, cf + 2 * cv + cp, h, w), dtype=torch.float32, device=dev,
+                                     memory_format=torch.channels_last)
+                tc.resize_bilinear(feature, (h, w), False, out=concat, out_channel_offset=0)
+                with torch.cuda.device(dev):
+                    _lib.check(lib.fvfi_phasenet_assemble(ph.data_ptr(), am.data_ptr(), den[l].data_ptr(),
+                                                          concat.data_ptr() + 4 * cf, concat.stride(3), P, p0, pc, nb, h, w,
+                                                          _lib.stream_ptr()))
+                tc.resize_bilinear(prediction, (h, w), False, out=concat, out_channel_offset=cf + 2 * cv)
+                i = idx + 1 if idx + 1 < len(self.layers) - 1 else len(self.layers) - 1
+                feature, prediction = self.layers[i](concat)
+                del concat
+                pr = tc.to_nhwc(prediction)
+                with torch.cuda.device(dev):
+                    _lib.check(lib.fvfi_phasenet_outputs(pr.data_ptr(), pr.stride(3), am.data_ptr(), phase_out[l].data_ptr(),
+                                                         amp_out[l].data_ptr(), P, p0, pc, nb, h, w, _lib.stream_ptr()))
+        low_level = (lows[0] if len(lows) == 1 else torch.cat(lows, 0)) * self.max_low_level.view(-1, 1, 1, 1)
+        H, W = int(vals.phase[0].shape[2]), int(vals.phase[0].shape[3])
+        high_level = torch.zeros((1,), dtype=torch.float32, device=dev).expand(P, 1, H, W)  # zeros (phase_net.py:127-128), no storage
+        return DecompValues(high_level=high_level, low_level=low_level, amplitude=amp_out, phase=phase_out)
+
     def forward(self, vals, m=None):
         """phase_net.py:107-177."""
         if m is None:

@@ -37,6 +37,7 @@ class FusionPipeline(torch.nn.Module):
         self.stages = None  # set to a dict to capture intermediates (tests)
         self.max_batch = 8  # frame pairs per sub-batch at full HD (see forward)
         self.timing = None  # set to a list to collect (stage, start_event, end_event) (bench)
+        self.fused_phase_glue = True   # PhaseNet.forward_fused (False: the reference's step-by-step value plumbing)
 
     def _tick(self, name):
         """Stage timer: CUDA events on the current stream, only when ``self.timing`` is a list."""
@@ -81,12 +82,17 @@ class FusionPipeline(torch.nn.Module):
         self._tick('lab+adacofnet#1')
         # PhaseNet branch (:168-192)
         vals = pyr.filter(torch.cat((lab1.reshape(-1, H, W), lab2.reshape(-1, H, W)), 0), want_high=False)
-        vals_in = self.phase_net.normalize_vals(utils.get_concat_layers_inf(pyr, utils.separate_vals(vals, 2)))
+        self._tick('pyr.filter(12 planes/frame)')
+        if self.fused_phase_glue:
+            # separate_vals / get_concat_layers_inf / normalize_vals / forward / reverse_normalize with the regrouping and the
+            # (de)normalisation fused into the concat assembly and the output kernel (PhaseNet.forward_fused)
+            vals_pred = self.phase_net.forward_fused(vals, pyr.last_amp_max)
+        else:
+            vals_in = self.phase_net.normalize_vals(utils.get_concat_layers_inf(pyr, utils.separate_vals(vals, 2)))
+            vals_pred = self.phase_net(vals_in)
+            del vals_in
         del vals
-        self._tick('pyr.filter(12 planes/frame)+normalize')
-        vals_pred = self.phase_net(vals_in)
         self._tick('phase_net')
-        del vals_in
         lab_pred = pyr.inv_filter_sparse(vals_pred, use_high=False).reshape(r_shape)            # high_level is zeros (:127-128)
         del vals_pred
         self._tick('pyr.inv_filter(3 planes/frame)')

@@ -146,6 +146,19 @@ int fvfi_conv1x1_nhwc(const float* x, int x_pixel_stride, const float* weight, c
 int fvfi_upsample2_tapsum(const float* z, int z_pixel_stride, const float* bias, float* y, int B, int Hi, int Wi,
                           int activation, void* stream);
 
+/* PhaseNet glue, fused (src/train/utils.py:47-127 separate_vals / get_concat_layers_inf, src/phase_net/phase_net.py:42-78
+ * normalize_vals, :141 concat, :155-156 amplitude blend, :80-105 reverse_normalize).
+ * phase / amp: one level of fvfi_pyr_decompose of [frame-1 planes | frame-2 planes]: [2*P*nb, H, W], channel = plane*nb + band.
+ * fvfi_phasenet_assemble writes, for planes [p0, p0+pc), the 4*nb value channels of the NHWC concat
+ *   y[p - p0][h][w][0 .. 4nb) = [phase_1 / pi | phase_2 / pi | amp_1 / den[p] | amp_2 / den[p]]   (den [P]: per-plane max + eps).
+ * fvfi_phasenet_outputs takes the block's prediction pred [pc,H,W,>=2nb] (NHWC, tanh outputs) and writes
+ *   phase_out[(p*nb + b)] = pred[b] * pi,  amp_out[(p*nb + b)] = beta * amp_2 + (1 - beta) * amp_1,  beta = (pred[nb + b] + 1) / 2
+ * into [P*nb, H, W] tensors (the un-normalised values Pyramid.inv_filter consumes).  nb must be 4. */
+int fvfi_phasenet_assemble(const float* phase, const float* amp, const float* den, float* y, int y_pixel_stride, int P,
+                           int p0, int pc, int nb, int H, int W, void* stream);
+int fvfi_phasenet_outputs(const float* pred, int pred_pixel_stride, const float* amp, float* phase_out, float* amp_out,
+                          int P, int p0, int pc, int nb, int H, int W, void* stream);
+
 /* Bilinear resize of NHWC tensors (torch.nn.Upsample / F.interpolate 'bilinear' semantics, both align_corners
  * modes; src/fusion_net/fusion_adacofnet.py:31, src/fusion_net/fusion_net.py:41, src/phase_net/phase_net.py:138-139).
  * x [B,Hi,Wi,C] with x_pixel_stride floats per pixel -> y [B,Ho,Wo,C] (may be a channel slice: y_pixel_stride). */

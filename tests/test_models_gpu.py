@@ -233,3 +233,32 @@ def test_phasenet_training_step():
     # 64x64 -> 6 pyramid levels -> layers[0..6] are exercised; layers[7] (8 tensors) only exists for deeper pyramids
     assert sum(float(g.abs().sum()) > 0 for g in grads) >= len(grads) - 8
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("H,W,chunk", [(64, 96, None), (120, 70, 2)])
+def test_phasenet_forward_fused_matches_stepwise(H, W, chunk):
+    """PhaseNet.forward_fused (regrouping, normalisation, concat, amplitude blend and de-normalisation fused into two kernels,
+    fvfi_phasenet_assemble / fvfi_phasenet_outputs) == separate_vals -> get_concat_layers_inf -> normalize_vals -> forward
+    (-> reverse_normalize), the reference's step-by-step plumbing (src/train/utils.py:47-127, phase_net.py:42-177)."""
+    import math
+    from fvfi import utils
+    from fvfi.phase_net import PhaseNet
+    from fvfi.pyramid import Pyramid
+    torch.manual_seed(3)
+    P = 3
+    planes = torch.rand((2 * P, H, W), device="cuda")
+    height = utils.calc_pyr_height(planes)
+    pyr = Pyramid(height=height, nbands=4, scale_factor=math.sqrt(2), device=torch.device("cuda"))
+    net = PhaseNet(pyr, torch.device("cuda"), num_img=2).eval()
+    net.plane_chunk = chunk
+    with torch.no_grad():
+        vals = pyr.filter(planes, want_high=False)
+        ref = net(net.normalize_vals(utils.get_concat_layers_inf(pyr, utils.separate_vals(vals, 2))))
+        out = net.forward_fused(vals, pyr.last_amp_max)
+        assert len(out.phase) == len(ref.phase) == height - 2
+        for a, b in zip(out.phase + out.amplitude + [out.low_level], ref.phase + ref.amplitude + [ref.low_level]):
+            assert a.shape == b.shape
+            assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(b.abs().max()))
+        img_a = pyr.inv_filter_sparse(out, use_high=False)
+        img_b = pyr.inv_filter_sparse(ref, use_high=False)
+        assert float((img_a - img_b).abs().max()) <= 2e-6
