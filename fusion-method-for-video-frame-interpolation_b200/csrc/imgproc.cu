@@ -379,7 +379,8 @@ __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* 
 }
 
 // nn.AvgPool2d(2, 2) on NHWC storage (src/fusion_net/fusion_adacofnet.py:62-70): one thread = one output pixel x VEC channels
-template <int VEC>
+// MAX: nn.MaxPool2d(2, stride=2) (FusionNet's encoder, src/fusion_net/fusion_net.py:39,56)
+template <int VEC, bool MAX = false>
 __global__ void __launch_bounds__(256) avg_pool2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi, int Wi,
                                                              int C, int ldx, int ldy) {
     const int Ho = Hi >> 1, Wo = Wi >> 1;
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(256) avg_pool2_nhwc_kernel(const float* __rest
         a[0] = __ldg(p00); b[0] = __ldg(p00 + ldx); c[0] = __ldg(p10); d[0] = __ldg(p10 + ldx);
     }
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) o[i] = ((a[i] + b[i]) + (c[i] + d[i])) * 0.25f;
+    for (int i = 0; i < VEC; ++i) o[i] = MAX ? fmaxf(fmaxf(a[i], b[i]), fmaxf(c[i], d[i])) : ((a[i] + b[i]) + (c[i] + d[i])) * 0.25f;
     if (VEC == 8) stg256f(dst, o);
     else dst[0] = o[0];
 }
@@ -486,7 +487,53 @@ __global__ void __launch_bounds__(256) phasenet_outputs_kernel(const float* __re
         __stcs(amp_out + o, beta * a2 + (1.f - beta) * a1);
     }
 }
+
+// ---- AdaCoFNet.forward input preparation (src/fusion_net/fusion_adacofnet.py:176-196, src/adacof/utility.py:86-87) ------------
+// One pass over the two frames replaces  F.pad(reflect, bottom/right to multiples of 32) x2 -> moduleNormalize x2 -> cat -> NHWC
+// (KernelEstimation's input, 6 channels + 2 zero channels)  and  ReplicationPad2d(kpad) x2  (the frames the warp samples):
+//   x[b][y][x][0..2] = f0 - mean, [3..5] = f2 - mean, [6..7] = 0          for (y, x) in the reflect-padded Hp x Wp frame
+//   p0 / p2[b][c][y'][x'] = reflect-padded frame at clamp(y' - kpad), clamp(x' - kpad)      (un-normalised, :195)
+__global__ void __launch_bounds__(256) adacofnet_prep_kernel(const float* __restrict__ f0, const float* __restrict__ f2,
+                                                             float* __restrict__ x, float* __restrict__ p0, float* __restrict__ p2,
+                                                             int H, int W, int Hp, int Wp, int kpad, float m0, float m1, float m2) {
+    const int Hq = Hp + 2 * kpad, Wq = Wp + 2 * kpad;
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (unsigned)Hq * (unsigned)Wq) return;
+    const int yq = (int)(q / (unsigned)Wq), xq = (int)(q - (unsigned)yq * (unsigned)Wq);
+    const int b = blockIdx.y;
+    const int yp = min(max(yq - kpad, 0), Hp - 1), xp = min(max(xq - kpad, 0), Wp - 1);      // replicate (clamp)
+    const int ys = yp < H ? yp : 2 * (H - 1) - yp, xs = xp < W ? xp : 2 * (W - 1) - xp;      // torch 'reflect' at the far edges
+    const size_t plane = (size_t)H * W, planeq = (size_t)Hq * Wq;
+    const size_t src = (size_t)b * 3 * plane + (size_t)ys * W + xs, dst = (size_t)b * 3 * planeq + q;
+    float a[3], c[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        a[ch] = __ldg(f0 + src + ch * plane);
+        c[ch] = __ldg(f2 + src + ch * plane);
+        p0[dst + ch * planeq] = a[ch];
+        p2[dst + ch * planeq] = c[ch];
+    }
+    if (yq - kpad == yp && xq - kpad == xp) {                       // interior of the padded frame: KernelEstimation's input pixel
+        float v[8] = {a[0] - m0, a[1] - m1, a[2] - m2, c[0] - m0, c[1] - m1, c[2] - m2, 0.f, 0.f};
+        stg256f(x + (((size_t)b * Hp + yp) * Wp + xp) * 8, v);
+    }
+}
 }  // namespace fvfi
+
+extern "C" int fvfi_adacofnet_prep(const float* frame0, const float* frame2, float* x_nhwc8, float* padded0, float* padded2, int B,
+                                   int H, int W, int Hp, int Wp, int kpad, const float* mean3_host, void* stream) {
+    FVFI_CHECK_ARG(frame0 && frame2 && x_nhwc8 && padded0 && padded2 && mean3_host && B > 0 && B <= 65535 && H > 1 && W > 1,
+                   "adacofnet_prep: bad argument");
+    FVFI_CHECK_ARG(Hp >= H && Wp >= W && Hp - H < H && Wp - W < W && kpad >= 0, "adacofnet_prep: reflect padding must be smaller than the frame");
+    FVFI_CHECK_ARG((((size_t)x_nhwc8) & 31) == 0, "adacofnet_prep: the NHWC output must be 32-byte aligned");
+    const size_t total = (size_t)(Hp + 2 * kpad) * (Wp + 2 * kpad);
+    FVFI_CHECK_ARG(total < (1ull << 32) - 256, "adacofnet_prep: frame too large");
+    dim3 grid((unsigned)((total + 255) / 256), B);
+    fvfi::adacofnet_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frame0, frame2, x_nhwc8, padded0, padded2, H, W, Hp, Wp, kpad,
+                                                                        mean3_host[0], mean3_host[1], mean3_host[2]);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
 
 extern "C" int fvfi_phasenet_assemble(const float* phase, const float* amp, const float* den, float* y, int y_pixel_stride, int P,
                                       int p0, int pc, int nb, int H, int W, void* stream) {
@@ -553,8 +600,18 @@ extern "C" int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, flo
     return FVFI_OK;
 }
 
+static int pool2_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi, int C, bool is_max,
+                      void* stream);
+extern "C" int fvfi_max_pool2_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi, int C,
+                                   void* stream) {
+    return pool2_nhwc(x, x_pixel_stride, y, y_pixel_stride, B, Hi, Wi, C, true, stream);
+}
 extern "C" int fvfi_avg_pool2_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi, int C,
                                    void* stream) {
+    return pool2_nhwc(x, x_pixel_stride, y, y_pixel_stride, B, Hi, Wi, C, false, stream);
+}
+static int pool2_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi, int C, bool is_max,
+                      void* stream) {
     FVFI_CHECK_ARG(x && y && B > 0 && Hi > 1 && Wi > 1 && C > 0 && B <= 65535, "avg_pool2: bad argument");
     FVFI_CHECK_ARG(x_pixel_stride >= C && y_pixel_stride >= C, "avg_pool2: pixel stride smaller than channel count");
     const bool a32 = ((((size_t)x) | ((size_t)y)) & 31) == 0;
@@ -562,8 +619,11 @@ extern "C" int fvfi_avg_pool2_nhwc(const float* x, int x_pixel_stride, float* y,
     const size_t total = (size_t)(Hi / 2) * (Wi / 2) * ((C + vec - 1) / vec);
     FVFI_CHECK_ARG(total < (1ull << 32) - 256, "avg_pool2: image too large");
     dim3 grid((unsigned)((total + 255) / 256), B);
-    if (vec == 8) fvfi::avg_pool2_nhwc_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, Hi, Wi, C, x_pixel_stride, y_pixel_stride);
-    else fvfi::avg_pool2_nhwc_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, Hi, Wi, C, x_pixel_stride, y_pixel_stride);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (vec == 8 && is_max) fvfi::avg_pool2_nhwc_kernel<8, true><<<grid, 256, 0, s>>>(x, y, Hi, Wi, C, x_pixel_stride, y_pixel_stride);
+    else if (vec == 8) fvfi::avg_pool2_nhwc_kernel<8, false><<<grid, 256, 0, s>>>(x, y, Hi, Wi, C, x_pixel_stride, y_pixel_stride);
+    else if (is_max) fvfi::avg_pool2_nhwc_kernel<1, true><<<grid, 256, 0, s>>>(x, y, Hi, Wi, C, x_pixel_stride, y_pixel_stride);
+    else fvfi::avg_pool2_nhwc_kernel<1, false><<<grid, 256, 0, s>>>(x, y, Hi, Wi, C, x_pixel_stride, y_pixel_stride);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }

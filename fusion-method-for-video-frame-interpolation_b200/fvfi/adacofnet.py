@@ -120,9 +120,13 @@ class KernelEstimation(torch.nn.Module):
         """tcgen05 path of fusion_adacofnet.py:109-155: every conv(+ReLU/sigmoid) is one fused kernel, the
         pooling / bilinear upsampling / softmax run on NHWC tensors, the seven heads are returned NCHW-contiguous
         (the warp kernel streams each coefficient plane)."""
-        run = self._seq_tc
         # 6 input channels padded to 8 (zeros): 16-byte loads in the first convolution
         x = tc.to_nhwc(torch.cat([rfield0, rfield2, rfield0.new_zeros((rfield0.shape[0], 2) + tuple(rfield0.shape[2:]))], 1))
+        return self._forward_tc_x(x)
+
+    def _forward_tc_x(self, x):
+        """``x``: [B,8,H,W] channels_last = (frame0 - mean | frame2 - mean | two zero channels)."""
+        run = self._seq_tc
         pool = tc.avg_pool2                    # modulePool1..5 = AvgPool2d(2, 2), on NHWC with 256-bit accesses
         c1 = run(self.moduleConv1, x)
         c2 = run(self.moduleConv2, pool(c1))
@@ -188,6 +192,33 @@ class AdaCoFNet(torch.nn.Module):
         self.modulePad = torch.nn.ReplicationPad2d([self.kernel_pad] * 4)
         self.moduleAdaCoF = adacof.FunctionAdaCoF.apply
 
+    def _forward_fused_prep(self, frame0, frame2, return_warped):
+        """Inference form of lines 176-213: reflect pad / normalise / concat / NHWC and the replicate pad in ONE kernel
+        (fvfi_adacofnet_prep), kernel estimation, fused two-warp synthesis."""
+        import ctypes
+        from . import _lib
+        B, _, h0, w0 = frame0.shape
+        hp, wp = (h0 + 31) // 32 * 32, (w0 + 31) // 32 * 32
+        k = self.kernel_pad
+        f0, f2 = frame0.contiguous(), frame2.contiguous()
+        x = torch.empty((B, 8, hp, wp), dtype=torch.float32, device=f0.device, memory_format=torch.channels_last)
+        p0 = torch.empty((B, 3, hp + 2 * k, wp + 2 * k), dtype=torch.float32, device=f0.device)
+        p2 = torch.empty_like(p0)
+        mean = (ctypes.c_float * 3)(0.4631, 0.4352, 0.3990)                           # src/adacof/utility.py:86-87
+        with torch.cuda.device(f0.device):
+            _lib.check(_lib.lib().fvfi_adacofnet_prep(f0.data_ptr(), f2.data_ptr(), x.data_ptr(), p0.data_ptr(), p2.data_ptr(),
+                                                      B, h0, w0, hp, wp, k, ctypes.cast(mean, ctypes.c_void_p),
+                                                      _lib.stream_ptr()))
+        W1, A1, B1, W2, A2, B2, Occ = self.get_kernel._forward_tc_x(x)
+        t1, t2, frame1, mask = adacof.adacofnet_warp_blend(p0, p2, W1.contiguous(), A1.contiguous(), B1.contiguous(),
+                                                           W2.contiguous(), A2.contiguous(), B2.contiguous(),
+                                                           Occ.contiguous(), self.dilation, want_t=return_warped)
+        if hp != h0 or wp != w0:
+            if t1 is not None:
+                t1, t2 = t1[:, :, :h0, :w0], t2[:, :, :h0, :w0]
+            frame1, mask = frame1[:, :, :h0, :w0].contiguous(), mask[:, :, :h0, :w0].contiguous()
+        return t1, t2, frame1, mask
+
     def load(self, state_dict):
         """The reference wraps models in src/adacof/models/__init__.py:Model whose ``load`` forwards here."""
         self.load_state_dict(state_dict)
@@ -196,6 +227,9 @@ class AdaCoFNet(torch.nn.Module):
         h0, w0 = int(frame0.shape[2]), int(frame0.shape[3])
         if h0 != int(frame2.shape[2]) or w0 != int(frame2.shape[3]):
             sys.exit('Frame sizes do not match')                                   # fusion_adacofnet.py:177-178
+        if (tc.use_tc(frame0) and not self.training and frame0.shape[1] == 3 and frame0.dtype == torch.float32
+                and not (frame0.requires_grad or frame2.requires_grad)):
+            return self._forward_fused_prep(frame0, frame2, return_warped)
         if h0 % 32 != 0:
             pad_h = 32 - (h0 % 32)
             frame0 = F.pad(frame0, (0, 0, 0, pad_h), mode='reflect')

@@ -180,13 +180,18 @@ def put_planar(x, out, out_channel_offset):
     return out
 
 
-def avg_pool2(x):
+def max_pool2(x):
+    """nn.MaxPool2d(2, stride=2) on NHWC storage."""
+    return avg_pool2(x, _fn="fvfi_max_pool2_nhwc")
+
+
+def avg_pool2(x, _fn="fvfi_avg_pool2_nhwc"):
     """nn.AvgPool2d(kernel_size=2, stride=2) on NHWC storage."""
     B, C, H, W = x.shape
     xc = to_nhwc(x.float())
     out = torch.empty((B, C, H // 2, W // 2), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().fvfi_avg_pool2_nhwc(xc.data_ptr(), xc.stride(3), out.data_ptr(), out.stride(3), B, H, W, C,
+        _lib.check(getattr(_lib.lib(), _fn)(xc.data_ptr(), xc.stride(3), out.data_ptr(), out.stride(3), B, H, W, C,
                                                   _lib.stream_ptr()))
     return out
 

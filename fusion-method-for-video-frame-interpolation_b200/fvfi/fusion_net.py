@@ -71,7 +71,7 @@ class FusionNet(torch.nn.Module):
             for layer in self.encoder_layers:
                 x = tc.conv_module(layer, x, "relu")
                 skip.append(x)
-                x = self.max_pool(x)
+                x = tc.max_pool2(x)                                   # nn.MaxPool2d(2, stride=2) on NHWC, 256-bit accesses
             x = tc.conv_module(self.bottleneck_layer, x, "relu")    # ReLU of the first decoder step folded in
             for i, (layer, s) in enumerate(zip(self.decoder_layers, skip[::-1])):
                 x = x if i == 0 else self.relu(x)

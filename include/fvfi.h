@@ -146,6 +146,13 @@ int fvfi_conv1x1_nhwc(const float* x, int x_pixel_stride, const float* weight, c
 int fvfi_upsample2_tapsum(const float* z, int z_pixel_stride, const float* bias, float* y, int B, int Hi, int Wi,
                           int activation, void* stream);
 
+/* Input preparation of AdaCoFNet.forward in one pass (src/fusion_net/fusion_adacofnet.py:176-196, src/adacof/utility.py:86-87):
+ * frames [B,3,H,W] -> x_nhwc8 [B,Hp,Wp,8] = (frame0 - mean | frame2 - mean | 0 0) of the frames reflect-padded at the bottom /
+ * right to Hp x Wp (multiples of 32), KernelEstimation's NHWC input; padded0 / padded2 [B,3,Hp+2k,Wp+2k] = ReplicationPad2d(k)
+ * of the reflect-padded frames, what the warp samples.  mean3_host: three floats on the HOST (the channel means). */
+int fvfi_adacofnet_prep(const float* frame0, const float* frame2, float* x_nhwc8, float* padded0, float* padded2, int B,
+                        int H, int W, int Hp, int Wp, int kpad, const float* mean3_host, void* stream);
+
 /* PhaseNet glue, fused (src/train/utils.py:47-127 separate_vals / get_concat_layers_inf, src/phase_net/phase_net.py:42-78
  * normalize_vals, :141 concat, :155-156 amplitude blend, :80-105 reverse_normalize).
  * phase / amp: one level of fvfi_pyr_decompose of [frame-1 planes | frame-2 planes]: [2*P*nb, H, W], channel = plane*nb + band.
@@ -168,6 +175,9 @@ int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, float* y, int 
 /* nn.AvgPool2d(kernel_size=2, stride=2) on NHWC tensors (KernelEstimation's encoder, src/fusion_net/fusion_adacofnet.py:62-70,
  * 111-123): x [B,Hi,Wi,C] -> y [B,Hi/2,Wi/2,C]. */
 int fvfi_avg_pool2_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi, int C,
+                        void* stream);
+/* nn.MaxPool2d(2, stride=2) on NHWC tensors (FusionNet's encoder, src/fusion_net/fusion_net.py:39,56-60), same layout contract. */
+int fvfi_max_pool2_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi, int C,
                         void* stream);
 
 /* Planar [B,C,H,W] -> channels [0,C) of an NHWC buffer whose pixels are y_pixel_stride floats apart (pass y + offset for a

@@ -149,6 +149,8 @@ def test_avg_pool2_nhwc_matches_torch():
         y = conv.avg_pool2(x)
         ref = F.avg_pool2d(x, 2, 2)
         assert y.shape == ref.shape and float((y - ref).abs().max()) <= 1e-6
+        ym = conv.max_pool2(x)                                      # nn.MaxPool2d(2, stride=2) (fusion_net.py:39): exact
+        assert torch.equal(ym, F.max_pool2d(x, 2, 2))
 
 
 def test_put_planar_slice():
@@ -189,13 +191,15 @@ def test_upsample2_conv_single_channel(B, C, H, W, prec):
     from fvfi import conv
     g = torch.Generator(device="cuda").manual_seed(2)
     x = torch.randn((B, C, H, W), device="cuda", generator=g)
+    torch.manual_seed(2)                                   # the module's default init draws from the global generator
     m = torch.nn.Conv2d(C, 1, 3, 1, 1).cuda()
     with torch.no_grad():
         y = conv.upsample2_conv3x3_single(m, x, "sigmoid")
         up = F.interpolate(x.double(), scale_factor=2, mode="bilinear", align_corners=True)
         ref = torch.sigmoid(F.conv2d(up, m.weight.double(), m.bias.double(), padding=1))
     assert y.shape == ref.shape and y.is_contiguous()
-    assert float((y.double() - ref).abs().max()) <= 3e-6
+    # pre-activation error <= 2e-5 * max|z| (the convolution's own bound, both operand splits); sigmoid' <= 1/4
+    assert float((y.double() - ref).abs().max()) <= 8e-6
     conv.check_overflow()
 
 

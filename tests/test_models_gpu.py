@@ -5,6 +5,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import fusion_pipeline as fp
 
@@ -262,3 +263,33 @@ def test_phasenet_forward_fused_matches_stepwise(H, W, chunk):
         img_a = pyr.inv_filter_sparse(out, use_high=False)
         img_b = pyr.inv_filter_sparse(ref, use_high=False)
         assert float((img_a - img_b).abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 40, 72), (1, 64, 96), (3, 33, 50)])
+def test_adacofnet_prep_kernel(B, H, W):
+    """fvfi_adacofnet_prep == reflect pad to multiples of 32 (fusion_adacofnet.py:182-192), moduleNormalize (utility.py:86-87), concat,
+    NHWC, and ReplicationPad2d(kernel_pad) (:168,195) of the un-normalised frames -- bit exact (data movement + one subtraction)."""
+    import ctypes
+    from fvfi import _lib
+    from fvfi.adacofnet import moduleNormalize
+    torch.manual_seed(5)
+    f0, f2 = torch.rand((B, 3, H, W), device="cuda"), torch.rand((B, 3, H, W), device="cuda")
+    hp, wp, k = (H + 31) // 32 * 32, (W + 31) // 32 * 32, 2
+    x = torch.full((B, 8, hp, wp), 9.0, device="cuda").contiguous(memory_format=torch.channels_last)
+    p0 = torch.full((B, 3, hp + 2 * k, wp + 2 * k), 9.0, device="cuda")
+    p2 = torch.full_like(p0, 9.0)
+    mean = (ctypes.c_float * 3)(0.4631, 0.4352, 0.3990)
+    _lib.check(_lib.lib().fvfi_adacofnet_prep(f0.data_ptr(), f2.data_ptr(), x.data_ptr(), p0.data_ptr(), p2.data_ptr(), B, H, W, hp, wp, k,
+                                              ctypes.cast(mean, ctypes.c_void_p), _lib.stream_ptr()))
+
+    def pad(f):
+        if hp != H:
+            f = F.pad(f, (0, 0, 0, hp - H), mode='reflect')
+        if wp != W:
+            f = F.pad(f, (0, wp - W, 0, 0), mode='reflect')
+        return f
+    r0, r2 = pad(f0), pad(f2)
+    ref_x = torch.cat([moduleNormalize(r0), moduleNormalize(r2), torch.zeros((B, 2, hp, wp), device="cuda")], 1)
+    assert torch.equal(x, ref_x)
+    rp = torch.nn.ReplicationPad2d([k] * 4)
+    assert torch.equal(p0, rp(r0)) and torch.equal(p2, rp(r2))
