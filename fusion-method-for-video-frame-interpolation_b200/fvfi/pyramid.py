@@ -159,6 +159,39 @@ class Pyramid:
                                                        plan.workspace(N).data_ptr(), _lib.stream_ptr()))
         return out
 
+    def inv_filter_bands(self, bands, N, H, W, high=None):
+        """Reconstruction from COMPLEX band coefficients of some levels only: ``bands`` = {level: [nb tensors [N,h,w,2]]}, optionally
+        the high-pass residual ``high`` [N,H,W]; the low residual and the other levels are absent (contribute nothing).  -> [N,H,W]."""
+        dev = next(iter(bands.values()))[0].device
+        plan = self._plan(H, W, dev)
+        flat = [None] * (plan.L * self.nbands)
+        keep = []
+        for l, lst in bands.items():
+            for b, t in enumerate(lst):
+                assert tuple(t.shape) == (N,) + tuple(plan.shapes[l]) + (2,) and t.is_cuda
+                t = t.contiguous().float()
+                keep.append(t)
+                flat[l * self.nbands + b] = t
+        out = torch.empty((N, H, W), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            if high is not None:
+                high = high.reshape(N, H, W).contiguous().float()
+            _lib.check(_lib.lib().fvfi_pyr_reconstruct_complex(plan.handle, _lib.ptr(high), ptr_array(flat), None, N, out.data_ptr(),
+                                                               plan.workspace(N).data_ptr(), _lib.stream_ptr()))
+        return out
+
+    def level_mean_diff(self, vals, level, B, C):
+        """zbar [nb,B,h,w,2] = 1/C * sum_c (z_a - z_b) at ``level`` for ``vals`` = filter(cat(a planes [B*C], b planes [B*C]))
+        (fvfi_polar_mean_diff): the coefficient-domain form of (recon(a) - recon(b)).mean over the colour planes."""
+        ph, am = vals.phase[level], vals.amplitude[level]
+        h, w = int(ph.shape[2]), int(ph.shape[3])
+        assert ph.shape[0] == 2 * B * C * self.nbands
+        z = torch.empty((self.nbands, B, h, w, 2), dtype=torch.float32, device=ph.device)
+        with torch.cuda.device(ph.device):
+            _lib.check(_lib.lib().fvfi_polar_mean_diff(ph.data_ptr(), am.data_ptr(), z.data_ptr(), B, C, self.nbands, h, w,
+                                                       _lib.stream_ptr()))
+        return z
+
     # ---- API-compat helpers (the reference calls these from filter / inv_filter) -------------
     def coeff_to_values(self, coeff):
         """pyramid.py:48-78, vectorised: band list -> (phase, amplitude) in [N*nb,1,h,w] layout."""

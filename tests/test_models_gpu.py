@@ -293,3 +293,27 @@ def test_adacofnet_prep_kernel(B, H, W):
     assert torch.equal(x, ref_x)
     rp = torch.nn.ReplicationPad2d([k] * 4)
     assert torch.equal(p0, rp(r0)) and torch.equal(p2, rp(r2))
+
+
+def test_level0_difference_reconstruction_is_linear():
+    """mean_c(recon_{high + level 0}(a) - recon_{high + level 0}(b)) == ONE reconstruction of the channel-mean coefficient difference
+    (fvfi_polar_mean_diff + fvfi_pyr_reconstruct_complex): the uncertainty branch's h_freq difference (interpolate_twoframe.py:205-209)."""
+    import math
+    from fvfi import utils
+    from fvfi.pyramid import Pyramid
+    torch.manual_seed(11)
+    B, H, W = 2, 72, 104
+    a, b = torch.rand((B, 3, H, W), device="cuda"), torch.rand((B, 3, H, W), device="cuda")
+    height = utils.calc_pyr_height(a[0])
+    pyr = Pyramid(height=height, nbands=4, scale_factor=math.sqrt(2), device=torch.device("cuda"))
+    with torch.no_grad():
+        vals = pyr.filter(torch.cat((a.reshape(-1, H, W), b.reshape(-1, H, W)), 0))
+        va, vb = utils.separate_vals(vals, 2)
+        ra = pyr.inv_filter_sparse(va, use_low=False, levels=[0]).reshape(B, 3, H, W).mean(1)
+        rb = pyr.inv_filter_sparse(vb, use_low=False, levels=[0]).reshape(B, 3, H, W).mean(1)
+        zbar = pyr.level_mean_diff(vals, 0, B, 3)
+        high_bar = (va.high_level - vb.high_level).reshape(B, 3, H, W).mean(1)
+        d = pyr.inv_filter_bands({0: [zbar[i] for i in range(4)]}, B, H, W, high=high_bar)
+    ref = ra - rb
+    assert d.shape == ref.shape
+    assert float((d - ref).abs().max()) <= 5e-6 * max(1.0, float(ref.abs().max()))
