@@ -519,44 +519,7 @@ __global__ void __launch_bounds__(256) adacofnet_prep_kernel(const float* __rest
     }
 }
 
-// ---- high-frequency disagreement of two predictions (src/fusion_net/interpolate_twoframe.py:205-211) --------------------------
-// h_freq = mean over the 3 colour planes of the level-0-only reconstruction of each prediction; the map uses h_freq_a - h_freq_b.
-// Reconstruction is real-linear in the complex coefficients z = A e^{i phi}, so the difference and the channel mean are taken on
-// the coefficients:  zbar[band][b] = 1/C * sum_c ( z_a[b*C + c] - z_b[b*C + c] )  -- ONE plane per frame pair is reconstructed
-// instead of 2*C.  phase / amp: level tensors [2*P*NB, h, w] of the decomposition of [a planes | b planes], P = B*C.
-template <int NB>
-__global__ void __launch_bounds__(256) polar_mean_diff_kernel(const float* __restrict__ phase, const float* __restrict__ amp,
-                                                              float2* __restrict__ zbar, size_t plane, int B, int C) {
-    const size_t px = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (px >= plane) return;
-    const int b = blockIdx.y, P = B * C;
-    const float inv = 1.f / (float)C;
-#pragma unroll
-    for (int band = 0; band < NB; ++band) {
-        float re = 0.f, im = 0.f;
-        for (int c = 0; c < C; ++c) {
-            const size_t ia = ((size_t)(b * C + c) * NB + band) * plane + px, ib = ((size_t)(P + b * C + c) * NB + band) * plane + px;
-            float sa, ca, sb, cb;
-            sincosf(__ldg(phase + ia), &sa, &ca);
-            sincosf(__ldg(phase + ib), &sb, &cb);
-            const float Aa = __ldg(amp + ia), Ab = __ldg(amp + ib);
-            re += Aa * ca - Ab * cb;
-            im += Aa * sa - Ab * sb;
-        }
-        zbar[((size_t)band * B + b) * plane + px] = make_float2(re * inv, im * inv);
-    }
-}
 }  // namespace fvfi
-
-extern "C" int fvfi_polar_mean_diff(const float* phase, const float* amp, float* zbar, int B, int C, int nb, int H, int W, void* stream) {
-    FVFI_CHECK_ARG(phase && amp && zbar && B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "polar_mean_diff: bad argument");
-    FVFI_CHECK_ARG(nb == 4, "polar_mean_diff: nbands must be 4 (got %d)", nb);
-    const size_t plane = (size_t)H * W;
-    dim3 grid((unsigned)((plane + 255) / 256), B);
-    fvfi::polar_mean_diff_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(phase, amp, (float2*)zbar, plane, B, C);
-    FVFI_LAUNCH_CHECK();
-    return FVFI_OK;
-}
 
 extern "C" int fvfi_adacofnet_prep(const float* frame0, const float* frame2, float* x_nhwc8, float* padded0, float* padded2, int B,
                                    int H, int W, int Hp, int Wp, int kpad, const float* mean3_host, void* stream) {

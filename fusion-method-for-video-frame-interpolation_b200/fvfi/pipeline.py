@@ -98,25 +98,27 @@ class FusionPipeline(torch.nn.Module):
         self._tick('pyr.inv_filter(3 planes/frame)')
         phase_pred = transform.lab2rgb(lab_pred)                                                # :192
         # uncertainty maps (:197-225)
-        # only level 0 (h_freq) and the six coarsest levels + low pass (freq_diff) of these pyramids are ever read
+        # only level 0 + the high residual (h_freq) and the six coarsest levels + low pass (freq_diff) of these pyramids are ever read
         L = pyr.height - 2
-        used = sorted(set([0]) | set(range(L - 6, L)))
-        vals_both = pyr.filter(torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), levels=used)
-        vals_ada, vals_ph = utils.separate_vals(vals_both, 2)
-        self._tick('lab2rgb+pyr.filter(6 planes/frame)')
+        coarse = list(range(L - 6, L))
         if self.fused_phase_glue:
-            # h_freq - h_freq_ph = mean_c(recon_level0(ada) - recon_level0(phase)) (get_last_value_levels(., 1), :205-209): the
-            # reconstruction is linear, so difference and channel mean are taken on the residual / complex level-0 coefficients and ONE plane
-            # per frame pair is reconstructed instead of six
-            zbar = pyr.level_mean_diff(vals_both, 0, B, 3)
-            high_bar = (vals_ada.high_level - vals_ph.high_level).reshape(r_shape).mean(1)      # the high residual is kept too
-            h_diff = pyr.inv_filter_bands({0: [zbar[b] for b in range(pyr.nbands)]}, B, H, W, high=high_bar)
-            del zbar, high_bar
+            # h_freq - h_freq_ph = mean_c(recon_{high + level 0}(ada_c) - recon_{high + level 0}(phase_c))  (get_last_value_levels(., 1),
+            # :205-209).  Decomposition and reconstruction are linear in the image, so this is recon_{high + level 0} of the single
+            # plane  xbar = mean_c(ada_c - phase_c): the six colour planes are decomposed on the (tiny) coarse levels only.
+            vals_ada, vals_ph = utils.separate_vals(
+                pyr.filter(torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), want_high=False, levels=coarse), 2)
+            self._tick('lab2rgb+pyr.filter(6 planes/frame)')
+            v0 = pyr.filter((ada_pred - phase_pred).mean(1), levels=[0])
+            h_diff = pyr.inv_filter_sparse(v0, use_low=False, levels=[0])
+            del v0
         else:
+            used = sorted(set([0]) | set(coarse))
+            vals_ada, vals_ph = utils.separate_vals(
+                pyr.filter(torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), levels=used), 2)
+            self._tick('lab2rgb+pyr.filter(6 planes/frame)')
             h_freq = pyr.inv_filter_sparse(vals_ada, use_low=False, levels=[0]).reshape(r_shape).mean(1)
             h_freq_ph = pyr.inv_filter_sparse(vals_ph, use_low=False, levels=[0]).reshape(r_shape).mean(1)
             h_diff = h_freq - h_freq_ph
-        del vals_both
         h_freq_diff = (h_diff.abs() * 100).clamp(min=0, max=1.0)
         self._tick('pyr.inv_filter(level0 x2)')
         phase_uncertainty = filters.gaussian_filter(h_freq_diff, 5)

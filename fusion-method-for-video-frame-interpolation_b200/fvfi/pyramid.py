@@ -180,18 +180,6 @@ class Pyramid:
                                                                plan.workspace(N).data_ptr(), _lib.stream_ptr()))
         return out
 
-    def level_mean_diff(self, vals, level, B, C):
-        """zbar [nb,B,h,w,2] = 1/C * sum_c (z_a - z_b) at ``level`` for ``vals`` = filter(cat(a planes [B*C], b planes [B*C]))
-        (fvfi_polar_mean_diff): the coefficient-domain form of (recon(a) - recon(b)).mean over the colour planes."""
-        ph, am = vals.phase[level], vals.amplitude[level]
-        h, w = int(ph.shape[2]), int(ph.shape[3])
-        assert ph.shape[0] == 2 * B * C * self.nbands
-        z = torch.empty((self.nbands, B, h, w, 2), dtype=torch.float32, device=ph.device)
-        with torch.cuda.device(ph.device):
-            _lib.check(_lib.lib().fvfi_polar_mean_diff(ph.data_ptr(), am.data_ptr(), z.data_ptr(), B, C, self.nbands, h, w,
-                                                       _lib.stream_ptr()))
-        return z
-
     # ---- API-compat helpers (the reference calls these from filter / inv_filter) -------------
     def coeff_to_values(self, coeff):
         """pyramid.py:48-78, vectorised: band list -> (phase, amplitude) in [N*nb,1,h,w] layout."""

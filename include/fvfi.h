@@ -153,12 +153,6 @@ int fvfi_upsample2_tapsum(const float* z, int z_pixel_stride, const float* bias,
 int fvfi_adacofnet_prep(const float* frame0, const float* frame2, float* x_nhwc8, float* padded0, float* padded2, int B,
                         int H, int W, int Hp, int Wp, int kpad, const float* mean3_host, void* stream);
 
-/* Coefficient-domain form of "mean over the C colour planes of (reconstruction of prediction a - reconstruction of prediction b)"
- * for one pyramid level (src/fusion_net/interpolate_twoframe.py:205-211): phase / amp [2*B*C*nb, H, W] = that level of the
- * decomposition of [a planes | b planes];  zbar [nb][B][H][W][2] (complex interleaved) = 1/C * sum_c (z_a - z_b), z = amp e^{i phase}.
- * Feed zbar's nb slices to fvfi_pyr_reconstruct_complex: one plane per frame pair is reconstructed instead of 2*C.  nb must be 4. */
-int fvfi_polar_mean_diff(const float* phase, const float* amp, float* zbar, int B, int C, int nb, int H, int W, void* stream);
-
 /* PhaseNet glue, fused (src/train/utils.py:47-127 separate_vals / get_concat_layers_inf, src/phase_net/phase_net.py:42-78
  * normalize_vals, :141 concat, :155-156 amplitude blend, :80-105 reverse_normalize).
  * phase / amp: one level of fvfi_pyr_decompose of [frame-1 planes | frame-2 planes]: [2*P*nb, H, W], channel = plane*nb + band.

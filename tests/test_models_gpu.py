@@ -296,8 +296,9 @@ def test_adacofnet_prep_kernel(B, H, W):
 
 
 def test_level0_difference_reconstruction_is_linear():
-    """mean_c(recon_{high + level 0}(a) - recon_{high + level 0}(b)) == ONE reconstruction of the channel-mean coefficient difference
-    (fvfi_polar_mean_diff + fvfi_pyr_reconstruct_complex): the uncertainty branch's h_freq difference (interpolate_twoframe.py:205-209)."""
+    """mean_c(recon_{high + level 0}(a_c) - recon_{high + level 0}(b_c)) == recon_{high + level 0}(filter(mean_c(a_c - b_c))): the
+    uncertainty branch's h_freq difference (interpolate_twoframe.py:205-209) from ONE decomposed plane per frame pair; also through
+    the complex-band entry point (Pyramid.inv_filter_bands)."""
     import math
     from fvfi import utils
     from fvfi.pyramid import Pyramid
@@ -307,13 +308,15 @@ def test_level0_difference_reconstruction_is_linear():
     height = utils.calc_pyr_height(a[0])
     pyr = Pyramid(height=height, nbands=4, scale_factor=math.sqrt(2), device=torch.device("cuda"))
     with torch.no_grad():
-        vals = pyr.filter(torch.cat((a.reshape(-1, H, W), b.reshape(-1, H, W)), 0))
-        va, vb = utils.separate_vals(vals, 2)
+        va, vb = utils.separate_vals(pyr.filter(torch.cat((a.reshape(-1, H, W), b.reshape(-1, H, W)), 0)), 2)
         ra = pyr.inv_filter_sparse(va, use_low=False, levels=[0]).reshape(B, 3, H, W).mean(1)
         rb = pyr.inv_filter_sparse(vb, use_low=False, levels=[0]).reshape(B, 3, H, W).mean(1)
-        zbar = pyr.level_mean_diff(vals, 0, B, 3)
-        high_bar = (va.high_level - vb.high_level).reshape(B, 3, H, W).mean(1)
-        d = pyr.inv_filter_bands({0: [zbar[i] for i in range(4)]}, B, H, W, high=high_bar)
+        v0 = pyr.filter((a - b).mean(1), levels=[0])
+        d = pyr.inv_filter_sparse(v0, use_low=False, levels=[0])
+        z = torch.stack((torch.cos(v0.phase[0]) * v0.amplitude[0], torch.sin(v0.phase[0]) * v0.amplitude[0]), -1)   # [B*4,1,h,w,2]
+        z = z.reshape(B, 4, z.shape[2], z.shape[3], 2)
+        d2 = pyr.inv_filter_bands({0: [z[:, i].contiguous() for i in range(4)]}, B, H, W, high=v0.high_level)
     ref = ra - rb
     assert d.shape == ref.shape
     assert float((d - ref).abs().max()) <= 5e-6 * max(1.0, float(ref.abs().max()))
+    assert float((d2 - d).abs().max()) <= 5e-6 * max(1.0, float(ref.abs().max()))
