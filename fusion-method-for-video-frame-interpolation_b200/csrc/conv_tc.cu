@@ -80,6 +80,8 @@ struct ConvArgs {
     int nacc;              // TMEM accumulator buffers (2 when they fit: epilogue of tile j-1 overlaps the MMAs of tile j)
     int tiles_x, tiles_y, ntiles;
     unsigned a_stage_bytes, b_stage_bytes;
+    const float* res;      // optional residual [B,H,W,>=Cout] NHWC added AFTER the activation (U-Net skip connections), or null
+    int ldr;               // floats per pixel of the residual
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -387,6 +389,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
         const size_t plane = (size_t)A.H * A.W;
         const int quarter = warp & 3;                              // a warp reads TMEM lanes 32*(warp % 4) .. +31
         const int m = quarter * 32 + lane;                         // accumulator row = TMEM lane
+        const bool res_vec = A.res && (A.Cout & 15) == 0 && (A.ldr & 7) == 0 && ((((size_t)A.res) & 31) == 0);
 
         // ---- epilogue of tile number jt (coordinates T): TMEM -> registers -> bias/activation -> global
         auto epilogue = [&](int jt, const TileCoord& T) {
@@ -461,6 +464,24 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     } else {
                         v[i] = apply_act<ACT>(z0); v[i + 1] = apply_act<ACT>(z1);
                         v[i + 2] = apply_act<ACT>(z2); v[i + 3] = apply_act<ACT>(z3);
+                    }
+                }
+                if (ACT != ACT_SOFTMAX && A.res) {
+                    // skip connection fused into the epilogue:  y = act(conv(x)) + residual   (fusion_adacofnet.py:128-138: d5 + c5 ...)
+                    const int ocol = T.x0 + t * 8 + (m & 7);
+                    if (orow < A.H && ocol < A.W) {
+                        const float* rp = A.res + (((size_t)T.img * A.H + orow) * A.W + ocol) * A.ldr + n0;
+                        if (res_vec) {
+                            float q[16];
+                            ldg256(rp, q);
+                            ldg256(rp + 8, q + 8);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] += q[i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (n0 + i < A.Cout) v[i] += __ldg(rp + i);
+                        }
                     }
                 }
                 store16(t, n0, v);
@@ -916,6 +937,16 @@ extern "C" int fvfi_conv2d_overflow_count(void) {
 extern "C" int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias, float* y,
                                 int y_pixel_stride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad_mode,
                                 int activation, int out_nchw, int precision, void* stream) {
+    return fvfi_conv2d_nhwc_residual(x, x_pixel_stride, packed_weight, bias, nullptr, 0, y, y_pixel_stride, B, H, W, Cin, Cout, KH, KW,
+                                     pad_mode, activation, out_nchw, precision, stream);
+}
+
+extern "C" int fvfi_conv2d_nhwc_residual(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias,
+                                         const float* residual, int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H,
+                                         int W, int Cin, int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw,
+                                         int precision, void* stream) {
+    FVFI_CHECK_ARG(!residual || (activation != ACT_SOFTMAX && residual_pixel_stride >= Cout),
+                   "conv2d: a residual needs a pixel stride >= Cout and no softmax");
     FVFI_CHECK_ARG(x && packed_weight && y, "conv2d: null pointer");
     FVFI_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && B <= 65535, "conv2d: bad dimension");
     FVFI_CHECK_ARG((KH == 1 || KH == 3 || KH == 5) && KW == KH, "conv2d: kernel must be 1x1, 3x3 or 5x5");
@@ -927,6 +958,7 @@ extern "C" int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float*
     ConvArgs a{};
     a.x = x; a.hdr = packed_weight; a.wpack = packed_weight + CV_HDR; a.bias = bias; a.y = y;
     a.ldx = x_pixel_stride; a.ldy = y_pixel_stride; a.out_nchw = (out_nchw == 1) ? 1 : 0;
+    a.res = residual; a.ldr = residual_pixel_stride;
     a.cout_store = (out_nchw == 2) ? ((Cout + 15) & ~15) : Cout;
     FVFI_CHECK_ARG(out_nchw >= 0 && out_nchw <= 2, "conv2d: output layout must be 0 (NHWC), 1 (NCHW) or 2 (NHWC, zero-padded channels)");
     FVFI_CHECK_ARG(out_nchw != 2 || y_pixel_stride >= a.cout_store, "conv2d: padded NHWC output needs a pixel stride >= round16(Cout)");

@@ -85,7 +85,7 @@ class KernelEstimation(torch.nn.Module):
         self.moduleOcclusion = Subnet(1, nn.Sigmoid(), last_in=64)
 
     @staticmethod
-    def _seq_tc(seq, x, nchw_last=False):
+    def _seq_tc(seq, x, nchw_last=False, residual=None):
         """Run an nn.Sequential of Conv2d / ReLU / Upsample / Softmax / Sigmoid: conv + activation is one tcgen05 kernel,
         bilinear upsampling is the NHWC resize kernel; with ``nchw_last`` the final conv writes planar NCHW."""
         mods = list(seq)
@@ -99,7 +99,8 @@ class KernelEstimation(torch.nn.Module):
                 # a conv feeding an Upsample keeps its channels padded to 16 (zeros): resize and the next conv then
                 # use 16-byte accesses even for the 25-channel heads
                 pad = (i + 2 < len(mods) and isinstance(mods[i + 2], torch.nn.Upsample) and m.out_channels % 4 != 0)
-                x = tc.conv_module(m, x, act, nchw_out=nchw_last and i == last_conv, pad_out=pad)
+                x = tc.conv_module(m, x, act, nchw_out=nchw_last and i == last_conv, pad_out=pad,
+                                   residual=residual if i == last_conv else None)   # skip connection after the last conv + act
                 i += 2 if act else 1
             elif (isinstance(m, torch.nn.Upsample) and i + 1 == last_conv and mods[last_conv].out_channels == 1
                   and m.scale_factor == 2 and m.mode == 'bilinear' and m.align_corners):
@@ -134,11 +135,11 @@ class KernelEstimation(torch.nn.Module):
         c3 = run(self.moduleConv3, pool(c2))
         c4 = run(self.moduleConv4, pool(c3))
         c5 = run(self.moduleConv5, pool(c4))
-        d5 = run(self.moduleUpsample5, run(self.moduleDeconv5, pool(c5)))
-        d4 = run(self.moduleUpsample4, run(self.moduleDeconv4, d5 + c5))
-        d3 = run(self.moduleUpsample3, run(self.moduleDeconv3, d4 + c4))
-        d2 = run(self.moduleUpsample2, run(self.moduleDeconv2, d3 + c3))
-        comb = d2 + c2
+        # the skip additions (fusion_adacofnet.py:128-138) ride on the epilogue of the Upsample modules' convolution
+        s5 = run(self.moduleUpsample5, run(self.moduleDeconv5, pool(c5)), residual=c5)      # d5 + c5
+        s4 = run(self.moduleUpsample4, run(self.moduleDeconv4, s5), residual=c4)            # d4 + c4
+        s3 = run(self.moduleUpsample3, run(self.moduleDeconv3, s4), residual=c3)            # d3 + c3
+        comb = run(self.moduleUpsample2, run(self.moduleDeconv2, s3), residual=c2)          # d2 + c2
         heads = (self.moduleWeight1, self.moduleAlpha1, self.moduleBeta1, self.moduleWeight2, self.moduleAlpha2,
                  self.moduleBeta2, self.moduleOcclusion)
         # the seven heads start with a 64 -> 64 convolution of the SAME tensor: one 64 -> 448 convolution (N = 256 + 192

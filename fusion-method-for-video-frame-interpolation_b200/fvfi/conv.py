@@ -66,11 +66,12 @@ def to_nhwc(x):
     return x.contiguous(memory_format=torch.channels_last)
 
 
-def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_out=False, pad_out=False):
+def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_out=False, pad_out=False, residual=None):
     """x [B,Cin,H,W] (any memory format; channels_last avoids a copy) -> [B,Cout,H,W] channels_last
     (``nchw_out=True``: plain contiguous NCHW, written directly by the epilogue).
     Equivalent to act(F.conv2d(pad(x), weight, bias)) with 'same' padding (K//2) in zeros or reflect mode;
     act 'softmax' is over the channel dimension.
+    ``residual`` (channels_last [B,Cout,H,W]): added after the activation in the epilogue (skip connection).
     ``pad_out=True``: the result has round16(Cout) channels, the extra ones zero (keeps 16-byte accesses for channel
     counts such as 25).  ``x`` may carry such zero padding channels beyond the weight's Cin."""
     if not x.is_cuda:
@@ -83,7 +84,7 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
     assert xc.stride(1) == 1
     ldx = xc.stride(3)                       # floats per pixel
     if (KH == 1 and Cout <= 8 and Cin % 8 == 0 and Cin <= 128 and ldx % 8 == 0 and xc.data_ptr() % 32 == 0
-            and act != "softmax" and out is None and not nchw_out and not pad_out):
+            and act != "softmax" and out is None and not nchw_out and not pad_out and residual is None):
         return _conv1x1_direct(xc, weight, bias, act)
     if out is None:
         out = torch.empty((B, (Cout + 15) // 16 * 16 if pad_out else Cout, H, W), dtype=torch.float32, device=x.device,
@@ -96,15 +97,20 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
     L = _lib.lib()
     pad_mode = {"zeros": 0, "reflect": 1}[padding_mode]
     b = None if bias is None else bias.detach().contiguous().float()
+    rc = None
+    if residual is not None:
+        assert not nchw_out and act != "softmax" and tuple(residual.shape) == (B, Cout, H, W)
+        rc = to_nhwc(residual.float())
     with torch.cuda.device(x.device):
         parts = _packed(weight)
         if timing is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         for (o, n, buf, _) in parts:
-            _lib.check(L.fvfi_conv2d_nhwc(xc.data_ptr(), ldx, buf.data_ptr(), None if b is None else b.data_ptr() + 4 * o,
-                                          out.data_ptr() + 4 * o, ldy, B, H, W, Cin, n, KH, KW, pad_mode, ACT[act],
-                                          1 if nchw_out else (2 if pad_out else 0), precision, _lib.stream_ptr()))
+            _lib.check(L.fvfi_conv2d_nhwc_residual(xc.data_ptr(), ldx, buf.data_ptr(), None if b is None else b.data_ptr() + 4 * o,
+                                                   None if rc is None else rc.data_ptr() + 4 * o, 0 if rc is None else rc.stride(3),
+                                                   out.data_ptr() + 4 * o, ldy, B, H, W, Cin, n, KH, KW, pad_mode, ACT[act],
+                                                   1 if nchw_out else (2 if pad_out else 0), precision, _lib.stream_ptr()))
         if timing is not None:
             e1.record()
             timing.append((2.0 * B * H * W * Cin * Cout * KH * KW, e0, e1, len(parts), (B, Cin, Cout, KH, H, W, act)))
@@ -196,13 +202,13 @@ def avg_pool2(x, _fn="fvfi_avg_pool2_nhwc"):
     return out
 
 
-def conv_module(conv, x, act=None, nchw_out=False, pad_out=False):
+def conv_module(conv, x, act=None, nchw_out=False, pad_out=False, residual=None):
     """Run an nn.Conv2d (stride 1, dilation 1, padding == K//2) through the tensor-core kernel."""
     k = conv.kernel_size[0]
     assert conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
     assert conv.padding == (k // 2, k // 2) or (k == 1 and conv.padding == (0, 0))
     mode = "zeros" if k == 1 else conv.padding_mode
-    return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out, pad_out=pad_out)
+    return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out, pad_out=pad_out, residual=residual)
 
 
 _fold_cache = {}

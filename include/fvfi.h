@@ -125,6 +125,13 @@ int fvfi_conv2d_pack_weights(const float* weight_oihw, float* packed, int Cout, 
 int fvfi_conv2d_nhwc(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias, float* y,
                      int y_pixel_stride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad_mode,
                      int activation, int out_nchw, int precision, void* stream);
+/* Same with a skip connection fused into the epilogue:  y = act(conv(x) + bias) + residual,  residual [B,H,W,>=Cout] NHWC with
+ * residual_pixel_stride floats per pixel (KernelEstimation's decoder, src/fusion_net/fusion_adacofnet.py:128-138: d5 + c5, ...);
+ * residual == NULL is fvfi_conv2d_nhwc.  Not with the softmax activation. */
+int fvfi_conv2d_nhwc_residual(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias,
+                              const float* residual, int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H,
+                              int W, int Cin, int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw,
+                              int precision, void* stream);
 /* FVFI_CONV_F16X3 scales activations by 2^4 before the fp16 split; |x| > 4094 would leave fp16's range.  Returns 1
  * (and clears the flag) if any convolution since the last call saw such a value, 0 if not, -1 on error.
  * Synchronises the device. */

@@ -222,3 +222,20 @@ def test_conv_planar_output_tiles(B, Cin, Cout, H, W, act, prec):
     assert float((y.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
     assert float((canary[B * Cout * H * W:] - 7.5).abs().max()) == 0.0           # nothing written past the last plane
     conv.check_overflow()
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 64, 64, 40, 56), (1, 128, 512, 17, 30), (1, 32, 25, 33, 47)])
+def test_conv_residual_epilogue(B, Cin, Cout, H, W, prec):
+    """y = relu(conv(x)) + skip in one launch (fvfi_conv2d_nhwc_residual): KernelEstimation's decoder additions d_k + c_k
+    (fusion_adacofnet.py:128-138); vector and scalar residual loads, Cout > 256 split."""
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn((B, Cin, H, W), device="cuda", generator=g)
+    w = torch.randn((Cout, Cin, 3, 3), device="cuda", generator=g) / (3 * Cin ** 0.5)
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    skip = torch.randn((B, Cout, H, W), device="cuda", generator=g)
+    y = conv.conv2d(x, w, b, "zeros", "relu", residual=skip)
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)) + skip.double()
+    assert y.shape == ref.shape
+    assert float((y.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    conv.check_overflow()
