@@ -597,7 +597,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
         const bool vec8 = ((A.ldx & 7) == 0) && (A.ldx >= cin8) && ((((size_t)A.x) & 31) == 0);
         constexpr int CPK = cv_cpk(PREC);
         constexpr int CHUNK = cv_chunk(PREC);
-        constexpr int U = (PREC == PREC_F16X3) ? 4 : 6;            // loads in flight per thread
         const float xs = (float)(1 << CV_X_SHIFT);
         float amax = 0.f;
         int g = 0;                                                 // running chunk counter of the A ring
