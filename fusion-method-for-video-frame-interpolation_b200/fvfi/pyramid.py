@@ -148,8 +148,9 @@ class Pyramid:
         plan = self._plan(H, W, high.device)
         L = plan.L
         levels = set(range(L)) if levels is None else set(levels)
-        phase = [vals.phase[l].contiguous() if l in levels else None for l in range(L)]
-        amp = [vals.amplitude[l].contiguous() if l in levels else None for l in range(L)]
+        ok = lambda t: torch.is_tensor(t)          # levels given as the int 0 are absent (phase_net.py:91-93)
+        phase = [vals.phase[l].contiguous() if l in levels and ok(vals.phase[l]) and ok(vals.amplitude[l]) else None for l in range(L)]
+        amp = [vals.amplitude[l].contiguous() if phase[l] is not None else None for l in range(L)]
         high_c = high.contiguous() if use_high else None
         low_c = vals.low_level.contiguous() if use_low else None
         out = torch.empty((N, H, W), dtype=torch.float32, device=high.device)
