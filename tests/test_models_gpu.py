@@ -263,6 +263,16 @@ def test_phasenet_forward_fused_matches_stepwise(H, W, chunk):
         img_a = pyr.inv_filter_sparse(out, use_high=False)
         img_b = pyr.inv_filter_sparse(ref, use_high=False)
         assert float((img_a - img_b).abs().max()) <= 2e-6
+        # hierarchical mode (phase_net.py:91-93): only the m coarsest levels are predicted, the finer ones are the int 0
+        m = height - 4
+        ref_m = net(net.normalize_vals(utils.get_concat_layers_inf(pyr, utils.separate_vals(vals, 2))), m)
+        out_m = net.forward_fused(vals, pyr.last_amp_max, m)
+        for a, b in zip(out_m.phase + out_m.amplitude, ref_m.phase + ref_m.amplitude):
+            if torch.is_tensor(b):
+                assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(b.abs().max()))
+            else:
+                assert not torch.is_tensor(a) and a == 0 and b == 0
+        assert float((pyr.inv_filter_sparse(out_m, use_high=False) - pyr.inv_filter(ref_m)).abs().max()) <= 2e-6
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 40, 72), (1, 64, 96), (3, 33, 50)])
