@@ -22,7 +22,7 @@ class PipelineWorkload:
         torch.backends.cudnn.allow_tf32 = self.tf32
         torch.backends.cuda.matmul.allow_tf32 = self.tf32
         torch.backends.cudnn.benchmark = True
-        self.pipe = FusionPipeline(self.H, self.W, device, phase_plane_chunk=int(os.environ.get("FVFI_PLANE_CHUNK", "12")))
+        self.pipe = FusionPipeline(self.H, self.W, device, phase_plane_chunk=int(os.environ.get("FVFI_PLANE_CHUNK", "24")))
         self.pipe.max_batch = int(os.environ.get("FVFI_MAX_BATCH", "8" if self.H <= 1080 else "2"))
         self.pipe.load_state(fp.seeded_state(0))
         r1, r2 = fp.seeded_frames(1, self.H, self.W, seed)
