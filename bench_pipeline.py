@@ -138,6 +138,10 @@ class PipelineWorkload:
         return {"bound": "tensor", "kernel": "conv_split_kernel<ACT, PREC_F16X3> (all %d launches of one step)" % launches,
                 "achieved": round(ach, 1), "peak": tpeak, "unit": "TFLOP/s", "frac": round(ach / tpeak, 4),
                 "mma_frac": round(3 * ach / tpeak, 4), "traffic": None, "peak_source": tsrc,
+                # `achieved` aggregates ~660 launches of different shapes, so there is no single per-launch DRAM figure; one
+                # representative launch from the ncu --set full capture (profiles/r01_conv_v7_summary.txt):
+                "traffic_example": {"launch": "64->64 3x3 ReLU @544x960, batch 4", "dram_bytes": 1020526336,
+                                    "algorithmic_bytes": 1069842432, "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum"},
                 "ms_per_step_in_kernel": round(ms, 2), "share_of_step": round(ms / max(step_ms, 1e-9), 3),
                 "algorithmic_flops_per_step": flops,
                 "other_kernels": self._time_hbm_kernels(peak), "hbm_peak": peak, "hbm_peak_source": peak_src,
