@@ -150,11 +150,11 @@ def upsample2_conv3x3_single(conv, x, act=None):
         hit = (key, w.detach()[0].reshape(C, 9).t().reshape(9, C, 1, 1).contiguous())     # [tap = ky*3+kx, c]
         _tap_cache[id(conv)] = hit
     B, _, H, W = x.shape
-    z = conv2d(x, hit[1], None, "zeros", None, pad_out=True)                              # [B,16,H,W] NHWC, 9 used
+    z = conv2d(x, hit[1], None, "zeros", None, nchw_out=True)                             # planar [B,9,H,W]: coalesced tap reads
     out = torch.empty((B, 1, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
     b = None if conv.bias is None else conv.bias.detach().contiguous().float()
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().fvfi_upsample2_tapsum(z.data_ptr(), z.stride(3), None if b is None else b.data_ptr(),
+        _lib.check(_lib.lib().fvfi_upsample2_tapsum(z.data_ptr(), 0, None if b is None else b.data_ptr(),
                                                     out.data_ptr(), B, H, W, ACT[act], _lib.stream_ptr()))
     return out
 

@@ -147,7 +147,7 @@ int fvfi_conv1x1_nhwc(const float* x, int x_pixel_stride, const float* weight, c
 
 /* Tail of KernelEstimation's occlusion head, Upsample(x2, bilinear, align_corners=True) -> Conv2d(C, 1, 3, padding 1) ->
  * Sigmoid (src/fusion_net/fusion_adacofnet.py:50-59, 103-104), with the channel contraction done first at half resolution:
- * z [B,Hi,Wi,z_pixel_stride] holds in channels 0..8 the nine tap maps z_t = sum_c w[0,c,t] x_c (t = ky*3 + kx; a 1x1
+ * z [B,Hi,Wi,z_pixel_stride] (or, with z_pixel_stride == 0, planar [B,9,Hi,Wi]) holds the nine tap maps z_t = sum_c w[0,c,t] x_c (t = ky*3 + kx; a 1x1
  * convolution C -> 9 of the half-resolution feature), and  y[b,i,j] = act(bias[0] + sum_t [p_t inside] bilinear(z_t)(p_t)),
  * p_t = (i + ky - 1, j + kx - 1), y [B, 2*Hi, 2*Wi].  Same real-number result as the reference's order of operations. */
 int fvfi_upsample2_tapsum(const float* z, int z_pixel_stride, const float* bias, float* y, int B, int Hi, int Wi,
