@@ -161,6 +161,7 @@ class KernelEstimation(torch.nn.Module):
             self._first_cache = hit
         return hit[1]
 
+    @tc.range_checked
     def forward(self, rfield0, rfield2):
         if tc.use_tc(rfield0) and not self.training:
             return self._forward_tc(rfield0, rfield2)
@@ -224,6 +225,7 @@ class AdaCoFNet(torch.nn.Module):
         """The reference wraps models in src/adacof/models/__init__.py:Model whose ``load`` forwards here."""
         self.load_state_dict(state_dict)
 
+    @tc.range_checked
     def forward(self, frame0, frame2, return_warped=True):
         h0, w0 = int(frame0.shape[2]), int(frame0.shape[3])
         if h0 != int(frame2.shape[2]) or w0 != int(frame2.shape[3]):

@@ -12,16 +12,69 @@ import torch
 
 from . import _lib
 
-enabled = True   # use the tcgen05 kernels for inference convolutions (False -> torch/cuDNN scaffolding)
+enabled = True   # use the tcgen05 kernels for inference convolutions (False -> torch/cuDNN scaffolding, tests only)
 PRECISIONS = {"tf32x3": 0, "f16x3": 1}
 precision = PRECISIONS[os.environ.get("FVFI_CONV_PREC", "f16x3")]   # operand split (include/fvfi.h: FVFI_CONV_*)
+range_check = True   # range_checked() forwards verify the 3xFP16 range flag and re-run in 3xTF32 when it was raised
+_guard_depth = 0
+
+
+def overflow_pending():
+    """True if a 3xFP16 convolution enqueued on the current stream since the last check saw an activation outside the
+    representable range (|x| * 2^4 > 65504).  Synchronises the current stream and clears the flag."""
+    import torch as _t
+    _t.cuda.current_stream().synchronize()
+    return _lib.lib().fvfi_conv2d_overflow_count() > 0
 
 
 def check_overflow():
-    """Raise if a convolution since the last check saw an activation outside the 3xFP16 range (|x| > 4094).
-    Synchronises; call it where the caller synchronises anyway (end of an inference call)."""
-    if precision == PRECISIONS["f16x3"] and _lib.lib().fvfi_conv2d_overflow_count() > 0:
-        raise FloatingPointError("fvfi.conv: activation beyond the 3xFP16 range (|x| > 4094); set FVFI_CONV_PREC=tf32x3")
+    """Raise if a convolution since the last check left the 3xFP16 range (for callers that run the convolutions directly,
+    outside the range_checked() module forwards)."""
+    if precision == PRECISIONS["f16x3"] and overflow_pending():
+        raise FloatingPointError("fvfi.conv: activation beyond the 3xFP16 range (|x| > 4094); use conv.forced_precision('tf32x3')")
+
+
+class forced_precision:
+    """``with forced_precision('tf32x3'):`` -- run the enclosed convolutions with the given operand split."""
+
+    def __init__(self, name):
+        self.value = PRECISIONS[name]
+
+    def __enter__(self):
+        global precision
+        self.old, precision = precision, self.value
+        return self
+
+    def __exit__(self, *exc):
+        global precision
+        precision = self.old
+
+
+def range_checked(fn):
+    """Decorator of the inference entry points (FusionPipeline.forward / fusion_inputs, AdaCoFNet.forward, PhaseNet.forward /
+    forward_fused, FusionNet.forward).  The default operand split (3xFP16) represents activations up to |x| = 4094; a kernel that
+    meets a larger value raises a device flag instead of saturating.  The OUTERMOST decorated call reads the flag when its work
+    is enqueued (one stream synchronisation per call) and, if it was raised, runs the whole call again with the range-unlimited
+    3xTF32 split -- the caller never sees an out-of-range result and never has to choose a precision."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        global _guard_depth
+        t = next((a for a in args if torch.is_tensor(a)), None)
+        if (_guard_depth > 0 or not range_check or not enabled or precision != PRECISIONS["f16x3"] or torch.is_grad_enabled()
+                or (t is not None and not t.is_cuda)):
+            return fn(*args, **kwargs)
+        _guard_depth += 1
+        try:
+            out = fn(*args, **kwargs)
+            if overflow_pending():
+                with forced_precision("tf32x3"):
+                    out = fn(*args, **kwargs)
+        finally:
+            _guard_depth -= 1
+        return out
+    return wrapper
 
 
 def use_tc(x):
@@ -31,13 +84,17 @@ def use_tc(x):
 
 
 ACT = {None: 0, "none": 0, "relu": 1, "elu": 2, "tanh": 3, "sigmoid": 4, "softmax": 5}
-_pack_cache = {}
 timing = None    # set to a list to collect (flops, start_event, end_event) per convolution launch (bench.py roofline)
 
 
 def _packed(weight):
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device), precision)
-    hit = _pack_cache.get(id(weight))
+    """Packed (hi|lo split, canonical tensor-core layout) copy of a weight tensor, per operand split.  The cache lives ON the
+    tensor object (``weight._fvfi_pack``), so it dies with it -- folded / concatenated temporaries do not accumulate; it is
+    rebuilt when the tensor's version counter or storage changes (optimizer steps and load_state_dict bump the version; edits
+    through ``.data`` do not -- call ``invalidate(weight)`` after those)."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device))
+    cache = weight.__dict__.setdefault("_fvfi_pack", {})
+    hit = cache.get(precision)
     if hit is not None and hit[0] == key:
         return hit[1]
     Cout, Cin, KH, KW = weight.shape
@@ -51,9 +108,20 @@ def _packed(weight):
         with torch.cuda.device(weight.device):
             _lib.check(L.fvfi_conv2d_pack_weights(wo.data_ptr(), buf.data_ptr(), wo.shape[0], Cin, KH, KW, precision,
                                                   _lib.stream_ptr()))
-        parts.append((o, wo.shape[0], buf, wo))
-    _pack_cache[id(weight)] = (key, parts)
+        parts.append((o, wo.shape[0], buf))
+    cache[precision] = (key, parts)
     return parts
+
+
+def invalidate(obj):
+    """Drop the cached packed / folded / tap-map weights of a tensor or module (after in-place edits through ``.data``)."""
+    for k in ("_fvfi_pack", "_fvfi_fold", "_fvfi_taps", "_first_cache"):
+        obj.__dict__.pop(k, None)
+    if isinstance(obj, torch.nn.Module):
+        for m in obj.children():
+            invalidate(m)
+        for p in obj.parameters(recurse=False):
+            invalidate(p)
 
 
 def to_nhwc(x):
@@ -106,7 +174,7 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
         if timing is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        for (o, n, buf, _) in parts:
+        for (o, n, buf) in parts:
             _lib.check(L.fvfi_conv2d_nhwc_residual(xc.data_ptr(), ldx, buf.data_ptr(), None if b is None else b.data_ptr() + 4 * o,
                                                    None if rc is None else rc.data_ptr() + 4 * o, 0 if rc is None else rc.stride(3),
                                                    out.data_ptr() + 4 * o, ldy, B, H, W, Cin, n, KH, KW, pad_mode, ACT[act],
@@ -133,9 +201,6 @@ def _conv1x1_direct(xc, weight, bias, act):
     return out
 
 
-_tap_cache = {}
-
-
 def upsample2_conv3x3_single(conv, x, act=None):
     """act(conv(Upsample(scale_factor=2, bilinear, align_corners=True)(x))) for a 3x3, zero-padded ``conv`` with ONE output
     channel (KernelEstimation's occlusion head, fusion_adacofnet.py:50-59,103-104) -> contiguous [B,1,2H,2W].
@@ -144,11 +209,11 @@ def upsample2_conv3x3_single(conv, x, act=None):
     assert conv.out_channels == 1 and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.padding_mode == "zeros"
     w = conv.weight
     key = (w.data_ptr(), w._version)
-    hit = _tap_cache.get(id(conv))
+    hit = conv.__dict__.get("_fvfi_taps")
     if hit is None or hit[0] != key:
         C = w.shape[1]
         hit = (key, w.detach()[0].reshape(C, 9).t().reshape(9, C, 1, 1).contiguous())     # [tap = ky*3+kx, c]
-        _tap_cache[id(conv)] = hit
+        conv.__dict__["_fvfi_taps"] = hit
     B, _, H, W = x.shape
     z = conv2d(x, hit[1], None, "zeros", None, nchw_out=True)                             # planar [B,9,H,W]: coalesced tap reads
     out = torch.empty((B, 1, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
@@ -211,19 +276,17 @@ def conv_module(conv, x, act=None, nchw_out=False, pad_out=False, residual=None)
     return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out, pad_out=pad_out, residual=residual)
 
 
-_fold_cache = {}
-
-
 def conv_bn_module(conv, bn, x, act=None):
     """conv -> BatchNorm2d (eval: running statistics) -> act, with the BN affine folded into the weights."""
-    key = (conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.running_mean._version, bn.running_var._version)
-    hit = _fold_cache.get(id(conv))
+    key = (conv.weight.data_ptr(), conv.weight._version, None if conv.bias is None else conv.bias._version, bn.weight._version,
+           bn.bias._version, bn.running_mean._version, bn.running_var._version)
+    hit = conv.__dict__.get("_fvfi_fold")          # lives on the module: replaced (and its packed copy freed) when a version moves
     if hit is None or hit[0] != key:
         scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach()
         w = (conv.weight.detach() * scale.view(-1, 1, 1, 1)).contiguous()
         b = ((conv.bias.detach() if conv.bias is not None else 0) - bn.running_mean) * scale + bn.bias.detach()
         hit = (key, w, b.contiguous())
-        _fold_cache[id(conv)] = hit
+        conv.__dict__["_fvfi_fold"] = hit
     k = conv.kernel_size[0]
     mode = "zeros" if k == 1 else conv.padding_mode
     return conv2d(x, hit[1], hit[2], mode, act)

@@ -62,6 +62,7 @@ class FusionNet(torch.nn.Module):
         all-reduce bucket is built from these."""
         return [p for n, p in self.named_parameters() if not n.startswith("net.")]
 
+    @tc.range_checked
     def forward(self, base, adacof, phase, other, maps, save=False, variant=0):
         x = torch.cat([base, adacof, phase, other, maps], 1)
         skip = []

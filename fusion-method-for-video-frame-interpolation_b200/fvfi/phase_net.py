@@ -36,6 +36,7 @@ class PhaseNetBlock(nn.Module):
         )
         self.to(device)
 
+    @tc.range_checked
     def forward(self, x):
         if tc.use_tc(x) and not self.training:
             # tcgen05 path: conv+BN(folded)+ELU, conv+ELU, 1x1 conv+tanh -- three fused kernels (phase_net.py:190-200)
@@ -148,6 +149,7 @@ class PhaseNet(nn.Module):
             amplitudes.append(amp.reshape(-1, 1, r1, r2))
         return low_level, phases, amplitudes
 
+    @tc.range_checked
     def forward_fused(self, vals, amp_max, m=None):
         """Fused inference form of  separate_vals -> get_concat_layers_inf -> normalize_vals -> forward -> reverse_normalize
         (src/train/utils.py:47-127, phase_net.py:42-177) for two input frames.
@@ -208,6 +210,7 @@ class PhaseNet(nn.Module):
         high_level = torch.zeros((1,), dtype=torch.float32, device=dev).expand(P, 1, H, W)  # zeros (phase_net.py:127-128), no storage
         return DecompValues(high_level=high_level, low_level=low_level, amplitude=amp_out, phase=phase_out)
 
+    @tc.range_checked
     def forward(self, vals, m=None):
         """phase_net.py:107-177."""
         if m is None:

@@ -38,6 +38,8 @@ class FusionPipeline(torch.nn.Module):
         self.max_batch = 8  # frame pairs per sub-batch at full HD (see forward)
         self.timing = None  # set to a list to collect (stage, start_event, end_event) (bench)
         self.fused_phase_glue = True   # PhaseNet.forward_fused (False: the reference's step-by-step value plumbing)
+        self.pair_baseline = True      # baseline passes 2 and 3 (interpolate_twoframe.py:229,233) as one AdaCoFNet call on 2B frames
+        self.max_batch_adacof = 16     # largest AdaCoFNet batch at full HD (the 64 -> 448 fused head tensor is 15 GB at 16)
 
     def _tick(self, name):
         """Stage timer: CUDA events on the current stream, only when ``self.timing`` is a list."""
@@ -53,6 +55,7 @@ class FusionPipeline(torch.nn.Module):
         self.adacof.load_state_dict(state["adacof"])
 
     @torch.no_grad()
+    @tc.range_checked
     def forward(self, rgb1, rgb2):
         B = rgb1.shape[0]
         if B > self.max_batch:
@@ -69,6 +72,7 @@ class FusionPipeline(torch.nn.Module):
         return final
 
     @torch.no_grad()
+    @tc.range_checked
     def fusion_inputs(self, rgb1, rgb2):
         """Everything of the recipe up to FusionNet's five inputs (``Trainer.predict`` runs exactly this part
         under no_grad, src/fusion_net/trainer.py:65-213)."""
@@ -136,8 +140,13 @@ class FusionPipeline(torch.nn.Module):
         ada_uncertainty = ((freq_diff - filters.median_filter(freq_diff, 50)).abs() * 5).clamp(0, 1)
         self._tick('median50')
         # baseline (:228-238)
-        inb1 = self.adacof(rgb1, phase_pred, return_warped=False)[2]
-        inb2 = self.adacof(phase_pred, rgb2, return_warped=False)[2]
+        if self.pair_baseline and 2 * B <= self.max_batch_adacof:
+            # passes 2 and 3 (:229, :233) are independent: ONE AdaCoFNet call on a 2B batch (twice the tiles for the coarse layers)
+            inb = self.adacof(torch.cat((rgb1, phase_pred), 0), torch.cat((phase_pred, rgb2), 0), return_warped=False)[2]
+            inb1, inb2 = inb[:B], inb[B:]
+        else:
+            inb1 = self.adacof(rgb1, phase_pred, return_warped=False)[2]
+            inb2 = self.adacof(phase_pred, rgb2, return_warped=False)[2]
         base = self.adacof(inb1, inb2, return_warped=False)[2]
         self._tick('adacofnet#2-4')
         # fusion (:324-330)
@@ -149,6 +158,30 @@ class FusionPipeline(torch.nn.Module):
                                ada_uncertainty=ada_uncertainty, freq_diff=freq_diff, h_freq_diff=h_freq_diff, base=base)
         return base, ada_pred, phase_pred, other, maps
 
+    @torch.no_grad()
+    @tc.range_checked
+    def phase_interp(self, rgb1, rgb2):
+        """BASELINE.json configs[0] -- the PhaseNet-only interpolation (src/phase_net/interpolate_twoframe.py:52-107; the PhaseNet
+        branch of the fusion recipe, src/fusion_net/interpolate_twoframe.py:168-192): rgb2lab -> Pyramid.filter -> PhaseNet ->
+        Pyramid.inv_filter -> lab2rgb on [B,3,H,W] frames; the three colour planes of every frame are one batch instead of the
+        reference's per-channel loop.  ``self.stages`` (dict) receives lab_pred, phase_pred and the predicted pyramid values."""
+        B, _, H, W = rgb1.shape
+        assert (H, W) == (self.H, self.W) and rgb2.shape == rgb1.shape
+        pyr = self.pyr
+        lab1, lab2 = transform.rgb2lab(rgb1), transform.rgb2lab(rgb2)
+        vals = pyr.filter(torch.cat((lab1.reshape(-1, H, W), lab2.reshape(-1, H, W)), 0), want_high=False)
+        if self.fused_phase_glue:
+            vals_pred = self.phase_net.forward_fused(vals, pyr.last_amp_max)
+        else:
+            vals_pred = self.phase_net(self.phase_net.normalize_vals(utils.get_concat_layers_inf(pyr, utils.separate_vals(vals, 2))))
+        lab_pred = pyr.inv_filter_sparse(vals_pred, use_high=False).reshape(B, 3, H, W)
+        phase_pred = transform.lab2rgb(lab_pred)
+        if self.stages is not None:
+            self.stages.update(lab_pred=lab_pred, phase_pred=phase_pred, low_level=vals_pred.low_level)
+            for l, (p, a) in enumerate(zip(vals_pred.phase, vals_pred.amplitude)):
+                self.stages["phase%d" % l], self.stages["amp%d" % l] = p, a
+        return phase_pred
+
     def interpolate_host(self, rgb1_host, rgb2_host, out_host=None):
         """End-to-end call on HOST (pinned) tensors: H2D copy of the two frames, the pipeline, D2H of the result."""
         d1 = rgb1_host.to(self.device, non_blocking=True)
@@ -156,7 +189,6 @@ class FusionPipeline(torch.nn.Module):
         out = self.forward(d1, d2)
         if out_host is None:
             out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
-        out_host.copy_(out, non_blocking=True)
+        out_host.copy_(out, non_blocking=True)      # forward() has already verified the 3xFP16 range (tc.range_checked)
         torch.cuda.current_stream().synchronize()
-        tc.check_overflow()     # 3xFP16 convolutions report out-of-range activations instead of saturating silently
         return out_host

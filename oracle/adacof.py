@@ -39,6 +39,13 @@ def _f32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
 
 
+def _prep(arrays):
+    """Contiguous operands in ONE dtype: float64 if the first operand is float64 (the fp64 arbiter instantiation
+    oracle_*_f64 of the same C source), else float32 (the reference's arithmetic).  -> (arrays, dtype, symbol suffix)"""
+    dt = np.float64 if np.asarray(arrays[0]).dtype == np.float64 else np.float32
+    return [np.ascontiguousarray(np.asarray(a, dtype=dt)) for a in arrays], dt, ("_f64" if dt == np.float64 else "")
+
+
 def _slabs(H, threads):
     threads = max(1, min(int(threads), H))
     edges = np.linspace(0, H, threads + 1).astype(int)
@@ -63,11 +70,12 @@ def _dims(inp, weight, dilation):
 
 
 def forward(inp, weight, off_i, off_j, dilation=1, threads=1):
-    inp, weight, off_i, off_j = map(_f32, (inp, weight, off_i, off_j))
+    (inp, weight, off_i, off_j), dt, suf = _prep((inp, weight, off_i, off_j))
     B, C, Hin, Win, H, W, F = _dims(inp, weight, dilation)
-    out = np.empty((B, C, H, W), np.float32)
+    out = np.empty((B, C, H, W), dt)
     L = _lib()
-    _run(lambda i0, i1: L.oracle_adacof_forward(_p(inp), _p(weight), _p(off_i), _p(off_j), _p(out),
+    fwd = getattr(L, "oracle_adacof_forward" + suf)
+    _run(lambda i0, i1: fwd(_p(inp), _p(weight), _p(off_i), _p(off_j), _p(out),
                                                 B, C, Hin, Win, H, W, F, dilation, i0, i1), H, threads)
     return out
 
@@ -96,13 +104,14 @@ def grad_input(gout, inp_shape, weight, off_i, off_j, dilation=1):
 
 
 def adacofnet_tail(t1, t2, occ, w1, a1, b1, w2, a2, b2, threads=1):
-    t1, t2, occ, w1, a1, b1, w2, a2, b2 = map(_f32, (t1, t2, occ, w1, a1, b1, w2, a2, b2))
+    (t1, t2, occ, w1, a1, b1, w2, a2, b2), dt, suf = _prep((t1, t2, occ, w1, a1, b1, w2, a2, b2))
     B, C, H, W = t1.shape
     FF = w1.shape[1]
     frame = np.empty_like(t1)
-    mask = np.empty((B, 1, H, W), np.float32)
+    mask = np.empty((B, 1, H, W), dt)
     L = _lib()
-    _run(lambda i0, i1: L.oracle_adacofnet_tail(_p(t1), _p(t2), _p(occ), _p(w1), _p(a1), _p(b1), _p(w2),
+    tail = getattr(L, "oracle_adacofnet_tail" + suf)
+    _run(lambda i0, i1: tail(_p(t1), _p(t2), _p(occ), _p(w1), _p(a1), _p(b1), _p(w2),
                                                 _p(a2), _p(b2), _p(frame), _p(mask), B, C, H, W, FF,
                                                 i0, i1), H, threads)
     return frame, mask

@@ -154,7 +154,7 @@ class PhaseNet(nn.Module):                                                   # s
         amps = [(a.reshape(a.shape[0] // self.pyr.nbands, -1) * mx.view(-1, 1)).reshape(a.shape)
                 for a, mx in zip(amps, self.max_amplitudes)]
         hl = vals.high_level.shape
-        return DecompValues(high_level=torch.zeros((hl[0], 1, hl[2], hl[3])), low_level=low * self.max_low_level.view(-1, 1, 1, 1),
+        return DecompValues(high_level=torch.zeros((hl[0], 1, hl[2], hl[3]), dtype=low.dtype), low_level=low * self.max_low_level.view(-1, 1, 1, 1),
                             amplitude=amps[::-1], phase=phases[::-1])
 
 
@@ -241,7 +241,7 @@ class AdaCoFNet(nn.Module):                                                  # s
             frame0, frame2 = (F.pad(f, (0, 0, 0, 32 - h0 % 32), mode='reflect') for f in (frame0, frame2))
         if w0 % 32:                                                           # :188-192
             frame0, frame2 = (F.pad(f, (0, 32 - w0 % 32, 0, 0), mode='reflect') for f in (frame0, frame2))
-        mean = torch.tensor([0.4631, 0.4352, 0.3990]).view(1, 3, 1, 1)       # src/adacof/utility.py:86-87
+        mean = torch.tensor([0.4631, 0.4352, 0.3990], dtype=frame0.dtype).view(1, 3, 1, 1)       # src/adacof/utility.py:86-87
         maps = [m.contiguous() for m in self.get_kernel(frame0 - mean, frame2 - mean)]
         W1, A1, B1, W2, A2, B2, Occ = [m.numpy() for m in maps]
         p = self.kernel_pad

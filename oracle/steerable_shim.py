@@ -91,7 +91,7 @@ class SCFpyr_PyTorch(object):
     build(im[N,1,H,W]) -> [hi0 [N,H,W],  [band_b [N,h_l,w_l,2] for b<nbands] for l<height-2,  lo [N,h_L,w_L]]
     reconstruct(coeff)  -> [N,H,W]
     dtype: computations run in ``self.cdtype`` (complex64 default like the fp32 reference path;
-    complex128 for the high-precision checker).
+    complex128 for the high-precision checker; outputs keep that precision).
     """
 
     def __init__(self, height=5, nbands=4, scale_factor=2, device=None, precision="fp32"):
@@ -123,13 +123,13 @@ class SCFpyr_PyTorch(object):
         coeff = self._build_levels(lo0dft, log_rad, angle, Xrcos, Yrcos, self.height - 1)
         hi0dft = batch_dft * hi0mask
         hi0 = torch.fft.ifft2(torch.fft.ifftshift(hi0dft, dim=(-2, -1))).real
-        coeff.insert(0, hi0.to(torch.float32).to(self.device))
+        coeff.insert(0, hi0.to(self.rdtype).to(self.device))
         return coeff
 
     def _build_levels(self, lodft, log_rad, angle, Xrcos, Yrcos, height):
         if height <= 1:
             lo0 = torch.fft.ifft2(torch.fft.ifftshift(lodft, dim=(-2, -1))).real
-            return [lo0.to(torch.float32).to(self.device)]
+            return [lo0.to(self.rdtype).to(self.device)]
         Xrcos = Xrcos - np.log2(self.scale_factor)
         himask = self._t(pointOp(log_rad, Yrcos, Xrcos))
         Xcosn, Ycosn = angle_lut(self.nbands, two_sided=False)
@@ -139,7 +139,7 @@ class SCFpyr_PyTorch(object):
             banddft = lodft * anglemask * himask
             banddft = banddft * complex(self.complex_fact_construct)
             band = torch.fft.ifft2(torch.fft.ifftshift(banddft, dim=(-2, -1)))
-            orientations.append(torch.view_as_real(band.to(torch.complex64)).contiguous().to(self.device))
+            orientations.append(torch.view_as_real(band.to(self.cdtype)).contiguous().to(self.device))
         dims = np.array(lodft.shape[1:3])
         nxt = np.array([next_size(int(d), self.scale_factor) for d in dims])
         st = np.array([crop_start(int(d), int(n)) for d, n in zip(dims, nxt)])
@@ -169,7 +169,7 @@ class SCFpyr_PyTorch(object):
         hidft = torch.fft.fftshift(torch.fft.fft2(coeff[0].detach().cpu().to(self.cdtype)), dim=(-2, -1))
         outdft = tempdft * lo0mask + hidft * hi0mask
         rec = torch.fft.ifft2(torch.fft.ifftshift(outdft, dim=(-2, -1))).real
-        return rec.to(torch.float32).to(self.device)
+        return rec.to(self.rdtype).to(self.device)
 
     def _band_complex(self, band):
         if isinstance(band, (int, float)):
