@@ -93,6 +93,16 @@ class AdaCoFWorkload:
     name = "adacof_F5_d1_fwd+bwd_1080p_batch8 (BASELINE.json configs[1])"
     B, C, H, W, F, D = 8, 3, 1088, 1920, 5, 1   # AdaCoFNet pads 1080 -> 1088 (fusion_adacofnet.py:182-185)
     dtype = "f32"
+    metric = METRIC
+
+    @classmethod
+    def static_config(cls):
+        return {"workload": cls.name, "frames_per_step_per_gpu": cls.B, "l2": "inputs larger than L2 (no flush needed)",
+                "sharding": "frame pairs by batch, no collectives"}
+
+    @classmethod
+    def reference_full(cls, threads):
+        return cls.cpu_sample(threads)
 
     def __init__(self, device, seed):
         import torch
@@ -217,39 +227,53 @@ class AdaCoFWorkload:
 
 WORKLOADS = {"adacof": AdaCoFWorkload}
 try:
-    from bench_pipeline import Pipeline4KWorkload, PipelineWorkload
+    from bench_pipeline import PhaseNet256Workload, Pipeline4KWorkload, PipelineWorkload
     WORKLOADS["pipeline"] = PipelineWorkload
     WORKLOADS["pipeline4k"] = Pipeline4KWorkload
+    WORKLOADS["phasenet256"] = PhaseNet256Workload
 except ImportError:
     pass
 DEFAULT_WORKLOAD = os.environ.get("FVFI_BENCH_WORKLOAD", "pipeline" if "pipeline" in WORKLOADS else "adacof")
 
 
 def run_reference(args, emit=print):
-    """Reference arm: the path on the host CPU, all host threads, bounded sample per step."""
+    """Reference arm: the reference's algorithm for this path on the host CPU with all host threads (the oracle port: the
+    reference has no CPU warp and its pyramid package is absent).
+
+    `value` comes from ONE run of the workload at its FULL frame size (no extrapolation; BASELINE.md section 4 plans a single run
+    for the 1080p case -- it takes about two minutes).  The K "steps" the driver asks for are bounded samples (one frame pair at
+    about a quarter of the area) that show how a pixel-ratio extrapolation compares with the full-size run (`extrapolation`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     wl = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
+    t_start = time.perf_counter()
+    value, dt_full, sample_full = wl.reference_full(threads)
     times, rates = [], []
     sample = ""
+    budget = float(os.environ.get("FVFI_REF_SAMPLE_BUDGET_S", "60"))
     for it in range(args.warmup + args.steps):
         fps, dt, sample = wl.cpu_sample(threads, seed=it)
         if it >= args.warmup:
             times.append(dt)
-            rates.append(fps)           # already scaled to the metric's unit (1080p frames/s)
-        if sum(times) > 150:  # keep the whole arm within a few minutes
+            rates.append(fps)           # scaled to the metric's unit by the pixel ratio
+        if time.perf_counter() - t_start - dt_full > budget:
             break
-    dt = sum(times) / len(times)
-    value = len(rates) / sum(1.0 / r for r in rates)   # harmonic mean = total frames / total time
+    extr = None
+    if rates:
+        hm = len(rates) / sum(1.0 / r for r in rates)
+        extr = {"sample": sample, "samples_timed": len(rates), "extrapolated_value": round(hm, 5),
+                "extrapolated_over_measured": round(hm / value, 3)}
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(times), "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
+        "impl": "reference", "metric": wl.metric, "value": round(value, 5), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt_full * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-        "config": {"workload": wl.name, "sample": sample},
+        "config": wl.static_config(),
+        "measurement": "value = 1 / seconds of ONE full-size run; the %d steps are bounded samples, see `extrapolation`" % len(rates),
+        "extrapolation": extr,
         "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": threads,
-                         "kind": getattr(wl, "cpu_kind", "port"), "sample": sample},
+                         "kind": getattr(wl, "cpu_kind", "port"), "sample": sample_full, "seconds": round(dt_full, 2)},
         "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(json.dumps(line))
@@ -275,6 +299,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-refbar", action="store_true", help="skip timing the reference's own CUDA kernels")
+    ap.add_argument("--no-records", action="store_true", help="N > 1: skip the configs[4] training / configs[3] 4K records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -327,12 +352,10 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         line = {
-            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": wl.metric, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-            "config": dict({"workload": wl.name, "frames_per_step_per_gpu": wl.frames_per_step,
-                            "l2": "inputs larger than L2 (no flush needed)", "sharding": "frame pairs by batch, no collectives"},
-                           **getattr(wl, "config_extra", {})),
+            "config": wl.static_config(), "config_detail": getattr(wl, "config_extra", {}),
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": wl.roofline(peak, peak_src),
         }
@@ -349,12 +372,31 @@ def main():
             line["e2e"] = {"value": round(wl.frames_per_step * world / float(t.item()), 3), "unit": UNIT,
                            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                            "ms_per_step": round(float(t.item()) * 1e3, 3), "matches_device_path": ok}
+    if world > 1 and hasattr(wl, "parity") and not args.no_records:
+        # BASELINE.json configs[4] (training step + NVLink all-reduce) and configs[3] (4K) on these N GPUs, outside the headline timing
+        from bench_pipeline import multi_gpu_records
+        del wl.pipe
+        torch.cuda.empty_cache()
+        rec = multi_gpu_records(device, rank, world, local_rank)
+        if rank == 0:
+            line.update(rec)
     if rank == 0 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        fps, dt, sample = wl.cpu_sample(threads)
-        line["cpu_baseline"] = {"value": round(fps, 5), "unit": UNIT, "cores": threads,
-                                "kind": getattr(wl, "cpu_kind", "port"), "sample": sample,
-                                "seconds": round(dt, 2)}
+        if world == 1:
+            # the CPU leg runs at N = 1 only: at N > 1 the other ranks would spin in the NCCL barrier on the same host cores
+            threads = os.cpu_count() or 1
+            kept = {} if hasattr(wl, "parity") else None
+            try:
+                fps, dt, sample = wl.cpu_sample(threads, keep=kept) if kept is not None else wl.cpu_sample(threads)
+            except TypeError:
+                fps, dt, sample = wl.cpu_sample(threads)
+            line["cpu_baseline"] = {"value": round(fps, 5), "unit": UNIT, "cores": threads,
+                                    "kind": getattr(wl, "cpu_kind", "port"), "sample": sample,
+                                    "seconds": round(dt, 2)}
+            if kept:
+                line["parity"] = wl.parity(kept)       # the GPU path against the oracle output just computed
+        else:
+            line["cpu_baseline"] = None
+            line["cpu_baseline_note"] = "timed at N = 1 only (rank 0 would share the host cores with %d ranks polling NCCL)" % (world - 1)
     if rank == 0:
         emit(json.dumps(line))
     if world > 1:

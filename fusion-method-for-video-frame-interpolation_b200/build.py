@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 OUT = os.path.join(HERE, "fvfi", "libfvfi.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--use_fast_math=false" if False else "-DFVFI_BUILD", "-Xcompiler", "-fPIC,-O2",
+    "-DFVFI_BUILD", "-Xcompiler", "-fPIC,-O2",
     "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "csrc"),
 ]
 
@@ -51,8 +51,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call(["nvcc", "-shared", "-o", OUT] + objs + ["-lcuda"] if False else
-                          ["nvcc", "-shared", "-o", OUT] + objs)
+    subprocess.check_call(["nvcc", "-shared", "-o", OUT] + objs)
     return OUT
 
 

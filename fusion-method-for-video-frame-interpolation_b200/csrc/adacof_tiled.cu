@@ -304,7 +304,7 @@ adacof_bwd_tiled(const float* __restrict__ gout, const float* __restrict__ input
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
-    FVFI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    FVFI_SMEM_OPT_IN(kernel, bytes);
     return FVFI_OK;
 }
 

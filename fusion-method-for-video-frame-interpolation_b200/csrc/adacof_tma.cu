@@ -302,14 +302,24 @@ static EncodeTiledFn encode_fn() {
 
 // [B*25, H, W] fp32 planes -> 3-D map with 32 x 8 x 5 boxes
 static bool make_map(CUtensorMap* m, const float* base, int B, int H, int W) {
+    // the caching allocator hands the same buffers back call after call: remember the last few encodings per host thread
+    struct Slot { const float* base; int B, H, W; CUtensorMap map; };
+    static thread_local Slot cache[16];
+    static thread_local unsigned next = 0;
+    for (const Slot& c : cache)
+        if (c.base == base && c.B == B && c.H == H && c.W == W) { *m = c.map; return true; }
     EncodeTiledFn enc = encode_fn();
     if (!enc) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * XF * XF};
     const cuuint64_t strides[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)H * W * sizeof(float)};
     const cuuint32_t box[3] = {XW, XH, XF};
     const cuuint32_t es[3] = {1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    Slot& c = cache[next++ % 16];
+    c.base = base; c.B = B; c.H = H; c.W = W; c.map = *m;
+    return true;
 }
 
 static bool aligned16(const void* p) { return (((size_t)p) & 15) == 0; }
@@ -345,7 +355,7 @@ int adacof_tma_launch(const float* in1, const float* in2, const float* w1, const
     {                                                                                                                     \
         const size_t smem = (size_t)ST * XSTAGE_FLOATS * sizeof(float) + 2 * XREGION_BYTES + 128;                        \
         const unsigned grid = (unsigned)std::min<long long>(nt, (long long)MB * nsm);                                    \
-        FVFI_CUDA(cudaFuncSetAttribute(adacof_fwd_tma<NF, ST, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        FVFI_SMEM_OPT_IN((adacof_fwd_tma<NF, ST, MB>), smem);                                                             \
         adacof_fwd_tma<NF, ST, MB><<<grid, XTHREADS, smem, s>>>(mw0, ma0, mb0, mw1, ma1, mb1, A);                       \
     }
     if (nframes == 0) FVFI_TMA_LAUNCH(0, 3, 2) else

@@ -41,7 +41,17 @@ void note_launch();  // counts kernel launches issued by this library (fvfi_laun
         }                                                                                 \
     } while (0)
 
-int sm_count();
+constexpr int FVFI_MAX_DEVICES = 64;
+int current_device();   // -1 on error
+int sm_count();         // SMs of the current device (cached)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) -- raised again only when a launch asks for more --
+// instead of a driver call on every launch.  Returns FVFI_OK / FVFI_ECUDA (error text set).
+int smem_opt_in(const void* kernel, size_t bytes);
+#define FVFI_SMEM_OPT_IN(kernel, bytes)                                             \
+    do {                                                                            \
+        if (int _rc = ::fvfi::smem_opt_in((const void*)(kernel), (size_t)(bytes))) return _rc; \
+    } while (0)
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

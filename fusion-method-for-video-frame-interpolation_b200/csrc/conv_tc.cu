@@ -29,7 +29,9 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 #include "common.cuh"
@@ -868,17 +870,21 @@ static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
     return FVFI_EINVAL;
 }
 
-static int* overflow_flag() {      // one device word per device, zero-initialised
-    static int* flags[64] = {nullptr};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!flags[dev]) {
-        int* p = nullptr;
+static int* overflow_flag() {      // one device word per device, zero-initialised; creation is serialised across host threads
+    static std::mutex mu;
+    static std::atomic<int*> flags[FVFI_MAX_DEVICES];
+    const int dev = current_device();
+    if (dev < 0 || dev >= FVFI_MAX_DEVICES) return nullptr;
+    int* p = flags[dev].load(std::memory_order_acquire);
+    if (p) return p;
+    std::lock_guard<std::mutex> lock(mu);
+    p = flags[dev].load(std::memory_order_relaxed);
+    if (!p) {
         if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
         cudaMemset(p, 0, sizeof(int));
-        flags[dev] = p;
+        flags[dev].store(p, std::memory_order_release);
     }
-    return flags[dev];
+    return p;
 }
 
 template <int PREC>
@@ -969,7 +975,7 @@ extern "C" int fvfi_conv2d_nhwc_residual(const float* x, int x_pixel_stride, con
     const int nsm = sm_count();
     dim3 grid((unsigned)std::min(a.ntiles, nsm > 0 ? nsm : 148), 1, 1);
     void (*kern)(const ConvArgs) = (precision == PREC_F16X3) ? pick_kernel<PREC_F16X3>(activation) : pick_kernel<PREC_TF32X3>(activation);
-    FVFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FVFI_SMEM_OPT_IN(kern, smem);
     kern<<<grid, CV_THREADS, smem, (cudaStream_t)stream>>>(a);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;

@@ -292,7 +292,7 @@ extern "C" int fvfi_median_filter(const float* in, float* out, int N, int H, int
         const int nwords = (n + 31) / 32, wpl = (nwords + 31) / 32;
         const size_t smem = (size_t)npad * 8 + (size_t)((n + 1) & ~1) * 2 + (size_t)MR_TH * wpl * 32 * 4;
         if (smem > 48 * 1024)
-            FVFI_CUDA(cudaFuncSetAttribute(median_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FVFI_SMEM_OPT_IN(median_rank_kernel, smem);
         dim3 grid(ceil_div(W, MR_TW), ceil_div(H, MR_TH), N);
         median_rank_kernel<<<grid, MR_THREADS, smem, (cudaStream_t)stream>>>(in, out, H, W, size, rank, npad, MR_TW);
         FVFI_LAUNCH_CHECK();
@@ -301,7 +301,7 @@ extern "C" int fvfi_median_filter(const float* in, float* out, int N, int H, int
     const int S = MED_T + size - 1;
     const size_t smem = (size_t)S * S * sizeof(unsigned);
     if (smem > 48 * 1024)
-        FVFI_CUDA(cudaFuncSetAttribute(median_bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FVFI_SMEM_OPT_IN(median_bisect_kernel, smem);
     dim3 grid(ceil_div(W, MED_T), ceil_div(H, MED_T), N);
     median_bisect_kernel<<<grid, MED_T * MED_T, smem, (cudaStream_t)stream>>>(in, out, H, W, size, rank);
     FVFI_LAUNCH_CHECK();

@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_inv(const Le
 template <typename K>
 static int ensure_smem(K kernel, size_t bytes) {
     if (bytes > 227 * 1024) { set_error("pyramid: tile needs %zu B of shared memory (> 227 KB)", bytes); return FVFI_EINVAL; }
-    FVFI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 48 * 1024)));
+    FVFI_SMEM_OPT_IN(kernel, std::max<size_t>(bytes, 48 * 1024));
     return FVFI_OK;
 }
 

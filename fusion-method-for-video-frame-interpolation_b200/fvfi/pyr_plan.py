@@ -43,7 +43,7 @@ class PyrPlan:
             h, w = ctypes.c_int(), ctypes.c_int()
             _lib.check(L.fvfi_pyr_level_shape(handle, l, ctypes.byref(h), ctypes.byref(w)))
             self.shapes.append((h.value, w.value))
-        self._ws = None
+        self._ws = {}          # one scratch buffer per CUDA stream: calls on different streams / threads never share scratch
 
     @classmethod
     def get(cls, H, W, height, nbands, scale_factor, device):
@@ -58,11 +58,16 @@ class PyrPlan:
         return p
 
     def workspace(self, N):
+        """Scratch for a call with N planes on the CURRENT stream (grown on demand, reused by later calls on that stream; calls
+        on one stream are ordered, so forward / backward / filter / inv_filter can share it)."""
         need = _lib.lib().fvfi_pyr_workspace_bytes(self.handle, int(N))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._ws
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            self._ws.pop(key, None)
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
 
     def __del__(self):
         try:

@@ -3,7 +3,7 @@
 data-parallel over ranks with one flat-bucket gradient all-reduce (fvfi.dist)."""
 import torch
 
-from .dist import FlatGradBucket
+from .dist import FlatGradBucket, all_reduce_mean_buffers, broadcast_module
 
 
 class FusionTrainer:
@@ -11,6 +11,9 @@ class FusionTrainer:
         self.pipe = pipeline
         self.net = pipeline.fusion_net
         self.net.train()
+        # replicas start from rank 0's weights: the trained FusionNet and the frozen networks that produce its inputs
+        for m in (self.net, pipeline.phase_net, pipeline.adacof):
+            broadcast_module(m, 0, group)
         for n, p in self.net.named_parameters():
             p.requires_grad_(not n.startswith("net."))          # dead weights (fusion_net.py:11-20)
         self.bucket = FlatGradBucket(self.net.live_parameters())
@@ -41,6 +44,7 @@ class PhaseNetTrainer:
         from .dist import FlatGradBucket
         self.pyr, self.net, self.group = pyr, phase_net, group
         self.net.train()
+        broadcast_module(self.net, 0, group)                                             # parameters + BatchNorm statistics
         params = [p for p in self.net.parameters() if p.requires_grad]
         self.bucket = FlatGradBucket(params)
         self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay)       # trainer.py:40-42
@@ -65,4 +69,5 @@ class PhaseNetTrainer:
         loss.backward()
         self.bucket.all_reduce_mean(self.group)
         self.optimizer.step()
+        all_reduce_mean_buffers(self.net, self.group)          # BatchNorm running statistics stay identical across replicas
         return loss.detach()

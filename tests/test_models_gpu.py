@@ -100,41 +100,118 @@ def test_models_vs_oracle_nets(conv_backend):
         assert float((a.cpu() - b).abs().max()) <= 1e-4, name
 
 
+def _state_for(z, name, seed):
+    """Seeded random-init weights, or (fixtures named *_ckpt_*) the reference's SHIPPED phase_net.pt / fusion_net.pt, which
+    __graft_entry__.build() copies next to the reference cubins (oracle/_ref/, travels to the GPU box)."""
+    state = fp.seeded_state(seed)
+    if "_ckpt_" in name:
+        ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+        pn, fn = os.path.join(ref, "phase_net.pt"), os.path.join(ref, "fusion_net.pt")
+        if not (os.path.exists(pn) and os.path.exists(fn)):
+            pytest.skip("shipped checkpoints not staged in oracle/_ref (build container without /root/reference)")
+        state["phase_net"] = torch.load(pn, map_location="cpu")
+        state["fusion_net"] = torch.load(fn, map_location="cpu")
+    chk = [float(sum(v.double().sum() for v in state[n].values())) for n in ("phase_net", "fusion_net", "adacof")]
+    assert np.allclose(chk, z["checksum"], rtol=1e-9), "weights differ from the fixture's"
+    return state
+
+
 def test_pipeline_vs_reference_golden(golden_dir, conv_backend):
-    """Full fusion recipe on the GPU vs the fixtures produced by the reference modules on CPU.
-    Tolerance: 1e-4 max abs on [0,1] images (the north-star bound) -- measured error is reported."""
+    """Full fusion recipe on the GPU vs the fixtures produced by the reference's own modules on CPU: 64x64 / 64x96 (round 1),
+    256x256 (training crop size: pyramid height 12, PhaseNet.layers[7] shared by four levels), 184x328 (Bluestein / Rader FFT
+    lengths, AdaCoFNet reflect padding in both axes) and 256x256 with the SHIPPED phase_net.pt / fusion_net.pt.
+    Bound: 1e-4 max abs per stage against the reference (north star), or -- where the fixture carries the fp64 arbiter -- no
+    further from the fp64 result than twice the reference's own fp32 run (tests/_parity.py)."""
+    from _parity import fmt, psnr, stage_report
     from fvfi.pipeline import FusionPipeline
-    files = sorted(glob.glob(os.path.join(golden_dir, "pipeline_ref_*.npz")))
-    assert files
+    files = sorted(glob.glob(os.path.join(golden_dir, "pipeline_*.npz")))
+    assert len(files) >= 5
     for f in files:
         z = np.load(f)
         B, H, W, seed = [int(v) for v in z["meta"]]
         pipe = FusionPipeline(H, W, "cuda")
-        pipe.load_state(fp.seeded_state(seed))
+        pipe.load_state(_state_for(z, os.path.basename(f), seed))
         pipe.stages = {}
         rgb1, rgb2 = fp.seeded_frames(B, H, W, seed)
-        out = pipe(rgb1.cuda(), rgb2.cuda()).cpu().numpy()
-        errs = {k: float(np.abs(pipe.stages[k].cpu().numpy() - z[k]).max()) for k in z.files if k in pipe.stages}
-        print(conv_backend, os.path.basename(f), {k: "%.1e" % v for k, v in errs.items()})
-        assert errs["lab1"] <= 3e-6 and errs["ada_pred"] <= 1e-4 and errs["flow_var_map"] <= 1e-4
-        assert errs["lab_pred"] <= 1e-4 and errs["phase_pred"] <= 2e-4   # lab2rgb amplifies Lab error ~2x near black
-        assert errs["phase_uncertainty"] <= 1e-3 and errs["ada_uncertainty"] <= 5e-3   # x100 / x150 gains before the clamp
-        assert errs["base"] <= 2e-4
-        err = float(np.abs(out - z["final"]).max())
-        mse = float(((out - z["final"]) ** 2).mean())
-        psnr = 10 * np.log10(1.0 / max(mse, 1e-20))
-        print("final max abs err %.2e, PSNR(GPU vs reference) %.1f dB" % (err, psnr))
-        # End to end the recipe multiplies pyramid residuals by 100 / 150 before clamping them into the
-        # uncertainty maps (interpolate_twoframe.py:211,220,224), so fp32 rounding differences between
-        # cuDNN and the CPU reference (~5e-5 per network, see above) reach the output amplified; the
-        # 1e-4 bound holds per operator on identical inputs (all other tests), end to end we assert
-        # 1e-3 and a PSNR against the reference output of >= 70 dB (a 0.01 dB PSNR delta at 30 dB
-        # corresponds to an error energy ratio of 2e-3, i.e. ~57 dB).
-        assert err <= 1e-3, err
-        assert psnr >= 70
-        # host-buffer entry point == device path
-        host = pipe.interpolate_host(rgb1.pin_memory(), rgb2.pin_memory())
-        assert np.array_equal(host.numpy(), out)
+        out = pipe(rgb1.cuda(), rgb2.cuda())
+        if "final__d64" in z.files:
+            rep = stage_report(z, pipe.stages)
+            print(conv_backend, os.path.basename(f), fmt(rep))
+            bad = [k for k, v in rep.items() if not v["ok"]]
+            assert not bad, (bad, fmt(rep))
+            st = int(z["final__stride"]) if "final__stride" in z.files else 1
+            o = out.cpu().numpy()[..., ::st, ::st]
+            print("final: max abs err %.2e, PSNR(GPU vs reference) %.1f dB" % (float(np.abs(o - z["final"]).max()), psnr(o, z["final"])))
+            assert psnr(o, z["final"]) >= 70
+        else:
+            out = out.cpu().numpy()
+            errs = {k: float(np.abs(pipe.stages[k].cpu().numpy() - z[k]).max()) for k in z.files if k in pipe.stages}
+            print(conv_backend, os.path.basename(f), {k: "%.1e" % v for k, v in errs.items()})
+            assert errs["lab1"] <= 3e-6 and errs["ada_pred"] <= 1e-4 and errs["flow_var_map"] <= 1e-4
+            assert errs["lab_pred"] <= 1e-4 and errs["phase_pred"] <= 2e-4   # lab2rgb amplifies Lab error ~2x near black
+            assert errs["phase_uncertainty"] <= 1e-3 and errs["ada_uncertainty"] <= 5e-3   # x100 / x150 gains before the clamp
+            assert errs["base"] <= 2e-4
+            err = float(np.abs(out - z["final"]).max())
+            print("final max abs err %.2e, PSNR(GPU vs reference) %.1f dB" % (err, psnr(out, z["final"])))
+            # round-1 fixtures carry no arbiter: the recipe multiplies pyramid residuals by 100 / 150 before clamping them into the
+            # uncertainty maps (interpolate_twoframe.py:211,220,224); the round-2 fixtures above state the bound properly.
+            assert err <= 1e-3, err
+            assert psnr(out, z["final"]) >= 70
+            # host-buffer entry point == device path
+            host = pipe.interpolate_host(rgb1.pin_memory(), rgb2.pin_memory())
+            assert np.array_equal(host.numpy(), out)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_phasenet_256_vs_reference_golden(golden_dir, fused):
+    """BASELINE.json configs[0]: PhaseNet decompose -> predict -> reconstruct on one 256x256 frame pair, random-init weights, against
+    the reference's own Pyramid wrapper + PhaseNet on CPU (tests/golden/phasenet_ref_256x256_s5.npz): every predicted level
+    (as complex coefficients), the low pass, the reconstructed Lab planes and the RGB frame.  Pyramid(12, 4, sqrt 2):
+    levels 256,181,128,91,64,45,32,23,16,11 + low 8 -> layers[7] (phase_net.py:148) serves the four finest levels."""
+    from _parity import fmt, stage_report
+    from fvfi.pipeline import FusionPipeline
+    z = np.load(os.path.join(golden_dir, "phasenet_ref_256x256_s5.npz"))
+    B, H, W, seed = [int(v) for v in z["meta"]]
+    pipe = FusionPipeline(H, W, "cuda")
+    assert pipe.pyr.height == 12
+    pipe.load_state(_state_for(z, "phasenet_ref", seed))
+    pipe.fused_phase_glue = fused
+    pipe.stages = {}
+    rgb1, rgb2 = fp.seeded_frames(B, H, W, seed)
+    pipe.phase_interp(rgb1.cuda(), rgb2.cuda())
+    rep = stage_report(z, pipe.stages)
+    print("fused" if fused else "stepwise", fmt(rep))
+    assert len(rep) == 13                      # 10 levels + low_level + lab_pred + phase_pred
+    bad = [k for k, v in rep.items() if not v["ok"]]
+    assert not bad, (bad, fmt(rep))
+    assert rep["lab_pred"]["err_ref"] <= 1e-4 and rep["phase_pred"]["err_ref"] <= 1e-4      # the north-star bound itself
+
+
+def test_conv_range_guard_reruns_in_tf32x3():
+    """|activation| > 4094 leaves the 3xFP16 operand range: the decorated module forwards notice the device flag and run again with
+    the 3xTF32 split instead of returning inf/NaN (device-resident path)."""
+    from fvfi import conv as tc
+    from fvfi.fusion_net import FusionNet
+    from oracle import nets
+    state = fp.seeded_state(13)
+    g = torch.Generator().manual_seed(13)
+    ins = [torch.rand((1, c, 32, 48), generator=g) for c in (3, 3, 3, 6, 3)]
+    ins[3] = ins[3] * 3.0e4                                         # far beyond 4094
+    ofn = nets.FusionNet().eval()
+    ofn.load_state_dict(state["fusion_net"])
+    gfn = FusionNet().cuda().eval()
+    gfn.load_state_dict(state["fusion_net"])
+    with torch.no_grad():
+        ref = ofn(*ins)
+        got = gfn(*[t.cuda() for t in ins]).cpu()
+        assert bool(torch.isfinite(got).all())
+        assert float((got - ref).abs().max()) <= 1e-4
+        assert not tc.overflow_pending()                            # the guard consumed the flag
+        x = (torch.rand((1, 16, 32, 48), generator=g) * 3.0e4).cuda()
+        w = torch.rand((16, 16, 3, 3), generator=g).cuda()
+        tc.conv2d(x, w)                                             # raw op outside a guarded forward: flag stays for the caller
+        with pytest.raises(FloatingPointError):
+            tc.check_overflow()
 
 
 def test_training_step_gradients_match_oracle():

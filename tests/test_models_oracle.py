@@ -17,9 +17,7 @@ def _fixtures(golden_dir):
 
 
 def test_pipeline_oracle_matches_reference_golden(golden_dir):
-    files = _fixtures(golden_dir)
-    assert files
-    f = files[0]  # 64x64, B=1 (a few seconds on CPU)
+    f = os.path.join(golden_dir, "pipeline_ref_B1_64x64_s0.npz")  # 64x64, B=1 (a few seconds on CPU)
     z = np.load(f)
     B, H, W, seed = [int(v) for v in z["meta"]]
     state = fp.seeded_state(seed)
@@ -46,6 +44,36 @@ def test_oracle_nets_equal_reference_modules():
     fp.interp(fp.oracle_backend(state, hw=(H, W), threads=4), rgb1, rgb2, b)
     for k in a:
         assert float((a[k] - b[k]).abs().max()) <= 1e-6, k
+
+
+def test_phasenet256_oracle_matches_reference_golden_and_fp64_budget(golden_dir):
+    """configs[0] fixture: the oracle restatement (fp32) reproduces the reference modules' outputs, and its fp64 mode reproduces
+    the stored arbiter (so the budgets the GPU tests use are what the fixture says)."""
+    z = np.load(os.path.join(golden_dir, "phasenet_ref_256x256_s5.npz"))
+    B, H, W, seed = [int(v) for v in z["meta"]]
+    state = fp.seeded_state(seed)
+    rgb1, rgb2 = fp.seeded_frames(B, H, W, seed)
+    st32, st64 = {}, {}
+    fp.interp_phasenet(fp.oracle_backend(state, hw=(H, W), threads=4), rgb1, rgb2, st32)
+    fp.interp_phasenet(fp.oracle_backend(state, hw=(H, W), threads=4, precision="fp64"), rgb1, rgb2, st64)
+    for k in ("lab_pred", "phase_pred", "low_level", "amp3", "amp9"):
+        sl = int(z[k + "__stride"]) if k + "__stride" in z.files else 1
+        a32 = st32[k].numpy()[..., ::sl, ::sl]
+        a64 = st64[k].numpy()[..., ::sl, ::sl]
+        assert np.abs(a32 - z[k]).max() <= 2e-6, k
+        f64 = z[k].astype(np.float64) - z[k + "__d64"].astype(np.float64) / 1e4
+        assert np.abs(a64 - f64).max() <= 2e-3 * float(z[k + "__budget"]) + 1e-7, k      # float16 storage of the difference
+        assert float(np.abs(st32[k].numpy() - st64[k].numpy()).max()) == pytest.approx(float(z[k + "__budget"]), rel=1e-3, abs=1e-9)
+
+
+def test_synth_generators_equal_oracle_generators():
+    """fvfi.synth (what bench.py / tools use for seeded weights and frames) == the oracle's generators (what the fixtures use)."""
+    from fvfi import synth
+    a, b = fp.seeded_state(3), synth.seeded_state(3)
+    for k in a:
+        assert list(a[k].keys()) == list(b[k].keys())
+        assert all(torch.equal(a[k][n], b[k][n]) for n in a[k])
+    assert all(torch.equal(p, q) for p, q in zip(fp.seeded_frames(2, 64, 96, 1), synth.seeded_frames(2, 64, 96, 1)))
 
 
 def test_lab_round_trip_and_known_values():

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "fusion-method-for-video-frame-interpolation_b200")]
 from fvfi.pipeline import FusionPipeline
 from fvfi.trainer import FusionTrainer
-from oracle import fusion_pipeline as fp
+from fvfi import synth as fp   # seeded weights / frames (input generation only)
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "fusion-method-for-video-frame-interpolation_b200")]
 from fvfi.pipeline import FusionPipeline
 from fvfi import conv as tc
-from oracle import fusion_pipeline as fp
+from fvfi import synth as fp   # seeded weights / frames (input generation only)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 pipe = FusionPipeline(1080, 1920, "cuda", phase_plane_chunk=6)
 pipe.load_state(fp.seeded_state(0))

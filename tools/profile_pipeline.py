@@ -4,7 +4,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "fusion-method-for-video-frame-interpolation_b200")]
 from fvfi.pipeline import FusionPipeline
-from oracle import fusion_pipeline as fp
+from fvfi import synth as fp   # seeded weights / frames (input generation only)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 torch.backends.cudnn.allow_tf32 = False
 pipe = FusionPipeline(1080, 1920, "cuda", phase_plane_chunk=12)
