@@ -117,9 +117,8 @@ adacof_fwd_direct_anyc(const float* __restrict__ input, const float* __restrict_
 //   gW     = S00 (1-a)(1-b) + S10 a(1-b) + S01 (1-a) b + S11 a b                  (:118-123)
 //   gAlpha = w * ( (S10 - S00)(1-b) + (S11 - S01) b )                            (:183-188)
 //   gBeta  = w * ( (S01 - S00)(1-a) + (S11 - S10) a )                            (:248-253)
-// GIN: optional true adjoint scatter (extension; the reference returns zeros).
+// The optional true gradInput (extension; the reference returns zeros) is a separate scatter kernel below.
 // ---------------------------------------------------------------------------------------------
-template <bool GIN>
 __global__ void __launch_bounds__(256)
 adacof_bwd_direct(const float* __restrict__ gout, const float* __restrict__ input,
                   const float* __restrict__ weight, const float* __restrict__ off_i,
@@ -162,18 +161,85 @@ adacof_bwd_direct(const float* __restrict__ gout, const float* __restrict__ inpu
             st_stream(gw + q, s00 * (na * nb) + s10 * (a * nb) + s01 * (na * b) + s11 * (a * b));
             st_stream(goi + q, w * ((s10 - s00) * nb + (s11 - s01) * b));
             st_stream(goj + q, w * ((s01 - s00) * na + (s11 - s10) * a));
-            if (GIN) {
-                float* G = gin + (size_t)n * C * plane_in;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// True gradInput (gin_mode = FVFI_GIN_TRUE; NOT in the reference, which returns zeros -- adacof.py:382,445): the adjoint of the
+// forward gather, a scatter-add of  gout[c] * w * bilinear weight  into the four taps of every (pixel, k, l).
+// WARP-AGGREGATED atomics: a warp owns 32 horizontally adjacent pixels of one tap; neighbouring pixels of a smooth flow field hit
+// the same or adjacent frame samples, so for each of the four corners the lanes are grouped by target address
+// (__match_any_sync), every group sums its three channel values with shuffles and only the group leader issues the
+// red.global.add -- one atomic per DISTINCT address per warp instead of one per lane.  Lanes outside the image contribute to
+// no group (address -1 is matched but skipped).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_agg_add3(float* __restrict__ G, size_t plane_in, int o, float v0, float v1, float v2,
+                                              unsigned lane) {
+    const unsigned peers = __match_any_sync(0xffffffffu, o);
+    if (peers == (1u << lane)) {                      // address unique in the warp: plain reductions
+        if (o >= 0) {
+            atomicAdd(G + o, v0);
+            atomicAdd(G + plane_in + o, v1);
+            atomicAdd(G + 2 * plane_in + o, v2);
+        }
+        return;
+    }
+    // every lane of the group walks the same peer list (same mask -> same trip count), so the shuffles converge per group
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (unsigned m = peers; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        s0 += __shfl_sync(peers, v0, src);
+        s1 += __shfl_sync(peers, v1, src);
+        s2 += __shfl_sync(peers, v2, src);
+    }
+    if (o >= 0 && lane == (unsigned)(__ffs(peers) - 1)) {
+        atomicAdd(G + o, s0);
+        atomicAdd(G + plane_in + o, s1);
+        atomicAdd(G + 2 * plane_in + o, s2);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adacof_grad_input_scatter(const float* __restrict__ gout, const float* __restrict__ weight, const float* __restrict__ off_i,
+                          const float* __restrict__ off_j, float* __restrict__ gin, int Hin, int Win, int H, int W, int F,
+                          int dil) {
+    constexpr int C = 3;
+    const int j = blockIdx.x * 32 + threadIdx.x;         // a warp = 32 adjacent pixels of one row
+    const int i = blockIdx.y * 8 + threadIdx.y;
+    const int n = blockIdx.z;
+    const bool live = j < W && i < H;                    // whole warps stay in the loop: the match/shuffle masks are full
+    if (i >= H) return;                                  // uniform per warp (threadIdx.y is the warp index)
+    const unsigned lane = threadIdx.x;
+    const size_t plane = (size_t)H * W, plane_in = (size_t)Hin * Win;
+    float* G = gin + (size_t)n * C * plane_in;
+    float g[C] = {0.f, 0.f, 0.f};
+    if (live) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const float dw = g[c] * w;
-                    float* Gc = G + (size_t)c * plane_in;
-                    atomicAdd(Gc + o00, dw * (na * nb));
-                    atomicAdd(Gc + o10, dw * (a * nb));
-                    atomicAdd(Gc + o01, dw * (na * b));
-                    atomicAdd(Gc + o11, dw * (a * b));
-                }
+        for (int c = 0; c < C; ++c) g[c] = ld_stream(gout + ((size_t)n * C + c) * plane + (size_t)i * W + j);
+    }
+    size_t q = (size_t)n * F * F * plane + (size_t)i * W + (live ? j : 0);
+    for (int k = 0; k < F; ++k) {
+        for (int l = 0; l < F; ++l, q += plane) {
+            int o00 = -1, o10 = -1, o01 = -1, o11 = -1;
+            float w00 = 0.f, w10 = 0.f, w01 = 0.f, w11 = 0.f, w = 0.f;
+            if (live) {
+                w = ld_stream(weight + q);
+                const float al = ld_stream(off_i + q), be = ld_stream(off_j + q);
+                const int A = (int)al, B = (int)be;                          // truncation, adacof.py:27-28
+                const float a = al - (float)A, b = be - (float)B;
+                const int r = i + k * dil + A, cc = j + l * dil + B;
+                const int r0 = min(max(r, 0), Hin - 1), r1 = min(max(r + 1, 0), Hin - 1);
+                const int c0 = min(max(cc, 0), Win - 1), c1 = min(max(cc + 1, 0), Win - 1);
+                o00 = r0 * Win + c0; o10 = r1 * Win + c0; o01 = r0 * Win + c1; o11 = r1 * Win + c1;
+                const float na = 1.f - a, nb = 1.f - b;
+                w00 = na * nb; w10 = a * nb; w01 = na * b; w11 = a * b;
             }
+            const float d0 = g[0] * w, d1 = g[1] * w, d2 = g[2] * w;
+            warp_agg_add3(G, plane_in, o00, d0 * w00, d1 * w00, d2 * w00, lane);
+            warp_agg_add3(G, plane_in, o10, d0 * w10, d1 * w10, d2 * w10, lane);
+            warp_agg_add3(G, plane_in, o01, d0 * w01, d1 * w01, d2 * w01, lane);
+            warp_agg_add3(G, plane_in, o11, d0 * w11, d1 * w11, d2 * w11, lane);
         }
     }
 }
@@ -384,7 +450,13 @@ extern "C" int fvfi_adacof_backward(const float* gout, const float* input, const
     cudaStream_t s = (cudaStream_t)stream;
     if (gin_mode != FVFI_GIN_NONE)
         FVFI_CUDA(cudaMemsetAsync(gin, 0, (size_t)B * C * Hin * Win * sizeof(float), s));
-    if (C == 3 && gin_mode != FVFI_GIN_TRUE && (algo == 0 || algo == 3)) {
+    if (gin_mode == FVFI_GIN_TRUE) {     // true adjoint (extension): warp-aggregated scatter, independent of the gradient path below
+        FVFI_CHECK_ARG((long long)Hin * Win <= 0x7fffffffLL, "adacof_backward: frame too large for the gradInput scatter");
+        dim3 sblock(32, 8), sgrid(ceil_div(W, 32), ceil_div(H, 8), B);
+        adacof_grad_input_scatter<<<sgrid, sblock, 0, s>>>(gout, weight, off_i, off_j, gin, Hin, Win, H, W, F, dilation);
+        FVFI_LAUNCH_CHECK();
+    }
+    if (C == 3 && (algo == 0 || algo == 3)) {
         int handled = 0;
         if (int rc = adacof_tma_launch(input, nullptr, weight, off_i, off_j, nullptr, nullptr, nullptr, nullptr, nullptr,
                                        nullptr, nullptr, nullptr, 0, B, Hin, Win, H, W, F, dilation, s, &handled, gout, gw,
@@ -393,7 +465,7 @@ extern "C" int fvfi_adacof_backward(const float* gout, const float* input, const
         if (handled) return FVFI_OK;
         FVFI_CHECK_ARG(algo != 3, "adacof_backward: TMA algorithm needs F = 5, dilation 1, W %% 4 == 0 and 16-byte aligned maps");
     }
-    if (gin_mode != FVFI_GIN_TRUE && algo != 1 && algo != 3) {
+    if (algo != 1 && algo != 3) {
         int handled = 0;
         if (int rc = adacof_backward_tiled(gout, input, weight, off_i, off_j, gw, goi, goj, B, Hin, Win, H, W, F,
                                            dilation, s, &handled))
@@ -403,12 +475,8 @@ extern "C" int fvfi_adacof_backward(const float* gout, const float* input, const
                        dilation);
     }
     dim3 block(32, 8), grid(ceil_div(W, 32), ceil_div(H, 8), B);
-    if (gin_mode == FVFI_GIN_TRUE)
-        adacof_bwd_direct<true><<<grid, block, 0, s>>>(gout, input, weight, off_i, off_j, gin, gw, goi, goj, Hin,
-                                                       Win, H, W, F, dilation);
-    else
-        adacof_bwd_direct<false><<<grid, block, 0, s>>>(gout, input, weight, off_i, off_j, nullptr, gw, goi, goj,
-                                                        Hin, Win, H, W, F, dilation);
+    adacof_bwd_direct<<<grid, block, 0, s>>>(gout, input, weight, off_i, off_j, nullptr, gw, goi, goj, Hin, Win, H, W, F,
+                                             dilation);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }

@@ -8,7 +8,8 @@ memsets (adacof.py:382-438).
 
 ``gin_mode`` (module attribute, default "zeros") selects what ``gradInput`` is:
   "zeros" -- reference semantics, gradInput == 0 (adacof.py:382,445)
-  "true"  -- extension: the true adjoint (warp-aggregated atomic scatter)
+  "true"  -- extension: the true adjoint (csrc/adacof.cu adacof_grad_input_scatter: warp-aggregated atomic scatter --
+             lanes grouped by target address with __match_any_sync, one reduction per distinct address)
 """
 import math
 

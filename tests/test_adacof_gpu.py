@@ -162,6 +162,39 @@ def test_autograd_function_and_true_grad_input():
     assert np.abs(gin.cpu().numpy() - ref).max() <= 2e-4  # atomics: order-dependent fp32 sums
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 40, 56, 5, 1), (1, 3, 33, 47, 5, 2), (1, 3, 24, 40, 3, 1), (1, 3, 17, 70, 5, 1)])
+@pytest.mark.parametrize("offsets", ["iid", "zero", "smooth", "clamped"])
+def test_true_grad_input_warp_aggregated_scatter(shape, offsets):
+    """gin_mode "true" (extension beyond the reference, which returns zeros): the warp-aggregated atomic scatter
+    (adacof_grad_input_scatter: __match_any_sync groups lanes by target address, one reduction per distinct address) equals the
+    serial adjoint of the oracle -- for scattered addresses (no aggregation), identical addresses in every lane (zero offsets with
+    F = 1 neighbours / clamped far-out offsets: whole warps collapse onto border samples) and smooth fields (partial groups);
+    ragged widths leave inactive lanes in the last warp.  The other three gradients come from the same fast path as mode "none"."""
+    from fvfi import adacof
+    B, C, H, W, F, d = shape
+    inp, w, oi, oj, g = oa.synth(B, C, H, W, F, d, seed=23)
+    if offsets == "zero":
+        oi, oj = np.zeros_like(oi), np.zeros_like(oj)
+    elif offsets == "smooth":
+        yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+        oi = np.broadcast_to(1.7 * np.sin(yy / 9.0) - 0.4 + 0.002 * xx, oi.shape).astype(np.float32).copy()
+        oj = np.broadcast_to(-2.3 * np.cos(xx / 11.0) + 0.3, oj.shape).astype(np.float32).copy()
+    elif offsets == "clamped":
+        oi, oj = (oi * 60).astype(np.float32), (oj * -60).astype(np.float32)
+    t_g, t_inp, t_w, t_oi, t_oj = _dev(g, inp, w, oi, oj)
+    gin, gw, gi, gj = adacof.adacof_backward(t_g, t_inp, t_w, t_oi, t_oj, d, "true")
+    ref = oa.grad_input(g, inp.shape, w, oi, oj, d)
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert np.abs(gin.cpu().numpy() - ref).max() <= 2e-5 * scale      # fp32 sums in a different (atomic) order
+    _, gw0, gi0, gj0 = adacof.adacof_backward(t_g, t_inp, t_w, t_oi, t_oj, d, "none")
+    assert torch.equal(gw, gw0) and torch.equal(gi, gi0) and torch.equal(gj, gj0)
+    # adjoint identity <gout, forward(x)> == <gradInput, x> (the forward is linear in the frame)
+    x = torch.randn(t_inp.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    lhs = float((t_g.double() * adacof.adacof_forward(x, t_w, t_oi, t_oj, d).double()).sum())
+    rhs = float((gin.double() * x.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
 def test_fused_warp_blend_and_tail():
     from fvfi import adacof
     B, H, W, F, d = 2, 48, 80, 5, 1
