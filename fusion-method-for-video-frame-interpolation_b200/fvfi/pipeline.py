@@ -22,6 +22,38 @@ from .phase_net import PhaseNet
 from .pyramid import Pyramid
 
 
+class GraphedCall:
+    """CUDA-graph replay of one fixed-shape entry point of the pipeline (``FusionPipeline.graphed``).
+
+    Small frames (256x256 crops: BASELINE.json configs[0] and the frozen part of the configs[4] training step) are bound by the
+    ~400-1000 kernel launches of a call, not by the kernels; capturing the launch sequence once and replaying it removes the
+    host from the loop.  Inputs are copied into the captured input buffers; the returned tensors are the captured output
+    buffers -- valid until the next call (clone them to keep them).  The 3xFP16 range flag is read after every replay; if a
+    replay left the range, the call is repeated eagerly (where the range guard re-runs it with the 3xTF32 split)."""
+
+    def __init__(self, fn, example_inputs, warmup=2):
+        self.fn = fn
+        self.static_in = [t.clone() for t in example_inputs]
+        side = torch.cuda.Stream(self.static_in[0].device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # warm-up off the default stream: plans, packed weights, workspaces exist
+            for _ in range(warmup):
+                fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = fn(*self.static_in)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        if tc.range_check and tc.precision == tc.PRECISIONS["f16x3"] and tc.overflow_pending():
+            return self.fn(*inputs)
+        return self.static_out
+
+
 class FusionPipeline(torch.nn.Module):
     def __init__(self, H, W, device, kernel_size=5, dilation=1, phase_plane_chunk=None):
         super().__init__()
@@ -40,6 +72,18 @@ class FusionPipeline(torch.nn.Module):
         self.fused_phase_glue = True   # PhaseNet.forward_fused (False: the reference's step-by-step value plumbing)
         self.pair_baseline = True      # baseline passes 2 and 3 (interpolate_twoframe.py:229,233) as one AdaCoFNet call on 2B frames
         self.max_batch_adacof = 16     # largest AdaCoFNet batch at full HD (the 64 -> 448 fused head tensor is 15 GB at 16)
+        self._copy_streams = None      # (host -> device, device -> host) side streams of interpolate_host
+        self._graphs = {}              # (method, input shapes) -> GraphedCall
+
+    def graphed(self, method, *example_inputs):
+        """``GraphedCall`` of ``self.<method>`` ('forward', 'fusion_inputs', 'phase_interp') for inputs of exactly these shapes:
+        captured on first use, replayed afterwards.  ``stages`` / ``timing`` capture must be off."""
+        assert self.stages is None and self.timing is None
+        key = (method,) + tuple(tuple(t.shape) for t in example_inputs)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = GraphedCall(getattr(self, method), example_inputs)
+        return g
 
     def _tick(self, name):
         """Stage timer: CUDA events on the current stream, only when ``self.timing`` is a list."""
@@ -183,12 +227,43 @@ class FusionPipeline(torch.nn.Module):
         return phase_pred
 
     def interpolate_host(self, rgb1_host, rgb2_host, out_host=None):
-        """End-to-end call on HOST (pinned) tensors: H2D copy of the two frames, the pipeline, D2H of the result."""
-        d1 = rgb1_host.to(self.device, non_blocking=True)
-        d2 = rgb2_host.to(self.device, non_blocking=True)
-        out = self.forward(d1, d2)
+        """End-to-end call on HOST (pinned) tensors [B,3,H,W]: host -> device copies of the frames, the pipeline, device -> host
+        copy of the result, all inside the call.  The batch is processed in sub-batches of ``max_batch`` pairs; the copies run
+        on two side streams, so sub-batch k+1's frames arrive and sub-batch k-1's result leaves while sub-batch k computes."""
+        B = rgb1_host.shape[0]
         if out_host is None:
-            out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
-        out_host.copy_(out, non_blocking=True)      # forward() has already verified the 3xFP16 range (tc.range_checked)
-        torch.cuda.current_stream().synchronize()
+            out_host = torch.empty((B, 3, self.H, self.W), dtype=torch.float32).pin_memory()
+        if self._copy_streams is None:
+            self._copy_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        self._interp_chunks(rgb1_host, rgb2_host, out_host)
+        return out_host
+
+    @torch.no_grad()
+    @tc.range_checked       # ONE range check (stream sync) for the whole call; the sub-batch forwards below are nested in it
+    def _interp_chunks(self, h1, h2, out_host):
+        compute = torch.cuda.current_stream(self.device)
+        s_in, s_out = self._copy_streams
+        B, mb = h1.shape[0], self.max_batch
+        s_in.wait_stream(compute)                      # the caller's earlier work on these buffers is ordered before the copies
+        staged = []
+        for a in range(0, B, mb):                      # all uploads are queued at once; they run in order on the input stream
+            with torch.cuda.stream(s_in):
+                d1 = h1[a:a + mb].to(self.device, non_blocking=True)
+                d2 = h2[a:a + mb].to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            staged.append((a, d1, d2, ev))
+        for a, d1, d2, ev in staged:
+            compute.wait_event(ev)
+            d1.record_stream(compute)
+            d2.record_stream(compute)
+            out = self.forward(d1, d2)
+            done = torch.cuda.Event()
+            done.record(compute)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                out_host[a:a + out.shape[0]].copy_(out, non_blocking=True)
+            out.record_stream(s_out)
+        compute.wait_stream(s_out)                     # the call returns with the result on the host
+        compute.synchronize()
         return out_host

@@ -7,8 +7,9 @@ from .dist import FlatGradBucket, all_reduce_mean_buffers, broadcast_module
 
 
 class FusionTrainer:
-    def __init__(self, pipeline, lr=1e-4, group=None):
+    def __init__(self, pipeline, lr=1e-4, group=None, graph_frozen=False):
         self.pipe = pipeline
+        self.graph_frozen = graph_frozen        # replay the frozen PhaseNet / AdaCoF part as a CUDA graph (fixed crop shape)
         self.net = pipeline.fusion_net
         self.net.train()
         # replicas start from rank 0's weights: the trained FusionNet and the frozen networks that produce its inputs
@@ -23,7 +24,10 @@ class FusionTrainer:
     def step(self, rgb1, rgb2, target):
         """One optimisation step on this rank's shard; returns the (local) loss tensor."""
         with torch.no_grad():                                    # frozen PhaseNet + AdaCoF (trainer.py:68-159)
-            inputs = self.pipe.fusion_inputs(rgb1, rgb2)
+            if self.graph_frozen:
+                inputs = self.pipe.graphed("fusion_inputs", rgb1, rgb2)(rgb1, rgb2)
+            else:
+                inputs = self.pipe.fusion_inputs(rgb1, rgb2)
         self.bucket.zero()
         pred = self.net(*inputs, variant=0)                      # trainer.py:215
         loss = torch.nn.functional.l1_loss(target, torch.clip(pred, 0, 1))     # trainer.py:246-254

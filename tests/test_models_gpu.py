@@ -187,6 +187,27 @@ def test_phasenet_256_vs_reference_golden(golden_dir, fused):
     assert rep["lab_pred"]["err_ref"] <= 1e-4 and rep["phase_pred"]["err_ref"] <= 1e-4      # the north-star bound itself
 
 
+def test_cuda_graph_replay_matches_eager():
+    """FusionPipeline.graphed: the captured launch sequence of a fixed-shape call (256x256 PhaseNet interpolation, and the frozen
+    part of the training step) replays to exactly the eager result, for new input values too."""
+    from fvfi.pipeline import FusionPipeline
+    H = W = 128
+    pipe = FusionPipeline(H, W, "cuda")
+    pipe.load_state(fp.seeded_state(21))
+    a1, a2 = [t.cuda() for t in fp.seeded_frames(2, H, W, 21)]
+    b1, b2 = [t.cuda() for t in fp.seeded_frames(2, H, W, 22)]
+    with torch.no_grad():
+        g = pipe.graphed("phase_interp", a1, a2)
+        assert pipe.graphed("phase_interp", a1, a2) is g                 # captured once per (method, shapes)
+        for x1, x2 in ((a1, a2), (b1, b2), (a1, a2)):
+            assert torch.equal(g(x1, x2).clone(), pipe.phase_interp(x1, x2))
+        gi = pipe.graphed("fusion_inputs", a1, a2)
+        for x1, x2 in ((b1, b2), (a1, a2)):
+            got = [t.clone() for t in gi(x1, x2)]
+            ref = pipe.fusion_inputs(x1, x2)
+            assert all(torch.equal(p, q) for p, q in zip(got, ref))
+
+
 def test_conv_range_guard_reruns_in_tf32x3():
     """|activation| > 4094 leaves the 3xFP16 operand range: the decorated module forwards notice the device flag and run again with
     the 3xTF32 split instead of returning inf/NaN (device-resident path)."""
