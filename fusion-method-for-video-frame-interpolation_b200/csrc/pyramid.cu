@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -72,6 +73,8 @@ struct LevelJob {
     long long t_off;             // intermediate T of this level starts at regionB + N * t_off (complex elements)
     long long c_off;             // per-plane offset of the level spectrum in region C
     const float* radial;         // D_l (band levels), low-pass product (L), hi0 (L+1)
+    const float* band_build;     // band levels: [nb][h][w] = D_l * one-sided angular mask (decomposition); null otherwise
+    const float* band_rec;       // band levels: [nb][h][w] = D_l * two-sided angular mask (reconstruction and its adjoint)
     FftPlan fy, fx;              // column / row transforms
 };
 
@@ -98,6 +101,7 @@ struct fvfi_pyr_plan {
     std::vector<fvfi::LevelJob> jobs;           // host copy of the job table (L + 2 entries)
     const fvfi::LevelJob* d_jobs = nullptr;     // device job table
     std::vector<const float*> radial;           // device, per level (index L = low-pass product)
+    std::vector<const float*> band_build, band_rec;   // device, per band level: [nb][h_l][w_l] combined radial x angular masks
     const float* hi0 = nullptr;                 // device [H*W], unshifted
     std::map<std::pair<int, int>, fvfi::FftPlan> fft_cache;   // (length, stockham) -> plan with device tables
     std::vector<void*> owned;
@@ -177,6 +181,8 @@ static int build_jobs(fvfi_pyr_plan* p) {
         J.nb = (l < L) ? nb : 1;
         J.is_band = (l < L) ? 1 : 0;
         J.radial = full ? p->hi0 : p->radial[l];
+        J.band_build = (l < L) ? p->band_build[l] : nullptr;
+        J.band_rec = (l < L) ? p->band_rec[l] : nullptr;
         J.t_off = full ? (long long)nb * (long long)p->level_elems : (long long)nb * (long long)p->lv[l].off;
         J.c_off = full ? 0 : (long long)p->lv[l].off;
         J.mag_w = fft_magic((unsigned)J.w);
@@ -280,6 +286,75 @@ static int build_plan(fvfi_pyr_plan* p) {
         const double hi = -(double)l * dlt;
         p->lv[l].rad2_lo = (l < L) ? (float)(pow(2.0, 2.0 * lo) * (1.0 - 1e-4)) : -1.f;
         p->lv[l].rad2_hi = (float)(pow(2.0, 2.0 * hi) * (1.0 + 1e-4));
+    }
+    // Combined band masks  D_l * anglemask_b, with the angular mask computed EXACTLY as the published algorithm does (upstream
+    // SCFpyr: angle = arctan2 on the cropped prepare_grid, then np.interp in the 1024-step cos^(nb-1) lookup table shifted by
+    // pi*b/nb -- one-sided table for build, two-sided for reconstruct).  A closed-form cos^(nb-1) differs from the interpolated
+    // table by up to 3e-6 relative, which PhaseNet turns into 1e-4 .. 5e-3 output differences (phase of weak coefficients);
+    // evaluating the table in double here makes the masks equal to the oracle's to float32 rounding.
+    {
+        const int order_ = nb - 1, lutsize = 1024, NL = 3 * lutsize + 3;      // Xcosn = pi * (-(2*lutsize+1) .. lutsize+1) / lutsize
+        double fo_ = 1, f2o_ = 1;
+        for (int i = 2; i <= order_; ++i) fo_ *= i;
+        for (int i = 2; i <= 2 * order_; ++i) f2o_ *= i;
+        const double cst_ = pow(2.0, 2.0 * order_) * fo_ * fo_ / (nb * f2o_);
+        std::vector<double> Xc(NL), Y1(NL), Y2(NL);
+        for (int i = 0; i < NL; ++i) {
+            Xc[i] = M_PI * (double)(i - (2 * lutsize + 1)) / lutsize;
+            const double cp = pow(cos(Xc[i]), (double)order_);
+            double alpha = fmod(Xc[i] + M_PI, 2.0 * M_PI);                    // numpy %: result has the sign of the divisor
+            if (alpha < 0) alpha += 2.0 * M_PI;
+            alpha -= M_PI;
+            Y1[i] = 2.0 * sqrt(cst_) * cp * (fabs(alpha) < M_PI / 2 ? 1.0 : 0.0);
+            Y2[i] = sqrt(cst_) * cp;
+        }
+        p->band_build.assign(L, nullptr);
+        p->band_rec.assign(L, nullptr);
+        for (int l = 0; l < L; ++l) {
+            const int hl = p->lv[l].h, wl = p->lv[l].w;
+            const size_t plane = (size_t)hl * wl;
+            std::vector<float> rad(plane);
+            FVFI_CUDA(cudaMemcpy(rad.data(), p->radial[l], plane * sizeof(float), cudaMemcpyDeviceToHost));
+            std::vector<float> t1((size_t)nb * plane), t2((size_t)nb * plane);
+            auto rows = [&](int y_begin, int y_end) {
+                std::vector<double> Xs(NL);
+                for (int ky = y_begin; ky < y_end; ++ky)
+                    for (int kx = 0; kx < wl; ++kx) {
+                        const size_t o = (size_t)ky * wl + kx;
+                        const double d = rad[o];
+                        if (d == 0.0) {
+                            for (int b = 0; b < nb; ++b) t1[b * plane + o] = t2[b * plane + o] = 0.f;
+                            continue;
+                        }
+                        const double xv = sfreq_h(kx, wl) * 2.0 / W, yv = sfreq_h(ky, hl) * 2.0 / H;
+                        const double ang = atan2(yv, xv);
+                        for (int b = 0; b < nb; ++b) {
+                            const double sh = M_PI * b / nb;
+                            // np.interp(ang, Xc + sh, Y): locate the interval directly (uniform abscissa), then numpy's formula
+                            int j = (int)floor((ang - sh - Xc[0]) / (M_PI / lutsize));
+                            j = std::max(0, std::min(NL - 2, j));
+                            while (j > 0 && Xc[j] + sh > ang) --j;
+                            while (j < NL - 2 && Xc[j + 1] + sh <= ang) ++j;
+                            const double x0 = Xc[j] + sh, x1 = Xc[j + 1] + sh;
+                            const double a1 = (Y1[j + 1] - Y1[j]) / (x1 - x0) * (ang - x0) + Y1[j];
+                            const double a2 = (Y2[j + 1] - Y2[j]) / (x1 - x0) * (ang - x0) + Y2[j];
+                            // float32 masks multiplied in float32, like the oracle's torch tensors
+                            t1[b * plane + o] = (float)d * (float)a1;
+                            t2[b * plane + o] = (float)d * (float)a2;
+                        }
+                    }
+            };
+            const int nthr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            if (plane < 65536 || nthr == 1) {
+                rows(0, hl);
+            } else {
+                std::vector<std::thread> pool;
+                for (int t = 0; t < nthr; ++t) pool.emplace_back(rows, (int)((long long)hl * t / nthr), (int)((long long)hl * (t + 1) / nthr));
+                for (auto& th : pool) th.join();
+            }
+            if (int rc = upload(p, t1, &p->band_build[l])) return rc;
+            if (int rc = upload(p, t2, &p->band_rec[l])) return rc;
+        }
     }
     // angular parameters
     const int order = nb - 1;
@@ -476,7 +551,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_fwd(const Le
             for (int q = threadIdx.x; q < E_; q += blockDim.x) {
                 const int pos = q >> cs, c = q & (CT - 1);
                 const int ky = R.perm ? (int)__ldg(R.perm + pos) : pos;
-                const float g = ang_factor(A, b, sfreq(ky, h), sfreq(min(x0 + c, w - 1), w));
+                const float g = __ldg(J.band_rec + ((size_t)b * h + ky) * w + min(x0 + c, w - 1));   // D_l * two-sided angular mask
                 const float2 rv = fft_get<true>(ioy, R, c, pos, cs, 0);
                 const float2 v = cmul(make_float2(rv.x * g, rv.y * g), A.fac);
                 acc[q] = (b == 0) ? v : cadd(acc[q], v);
@@ -484,7 +559,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_fwd(const Le
             __syncthreads();
         }
     }
-    const float* radial = use_radial ? J.radial : nullptr;
+    const float* radial = (use_radial && !combine) ? J.radial : nullptr;      // combine: the radial mask is part of band_rec
     float2* dst = outbase + (size_t)n * out_stride + (add_c_off ? (size_t)J.c_off : 0);
     for (int q = threadIdx.x; q < E_; q += blockDim.x) {
         const int pos = q >> cs, c = q & (CT - 1);
@@ -504,8 +579,8 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_fwd(const Le
 // grid: (column tiles of all jobs, nb, N)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_decomp(const LevelJob* __restrict__ jobs, const LaunchSet S,
-                                                                    AngParams A, int H, int W, const float2* __restrict__ X,
-                                                                    float2* __restrict__ regionB) {
+                                                                    float2 band_fac, int use_rec_table, int H, int W,
+                                                                    const float2* __restrict__ X, float2* __restrict__ regionB) {
     extern __shared__ float2 smem[];
     const SetEntry& E = find_entry(S, blockIdx.x);
     const LevelJob& J = jobs[E.job];
@@ -519,7 +594,8 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_decomp(c
     const bool band = J.is_band != 0;
     float2* a = smem;
     const float2* Xn = X + (size_t)n * H * W;
-    const float* radial = J.radial;
+    // band levels: the combined radial x angular mask of band b (plan table, equal to the oracle's masks); else the radial mask
+    const float* radial = band ? (use_rec_table ? J.band_rec : J.band_build) + (size_t)b * h * w : J.radial;
     {
         constexpr int U = 4;                  // two dependent global loads per element: batch them
         for (int q0 = threadIdx.x; q0 < E_; q0 += U * blockDim.x) {
@@ -536,7 +612,6 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_decomp(c
                 const int q = q0 + u * blockDim.x;
                 const int ky = q >> cs, c = q & (CT - 1);
                 const int fy = sfreq(ky, h), fx = sfreq(x0 + c, w);
-                if (band && m[u] != 0.f) m[u] *= ang_factor(A, b, fy, fx);
                 xv[u] = make_float2(0.f, 0.f);
                 if (m[u] != 0.f) xv[u] = __ldg(Xn + (size_t)wrapi(fy, H) * W + wrapi(fx, W));
             }
@@ -545,7 +620,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_decomp(c
                 const int q = q0 + u * blockDim.x;
                 if (q < E_) {
                     float2 v = make_float2(xv[u].x * m[u], xv[u].y * m[u]);
-                    if (band) v = cmul(v, A.fac);
+                    if (band) v = cmul(v, band_fac);
                     v.y = -v.y;
                     fft_put<true>(ioy, a, q & (CT - 1), q >> cs, v, cs, 0);
                 }
@@ -770,7 +845,8 @@ static int launch_cols_inv_decomp(const fvfi_pyr_plan* p, const SetBuilder& sb, 
     int nbmax = 1;
     for (int i = 0; i < sb.cols.n; ++i) nbmax = std::max(nbmax, p->jobs[sb.cols.e[i].job].nb);
     dim3 grid(sb.cols.total, nbmax, N);
-    k_cols_inv_decomp<<<grid, PYR_THREADS, sb.cols_smem, s>>>(p->d_jobs, sb.cols, ang ? *ang : p->ang_build, p->H, p->W, X, regionB);
+    k_cols_inv_decomp<<<grid, PYR_THREADS, sb.cols_smem, s>>>(p->d_jobs, sb.cols, ang ? ang->fac : p->ang_build.fac, ang ? 1 : 0, p->H, p->W,
+                                                              X, regionB);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }

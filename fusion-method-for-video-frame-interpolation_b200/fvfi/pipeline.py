@@ -74,6 +74,9 @@ class FusionPipeline(torch.nn.Module):
         self.max_batch_adacof = 16     # largest AdaCoFNet batch at full HD (the 64 -> 448 fused head tensor is 15 GB at 16)
         self._copy_streams = None      # (host -> device, device -> host) side streams of interpolate_host
         self._graphs = {}              # (method, input shapes) -> GraphedCall
+        # optional callable (tag, planes, vals) -> vals applied to every decomposition (tests: aligns the branch of phase values
+        # at +-pi with the reference's, see tests/_parity.py; None in production)
+        self.filter_hook = None
 
     def graphed(self, method, *example_inputs):
         """``GraphedCall`` of ``self.<method>`` ('forward', 'fusion_inputs', 'phase_interp') for inputs of exactly these shapes:
@@ -84,6 +87,12 @@ class FusionPipeline(torch.nn.Module):
         if g is None:
             g = self._graphs[key] = GraphedCall(getattr(self, method), example_inputs)
         return g
+
+    def _filter(self, tag, planes, **kw):
+        vals = self.pyr.filter(planes, **kw)
+        if self.filter_hook is not None:
+            vals = self.filter_hook(tag, planes, vals)
+        return vals
 
     def _tick(self, name):
         """Stage timer: CUDA events on the current stream, only when ``self.timing`` is a list."""
@@ -129,7 +138,7 @@ class FusionPipeline(torch.nn.Module):
         flow_var_map = flow_var_map.squeeze(1)
         self._tick('lab+adacofnet#1')
         # PhaseNet branch (:168-192)
-        vals = pyr.filter(torch.cat((lab1.reshape(-1, H, W), lab2.reshape(-1, H, W)), 0), want_high=False)
+        vals = self._filter("phasenet", torch.cat((lab1.reshape(-1, H, W), lab2.reshape(-1, H, W)), 0), want_high=False)
         self._tick('pyr.filter(12 planes/frame)')
         if self.fused_phase_glue:
             # separate_vals / get_concat_layers_inf / normalize_vals / forward / reverse_normalize with the regrouping and the
@@ -154,15 +163,16 @@ class FusionPipeline(torch.nn.Module):
             # :205-209).  Decomposition and reconstruction are linear in the image, so this is recon_{high + level 0} of the single
             # plane  xbar = mean_c(ada_c - phase_c): the six colour planes are decomposed on the (tiny) coarse levels only.
             vals_ada, vals_ph = utils.separate_vals(
-                pyr.filter(torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), want_high=False, levels=coarse), 2)
+                self._filter("uncertainty", torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), want_high=False,
+                             levels=coarse), 2)
             self._tick('lab2rgb+pyr.filter(6 planes/frame)')
-            v0 = pyr.filter((ada_pred - phase_pred).mean(1), levels=[0])
+            v0 = pyr.filter((ada_pred - phase_pred).mean(1), levels=[0])      # reconstructed at once: its phases feed cos / sin only
             h_diff = pyr.inv_filter_sparse(v0, use_low=False, levels=[0])
             del v0
         else:
             used = sorted(set([0]) | set(coarse))
             vals_ada, vals_ph = utils.separate_vals(
-                pyr.filter(torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), levels=used), 2)
+                self._filter("uncertainty", torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), levels=used), 2)
             self._tick('lab2rgb+pyr.filter(6 planes/frame)')
             h_freq = pyr.inv_filter_sparse(vals_ada, use_low=False, levels=[0]).reshape(r_shape).mean(1)
             h_freq_ph = pyr.inv_filter_sparse(vals_ph, use_low=False, levels=[0]).reshape(r_shape).mean(1)
@@ -213,7 +223,7 @@ class FusionPipeline(torch.nn.Module):
         assert (H, W) == (self.H, self.W) and rgb2.shape == rgb1.shape
         pyr = self.pyr
         lab1, lab2 = transform.rgb2lab(rgb1), transform.rgb2lab(rgb2)
-        vals = pyr.filter(torch.cat((lab1.reshape(-1, H, W), lab2.reshape(-1, H, W)), 0), want_high=False)
+        vals = self._filter("phasenet", torch.cat((lab1.reshape(-1, H, W), lab2.reshape(-1, H, W)), 0), want_high=False)
         if self.fused_phase_glue:
             vals_pred = self.phase_net.forward_fused(vals, pyr.last_amp_max)
         else:

@@ -122,7 +122,7 @@ def test_pipeline_vs_reference_golden(golden_dir, conv_backend):
     lengths, AdaCoFNet reflect padding in both axes) and 256x256 with the SHIPPED phase_net.pt / fusion_net.pt.
     Bound: 1e-4 max abs per stage against the reference (north star), or -- where the fixture carries the fp64 arbiter -- no
     further from the fp64 result than twice the reference's own fp32 run (tests/_parity.py)."""
-    from _parity import fmt, psnr, stage_report
+    from _parity import WrapAligner, fmt, psnr, stage_report
     from fvfi.pipeline import FusionPipeline
     files = sorted(glob.glob(os.path.join(golden_dir, "pipeline_*.npz")))
     assert len(files) >= 5
@@ -133,12 +133,21 @@ def test_pipeline_vs_reference_golden(golden_dir, conv_backend):
         pipe.load_state(_state_for(z, os.path.basename(f), seed))
         pipe.stages = {}
         rgb1, rgb2 = fp.seeded_frames(B, H, W, seed)
-        out = pipe(rgb1.cuda(), rgb2.cuda())
         if "final__d64" in z.files:
+            raw = pipe(rgb1.cuda(), rgb2.cuda()).cpu().numpy()        # as shipped: whatever branch the GPU's own rounding picks
+            # parity run on the reference's branch of the wrapped phases (tests/_parity.py: WrapAligner)
+            pipe.filter_hook = al = WrapAligner(pipe.pyr.height)
+            pipe.stages = {}
+            out = pipe(rgb1.cuda(), rgb2.cuda())
             rep = stage_report(z, pipe.stages)
-            print(conv_backend, os.path.basename(f), fmt(rep))
+            print(conv_backend, os.path.basename(f), "wrap flips aligned: %d of %d phase values" % (al.flips, al.coefficients), fmt(rep))
             bad = [k for k, v in rep.items() if not v["ok"]]
             assert not bad, (bad, fmt(rep))
+            assert al.flips <= 1e-5 * al.coefficients                 # a handful of coefficients, not a systematic difference
+            st0 = int(z["final__stride"]) if "final__stride" in z.files else 1
+            print("  unaligned run: final max abs err %.2e, PSNR %.1f dB" % (float(np.abs(raw[..., ::st0, ::st0] - z["final"]).max()),
+                                                                            psnr(raw[..., ::st0, ::st0], z["final"])))
+            assert psnr(raw[..., ::st0, ::st0], z["final"]) >= 70
             st = int(z["final__stride"]) if "final__stride" in z.files else 1
             o = out.cpu().numpy()[..., ::st, ::st]
             print("final: max abs err %.2e, PSNR(GPU vs reference) %.1f dB" % (float(np.abs(o - z["final"]).max()), psnr(o, z["final"])))
@@ -168,7 +177,7 @@ def test_phasenet_256_vs_reference_golden(golden_dir, fused):
     the reference's own Pyramid wrapper + PhaseNet on CPU (tests/golden/phasenet_ref_256x256_s5.npz): every predicted level
     (as complex coefficients), the low pass, the reconstructed Lab planes and the RGB frame.  Pyramid(12, 4, sqrt 2):
     levels 256,181,128,91,64,45,32,23,16,11 + low 8 -> layers[7] (phase_net.py:148) serves the four finest levels."""
-    from _parity import fmt, stage_report
+    from _parity import WrapAligner, fmt, stage_report
     from fvfi.pipeline import FusionPipeline
     z = np.load(os.path.join(golden_dir, "phasenet_ref_256x256_s5.npz"))
     B, H, W, seed = [int(v) for v in z["meta"]]
@@ -176,11 +185,13 @@ def test_phasenet_256_vs_reference_golden(golden_dir, fused):
     assert pipe.pyr.height == 12
     pipe.load_state(_state_for(z, "phasenet_ref", seed))
     pipe.fused_phase_glue = fused
+    pipe.filter_hook = al = WrapAligner(pipe.pyr.height)     # compare on the reference's branch of the wrapped input phases
     pipe.stages = {}
     rgb1, rgb2 = fp.seeded_frames(B, H, W, seed)
     pipe.phase_interp(rgb1.cuda(), rgb2.cuda())
     rep = stage_report(z, pipe.stages)
-    print("fused" if fused else "stepwise", fmt(rep))
+    print("fused" if fused else "stepwise", "wrap flips aligned: %d of %d" % (al.flips, al.coefficients), fmt(rep))
+    assert al.flips <= 1e-5 * al.coefficients
     assert len(rep) == 13                      # 10 levels + low_level + lab_pred + phase_pred
     bad = [k for k, v in rep.items() if not v["ok"]]
     assert not bad, (bad, fmt(rep))
@@ -224,9 +235,13 @@ def test_conv_range_guard_reruns_in_tf32x3():
     gfn.load_state_dict(state["fusion_net"])
     with torch.no_grad():
         ref = ofn(*ins)
-        got = gfn(*[t.cuda() for t in ins]).cpu()
+        cins = [t.cuda() for t in ins]
+        got = gfn(*cins).cpu()
         assert bool(torch.isfinite(got).all())
-        assert float((got - ref).abs().max()) <= 1e-4
+        with tc.forced_precision("tf32x3"):
+            want = gfn(*cins).cpu()
+        assert torch.equal(got, want)                               # the guarded call returned the 3xTF32 result
+        assert float((got - ref).abs().max()) <= 2e-2               # |x| ~ 3e4 through 7 layers: fp32 rounding of both sides
         assert not tc.overflow_pending()                            # the guard consumed the flag
         x = (torch.rand((1, 16, 32, 48), generator=g) * 3.0e4).cuda()
         w = torch.rand((16, 16, 3, 3), generator=g).cuda()
