@@ -219,14 +219,14 @@ class PipelineWorkload:
 
     # ------------------------------------------------------------------------------------------ CPU legs (oracle = the checker)
     @classmethod
-    def _cpu_run(cls, H, W, threads, seed, stages=None):
+    def _cpu_run(cls, H, W, threads, seed, stages=None, decomps=None):
         import torch
         from oracle import fusion_pipeline as fp
         torch.set_num_threads(threads)
         be = fp.oracle_backend(fp.seeded_state(0), hw=(H, W), threads=threads)
         r1, r2 = fp.seeded_frames(1, H, W, seed)
         t0 = time.perf_counter()
-        out = fp.interp(be, r1, r2, stages)
+        out = fp.interp(be, r1, r2, stages, decomps)
         return time.perf_counter() - t0, (r1, r2, out)
 
     @classmethod
@@ -235,9 +235,10 @@ class PipelineWorkload:
         frame pair at ``size`` (default CPU_SAMPLE); frames/s is scaled to the workload's frame by the pixel ratio."""
         H, W = size or cls.CPU_SAMPLE
         stages = {} if keep is not None else None
-        dt, io = cls._cpu_run(H, W, threads, seed, stages)
+        decomps = {} if keep is not None else None
+        dt, io = cls._cpu_run(H, W, threads, seed, stages, decomps)
         if keep is not None:
-            keep.update(size=(H, W), io=io, stages=stages)
+            keep.update(size=(H, W), io=io, stages=stages, decomps=decomps)
         scale = (H * W) / float(cls.H * cls.W)
         return scale / dt, dt, ("1 frame pair at %dx%d (%.4f of the %dx%d area), frames/s scaled by the pixel ratio; "
                                 "oracle port of the reference recipe: torch CPU + scipy + C warp" % (W, H, scale, cls.W, cls.H))
@@ -263,7 +264,7 @@ class PipelineWorkload:
         raw = pipe(r1.to(self.device), r2.to(self.device)).cpu().numpy()         # as shipped
         # the same call evaluated on the reference's branch of the wrapped phases at the few coefficients on the negative real
         # axis (oracle/wrap_align.py; the reference recipe is discontinuous there, tests/test_models_oracle.py)
-        pipe.filter_hook = al = WrapAligner(pipe.pyr.height)
+        pipe.filter_hook = al = WrapAligner.from_decomps(kept["decomps"])
         pipe.stages = {}
         out = pipe(r1.to(self.device), r2.to(self.device)).cpu().numpy()
         per = {k: float(np.abs(pipe.stages[k].cpu().numpy() - v.numpy()).max()) for k, v in kept["stages"].items()
@@ -359,7 +360,7 @@ class PhaseNet256Workload(PipelineWorkload):
         return dt, nb(self.h1) + nb(self.h2), nb(self.out_host), bool(torch.equal(self.out_host, self.out.cpu()))
 
     @classmethod
-    def _cpu_run(cls, H, W, threads, seed, stages=None):
+    def _cpu_run(cls, H, W, threads, seed, stages=None, decomps=None):
         import torch
         from oracle import fusion_pipeline as fp
         torch.set_num_threads(threads)
@@ -367,14 +368,14 @@ class PhaseNet256Workload(PipelineWorkload):
         r1, r2 = fp.seeded_frames(1, H, W, seed)
         fp.interp_phasenet(be, r1, r2)                    # warm-up (thread pools, FFT plans): this config runs in < 1 s
         t0 = time.perf_counter()
-        out = fp.interp_phasenet(be, r1, r2, stages)
+        out = fp.interp_phasenet(be, r1, r2, stages, decomps)
         return time.perf_counter() - t0, (r1, r2, out)
 
     def parity(self, kept):
         from oracle.wrap_align import WrapAligner
         r1, r2, ref = kept["io"]
         raw = self.pipe.phase_interp(r1.to(self.device), r2.to(self.device)).cpu().numpy()
-        self.pipe.filter_hook = al = WrapAligner(self.pipe.pyr.height)
+        self.pipe.filter_hook = al = WrapAligner.from_decomps(kept["decomps"])
         self.pipe.stages = {}
         out = self.pipe.phase_interp(r1.to(self.device), r2.to(self.device)).cpu().numpy()
         st, self.pipe.stages, self.pipe.filter_hook = self.pipe.stages, None, None

@@ -62,9 +62,10 @@ def oracle_backend(state, kernel_size=5, dilation=1, threads=1, height=None, hw=
 
 
 @torch.no_grad()
-def interp(backend, rgb1, rgb2, stages=None):
+def interp(backend, rgb1, rgb2, stages=None, decomps=None):
     """rgb1, rgb2: [B,3,H,W] in [0,1] (CPU).  Returns the fused frame [B,3,H,W]; ``stages`` (dict) receives
-    the intermediate tensors named as in the reference script."""
+    the intermediate tensors named as in the reference script, ``decomps`` (dict) the two raw decompositions
+    ("phasenet", "uncertainty") -- what oracle/wrap_align.py needs to know the reference's branch of phases at +-pi."""
     be = backend
     dt = getattr(be, "dtype", torch.float32)
     rgb1, rgb2 = rgb1.to(dt), rgb2.to(dt)
@@ -75,7 +76,10 @@ def interp(backend, rgb1, rgb2, stages=None):
     flow_var_map = flow_var_map.squeeze(1)                                                     # :165
     # PhaseNet branch :168-192
     img_batch = torch.cat((lab1.reshape(-1, H, W), lab2.reshape(-1, H, W)), 0)
-    vals_list = be.separate_vals(be.pyr.filter(img_batch.to(dt)), 2)
+    vals_raw = be.pyr.filter(img_batch.to(dt))
+    if decomps is not None:
+        decomps["phasenet"] = vals_raw
+    vals_list = be.separate_vals(vals_raw, 2)
     inp = be.phase_net.normalize_vals(be.get_concat_layers_inf(be.pyr, vals_list))
     vals_pred = be.phase_net(inp)
     lab_pred = be.pyr.inv_filter(vals_pred).reshape(r_shape).to(dt)
@@ -83,7 +87,10 @@ def interp(backend, rgb1, rgb2, stages=None):
     phase_pred = rgb_pred.clone()
     # uncertainty maps :197-225
     img_batch = torch.cat((ada_pred.reshape(-1, H, W), rgb_pred.reshape(-1, H, W)), 0)
-    vals_ada, vals_ph = be.separate_vals(be.pyr.filter(img_batch.to(dt)), 2)
+    vals_raw = be.pyr.filter(img_batch.to(dt))
+    if decomps is not None:
+        decomps["uncertainty"] = vals_raw
+    vals_ada, vals_ph = be.separate_vals(vals_raw, 2)
     h_freq = be.pyr.inv_filter(be.get_last_value_levels(vals_ada, use_levels=1)).reshape(r_shape).mean(1)
     h_freq_ph = be.pyr.inv_filter(be.get_last_value_levels(vals_ph, use_levels=1)).reshape(r_shape).mean(1)
     h_freq_diff = (torch.abs(h_freq - h_freq_ph) * 100).clamp(min=0, max=1.0)
@@ -108,7 +115,7 @@ def interp(backend, rgb1, rgb2, stages=None):
 
 
 @torch.no_grad()
-def interp_phasenet(backend, rgb1, rgb2, stages=None):
+def interp_phasenet(backend, rgb1, rgb2, stages=None, decomps=None):
     """BASELINE.json configs[0]: PhaseNet decompose -> phase/amplitude prediction -> reconstruct on a frame pair
     (src/phase_net/interpolate_twoframe.py:52-107: rgb2lab -> pyr.filter -> concat layers -> normalize_vals -> phase_net ->
     inv_filter -> lab2rgb; the three colour planes are a batch here instead of that script's per-channel loop "to save
@@ -120,7 +127,10 @@ def interp_phasenet(backend, rgb1, rgb2, stages=None):
     B, _, H, W = rgb1.shape
     lab1, lab2 = rgb2lab_planes(rgb1, dt), rgb2lab_planes(rgb2, dt)
     img_batch = torch.cat((lab1.reshape(-1, H, W), lab2.reshape(-1, H, W)), 0)
-    vals_list = be.separate_vals(be.pyr.filter(img_batch.to(dt)), 2)
+    vals_raw = be.pyr.filter(img_batch.to(dt))
+    if decomps is not None:
+        decomps["phasenet"] = vals_raw
+    vals_list = be.separate_vals(vals_raw, 2)
     vals_pred = be.phase_net(be.phase_net.normalize_vals(be.get_concat_layers_inf(be.pyr, vals_list)))
     lab_pred = be.pyr.inv_filter(vals_pred).reshape(B, 3, H, W).to(dt)
     phase_pred = lab2rgb_planes(lab_pred, dt)

@@ -16,6 +16,8 @@ The oracle restatement (fp32) is asserted equal to the reference modules on ever
                                      58, 82, 116, 164, 232) and whose AdaCoFNet input is reflect-padded to /32 in both axes.
 * pipeline_ckpt_B1_256x256_s4.npz    full recipe with the SHIPPED checkpoints src/phase_net/phase_net.pt and
                                      src/fusion_net/fusion_net.pt (AdaCoF: seeded random init -- its checkpoint is a missing LFS blob).
+``wrap_<call>_<level>_idx/_val``: the reference's phase at every coefficient within 0.05 rad of +-pi, per decomposition call of the
+recipe -- the branch the parity runs align the GPU's wrapped phases to (oracle/wrap_align.py explains why).
 Stages above 30k elements are stored subsampled in the two image axes (stride in ``<k>__stride``); ``<k>__budget`` is
 max|k - fp64| over ALL elements.  Inputs are regenerated from the seed.
 """
@@ -31,6 +33,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 from oracle import fusion_pipeline as fp, ref_import  # noqa: E402
+from oracle.wrap_align import wrap_lists  # noqa: E402
 from make_golden_models import reference_backend  # noqa: E402
 
 torch.set_grad_enabled(False)
@@ -50,8 +53,8 @@ SKIP = ("lab1", "lab2")      # per-pixel Lab conversion: covered by tests/test_m
 def run_case(recipe, state, B, H, W, seed, name, stride_over=30000):
     rgb1, rgb2 = fp.seeded_frames(B, H, W, seed)
     t0 = time.time()
-    ref, o32, o64 = {}, {}, {}
-    recipe(reference_backend(state, H, W), rgb1, rgb2, ref)
+    ref, o32, o64, dec = {}, {}, {}, {}
+    recipe(reference_backend(state, H, W), rgb1, rgb2, ref, dec)
     recipe(fp.oracle_backend(state, hw=(H, W), threads=8), rgb1, rgb2, o32)
     err = {k: float((ref[k] - o32[k]).abs().max()) for k in ref}
     print(name, "oracle(fp32) vs reference modules:", {k: "%.1e" % v for k, v in err.items() if v > 0})
@@ -73,6 +76,10 @@ def run_case(recipe, state, B, H, W, seed, name, stride_over=30000):
             keep[k + "__stride"] = np.array(st)
         keep[k] = np.ascontiguousarray(a)
         keep[k + "__d64"] = np.clip((a.astype(np.float64) - b) * 1e4, -6e4, 6e4).astype(np.float16)
+    # the reference's branch at the coefficients within rounding of the negative real axis (oracle/wrap_align.py)
+    wl = wrap_lists(dec)
+    keep.update(wl)
+    print(name, "coefficients within %.2f rad of +-pi: %d" % (0.05, sum(v.size for k, v in wl.items() if k.endswith("_idx"))))
     print(name, "reference fp32 vs fp64 arbiter:", {k: "%.1e" % v for k, v in budget.items()})
     np.savez_compressed(os.path.join(HERE, name), **keep)
     print("wrote", name, "%.1f MB, %.0f s" % (os.path.getsize(os.path.join(HERE, name)) / 1e6, time.time() - t0))

@@ -136,7 +136,7 @@ def test_pipeline_vs_reference_golden(golden_dir, conv_backend):
         if "final__d64" in z.files:
             raw = pipe(rgb1.cuda(), rgb2.cuda()).cpu().numpy()        # as shipped: whatever branch the GPU's own rounding picks
             # parity run on the reference's branch of the wrapped phases (tests/_parity.py: WrapAligner)
-            pipe.filter_hook = al = WrapAligner(pipe.pyr.height)
+            pipe.filter_hook = al = WrapAligner(z)
             pipe.stages = {}
             out = pipe(rgb1.cuda(), rgb2.cuda())
             rep = stage_report(z, pipe.stages)
@@ -185,7 +185,7 @@ def test_phasenet_256_vs_reference_golden(golden_dir, fused):
     assert pipe.pyr.height == 12
     pipe.load_state(_state_for(z, "phasenet_ref", seed))
     pipe.fused_phase_glue = fused
-    pipe.filter_hook = al = WrapAligner(pipe.pyr.height)     # compare on the reference's branch of the wrapped input phases
+    pipe.filter_hook = al = WrapAligner(z)                    # compare on the reference's branch of the wrapped input phases
     pipe.stages = {}
     rgb1, rgb2 = fp.seeded_frames(B, H, W, seed)
     pipe.phase_interp(rgb1.cuda(), rgb2.cuda())
