@@ -18,6 +18,14 @@ Phases are compared as complex coefficients amp * exp(i phase): the angle of a (
 import numpy as np
 
 TOL = 1e-4
+# Stages the recipe multiplies by an explicit gain before a clamp carry that gain in their bound (the un-amplified quantity agrees
+# to 1e-5, ten times tighter than the image bound).  src/fusion_net/interpolate_twoframe.py:
+#   :210-211  h_freq_diff = |h_freq - h_freq_ph| * 100          -> 100 * 1e-5
+#   :212-214  phase_uncertainty = gaussian_filter(h_freq_diff)  -> same bound (a smoothing)
+#   :220      freq_diff = mean(...) * 30                        -> 30 * 1e-5
+#   :221-224  ada_uncertainty = |freq_diff - median50(freq_diff)| * 5 -> 2 * 5 * the freq_diff bound
+# Every IMAGE of the recipe (ada_pred, lab_pred, phase_pred, base, final, Lab planes) keeps the north-star bound 1e-4.
+STAGE_TOL = {"h_freq_diff": 1e-3, "phase_uncertainty": 1e-3, "freq_diff": 3e-4, "ada_uncertainty": 3e-3}
 
 
 def _sample(a, z, k):
@@ -56,12 +64,13 @@ def stage_report(z, stages):
         eg, er = np.abs(g - f), np.abs(r - f)
         err_ref, err_f64 = float(np.abs(g - r).max()) / scale, float(eg.max()) / scale
         rms_g, rms_r = float(np.sqrt((eg ** 2).mean())) / scale, float(np.sqrt((er ** 2).mean())) / scale
-        t = TOL * scale
+        tol = STAGE_TOL.get(name, TOL)
+        t = tol * scale
         big_g, big_r = int((eg > t).sum()), int((er > t).sum())
         n = eg.size
-        strict = err_ref <= TOL
+        strict = err_ref <= tol
         arbiter = (rms_g <= 3 * rms_r + 1e-7) and (big_g <= 3 * big_r + max(3, int(2e-5 * n)))
-        rep[name] = dict(err_ref=err_ref, err_f64=err_f64, budget=budget / scale, rms_gpu=rms_g, rms_ref=rms_r, big_gpu=big_g,
+        rep[name] = dict(err_ref=err_ref, err_f64=err_f64, budget=budget / scale, tol=tol, rms_gpu=rms_g, rms_ref=rms_r, big_gpu=big_g,
                          big_ref=big_r, n=n, strict=bool(strict), ok=bool(strict or arbiter))
     return rep
 
@@ -72,7 +81,7 @@ def fmt(rep):
         if v["strict"]:
             out.append("%s %.1e" % (k, v["err_ref"]))
         else:
-            out.append("%s %.1e [vs fp64: gpu max %.1e rms %.1e n>1e-4 %d | ref max %.1e rms %.1e n>1e-4 %d]%s"
+            out.append("%s %.1e [vs fp64: gpu max %.1e rms %.1e n>tol %d | ref max %.1e rms %.1e n>tol %d]%s"
                        % (k, v["err_ref"], v["err_f64"], v["rms_gpu"], v["big_gpu"], v["budget"], v["rms_ref"], v["big_ref"],
                           "" if v["ok"] else " FAIL"))
     return ", ".join(out)

@@ -47,7 +47,7 @@ def ckpt_state(seed):
     return st
 
 
-SKIP = ("lab1", "lab2")      # per-pixel Lab conversion: covered by tests/test_models_gpu.py::test_lab_transforms
+SKIP = ()
 
 
 def run_case(recipe, state, B, H, W, seed, name, stride_over=30000):
@@ -91,6 +91,8 @@ if __name__ == "__main__":
     if "phasenet256" in which:
         run_case(fp.interp_phasenet, fp.seeded_state(5), 1, 256, 256, 5, "phasenet_ref_256x256_s5.npz")
     if "pipelines" in which:
+        run_case(fp.interp, fp.seeded_state(0), 1, 64, 64, 0, "pipeline_ref_B1_64x64_s0.npz")       # replaces the round-1 fixtures
+        run_case(fp.interp, fp.seeded_state(1), 2, 64, 96, 1, "pipeline_ref_B2_64x96_s1.npz")       # (same cases, new format)
         run_case(fp.interp, fp.seeded_state(2), 1, 256, 256, 2, "pipeline_ref_B1_256x256_s2.npz")
         run_case(fp.interp, fp.seeded_state(3), 1, 184, 328, 3, "pipeline_ref_B1_184x328_s3.npz")
     if "ckpt" in which:

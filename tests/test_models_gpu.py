@@ -117,11 +117,11 @@ def _state_for(z, name, seed):
 
 
 def test_pipeline_vs_reference_golden(golden_dir, conv_backend):
-    """Full fusion recipe on the GPU vs the fixtures produced by the reference's own modules on CPU: 64x64 / 64x96 (round 1),
+    """Full fusion recipe on the GPU vs the fixtures produced by the reference's own modules on CPU: 64x64, 64x96 (batch 2),
     256x256 (training crop size: pyramid height 12, PhaseNet.layers[7] shared by four levels), 184x328 (Bluestein / Rader FFT
     lengths, AdaCoFNet reflect padding in both axes) and 256x256 with the SHIPPED phase_net.pt / fusion_net.pt.
-    Bound: 1e-4 max abs per stage against the reference (north star), or -- where the fixture carries the fp64 arbiter -- no
-    further from the fp64 result than twice the reference's own fp32 run (tests/_parity.py)."""
+    Bound: 1e-4 max abs on every image of the recipe against the reference (north star); the maps the recipe amplifies carry
+    their explicit gain; the fp64 arbiter of the fixture backs anything beyond (tests/_parity.py)."""
     from _parity import WrapAligner, fmt, psnr, stage_report
     from fvfi.pipeline import FusionPipeline
     files = sorted(glob.glob(os.path.join(golden_dir, "pipeline_*.npz")))
@@ -133,42 +133,26 @@ def test_pipeline_vs_reference_golden(golden_dir, conv_backend):
         pipe.load_state(_state_for(z, os.path.basename(f), seed))
         pipe.stages = {}
         rgb1, rgb2 = fp.seeded_frames(B, H, W, seed)
-        if "final__d64" in z.files:
-            raw = pipe(rgb1.cuda(), rgb2.cuda()).cpu().numpy()        # as shipped: whatever branch the GPU's own rounding picks
-            # parity run on the reference's branch of the wrapped phases (tests/_parity.py: WrapAligner)
-            pipe.filter_hook = al = WrapAligner(z)
-            pipe.stages = {}
-            out = pipe(rgb1.cuda(), rgb2.cuda())
-            rep = stage_report(z, pipe.stages)
-            print(conv_backend, os.path.basename(f), "wrap flips aligned: %d of %d phase values" % (al.flips, al.coefficients), fmt(rep))
-            bad = [k for k, v in rep.items() if not v["ok"]]
-            assert not bad, (bad, fmt(rep))
-            assert al.flips <= 1e-5 * al.coefficients                 # a handful of coefficients, not a systematic difference
-            st0 = int(z["final__stride"]) if "final__stride" in z.files else 1
-            print("  unaligned run: final max abs err %.2e, PSNR %.1f dB" % (float(np.abs(raw[..., ::st0, ::st0] - z["final"]).max()),
-                                                                            psnr(raw[..., ::st0, ::st0], z["final"])))
-            assert psnr(raw[..., ::st0, ::st0], z["final"]) >= 70
-            st = int(z["final__stride"]) if "final__stride" in z.files else 1
-            o = out.cpu().numpy()[..., ::st, ::st]
-            print("final: max abs err %.2e, PSNR(GPU vs reference) %.1f dB" % (float(np.abs(o - z["final"]).max()), psnr(o, z["final"])))
-            assert psnr(o, z["final"]) >= 70
-        else:
-            out = out.cpu().numpy()
-            errs = {k: float(np.abs(pipe.stages[k].cpu().numpy() - z[k]).max()) for k in z.files if k in pipe.stages}
-            print(conv_backend, os.path.basename(f), {k: "%.1e" % v for k, v in errs.items()})
-            assert errs["lab1"] <= 3e-6 and errs["ada_pred"] <= 1e-4 and errs["flow_var_map"] <= 1e-4
-            assert errs["lab_pred"] <= 1e-4 and errs["phase_pred"] <= 2e-4   # lab2rgb amplifies Lab error ~2x near black
-            assert errs["phase_uncertainty"] <= 1e-3 and errs["ada_uncertainty"] <= 5e-3   # x100 / x150 gains before the clamp
-            assert errs["base"] <= 2e-4
-            err = float(np.abs(out - z["final"]).max())
-            print("final max abs err %.2e, PSNR(GPU vs reference) %.1f dB" % (err, psnr(out, z["final"])))
-            # round-1 fixtures carry no arbiter: the recipe multiplies pyramid residuals by 100 / 150 before clamping them into the
-            # uncertainty maps (interpolate_twoframe.py:211,220,224); the round-2 fixtures above state the bound properly.
-            assert err <= 1e-3, err
-            assert psnr(out, z["final"]) >= 70
-            # host-buffer entry point == device path
-            host = pipe.interpolate_host(rgb1.pin_memory(), rgb2.pin_memory())
-            assert np.array_equal(host.numpy(), out)
+        raw = pipe(rgb1.cuda(), rgb2.cuda()).cpu().numpy()            # as shipped: whatever branch the GPU's own rounding picks
+        host = pipe.interpolate_host(rgb1.pin_memory(), rgb2.pin_memory())
+        assert np.array_equal(host.numpy(), raw)                      # host-buffer entry point == device path
+        # parity run on the reference's branch of the wrapped phases (oracle/wrap_align.py)
+        pipe.filter_hook = al = WrapAligner(z)
+        pipe.stages = {}
+        pipe(rgb1.cuda(), rgb2.cuda())
+        rep = stage_report(z, pipe.stages)
+        print(conv_backend, os.path.basename(f), "wrap flips aligned: %d of %d phase values;" % (al.flips, al.coefficients), fmt(rep))
+        bad = [k for k, v in rep.items() if not v["ok"]]
+        assert not bad, (bad, fmt(rep))
+        for k in ("lab1", "lab2", "ada_pred", "lab_pred", "phase_pred", "base", "final"):
+            if "_ckpt_" in f and k in ("lab_pred", "phase_pred"):
+                continue      # shipped phase_net.pt: the reference's own fp32 run is ~1e-4 from fp64 at some inputs -> arbiter
+            assert rep[k]["strict"], (k, fmt(rep))                    # the north-star bound itself on every image of the recipe
+        assert al.flips <= 1e-5 * al.coefficients                     # a handful of coefficients, not a systematic difference
+        st0 = int(z["final__stride"]) if "final__stride" in z.files else 1
+        print("  unaligned run: final max abs err %.2e, PSNR %.1f dB" % (float(np.abs(raw[..., ::st0, ::st0] - z["final"]).max()),
+                                                                        psnr(raw[..., ::st0, ::st0], z["final"])))
+        assert psnr(raw[..., ::st0, ::st0], z["final"]) >= 70
 
 
 @pytest.mark.parametrize("fused", [True, False])
