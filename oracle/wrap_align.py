@@ -10,14 +10,18 @@ perturbation without the flips moves it by 3e-7.
 
 For a meaningful comparison the parity runs evaluate the GPU pipeline ON THE REFERENCE'S BRANCH: ``WrapAligner`` is installed as
 ``FusionPipeline.filter_hook``; it knows, per decomposition call of the recipe ("phasenet", "uncertainty"), the reference's phase at
-every coefficient within ``WINDOW`` of +-pi, and where the GPU phase of such a coefficient has the other sign (differs by ~2 pi) it
-is replaced by the reference's value.  Nothing else is touched; ``flips`` counts the replaced values, ``coefficients`` all phase
-values seen."""
+every coefficient within a window of +-pi, and where the GPU phase of such a coefficient lies on the other side of the cut (differs
+by more than 3 rad) it is moved by 2 pi onto the reference's side -- the value itself is kept, only the branch changes.  Nothing
+else is touched; ``flips`` counts the moved values, ``coefficients`` all phase values seen."""
 import math
 
 import numpy as np
 
-WINDOW = 0.05       # radians from +-pi: far wider than any rounding-level phase difference of a coefficient that can flip
+# radians from +-pi.  "phasenet": inputs agree to 3e-7, a coefficient that can flip is within rounding of the cut.  "uncertainty":
+# the decomposed images are the recipe's own intermediate results (agreeing to ~1e-5), weak coefficients of the coarse levels move
+# further; only the six coarsest levels are read there (src/train/utils.py:282-320 with use_levels = 6), so a wide window is cheap.
+WINDOW = {"phasenet": 0.05, "uncertainty": 1.0}
+UNCERTAINTY_LEVELS = 6
 
 
 def wrap_lists(decomps):
@@ -25,9 +29,12 @@ def wrap_lists(decomps):
     the coefficients within WINDOW of +-pi (what a fixture stores)."""
     out = {}
     for tag, vals in decomps.items():
+        L = len(vals.phase)
         for l, p in enumerate(vals.phase):
+            if tag == "uncertainty" and l < L - UNCERTAINTY_LEVELS:
+                continue
             flat = np.asarray(p.detach().cpu().numpy(), dtype=np.float32).reshape(-1)
-            idx = np.nonzero(np.abs(flat) > math.pi - WINDOW)[0].astype(np.int32)
+            idx = np.nonzero(np.abs(flat) > math.pi - WINDOW.get(tag, 0.05))[0].astype(np.int32)
             out["wrap_%s_%d_idx" % (tag, l)] = idx
             out["wrap_%s_%d_val" % (tag, l)] = flat[idx]
     return out
@@ -63,6 +70,6 @@ class WrapAligner:
             got = flat[idx]
             flip = (got - ref).abs() > 3.0
             self.flips += int(flip.sum())
-            flat[idx[flip]] = ref[flip]
+            flat[idx[flip]] = got[flip] + 2 * math.pi * torch.sign(ref[flip] - got[flip])
             phase[l] = flat.reshape(p.shape)
         return vals._replace(phase=phase)

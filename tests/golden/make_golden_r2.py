@@ -16,7 +16,7 @@ The oracle restatement (fp32) is asserted equal to the reference modules on ever
                                      58, 82, 116, 164, 232) and whose AdaCoFNet input is reflect-padded to /32 in both axes.
 * pipeline_ckpt_B1_256x256_s4.npz    full recipe with the SHIPPED checkpoints src/phase_net/phase_net.pt and
                                      src/fusion_net/fusion_net.pt (AdaCoF: seeded random init -- its checkpoint is a missing LFS blob).
-``wrap_<call>_<level>_idx/_val``: the reference's phase at every coefficient within 0.05 rad of +-pi, per decomposition call of the
+``wrap_<call>_<level>_idx/_val``: the reference's phase at every coefficient within a window of +-pi, per decomposition call of the
 recipe -- the branch the parity runs align the GPU's wrapped phases to (oracle/wrap_align.py explains why).
 Stages above 30k elements are stored subsampled in the two image axes (stride in ``<k>__stride``); ``<k>__budget`` is
 max|k - fp64| over ALL elements.  Inputs are regenerated from the seed.
@@ -79,7 +79,7 @@ def run_case(recipe, state, B, H, W, seed, name, stride_over=30000):
     # the reference's branch at the coefficients within rounding of the negative real axis (oracle/wrap_align.py)
     wl = wrap_lists(dec)
     keep.update(wl)
-    print(name, "coefficients within %.2f rad of +-pi: %d" % (0.05, sum(v.size for k, v in wl.items() if k.endswith("_idx"))))
+    print(name, "coefficients stored for the branch alignment: %d" % sum(v.size for k, v in wl.items() if k.endswith("_idx")))
     print(name, "reference fp32 vs fp64 arbiter:", {k: "%.1e" % v for k, v in budget.items()})
     np.savez_compressed(os.path.join(HERE, name), **keep)
     print("wrote", name, "%.1f MB, %.0f s" % (os.path.getsize(os.path.join(HERE, name)) / 1e6, time.time() - t0))
