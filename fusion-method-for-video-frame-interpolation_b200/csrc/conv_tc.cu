@@ -12,9 +12,10 @@
 //
 // Used for the PhaseNet / KernelEstimation / FusionNet convolutions (the only dense contractions on the path;
 // reference: torch.nn.Conv2d -> cuDNN, src/phase_net/phase_net.py:190-199, src/fusion_net/fusion_adacofnet.py:19-83,
-// src/fusion_net/fusion_net.py:24-36).  Plain TF32 (10-bit mantissa) does not hold the 1e-4 output bound through
-// ~30 layers, so every product a*b is formed as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with a_hi = rna_tf32(a),
-// a_lo = a - a_hi (exact), three tcgen05.mma.kind::tf32 per K-step accumulating in fp32 in TMEM.
+// src/fusion_net/fusion_net.py:24-36).  A single reduced-precision product (TF32: 10-bit mantissa) does not hold the 1e-4 output
+// bound through ~30 layers, so every product a*b is formed as a_lo*b_hi + a_hi*b_lo + a_hi*b_hi from the hi/lo halves of the chosen
+// split (default: fp16 halves, tcgen05.mma.kind::f16; PREC_TF32X3: tf32 halves, kind::tf32), three MMAs per K-step accumulating in
+// fp32 in TMEM; the dropped a_lo*b_lo term is 2^-22 relative.
 //
 // Formulation (stride 1, "same" padding, zero or reflect):
 //   activations NHWC (torch channels_last), GEMM M = output pixels, N = Cout, K = taps x Cin.

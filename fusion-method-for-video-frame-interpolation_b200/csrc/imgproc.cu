@@ -330,7 +330,8 @@ __device__ __forceinline__ void stg256f(float* p, const float* v) {
 template <int VEC>
 __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi,
                                                                    int Wi, int Ho, int Wo, int C, int ldx, int ldy,
-                                                                   float sy, float sx, int align_corners) {
+                                                                   float sy, float sx, int align_corners,
+                                                                   const float* __restrict__ addend, int lda, int relu_in) {
     const unsigned cg_n = (unsigned)(C + VEC - 1) / VEC;
     const unsigned total = (unsigned)Ho * (unsigned)Wo * cg_n;      // per image; < 2^32 checked by the launcher
     const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -371,8 +372,26 @@ __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* 
     } else {
         a[0] = __ldg(p00); b[0] = __ldg(p01); c[0] = __ldg(p10); d[0] = __ldg(p11);
     }
+    if (relu_in) {                      // Upsample(ReLU(x)): the activation applies to the source samples (fusion_net.py:61)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { a[i] = fmaxf(a[i], 0.f); b[i] = fmaxf(b[i], 0.f); c[i] = fmaxf(c[i], 0.f); d[i] = fmaxf(d[i], 0.f); }
+    }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+    if (addend) {                       // + skip connection (fusion_net.py:62)
+        const float* ap = addend + ((size_t)n * Ho * Wo + p) * lda + ch;
+        float e[VEC];
+        if (VEC == 8) {
+            ldg256f(ap, e);
+        } else if (VEC == 4) {
+            const float4 e4 = __ldg((const float4*)ap);
+            e[0] = e4.x; e[1] = e4.y; e[2] = e4.z; e[3] = e4.w;
+        } else {
+            e[0] = __ldg(ap);
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] += e[i];
+    }
     if (VEC == 8) stg256f(dst, o);
     else if (VEC == 4) *(float4*)dst = make_float4(o[0], o[1], o[2], o[3]);
     else dst[0] = o[0];
@@ -574,8 +593,17 @@ extern "C" int fvfi_nchw_to_nhwc_slice(const float* x, float* y, int y_pixel_str
 
 extern "C" int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi,
                                          int Ho, int Wo, int C, int align_corners, void* stream) {
+    return fvfi_resize_bilinear_nhwc_fused(x, x_pixel_stride, nullptr, 0, y, y_pixel_stride, B, Hi, Wi, Ho, Wo, C, align_corners, 0, stream);
+}
+
+extern "C" int fvfi_resize_bilinear_nhwc_fused(const float* x, int x_pixel_stride, const float* addend, int addend_pixel_stride,
+                                               float* y, int y_pixel_stride, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                                               int align_corners, int relu_input, void* stream) {
     FVFI_CHECK_ARG(x && y && B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0 && B <= 65535, "resize_bilinear: bad argument");
     FVFI_CHECK_ARG(x_pixel_stride >= C && y_pixel_stride >= C, "resize_bilinear: pixel stride smaller than channel count");
+    FVFI_CHECK_ARG(!addend || addend_pixel_stride >= C, "resize_bilinear: addend pixel stride smaller than channel count");
+    const size_t addbits = addend ? ((size_t)addend | ((size_t)addend_pixel_stride * 4)) : 0;
+    const int lda = addend_pixel_stride, relu_in = relu_input ? 1 : 0;
     float sy, sx;
     if (align_corners) {
         sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
@@ -584,7 +612,7 @@ extern "C" int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, flo
         sy = (float)Hi / (float)Ho;
         sx = (float)Wi / (float)Wo;
     }
-    const bool a32 = ((((size_t)x) | ((size_t)y)) & 31) == 0, a16 = ((((size_t)x) | ((size_t)y)) & 15) == 0;
+    const bool a32 = ((((size_t)x) | ((size_t)y) | addbits) & 31) == 0, a16 = ((((size_t)x) | ((size_t)y) | addbits) & 15) == 0;
     const int vec = (a32 && (C & 7) == 0 && (x_pixel_stride & 7) == 0 && (y_pixel_stride & 7) == 0) ? 8
                   : (a16 && (C & 3) == 0 && (x_pixel_stride & 3) == 0 && (y_pixel_stride & 3) == 0) ? 4 : 1;
     const size_t total = (size_t)Ho * Wo * ((C + vec - 1) / vec);
@@ -592,11 +620,11 @@ extern "C" int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, flo
     dim3 grid((unsigned)((total + 255) / 256), B);
     cudaStream_t s = (cudaStream_t)stream;
     if (vec == 8)
-        fvfi::resize_bilinear_nhwc_kernel<8><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners);
+        fvfi::resize_bilinear_nhwc_kernel<8><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners, addend, lda, relu_in);
     else if (vec == 4)
-        fvfi::resize_bilinear_nhwc_kernel<4><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners);
+        fvfi::resize_bilinear_nhwc_kernel<4><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners, addend, lda, relu_in);
     else
-        fvfi::resize_bilinear_nhwc_kernel<1><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners);
+        fvfi::resize_bilinear_nhwc_kernel<1><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners, addend, lda, relu_in);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }

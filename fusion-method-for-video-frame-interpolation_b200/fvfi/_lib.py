@@ -52,6 +52,7 @@ _PROTOS = {
     "fvfi_adacofnet_prep": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_fp]),
     "fvfi_avg_pool2_nhwc": (c_int, [c_fp, c_int, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "fvfi_resize_bilinear_nhwc": (c_int, [c_fp, c_int, c_fp, c_int] + [c_int] * 7 + [c_fp]),
+    "fvfi_resize_bilinear_nhwc_fused": (c_int, [c_fp, c_int, c_fp, c_int, c_fp, c_int] + [c_int] * 8 + [c_fp]),
     "fvfi_adacof_forward_host": (c_int, [c_fp] * 5 + [c_int] * 8),
     "fvfi_adacof_backward_host": (c_int, [c_fp] * 8 + [c_int] * 8),
     "fvfi_pyr_plan_create": (c_int, [c_int, c_int, c_int, c_int, ctypes.c_double, ctypes.POINTER(c_fp)]),

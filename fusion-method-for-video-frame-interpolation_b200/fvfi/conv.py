@@ -223,19 +223,27 @@ def upsample2_conv3x3_single(conv, x, act=None):
     return out
 
 
-def resize_bilinear(x, size, align_corners, out=None, out_channel_offset=0):
+def resize_bilinear(x, size, align_corners, out=None, out_channel_offset=0, relu_input=False, add=None):
     """F.interpolate(x, size=size, mode='bilinear', align_corners=align_corners) on NHWC storage.  ``out`` may be a
-    wider channels_last buffer; the result is written to channels [out_channel_offset, out_channel_offset + C)."""
+    wider channels_last buffer; the result is written to channels [out_channel_offset, out_channel_offset + C).
+    ``relu_input``: interpolate max(x, 0); ``add`` ([B,C,Ho,Wo]): added to the result -- FusionNet's decoder step
+    ``Upsample(ReLU(x)) + skip`` (fusion_net.py:60-62) as one pass."""
     B, C, Hi, Wi = x.shape
     Ho, Wo = int(size[0]), int(size[1])
     xc = to_nhwc(x.float())
     if out is None:
         out = torch.empty((B, C, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
     assert out.stride(1) == 1 and out.shape[2] == Ho and out.shape[3] == Wo
+    ac = None
+    if add is not None:
+        assert tuple(add.shape) == (B, C, Ho, Wo)
+        ac = to_nhwc(add.float())
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().fvfi_resize_bilinear_nhwc(xc.data_ptr(), xc.stride(3), out.data_ptr() + 4 * out_channel_offset,
-                                                        out.stride(3), B, Hi, Wi, Ho, Wo, C, 1 if align_corners else 0,
-                                                        _lib.stream_ptr()))
+        _lib.check(_lib.lib().fvfi_resize_bilinear_nhwc_fused(xc.data_ptr(), xc.stride(3), None if ac is None else ac.data_ptr(),
+                                                              0 if ac is None else ac.stride(3),
+                                                              out.data_ptr() + 4 * out_channel_offset, out.stride(3), B, Hi, Wi, Ho,
+                                                              Wo, C, 1 if align_corners else 0, 1 if relu_input else 0,
+                                                              _lib.stream_ptr()))
     return out
 
 

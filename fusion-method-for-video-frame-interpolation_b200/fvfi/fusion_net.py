@@ -75,9 +75,8 @@ class FusionNet(torch.nn.Module):
                 x = tc.max_pool2(x)                                   # nn.MaxPool2d(2, stride=2) on NHWC, 256-bit accesses
             x = tc.conv_module(self.bottleneck_layer, x, "relu")    # ReLU of the first decoder step folded in
             for i, (layer, s) in enumerate(zip(self.decoder_layers, skip[::-1])):
-                x = x if i == 0 else self.relu(x)
-                x = tc.resize_bilinear(x, (x.shape[2] * 2, x.shape[3] * 2), False)
-                x = x + s
+                # Upsample(ReLU(x)) + skip (fusion_net.py:60-62) in one pass
+                x = tc.resize_bilinear(x, (x.shape[2] * 2, x.shape[3] * 2), False, relu_input=i > 0, add=s)
                 x = tc.conv_module(layer, x, None)
             x = x.contiguous()
         else:

@@ -107,8 +107,8 @@ class Pyramid:
                                                      ptr_array(amp), low.data_ptr(), amp_max.data_ptr(),
                                                      plan.workspace(N).data_ptr(), _lib.stream_ptr()))
         self.last_amp_max = amp_max
-        if high is None:
-            high = torch.zeros((N, 1, H, W), dtype=torch.float32, device=img.device)
+        if high is None:     # not computed: a stride-0 view of one zero (shape-compatible with the reference's layout, no storage)
+            high = torch.zeros((1,), dtype=torch.float32, device=img.device).expand(N, 1, H, W)
         return DecompValues(high_level=high, phase=phase, amplitude=amp, low_level=low)
 
     def inv_filter(self, vals):

@@ -178,6 +178,11 @@ int fvfi_phasenet_outputs(const float* pred, int pred_pixel_stride, const float*
  * x [B,Hi,Wi,C] with x_pixel_stride floats per pixel -> y [B,Ho,Wo,C] (may be a channel slice: y_pixel_stride). */
 int fvfi_resize_bilinear_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixel_stride, int B, int Hi, int Wi,
                               int Ho, int Wo, int C, int align_corners, void* stream);
+/* The decoder step of FusionNet in one pass (src/fusion_net/fusion_net.py:60-62: x = Upsample(ReLU(x)); x = x + skip):
+ * y = resize(relu_input ? max(x, 0) : x) + addend (addend [B,Ho,Wo,C] NHWC with its own pixel stride, or NULL). */
+int fvfi_resize_bilinear_nhwc_fused(const float* x, int x_pixel_stride, const float* addend, int addend_pixel_stride, float* y,
+                                    int y_pixel_stride, int B, int Hi, int Wi, int Ho, int Wo, int C, int align_corners,
+                                    int relu_input, void* stream);
 
 /* nn.AvgPool2d(kernel_size=2, stride=2) on NHWC tensors (KernelEstimation's encoder, src/fusion_net/fusion_adacofnet.py:62-70,
  * 111-123): x [B,Hi,Wi,C] -> y [B,Hi/2,Wi/2,C]. */
