@@ -9,6 +9,13 @@
 //     input and output are both in natural order (coalesced global traffic); columns use an IN-PLACE
 //     decimation-in-frequency network whose digit-reversed output order is free (a column pass writes 64-byte row
 //     segments, their order does not matter) -- half the shared memory, twice the resident CTAs.
+//   * lengths n = r * p with ONE prime factor p > 19 whose p - 1 is smooth (97, 191, 241, 61, 43, 31, 23 ... -- every such
+//     length of the 1080p / 4K pyramids): Cooley-Tukey split into r interleaved length-p DFTs (ordinary in-place DIF stages
+//     for the radices of r), each done by RADER's algorithm: a length-p DFT is y0 plus a cyclic convolution of length p - 1
+//     of the inputs taken in the order g^q (g a primitive root of p) with the constant sequence W_p^(g^-q).  The convolution
+//     runs on the same stage code as everything else: one permuting copy into the second buffer, in-place DIF of the
+//     (p-1)-point sub-sequences, multiply by the precomputed spectrum (stored in DIF order, DC bin carries y0), in-place
+//     DIT back -- no zero padding, all passes over n points instead of Bluestein's M >= 2n - 1.
 //   * other lengths: Bluestein (chirp-z) on a smooth length M >= 2n-1 chosen by the plan: chirp, in-place DIF,
 //     multiply by the precomputed spectrum of the chirp filter (stored in DIF order, pre-scaled by 1/M), in-place
 //     DIT (digit-reversed in, natural out), chirp.  No permutation pass anywhere, and no extra pass either: the
@@ -36,18 +43,26 @@ constexpr int FFT_MAX_STAGES = 8;
 
 struct FftPlan {
     int n;                       // logical transform length
-    int M;                       // machine length: n (direct) or the Bluestein convolution length
+    int M;                       // machine length: n (direct, Rader) or the Bluestein convolution length
+    int alloc;                   // slots per sequence the caller provides: M, or 2n for Rader in the column layout (two halves)
     int nfac;
     int bluestein;
+    int rader;                   // 1: n = rr * rp, stages [0, nouter) are DIF stages on length n, stages [nouter, nfac) the sub-FFT of length rq
+    int rr, rp, rq, nouter;      // rq = rp - 1
     int pad;                     // sequence-major layout: 1 = skew i + (i >> 4) (smallest butterfly stride is even)
-    int fac[FFT_MAX_STAGES];     // radices in network order (product = M)
+    int fac[FFT_MAX_STAGES];     // radices in network order (product = M; Rader: product = rr * rq)
     int sub[FFT_MAX_STAGES];     // DIF/DIT: butterfly stride m_s (block length = fac*sub); Stockham: Ns (product of earlier radices)
     unsigned mag_sub[FFT_MAX_STAGES];    // ceil(2^32 / sub)
-    unsigned mag_items[FFT_MAX_STAGES];  // ceil(2^32 / (M / fac))
+    unsigned mag_items[FFT_MAX_STAGES];  // ceil(2^32 / (M / fac));  Rader sub stages: ceil(2^32 / (rq / fac))
+    unsigned mag_ritems[FFT_MAX_STAGES]; // Rader sub stages: ceil(2^32 / (rr * rq / fac))
+    unsigned mag_rp;             // ceil(2^32 / rp)
     const float2* tw;            // W_M^t = exp(-2 pi i t / M), t < M
-    const unsigned short* perm;  // direct DIF: natural index held at position p after the network (null: natural)
+    const unsigned short* perm;  // direct DIF / Rader: natural index held at position p after the network (null: natural)
     const float2* chirp;         // Bluestein: exp(-i pi k^2 / n), k < n
-    const float2* bhat;          // Bluestein: FFT_M(chirp filter) / M in DIF (digit-reversed) order
+    const float2* bhat;          // Bluestein: FFT_M(chirp filter) / M in DIF (digit-reversed) order;  Rader: FFT_rq(W_rp^(g^-t)) / rq, DIF order
+    const float2* tw2;           // Rader: W_rq^t, t < rq
+    const unsigned short* pin;   // Rader: slot of input j inside its length-rp block (0 for j = 0, 1 + dlog_g(j) otherwise)
+    const unsigned short* inv;   // Rader: position of natural index k in the result (sequence-major layout reads in natural order)
 };
 
 struct FftCtx { int tid, nthr; };
@@ -326,6 +341,72 @@ FVFI_HD void fft_stage_impl(const FftPlan& P, int s, const float2* in, float2* o
     }
 }
 
+// Rader sub-FFT stage: in-place DIF / DIT butterflies on the (p-1)-point sub-sequences that sit at offset 1 of every length-p
+// block of `buf` (rr blocks per sequence).  POST (last DIF stage): multiply by the convolution spectrum, fold y0 (slot 0 of the
+// block) into the DC bin, leave conj(X[0]) in slot 0, conjugate (the inverse transform is conj -> forward DIT -> conj, the last
+// conj being applied by fft_get).
+template <int R, int KIND, bool COL>
+FVFI_HD void fft_stage_sub_impl(const FftPlan& P, int s, float2* buf, int batch, int ctshift, int pitch, const float2* post,
+                                FftCtx cx) {
+    const int rq = P.rq, rp = P.rp, qitems = rq / R, items = P.rr * qitems, total = batch * items;
+    const int m = P.sub[s];
+    const unsigned mag_sub = P.mag_sub[s], mag_q = P.mag_items[s], mag_items = P.mag_ritems[s];
+    const float2* tw = P.tw2;
+    for (int q = cx.tid; q < total; q += cx.nthr) {
+        int b, t;
+        if (COL) {
+            t = q >> ctshift;
+            b = q & ((1 << ctshift) - 1);
+        } else {
+            b = (int)fast_div((unsigned)q, (unsigned)items, mag_items);
+            t = q - b * items;
+        }
+        const int blk = (int)fast_div((unsigned)t, (unsigned)qitems, mag_q);
+        const int tt = t - blk * qitems;
+        const int c = (int)fast_div((unsigned)tt, (unsigned)m, mag_sub);
+        const int j = tt - c * m;
+        const int base = c * R * m + j;                       // position inside the sub-sequence
+        const int a0 = fft_addr<COL>(b, blk * rp + 1 + base, ctshift, pitch, 0);
+        const int st = COL ? (m << ctshift) : m;
+        float2 v[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) v[u] = buf[a0 + u * st];
+        if (KIND == FFT_DIT && m > 1) twiddle_powers<R>(v, ldg_(tw + j * (rq / (R * m))));
+        dft(v, Radix<R>());
+        if (KIND == FFT_DIF && m > 1) twiddle_powers<R>(v, ldg_(tw + j * (rq / (R * m))));
+        if (KIND == FFT_DIF && post) {
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                float2 w = cmul(v[u], ldg_(post + base + u * m));
+                if (u == 0 && base == 0) {                    // DC bin of this block: X[0] = y0 + sum, and y0 rides on every output
+                    const int a00 = fft_addr<COL>(b, blk * rp, ctshift, pitch, 0);
+                    const float2 y0 = buf[a00];
+                    buf[a00] = cconj(cadd(y0, v[0]));
+                    w = cadd(w, y0);
+                }
+                v[u] = cconj(w);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < R; ++u) buf[a0 + u * st] = v[u];
+    }
+}
+
+// Rader: copy the natural-order blocks of `src` into `dst` in generator order (slot pin[j] of the same block).
+template <bool COL>
+FVFI_HD void fft_rader_permute(const FftPlan& P, const float2* src, float2* dst, int batch, int ctshift, int pitch, FftCtx cx) {
+    const int n = P.n, rp = P.rp, total = batch * n;
+    const unsigned mag_rp = P.mag_rp;
+    const unsigned short* pin = P.pin;
+    for (int q = cx.tid; q < total; q += cx.nthr) {
+        int b, i;
+        if (COL) { i = q >> ctshift; b = q & ((1 << ctshift) - 1); } else { b = q / n; i = q - b * n; }
+        const int blk = (int)fast_div((unsigned)i, (unsigned)rp, mag_rp);
+        const int j = i - blk * rp;
+        dst[fft_addr<COL>(b, blk * rp + (int)ldg_(pin + j), ctshift, pitch, 0)] = src[fft_addr<COL>(b, i, ctshift, pitch, 0)];
+    }
+}
+
 #if defined(__CUDA_ARCH__)
 #define FVFI_STAGE_ATTR __device__ __noinline__
 #else
@@ -337,6 +418,25 @@ template <int R, int KIND, bool COL, bool PAD>
 FVFI_STAGE_ATTR void fft_stage(const FftPlan* P, int s, const float2* in, float2* out, int batch, int ctshift, int pitch,
                                const float2* post, int tid, int nthr) {
     fft_stage_impl<R, KIND, COL, PAD>(*P, s, in, out, batch, ctshift, pitch, post, FftCtx{tid, nthr});
+}
+
+template <int R, int KIND, bool COL>
+FVFI_STAGE_ATTR void fft_stage_sub(const FftPlan* P, int s, float2* buf, int batch, int ctshift, int pitch, const float2* post,
+                                   int tid, int nthr) {
+    fft_stage_sub_impl<R, KIND, COL>(*P, s, buf, batch, ctshift, pitch, post, FftCtx{tid, nthr});
+}
+
+template <int KIND, bool COL>
+FVFI_HD void fft_run_stage_sub(const FftPlan& P, int s, float2* buf, int batch, int ctshift, int pitch, const float2* post,
+                               FftCtx cx) {
+#define FVFI_CASE(R) \
+    case R: fft_stage_sub<R, KIND, COL>(&P, s, buf, batch, ctshift, pitch, post, cx.tid, cx.nthr); break;
+    switch (P.fac[s]) {
+        FVFI_CASE(2) FVFI_CASE(3) FVFI_CASE(4) FVFI_CASE(5) FVFI_CASE(6) FVFI_CASE(7) FVFI_CASE(8) FVFI_CASE(9)
+        FVFI_CASE(10) FVFI_CASE(11) FVFI_CASE(12) FVFI_CASE(13) FVFI_CASE(15) FVFI_CASE(16) FVFI_CASE(17) FVFI_CASE(19)
+        default: break;
+    }
+#undef FVFI_CASE
 }
 
 template <int KIND, bool COL>
@@ -369,10 +469,14 @@ struct FftResult {
 // What fft_put / fft_get need from a plan, read ONCE per kernel (the plan lives in global memory: re-reading `bluestein` / `pad`
 // per element put an L1 round trip on every load and store of the prologue / epilogue loops).
 struct FftIO {
-    int bluestein, pad;
+    int bluestein, pad, rader;
     const float2* chirp;
+    const unsigned short* inv;
 };
-FVFI_HD FftIO fft_io(const FftPlan& P) { return FftIO{P.bluestein, P.pad, P.chirp}; }
+FVFI_HD FftIO fft_io(const FftPlan& P) { return FftIO{P.bluestein, P.pad, P.rader, P.chirp, P.inv}; }
+
+// Pitch (floats2 per sequence) of the sequence-major layout for this plan.
+FVFI_HD int fft_pitch(const FftPlan& P) { return fft_row_pitch(P.alloc, P.pad); }
 
 // Callers WRITE their input through fft_put (Bluestein: the chirp is applied on the way in) ...
 template <bool COL>
@@ -384,6 +488,10 @@ FVFI_HD void fft_put(const FftIO& io, float2* buf, int b, int i, float2 v, int c
 // of the value is R.perm ? R.perm[pos] : pos.
 template <bool COL>
 FVFI_HD float2 fft_get(const FftIO& io, const FftResult& R, int b, int pos, int ctshift, int pitch) {
+    if (io.rader) {      // result sits in generator order: the column layout walks positions (R.perm names them), rows look them up
+        const int p2 = COL ? pos : (int)ldg_(io.inv + pos);
+        return cconj(R.buf[fft_addr<COL>(b, p2, ctshift, pitch, 0)]);
+    }
     const float2 v = R.buf[fft_addr<COL>(b, pos, ctshift, pitch, io.pad)];
     return io.bluestein ? cmul(cconj(v), ldg_(io.chirp + pos)) : v;
 }
@@ -396,6 +504,24 @@ template <bool COL>
 FVFI_HD FftResult fft_forward(const FftPlan& P, float2* a, float2* b, int batch, int ctshift, int pitch, bool inplace,
                               FftCtx cx) {
     const int M = P.M, n = P.n, pad = P.pad;
+    if (P.rader) {
+        for (int s = 0; s < P.nouter; ++s) {                 // Cooley-Tukey stages for the smooth part r of n = r * p
+            fft_run_stage<FFT_DIF, COL>(P, s, a, a, batch, ctshift, pitch, nullptr, cx);
+            fft_sync();
+        }
+        float2* w = COL ? a + ((size_t)n << ctshift) : b;    // second half (column tile) / second buffer (rows)
+        fft_rader_permute<COL>(P, a, w, batch, ctshift, pitch, cx);
+        fft_sync();
+        for (int s = P.nouter; s < P.nfac; ++s) {
+            fft_run_stage_sub<FFT_DIF, COL>(P, s, w, batch, ctshift, pitch, s == P.nfac - 1 ? P.bhat : nullptr, cx);
+            fft_sync();
+        }
+        for (int s = P.nfac - 1; s >= P.nouter; --s) {
+            fft_run_stage_sub<FFT_DIT, COL>(P, s, w, batch, ctshift, pitch, nullptr, cx);
+            fft_sync();
+        }
+        return FftResult{w, P.perm};
+    }
     if (P.bluestein) {
         const int tail = M - n;                              // zero padding of the convolution
         for (int q = cx.tid; q < batch * tail; q += cx.nthr) {

@@ -12,9 +12,15 @@ namespace fvfi {
 
 struct HostFftPlan {
     FftPlan p{};                       // pointers are filled in by whoever owns the storage (device upload or host test)
-    std::vector<float2> tw, chirp, bhat;
-    std::vector<unsigned short> perm;
+    std::vector<float2> tw, chirp, bhat, tw2;
+    std::vector<unsigned short> perm, pin, inv;
 };
+
+// Test / A-B switch: 0 makes every non-smooth length use Bluestein (round-1 behaviour).
+inline int& fft_rader_enabled() {
+    static int on = 1;
+    return on;
+}
 
 // Split n into the radices the engine implements; false if n has a prime factor > 19.
 inline bool fft_radices(int n, std::vector<int>& out) {
@@ -87,12 +93,154 @@ inline void fft_host_dft(std::vector<std::complex<double>>& x) {
 
 inline unsigned fft_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) + d - 1) / d); }
 
+inline long long fft_powmod(long long b, long long e, long long m) {
+    long long r = 1 % m;
+    b %= m;
+    while (e > 0) {
+        if (e & 1) r = r * b % m;
+        b = b * b % m;
+        e >>= 1;
+    }
+    return r;
+}
+
+// n = r * p with exactly one prime factor p > 19 (to the first power), r and p - 1 both products of the implemented radices.
+inline bool fft_rader_split(int n, int* r_out, int* p_out) {
+    int rem = n;
+    for (int q : {2, 3, 5, 7, 11, 13, 17, 19})
+        while (rem % q == 0) rem /= q;
+    if (rem <= 19) return false;                       // smooth (handled directly) -- or nothing left
+    for (int d = 2; (long long)d * d <= rem; ++d)
+        if (rem % d == 0) return false;                // more than one large prime factor (or a square): Bluestein
+    const int p = rem, r = n / p;
+    std::vector<int> t;
+    if (!fft_radices(r, t) || !fft_radices(p - 1, t)) return false;
+    *r_out = r;
+    *p_out = p;
+    return true;
+}
+
+// Rader plan (see fft_engine.cuh): outer DIF stages for r, sub-FFT stages for q = p - 1, generator-order tables.
+inline bool fft_make_rader_plan(int n, int r, int pr, bool column_layout, HostFftPlan& H) {
+    FftPlan& p = H.p;
+    const int q = pr - 1;
+    std::vector<int> rad_r, rad_q;
+    if (!fft_radices(r, rad_r) || !fft_radices(q, rad_q)) return false;
+    if (r == 1) rad_r.clear();
+    if ((int)(rad_r.size() + rad_q.size()) > FFT_MAX_STAGES || n > 32767) return false;
+    p.M = n;
+    p.alloc = column_layout ? 2 * n : n;
+    p.bluestein = 0;
+    p.rader = 1;
+    p.rr = r; p.rp = pr; p.rq = q;
+    p.nouter = (int)rad_r.size();
+    p.nfac = p.nouter + (int)rad_q.size();
+    p.pad = 0;
+    p.mag_rp = fft_magic((unsigned)pr);
+    int prod = 1;
+    for (int s = 0; s < p.nouter; ++s) {               // DIF on length n
+        p.fac[s] = rad_r[s];
+        prod *= rad_r[s];
+        p.sub[s] = n / prod;
+        p.mag_sub[s] = fft_magic((unsigned)p.sub[s]);
+        p.mag_items[s] = fft_magic((unsigned)(n / rad_r[s]));
+    }
+    prod = 1;
+    for (int i = 0; i < (int)rad_q.size(); ++i) {      // DIF / DIT on length q
+        const int s = p.nouter + i;
+        p.fac[s] = rad_q[i];
+        prod *= rad_q[i];
+        p.sub[s] = q / prod;
+        p.mag_sub[s] = fft_magic((unsigned)p.sub[s]);
+        p.mag_items[s] = fft_magic((unsigned)(q / rad_q[i]));
+        p.mag_ritems[s] = fft_magic((unsigned)(r * (q / rad_q[i])));
+    }
+    H.tw.resize(n);
+    for (int t = 0; t < n; ++t) {
+        const double a = -2.0 * M_PI * (double)t / (double)n;
+        H.tw[t] = make_float2((float)cos(a), (float)sin(a));
+    }
+    H.tw2.resize(q);
+    for (int t = 0; t < q; ++t) {
+        const double a = -2.0 * M_PI * (double)t / (double)q;
+        H.tw2[t] = make_float2((float)cos(a), (float)sin(a));
+    }
+    // primitive root g of pr, powers and discrete logarithms
+    int g = 0;
+    {
+        std::vector<int> pf;
+        int rem = q;
+        for (int d = 2; d * d <= rem; ++d)
+            if (rem % d == 0) { pf.push_back(d); while (rem % d == 0) rem /= d; }
+        if (rem > 1) pf.push_back(rem);
+        for (int c = 2; c < pr && !g; ++c) {
+            bool ok = true;
+            for (int f : pf) ok = ok && fft_powmod(c, q / f, pr) != 1;
+            if (ok) g = c;
+        }
+        if (!g) return false;
+    }
+    std::vector<int> gpow(q), dlog(pr, 0);
+    for (int t = 0; t < q; ++t) { gpow[t] = (int)fft_powmod(g, t, pr); dlog[gpow[t]] = t; }
+    H.pin.assign(pr, 0);
+    for (int j = 1; j < pr; ++j) H.pin[j] = (unsigned short)(1 + dlog[j]);        // slot 1 + t holds y[g^t]
+    // digit reversal of the sub network (position -> natural bin of the q-point DFT)
+    std::vector<int> subperm(q);
+    for (int pos = 0; pos < q; ++pos) {
+        int rem = pos, k = 0, w = 1;
+        for (int s = p.nouter; s < p.nfac; ++s) {
+            const int d = rem / p.sub[s];
+            rem -= d * p.sub[s];
+            k += d * w;
+            w *= p.fac[s];
+        }
+        subperm[pos] = k;
+    }
+    // convolution kernel b[t] = W_p^(g^-t) = W_p^(g^((q - t) mod q)); spectrum / q in DIF order
+    std::vector<std::complex<double>> bk(q);
+    for (int t = 0; t < q; ++t) bk[t] = std::polar(1.0, -2.0 * M_PI * (double)gpow[(q - t) % q] / (double)pr);
+    fft_host_dft(bk);
+    H.bhat.resize(q);
+    for (int pos = 0; pos < q; ++pos) {
+        const std::complex<double> v = bk[subperm[pos]] / (double)q;
+        H.bhat[pos] = make_float2((float)v.real(), (float)v.imag());
+    }
+    // where every output lands: block position -> k1 (digits of the outer DIF network), slot -> k2; natural k = k1 + r * k2
+    H.perm.assign(n, 0);
+    H.inv.assign(n, 0);
+    for (int blk = 0; blk < r; ++blk) {
+        int rem = blk * pr, k1 = 0, w = 1;
+        for (int s = 0; s < p.nouter; ++s) {
+            const int d = rem / p.sub[s];
+            rem -= d * p.sub[s];
+            k1 += d * w;
+            w *= p.fac[s];
+        }
+        for (int slot = 0; slot < pr; ++slot) {
+            const int k2 = slot == 0 ? 0 : gpow[(q - (slot - 1)) % q];             // slot 1 + m holds X[g^-m]
+            const int k = k1 + r * k2;
+            H.perm[blk * pr + slot] = (unsigned short)k;
+            H.inv[k] = (unsigned short)(blk * pr + slot);
+        }
+    }
+    H.chirp.clear();
+    return true;
+}
+
 // Build the plan for length n.  stockham = true: out-of-place autosort order for direct lengths (rows).
 inline bool fft_make_plan(int n, bool stockham, HostFftPlan& H) {
     FftPlan& p = H.p;
     p = FftPlan{};
     p.n = n;
     std::vector<int> rad;
+    {
+        int rr = 0, rp = 0;
+        // `stockham` is what the callers pass for the sequence-major (row) layout; the column layout needs the two halves
+        if (fft_rader_enabled() && !fft_radices(n, rad) && fft_rader_split(n, &rr, &rp) && fft_make_rader_plan(n, rr, rp, !stockham, H))
+            return true;
+        p = FftPlan{};
+        p.n = n;
+    }
     if (fft_radices(n, rad)) {
         p.M = n;
         p.bluestein = 0;
@@ -116,6 +264,7 @@ inline bool fft_make_plan(int n, bool stockham, HostFftPlan& H) {
         stockham = false;
     }
     const int M = p.M;
+    p.alloc = M;
     if (M > 65535) return false;
     if (stockham) std::reverse(rad.begin(), rad.end());   // odd radix first: its stride-R stores are conflict free
     p.nfac = (int)rad.size();

@@ -155,7 +155,16 @@ static int get_fft(fvfi_pyr_plan* p, int n, bool stockham, FftPlan* out) {
     f.perm = nullptr;
     f.chirp = nullptr;
     f.bhat = nullptr;
-    if (f.bluestein) {
+    f.tw2 = nullptr;
+    f.pin = nullptr;
+    f.inv = nullptr;
+    if (f.rader) {
+        if (int rc = upload(p, H.perm, &f.perm)) return rc;
+        if (int rc = upload(p, H.bhat, &f.bhat)) return rc;
+        if (int rc = upload(p, H.tw2, &f.tw2)) return rc;
+        if (int rc = upload(p, H.pin, &f.pin)) return rc;
+        if (int rc = upload(p, H.inv, &f.inv)) return rc;
+    } else if (f.bluestein) {
         if (int rc = upload(p, H.chirp, &f.chirp)) return rc;
         if (int rc = upload(p, H.bhat, &f.bhat)) return rc;
     } else if (!stockham) {
@@ -167,7 +176,7 @@ static int get_fft(fvfi_pyr_plan* p, int n, bool stockham, FftPlan* out) {
 }
 
 static size_t row_bytes_per_row(const FftPlan& fx) {
-    return (size_t)(fx.bluestein ? 1 : 2) * fft_row_pitch(fx.M, fx.pad) * sizeof(float2);
+    return (size_t)(fx.bluestein ? 1 : 2) * fft_pitch(fx) * sizeof(float2);      // Bluestein runs in place; Stockham / Rader use two buffers
 }
 
 static int build_jobs(fvfi_pyr_plan* p) {
@@ -189,8 +198,8 @@ static int build_jobs(fvfi_pyr_plan* p) {
         if (int rc = get_fft(p, J.h, false, &J.fy)) return rc;
         if (int rc = get_fft(p, J.w, true, &J.fx)) return rc;
         int cs = 3;
-        while (cs > 0 && ((size_t)J.fy.M << cs) * sizeof(float2) > COL_SMEM_MAX) --cs;
-        if (((size_t)J.fy.M << cs) * sizeof(float2) > 220 * 1024) { set_error("pyramid: column length %d too large", J.h); return FVFI_EINVAL; }
+        while (cs > 0 && ((size_t)J.fy.alloc << cs) * sizeof(float2) > COL_SMEM_MAX) --cs;
+        if (((size_t)J.fy.alloc << cs) * sizeof(float2) > 220 * 1024) { set_error("pyramid: column length %d too large", J.h); return FVFI_EINVAL; }
         J.ct_shift = cs;
         const size_t per_row = row_bytes_per_row(J.fx);
         if (per_row > 220 * 1024) { set_error("pyramid: row length %d too large", J.w); return FVFI_EINVAL; }
@@ -199,7 +208,7 @@ static int build_jobs(fvfi_pyr_plan* p) {
         J.rb = rb;
         J.col_tiles = ceil_div(J.w, 1 << cs);
         int cc = cs;                 // combine pass: transform buffer + accumulator, aim for three CTAs per SM
-        while (cc > 2 && (((size_t)J.fy.M + J.h) << cc) * sizeof(float2) > 75 * 1024) --cc;
+        while (cc > 2 && (((size_t)J.fy.alloc + J.h) << cc) * sizeof(float2) > 75 * 1024) --cc;
         J.ct_shift_c = cc;
         J.col_tiles_c = ceil_div(J.w, 1 << cc);
         J.row_tiles = ceil_div(J.h, rb);
@@ -450,7 +459,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_fwd(const Le
     const int h = J.h, w = J.w, rb = J.rb;
     const int y0 = (blockIdx.x - E.start) * rb;
     const int rows = min(rb, h - y0);
-    const int pitch = fft_row_pitch(J.fx.M, J.fx.pad);
+    const int pitch = fft_pitch(J.fx);
     const FftIO iox = fft_io(J.fx);
     float2* a = smem;
     float2* bq = smem + (size_t)rb * pitch;
@@ -521,7 +530,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_fwd(const Le
     const int E_ = h << cs;
     const FftIO ioy = fft_io(J.fy);
     float2* a = smem;
-    float2* acc = smem + ((size_t)J.fy.M << cs);
+    float2* acc = smem + ((size_t)J.fy.alloc << cs);
     const size_t plane = (size_t)h * w;
     const FftCtx cx{(int)threadIdx.x, (int)blockDim.x};
     FftResult R{a, nullptr};
@@ -716,7 +725,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_inv(const Le
     const int h = J.h, w = J.w, rb = J.rb;
     const int y0 = (blockIdx.x - E.start) * rb;
     const int rows = min(rb, h - y0);
-    const int pitch = fft_row_pitch(J.fx.M, J.fx.pad);
+    const int pitch = fft_pitch(J.fx);
     const FftIO iox = fft_io(J.fx);
     float2* a = smem;
     float2* bq = smem + (size_t)rb * pitch;
@@ -790,7 +799,7 @@ static int ensure_smem(K kernel, size_t bytes) {
 
 static size_t row_smem(const LevelJob& J) { return (size_t)J.rb * row_bytes_per_row(J.fx); }
 static size_t col_smem(const LevelJob& J, bool combine) {
-    return combine ? ((((size_t)J.fy.M + J.h) << J.ct_shift_c) * sizeof(float2)) : (((size_t)J.fy.M << J.ct_shift) * sizeof(float2));
+    return combine ? ((((size_t)J.fy.alloc + J.h) << J.ct_shift_c) * sizeof(float2)) : (((size_t)J.fy.alloc << J.ct_shift) * sizeof(float2));
 }
 
 struct SetBuilder {

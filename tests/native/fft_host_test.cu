@@ -18,11 +18,17 @@ extern "C" int fft_host_run(int n, int mode, int batch, const float* in, float* 
     H.p.perm = H.p.bluestein ? nullptr : H.perm.data();
     H.p.chirp = H.chirp.data();
     H.p.bhat = H.bhat.data();
+    if (H.p.rader) {
+        H.p.perm = H.perm.data();
+        H.p.tw2 = H.tw2.data();
+        H.p.pin = H.pin.data();
+        H.p.inv = H.inv.data();
+    }
     const int M = H.p.M;
     int ctshift = 0;
     while ((1 << ctshift) < batch) ++ctshift;
-    const int pitch = fft_row_pitch(M, H.p.pad);
-    const size_t elems = col ? ((size_t)M << ctshift) : (size_t)batch * pitch;
+    const int pitch = fft_pitch(H.p);
+    const size_t elems = col ? ((size_t)H.p.alloc << ctshift) : (size_t)batch * pitch;
     std::vector<float2> a(elems, make_float2(7.f, 7.f)), b(elems, make_float2(9.f, 9.f));   // garbage-filled on purpose
     for (int bb = 0; bb < batch; ++bb)
         for (int i = 0; i < n; ++i) {
@@ -35,15 +41,17 @@ extern "C" int fft_host_run(int n, int mode, int batch, const float* in, float* 
     for (int bb = 0; bb < batch; ++bb)
         for (int pos = 0; pos < n; ++pos) {
             const float2 v = col ? fft_get<true>(fft_io(H.p), r, bb, pos, ctshift, pitch) : fft_get<false>(fft_io(H.p), r, bb, pos, ctshift, pitch);
-            const int k = r.perm ? r.perm[pos] : pos;
+            const int k = (r.perm && (col || !H.p.rader)) ? r.perm[pos] : pos;     // rows of a Rader plan read in natural order (inv table)
             out[((size_t)bb * n + k) * 2] = v.x;
             out[((size_t)bb * n + k) * 2 + 1] = v.y;
         }
     if (info) {
         info[0] = M;
-        info[1] = H.p.bluestein;
+        info[1] = H.p.bluestein + 2 * H.p.rader;
         info[2] = H.p.nfac;
         for (int s = 0; s < H.p.nfac; ++s) info[3 + s] = H.p.fac[s];
     }
     return 0;
 }
+
+extern "C" void fft_host_set_rader(int on) { fft_rader_enabled() = on; }

@@ -49,23 +49,32 @@ def run(L, n, mode, batch, rng):
 
 
 LENGTHS = sorted(set(
-    list(range(2, 41)) + [45, 49, 64, 77, 81, 91, 96, 100, 121, 128, 169, 171, 181, 191, 241, 256, 289, 361]
+    list(range(2, 41)) + [45, 47, 49, 59, 64, 77, 81, 91, 94, 96, 100, 121, 128, 169, 171, 181, 191, 241, 256, 289, 361, 529, 1334]
     + level_lengths(256, 11) + level_lengths(1080, 16) + level_lengths(1920, 16) + level_lengths(2048, 17)
     + level_lengths(2160, 18) + level_lengths(3840, 18)))
 
 
+@pytest.mark.parametrize("rader", [1, 0])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_all_lengths(lib, mode):
+def test_all_lengths(lib, mode, rader):
+    """rader = 1: the shipped plans (Rader for n = r * p, p - 1 smooth; Bluestein for the rest); rader = 0: Bluestein for every
+    non-smooth length (the fallback path stays tested)."""
+    lib.fft_host_set_rader(rader)
     rng = np.random.default_rng(mode)
-    worst = 0.0
-    for n in LENGTHS:
-        batch = 2 if n > 512 else 4
-        err, info = run(lib, n, mode, batch, rng)
-        tol = 4e-6 if info[1] else 2e-6      # Bluestein: two FFTs of ~2n + chirps
-        assert err < tol, "n=%d mode=%d rel err %.3g (M=%d bluestein=%d radices=%s)" % (
-            n, mode, err, info[0], info[1], list(info[3:3 + info[2]]))
-        worst = max(worst, err)
-    print("worst relative error", worst)
+    worst, kinds = 0.0, {0: 0, 1: 0, 2: 0}
+    try:
+        for n in LENGTHS:
+            batch = 2 if n > 512 else 4
+            err, info = run(lib, n, mode, batch, rng)
+            kinds[int(info[1])] += 1
+            tol = 4e-6 if info[1] else 2e-6      # Bluestein: two FFTs of ~2n + chirps; Rader: two FFTs of p - 1 + the outer stages
+            assert err < tol, "n=%d mode=%d rel err %.3g (M=%d kind=%d radices=%s)" % (
+                n, mode, err, info[0], info[1], list(info[3:3 + info[2]]))
+            worst = max(worst, err)
+    finally:
+        lib.fft_host_set_rader(1)
+    print("worst relative error", worst, "plans direct/bluestein/rader:", kinds)
+    assert (kinds[2] > 10) == bool(rader)
 
 
 def test_plan_choices(lib):
@@ -73,6 +82,10 @@ def test_plan_choices(lib):
     for n, stages in ((1080, 3), (1920, 3), (960, 3), (540, 3), (135, 2)):
         _, info = run(lib, n, 1, 1, rng)
         assert info[1] == 0 and info[2] == stages, (n, info[:8])
-    for n in (764, 1358, 191, 241):
+    for n in (764, 1358, 191, 241, 382, 679, 97, 61, 43, 31, 23):      # one large prime factor p with p - 1 smooth: Rader, no padding
+        for mode in (0, 1):
+            _, info = run(lib, n, mode, 1, rng)
+            assert info[1] == 2 and info[0] == n, (n, info[:8])
+    for n in (47, 59, 94, 529, 2 * 23 * 29):                           # p - 1 not smooth / two large primes / p^2: Bluestein
         _, info = run(lib, n, 0, 1, rng)
-        assert info[1] == 1 and info[0] >= 2 * n - 1
+        assert info[1] == 1 and info[0] >= 2 * n - 1, (n, info[:8])
