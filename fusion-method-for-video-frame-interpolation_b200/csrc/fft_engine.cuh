@@ -269,12 +269,13 @@ FVFI_HD int fft_addr(int b, int i, int ctshift, int pitch, int pad) {
     return COL ? ((i << ctshift) + b) : (b * pitch + i + (pad ? (i >> 4) : 0));
 }
 
-FVFI_HD int fft_row_pitch(int M, int pad) { return pad ? (M + (M >> 4) + 1) : (M | 1); }
+// even, so that every row of the sequence-major layout starts 16-byte aligned (rows can be landed by cp.async.bulk)
+FVFI_HD int fft_row_pitch(int M, int pad) { return pad ? ((M + (M >> 4) + 2) & ~1) : ((M + 2) & ~1); }
 
 // PAD (sequence-major layout only): the skewed addressing; without it every access is base + u*stride.
 template <int R, int KIND, bool COL, bool PAD>
 FVFI_HD void fft_stage_impl(const FftPlan& P, int s, const float2* in, float2* out, int batch, int ctshift,
-                            int pitch, const float2* post, FftCtx cx) {
+                            int pitch, const float2* post, FftCtx cx, int src_plain = 0) {
     const int M = P.M, items = M / R, total = batch * items;
     const int sub = P.sub[s];
     const unsigned mag_sub = P.mag_sub[s], mag_items = P.mag_items[s];
@@ -299,6 +300,10 @@ FVFI_HD void fft_stage_impl(const FftPlan& P, int s, const float2* in, float2* o
                 const int st = COL ? (items << ctshift) : items;
 #pragma unroll
                 for (int u = 0; u < R; ++u) v[u] = src[u * st];
+            } else if (src_plain) {       // first stage of a transform whose rows were landed unskewed (bulk copy): plain reads
+                const float2* src = in + fft_addr<COL>(b, t, ctshift, pitch, 0);
+#pragma unroll
+                for (int u = 0; u < R; ++u) v[u] = src[u * items];
             } else {
 #pragma unroll
                 for (int u = 0; u < R; ++u) v[u] = in[fft_addr<COL>(b, t + u * items, ctshift, pitch, 1)];
@@ -416,8 +421,8 @@ FVFI_HD void fft_rader_permute(const FftPlan& P, const float2* src, float2* dst,
 // Out-of-line per (radix, kind, layout): the stage bodies are shared by every kernel of the translation unit.
 template <int R, int KIND, bool COL, bool PAD>
 FVFI_STAGE_ATTR void fft_stage(const FftPlan* P, int s, const float2* in, float2* out, int batch, int ctshift, int pitch,
-                               const float2* post, int tid, int nthr) {
-    fft_stage_impl<R, KIND, COL, PAD>(*P, s, in, out, batch, ctshift, pitch, post, FftCtx{tid, nthr});
+                               const float2* post, int tid, int nthr, int src_plain) {
+    fft_stage_impl<R, KIND, COL, PAD>(*P, s, in, out, batch, ctshift, pitch, post, FftCtx{tid, nthr}, src_plain);
 }
 
 template <int R, int KIND, bool COL>
@@ -441,11 +446,11 @@ FVFI_HD void fft_run_stage_sub(const FftPlan& P, int s, float2* buf, int batch, 
 
 template <int KIND, bool COL>
 FVFI_HD void fft_run_stage(const FftPlan& P, int s, const float2* in, float2* out, int batch, int ctshift, int pitch,
-                           const float2* post, FftCtx cx) {
+                           const float2* post, FftCtx cx, int src_plain = 0) {
 #define FVFI_CASE(R)                                                                                               \
     case R:                                                                                                        \
-        if (!COL && P.pad) fft_stage<R, KIND, COL, !COL>(&P, s, in, out, batch, ctshift, pitch, post, cx.tid, cx.nthr); \
-        else fft_stage<R, KIND, COL, false>(&P, s, in, out, batch, ctshift, pitch, post, cx.tid, cx.nthr);          \
+        if (!COL && P.pad) fft_stage<R, KIND, COL, !COL>(&P, s, in, out, batch, ctshift, pitch, post, cx.tid, cx.nthr, src_plain); \
+        else fft_stage<R, KIND, COL, false>(&P, s, in, out, batch, ctshift, pitch, post, cx.tid, cx.nthr, 0);       \
         break;
     switch (P.fac[s]) {
         FVFI_CASE(2) FVFI_CASE(3) FVFI_CASE(4) FVFI_CASE(5) FVFI_CASE(6) FVFI_CASE(7) FVFI_CASE(8) FVFI_CASE(9)
@@ -501,8 +506,11 @@ FVFI_HD float2 fft_get(const FftIO& io, const FftResult& R, int b, int pos, int 
 // network (may be null when inplace).  The input must be visible to all threads on entry (caller syncs); on return
 // the result is visible (trailing sync) and is read with fft_get.
 template <bool COL>
+// `src_plain`: the rows of `a` were written WITHOUT the skew (element i of sequence s at s*pitch + i -- what a bulk copy of a row
+// delivers) although the plan uses the skewed layout: only valid for the out-of-place (Stockham) network, whose first stage then
+// reads plainly and writes skewed.  Plans without skew (Rader, odd first radix) need nothing.
 FVFI_HD FftResult fft_forward(const FftPlan& P, float2* a, float2* b, int batch, int ctshift, int pitch, bool inplace,
-                              FftCtx cx) {
+                              FftCtx cx, int src_plain = 0) {
     const int M = P.M, n = P.n, pad = P.pad;
     if (P.rader) {
         for (int s = 0; s < P.nouter; ++s) {                 // Cooley-Tukey stages for the smooth part r of n = r * p
@@ -548,7 +556,7 @@ FVFI_HD FftResult fft_forward(const FftPlan& P, float2* a, float2* b, int batch,
         return FftResult{a, P.perm};
     }
     for (int s = 0; s < P.nfac; ++s) {
-        fft_run_stage<FFT_STOCKHAM, COL>(P, s, a, b, batch, ctshift, pitch, nullptr, cx);
+        fft_run_stage<FFT_STOCKHAM, COL>(P, s, a, b, batch, ctshift, pitch, nullptr, cx, s == 0 ? src_plain : 0);
         fft_sync();
         float2* t = a; a = b; b = t;
     }

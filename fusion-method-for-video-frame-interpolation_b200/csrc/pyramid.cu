@@ -25,6 +25,7 @@
 //    row pass of the band IFFT -- the complex band never goes to HBM; reconstruction reads
 //    (phase, amplitude) and forms A*(cos,sin) in the first row pass (pyramid.py:103-108).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <map>
@@ -732,7 +733,34 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_inv(const Le
     const unsigned mag_w = J.mag_w;
     const size_t plane = (size_t)h * w;
     const float2* src = regionB + (size_t)N * J.t_off + ((size_t)n * nbB + b) * plane + (size_t)y0 * w;
-    {
+    // Rows of the intermediate are contiguous in HBM: when they are 16-byte aligned (even width) and need no transformation on the
+    // way in (no Bluestein chirp), one elected thread lands every row at its pitch with cp.async.bulk (bulk async-copy engine,
+    // completion on an mbarrier) -- no per-element load / address / store instructions, no registers in flight.
+    const bool bulk = !iox.bluestein && !(w & 1) && ((((size_t)src) & 15) == 0) && J.fx.nfac > 0;
+    const int src_plain = (bulk && J.fx.pad) ? 1 : 0;     // landed unskewed: the first (out-of-place) stage reads plainly
+    if (bulk) {
+        unsigned long long* bar = (unsigned long long*)(smem + (size_t)2 * rb * pitch);
+        const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned row_bytes = (unsigned)w * (unsigned)sizeof(float2);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(row_bytes * (unsigned)rows) : "memory");
+            for (int r = 0; r < rows; ++r)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"((unsigned)__cvta_generic_to_shared(a + (size_t)r * pitch)), "l"(src + (size_t)r * w), "r"(row_bytes), "r"(bar_s)
+                             : "memory");
+        }
+        unsigned done = 0, spins = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar_s) : "memory");
+            if (++spins > 200000000u) __trap();       // bounded wait: a protocol bug traps instead of hanging the GPU
+        }
+    } else {
         constexpr int U = 8;                  // independent global loads in flight per thread
         const int total = rows * w;
         for (int q0 = threadIdx.x; q0 < total; q0 += U * blockDim.x) {
@@ -753,7 +781,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_inv(const Le
         }
     }
     __syncthreads();
-    const FftResult R = fft_forward<false>(J.fx, a, bq, rows, 0, pitch, false, FftCtx{(int)threadIdx.x, (int)blockDim.x});
+    const FftResult R = fft_forward<false>(J.fx, a, bq, rows, 0, pitch, false, FftCtx{(int)threadIdx.x, (int)blockDim.x}, src_plain);
     const float scale = E.scale > 0.f ? E.scale : 1.f / ((float)h * (float)w);
     float mx = 0.f;
     for (int q = threadIdx.x; q < rows * w; q += blockDim.x) {
@@ -797,7 +825,7 @@ static int ensure_smem(K kernel, size_t bytes) {
     return FVFI_OK;
 }
 
-static size_t row_smem(const LevelJob& J) { return (size_t)J.rb * row_bytes_per_row(J.fx); }
+static size_t row_smem(const LevelJob& J) { return (size_t)J.rb * row_bytes_per_row(J.fx) + 16; }   // + the mbarrier of the bulk row loads
 static size_t col_smem(const LevelJob& J, bool combine) {
     return combine ? ((((size_t)J.fy.alloc + J.h) << J.ct_shift_c) * sizeof(float2)) : (((size_t)J.fy.alloc << J.ct_shift) * sizeof(float2));
 }
@@ -1080,6 +1108,7 @@ int fvfi_pyr_plan_create(int H, int W, int height, int nbands, double scale_fact
     FVFI_CHECK_ARG(height >= 2 && height - 2 < MAX_LEVELS - 1, "pyr_plan_create: bad height %d", height);
     FVFI_CHECK_ARG(nbands >= 1 && nbands <= MAX_BANDS, "pyr_plan_create: nbands must be 1..%d", MAX_BANDS);
     FVFI_CHECK_ARG(scale_factor > 1.0 && scale_factor <= 4.0, "pyr_plan_create: scale_factor must be in (1,4]");
+    if (const char* e = getenv("FVFI_FFT_NO_RADER")) fvfi::fft_rader_enabled() = (e[0] == '1') ? 0 : 1;   // A/B switch: Bluestein everywhere
     fvfi_pyr_plan* p = new fvfi_pyr_plan();
     p->H = H; p->W = W; p->height = height; p->nbands = nbands; p->L = height - 2; p->scale = scale_factor;
     if (int rc = build_plan(p)) { fvfi_pyr_plan_destroy(p); return rc; }

@@ -18,6 +18,7 @@ def t(fn, reps=reps):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 vals = pyr.filter(x)
+t(lambda: pyr.filter(x))
 td = t(lambda: pyr.filter(x))
 tdn = t(lambda: pyr.filter(x, want_high=False))
 tr = t(lambda: pyr.inv_filter(vals))
