@@ -12,7 +12,6 @@ import torch
 
 from . import _lib
 
-enabled = True   # use the tcgen05 kernels for inference convolutions (False -> torch/cuDNN scaffolding, tests only)
 PRECISIONS = {"tf32x3": 0, "f16x3": 1}
 precision = PRECISIONS[os.environ.get("FVFI_CONV_PREC", "f16x3")]   # operand split (include/fvfi.h: FVFI_CONV_*)
 range_check = True   # range_checked() forwards verify the 3xFP16 range flag and re-run in 3xTF32 when it was raised
@@ -61,7 +60,7 @@ def range_checked(fn):
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
         global _guard_depth
-        if (_guard_depth > 0 or not range_check or not enabled or precision != PRECISIONS["f16x3"] or torch.is_grad_enabled()
+        if (_guard_depth > 0 or not range_check or precision != PRECISIONS["f16x3"] or torch.is_grad_enabled()
                 or not torch.cuda.is_available() or torch.cuda.is_current_stream_capturing()):
             return fn(*args, **kwargs)
         _guard_depth += 1
@@ -77,9 +76,53 @@ def range_checked(fn):
 
 
 def use_tc(x):
-    """Tensor-core path applies to CUDA inference (autograd off: the kernel has no backward; training uses
-    the torch/cuDNN path)."""
-    return enabled and x.is_cuda and not torch.is_grad_enabled()
+    """The fused inference forwards of the drop-in modules apply to CUDA tensors with autograd off.  (With autograd on, the modules
+    run their step-by-step torch graph; FusionNet -- the network the fusion recipe trains -- still takes its convolutions from the
+    tensor-core kernel there through ``conv2d``'s autograd Function.)"""
+    return x.is_cuda and not torch.is_grad_enabled()
+
+
+class _ConvTC(torch.autograd.Function):
+    """act(conv(pad(x), w) + b) with the FORWARD on the tcgen05 kernel (activations saved for backward); the backward (dgrad, wgrad,
+    bias grad) is ATen's convolution_backward on the saved input -- hand-written dgrad / wgrad kernels are not built."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, padding_mode, act):
+        y = conv2d(x.detach(), weight.detach(), None if bias is None else bias.detach(), padding_mode, act)
+        ctx.save_for_backward(x, weight, y)
+        ctx.has_bias, ctx.padding_mode, ctx.act = bias is not None, padding_mode, act
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, y = ctx.saved_tensors
+        act, p = ctx.act, weight.shape[2] // 2
+        if act == "relu":
+            g = gy * (y > 0)
+        elif act == "elu":
+            g = gy * torch.where(y > 0, torch.ones_like(y), y + 1)          # d/dx elu = exp(x) = y + 1 for x < 0
+        elif act == "tanh":
+            g = gy * (1 - y * y)
+        elif act == "sigmoid":
+            g = gy * y * (1 - y)
+        else:
+            assert act in (None, "none"), "no backward for activation %r" % (act,)
+            g = gy
+        g = g.contiguous(memory_format=torch.channels_last)
+        xin = x.float()
+        if xin.shape[1] > weight.shape[1]:
+            xin = xin[:, :weight.shape[1]]
+        reflect = ctx.padding_mode == "reflect" and p > 0
+        if reflect:
+            xin = torch.nn.functional.pad(xin, (p, p, p, p), mode="reflect")
+        mask = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]]
+        gx, gw, gb = torch.ops.aten.convolution_backward(g, xin, weight, [weight.shape[0]] if ctx.has_bias else None, [1, 1],
+                                                         [0, 0] if reflect else [p, p], [1, 1], False, [0, 0], 1, mask)
+        if gx is not None and reflect:
+            gx = torch.ops.aten.reflection_pad2d_backward(gx, x.float()[:, :weight.shape[1]], [p, p, p, p])
+        if gx is not None and gx.shape[1] < x.shape[1]:
+            gx = torch.nn.functional.pad(gx, (0, 0, 0, 0, 0, x.shape[1] - gx.shape[1]))
+        return gx, gw, (gb if ctx.has_bias else None), None, None
 
 
 ACT = {None: 0, "none": 0, "relu": 1, "elu": 2, "tanh": 3, "sigmoid": 4, "softmax": 5}
@@ -143,6 +186,10 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
     counts such as 25).  ``x`` may carry such zero padding channels beyond the weight's Cin."""
     if not x.is_cuda:
         raise NotImplementedError("fvfi.conv.conv2d: CUDA tensors only")
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
+        assert out is None and not nchw_out and not pad_out and residual is None and act != "softmax", \
+            "conv2d under autograd supports the plain NHWC form (bias + relu / elu / tanh / sigmoid)"
+        return _ConvTC.apply(x, weight, bias, padding_mode, act)
     B, Cin, H, W = x.shape
     Cout, Cin_w, KH, KW = weight.shape
     assert Cin >= Cin_w and KH == KW and KH in (1, 3, 5)

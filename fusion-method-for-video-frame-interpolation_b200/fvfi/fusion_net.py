@@ -64,33 +64,29 @@ class FusionNet(torch.nn.Module):
 
     @tc.range_checked
     def forward(self, base, adacof, phase, other, maps, save=False, variant=0):
+        """fusion_net.py:46-77.  Every convolution (+ its ReLU) is one tcgen05 kernel -- in inference AND under autograd (training:
+        ``conv.conv2d`` saves the activations and differentiates through its autograd Function); pooling, upsampling and the skip
+        additions are the fused NHWC kernels in inference and the differentiable torch operators under autograd."""
         x = torch.cat([base, adacof, phase, other, maps], 1)
+        if not x.is_cuda:
+            raise NotImplementedError("fvfi FusionNet runs on CUDA tensors only (no CPU fallback)")
+        grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.live_parameters()))
         skip = []
-        if tc.use_tc(x):
-            # tcgen05 path (fusion_net.py:52-65): conv+ReLU fused, pooling / upsampling on NHWC tensors
-            x = tc.to_nhwc(x)
-            for layer in self.encoder_layers:
-                x = tc.conv_module(layer, x, "relu")
-                skip.append(x)
-                x = tc.max_pool2(x)                                   # nn.MaxPool2d(2, stride=2) on NHWC, 256-bit accesses
-            x = tc.conv_module(self.bottleneck_layer, x, "relu")    # ReLU of the first decoder step folded in
-            for i, (layer, s) in enumerate(zip(self.decoder_layers, skip[::-1])):
-                # Upsample(ReLU(x)) + skip (fusion_net.py:60-62) in one pass
+        x = tc.to_nhwc(x)
+        for layer in self.encoder_layers:
+            x = tc.conv_module(layer, x, "relu")                          # fusion_net.py:52-56
+            skip.append(x)
+            x = nn.functional.max_pool2d(x, 2, 2) if grad else tc.max_pool2(x)
+        x = tc.conv_module(self.bottleneck_layer, x, "relu")              # the ReLU of the first decoder step folded in (:58-61)
+        for i, (layer, s) in enumerate(zip(self.decoder_layers, skip[::-1])):
+            if grad:                                                       # Upsample(ReLU(x)) + skip, differentiable form
+                x = nn.functional.interpolate(x if i == 0 else torch.relu(x), scale_factor=2, mode='bilinear') + s
+            else:                                                          # ... as one pass (fvfi_resize_bilinear_nhwc_fused)
                 x = tc.resize_bilinear(x, (x.shape[2] * 2, x.shape[3] * 2), False, relu_input=i > 0, add=s)
-                x = tc.conv_module(layer, x, None)
-            x = x.contiguous()
-        else:
-            for layer in self.encoder_layers:
-                x = self.relu(layer(x))
-                skip.append(x)
-                x = self.max_pool(x)
-            x = self.bottleneck_layer(x)
-            for layer, s in zip(self.decoder_layers, skip[::-1]):
-                x = self.deconvolution(self.relu(x))
-                x = x + s
-                x = layer(x)
+            x = tc.conv_module(layer, x, None)
+        x = x.contiguous()
         anchor = phase if variant == 1 else base
-        if torch.is_grad_enabled() and x.requires_grad or not x.is_cuda:
+        if grad:
             res = self.tanh(x)
             if save:
                 self.residuals.append(torch.sum(res).cpu().detach().item())

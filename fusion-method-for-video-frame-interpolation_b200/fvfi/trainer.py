@@ -3,6 +3,7 @@
 data-parallel over ranks with one flat-bucket gradient all-reduce (fvfi.dist)."""
 import torch
 
+from . import conv as tc
 from .dist import FlatGradBucket, all_reduce_mean_buffers, broadcast_module
 
 
@@ -10,6 +11,7 @@ class FusionTrainer:
     def __init__(self, pipeline, lr=1e-4, group=None, graph_frozen=False):
         self.pipe = pipeline
         self.graph_frozen = graph_frozen        # replay the frozen PhaseNet / AdaCoF part as a CUDA graph (fixed crop shape)
+        self.check_range = False                # True: read the 3xFP16 range flag after every step (one stream sync per step)
         self.net = pipeline.fusion_net
         self.net.train()
         # replicas start from rank 0's weights: the trained FusionNet and the frozen networks that produce its inputs
@@ -34,6 +36,8 @@ class FusionTrainer:
         loss.backward()                                          # grads land in the flat bucket
         self.bucket.all_reduce_mean(self.group)
         self.optimizer.step()                                    # trainer.py:257-259
+        if self.check_range and tc.overflow_pending():           # FusionNet's training forward runs on the 3xFP16 kernels too
+            raise FloatingPointError("FusionTrainer: activation beyond the 3xFP16 range; use fvfi.conv.forced_precision('tf32x3')")
         return loss.detach()
 
 

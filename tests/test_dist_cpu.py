@@ -34,13 +34,14 @@ def _worker(rank, world, port, q):
     sys.path[:0] = [root, os.path.join(root, "fusion-method-for-video-frame-interpolation_b200")]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from fvfi.dist import FlatGradBucket, shard_range
-    from fvfi.fusion_net import FusionNet
-    torch.manual_seed(0)
+    from fvfi.dist import FlatGradBucket, broadcast_module, shard_range
+    from oracle.nets import FusionNet            # CPU stand-in with FusionNet's parameters: the product module is CUDA-only
+    torch.manual_seed(rank)                      # ranks start different; the broadcast makes them rank 0's
     net = FusionNet()
+    broadcast_module(net, 0)
     for n, p in net.named_parameters():
         p.requires_grad_(not n.startswith("net."))
-    bucket = FlatGradBucket(net.live_parameters())
+    bucket = FlatGradBucket([p for n, p in net.named_parameters() if not n.startswith("net.")])
     g = torch.Generator().manual_seed(1)
     ins = [torch.rand((4, c, 16, 16), generator=g) for c in (3, 3, 3, 6, 3)]
     target = torch.rand((4, 3, 16, 16), generator=g)
@@ -70,12 +71,12 @@ def test_flat_bucket_allreduce_matches_full_batch_gloo():
         assert p.exitcode == 0
     # single-process full-batch reference
     from fvfi.dist import FlatGradBucket
-    from fvfi.fusion_net import FusionNet
+    from oracle.nets import FusionNet
     torch.manual_seed(0)
     net = FusionNet()
     for n, p in net.named_parameters():
         p.requires_grad_(not n.startswith("net."))
-    bucket = FlatGradBucket(net.live_parameters())
+    bucket = FlatGradBucket([p for n, p in net.named_parameters() if not n.startswith("net.")])
     g = torch.Generator().manual_seed(1)
     ins = [torch.rand((4, c, 16, 16), generator=g) for c in (3, 3, 3, 6, 3)]
     target = torch.rand((4, 3, 16, 16), generator=g)

@@ -72,13 +72,13 @@ with torch.no_grad():
         return pipe.phase_net(vin)
     print("B  PhaseNet on the oracle's decomposition: max |coef - oracle fp32 coef| / max|level| per level, then low_level abs")
     for name in ("f16x3", "tf32x3", "cudnn"):
-        tc.enabled = name != "cudnn"
-        if tc.enabled:
+        if name != "cudnn":
             with tc.forced_precision(name):
                 gp = run_net()
         else:
-            gp = run_net()
-        tc.enabled = True
+            with torch.enable_grad():              # PhaseNet's differentiable graph = torch convolutions (cuDNN fp32)
+                gp = run_net()
+            gp = gp._replace(phase=[p.detach() for p in gp.phase], amplitude=[a.detach() for a in gp.amplitude], low_level=gp.low_level.detach())
         errs = []
         for l in range(L):
             g = cplx(gp.phase[l].cpu(), gp.amplitude[l].cpu())
