@@ -326,20 +326,21 @@ __device__ __forceinline__ void stg256f(float* p, const float* v) {
                  : "memory");
 }
 
-// VEC = channels per thread: 8 (256-bit accesses), 4 (128-bit) or 1 (any stride / alignment)
+// VEC = channels per thread: 8 (256-bit accesses), 4 (128-bit) or 1 (any stride / alignment).
+// grid = (column x channel-group blocks, output rows, images): the row coordinates are uniform per block and nothing is divided
+// per thread when the number of channel groups is a power of two (cg_shift >= 0).
 template <int VEC>
 __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi,
                                                                    int Wi, int Ho, int Wo, int C, int ldx, int ldy,
                                                                    float sy, float sx, int align_corners,
-                                                                   const float* __restrict__ addend, int lda, int relu_in) {
-    const unsigned cg_n = (unsigned)(C + VEC - 1) / VEC;
-    const unsigned total = (unsigned)Ho * (unsigned)Wo * cg_n;      // per image; < 2^32 checked by the launcher
+                                                                   const float* __restrict__ addend, int lda, int relu_in,
+                                                                   int cg_n, int cg_shift) {
     const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= total) return;
-    const unsigned p = q / cg_n;
-    const int ch = (int)(q - p * cg_n) * VEC;
-    const int oy = (int)(p / (unsigned)Wo), ox = (int)(p - (unsigned)oy * (unsigned)Wo);
-    const int n = blockIdx.y;
+    const int ox = cg_shift >= 0 ? (int)(q >> cg_shift) : (int)(q / (unsigned)cg_n);
+    if (ox >= Wo) return;
+    const int ch = (int)(q - (unsigned)ox * (unsigned)cg_n) * VEC;
+    const int oy = blockIdx.y, n = blockIdx.z;
+    const size_t p = (size_t)oy * Wo + ox;
     // source coordinates exactly as ATen's area_pixel_compute_source_index
     float fy, fx;
     if (align_corners) {
@@ -359,9 +360,11 @@ __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* 
     const float* p10 = X + ((size_t)y1 * Wi + x0) * ldx + ch;
     const float* p11 = X + ((size_t)y1 * Wi + x1) * ldx + ch;
     float* dst = y + ((size_t)n * Ho * Wo + p) * ldy + ch;
-    float a[VEC], b[VEC], c[VEC], d[VEC], o[VEC];
+    float a[VEC], b[VEC], c[VEC], d[VEC], o[VEC], e[VEC];
+    const float* ap = addend ? addend + ((size_t)n * Ho * Wo + p) * lda + ch : nullptr;
     if (VEC == 8) {
         ldg256f(p00, a); ldg256f(p01, b); ldg256f(p10, c); ldg256f(p11, d);
+        if (ap) ldg256f(ap, e);
     } else if (VEC == 4) {
         const float4 a4 = __ldg((const float4*)p00), b4 = __ldg((const float4*)p01), c4 = __ldg((const float4*)p10),
                      d4 = __ldg((const float4*)p11);
@@ -369,8 +372,13 @@ __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* 
         b[0] = b4.x; b[1] = b4.y; b[2] = b4.z; b[3] = b4.w;
         c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
         d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
+        if (ap) {
+            const float4 e4 = __ldg((const float4*)ap);
+            e[0] = e4.x; e[1] = e4.y; e[2] = e4.z; e[3] = e4.w;
+        }
     } else {
         a[0] = __ldg(p00); b[0] = __ldg(p01); c[0] = __ldg(p10); d[0] = __ldg(p11);
+        if (ap) e[0] = __ldg(ap);
     }
     if (relu_in) {                      // Upsample(ReLU(x)): the activation applies to the source samples (fusion_net.py:61)
 #pragma unroll
@@ -378,17 +386,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* 
     }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
-    if (addend) {                       // + skip connection (fusion_net.py:62)
-        const float* ap = addend + ((size_t)n * Ho * Wo + p) * lda + ch;
-        float e[VEC];
-        if (VEC == 8) {
-            ldg256f(ap, e);
-        } else if (VEC == 4) {
-            const float4 e4 = __ldg((const float4*)ap);
-            e[0] = e4.x; e[1] = e4.y; e[2] = e4.z; e[3] = e4.w;
-        } else {
-            e[0] = __ldg(ap);
-        }
+    if (ap) {                           // + skip connection (fusion_net.py:62)
 #pragma unroll
         for (int i = 0; i < VEC; ++i) o[i] += e[i];
     }
@@ -615,16 +613,20 @@ extern "C" int fvfi_resize_bilinear_nhwc_fused(const float* x, int x_pixel_strid
     const bool a32 = ((((size_t)x) | ((size_t)y) | addbits) & 31) == 0, a16 = ((((size_t)x) | ((size_t)y) | addbits) & 15) == 0;
     const int vec = (a32 && (C & 7) == 0 && (x_pixel_stride & 7) == 0 && (y_pixel_stride & 7) == 0) ? 8
                   : (a16 && (C & 3) == 0 && (x_pixel_stride & 3) == 0 && (y_pixel_stride & 3) == 0) ? 4 : 1;
-    const size_t total = (size_t)Ho * Wo * ((C + vec - 1) / vec);
-    FVFI_CHECK_ARG(total < (1ull << 32) - 256, "resize_bilinear: image too large");
-    dim3 grid((unsigned)((total + 255) / 256), B);
+    const int cg_n = (C + vec - 1) / vec;
+    int cg_shift = -1;
+    for (int sh = 0; sh < 16; ++sh)
+        if ((1 << sh) == cg_n) cg_shift = sh;
+    const size_t per_row = (size_t)Wo * cg_n;
+    FVFI_CHECK_ARG(per_row < (1ull << 31) && Ho <= 65535, "resize_bilinear: image too large");
+    dim3 grid((unsigned)((per_row + 255) / 256), (unsigned)Ho, (unsigned)B);
     cudaStream_t s = (cudaStream_t)stream;
     if (vec == 8)
-        fvfi::resize_bilinear_nhwc_kernel<8><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners, addend, lda, relu_in);
+        fvfi::resize_bilinear_nhwc_kernel<8><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners, addend, lda, relu_in, cg_n, cg_shift);
     else if (vec == 4)
-        fvfi::resize_bilinear_nhwc_kernel<4><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners, addend, lda, relu_in);
+        fvfi::resize_bilinear_nhwc_kernel<4><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners, addend, lda, relu_in, cg_n, cg_shift);
     else
-        fvfi::resize_bilinear_nhwc_kernel<1><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners, addend, lda, relu_in);
+        fvfi::resize_bilinear_nhwc_kernel<1><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners, addend, lda, relu_in, cg_n, cg_shift);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }

@@ -88,6 +88,15 @@ def test_resize_bilinear_nhwc_matches_torch(align):
     conv.resize_bilinear(x, (16, 16), False, out=buf, out_channel_offset=8)
     assert float((buf[:, 8:72] - F.interpolate(x, size=(16, 16), mode="bilinear", align_corners=False)).abs().max()) <= 2e-6
     assert float(buf[:, :8].abs().max()) == 0.0 and float(buf[:, 72:].abs().max()) == 0.0
+    # fused decoder step of FusionNet: Upsample(ReLU(x)) + skip (fusion_net.py:60-62), every vector width / channel-group count
+    for (B, C, Hi, Wi) in [(2, 64, 9, 13), (1, 88, 7, 5), (1, 12, 6, 10), (2, 3, 5, 4), (1, 32, 33, 17)]:
+        x = torch.randn((B, C, Hi, Wi), device="cuda", generator=g)
+        sk = torch.randn((B, C, 2 * Hi, 2 * Wi), device="cuda", generator=g)
+        ref = F.interpolate(torch.relu(x), scale_factor=2, mode="bilinear", align_corners=align) + sk
+        got = conv.resize_bilinear(x, (2 * Hi, 2 * Wi), align, relu_input=True, add=sk)
+        assert float((got - ref).abs().max()) <= 2e-6, (B, C, Hi, Wi)
+        got = conv.resize_bilinear(x, (2 * Hi, 2 * Wi), align, add=sk.contiguous(memory_format=torch.channels_last))
+        assert float((got - (F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=align) + sk)).abs().max()) <= 2e-6
 
 
 def test_conv_softmax_and_nchw_epilogues(prec):
