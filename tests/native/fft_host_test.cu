@@ -29,7 +29,12 @@ extern "C" int fft_host_run(int n, int mode, int batch, const float* in, float* 
     while ((1 << ctshift) < batch) ++ctshift;
     const int pitch = fft_pitch(H.p);
     const size_t elems = col ? ((size_t)H.p.alloc << ctshift) : (size_t)batch * pitch;
-    std::vector<float2> a(elems, make_float2(7.f, 7.f)), b(elems, make_float2(9.f, 9.f));   // garbage-filled on purpose
+    // garbage-filled on purpose, with a guard zone behind each buffer: the stage code must stay inside [0, elems) -- the bound the
+    // kernels size their shared memory by (alloc << ctshift columns / batch * pitch rows)
+    constexpr size_t GUARD = 256;
+    const float2 canary = make_float2(-12345.f, 54321.f);
+    std::vector<float2> a(elems + GUARD, make_float2(7.f, 7.f)), b(elems + GUARD, make_float2(9.f, 9.f));
+    for (size_t i = 0; i < GUARD; ++i) a[elems + i] = b[elems + i] = canary;
     for (int bb = 0; bb < batch; ++bb)
         for (int i = 0; i < n; ++i) {
             const float2 v = make_float2(in[((size_t)bb * n + i) * 2], in[((size_t)bb * n + i) * 2 + 1]);
@@ -45,6 +50,8 @@ extern "C" int fft_host_run(int n, int mode, int batch, const float* in, float* 
             out[((size_t)bb * n + k) * 2] = v.x;
             out[((size_t)bb * n + k) * 2 + 1] = v.y;
         }
+    for (size_t i = 0; i < GUARD; ++i)
+        if (a[elems + i].x != canary.x || a[elems + i].y != canary.y || b[elems + i].x != canary.x || b[elems + i].y != canary.y) return -2;
     if (info) {
         info[0] = M;
         info[1] = H.p.bluestein + 2 * H.p.rader;

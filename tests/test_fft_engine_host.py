@@ -42,6 +42,7 @@ def run(L, n, mode, batch, rng):
     out = np.zeros((batch, n), np.complex64)
     info = np.zeros(16, np.int32)
     rc = L.fft_host_run(n, mode, batch, x.ctypes.data, out.ctypes.data, info.ctypes.data)
+    assert rc != -2, "n=%d mode=%d: the transform wrote outside its buffers (guard zone overwritten)" % (n, mode)
     assert rc == 0, "no plan for n=%d" % n
     ref = np.fft.fft(x.astype(np.complex128), axis=1)
     err = np.abs(out - ref).max() / np.abs(ref).max()
