@@ -74,6 +74,10 @@ class FusionPipeline(torch.nn.Module):
         self.max_batch_adacof = 16     # largest AdaCoFNet batch at full HD (the 64 -> 448 fused head tensor is 15 GB at 16)
         self._copy_streams = None      # (host -> device, device -> host) side streams of interpolate_host
         self._graphs = {}              # (method, input shapes) -> GraphedCall
+        # small frames (<= 512x512) leave most SMs idle in any single kernel: the first AdaCoFNet pass does not depend on the
+        # PhaseNet branch, so it runs on a side stream next to it (fork / join by events; also inside a captured CUDA graph)
+        self.concurrent_small = True
+        self._side_stream = None
         # optional callable (tag, planes, vals) -> vals applied to every decomposition (tests: aligns the branch of phase values
         # at +-pi with the reference's, see tests/_parity.py; None in production)
         self.filter_hook = None
@@ -134,8 +138,19 @@ class FusionPipeline(torch.nn.Module):
         pyr, r_shape = self.pyr, (B, 3, H, W)
         self._tick('start')
         lab1, lab2 = transform.rgb2lab(rgb1), transform.rgb2lab(rgb2)                           # :148-149
-        _, _, ada_pred, flow_var_map = self.adacof(rgb1, rgb2, return_warped=False)                                  # :156
-        flow_var_map = flow_var_map.squeeze(1)
+        fork = self.concurrent_small and H * W <= 512 * 512 and self.timing is None
+        if fork:
+            main = torch.cuda.current_stream(rgb1.device)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(rgb1.device)
+            side = self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                _, _, ada_pred, flow_var_map = self.adacof(rgb1, rgb2, return_warped=False)                          # :156
+                flow_var_map = flow_var_map.squeeze(1)
+        else:
+            _, _, ada_pred, flow_var_map = self.adacof(rgb1, rgb2, return_warped=False)                              # :156
+            flow_var_map = flow_var_map.squeeze(1)
         self._tick('lab+adacofnet#1')
         # PhaseNet branch (:168-192)
         vals = self._filter("phasenet", torch.cat((lab1.reshape(-1, H, W), lab2.reshape(-1, H, W)), 0), want_high=False)
@@ -154,6 +169,10 @@ class FusionPipeline(torch.nn.Module):
         del vals_pred
         self._tick('pyr.inv_filter(3 planes/frame)')
         phase_pred = transform.lab2rgb(lab_pred)                                                # :192
+        if fork:                                  # join: everything below reads ada_pred
+            main.wait_stream(side)
+            ada_pred.record_stream(main)
+            flow_var_map.record_stream(main)
         # uncertainty maps (:197-225)
         # only level 0 + the high residual (h_freq) and the six coarsest levels + low pass (freq_diff) of these pyramids are ever read
         L = pyr.height - 2

@@ -200,6 +200,12 @@ def test_cuda_graph_replay_matches_eager():
             got = [t.clone() for t in gi(x1, x2)]
             ref = pipe.fusion_inputs(x1, x2)
             assert all(torch.equal(p, q) for p, q in zip(got, ref))
+        # small frames run the first AdaCoFNet pass on a side stream next to the PhaseNet branch: same values as in sequence
+        assert pipe.concurrent_small
+        out_c = pipe(a1, a2)
+        pipe.concurrent_small = False
+        out_s = pipe(a1, a2)
+        assert torch.equal(out_c, out_s)
 
 
 def test_conv_range_guard_reruns_in_tf32x3():
