@@ -173,45 +173,55 @@ class FusionPipeline(torch.nn.Module):
             main.wait_stream(side)
             ada_pred.record_stream(main)
             flow_var_map.record_stream(main)
-        # uncertainty maps (:197-225)
-        # only level 0 + the high residual (h_freq) and the six coarsest levels + low pass (freq_diff) of these pyramids are ever read
-        L = pyr.height - 2
-        coarse = list(range(L - 6, L))
-        if self.fused_phase_glue:
-            # h_freq - h_freq_ph = mean_c(recon_{high + level 0}(ada_c) - recon_{high + level 0}(phase_c))  (get_last_value_levels(., 1),
-            # :205-209).  Decomposition and reconstruction are linear in the image, so this is recon_{high + level 0} of the single
-            # plane  xbar = mean_c(ada_c - phase_c): the six colour planes are decomposed on the (tiny) coarse levels only.
-            vals_ada, vals_ph = utils.separate_vals(
-                self._filter("uncertainty", torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), want_high=False,
-                             levels=coarse), 2)
-            self._tick('lab2rgb+pyr.filter(6 planes/frame)')
-            v0 = pyr.filter((ada_pred - phase_pred).mean(1), levels=[0])      # reconstructed at once: its phases feed cos / sin only
-            h_diff = pyr.inv_filter_sparse(v0, use_low=False, levels=[0])
-            del v0
+
+        def uncertainty_maps():
+            # uncertainty maps (:197-225)
+            # only level 0 + the high residual (h_freq) and the six coarsest levels + low pass (freq_diff) of these pyramids are ever read
+            L = pyr.height - 2
+            coarse = list(range(L - 6, L))
+            if self.fused_phase_glue:
+                # h_freq - h_freq_ph = mean_c(recon_{high + level 0}(ada_c) - recon_{high + level 0}(phase_c))  (get_last_value_levels(., 1),
+                # :205-209).  Decomposition and reconstruction are linear in the image, so this is recon_{high + level 0} of the single
+                # plane  xbar = mean_c(ada_c - phase_c): the six colour planes are decomposed on the (tiny) coarse levels only.
+                vals_ada, vals_ph = utils.separate_vals(
+                    self._filter("uncertainty", torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), want_high=False,
+                                 levels=coarse), 2)
+                self._tick('lab2rgb+pyr.filter(6 planes/frame)')
+                v0 = pyr.filter((ada_pred - phase_pred).mean(1), levels=[0])      # reconstructed at once: its phases feed cos / sin only
+                h_diff = pyr.inv_filter_sparse(v0, use_low=False, levels=[0])
+                del v0
+            else:
+                used = sorted(set([0]) | set(coarse))
+                vals_ada, vals_ph = utils.separate_vals(
+                    self._filter("uncertainty", torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), levels=used), 2)
+                self._tick('lab2rgb+pyr.filter(6 planes/frame)')
+                h_freq = pyr.inv_filter_sparse(vals_ada, use_low=False, levels=[0]).reshape(r_shape).mean(1)
+                h_freq_ph = pyr.inv_filter_sparse(vals_ph, use_low=False, levels=[0]).reshape(r_shape).mean(1)
+                h_diff = h_freq - h_freq_ph
+            h_freq_diff = (h_diff.abs() * 100).clamp(min=0, max=1.0)
+            self._tick('pyr.inv_filter(level0 x2)')
+            phase_uncertainty = filters.gaussian_filter(h_freq_diff, 5)
+            self._tick('gaussian')
+            L = len(vals_ph.phase)
+            # subtract_values + get_first_value_levels(., 6): only the 6 coarsest levels and the low pass are used
+            keep = range(L - 6, L)
+            vals_diff = vals_ph._replace(
+                low_level=(vals_ph.low_level - vals_ada.low_level).abs(),
+                phase=[(vals_ph.phase[l] - vals_ada.phase[l]).abs() if l in keep else None for l in range(L)],
+                amplitude=[(vals_ph.amplitude[l] - vals_ada.amplitude[l]).abs() if l in keep else None for l in range(L)])
+            freq_diff = pyr.inv_filter_sparse(vals_diff, use_high=False, levels=keep).reshape(r_shape).mean(1) * 30
+            del vals_diff, vals_ada, vals_ph
+            self._tick('pyr.inv_filter(coarse6)')
+            ada_uncertainty = ((freq_diff - filters.median_filter(freq_diff, 50)).abs() * 5).clamp(0, 1)
+            self._tick('median50')
+            return phase_uncertainty, ada_uncertainty, freq_diff, h_freq_diff
+
+        if fork:                                  # the uncertainty branch and the baseline passes only share their inputs
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                phase_uncertainty, ada_uncertainty, freq_diff, h_freq_diff = uncertainty_maps()
         else:
-            used = sorted(set([0]) | set(coarse))
-            vals_ada, vals_ph = utils.separate_vals(
-                self._filter("uncertainty", torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), levels=used), 2)
-            self._tick('lab2rgb+pyr.filter(6 planes/frame)')
-            h_freq = pyr.inv_filter_sparse(vals_ada, use_low=False, levels=[0]).reshape(r_shape).mean(1)
-            h_freq_ph = pyr.inv_filter_sparse(vals_ph, use_low=False, levels=[0]).reshape(r_shape).mean(1)
-            h_diff = h_freq - h_freq_ph
-        h_freq_diff = (h_diff.abs() * 100).clamp(min=0, max=1.0)
-        self._tick('pyr.inv_filter(level0 x2)')
-        phase_uncertainty = filters.gaussian_filter(h_freq_diff, 5)
-        self._tick('gaussian')
-        L = len(vals_ph.phase)
-        # subtract_values + get_first_value_levels(., 6): only the 6 coarsest levels and the low pass are used
-        keep = range(L - 6, L)
-        vals_diff = vals_ph._replace(
-            low_level=(vals_ph.low_level - vals_ada.low_level).abs(),
-            phase=[(vals_ph.phase[l] - vals_ada.phase[l]).abs() if l in keep else None for l in range(L)],
-            amplitude=[(vals_ph.amplitude[l] - vals_ada.amplitude[l]).abs() if l in keep else None for l in range(L)])
-        freq_diff = pyr.inv_filter_sparse(vals_diff, use_high=False, levels=keep).reshape(r_shape).mean(1) * 30
-        del vals_diff, vals_ada, vals_ph
-        self._tick('pyr.inv_filter(coarse6)')
-        ada_uncertainty = ((freq_diff - filters.median_filter(freq_diff, 50)).abs() * 5).clamp(0, 1)
-        self._tick('median50')
+            phase_uncertainty, ada_uncertainty, freq_diff, h_freq_diff = uncertainty_maps()
         # baseline (:228-238)
         if self.pair_baseline and 2 * B <= self.max_batch_adacof:
             # passes 2 and 3 (:229, :233) are independent: ONE AdaCoFNet call on a 2B batch (twice the tiles for the coarse layers)
@@ -222,6 +232,10 @@ class FusionPipeline(torch.nn.Module):
             inb2 = self.adacof(phase_pred, rgb2, return_warped=False)[2]
         base = self.adacof(inb1, inb2, return_warped=False)[2]
         self._tick('adacofnet#2-4')
+        if fork:
+            main.wait_stream(side)
+            for t in (phase_uncertainty, ada_uncertainty, freq_diff, h_freq_diff):
+                t.record_stream(main)
         # fusion (:324-330)
         other = torch.cat([lab1, lab2], 1)
         maps = torch.stack([ada_uncertainty, phase_uncertainty, flow_var_map], 1)
