@@ -56,7 +56,6 @@ constexpr int CV_THREADS = CV_LOADERS + CV_EPI_THREADS + 128;
 constexpr int CV_REGS_LOADER = 152, CV_REGS_EPI = 144, CV_REGS_MISC = 56;
 constexpr int CV_REGS_LAUNCH = 65536 / CV_THREADS;      // what __launch_bounds__(CV_THREADS, 1) gives every thread
 static_assert(CV_LOADERS * CV_REGS_LOADER + CV_EPI_THREADS * CV_REGS_EPI + 128 * CV_REGS_MISC <= 65536, "register pool");
-constexpr int CV_PROJ_MAX = 8, CV_PROJ_CIN = 64;        // fused 1x1 projection in the epilogue: at most 64 -> 8
 constexpr int CV_MAX_ASTAGES = 4;
 constexpr int CV_MAX_BSTAGES = 4;
 constexpr unsigned CV_SPIN_LIMIT = 200u * 1000u * 1000u;   // bounded waits: trap instead of hanging the GPU
@@ -86,13 +85,6 @@ struct ConvArgs {
     unsigned a_stage_bytes, b_stage_bytes;
     const float* res;      // optional residual [B,H,W,>=Cout] NHWC added AFTER the activation (U-Net skip connections), or null
     int ldr;               // floats per pixel of the residual
-    // optional fused 1x1 projection of the activated outputs (PhaseNet's prediction map on top of its feature map,
-    // src/phase_net/phase_net.py:197-200): y2[pixel][o] = act2(b2[o] + sum_c w2[o][c] * y[pixel][c]), o < cout2 <= 8, Cout <= 64.
-    // The weights travel in the kernel parameters (constant bank: FFMA takes them as immediate-offset operands).
-    int cout2, act2, ldy2;
-    float* y2;
-    float b2[CV_PROJ_MAX];
-    float w2[CV_PROJ_MAX][CV_PROJ_CIN];
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -348,8 +340,7 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvArgs& A, int tile) {
     return t;
 }
 
-// PROJ: the fused 1x1 projection epilogue (ConvArgs::cout2) is compiled into dedicated instantiations only
-template <int ACT, int PREC, bool PROJ = false>
+template <int ACT, int PREC>
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [A stages: hi, lo] [B stages] [barriers] [tmem ptr] [pixoff] [bias]
@@ -463,17 +454,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                         if (n0 + i < A.cout_store) dst[n0 + i] = v[i];
                 }
             };
-            float acc2[CV_PROJ_MAX];                                       // fused projection of the current pixel (A.cout2 > 0)
-            auto project16 = [&](auto N0, const float* v) {               // N0: compile-time channel offset -> immediate constant operands
-                constexpr int n0c = decltype(N0)::value;
-#pragma unroll
-                for (int o = 0; o < CV_PROJ_MAX; ++o) {
-                    float a = (n0c == 0) ? A.b2[o] : acc2[o];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) a = fmaf(v[i], A.w2[o][n0c + i], a);
-                    acc2[o] = a;
-                }
-            };
             auto emit = [&](int t, int n0, const float* r, float smax, float sinv) {
                 float v[16];
 #pragma unroll
@@ -508,23 +488,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     }
                 }
                 store16(t, n0, v);
-                if (PROJ && ACT != ACT_SOFTMAX && A.cout2) {
-                    switch (n0 >> 4) {
-                        case 0: project16(std::integral_constant<int, 0>{}, v); break;
-                        case 1: project16(std::integral_constant<int, 16>{}, v); break;
-                        case 2: project16(std::integral_constant<int, 32>{}, v); break;
-                        default: project16(std::integral_constant<int, 48>{}, v); break;
-                    }
-                    if (n0 + 16 >= A.Npad) {                                // all channels of this pixel seen: finish and store
-                        const int ocol = T.x0 + t * 8 + (m & 7);
-                        if (orow < A.H && ocol < A.W) {
-                            float* d2 = A.y2 + (((size_t)T.img * A.H + orow) * A.W + ocol) * A.ldy2;
-#pragma unroll
-                            for (int o = 0; o < CV_PROJ_MAX; ++o)
-                                if (o < A.cout2) d2[o] = (A.act2 == ACT_TANH) ? apply_act<ACT_TANH>(acc2[o]) : acc2[o];
-                        }
-                    }
-                }
             };
             if (ACT == ACT_SOFTMAX) {
                 for (int t = 0; t < A.MT; ++t) {
@@ -926,14 +889,7 @@ static int* overflow_flag() {      // one device word per device, zero-initialis
 }
 
 template <int PREC>
-static void (*pick_kernel(int activation, bool proj))(const ConvArgs) {
-    if (proj) {                       // fused projection epilogue: the activations PhaseNet / FusionNet-style blocks use
-        switch (activation) {
-            case ACT_RELU: return conv_split_kernel<ACT_RELU, PREC, true>;
-            case ACT_ELU: return conv_split_kernel<ACT_ELU, PREC, true>;
-            default: return nullptr;
-        }
-    }
+static void (*pick_kernel(int activation))(const ConvArgs) {
     switch (activation) {
         case ACT_RELU: return conv_split_kernel<ACT_RELU, PREC>;
         case ACT_ELU: return conv_split_kernel<ACT_ELU, PREC>;
@@ -995,15 +951,6 @@ extern "C" int fvfi_conv2d_nhwc_residual(const float* x, int x_pixel_stride, con
                                          const float* residual, int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H,
                                          int W, int Cin, int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw,
                                          int precision, void* stream) {
-    return fvfi_conv2d_nhwc_proj(x, x_pixel_stride, packed_weight, bias, residual, residual_pixel_stride, y, y_pixel_stride, B, H, W, Cin,
-                                 Cout, KH, KW, pad_mode, activation, out_nchw, precision, nullptr, nullptr, nullptr, 0, 0, 0, stream);
-}
-
-extern "C" int fvfi_conv2d_nhwc_proj(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias,
-                                     const float* residual, int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H,
-                                     int W, int Cin, int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw,
-                                     int precision, const float* proj_weight_host, const float* proj_bias_host, float* y2,
-                                     int y2_pixel_stride, int cout2, int activation2, void* stream) {
     FVFI_CHECK_ARG(!residual || (activation != ACT_SOFTMAX && residual_pixel_stride >= Cout),
                    "conv2d: a residual needs a pixel stride >= Cout and no softmax");
     FVFI_CHECK_ARG(x && packed_weight && y, "conv2d: null pointer");
@@ -1018,19 +965,6 @@ extern "C" int fvfi_conv2d_nhwc_proj(const float* x, int x_pixel_stride, const f
     a.x = x; a.hdr = packed_weight; a.wpack = packed_weight + CV_HDR; a.bias = bias; a.y = y;
     a.ldx = x_pixel_stride; a.ldy = y_pixel_stride; a.out_nchw = (out_nchw == 1) ? 1 : 0;
     a.res = residual; a.ldr = residual_pixel_stride;
-    a.cout2 = 0;
-    if (y2) {
-        FVFI_CHECK_ARG(proj_weight_host && cout2 >= 1 && cout2 <= CV_PROJ_MAX && Cout <= CV_PROJ_CIN && (Cout & 15) == 0,
-                       "conv2d: the fused projection needs Cout in {16,32,48,64} and 1..%d projected channels", CV_PROJ_MAX);
-        FVFI_CHECK_ARG(activation != ACT_SOFTMAX && out_nchw != 1 && y2_pixel_stride >= cout2,
-                       "conv2d: the fused projection needs an NHWC output without softmax");
-        FVFI_CHECK_ARG(activation2 == ACT_NONE || activation2 == ACT_TANH, "conv2d: projection activation must be none (0) or tanh (3)");
-        a.cout2 = cout2; a.act2 = activation2; a.ldy2 = y2_pixel_stride; a.y2 = y2;
-        for (int o = 0; o < CV_PROJ_MAX; ++o) {
-            a.b2[o] = (o < cout2 && proj_bias_host) ? proj_bias_host[o] : 0.f;
-            for (int c = 0; c < CV_PROJ_CIN; ++c) a.w2[o][c] = (o < cout2 && c < Cout) ? proj_weight_host[(size_t)o * Cout + c] : 0.f;
-        }
-    }
     a.cout_store = (out_nchw == 2) ? ((Cout + 15) & ~15) : Cout;
     FVFI_CHECK_ARG(out_nchw >= 0 && out_nchw <= 2, "conv2d: output layout must be 0 (NHWC), 1 (NCHW) or 2 (NHWC, zero-padded channels)");
     FVFI_CHECK_ARG(out_nchw != 2 || y_pixel_stride >= a.cout_store, "conv2d: padded NHWC output needs a pixel stride >= round16(Cout)");
@@ -1041,9 +975,7 @@ extern "C" int fvfi_conv2d_nhwc_proj(const float* x, int x_pixel_stride, const f
     if (int rc = conv_geometry(a, precision, &smem)) return rc;
     const int nsm = sm_count();
     dim3 grid((unsigned)std::min(a.ntiles, nsm > 0 ? nsm : 148), 1, 1);
-    void (*kern)(const ConvArgs) = (precision == PREC_F16X3) ? pick_kernel<PREC_F16X3>(activation, a.cout2 > 0)
-                                                             : pick_kernel<PREC_TF32X3>(activation, a.cout2 > 0);
-    FVFI_CHECK_ARG(kern != nullptr, "conv2d: the fused projection is available after ReLU / ELU only");
+    void (*kern)(const ConvArgs) = (precision == PREC_F16X3) ? pick_kernel<PREC_F16X3>(activation) : pick_kernel<PREC_TF32X3>(activation);
     FVFI_SMEM_OPT_IN(kern, smem);
     kern<<<grid, CV_THREADS, smem, (cudaStream_t)stream>>>(a);
     FVFI_LAUNCH_CHECK();

@@ -176,34 +176,14 @@ def to_nhwc(x):
     return x.contiguous(memory_format=torch.channels_last)
 
 
-def _proj_host(proj):
-    """Host copy (ctypes float arrays) of a 1x1 projection's weight / bias for the kernel-parameter path, per weight version."""
-    import ctypes
-    w, b = proj.weight, proj.bias
-    key = (w.data_ptr(), w._version, None if b is None else b._version)
-    hit = proj.__dict__.get("_fvfi_proj_host")
-    if hit is None or hit[0] != key:
-        wh = w.detach().reshape(w.shape[0], -1).float().cpu().contiguous()
-        bh = None if b is None else b.detach().float().cpu().contiguous()
-        wa = (ctypes.c_float * wh.numel()).from_buffer_copy(wh.numpy().tobytes())
-        ba = None if bh is None else (ctypes.c_float * bh.numel()).from_buffer_copy(bh.numpy().tobytes())
-        hit = (key, wa, ba)
-        proj.__dict__["_fvfi_proj_host"] = hit
-    return hit[1], hit[2]
-
-
-def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_out=False, pad_out=False, residual=None,
-           proj=None, proj_act=None):
+def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_out=False, pad_out=False, residual=None):
     """x [B,Cin,H,W] (any memory format; channels_last avoids a copy) -> [B,Cout,H,W] channels_last
     (``nchw_out=True``: plain contiguous NCHW, written directly by the epilogue).
     Equivalent to act(F.conv2d(pad(x), weight, bias)) with 'same' padding (K//2) in zeros or reflect mode;
     act 'softmax' is over the channel dimension.
     ``residual`` (channels_last [B,Cout,H,W]): added after the activation in the epilogue (skip connection).
     ``pad_out=True``: the result has round16(Cout) channels, the extra ones zero (keeps 16-byte accesses for channel
-    counts such as 25).  ``x`` may carry such zero padding channels beyond the weight's Cin.
-    ``proj`` (an nn.Conv2d with a 1x1 kernel, <= 8 outputs; Cout in {16,32,48,64}; act relu / elu): the projection
-    ``proj_act(proj(y))`` is computed in the same kernel's epilogue and ``(y, projection)`` is returned (PhaseNet's prediction map
-    on top of its feature map, phase_net.py:197-200: the feature map is not read again)."""
+    counts such as 25).  ``x`` may carry such zero padding channels beyond the weight's Cin."""
     if not x.is_cuda:
         raise NotImplementedError("fvfi.conv.conv2d: CUDA tensors only")
     if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
@@ -240,20 +220,6 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
         if timing is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        y2 = None
-        if proj is not None:
-            assert len(parts) == 1 and not nchw_out and not pad_out and act in ("relu", "elu") and proj.kernel_size == (1, 1)
-            assert proj.in_channels == Cout and proj.out_channels <= 8 and Cout <= 64 and Cout % 16 == 0
-            import ctypes
-            wa, ba = _proj_host(proj)
-            y2 = torch.empty((B, proj.out_channels, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
-            (o, n, buf) = parts[0]
-            _lib.check(L.fvfi_conv2d_nhwc_proj(xc.data_ptr(), ldx, buf.data_ptr(), None if b is None else b.data_ptr(),
-                                               None if rc is None else rc.data_ptr(), 0 if rc is None else rc.stride(3),
-                                               out.data_ptr(), ldy, B, H, W, Cin, n, KH, KW, pad_mode, ACT[act], 0, precision,
-                                               ctypes.cast(wa, ctypes.c_void_p), None if ba is None else ctypes.cast(ba, ctypes.c_void_p),
-                                               y2.data_ptr(), y2.stride(3), proj.out_channels, ACT[proj_act], _lib.stream_ptr()))
-            parts = []
         for (o, n, buf) in parts:
             _lib.check(L.fvfi_conv2d_nhwc_residual(xc.data_ptr(), ldx, buf.data_ptr(), None if b is None else b.data_ptr() + 4 * o,
                                                    None if rc is None else rc.data_ptr() + 4 * o, 0 if rc is None else rc.stride(3),
@@ -261,8 +227,8 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
                                                    1 if nchw_out else (2 if pad_out else 0), precision, _lib.stream_ptr()))
         if timing is not None:
             e1.record()
-            timing.append((2.0 * B * H * W * Cin * Cout * KH * KW, e0, e1, max(len(parts), 1), (B, Cin, Cout, KH, H, W, act)))
-    return out if proj is None else (out, y2)
+            timing.append((2.0 * B * H * W * Cin * Cout * KH * KW, e0, e1, len(parts), (B, Cin, Cout, KH, H, W, act)))
+    return out
 
 
 def _conv1x1_direct(xc, weight, bias, act):
@@ -355,14 +321,13 @@ def avg_pool2(x, _fn="fvfi_avg_pool2_nhwc"):
     return out
 
 
-def conv_module(conv, x, act=None, nchw_out=False, pad_out=False, residual=None, proj=None, proj_act=None):
+def conv_module(conv, x, act=None, nchw_out=False, pad_out=False, residual=None):
     """Run an nn.Conv2d (stride 1, dilation 1, padding == K//2) through the tensor-core kernel."""
     k = conv.kernel_size[0]
     assert conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
     assert conv.padding == (k // 2, k // 2) or (k == 1 and conv.padding == (0, 0))
     mode = "zeros" if k == 1 else conv.padding_mode
-    return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out, pad_out=pad_out, residual=residual, proj=proj,
-                  proj_act=proj_act)
+    return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out, pad_out=pad_out, residual=residual)
 
 
 def conv_bn_module(conv, bn, x, act=None):

@@ -41,14 +41,8 @@ class PhaseNetBlock(nn.Module):
         if tc.use_tc(x) and not self.training:
             # tcgen05 path: conv+BN(folded)+ELU, conv+ELU, 1x1 conv+tanh -- three fused kernels (phase_net.py:190-200)
             f = tc.conv_bn_module(self.feature_map[0], self.feature_map[1], x, "elu")
-            pm = self.prediction_map[0]
-            if self.feature_map[3].out_channels in (16, 32, 48, 64) and pm.out_channels <= 8 and pm.kernel_size == (1, 1):
-                # conv + ELU and the 1x1 prediction map + tanh in ONE kernel: the projection runs in the convolution's epilogue
-                # on the 64 activated channels it just produced (the feature map is not read again)
-                f, c = tc.conv_module(self.feature_map[3], f, "elu", proj=pm, proj_act="tanh")
-                return f, c
             f = tc.conv_module(self.feature_map[3], f, "elu")
-            c = tc.conv_module(pm, f, "tanh")
+            c = tc.conv_module(self.prediction_map[0], f, "tanh")
             return f, c
         f = self.feature_map(x)
         c = self.prediction_map(f)

@@ -132,15 +132,6 @@ int fvfi_conv2d_nhwc_residual(const float* x, int x_pixel_stride, const float* p
                               const float* residual, int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H,
                               int W, int Cin, int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw,
                               int precision, void* stream);
-/* Same with a 1x1 projection of the activated outputs fused into the epilogue (PhaseNet's prediction map on top of its feature
- * map, src/phase_net/phase_net.py:197-200):  y2[pixel][o] = act2(proj_bias[o] + sum_c proj_weight[o][c] * y[pixel][c]),
- * o < cout2 <= 8, Cout in {16,32,48,64}; activation2: 0 none, 3 tanh.  proj_weight_host [cout2][Cout] and proj_bias_host [cout2] are
- * HOST pointers (they are passed to the kernel as parameters); y2 [B,H,W,cout2] NHWC with y2_pixel_stride floats per pixel.
- * y2 == NULL is fvfi_conv2d_nhwc_residual. */
-int fvfi_conv2d_nhwc_proj(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias, const float* residual,
-                          int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H, int W, int Cin, int Cout, int KH,
-                          int KW, int pad_mode, int activation, int out_nchw, int precision, const float* proj_weight_host,
-                          const float* proj_bias_host, float* y2, int y2_pixel_stride, int cout2, int activation2, void* stream);
 /* FVFI_CONV_F16X3 scales activations by 2^4 before the fp16 split; |x| > 4094 would leave fp16's range.  Returns 1
  * (and clears the flag) if any convolution since the last call saw such a value, 0 if not, -1 on error.
  * Synchronises the device. */

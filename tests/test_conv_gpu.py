@@ -99,33 +99,6 @@ def test_resize_bilinear_nhwc_matches_torch(align):
         assert float((got - (F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=align) + sk)).abs().max()) <= 2e-6
 
 
-@pytest.mark.parametrize("k", [1, 3])
-@pytest.mark.parametrize("cout,cout2", [(64, 8), (64, 1), (32, 5), (16, 8)])
-def test_conv_fused_projection_epilogue(prec, k, cout, cout2):
-    """fvfi_conv2d_nhwc_proj: act(conv(x)) and tanh(1x1 projection of it) from ONE kernel (PhaseNetBlock: feature map + prediction map,
-    phase_net.py:190-200) against fp64 convolutions; ragged image sizes (partial tiles), reflect padding."""
-    from fvfi import conv
-    g = torch.Generator(device="cuda").manual_seed(11)
-    for (B, H, W, cin) in [(2, 37, 53, 88), (1, 16, 8, 64), (1, 9, 70, 24)]:
-        x = torch.randn((B, cin, H, W), device="cuda", generator=g)
-        c1 = torch.nn.Conv2d(cin, cout, k, padding=k // 2, padding_mode="reflect" if k > 1 else "zeros").cuda()
-        pm = torch.nn.Conv2d(cout, cout2, 1).cuda()
-        with torch.no_grad():
-            for act, fn in (("elu", F.elu), ("relu", F.relu)):
-                y, z = conv.conv_module(c1, x, act, proj=pm, proj_act="tanh")
-                xd = x.double()
-                xp = F.pad(xd, (k // 2,) * 4, mode="reflect") if k > 1 else xd
-                ry = fn(F.conv2d(xp, c1.weight.double(), c1.bias.double()))
-                rz = torch.tanh(F.conv2d(ry, pm.weight.double(), pm.bias.double()))
-                assert y.shape == ry.shape and z.shape == rz.shape
-                assert float((y - ry).abs().max()) <= 2e-5 * max(1.0, float(ry.abs().max()))
-                assert float((z - rz).abs().max()) <= 3e-6
-                # identical to the two-kernel form's feature map, bit for bit (same accumulators, same epilogue arithmetic)
-                assert torch.equal(y, conv.conv_module(c1, x, act))
-            y, z = conv.conv_module(c1, x, "elu", proj=pm, proj_act=None)
-            assert float((z - F.conv2d(F.elu(F.conv2d(xp, c1.weight.double(), c1.bias.double())), pm.weight.double(), pm.bias.double())).abs().max()) <= 2e-5
-
-
 def test_conv_softmax_and_nchw_epilogues(prec):
     from fvfi import conv
     g = torch.Generator(device="cuda").manual_seed(2)
