@@ -45,7 +45,10 @@ constexpr int PYR_THREADS = 256;
 #ifndef PYR_MIN_CTAS
 #define PYR_MIN_CTAS 3
 #endif
-constexpr size_t COL_SMEM_MAX = 113 * 1024;       // in-place column tile: two CTAs per SM
+#ifndef COL_SMEM_KB
+#define COL_SMEM_KB 76
+#endif
+constexpr size_t COL_SMEM_MAX = COL_SMEM_KB * 1024;   // in-place column tile: at least three CTAs per SM (two for the 113 KB of round 1)
 constexpr size_t ROW_SMEM_TARGET = 72 * 1024;     // row batch: three CTAs per SM
 constexpr int SMALL_LEVEL_ELEMS = 300 * 520;      // levels at or below this size share one launch per pass
 
