@@ -3,9 +3,11 @@
 
 Tolerances (fp32 kernels vs fp64 oracle; coefficients are NOT normalised -- a band at level l has
 magnitude ~ image_sum/(h_l w_l)-scaled spectra, so errors are stated relative to the level max):
-  complex band coefficients : 1e-5 * max|band level|   (3e-6 of it is the closed-form angular mask vs
-                                                        the oracle's 1024-step LUT)
-  reconstruction            : 3e-5 absolute on [0,1] images (north star: 1e-4)
+  complex band coefficients : 2e-6 * max|band level|   (measured 4-9e-7; the band masks are tabulated exactly as the published
+                                                        algorithm computes them -- round 1's closed-form angular factor needed 1e-5)
+  reconstruction            : 5e-6 absolute on [0,1] images (north star: 1e-4)
+Sizes include the benchmark's 1080x1920 (height 17: Rader lengths 764 = 4*191, 1358 = 14*97, 382, 679, 241, 191 ... in both passes,
+bulk-copied rows) and 184x328 (Rader 23, 29, 41 and their multiples).
 """
 import glob
 import os
@@ -18,7 +20,7 @@ from oracle import steerable_shim as ss
 
 pytestmark = pytest.mark.gpu
 S2 = np.sqrt(2)
-CASES = [(2, 256, 256, 12), (1, 90, 150, 8), (2, 135, 241, 9), (3, 48, 64, 6), (1, 33, 57, 5)]
+CASES = [(2, 256, 256, 12), (1, 90, 150, 8), (2, 135, 241, 9), (3, 48, 64, 6), (1, 33, 57, 5), (1, 184, 328, 12), (1, 1080, 1920, 17)]
 
 
 def _img(N, H, W, seed=0):
@@ -39,7 +41,7 @@ def test_build_complex_vs_oracle(N, H, W, height):
         for b in range(4):
             assert got[l][b].shape == ref[l][b].shape
             err = float((got[l][b].cpu() - ref[l][b]).abs().max())
-            assert err <= 1e-5 * scale, (l, b, err, scale)
+            assert err <= 2e-6 * scale, (l, b, err, scale)
 
 
 @pytest.mark.parametrize("N,H,W,height", CASES)
@@ -55,13 +57,13 @@ def test_reconstruct_complex_vs_oracle(N, H, W, height):
     gpyr = SCFpyr_PyTorch(height=height, nbands=4, scale_factor=S2, device="cuda")
     dev = [c2[0].cuda()] + [[b.cuda() for b in lv] for lv in c2[1:-1]] + [c2[-1].cuda()]
     got = gpyr.reconstruct(dev)
-    assert float((got.cpu() - ref).abs().max()) <= 3e-5
+    assert float((got.cpu() - ref).abs().max()) <= 5e-6
     # skipped level (int 0) == zero contribution
     dev0 = list(dev)
     dev0[2] = 0
     c0 = list(c2)
     c0[2] = 0
-    assert float((gpyr.reconstruct(dev0).cpu() - opyr.reconstruct(c0)).abs().max()) <= 3e-5
+    assert float((gpyr.reconstruct(dev0).cpu() - opyr.reconstruct(c0)).abs().max()) <= 5e-6
 
 
 @pytest.mark.parametrize("N,H,W,height", CASES)
@@ -79,10 +81,10 @@ def test_filter_round_trip_and_values(N, H, W, height):
         z = torch.stack([torch.view_as_complex(b) for b in oc[1 + l]], 1).reshape(N * 4, 1, h, w)  # plane*nb + band
         scale = float(z.abs().max())
         amp, ph = vals.amplitude[l].cpu(), vals.phase[l].cpu()
-        assert float((amp - z.abs()).abs().max()) <= 1e-5 * scale
+        assert float((amp - z.abs()).abs().max()) <= 2e-6 * scale
         # polar -> complex comparison avoids the ill-conditioned phase of near-zero coefficients
         zz = torch.polar(amp, ph)
-        assert float((zz - z.to(torch.complex64)).abs().max()) <= 1.5e-5 * scale
+        assert float((zz - z.to(torch.complex64)).abs().max()) <= 3e-6 * scale
         assert float(ph.abs().max()) <= np.pi + 1e-6
         # fused per-(level, plane) max amplitude (PhaseNet.normalize_vals, phase_net.py:47-59)
         want = amp.reshape(N, -1).max(1)[0]
@@ -92,7 +94,7 @@ def test_filter_round_trip_and_values(N, H, W, height):
     # reference point is the oracle's round trip, not the image
     opyr = ss.SCFpyr_PyTorch(height=height, nbands=4, scale_factor=S2, precision="fp64")
     orec = opyr.reconstruct(oc)
-    assert float((rec.cpu() - orec).abs().max()) <= 3e-5
+    assert float((rec.cpu() - orec).abs().max()) <= 5e-6
     if min(H, W) >= 48:
         assert float((rec.cpu() - img).abs().max()) <= 4e-5
     # dropping components == zero-filled copies (utils.py:242-320)
