@@ -149,10 +149,13 @@ __device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, unsigned long long 
 // N = 2*Npad.  WIDE (Npad <= 32): the packed weights hold [B_hi; B_lo] as one 2*Npad-row operand, so  A_hi x [B_hi; B_lo]
 // is ONE MMA writing two accumulators (columns [0,Npad) and [Npad,2Npad), summed by the epilogue) and A_lo x B_hi a second
 // one: two instead of three reads of the 4 KB A tile, which is what bounds an SS-mode MMA with N <= 64.
-#define FVFI_MMA3(KIND, D, AL, AH)                                                        \
-    "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AL ", %4, %6, pa;\n\t"        \
-    "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AH ", %5, %6, pt;\n\t"        \
-    "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AH ", %4, %6, pt;\n\t"
+// The second and third product of a step share their A operand (A_hi): the second MMA keeps it in the tensor core's A collector
+// buffer (collector::a::fill, SASS .A_KEEP), the third takes it from there (collector::a::lastuse, .A_REUSE) -- two instead of
+// three shared-memory reads of the 4 KB A tile per step, the traffic that bounds the N = 64 layers.
+#define FVFI_MMA3(KIND, D, AL, AH)                                                                            \
+    "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AL ", %4, %6, pa;\n\t"                            \
+    "@pe tcgen05.mma.cta_group::1.kind::" KIND ".collector::a::fill [" D "], " AH ", %5, %6, pt;\n\t"         \
+    "@pe tcgen05.mma.cta_group::1.kind::" KIND ".collector::a::lastuse [" D "], " AH ", %4, %6, pt;\n\t"
 #define FVFI_MMA2W(KIND, D, AL, AH)                                                       \
     "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AH ", %4, %8, pa;\n\t"        \
     "@pe tcgen05.mma.cta_group::1.kind::" KIND " [" D "], " AL ", %4, %6, pt;\n\t"
