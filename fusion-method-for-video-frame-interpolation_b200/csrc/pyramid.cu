@@ -107,6 +107,7 @@ struct fvfi_pyr_plan {
     std::vector<const float*> radial;           // device, per level (index L = low-pass product)
     std::vector<const float*> band_build, band_rec;   // device, per band level: [nb][h_l][w_l] combined radial x angular masks
     const float* hi0 = nullptr;                 // device [H*W], unshifted
+    const float* hf_transfer = nullptr;         // device [H*W]: transfer function of  reconstruct(high + finest level of decompose(x))
     std::map<std::pair<int, int>, fvfi::FftPlan> fft_cache;   // (length, stockham) -> plan with device tables
     std::vector<void*> owned;
     size_t level_elems = 0;                     // sum_l h_l*w_l  (l = 0..L)
@@ -274,8 +275,9 @@ static int build_plan(fvfi_pyr_plan* p) {
     auto clean = [](double v) { return fabs(v) < 1e-12 ? 0.0 : v; };
 
     // hi0 on the full grid
+    std::vector<float> hi0_host((size_t)H * W);
     {
-        std::vector<float> t((size_t)H * W);
+        std::vector<float>& t = hi0_host;
         for (int ky = 0; ky < H; ++ky)
             for (int kx = 0; kx < W; ++kx)
                 t[(size_t)ky * W + kx] = (float)clean(interp(log_rad(sfreq_h(ky, H), sfreq_h(kx, W)), Xr, Yr));
@@ -367,6 +369,23 @@ static int build_plan(fvfi_pyr_plan* p) {
             }
             if (int rc = upload(p, t1, &p->band_build[l])) return rc;
             if (int rc = upload(p, t2, &p->band_rec[l])) return rc;
+            if (l == 0) {
+                // Decomposing an image and reconstructing ONLY its high residual and finest band level (get_last_value_levels(., 1),
+                // src/train/utils.py:242-280) is a linear filter: Re IFFT2( X * T ),  T = hi0^2 + sum_b (D_0 A_b^one)(D_0 A_b^two)
+                // ((-i)^(nb-1) (i)^(nb-1) = 1; the coefficients pass through amplitude / phase and back unchanged).  The real part of
+                // the inverse transform symmetrises the spectrum, and X is Hermitian (real image): T_sym(k) = (T(k) + T(-k)) / 2.
+                std::vector<double> T(plane);
+                for (size_t o = 0; o < plane; ++o) {
+                    double v = (double)hi0_host[o] * hi0_host[o];
+                    for (int b = 0; b < nb; ++b) v += (double)t1[b * plane + o] * (double)t2[b * plane + o];
+                    T[o] = v;
+                }
+                std::vector<float> Ts(plane);
+                for (int ky = 0; ky < hl; ++ky)
+                    for (int kx = 0; kx < wl; ++kx)
+                        Ts[(size_t)ky * wl + kx] = (float)(0.5 * (T[(size_t)ky * wl + kx] + T[(size_t)((hl - ky) % hl) * wl + (wl - kx) % wl]));
+                if (int rc = upload(p, Ts, &p->hf_transfer)) return rc;
+            }
         }
     }
     // angular parameters
@@ -521,7 +540,8 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_fwd(const Le
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_fwd(const LevelJob* __restrict__ jobs, const LaunchSet S, AngParams A,
                                                              const float2* __restrict__ regionB, float2* __restrict__ outbase,
-                                                             size_t out_stride, int add_c_off, int use_radial) {
+                                                             size_t out_stride, int add_c_off, int use_radial,
+                                                             const float* __restrict__ radial_override) {
     extern __shared__ float2 smem[];
     const SetEntry& E = find_entry(S, blockIdx.x);
     const LevelJob& J = jobs[E.job];
@@ -572,7 +592,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_fwd(const Le
             __syncthreads();
         }
     }
-    const float* radial = (use_radial && !combine) ? J.radial : nullptr;      // combine: the radial mask is part of band_rec
+    const float* radial = (use_radial && !combine) ? (radial_override ? radial_override : J.radial) : nullptr;   // combine: part of band_rec
     float2* dst = outbase + (size_t)n * out_stride + (add_c_off ? (size_t)J.c_off : 0);
     for (int q = threadIdx.x; q < E_; q += blockDim.x) {
         const int pos = q >> cs, c = q & (CT - 1);
@@ -871,10 +891,11 @@ static int launch_rows_fwd(const fvfi_pyr_plan* p, const SetBuilder& sb, const P
 }
 
 static int launch_cols_fwd(const fvfi_pyr_plan* p, const SetBuilder& sb, int N, const float2* regionB, float2* out, size_t stride,
-                           int add_c_off, int use_radial, cudaStream_t s) {
+                           int add_c_off, int use_radial, cudaStream_t s, const float* radial_override = nullptr) {
     if (int rc = ensure_smem(k_cols_fwd, sb.cols_smem)) return rc;
     dim3 grid(sb.cols.total, 1, N);
-    k_cols_fwd<<<grid, PYR_THREADS, sb.cols_smem, s>>>(p->d_jobs, sb.cols, p->ang_rec, regionB, out, stride, add_c_off, use_radial);
+    k_cols_fwd<<<grid, PYR_THREADS, sb.cols_smem, s>>>(p->d_jobs, sb.cols, p->ang_rec, regionB, out, stride, add_c_off, use_radial,
+                                                       radial_override);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }
@@ -1045,6 +1066,33 @@ static int reconstruct(const fvfi_pyr_plan* p, const float* high, const float* c
     return launch_rows_inv(p, fin, mnone, N, ws.B, s);
 }
 
+// reconstruct(high + finest level of decompose(img)) as ONE spectral multiplication (plan table hf_transfer): 2 FFT2 instead of 10.
+static int highband_filter(const fvfi_pyr_plan* p, const float* img, int N, float* out, void* workspace, cudaStream_t s) {
+    const int H = p->H, W = p->W, FULL = p->L + 1;
+    Workspace ws = carve(p, N, workspace);
+    PtrTable none{};
+    MutPtrTable mnone{};
+    SetBuilder sb(p);
+    sb.add(FULL, 0, img, nullptr, nullptr, nullptr, nullptr, false);
+    if (int rc = launch_rows_fwd(p, sb, none, N, ws.B, s)) return rc;
+    if (int rc = launch_cols_fwd(p, sb, N, ws.B, ws.A, (size_t)H * W, 0, 1, s, p->hf_transfer)) return rc;
+    GatherArgs G{};
+    G.nlev = 0;
+    G.active = 0;
+    G.Y = ws.C;
+    G.plane_stride = p->level_elems;
+    G.Yhigh = ws.A;
+    const LevelJob& J = p->jobs[FULL];
+    const size_t smem = col_smem(J, false);
+    if (int rc = ensure_smem(k_cols_inv_gather, smem)) return rc;
+    dim3 grid(J.col_tiles, 1, N);
+    k_cols_inv_gather<<<grid, PYR_THREADS, smem, s>>>(p->d_jobs, FULL, G, p->ang_rec.inv_hh, p->ang_rec.inv_hw, ws.B);
+    FVFI_LAUNCH_CHECK();
+    SetBuilder fin(p);
+    fin.add(FULL, 0, nullptr, nullptr, out, nullptr, nullptr, false);
+    return launch_rows_inv(p, fin, mnone, N, ws.B, s);
+}
+
 // Backward of reconstruct(): img = Re M(high, bands, low) is real-linear in the complex bands, so dL/d(band) = M^H dL/d(img):
 //   FFT2 of the image gradient, then per level the SAME crop / radial mask as the forward, the conjugated two-sided angular
 //   factor, an unnormalised IFFT2 at the level size and 1/(H*W) -- i.e. the decomposition machinery with the reconstruction's
@@ -1162,6 +1210,12 @@ int fvfi_pyr_reconstruct_complex(const fvfi_pyr_plan* p, const float* high, cons
                                  const float* low, int N, float* img, void* workspace, void* stream) {
     FVFI_CHECK_ARG(p && bands && img && workspace && N > 0 && N <= 65535, "pyr_reconstruct_complex: bad argument");
     return reconstruct(p, high, nullptr, nullptr, bands, low, N, img, workspace, (cudaStream_t)stream);
+}
+
+int fvfi_pyr_highband_filter(const fvfi_pyr_plan* p, const float* img, int N, float* out, void* workspace, void* stream) {
+    FVFI_CHECK_ARG(p && img && out && workspace && N > 0 && N <= 65535, "pyr_highband_filter: bad argument");
+    FVFI_CHECK_ARG(p->L >= 1 && p->hf_transfer, "pyr_highband_filter: the plan has no band level");
+    return highband_filter(p, img, N, out, workspace, (cudaStream_t)stream);
 }
 
 int fvfi_pyr_reconstruct_backward(const fvfi_pyr_plan* p, const float* grad_img, int N, const float* const* phase,

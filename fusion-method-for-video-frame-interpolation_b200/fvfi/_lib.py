@@ -63,6 +63,7 @@ _PROTOS = {
     "fvfi_pyr_workspace_bytes": (c_size, [c_fp, c_int]),
     "fvfi_pyr_decompose": (c_int, [c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "fvfi_pyr_reconstruct": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp]),
+    "fvfi_pyr_highband_filter": (c_int, [c_fp, c_fp, c_int, c_fp, c_fp, c_fp]),
     "fvfi_pyr_reconstruct_backward": (c_int, [c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "fvfi_pyr_build_complex": (c_int, [c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "fvfi_pyr_reconstruct_complex": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp]),

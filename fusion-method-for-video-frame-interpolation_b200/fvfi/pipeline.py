@@ -187,9 +187,8 @@ class FusionPipeline(torch.nn.Module):
                     self._filter("uncertainty", torch.cat((ada_pred.reshape(-1, H, W), phase_pred.reshape(-1, H, W)), 0), want_high=False,
                                  levels=coarse), 2)
                 self._tick('lab2rgb+pyr.filter(6 planes/frame)')
-                v0 = pyr.filter((ada_pred - phase_pred).mean(1), levels=[0])      # reconstructed at once: its phases feed cos / sin only
-                h_diff = pyr.inv_filter_sparse(v0, use_low=False, levels=[0])
-                del v0
+                # ... and recon_{high + level 0}(D(x)) is a linear filter of x: one spectral multiplication (Pyramid.highband_filter)
+                h_diff = pyr.highband_filter((ada_pred - phase_pred).mean(1))
             else:
                 used = sorted(set([0]) | set(coarse))
                 vals_ada, vals_ph = utils.separate_vals(

@@ -160,6 +160,21 @@ class Pyramid:
                                                        plan.workspace(N).data_ptr(), _lib.stream_ptr()))
         return out
 
+    def highband_filter(self, img):
+        """``inv_filter(get_last_value_levels(filter(img), 1))`` (src/train/utils.py:242-280; the h_freq maps of
+        src/fusion_net/interpolate_twoframe.py:205-209): the high residual plus the finest band level of ``img`` [N,H,W], put
+        back together.  One spectral multiplication with a plan table instead of a decomposition and a reconstruction."""
+        if not img.is_cuda:
+            raise NotImplementedError("fvfi pyramid: CUDA tensors only")
+        img = img.contiguous().float()
+        N, H, W = img.shape
+        plan = self._plan(H, W, img.device)
+        out = torch.empty_like(img)
+        with torch.cuda.device(img.device):
+            _lib.check(_lib.lib().fvfi_pyr_highband_filter(plan.handle, img.data_ptr(), N, out.data_ptr(),
+                                                           plan.workspace(N).data_ptr(), _lib.stream_ptr()))
+        return out
+
     def inv_filter_bands(self, bands, N, H, W, high=None):
         """Reconstruction from COMPLEX band coefficients of some levels only: ``bands`` = {level: [nb tensors [N,h,w,2]]}, optionally
         the high-pass residual ``high`` [N,H,W]; the low residual and the other levels are absent (contribute nothing).  -> [N,H,W]."""

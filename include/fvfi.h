@@ -242,6 +242,12 @@ int fvfi_pyr_reconstruct_backward(const fvfi_pyr_plan* plan, const float* grad_i
                                   const float* const* amp, float* grad_high, float* const* grad_phase,
                                   float* const* grad_amp, float* grad_low, void* workspace, void* stream);
 
+/* out[N,H,W] = inv_filter(get_last_value_levels(filter(img), 1)) -- the high residual plus the finest band level of img, put back
+ * together (src/train/utils.py:242-280 with use_levels = 1; the h_freq maps of src/fusion_net/interpolate_twoframe.py:205-209).
+ * Decomposition and reconstruction are linear and nothing touches the coefficients in between, so this is ONE multiplication of
+ * the image spectrum by a real transfer function tabulated in the plan: 2 two-dimensional FFTs instead of 10. */
+int fvfi_pyr_highband_filter(const fvfi_pyr_plan* plan, const float* img, int N, float* out, void* workspace, void* stream);
+
 /* Complex coefficient interface (the SCFpyr_PyTorch.build/reconstruct layout, band tensors
  * [N,h_l,w_l,2], src/train/pyramid.py:58): bands[l*nb + b]. */
 int fvfi_pyr_build_complex(const fvfi_pyr_plan* plan, const float* img, int N, float* high,

@@ -104,6 +104,23 @@ def test_filter_round_trip_and_values(N, H, W, height):
     assert float((a - b).abs().max()) <= 1e-6
 
 
+@pytest.mark.parametrize("N,H,W,height", [(2, 256, 256, 12), (1, 90, 150, 8), (2, 135, 241, 9), (1, 184, 328, 12), (1, 540, 960, 15)])
+def test_highband_filter_equals_decompose_then_reconstruct(N, H, W, height):
+    """Pyramid.highband_filter(x) == inv_filter(get_last_value_levels(filter(x), 1)) (src/train/utils.py:242-280; the h_freq maps
+    of the fusion recipe, interpolate_twoframe.py:205-209): against the oracle's decomposition -> zeroing -> reconstruction in
+    fp64, and against the GPU's own two-step path."""
+    from fvfi.pyramid import Pyramid
+    from oracle import nets
+    img = _img(N, H, W, seed=4) - 0.3             # signed, like the ada - phase difference plane the recipe filters
+    pyr = Pyramid(height=height, nbands=4, scale_factor=S2, device=torch.device("cuda"))
+    got = pyr.highband_filter(img.cuda()).cpu()
+    opyr = nets.Pyramid(height, 4, S2, precision="fp64")
+    ref = opyr.inv_filter(nets.get_last_value_levels(opyr.filter(img.double()), use_levels=1))
+    assert float((got - ref).abs().max()) <= 3e-6
+    two = pyr.inv_filter_sparse(pyr.filter(img.cuda(), levels=[0]), use_low=False, levels=[0]).cpu()
+    assert float((got - two).abs().max()) <= 3e-6
+
+
 def test_golden_reference_wrapper(golden_dir):
     from fvfi.pyramid import Pyramid
     files = sorted(glob.glob(os.path.join(golden_dir, "pyramid_ref_*.npz")))
