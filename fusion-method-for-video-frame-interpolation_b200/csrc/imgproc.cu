@@ -327,28 +327,8 @@ __device__ __forceinline__ void stg256f(float* p, const float* v) {
 }
 
 // VEC = channels per thread: 8 (256-bit accesses), 4 (128-bit) or 1 (any stride / alignment).
-// grid = (column x channel-group blocks, output row PAIRS, images): the row coordinates are uniform per block, nothing is divided
-// per thread when the number of channel groups is a power of two (cg_shift >= 0), and a thread produces the two vertically
-// adjacent output pixels of its column: when upsampling, their source rows coincide or overlap (uniform per block), so the pair
-// costs 4 or 6 source loads instead of 8.
-template <int VEC>
-__device__ __forceinline__ void rs_load(const float* p, float* v) {
-    if (VEC == 8) {
-        ldg256f(p, v);
-    } else if (VEC == 4) {
-        const float4 t = __ldg((const float4*)p);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
-        v[0] = __ldg(p);
-    }
-}
-template <int VEC>
-__device__ __forceinline__ void rs_store(float* p, const float* v) {
-    if (VEC == 8) stg256f(p, v);
-    else if (VEC == 4) *(float4*)p = make_float4(v[0], v[1], v[2], v[3]);
-    else p[0] = v[0];
-}
-
+// grid = (column x channel-group blocks, output rows, images): the row coordinates are uniform per block and nothing is divided
+// per thread when the number of channel groups is a power of two (cg_shift >= 0).
 template <int VEC>
 __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi,
                                                                    int Wi, int Ho, int Wo, int C, int ldx, int ldy,
@@ -359,73 +339,60 @@ __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* 
     const int ox = cg_shift >= 0 ? (int)(q >> cg_shift) : (int)(q / (unsigned)cg_n);
     if (ox >= Wo) return;
     const int ch = (int)(q - (unsigned)ox * (unsigned)cg_n) * VEC;
-    const int oy0 = 2 * blockIdx.y, n = blockIdx.z;
-    const bool two = oy0 + 1 < Ho;
-    // source coordinates exactly as ATen's area_pixel_compute_source_index (rows: uniform per block)
-    float fya, fyb, fx;
+    const int oy = blockIdx.y, n = blockIdx.z;
+    const size_t p = (size_t)oy * Wo + ox;
+    // source coordinates exactly as ATen's area_pixel_compute_source_index
+    float fy, fx;
     if (align_corners) {
-        fya = sy * oy0;
-        fyb = sy * (oy0 + 1);
+        fy = sy * oy;
         fx = sx * ox;
     } else {
-        fya = fmaxf(sy * (oy0 + 0.5f) - 0.5f, 0.f);
-        fyb = fmaxf(sy * (oy0 + 1.5f) - 0.5f, 0.f);
+        fy = fmaxf(sy * (oy + 0.5f) - 0.5f, 0.f);
         fx = fmaxf(sx * (ox + 0.5f) - 0.5f, 0.f);
     }
-    const int x0 = min((int)fx, Wi - 1), x1 = min(x0 + 1, Wi - 1);
-    const float lx = fx - (float)x0, hx = 1.f - lx;
-    const int y0a = min((int)fya, Hi - 1), y1a = min(y0a + 1, Hi - 1);
-    const int y0b = min((int)fyb, Hi - 1), y1b = min(y0b + 1, Hi - 1);
-    const float lya = fya - (float)y0a, hya = 1.f - lya, lyb = fyb - (float)y0b, hyb = 1.f - lyb;
-    const float* X = x + (size_t)n * Hi * Wi * ldx + ch;
-    const size_t c0 = (size_t)x0 * ldx, c1 = (size_t)x1 * ldx;
-    // horizontally interpolated source rows (ReLU on the samples first when asked: Upsample(ReLU(x)), fusion_net.py:61)
-    auto hrow = [&](int yy, float* r) {
-        float a[VEC], b[VEC];
-        const float* row = X + (size_t)yy * Wi * ldx;
-        rs_load<VEC>(row + c0, a);
-        rs_load<VEC>(row + c1, b);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const float u = relu_in ? fmaxf(a[i], 0.f) : a[i], v = relu_in ? fmaxf(b[i], 0.f) : b[i];
-            r[i] = hx * u + lx * v;
+    const int y0 = min((int)fy, Hi - 1), x0 = min((int)fx, Wi - 1);
+    const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float* X = x + (size_t)n * Hi * Wi * ldx;
+    const float* p00 = X + ((size_t)y0 * Wi + x0) * ldx + ch;
+    const float* p01 = X + ((size_t)y0 * Wi + x1) * ldx + ch;
+    const float* p10 = X + ((size_t)y1 * Wi + x0) * ldx + ch;
+    const float* p11 = X + ((size_t)y1 * Wi + x1) * ldx + ch;
+    float* dst = y + ((size_t)n * Ho * Wo + p) * ldy + ch;
+    float a[VEC], b[VEC], c[VEC], d[VEC], o[VEC], e[VEC];
+    const float* ap = addend ? addend + ((size_t)n * Ho * Wo + p) * lda + ch : nullptr;
+    if (VEC == 8) {
+        ldg256f(p00, a); ldg256f(p01, b); ldg256f(p10, c); ldg256f(p11, d);
+        if (ap) ldg256f(ap, e);
+    } else if (VEC == 4) {
+        const float4 a4 = __ldg((const float4*)p00), b4 = __ldg((const float4*)p01), c4 = __ldg((const float4*)p10),
+                     d4 = __ldg((const float4*)p11);
+        a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+        b[0] = b4.x; b[1] = b4.y; b[2] = b4.z; b[3] = b4.w;
+        c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
+        d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
+        if (ap) {
+            const float4 e4 = __ldg((const float4*)ap);
+            e[0] = e4.x; e[1] = e4.y; e[2] = e4.z; e[3] = e4.w;
         }
-    };
-    float r0[VEC], r1[VEC], r2[VEC], r3[VEC], o[VEC], e[VEC];
-    hrow(y0a, r0);
-    hrow(y1a, r1);
-    const size_t pa = (size_t)oy0 * Wo + ox;
-    {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = hya * r0[i] + lya * r1[i];
-        if (addend) {                       // + skip connection (fusion_net.py:62)
-            rs_load<VEC>(addend + ((size_t)n * Ho * Wo + pa) * lda + ch, e);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) o[i] += e[i];
-        }
-        rs_store<VEC>(y + ((size_t)n * Ho * Wo + pa) * ldy + ch, o);
-    }
-    if (!two) return;
-    // second row of the pair: its source rows are the first row's (same interval), share one with it, or are new (uniform branches)
-    const float *t0 = r0, *t1 = r1;
-    if (y0b == y0a && y1b == y1a) {
-    } else if (y0b == y1a) {
-        hrow(y1b, r2);
-        t0 = r1; t1 = r2;
     } else {
-        hrow(y0b, r2);
-        hrow(y1b, r3);
-        t0 = r2; t1 = r3;
+        a[0] = __ldg(p00); b[0] = __ldg(p01); c[0] = __ldg(p10); d[0] = __ldg(p11);
+        if (ap) e[0] = __ldg(ap);
     }
-    const size_t pb = pa + Wo;
+    if (relu_in) {                      // Upsample(ReLU(x)): the activation applies to the source samples (fusion_net.py:61)
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) o[i] = hyb * t0[i] + lyb * t1[i];
-    if (addend) {
-        rs_load<VEC>(addend + ((size_t)n * Ho * Wo + pb) * lda + ch, e);
+        for (int i = 0; i < VEC; ++i) { a[i] = fmaxf(a[i], 0.f); b[i] = fmaxf(b[i], 0.f); c[i] = fmaxf(c[i], 0.f); d[i] = fmaxf(d[i], 0.f); }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+    if (ap) {                           // + skip connection (fusion_net.py:62)
 #pragma unroll
         for (int i = 0; i < VEC; ++i) o[i] += e[i];
     }
-    rs_store<VEC>(y + ((size_t)n * Ho * Wo + pb) * ldy + ch, o);
+    if (VEC == 8) stg256f(dst, o);
+    else if (VEC == 4) *(float4*)dst = make_float4(o[0], o[1], o[2], o[3]);
+    else dst[0] = o[0];
 }
 
 // nn.AvgPool2d(2, 2) on NHWC storage (src/fusion_net/fusion_adacofnet.py:62-70): one thread = one output pixel x VEC channels
@@ -651,8 +618,8 @@ extern "C" int fvfi_resize_bilinear_nhwc_fused(const float* x, int x_pixel_strid
     for (int sh = 0; sh < 16; ++sh)
         if ((1 << sh) == cg_n) cg_shift = sh;
     const size_t per_row = (size_t)Wo * cg_n;
-    FVFI_CHECK_ARG(per_row < (1ull << 31) && Ho <= 2 * 65535, "resize_bilinear: image too large");
-    dim3 grid((unsigned)((per_row + 255) / 256), (unsigned)((Ho + 1) / 2), (unsigned)B);
+    FVFI_CHECK_ARG(per_row < (1ull << 31) && Ho <= 65535, "resize_bilinear: image too large");
+    dim3 grid((unsigned)((per_row + 255) / 256), (unsigned)Ho, (unsigned)B);
     cudaStream_t s = (cudaStream_t)stream;
     if (vec == 8)
         fvfi::resize_bilinear_nhwc_kernel<8><<<grid, 256, 0, s>>>(x, y, Hi, Wi, Ho, Wo, C, x_pixel_stride, y_pixel_stride, sy, sx, align_corners, addend, lda, relu_in, cg_n, cg_shift);
