@@ -47,7 +47,10 @@ struct FftPlan {
     int alloc;                   // slots per sequence the caller provides: M, or 2n for Rader in the column layout (two halves)
     int nfac;
     int bluestein;
-    int rader;                   // 1: n = rr * rp, stages [0, nouter) are DIF stages on length n, stages [nouter, nfac) the sub-FFT of length rq
+    int rader;                   // n = rr * rp, stages [0, nouter) work on length n, stages [nouter, nfac) are the sub-FFT of length rq.
+                                 // 1: decimation in frequency (outer DIF stages, permuting copy into a second buffer, Rader);
+                                 // 2: decimation in time (inputs scattered by pos_in on the way in, Rader in place, outer DIT stages
+                                 //    whose twiddle index goes through `perm`): no copy pass, ONE buffer of n slots
     int rr, rp, rq, nouter;      // rq = rp - 1
     int pad;                     // sequence-major layout: 1 = skew i + (i >> 4) (smallest butterfly stride is even)
     int fac[FFT_MAX_STAGES];     // radices in network order (product = M; Rader: product = rr * rq)
@@ -63,6 +66,7 @@ struct FftPlan {
     const float2* tw2;           // Rader: W_rq^t, t < rq
     const unsigned short* pin;   // Rader: slot of input j inside its length-rp block (0 for j = 0, 1 + dlog_g(j) otherwise)
     const unsigned short* inv;   // Rader: position of natural index k in the result (sequence-major layout reads in natural order)
+    const unsigned short* pos_in; // Rader (decimation in time): position input i is written to
 };
 
 struct FftCtx { int tid, nthr; };
@@ -330,7 +334,11 @@ FVFI_HD void fft_stage_impl(const FftPlan& P, int s, const float2* in, float2* o
 #pragma unroll
             for (int u = 0; u < R; ++u)
                 v[u] = LINEAR ? in[a0 + u * st] : in[fft_addr<COL>(b, base + u * m, ctshift, pitch, 1)];
-            if (KIND == FFT_DIT && m > 1) twiddle_powers<R>(v, ldg_(tw + j * (M / (R * m))));
+            if (KIND == FFT_DIT && m > 1) {
+                // decimation-in-time Rader: the length-m blocks hold their spectrum in generator order; `perm` names the frequency
+                const int jf = (P.rader == 2) ? (int)ldg_(P.perm + j) : j;
+                twiddle_powers<R>(v, ldg_(tw + jf * (M / (R * m))));
+            }
             dft(v, Radix<R>());
             if (KIND == FFT_DIF && m > 1) twiddle_powers<R>(v, ldg_(tw + j * (M / (R * m))));
             if (KIND == FFT_DIF && post) {                        // Bluestein: spectrum of the chirp filter, then conj
@@ -386,14 +394,18 @@ FVFI_HD void fft_stage_sub_impl(const FftPlan& P, int s, float2* buf, int batch,
                 if (u == 0 && base == 0) {                    // DC bin of this block: X[0] = y0 + sum, and y0 rides on every output
                     const int a00 = fft_addr<COL>(b, blk * rp, ctshift, pitch, 0);
                     const float2 y0 = buf[a00];
-                    buf[a00] = cconj(cadd(y0, v[0]));
+                    const float2 x0 = cadd(y0, v[0]);
+                    buf[a00] = (P.rader == 2) ? x0 : cconj(x0);   // DIF variant: fft_get conjugates every slot; DIT variant: final value
                     w = cadd(w, y0);
                 }
                 v[u] = cconj(w);
             }
         }
+        // decimation-in-time variant: the last stage of the inverse sub-transform finishes the conj -> forward -> conj identity here
+        // (the outer radix stages that follow need the true block spectra)
+        const bool conj_out = KIND == FFT_DIT && P.rader == 2 && s == P.nouter;
 #pragma unroll
-        for (int u = 0; u < R; ++u) buf[a0 + u * st] = v[u];
+        for (int u = 0; u < R; ++u) buf[a0 + u * st] = conj_out ? cconj(v[u]) : v[u];
     }
 }
 
@@ -477,8 +489,9 @@ struct FftIO {
     int bluestein, pad, rader;
     const float2* chirp;
     const unsigned short* inv;
+    const unsigned short* pos_in;
 };
-FVFI_HD FftIO fft_io(const FftPlan& P) { return FftIO{P.bluestein, P.pad, P.rader, P.chirp, P.inv}; }
+FVFI_HD FftIO fft_io(const FftPlan& P) { return FftIO{P.bluestein, P.pad, P.rader, P.chirp, P.inv, P.pos_in}; }
 
 // Pitch (floats2 per sequence) of the sequence-major layout for this plan.
 FVFI_HD int fft_pitch(const FftPlan& P) { return fft_row_pitch(P.alloc, P.pad); }
@@ -487,6 +500,7 @@ FVFI_HD int fft_pitch(const FftPlan& P) { return fft_row_pitch(P.alloc, P.pad); 
 template <bool COL>
 FVFI_HD void fft_put(const FftIO& io, float2* buf, int b, int i, float2 v, int ctshift, int pitch) {
     if (io.bluestein) v = cmul(v, ldg_(io.chirp + i));
+    if (io.pos_in) i = (int)ldg_(io.pos_in + i);                 // decimation-in-time Rader: residue block, generator-order slot
     buf[fft_addr<COL>(b, i, ctshift, pitch, io.pad)] = v;
 }
 // ... and READ the result through fft_get (Bluestein: conj + chirp on the way out).  pos < n; the natural index
@@ -495,7 +509,8 @@ template <bool COL>
 FVFI_HD float2 fft_get(const FftIO& io, const FftResult& R, int b, int pos, int ctshift, int pitch) {
     if (io.rader) {      // result sits in generator order: the column layout walks positions (R.perm names them), rows look them up
         const int p2 = COL ? pos : (int)ldg_(io.inv + pos);
-        return cconj(R.buf[fft_addr<COL>(b, p2, ctshift, pitch, 0)]);
+        const float2 v = R.buf[fft_addr<COL>(b, p2, ctshift, pitch, 0)];
+        return io.rader == 2 ? v : cconj(v);              // decimation in time has already conjugated (before its outer stages)
     }
     const float2 v = R.buf[fft_addr<COL>(b, pos, ctshift, pitch, io.pad)];
     return io.bluestein ? cmul(cconj(v), ldg_(io.chirp + pos)) : v;
@@ -512,6 +527,23 @@ template <bool COL>
 FVFI_HD FftResult fft_forward(const FftPlan& P, float2* a, float2* b, int batch, int ctshift, int pitch, bool inplace,
                               FftCtx cx, int src_plain = 0) {
     const int M = P.M, n = P.n, pad = P.pad;
+    if (P.rader == 2) {
+        // decimation in time: fft_put has scattered the inputs into residue blocks in generator order; Rader on every block in
+        // place, then the radix stages of r across the blocks (twiddle index through `perm`: the blocks are in generator order)
+        for (int s = P.nouter; s < P.nfac; ++s) {
+            fft_run_stage_sub<FFT_DIF, COL>(P, s, a, batch, ctshift, pitch, s == P.nfac - 1 ? P.bhat : nullptr, cx);
+            fft_sync();
+        }
+        for (int s = P.nfac - 1; s >= P.nouter; --s) {
+            fft_run_stage_sub<FFT_DIT, COL>(P, s, a, batch, ctshift, pitch, nullptr, cx);
+            fft_sync();
+        }
+        for (int s = P.nouter - 1; s >= 0; --s) {
+            fft_run_stage<FFT_DIT, COL>(P, s, a, a, batch, ctshift, pitch, nullptr, cx);
+            fft_sync();
+        }
+        return FftResult{a, P.perm};
+    }
     if (P.rader) {
         for (int s = 0; s < P.nouter; ++s) {                 // Cooley-Tukey stages for the smooth part r of n = r * p
             fft_run_stage<FFT_DIF, COL>(P, s, a, a, batch, ctshift, pitch, nullptr, cx);

@@ -13,12 +13,13 @@ namespace fvfi {
 struct HostFftPlan {
     FftPlan p{};                       // pointers are filled in by whoever owns the storage (device upload or host test)
     std::vector<float2> tw, chirp, bhat, tw2;
-    std::vector<unsigned short> perm, pin, inv;
+    std::vector<unsigned short> perm, pin, inv, pos_in;
 };
 
-// Test / A-B switch: 0 makes every non-smooth length use Bluestein (round-1 behaviour).
+// Test / A-B switch: 0 makes every non-smooth length use Bluestein (round-1 behaviour); 1 = Rader, decimation in frequency
+// (permuting copy, two buffers); 2 = Rader, decimation in time (default: no copy pass, one buffer).
 inline int& fft_rader_enabled() {
-    static int on = 1;
+    static int on = 2;
     return on;
 }
 
@@ -121,7 +122,7 @@ inline bool fft_rader_split(int n, int* r_out, int* p_out) {
 }
 
 // Rader plan (see fft_engine.cuh): outer DIF stages for r, sub-FFT stages for q = p - 1, generator-order tables.
-inline bool fft_make_rader_plan(int n, int r, int pr, bool column_layout, HostFftPlan& H) {
+inline bool fft_make_rader_plan(int n, int r, int pr, bool column_layout, HostFftPlan& H, int variant = 1) {
     FftPlan& p = H.p;
     const int q = pr - 1;
     std::vector<int> rad_r, rad_q;
@@ -129,9 +130,9 @@ inline bool fft_make_rader_plan(int n, int r, int pr, bool column_layout, HostFf
     if (r == 1) rad_r.clear();
     if ((int)(rad_r.size() + rad_q.size()) > FFT_MAX_STAGES || n > 32767) return false;
     p.M = n;
-    p.alloc = column_layout ? 2 * n : n;
+    p.alloc = (column_layout && variant == 1) ? 2 * n : n;
     p.bluestein = 0;
-    p.rader = 1;
+    p.rader = variant;
     p.rr = r; p.rp = pr; p.rq = q;
     p.nouter = (int)rad_r.size();
     p.nfac = p.nouter + (int)rad_q.size();
@@ -223,6 +224,24 @@ inline bool fft_make_rader_plan(int n, int r, int pr, bool column_layout, HostFf
             H.inv[k] = (unsigned short)(blk * pr + slot);
         }
     }
+    H.pos_in.clear();
+    if (variant == 2) {
+        // decimation in time: input i = sum_s d_s prod_{t<s} fac_t + r * j sits at position sum_s d_s sub_s + slot(j); the radix stages of
+        // r then run over blocks that hold their spectra in generator order, so X[k2 + rp * K1] ends at position K1 * rp + slot(k2)
+        std::vector<int> slot_of_k2(pr, 0), k2_of_slot(pr, 0);
+        for (int m = 0; m < q; ++m) { const int k2 = gpow[(q - m) % q]; slot_of_k2[k2] = 1 + m; k2_of_slot[1 + m] = k2; }
+        H.pos_in.assign(n, 0);
+        for (int i = 0; i < n; ++i) {
+            int rem = i % r, pos = 0;
+            for (int s = 0; s < p.nouter; ++s) { pos += (rem % p.fac[s]) * p.sub[s]; rem /= p.fac[s]; }
+            H.pos_in[i] = (unsigned short)(pos + H.pin[i / r]);
+        }
+        for (int pos = 0; pos < n; ++pos) {
+            const int k = (pos / pr) * pr + k2_of_slot[pos % pr];
+            H.perm[pos] = (unsigned short)k;
+            H.inv[k] = (unsigned short)pos;
+        }
+    }
     H.chirp.clear();
     return true;
 }
@@ -236,7 +255,8 @@ inline bool fft_make_plan(int n, bool stockham, HostFftPlan& H) {
     {
         int rr = 0, rp = 0;
         // `stockham` is what the callers pass for the sequence-major (row) layout; the column layout needs the two halves
-        if (fft_rader_enabled() && !fft_radices(n, rad) && fft_rader_split(n, &rr, &rp) && fft_make_rader_plan(n, rr, rp, !stockham, H))
+        if (fft_rader_enabled() && !fft_radices(n, rad) && fft_rader_split(n, &rr, &rp) &&
+            fft_make_rader_plan(n, rr, rp, !stockham, H, fft_rader_enabled() == 2 ? 2 : 1))
             return true;
         p = FftPlan{};
         p.n = n;

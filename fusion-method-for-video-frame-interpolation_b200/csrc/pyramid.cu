@@ -163,6 +163,10 @@ static int get_fft(fvfi_pyr_plan* p, int n, bool stockham, FftPlan* out) {
     f.tw2 = nullptr;
     f.pin = nullptr;
     f.inv = nullptr;
+    f.pos_in = nullptr;
+    if (f.rader == 2) {
+        if (int rc = upload(p, H.pos_in, &f.pos_in)) return rc;
+    }
     if (f.rader) {
         if (int rc = upload(p, H.perm, &f.perm)) return rc;
         if (int rc = upload(p, H.bhat, &f.bhat)) return rc;
@@ -181,7 +185,8 @@ static int get_fft(fvfi_pyr_plan* p, int n, bool stockham, FftPlan* out) {
 }
 
 static size_t row_bytes_per_row(const FftPlan& fx) {
-    return (size_t)(fx.bluestein ? 1 : 2) * fft_pitch(fx) * sizeof(float2);      // Bluestein runs in place; Stockham / Rader use two buffers
+    // Bluestein and Rader (decimation in time) run in place; Stockham and the decimation-in-frequency Rader variant use two buffers
+    return (size_t)((fx.bluestein || fx.rader == 2) ? 1 : 2) * fft_pitch(fx) * sizeof(float2);
 }
 
 static int build_jobs(fvfi_pyr_plan* p) {
@@ -759,10 +764,10 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_inv(const Le
     // Rows of the intermediate are contiguous in HBM: when they are 16-byte aligned (even width) and need no transformation on the
     // way in (no Bluestein chirp), one elected thread lands every row at its pitch with cp.async.bulk (bulk async-copy engine,
     // completion on an mbarrier) -- no per-element load / address / store instructions, no registers in flight.
-    const bool bulk = !iox.bluestein && !(w & 1) && ((((size_t)src) & 15) == 0) && J.fx.nfac > 0;
+    const bool bulk = !iox.bluestein && !iox.pos_in && !(w & 1) && ((((size_t)src) & 15) == 0) && J.fx.nfac > 0;
     const int src_plain = (bulk && J.fx.pad) ? 1 : 0;     // landed unskewed: the first (out-of-place) stage reads plainly
     if (bulk) {
-        unsigned long long* bar = (unsigned long long*)(smem + (size_t)2 * rb * pitch);
+        unsigned long long* bar = (unsigned long long*)(smem + (size_t)2 * rb * pitch);     // bulk rows are two-buffer plans (row_smem)
         const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar);
         if (threadIdx.x == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
@@ -1159,7 +1164,7 @@ int fvfi_pyr_plan_create(int H, int W, int height, int nbands, double scale_fact
     FVFI_CHECK_ARG(height >= 2 && height - 2 < MAX_LEVELS - 1, "pyr_plan_create: bad height %d", height);
     FVFI_CHECK_ARG(nbands >= 1 && nbands <= MAX_BANDS, "pyr_plan_create: nbands must be 1..%d", MAX_BANDS);
     FVFI_CHECK_ARG(scale_factor > 1.0 && scale_factor <= 4.0, "pyr_plan_create: scale_factor must be in (1,4]");
-    if (const char* e = getenv("FVFI_FFT_NO_RADER")) fvfi::fft_rader_enabled() = (e[0] == '1') ? 0 : 1;   // A/B switch: Bluestein everywhere
+    if (const char* e = getenv("FVFI_FFT_NO_RADER")) fvfi::fft_rader_enabled() = (e[0] == '1') ? 0 : (e[0] == '2') ? 1 : 2;   // A/B switch: 1 = Bluestein everywhere, 2 = Rader with the permuting copy
     fvfi_pyr_plan* p = new fvfi_pyr_plan();
     p->H = H; p->W = W; p->height = height; p->nbands = nbands; p->L = height - 2; p->scale = scale_factor;
     if (int rc = build_plan(p)) { fvfi_pyr_plan_destroy(p); return rc; }

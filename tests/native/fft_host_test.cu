@@ -23,6 +23,7 @@ extern "C" int fft_host_run(int n, int mode, int batch, const float* in, float* 
         H.p.tw2 = H.tw2.data();
         H.p.pin = H.pin.data();
         H.p.inv = H.inv.data();
+        H.p.pos_in = H.pos_in.empty() ? nullptr : H.pos_in.data();
     }
     const int M = H.p.M;
     int ctshift = 0;
@@ -54,7 +55,8 @@ extern "C" int fft_host_run(int n, int mode, int batch, const float* in, float* 
         if (a[elems + i].x != canary.x || a[elems + i].y != canary.y || b[elems + i].x != canary.x || b[elems + i].y != canary.y) return -2;
     if (info) {
         info[0] = M;
-        info[1] = H.p.bluestein + 2 * H.p.rader;
+        info[1] = H.p.bluestein + 2 * (H.p.rader != 0);
+        info[15] = H.p.rader;
         info[2] = H.p.nfac;
         for (int s = 0; s < H.p.nfac; ++s) info[3 + s] = H.p.fac[s];
     }

@@ -55,11 +55,12 @@ LENGTHS = sorted(set(
     + level_lengths(2160, 18) + level_lengths(3840, 18)))
 
 
-@pytest.mark.parametrize("rader", [1, 0])
+@pytest.mark.parametrize("rader", [2, 1, 0])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_all_lengths(lib, mode, rader):
-    """rader = 1: the shipped plans (Rader for n = r * p, p - 1 smooth; Bluestein for the rest); rader = 0: Bluestein for every
-    non-smooth length (the fallback path stays tested)."""
+    """rader = 2: the shipped plans (Rader, decimation in time, for n = r * p with p - 1 smooth; Bluestein for the rest); rader = 1:
+    the decimation-in-frequency Rader variant (permuting copy, two buffers); rader = 0: Bluestein for every non-smooth length -- the
+    alternative paths stay tested."""
     lib.fft_host_set_rader(rader)
     rng = np.random.default_rng(mode)
     worst, kinds = 0.0, {0: 0, 1: 0, 2: 0}
@@ -68,12 +69,13 @@ def test_all_lengths(lib, mode, rader):
             batch = 2 if n > 512 else 4
             err, info = run(lib, n, mode, batch, rng)
             kinds[int(info[1])] += 1
+            assert info[1] != 2 or info[15] == rader, "n=%d: asked for Rader variant %d, plan is variant %d" % (n, rader, info[15])
             tol = 4e-6 if info[1] else 2e-6      # Bluestein: two FFTs of ~2n + chirps; Rader: two FFTs of p - 1 + the outer stages
             assert err < tol, "n=%d mode=%d rel err %.3g (M=%d kind=%d radices=%s)" % (
                 n, mode, err, info[0], info[1], list(info[3:3 + info[2]]))
             worst = max(worst, err)
     finally:
-        lib.fft_host_set_rader(1)
+        lib.fft_host_set_rader(2)
     print("worst relative error", worst, "plans direct/bluestein/rader:", kinds)
     assert (kinds[2] > 10) == bool(rader)
 
