@@ -837,14 +837,19 @@ static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
     // one persistent CTA per SM: as many A stages as fit (the loaders run that far ahead of the tensor core)
     const int taps = a.KH * a.KW;
     const size_t budget = 222 * 1024;
+    static const int force_mt = [] { const char* e = getenv("FVFI_CONV_MT"); return e ? atoi(e) : 0; }();   // tuning override
     for (int mt = 4; mt >= 1; mt >>= 1) {
+        if (force_mt && mt > force_mt) continue;
         // WIDE pays for N <= 32 (two A reads instead of three).  Measured again with the dedicated epilogue warps and the lean
         // issue loop: at N = 64 the halved tile (MT = 2: 340 vs 377 TF/s) or a single-buffered accumulator (MT = 4: 308) cost
         // more than the saved A read; the softmax heads are epilogue-bound and keep the one-load-per-block form.
         a.wide = (a.Npad <= 32 && a.act != ACT_SOFTMAX) ? 1 : 0;
         a.tcols = a.wide ? 2 * a.Npad : a.Npad;
         if (mt * a.tcols > 512) continue;
-        if (a.wide && mt > 1 && 2 * mt * a.tcols > 512) continue;      // small-N layers: keep the accumulator double-buffered
+        // Keep the accumulator DOUBLE-BUFFERED (epilogue of tile k under the MMAs of tile k+1) even when that halves the tile:
+        // measured at B = 8 (tools/tune_conv_split.py): 512->512 @68x120 282 -> 427 TF/s, 256->256 @136x240 429 -> 523,
+        // 128->128 @272x480 408 -> 522, the fused heads 64->448 399 -> 445 (MT = 1 for N > 128, MT = 2 for N = 128).
+        if (mt > 1 && 2 * mt * a.tcols > 512) continue;
         if (mt > 1 && 8 * (mt / 2) >= a.W) continue;                   // do not over-tile narrow images
         a.MT = mt;
         a.nacc = (2 * mt * a.tcols <= 512) ? 2 : 1;

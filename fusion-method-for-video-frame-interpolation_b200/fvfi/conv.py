@@ -129,12 +129,22 @@ ACT = {None: 0, "none": 0, "relu": 1, "elu": 2, "tanh": 3, "sigmoid": 4, "softma
 timing = None    # set to a list to collect (flops, start_event, end_event) per convolution launch (bench.py roofline)
 
 
+n_split = None   # tuning override (tools/tune_conv_split.py): output channels per launch for Cout > this value
+
+
+def _split(Cout):
+    """Output channels per launch (one launch holds at most 256: the TMEM accumulator is 512 columns)."""
+    if n_split is not None and Cout > n_split:
+        return n_split
+    return 256
+
+
 def _packed(weight):
     """Packed (hi|lo split, canonical tensor-core layout) copy of a weight tensor, per operand split.  The cache lives ON the
     tensor object (``weight._fvfi_pack``), so it dies with it -- folded / concatenated temporaries do not accumulate; it is
     rebuilt when the tensor's version counter or storage changes (optimizer steps and load_state_dict bump the version; edits
     through ``.data`` do not -- call ``invalidate(weight)`` after those)."""
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device))
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device), _split(weight.shape[0]))
     cache = weight.__dict__.setdefault("_fvfi_pack", {})
     hit = cache.get(precision)
     if hit is not None and hit[0] == key:
@@ -143,8 +153,9 @@ def _packed(weight):
     L = _lib.lib()
     parts = []
     w = weight.detach().contiguous().float()
-    for o in range(0, Cout, 256):
-        wo = w[o:o + 256].contiguous()
+    step = _split(Cout)
+    for o in range(0, Cout, step):
+        wo = w[o:o + step].contiguous()
         n = L.fvfi_conv2d_packed_weight_floats(wo.shape[0], Cin, KH, KW, precision)
         buf = torch.empty(n, dtype=torch.float32, device=weight.device)
         with torch.cuda.device(weight.device):

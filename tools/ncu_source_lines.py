@@ -27,5 +27,7 @@ for row in csv.reader(open(path, errors="ignore")):
     key = (func.split("(")[0][-40:], (fpath or "").split("/")[-1], d["Line No"])
     agg[key][0] += ie; agg[key][1] += sm; text[key] = d["Source"].strip()[:110]
     kern_tot[key[0]] += ie
-for k, (ie, sm, _) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    print("%5.1f%% inst %6d smp  %s:%s  %s" % (100.0 * ie / max(kern_tot[k[0]], 1), sm, k[1], k[2], text[k]))
+by = 1 if (len(sys.argv) > 4 and sys.argv[4] == "samples") else 0      # 5th argument "samples": order by stall samples instead
+smp_tot = sum(v[1] for v in agg.values())
+for k, (ie, sm, _) in sorted(agg.items(), key=lambda kv: -kv[1][by])[:top]:
+    print("%5.1f%% inst %5.1f%% smp  %s:%s  %s" % (100.0 * ie / max(kern_tot[k[0]], 1), 100.0 * sm / max(smp_tot, 1), k[1], k[2], text[k]))
