@@ -78,4 +78,20 @@ __device__ __forceinline__ void st_stream4(float4* p, float4 v) {
                  : "memory");
 }
 
+// Bilinear resampling exactly as ATen's upsample_bilinear2d (area_pixel_compute_source_index): source rows / columns and the
+// weight of the second one for output index o.  Shared by the resize kernel (imgproc.cu) and by the convolution loader that
+// upsamples its input on the fly (conv_tc.cu), so that both give the same bits.
+__host__ __device__ __forceinline__ void bilinear_src(int o, float scale, int align_corners, int n_in, int& i0, int& i1, float& l) {
+    const float f = align_corners ? scale * (float)o : fmaxf(scale * ((float)o + 0.5f) - 0.5f, 0.f);
+    i0 = min((int)f, n_in - 1);
+    i1 = min(i0 + 1, n_in - 1);
+    l = f - (float)i0;
+}
+__host__ __device__ __forceinline__ float bilinear_scale(int n_in, int n_out, int align_corners) {
+    if (align_corners) return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
+    return (float)n_in / (float)n_out;
+}
+__device__ __forceinline__ float bilerp(float hy, float hx, float ly, float lx, float a, float b, float c, float d) {
+    return fmaf(ly, fmaf(lx, d, hx * c), hy * fmaf(lx, b, hx * a));
+}
 }  // namespace fvfi

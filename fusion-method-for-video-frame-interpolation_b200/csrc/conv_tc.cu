@@ -85,6 +85,10 @@ struct ConvArgs {
     unsigned a_stage_bytes, b_stage_bytes;
     const float* res;      // optional residual [B,H,W,>=Cout] NHWC added AFTER the activation (U-Net skip connections), or null
     int ldr;               // floats per pixel of the residual
+    // fused bilinear upsampling of the input (torch.nn.Upsample -> Conv2d as ONE kernel): x is [B,Hs,Ws,Cin], the convolution runs
+    // on its [H,W] bilinear resampling, which the loaders evaluate while staging -- the upsampled tensor never exists in HBM
+    int up, Hs, Ws, up_align;
+    float up_sy, up_sx;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -359,6 +363,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
     unsigned* tmem_ptr = (unsigned*)(acc_empty + 2);
     int* pixoff = (int*)(tmem_ptr + 2);                      // [NPIX] global pixel index of every region pixel, -1 = zero pad
     float* bias_s = (float*)(((size_t)(pixoff + A.NPIX) + 15) & ~(size_t)15);   // [Npad], 16 B aligned
+    float2* up_w = (float2*)(bias_s + 256);                  // [NPIX] upsampling loaders: weights of the second source row / column
+    int* up_d = (int*)(up_w + A.NPIX);                       // [NPIX] ... and the offsets of the second source row / column
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int taps = A.KH * A.KW;
@@ -688,6 +694,84 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             fence_async_smem();          // generic-proxy stores -> visible to the tensor-core (async) proxy
             mbar_arrive(&a_full[s]);
         };
+        // Upsampling loaders: the four source samples of every (pixel, channel group) item are fetched, combined (bilerp: the resize
+        // kernel's own arithmetic) and stored in one go, two items at a time -- 64 registers of loads in flight per thread, the
+        // sources are L1 / L2 hits (each is shared by ~4 region pixels).
+        auto stage_up = [&](int c, const float* X) {
+            const int s = g % A.astages;
+            if (g >= A.astages) mbar_wait(&a_empty[s], ((g / A.astages) - 1) & 1);
+            ++g;
+            float4* hi = (float4*)(a_base + (size_t)s * A.a_stage_bytes);
+            float4* lo = (float4*)(a_base + (size_t)s * A.a_stage_bytes + a_half);
+            int ksh;
+            const int total = chunk_shape(c, ksh);
+            const int kmask = (1 << ksh) - 1, cbase = c * CHUNK;
+            constexpr int UB = (CPK == 8) ? 2 : 4;                  // items per batch
+            for (int u0 = 0; u0 < UMAX; u0 += UB) {
+                float sa[UB][CPK], sb[UB][CPK], sc[UB][CPK], sd[UB][CPK];
+                float2 wl[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int q = threadIdx.x + (u0 + u) * CV_LOADERS;
+                    wl[u] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int e = 0; e < CPK; ++e) sa[u][e] = sb[u][e] = sc[u][e] = sd[u][e] = 0.f;
+                    if (q < total) {
+                        const int pix = q >> ksh, ch = cbase + (q & kmask) * CPK;
+                        const int off = pixoff[pix];
+                        if (off >= 0 && ch < cin4) {
+                            const int d = up_d[pix];
+                            wl[u] = up_w[pix];
+                            const float* p = X + (size_t)off * A.ldx + ch;
+                            const size_t dx = (size_t)(d & 1) * A.ldx, dy = (size_t)(d >> 1) * A.ldx;
+                            if (CPK == 8) {
+                                ldg256(p, sa[u]); ldg256(p + dx, sb[u]); ldg256(p + dy, sc[u]); ldg256(p + dy + dx, sd[u]);
+                            } else {
+                                const float4 t0 = __ldg((const float4*)p), t1 = __ldg((const float4*)(p + dx));
+                                const float4 t2 = __ldg((const float4*)(p + dy)), t3 = __ldg((const float4*)(p + dy + dx));
+                                sa[u][0] = t0.x; sa[u][1] = t0.y; sa[u][2] = t0.z; sa[u][3] = t0.w;
+                                sb[u][0] = t1.x; sb[u][1] = t1.y; sb[u][2] = t1.z; sb[u][3] = t1.w;
+                                sc[u][0] = t2.x; sc[u][1] = t2.y; sc[u][2] = t2.z; sc[u][3] = t2.w;
+                                sd[u][0] = t3.x; sd[u][1] = t3.y; sd[u][2] = t3.z; sd[u][3] = t3.w;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int q = threadIdx.x + (u0 + u) * CV_LOADERS;
+                    if (q < total) {
+                        const float ly = wl[u].x, lx = wl[u].y, hy = 1.f - ly, hx = 1.f - lx;
+                        float w[CPK];
+#pragma unroll
+                        for (int e = 0; e < CPK; ++e) w[e] = bilerp(hy, hx, ly, lx, sa[u][e], sb[u][e], sc[u][e], sd[u][e]);
+                        const int o = (q & kmask) * A.NPIX + (q >> ksh);
+                        if (PREC == PREC_F16X3) {
+                            unsigned hw[4], lw[4];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                const float x0 = w[e] * xs, x1 = w[e + 1] * xs;
+                                amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+                                const __half2 h = __floats2half2_rn(x0, x1);
+                                const float2 hf = __half22float2(h);
+                                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                                hw[e >> 1] = *(const unsigned*)&h;
+                                lw[e >> 1] = *(const unsigned*)&l;
+                            }
+                            hi[o] = make_float4(__uint_as_float(hw[0]), __uint_as_float(hw[1]), __uint_as_float(hw[2]), __uint_as_float(hw[3]));
+                            lo[o] = make_float4(__uint_as_float(lw[0]), __uint_as_float(lw[1]), __uint_as_float(lw[2]), __uint_as_float(lw[3]));
+                        } else {
+                            float4 h;
+                            h.x = to_tf32_rna(w[0]); h.y = to_tf32_rna(w[1]); h.z = to_tf32_rna(w[2]); h.w = to_tf32_rna(w[3]);
+                            hi[o] = h;
+                            lo[o] = make_float4(w[0] - h.x, w[1] - h.y, w[2] - h.z, w[3] - h.w);
+                        }
+                    }
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(&a_full[s]);
+        };
         // region -> image mapping of a tile (the table is shared by the loaders: barrier before and after the rewrite)
         auto map_tile = [&](const TileCoord& T) {
             asm volatile("bar.sync 1, %0;" ::"n"(CV_LOADERS) : "memory");
@@ -701,7 +785,19 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                 } else {
                     ok = (gy >= 0 && gy < A.H && gx >= 0 && gx < A.W);
                 }
-                pixoff[pix] = ok ? gy * A.W + gx : -1;
+                if (A.up) {        // (gy, gx) is a pixel of the upsampled image: its four sources and weights
+                    int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
+                    float ly = 0.f, lx = 0.f;
+                    if (ok) {
+                        bilinear_src(gy, A.up_sy, A.up_align, A.Hs, y0, y1, ly);
+                        bilinear_src(gx, A.up_sx, A.up_align, A.Ws, x0, x1, lx);
+                    }
+                    pixoff[pix] = ok ? y0 * A.Ws + x0 : -1;
+                    up_w[pix] = make_float2(ly, lx);
+                    up_d[pix] = ((y1 - y0) * A.Ws) * 2 + (x1 - x0);
+                } else {
+                    pixoff[pix] = ok ? gy * A.W + gx : -1;
+                }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(CV_LOADERS) : "memory");
         };
@@ -709,7 +805,16 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
         // Stream of (tile, chunk): store chunk k, put chunk k+1's loads in flight.  The A ring (>= 2 stages) lets the
         // loaders run a stage ahead of the tensor core, which is what hides the load latency of the next chunk.
         TileCoord curT = tile_coord(A, blockIdx.x), nextT = curT;
-        const float* X = A.x + (size_t)curT.img * A.H * A.W * A.ldx;
+        const size_t img_px = A.up ? (size_t)A.Hs * A.Ws : (size_t)A.H * A.W;
+        const float* X = A.x + (size_t)curT.img * img_px * A.ldx;
+        if (A.up) {
+            for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+                const TileCoord T = tile_coord(A, tile);
+                X = A.x + (size_t)T.img * img_px * A.ldx;
+                map_tile(T);
+                for (int c = 0; c < A.nchunks; ++c) stage_up(c, X);
+            }
+        } else {
         if ((int)blockIdx.x < A.ntiles) {
             map_tile(curT);
             issue(0, X);
@@ -727,6 +832,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                 }
             }
             curT = nextT;
+        }
         }
         if (PREC == PREC_F16X3 && !(amax <= 65504.f) && A.overflow) atomicOr(A.overflow, 1);
     } else {
@@ -858,7 +964,7 @@ static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
         a.NPIX = a.RW * a.RH;
         a.a_stage_bytes = (unsigned)a.NPIX * CV_KCHUNKS * 16u * 2u;    // hi + lo
         if (a.NPIX * CV_KCHUNKS > CV_LOADERS * CV_UMAX) continue;          // the loaders keep a whole K chunk in registers (UMAX)
-        const size_t misc = 512 + (size_t)a.NPIX * 4 + 1024 + 16;
+        const size_t misc = 512 + (size_t)a.NPIX * 4 + 1024 + 16 + (a.up ? (size_t)a.NPIX * 12 : 0);
         const int min_b = std::min(2, a.nchunks * taps);
         if (misc + 2 * (size_t)a.a_stage_bytes + (size_t)min_b * a.b_stage_bytes > budget) continue;
         // weights first (up to 4 stages of a few KB), the rest goes to activation stages
@@ -959,6 +1065,15 @@ extern "C" int fvfi_conv2d_nhwc_residual(const float* x, int x_pixel_stride, con
                                          const float* residual, int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H,
                                          int W, int Cin, int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw,
                                          int precision, void* stream) {
+    return fvfi_conv2d_nhwc_upsampled(x, x_pixel_stride, 0, 0, 0, packed_weight, bias, residual, residual_pixel_stride, y, y_pixel_stride,
+                                      B, H, W, Cin, Cout, KH, KW, pad_mode, activation, out_nchw, precision, stream);
+}
+
+extern "C" int fvfi_conv2d_nhwc_upsampled(const float* x, int x_pixel_stride, int Hs, int Ws, int align_corners,
+                                          const float* packed_weight, const float* bias, const float* residual,
+                                          int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H, int W, int Cin,
+                                          int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw, int precision,
+                                          void* stream) {
     FVFI_CHECK_ARG(!residual || (activation != ACT_SOFTMAX && residual_pixel_stride >= Cout),
                    "conv2d: a residual needs a pixel stride >= Cout and no softmax");
     FVFI_CHECK_ARG(x && packed_weight && y, "conv2d: null pointer");
@@ -973,6 +1088,16 @@ extern "C" int fvfi_conv2d_nhwc_residual(const float* x, int x_pixel_stride, con
     a.x = x; a.hdr = packed_weight; a.wpack = packed_weight + CV_HDR; a.bias = bias; a.y = y;
     a.ldx = x_pixel_stride; a.ldy = y_pixel_stride; a.out_nchw = (out_nchw == 1) ? 1 : 0;
     a.res = residual; a.ldr = residual_pixel_stride;
+    a.up = (Hs > 0 || Ws > 0) ? 1 : 0;
+    if (a.up) {
+        const int cpk = cv_cpk(precision), cin_r = (Cin + cpk - 1) / cpk * cpk;
+        FVFI_CHECK_ARG(Hs > 0 && Ws > 0 && (size_t)Hs * Ws < (1u << 30), "conv2d: bad source size %dx%d for the upsampling loader", Hs, Ws);
+        FVFI_CHECK_ARG((x_pixel_stride % cpk) == 0 && x_pixel_stride >= cin_r && ((size_t)x % (4 * cpk)) == 0,
+                       "conv2d: the upsampling loader needs an aligned source whose pixel stride is a multiple of %d and >= %d", cpk, cin_r);
+        a.Hs = Hs; a.Ws = Ws; a.up_align = align_corners ? 1 : 0;
+        a.up_sy = bilinear_scale(Hs, H, a.up_align);
+        a.up_sx = bilinear_scale(Ws, W, a.up_align);
+    }
     a.cout_store = (out_nchw == 2) ? ((Cout + 15) & ~15) : Cout;
     FVFI_CHECK_ARG(out_nchw >= 0 && out_nchw <= 2, "conv2d: output layout must be 0 (NHWC), 1 (NCHW) or 2 (NHWC, zero-padded channels)");
     FVFI_CHECK_ARG(out_nchw != 2 || y_pixel_stride >= a.cout_store, "conv2d: padded NHWC output needs a pixel stride >= round16(Cout)");

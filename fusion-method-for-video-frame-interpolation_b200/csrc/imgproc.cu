@@ -342,17 +342,10 @@ __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* 
     const int oy = blockIdx.y, n = blockIdx.z;
     const size_t p = (size_t)oy * Wo + ox;
     // source coordinates exactly as ATen's area_pixel_compute_source_index
-    float fy, fx;
-    if (align_corners) {
-        fy = sy * oy;
-        fx = sx * ox;
-    } else {
-        fy = fmaxf(sy * (oy + 0.5f) - 0.5f, 0.f);
-        fx = fmaxf(sx * (ox + 0.5f) - 0.5f, 0.f);
-    }
-    const int y0 = min((int)fy, Hi - 1), x0 = min((int)fx, Wi - 1);
-    const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
-    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(oy, sy, align_corners, Hi, y0, y1, ly);
+    bilinear_src(ox, sx, align_corners, Wi, x0, x1, lx);
     const float hy = 1.f - ly, hx = 1.f - lx;
     const float* X = x + (size_t)n * Hi * Wi * ldx;
     const float* p00 = X + ((size_t)y0 * Wi + x0) * ldx + ch;
@@ -385,7 +378,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const float* 
         for (int i = 0; i < VEC; ++i) { a[i] = fmaxf(a[i], 0.f); b[i] = fmaxf(b[i], 0.f); c[i] = fmaxf(c[i], 0.f); d[i] = fmaxf(d[i], 0.f); }
     }
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+    for (int i = 0; i < VEC; ++i) o[i] = bilerp(hy, hx, ly, lx, a[i], b[i], c[i], d[i]);
     if (ap) {                           // + skip connection (fusion_net.py:62)
 #pragma unroll
         for (int i = 0; i < VEC; ++i) o[i] += e[i];
@@ -602,14 +595,7 @@ extern "C" int fvfi_resize_bilinear_nhwc_fused(const float* x, int x_pixel_strid
     FVFI_CHECK_ARG(!addend || addend_pixel_stride >= C, "resize_bilinear: addend pixel stride smaller than channel count");
     const size_t addbits = addend ? ((size_t)addend | ((size_t)addend_pixel_stride * 4)) : 0;
     const int lda = addend_pixel_stride, relu_in = relu_input ? 1 : 0;
-    float sy, sx;
-    if (align_corners) {
-        sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
-        sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
-    } else {
-        sy = (float)Hi / (float)Ho;
-        sx = (float)Wi / (float)Wo;
-    }
+    const float sy = fvfi::bilinear_scale(Hi, Ho, align_corners), sx = fvfi::bilinear_scale(Wi, Wo, align_corners);
     const bool a32 = ((((size_t)x) | ((size_t)y) | addbits) & 31) == 0, a16 = ((((size_t)x) | ((size_t)y) | addbits) & 15) == 0;
     const int vec = (a32 && (C & 7) == 0 && (x_pixel_stride & 7) == 0 && (y_pixel_stride & 7) == 0) ? 8
                   : (a16 && (C & 3) == 0 && (x_pixel_stride & 3) == 0 && (y_pixel_stride & 3) == 0) ? 4 : 1;

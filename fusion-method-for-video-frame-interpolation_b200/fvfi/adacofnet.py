@@ -91,6 +91,7 @@ class KernelEstimation(torch.nn.Module):
         mods = list(seq)
         last_conv = max(i for i, m in enumerate(mods) if isinstance(m, torch.nn.Conv2d))
         i = 0
+        up = None                      # pending Upsample: evaluated by the loaders of the convolution that follows it
         while i < len(mods):
             m = mods[i]
             if isinstance(m, torch.nn.Conv2d):
@@ -100,7 +101,9 @@ class KernelEstimation(torch.nn.Module):
                 # use 16-byte accesses even for the 25-channel heads
                 pad = (i + 2 < len(mods) and isinstance(mods[i + 2], torch.nn.Upsample) and m.out_channels % 4 != 0)
                 x = tc.conv_module(m, x, act, nchw_out=nchw_last and i == last_conv, pad_out=pad,
-                                   residual=residual if i == last_conv else None)   # skip connection after the last conv + act
+                                   residual=residual if i == last_conv else None,   # skip connection after the last conv + act
+                                   upsample=up)
+                up = None
                 i += 2 if act else 1
             elif (isinstance(m, torch.nn.Upsample) and i + 1 == last_conv and mods[last_conv].out_channels == 1
                   and m.scale_factor == 2 and m.mode == 'bilinear' and m.align_corners):
@@ -110,7 +113,12 @@ class KernelEstimation(torch.nn.Module):
                 x = tc.upsample2_conv3x3_single(mods[last_conv], x, act)
                 i += 3 if act else 2
             elif isinstance(m, torch.nn.Upsample):
-                x = tc.resize_bilinear(x, (x.shape[2] * 2, x.shape[3] * 2), bool(m.align_corners))
+                size = (x.shape[2] * 2, x.shape[3] * 2)
+                if (tc.fuse_upsample and m.mode == 'bilinear' and m.scale_factor == 2 and i + 1 < len(mods)
+                        and isinstance(mods[i + 1], torch.nn.Conv2d) and mods[i + 1].kernel_size[0] > 1):
+                    up = (size, bool(m.align_corners))      # Upsample -> Conv2d: one kernel (fvfi_conv2d_nhwc_upsampled)
+                else:
+                    x = tc.resize_bilinear(x, size, bool(m.align_corners))
                 i += 1
             else:
                 x = m(x)

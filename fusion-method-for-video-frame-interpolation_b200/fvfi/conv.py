@@ -187,17 +187,24 @@ def to_nhwc(x):
     return x.contiguous(memory_format=torch.channels_last)
 
 
-def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_out=False, pad_out=False, residual=None):
+fuse_upsample = True    # Upsample -> Conv2d as one kernel (A/B switch for tools/; the unfused form is resize_bilinear + conv2d)
+
+
+def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_out=False, pad_out=False, residual=None,
+           upsample=None):
     """x [B,Cin,H,W] (any memory format; channels_last avoids a copy) -> [B,Cout,H,W] channels_last
     (``nchw_out=True``: plain contiguous NCHW, written directly by the epilogue).
     Equivalent to act(F.conv2d(pad(x), weight, bias)) with 'same' padding (K//2) in zeros or reflect mode;
     act 'softmax' is over the channel dimension.
     ``residual`` (channels_last [B,Cout,H,W]): added after the activation in the epilogue (skip connection).
     ``pad_out=True``: the result has round16(Cout) channels, the extra ones zero (keeps 16-byte accesses for channel
-    counts such as 25).  ``x`` may carry such zero padding channels beyond the weight's Cin."""
+    counts such as 25).  ``x`` may carry such zero padding channels beyond the weight's Cin.
+    ``upsample=((H, W), align_corners)``: the convolution runs on the bilinear resampling of ``x`` to [H, W]
+    (torch.nn.Upsample -> Conv2d in one kernel, fvfi_conv2d_nhwc_upsampled); inference only."""
     if not x.is_cuda:
         raise NotImplementedError("fvfi.conv.conv2d: CUDA tensors only")
     if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
+        assert upsample is None, "conv2d(upsample=...) is an inference form"
         assert out is None and not nchw_out and not pad_out and residual is None and act != "softmax", \
             "conv2d under autograd supports the plain NHWC form (bias + relu / elu / tanh / sigmoid)"
         return _ConvTC.apply(x, weight, bias, padding_mode, act)
@@ -208,7 +215,16 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
     xc = to_nhwc(x.float())
     assert xc.stride(1) == 1
     ldx = xc.stride(3)                       # floats per pixel
-    if (KH == 1 and Cout <= 8 and Cin % 8 == 0 and Cin <= 128 and ldx % 8 == 0 and xc.data_ptr() % 32 == 0
+    Hs = Ws = align = 0
+    if upsample is not None:
+        cpk = 8 if precision == PRECISIONS["f16x3"] else 4
+        if ldx % cpk or ldx < (Cin + cpk - 1) // cpk * cpk or xc.data_ptr() % (4 * cpk):
+            # the upsampling loader wants aligned channel groups: materialise the resampled tensor instead
+            return conv2d(resize_bilinear(xc, tuple(upsample[0]), bool(upsample[1])), weight, bias, padding_mode, act, out, nchw_out,
+                          pad_out, residual)
+        Hs, Ws, align = H, W, int(bool(upsample[1]))
+        H, W = (int(v) for v in upsample[0])
+    if (upsample is None and KH == 1 and Cout <= 8 and Cin % 8 == 0 and Cin <= 128 and ldx % 8 == 0 and xc.data_ptr() % 32 == 0
             and act != "softmax" and out is None and not nchw_out and not pad_out and residual is None):
         return _conv1x1_direct(xc, weight, bias, act)
     if out is None:
@@ -232,10 +248,11 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         for (o, n, buf) in parts:
-            _lib.check(L.fvfi_conv2d_nhwc_residual(xc.data_ptr(), ldx, buf.data_ptr(), None if b is None else b.data_ptr() + 4 * o,
-                                                   None if rc is None else rc.data_ptr() + 4 * o, 0 if rc is None else rc.stride(3),
-                                                   out.data_ptr() + 4 * o, ldy, B, H, W, Cin, n, KH, KW, pad_mode, ACT[act],
-                                                   1 if nchw_out else (2 if pad_out else 0), precision, _lib.stream_ptr()))
+            _lib.check(L.fvfi_conv2d_nhwc_upsampled(xc.data_ptr(), ldx, Hs, Ws, align, buf.data_ptr(),
+                                                    None if b is None else b.data_ptr() + 4 * o,
+                                                    None if rc is None else rc.data_ptr() + 4 * o, 0 if rc is None else rc.stride(3),
+                                                    out.data_ptr() + 4 * o, ldy, B, H, W, Cin, n, KH, KW, pad_mode, ACT[act],
+                                                    1 if nchw_out else (2 if pad_out else 0), precision, _lib.stream_ptr()))
         if timing is not None:
             e1.record()
             timing.append((2.0 * B * H * W * Cin * Cout * KH * KW, e0, e1, len(parts), (B, Cin, Cout, KH, H, W, act)))
@@ -332,13 +349,13 @@ def avg_pool2(x, _fn="fvfi_avg_pool2_nhwc"):
     return out
 
 
-def conv_module(conv, x, act=None, nchw_out=False, pad_out=False, residual=None):
+def conv_module(conv, x, act=None, nchw_out=False, pad_out=False, residual=None, upsample=None):
     """Run an nn.Conv2d (stride 1, dilation 1, padding == K//2) through the tensor-core kernel."""
     k = conv.kernel_size[0]
     assert conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
     assert conv.padding == (k // 2, k // 2) or (k == 1 and conv.padding == (0, 0))
     mode = "zeros" if k == 1 else conv.padding_mode
-    return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out, pad_out=pad_out, residual=residual)
+    return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out, pad_out=pad_out, residual=residual, upsample=upsample)
 
 
 def conv_bn_module(conv, bn, x, act=None):

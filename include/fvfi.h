@@ -132,6 +132,17 @@ int fvfi_conv2d_nhwc_residual(const float* x, int x_pixel_stride, const float* p
                               const float* residual, int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H,
                               int W, int Cin, int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw,
                               int precision, void* stream);
+/* torch.nn.Upsample(mode='bilinear') -> Conv2d as ONE kernel (KernelEstimation's Upsample blocks and the tails of its heads,
+ * src/fusion_net/fusion_adacofnet.py:29-36,41-48: `Upsample(scale_factor=2, mode='bilinear', align_corners=True)` followed by a
+ * 3x3 convolution):  y = act(conv(resize(x, [H,W])) + bias) + residual.  x is the SOURCE [B,Hs,Ws,>=Cin] NHWC; the loaders of the
+ * convolution evaluate the bilinear resampling (ATen's upsample_bilinear2d arithmetic, the same as fvfi_resize_bilinear_nhwc)
+ * while they stage the operand, so the [B,H,W,Cin] intermediate never exists in HBM.  x must be 32-byte aligned (FVFI_CONV_TF32X3: 16)
+ * with x_pixel_stride a multiple of 8 (4) that covers Cin rounded up to it; channels between Cin and that bound must be finite.
+ * Hs == Ws == 0 is fvfi_conv2d_nhwc_residual. */
+int fvfi_conv2d_nhwc_upsampled(const float* x, int x_pixel_stride, int Hs, int Ws, int align_corners,
+                               const float* packed_weight, const float* bias, const float* residual, int residual_pixel_stride,
+                               float* y, int y_pixel_stride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad_mode,
+                               int activation, int out_nchw, int precision, void* stream);
 /* FVFI_CONV_F16X3 scales activations by 2^4 before the fp16 split; |x| > 4094 would leave fp16's range.  Returns 1
  * (and clears the flag) if any convolution since the last call saw such a value, 0 if not, -1 on error.
  * Synchronises the device. */

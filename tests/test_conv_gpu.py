@@ -248,3 +248,40 @@ def test_conv_residual_epilogue(B, Cin, Cout, H, W, prec):
     assert y.shape == ref.shape
     assert float((y.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
     conv.check_overflow()
+
+
+@pytest.mark.parametrize("B,Cin,Cout,Hs,Ws,mode,act,align,extra", [
+    (2, 25, 25, 37, 53, "zeros", None, True, "nchw"),        # head tail: 25 channels stored as 32, planar output
+    (1, 25, 25, 20, 31, "zeros", "softmax", True, "nchw"),
+    (2, 64, 64, 17, 30, "zeros", "relu", True, "residual"),  # moduleUpsample: Upsample -> Conv -> ReLU, + skip in the epilogue
+    (1, 128, 128, 9, 15, "zeros", "relu", True, None),       # several K chunks per tile
+    (1, 512, 512, 5, 8, "zeros", "relu", True, "residual"),  # Cout > 256: two launches
+    (1, 40, 16, 23, 19, "reflect", "elu", False, None),      # align_corners=False, reflect padding of the upsampled image
+])
+def test_conv_fused_bilinear_upsample(B, Cin, Cout, Hs, Ws, mode, act, align, extra, prec):
+    """Upsample(x2, bilinear) -> Conv2d as ONE kernel (fvfi_conv2d_nhwc_upsampled, fusion_adacofnet.py:29-36,41-48): the loaders
+    evaluate the resampling.  Bit-identical to resize kernel + convolution (same arithmetic), and within the convolution's own
+    tolerance of an fp64 F.interpolate -> conv2d."""
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(11)
+    Cs = (Cin + 15) // 16 * 16
+    src = torch.zeros((B, Cs, Hs, Ws), device="cuda").contiguous(memory_format=torch.channels_last)
+    src[:, :Cin] = torch.randn((B, Cin, Hs, Ws), device="cuda", generator=g)
+    w = torch.randn((Cout, Cin, 3, 3), device="cuda", generator=g) / (3 * Cin ** 0.5)
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    H, W = 2 * Hs, 2 * Ws
+    skip = torch.randn((B, Cout, H, W), device="cuda", generator=g) if extra == "residual" else None
+    kw = dict(nchw_out=(extra == "nchw"), residual=skip)
+    y = conv.conv2d(src, w, b, mode, act, upsample=((H, W), align), **kw)
+    up = conv.resize_bilinear(src, (H, W), align)
+    y2 = conv.conv2d(up, w, b, mode, act, **kw)
+    assert y.shape == (B, Cout, H, W) and torch.equal(y, y2)
+    xr = F.interpolate(src[:, :Cin].double(), size=(H, W), mode="bilinear", align_corners=align)
+    if mode == "reflect":
+        xr = F.pad(xr, (1, 1, 1, 1), mode="reflect")
+    ref = F.conv2d(xr, w.double(), b.double(), padding=0 if mode == "reflect" else 1)
+    ref = {None: lambda t: t, "relu": F.relu, "elu": F.elu, "softmax": lambda t: torch.softmax(t, 1)}[act](ref)
+    if skip is not None:
+        ref = ref + skip.double()
+    assert float((y.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    conv.check_overflow()
