@@ -694,9 +694,18 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             fence_async_smem();          // generic-proxy stores -> visible to the tensor-core (async) proxy
             mbar_arrive(&a_full[s]);
         };
-        // Upsampling loaders: the four source samples of every (pixel, channel group) item are fetched, combined (bilerp: the resize
-        // kernel's own arithmetic) and stored in one go, two items at a time -- 64 registers of loads in flight per thread, the
-        // sources are L1 / L2 hits (each is shared by ~4 region pixels).
+        // Upsampling loaders: one item = TWO horizontally adjacent region pixels x one channel group.  The second pixel's sources are
+        // the first one's (same source column pair) or share a column with them (its left column is the first one's right column) --
+        // 4 or 6 loads per pair instead of 8: the staging is bound by L1 bandwidth (every source sample is wanted by ~4 region pixels),
+        // not by latency.  Values are combined with bilerp (the resize kernel's own arithmetic), split and stored at once.
+        auto load_cpk = [&](const float* p, float* dst) {
+            if (CPK == 8) {
+                ldg256(p, dst);
+            } else {
+                const float4 t = __ldg((const float4*)p);
+                dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+            }
+        };
         auto stage_up = [&](int c, const float* X) {
             const int s = g % A.astages;
             if (g >= A.astages) mbar_wait(&a_empty[s], ((g / A.astages) - 1) & 1);
@@ -704,69 +713,70 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             float4* hi = (float4*)(a_base + (size_t)s * A.a_stage_bytes);
             float4* lo = (float4*)(a_base + (size_t)s * A.a_stage_bytes + a_half);
             int ksh;
-            const int total = chunk_shape(c, ksh);
+            const int total = chunk_shape(c, ksh) >> 1;             // pixel pairs x channel groups (RW is even: pairs do not straddle rows)
             const int kmask = (1 << ksh) - 1, cbase = c * CHUNK;
-            constexpr int UB = (CPK == 8) ? 2 : 4;                  // items per batch
-            for (int u0 = 0; u0 < UMAX; u0 += UB) {
-                float sa[UB][CPK], sb[UB][CPK], sc[UB][CPK], sd[UB][CPK];
-                float2 wl[UB];
+            auto put = [&](int o, const float* w) {
+                if (PREC == PREC_F16X3) {
+                    unsigned hw[4], lw[4];
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const int q = threadIdx.x + (u0 + u) * CV_LOADERS;
-                    wl[u] = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int e = 0; e < CPK; ++e) sa[u][e] = sb[u][e] = sc[u][e] = sd[u][e] = 0.f;
-                    if (q < total) {
-                        const int pix = q >> ksh, ch = cbase + (q & kmask) * CPK;
-                        const int off = pixoff[pix];
-                        if (off >= 0 && ch < cin4) {
-                            const int d = up_d[pix];
-                            wl[u] = up_w[pix];
-                            const float* p = X + (size_t)off * A.ldx + ch;
-                            const size_t dx = (size_t)(d & 1) * A.ldx, dy = (size_t)(d >> 1) * A.ldx;
-                            if (CPK == 8) {
-                                ldg256(p, sa[u]); ldg256(p + dx, sb[u]); ldg256(p + dy, sc[u]); ldg256(p + dy + dx, sd[u]);
-                            } else {
-                                const float4 t0 = __ldg((const float4*)p), t1 = __ldg((const float4*)(p + dx));
-                                const float4 t2 = __ldg((const float4*)(p + dy)), t3 = __ldg((const float4*)(p + dy + dx));
-                                sa[u][0] = t0.x; sa[u][1] = t0.y; sa[u][2] = t0.z; sa[u][3] = t0.w;
-                                sb[u][0] = t1.x; sb[u][1] = t1.y; sb[u][2] = t1.z; sb[u][3] = t1.w;
-                                sc[u][0] = t2.x; sc[u][1] = t2.y; sc[u][2] = t2.z; sc[u][3] = t2.w;
-                                sd[u][0] = t3.x; sd[u][1] = t3.y; sd[u][2] = t3.z; sd[u][3] = t3.w;
-                            }
-                        }
+                    for (int e = 0; e < 8; e += 2) {
+                        const float x0 = w[e] * xs, x1 = w[e + 1] * xs;
+                        amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+                        const __half2 h = __floats2half2_rn(x0, x1);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                        hw[e >> 1] = *(const unsigned*)&h;
+                        lw[e >> 1] = *(const unsigned*)&l;
                     }
+                    hi[o] = make_float4(__uint_as_float(hw[0]), __uint_as_float(hw[1]), __uint_as_float(hw[2]), __uint_as_float(hw[3]));
+                    lo[o] = make_float4(__uint_as_float(lw[0]), __uint_as_float(lw[1]), __uint_as_float(lw[2]), __uint_as_float(lw[3]));
+                } else {
+                    float4 h;
+                    h.x = to_tf32_rna(w[0]); h.y = to_tf32_rna(w[1]); h.z = to_tf32_rna(w[2]); h.w = to_tf32_rna(w[3]);
+                    hi[o] = h;
+                    lo[o] = make_float4(w[0] - h.x, w[1] - h.y, w[2] - h.z, w[3] - h.w);
                 }
+            };
+            for (int q = threadIdx.x; q < total; q += CV_LOADERS) {
+                const int pix = (q >> ksh) << 1, kg = q & kmask, ch = cbase + kg * CPK;
+                float a0[CPK], b0[CPK], c0[CPK], d0[CPK], a1[CPK], b1[CPK], c1[CPK], d1[CPK];
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const int q = threadIdx.x + (u0 + u) * CV_LOADERS;
-                    if (q < total) {
-                        const float ly = wl[u].x, lx = wl[u].y, hy = 1.f - ly, hx = 1.f - lx;
-                        float w[CPK];
+                for (int e = 0; e < CPK; ++e) a0[e] = b0[e] = c0[e] = d0[e] = a1[e] = b1[e] = c1[e] = d1[e] = 0.f;
+                const bool chok = ch < cin4;
+                const int off0 = chok ? pixoff[pix] : -1, off1 = chok ? pixoff[pix + 1] : -1;
+                const int e0 = up_d[pix], e1 = up_d[pix + 1];
+                const float2 w0 = up_w[pix], w1 = up_w[pix + 1];
+                // 0: all four sources of the second pixel are the first one's; 1: its left column is the first one's right column;
+                // 2: unrelated (image border / padding)
+                const int kind = (off0 >= 0 && off1 == off0 && e1 == e0) ? 0
+                               : (off0 >= 0 && off1 == off0 + (e0 & 1) && (e1 >> 1) == (e0 >> 1)) ? 1 : 2;
+                if (off0 >= 0) {
+                    const float* p = X + (size_t)off0 * A.ldx + ch;
+                    const size_t dx = (size_t)(e0 & 1) * A.ldx, dy = (size_t)(e0 >> 1) * A.ldx;
+                    load_cpk(p, a0); load_cpk(p + dx, b0); load_cpk(p + dy, c0); load_cpk(p + dy + dx, d0);
+                }
+                if (off1 >= 0 && kind != 0) {
+                    const float* p = X + (size_t)off1 * A.ldx + ch;
+                    const size_t dx = (size_t)(e1 & 1) * A.ldx, dy = (size_t)(e1 >> 1) * A.ldx;
+                    if (kind == 2) { load_cpk(p, a1); load_cpk(p + dy, c1); }
+                    load_cpk(p + dx, b1); load_cpk(p + dy + dx, d1);
+                }
+                float w[CPK];
+                {
+                    const float ly = w0.x, lx = w0.y, hy = 1.f - ly, hx = 1.f - lx;
 #pragma unroll
-                        for (int e = 0; e < CPK; ++e) w[e] = bilerp(hy, hx, ly, lx, sa[u][e], sb[u][e], sc[u][e], sd[u][e]);
-                        const int o = (q & kmask) * A.NPIX + (q >> ksh);
-                        if (PREC == PREC_F16X3) {
-                            unsigned hw[4], lw[4];
+                    for (int e = 0; e < CPK; ++e) w[e] = bilerp(hy, hx, ly, lx, a0[e], b0[e], c0[e], d0[e]);
+                    put(kg * A.NPIX + pix, w);
+                }
+                {
+                    const float ly = w1.x, lx = w1.y, hy = 1.f - ly, hx = 1.f - lx;
 #pragma unroll
-                            for (int e = 0; e < 8; e += 2) {
-                                const float x0 = w[e] * xs, x1 = w[e + 1] * xs;
-                                amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
-                                const __half2 h = __floats2half2_rn(x0, x1);
-                                const float2 hf = __half22float2(h);
-                                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                                hw[e >> 1] = *(const unsigned*)&h;
-                                lw[e >> 1] = *(const unsigned*)&l;
-                            }
-                            hi[o] = make_float4(__uint_as_float(hw[0]), __uint_as_float(hw[1]), __uint_as_float(hw[2]), __uint_as_float(hw[3]));
-                            lo[o] = make_float4(__uint_as_float(lw[0]), __uint_as_float(lw[1]), __uint_as_float(lw[2]), __uint_as_float(lw[3]));
-                        } else {
-                            float4 h;
-                            h.x = to_tf32_rna(w[0]); h.y = to_tf32_rna(w[1]); h.z = to_tf32_rna(w[2]); h.w = to_tf32_rna(w[3]);
-                            hi[o] = h;
-                            lo[o] = make_float4(w[0] - h.x, w[1] - h.y, w[2] - h.z, w[3] - h.w);
-                        }
+                    for (int e = 0; e < CPK; ++e) {
+                        const float a = kind == 0 ? a0[e] : kind == 1 ? b0[e] : a1[e], cc = kind == 0 ? c0[e] : kind == 1 ? d0[e] : c1[e];
+                        const float b = kind == 0 ? b0[e] : b1[e], d = kind == 0 ? d0[e] : d1[e];
+                        w[e] = off1 >= 0 ? bilerp(hy, hx, ly, lx, a, b, cc, d) : 0.f;
                     }
+                    put(kg * A.NPIX + pix + 1, w);
                 }
             }
             fence_async_smem();
