@@ -89,6 +89,11 @@ struct ConvArgs {
     // on its [H,W] bilinear resampling, which the loaders evaluate while staging -- the upsampled tensor never exists in HBM
     int up, Hs, Ws, up_align;
     float up_sy, up_sx;
+    // ... optionally only for the first up_chunks K chunks (channels [0, up_chunks * chunk)): the remaining input channels come from a
+    // second tensor x2 [B,H,W,>=Cin - up_chunks*chunk] at the convolution's own resolution -- conv(cat(resize(x), x2)) without the concat
+    // (PhaseNet: previous level's features resampled + this level's values, src/phase_net/phase_net.py:138-148)
+    const float* x2;
+    int ldx2, up_chunks;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -365,6 +370,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
     float* bias_s = (float*)(((size_t)(pixoff + A.NPIX) + 15) & ~(size_t)15);   // [Npad], 16 B aligned
     float2* up_w = (float2*)(bias_s + 256);                  // [NPIX] upsampling loaders: weights of the second source row / column
     int* up_d = (int*)(up_w + A.NPIX);                       // [NPIX] ... and the offsets of the second source row / column
+    int* up_off = up_d + A.NPIX;                             // [NPIX] ... and the first source sample (pixoff stays the direct mapping)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int taps = A.KH * A.KW;
@@ -603,12 +609,17 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
         const int padT = A.KH / 2, padL = A.KW / 2;
         // 16-byte loads need aligned pixels; a channel count that is not a multiple of 4 is fine when the pixel stride
         // leaves room for the rounded-up group (the producer zero-fills the padding channels, see out layout 2)
-        const int cin4 = (A.Cin + 3) & ~3;
-        const bool vec = ((A.ldx & 3) == 0) && (A.ldx >= cin4) && ((((size_t)A.x) & 15) == 0);
-        const int cin8 = (A.Cin + 7) & ~7;
-        const bool vec8 = ((A.ldx & 7) == 0) && (A.ldx >= cin8) && ((((size_t)A.x) & 31) == 0);
         constexpr int CPK = cv_cpk(PREC);
         constexpr int CHUNK = cv_chunk(PREC);
+        // the source the plain (issue / finish) path reads: x, or -- behind the upsampled channels -- x2
+        const int cshift = A.up ? A.up_chunks * CHUNK : 0;                       // first channel of that source in the weights' order
+        const float* xd = (A.up && A.x2) ? A.x2 : A.x;
+        const int ldd = (A.up && A.x2) ? A.ldx2 : A.ldx, cind = A.Cin - cshift;
+        const int cin4 = (cind + 3) & ~3;
+        const bool vec = ((ldd & 3) == 0) && (ldd >= cin4) && ((((size_t)xd) & 15) == 0);
+        const int cin8 = (cind + 7) & ~7;
+        const bool vec8 = ((ldd & 7) == 0) && (ldd >= cin8) && ((((size_t)xd) & 31) == 0);
+        const int cin4u = A.up ? ((min(A.Cin, cshift) + 3) & ~3) : 0;            // channels of the upsampled source
         const float xs = (float)(1 << CV_X_SHIFT);
         float amax = 0.f;
         int g = 0;                                                 // running chunk counter of the A ring
@@ -625,7 +636,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
         auto issue = [&](int c, const float* X) {
             int ksh;
             const int total = chunk_shape(c, ksh);
-            const int kmask = (1 << ksh) - 1, cbase = c * CHUNK;
+            const int kmask = (1 << ksh) - 1, cbase = c * CHUNK - cshift;
 #pragma unroll
             for (int u = 0; u < UMAX; ++u) {
                 const int q = threadIdx.x + u * CV_LOADERS;
@@ -635,7 +646,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     const int pix = q >> ksh, ch = cbase + (q & kmask) * CPK;   // consecutive threads read one pixel's chunk
                     const int off = pixoff[pix];
                     if (off >= 0 && ch < cin4) {
-                        const float* p = X + (size_t)off * A.ldx + ch;
+                        const float* p = X + (size_t)off * ldd + ch;
                         if (vec8 && CPK == 8 && ch + 8 <= cin8) {
                             ldg256(p, v[u]);
                         } else if (vec) {
@@ -649,7 +660,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                         } else {
 #pragma unroll
                             for (int e = 0; e < CPK; ++e)
-                                if (ch + e < A.Cin) v[u][e] = __ldg(p + e);
+                                if (ch + e < cind) v[u][e] = __ldg(p + e);
                         }
                     }
                 }
@@ -742,8 +753,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                 float a0[CPK], b0[CPK], c0[CPK], d0[CPK], a1[CPK], b1[CPK], c1[CPK], d1[CPK];
 #pragma unroll
                 for (int e = 0; e < CPK; ++e) a0[e] = b0[e] = c0[e] = d0[e] = a1[e] = b1[e] = c1[e] = d1[e] = 0.f;
-                const bool chok = ch < cin4;
-                const int off0 = chok ? pixoff[pix] : -1, off1 = chok ? pixoff[pix + 1] : -1;
+                const bool chok = ch < cin4u;
+                const int off0 = chok ? up_off[pix] : -1, off1 = chok ? up_off[pix + 1] : -1;
                 const int e0 = up_d[pix], e1 = up_d[pix + 1];
                 const float2 w0 = up_w[pix], w1 = up_w[pix + 1];
                 // 0: all four sources of the second pixel are the first one's; 1: its left column is the first one's right column;
@@ -802,12 +813,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                         bilinear_src(gy, A.up_sy, A.up_align, A.Hs, y0, y1, ly);
                         bilinear_src(gx, A.up_sx, A.up_align, A.Ws, x0, x1, lx);
                     }
-                    pixoff[pix] = ok ? y0 * A.Ws + x0 : -1;
+                    up_off[pix] = ok ? y0 * A.Ws + x0 : -1;
                     up_w[pix] = make_float2(ly, lx);
                     up_d[pix] = ((y1 - y0) * A.Ws) * 2 + (x1 - x0);
-                } else {
-                    pixoff[pix] = ok ? gy * A.W + gx : -1;
                 }
+                pixoff[pix] = ok ? gy * A.W + gx : -1;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(CV_LOADERS) : "memory");
         };
@@ -815,14 +825,18 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
         // Stream of (tile, chunk): store chunk k, put chunk k+1's loads in flight.  The A ring (>= 2 stages) lets the
         // loaders run a stage ahead of the tensor core, which is what hides the load latency of the next chunk.
         TileCoord curT = tile_coord(A, blockIdx.x), nextT = curT;
-        const size_t img_px = A.up ? (size_t)A.Hs * A.Ws : (size_t)A.H * A.W;
-        const float* X = A.x + (size_t)curT.img * img_px * A.ldx;
+        const float* X = xd + (size_t)curT.img * A.H * A.W * ldd;
         if (A.up) {
             for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
                 const TileCoord T = tile_coord(A, tile);
-                X = A.x + (size_t)T.img * img_px * A.ldx;
+                const float* Xu = A.x + (size_t)T.img * A.Hs * A.Ws * A.ldx;
+                X = xd + (size_t)T.img * A.H * A.W * ldd;
                 map_tile(T);
-                for (int c = 0; c < A.nchunks; ++c) stage_up(c, X);
+                for (int c = 0; c < A.up_chunks; ++c) stage_up(c, Xu);
+                for (int c = A.up_chunks; c < A.nchunks; ++c) {      // channels behind the upsampled ones: x2, at full resolution
+                    issue(c, X);
+                    finish(c);
+                }
             }
         } else {
         if ((int)blockIdx.x < A.ntiles) {
@@ -836,7 +850,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     issue(c + 1, X);
                 } else if (tile + (int)gridDim.x < A.ntiles) {
                     nextT = tile_coord(A, tile + gridDim.x);
-                    X = A.x + (size_t)nextT.img * A.H * A.W * A.ldx;
+                    X = xd + (size_t)nextT.img * A.H * A.W * ldd;
                     map_tile(nextT);
                     issue(0, X);
                 }
@@ -974,7 +988,7 @@ static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
         a.NPIX = a.RW * a.RH;
         a.a_stage_bytes = (unsigned)a.NPIX * CV_KCHUNKS * 16u * 2u;    // hi + lo
         if (a.NPIX * CV_KCHUNKS > CV_LOADERS * CV_UMAX) continue;          // the loaders keep a whole K chunk in registers (UMAX)
-        const size_t misc = 512 + (size_t)a.NPIX * 4 + 1024 + 16 + (a.up ? (size_t)a.NPIX * 12 : 0);
+        const size_t misc = 512 + (size_t)a.NPIX * 4 + 1024 + 16 + (a.up ? (size_t)a.NPIX * 16 : 0);
         const int min_b = std::min(2, a.nchunks * taps);
         if (misc + 2 * (size_t)a.a_stage_bytes + (size_t)min_b * a.b_stage_bytes > budget) continue;
         // weights first (up to 4 stages of a few KB), the rest goes to activation stages
@@ -1075,11 +1089,12 @@ extern "C" int fvfi_conv2d_nhwc_residual(const float* x, int x_pixel_stride, con
                                          const float* residual, int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H,
                                          int W, int Cin, int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw,
                                          int precision, void* stream) {
-    return fvfi_conv2d_nhwc_upsampled(x, x_pixel_stride, 0, 0, 0, packed_weight, bias, residual, residual_pixel_stride, y, y_pixel_stride,
-                                      B, H, W, Cin, Cout, KH, KW, pad_mode, activation, out_nchw, precision, stream);
+    return fvfi_conv2d_nhwc_upsampled(x, x_pixel_stride, 0, 0, 0, nullptr, 0, 0, packed_weight, bias, residual, residual_pixel_stride, y,
+                                      y_pixel_stride, B, H, W, Cin, Cout, KH, KW, pad_mode, activation, out_nchw, precision, stream);
 }
 
-extern "C" int fvfi_conv2d_nhwc_upsampled(const float* x, int x_pixel_stride, int Hs, int Ws, int align_corners,
+extern "C" int fvfi_conv2d_nhwc_upsampled(const float* x, int x_pixel_stride, int Hs, int Ws, int align_corners, const float* x_direct,
+                                          int x_direct_pixel_stride, int cin_upsampled,
                                           const float* packed_weight, const float* bias, const float* residual,
                                           int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H, int W, int Cin,
                                           int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw, int precision,
@@ -1102,17 +1117,29 @@ extern "C" int fvfi_conv2d_nhwc_upsampled(const float* x, int x_pixel_stride, in
     if (a.up) {
         const int cpk = cv_cpk(precision), cin_r = (Cin + cpk - 1) / cpk * cpk;
         FVFI_CHECK_ARG(Hs > 0 && Ws > 0 && (size_t)Hs * Ws < (1u << 30), "conv2d: bad source size %dx%d for the upsampling loader", Hs, Ws);
-        FVFI_CHECK_ARG((x_pixel_stride % cpk) == 0 && x_pixel_stride >= cin_r && ((size_t)x % (4 * cpk)) == 0,
+        FVFI_CHECK_ARG((x_pixel_stride % cpk) == 0 && (x_direct || x_pixel_stride >= cin_r) && ((size_t)x % (4 * cpk)) == 0,
                        "conv2d: the upsampling loader needs an aligned source whose pixel stride is a multiple of %d and >= %d", cpk, cin_r);
         a.Hs = Hs; a.Ws = Ws; a.up_align = align_corners ? 1 : 0;
         a.up_sy = bilinear_scale(Hs, H, a.up_align);
         a.up_sx = bilinear_scale(Ws, W, a.up_align);
+        const int chunk = cv_chunk(precision);
+        a.up_chunks = (Cin + chunk - 1) / chunk;
+        if (x_direct) {
+            FVFI_CHECK_ARG(cin_upsampled > 0 && cin_upsampled < Cin && (cin_upsampled % chunk) == 0,
+                           "conv2d: the upsampled part of a two-source input must be a multiple of %d channels (got %d of %d)", chunk,
+                           cin_upsampled, Cin);
+            FVFI_CHECK_ARG(x_direct_pixel_stride >= Cin - cin_upsampled, "conv2d: x_direct pixel stride smaller than its channel count");
+            a.x2 = x_direct; a.ldx2 = x_direct_pixel_stride; a.up_chunks = cin_upsampled / chunk;
+        }
+    } else {
+        FVFI_CHECK_ARG(!x_direct, "conv2d: x_direct needs an upsampled first source");
     }
     a.cout_store = (out_nchw == 2) ? ((Cout + 15) & ~15) : Cout;
     FVFI_CHECK_ARG(out_nchw >= 0 && out_nchw <= 2, "conv2d: output layout must be 0 (NHWC), 1 (NCHW) or 2 (NHWC, zero-padded channels)");
     FVFI_CHECK_ARG(out_nchw != 2 || y_pixel_stride >= a.cout_store, "conv2d: padded NHWC output needs a pixel stride >= round16(Cout)");
     a.overflow = (precision == PREC_F16X3) ? overflow_flag() : nullptr;
-    FVFI_CHECK_ARG(x_pixel_stride >= Cin && (out_nchw || y_pixel_stride >= Cout), "conv2d: pixel stride smaller than channel count");
+    FVFI_CHECK_ARG(x_pixel_stride >= (x_direct ? cin_upsampled : Cin) && (out_nchw || y_pixel_stride >= Cout),
+                   "conv2d: pixel stride smaller than channel count");
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.KH = KH; a.KW = KW; a.pad_mode = pad_mode; a.act = activation;
     size_t smem = 0;
     if (int rc = conv_geometry(a, precision, &smem)) return rc;

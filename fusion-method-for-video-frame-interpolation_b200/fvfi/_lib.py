@@ -42,7 +42,8 @@ _PROTOS = {
     "fvfi_conv2d_pack_weights": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "fvfi_conv2d_nhwc": (c_int, [c_fp, c_int, c_fp, c_fp, c_fp, c_int] + [c_int] * 11 + [c_fp]),
     "fvfi_conv2d_nhwc_residual": (c_int, [c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_int] + [c_int] * 11 + [c_fp]),
-    "fvfi_conv2d_nhwc_upsampled": (c_int, [c_fp, c_int, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_int] + [c_int] * 11 + [c_fp]),
+    "fvfi_conv2d_nhwc_upsampled": (c_int, [c_fp, c_int, c_int, c_int, c_int, c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_int]
+                                   + [c_int] * 11 + [c_fp]),
     "fvfi_conv2d_overflow_count": (c_int, []),
     "fvfi_nchw_to_nhwc_slice": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "fvfi_conv1x1_nhwc": (c_int, [c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_size, c_int, c_int, c_int, c_fp]),

@@ -191,7 +191,7 @@ fuse_upsample = True    # Upsample -> Conv2d as one kernel (A/B switch for tools
 
 
 def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_out=False, pad_out=False, residual=None,
-           upsample=None):
+           upsample=None, x_direct=None):
     """x [B,Cin,H,W] (any memory format; channels_last avoids a copy) -> [B,Cout,H,W] channels_last
     (``nchw_out=True``: plain contiguous NCHW, written directly by the epilogue).
     Equivalent to act(F.conv2d(pad(x), weight, bias)) with 'same' padding (K//2) in zeros or reflect mode;
@@ -200,7 +200,9 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
     ``pad_out=True``: the result has round16(Cout) channels, the extra ones zero (keeps 16-byte accesses for channel
     counts such as 25).  ``x`` may carry such zero padding channels beyond the weight's Cin.
     ``upsample=((H, W), align_corners)``: the convolution runs on the bilinear resampling of ``x`` to [H, W]
-    (torch.nn.Upsample -> Conv2d in one kernel, fvfi_conv2d_nhwc_upsampled); inference only."""
+    (torch.nn.Upsample -> Conv2d in one kernel, fvfi_conv2d_nhwc_upsampled); inference only.
+    ``x_direct`` [B,C2,H,W] (with ``upsample``): the input is ``cat(resize(x), x_direct)`` along the channels -- the concatenated
+    tensor is never built (x.shape[1] must be a multiple of the K chunk: 32 channels, 16 for tf32x3)."""
     if not x.is_cuda:
         raise NotImplementedError("fvfi.conv.conv2d: CUDA tensors only")
     if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
@@ -210,6 +212,13 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
         return _ConvTC.apply(x, weight, bias, padding_mode, act)
     B, Cin, H, W = x.shape
     Cout, Cin_w, KH, KW = weight.shape
+    xd, cin_up = None, 0
+    if x_direct is not None:
+        chunk = 32 if precision == PRECISIONS["f16x3"] else 16
+        assert upsample is not None and Cin % chunk == 0 and Cin + x_direct.shape[1] >= Cin_w > Cin
+        assert tuple(x_direct.shape[2:]) == tuple(int(v) for v in upsample[0]) and x_direct.shape[0] == B
+        xd, cin_up = to_nhwc(x_direct.float()), Cin
+        Cin = Cin_w
     assert Cin >= Cin_w and KH == KW and KH in (1, 3, 5)
     Cin = Cin_w
     xc = to_nhwc(x.float())
@@ -218,10 +227,12 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
     Hs = Ws = align = 0
     if upsample is not None:
         cpk = 8 if precision == PRECISIONS["f16x3"] else 4
-        if ldx % cpk or ldx < (Cin + cpk - 1) // cpk * cpk or xc.data_ptr() % (4 * cpk):
+        if ldx % cpk or ldx < ((cin_up or Cin) + cpk - 1) // cpk * cpk or xc.data_ptr() % (4 * cpk):
             # the upsampling loader wants aligned channel groups: materialise the resampled tensor instead
-            return conv2d(resize_bilinear(xc, tuple(upsample[0]), bool(upsample[1])), weight, bias, padding_mode, act, out, nchw_out,
-                          pad_out, residual)
+            up = resize_bilinear(xc, tuple(upsample[0]), bool(upsample[1]))
+            if xd is not None:
+                up = torch.cat((up[:, :cin_up], xd), 1)
+            return conv2d(up, weight, bias, padding_mode, act, out, nchw_out, pad_out, residual)
         Hs, Ws, align = H, W, int(bool(upsample[1]))
         H, W = (int(v) for v in upsample[0])
     if (upsample is None and KH == 1 and Cout <= 8 and Cin % 8 == 0 and Cin <= 128 and ldx % 8 == 0 and xc.data_ptr() % 32 == 0
@@ -248,7 +259,8 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         for (o, n, buf) in parts:
-            _lib.check(L.fvfi_conv2d_nhwc_upsampled(xc.data_ptr(), ldx, Hs, Ws, align, buf.data_ptr(),
+            _lib.check(L.fvfi_conv2d_nhwc_upsampled(xc.data_ptr(), ldx, Hs, Ws, align, None if xd is None else xd.data_ptr(),
+                                                    0 if xd is None else xd.stride(3), cin_up, buf.data_ptr(),
                                                     None if b is None else b.data_ptr() + 4 * o,
                                                     None if rc is None else rc.data_ptr() + 4 * o, 0 if rc is None else rc.stride(3),
                                                     out.data_ptr() + 4 * o, ldy, B, H, W, Cin, n, KH, KW, pad_mode, ACT[act],
@@ -349,16 +361,17 @@ def avg_pool2(x, _fn="fvfi_avg_pool2_nhwc"):
     return out
 
 
-def conv_module(conv, x, act=None, nchw_out=False, pad_out=False, residual=None, upsample=None):
+def conv_module(conv, x, act=None, nchw_out=False, pad_out=False, residual=None, upsample=None, x_direct=None):
     """Run an nn.Conv2d (stride 1, dilation 1, padding == K//2) through the tensor-core kernel."""
     k = conv.kernel_size[0]
     assert conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
     assert conv.padding == (k // 2, k // 2) or (k == 1 and conv.padding == (0, 0))
     mode = "zeros" if k == 1 else conv.padding_mode
-    return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out, pad_out=pad_out, residual=residual, upsample=upsample)
+    return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out, pad_out=pad_out, residual=residual, upsample=upsample,
+                  x_direct=x_direct)
 
 
-def conv_bn_module(conv, bn, x, act=None):
+def conv_bn_module(conv, bn, x, act=None, upsample=None, x_direct=None):
     """conv -> BatchNorm2d (eval: running statistics) -> act, with the BN affine folded into the weights."""
     key = (conv.weight.data_ptr(), conv.weight._version, None if conv.bias is None else conv.bias._version, bn.weight._version,
            bn.bias._version, bn.running_mean._version, bn.running_var._version)
@@ -371,4 +384,4 @@ def conv_bn_module(conv, bn, x, act=None):
         conv.__dict__["_fvfi_fold"] = hit
     k = conv.kernel_size[0]
     mode = "zeros" if k == 1 else conv.padding_mode
-    return conv2d(x, hit[1], hit[2], mode, act)
+    return conv2d(x, hit[1], hit[2], mode, act, upsample=upsample, x_direct=x_direct)

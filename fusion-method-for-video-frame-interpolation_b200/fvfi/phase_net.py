@@ -48,6 +48,16 @@ class PhaseNetBlock(nn.Module):
         c = self.prediction_map(f)
         return f, c
 
+    def forward_resampled(self, feature, direct, size):
+        """``forward(cat(interpolate(feature, size), direct))`` without the concatenated tensor: the first convolution's loaders
+        resample the previous level's features while they stage them (fvfi_conv2d_nhwc_upsampled, two-source form); ``direct``
+        [B, >= c_in - 64, h, w] holds this level's value channels and the resampled previous prediction (phase_net.py:138-148)."""
+        assert not self.training and not torch.is_grad_enabled()
+        f = tc.conv_bn_module(self.feature_map[0], self.feature_map[1], feature, "elu", upsample=(size, False), x_direct=direct)
+        f = tc.conv_module(self.feature_map[3], f, "elu")
+        c = tc.conv_module(self.prediction_map[0], f, "tanh")
+        return f, c
+
 
 class PhaseNet(nn.Module):
     """Phase Net for Video Frame Interpolation (phase_net.py:7-177)."""
@@ -190,17 +200,32 @@ class PhaseNet(nn.Module):
                 ph, am = vals.phase[l], vals.amplitude[l]
                 h, w = int(ph.shape[2]), int(ph.shape[3])
                 cf, cp, cv = feature.shape[1], prediction.shape[1], 2 * nb
-                concat = torch.empty((pc, cf + 2 * cv + cp, h, w), dtype=torch.float32, device=dev,
-                                     memory_format=torch.channels_last)
-                tc.resize_bilinear(feature, (h, w), False, out=concat, out_channel_offset=0)
-                with torch.cuda.device(dev):
-                    _lib.check(lib.fvfi_phasenet_assemble(ph.data_ptr(), am.data_ptr(), den[l].data_ptr(),
-                                                          concat.data_ptr() + 4 * cf, concat.stride(3), P, p0, pc, nb, h, w,
-                                                          _lib.stream_ptr()))
-                tc.resize_bilinear(prediction, (h, w), False, out=concat, out_channel_offset=cf + 2 * cv)
                 i = idx + 1 if idx + 1 < len(self.layers) - 1 else len(self.layers) - 1
-                feature, prediction = self.layers[i](concat)
-                del concat
+                if tc.fuse_upsample and cf % 32 == 0:
+                    # cat(interpolate(feature), values, interpolate(prediction)) is never built: the value channels and the resampled
+                    # prediction go into a compact [.., 24] record, the 64 feature channels are resampled by the loaders of the
+                    # level's first convolution
+                    cd = (2 * cv + cp + 7) // 8 * 8
+                    direct = torch.empty((pc, cd, h, w), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+                    if cd != 2 * cv + cp:
+                        direct.zero_()                                                     # padding channels must be finite
+                    with torch.cuda.device(dev):
+                        _lib.check(lib.fvfi_phasenet_assemble(ph.data_ptr(), am.data_ptr(), den[l].data_ptr(), direct.data_ptr(),
+                                                              direct.stride(3), P, p0, pc, nb, h, w, _lib.stream_ptr()))
+                    tc.resize_bilinear(prediction, (h, w), False, out=direct, out_channel_offset=2 * cv)
+                    feature, prediction = self.layers[i].forward_resampled(feature, direct, (h, w))
+                    del direct
+                else:
+                    concat = torch.empty((pc, cf + 2 * cv + cp, h, w), dtype=torch.float32, device=dev,
+                                         memory_format=torch.channels_last)
+                    tc.resize_bilinear(feature, (h, w), False, out=concat, out_channel_offset=0)
+                    with torch.cuda.device(dev):
+                        _lib.check(lib.fvfi_phasenet_assemble(ph.data_ptr(), am.data_ptr(), den[l].data_ptr(),
+                                                              concat.data_ptr() + 4 * cf, concat.stride(3), P, p0, pc, nb, h, w,
+                                                              _lib.stream_ptr()))
+                    tc.resize_bilinear(prediction, (h, w), False, out=concat, out_channel_offset=cf + 2 * cv)
+                    feature, prediction = self.layers[i](concat)
+                    del concat
                 pr = tc.to_nhwc(prediction)
                 with torch.cuda.device(dev):
                     _lib.check(lib.fvfi_phasenet_outputs(pr.data_ptr(), pr.stride(3), am.data_ptr(), phase_out[l].data_ptr(),

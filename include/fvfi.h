@@ -138,9 +138,13 @@ int fvfi_conv2d_nhwc_residual(const float* x, int x_pixel_stride, const float* p
  * convolution evaluate the bilinear resampling (ATen's upsample_bilinear2d arithmetic, the same as fvfi_resize_bilinear_nhwc)
  * while they stage the operand, so the [B,H,W,Cin] intermediate never exists in HBM.  x must be 32-byte aligned (FVFI_CONV_TF32X3: 16)
  * with x_pixel_stride a multiple of 8 (4) that covers Cin rounded up to it; channels between Cin and that bound must be finite.
- * Hs == Ws == 0 is fvfi_conv2d_nhwc_residual. */
-int fvfi_conv2d_nhwc_upsampled(const float* x, int x_pixel_stride, int Hs, int Ws, int align_corners,
-                               const float* packed_weight, const float* bias, const float* residual, int residual_pixel_stride,
+ * Hs == Ws == 0 is fvfi_conv2d_nhwc_residual.
+ * Two-source form (x_direct != NULL):  conv(cat(resize(x[:, :cin_upsampled]), x_direct), ...) without the concatenated tensor --
+ * PhaseNet's level input `cat(values, interpolate(previous features), interpolate(previous prediction))` (src/phase_net/phase_net.py:
+ * 138-148): the first cin_upsampled input channels (a multiple of 32; FVFI_CONV_TF32X3: 16) are the resampled x, the remaining
+ * Cin - cin_upsampled come from x_direct [B,H,W,x_direct_pixel_stride] at the convolution's own resolution. */
+int fvfi_conv2d_nhwc_upsampled(const float* x, int x_pixel_stride, int Hs, int Ws, int align_corners, const float* x_direct,
+                               int x_direct_pixel_stride, int cin_upsampled, const float* packed_weight, const float* bias, const float* residual, int residual_pixel_stride,
                                float* y, int y_pixel_stride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad_mode,
                                int activation, int out_nchw, int precision, void* stream);
 /* FVFI_CONV_F16X3 scales activations by 2^4 before the fp16 split; |x| > 4094 would leave fp16's range.  Returns 1

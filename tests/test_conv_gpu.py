@@ -285,3 +285,33 @@ def test_conv_fused_bilinear_upsample(B, Cin, Cout, Hs, Ws, mode, act, align, ex
         ref = ref + skip.double()
     assert float((y.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
     conv.check_overflow()
+
+
+@pytest.mark.parametrize("B,Cup,Cd,Cout,K,hs,ws,H,W", [
+    (2, 64, 24, 64, 3, 27, 38, 38, 54),      # PhaseNet level: 64 resampled feature channels + 16 value + 8 prediction channels, ratio sqrt(2)
+    (1, 64, 17, 64, 1, 9, 13, 13, 18),       # the first level: 1x1 convolution, 81 input channels (direct record padded to 24)
+    (1, 32, 40, 48, 3, 20, 20, 40, 40),      # several direct chunks
+])
+def test_conv_two_source_resampled_concat(B, Cup, Cd, Cout, K, hs, ws, H, W, prec):
+    """conv(cat(interpolate(x, size), x_direct)) without the concat (fvfi_conv2d_nhwc_upsampled, two-source form; phase_net.py:138-148):
+    bit-identical to resize kernel -> torch.cat -> convolution, and within the convolution's tolerance of the fp64 composition."""
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn((B, Cup, hs, ws), device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    Cs = (Cd + 7) // 8 * 8
+    xd = torch.zeros((B, Cs, H, W), device="cuda").contiguous(memory_format=torch.channels_last)
+    xd[:, :Cd] = torch.randn((B, Cd, H, W), device="cuda", generator=g)
+    Cin = Cup + Cd
+    w = torch.randn((Cout, Cin, K, K), device="cuda", generator=g) / (K * Cin ** 0.5)
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    mode = "reflect" if K == 3 else "zeros"
+    y = conv.conv2d(x, w, b, mode, "elu", upsample=((H, W), False), x_direct=xd)
+    cat = torch.cat((conv.resize_bilinear(x, (H, W), False), xd[:, :Cd]), 1)
+    y2 = conv.conv2d(cat, w, b, mode, "elu")
+    assert y.shape == (B, Cout, H, W) and torch.equal(y, y2)
+    xr = torch.cat((F.interpolate(x.double(), size=(H, W), mode="bilinear", align_corners=False), xd[:, :Cd].double()), 1)
+    if K == 3:
+        xr = F.pad(xr, (1, 1, 1, 1), mode="reflect")
+    ref = F.elu(F.conv2d(xr, w.double(), b.double()))
+    assert float((y.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    conv.check_overflow()
