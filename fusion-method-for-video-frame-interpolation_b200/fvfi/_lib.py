@@ -45,6 +45,11 @@ _PROTOS = {
     "fvfi_conv2d_nhwc_upsampled": (c_int, [c_fp, c_int, c_int, c_int, c_int, c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_int]
                                    + [c_int] * 11 + [c_fp]),
     "fvfi_conv2d_overflow_count": (c_int, []),
+    "fvfi_conv2d_grad_act_workspace_floats": (c_size, [c_int] * 5),
+    "fvfi_conv2d_grad_act": (c_int, [c_fp, c_int, c_fp, c_int, c_fp] + [c_int] * 6 + [c_fp, c_fp, c_fp]),
+    "fvfi_reflect_pad_backward_nhwc": (c_int, [c_fp, c_int, c_fp, c_int] + [c_int] * 5 + [c_fp]),
+    "fvfi_conv2d_wgrad_workspace_floats": (c_size, [c_int] * 6),
+    "fvfi_conv2d_wgrad_nhwc": (c_int, [c_fp, c_int, c_fp, c_int, ctypes.c_longlong, ctypes.c_longlong, c_fp] + [c_int] * 7 + [c_fp, c_fp]),
     "fvfi_nchw_to_nhwc_slice": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "fvfi_conv1x1_nhwc": (c_int, [c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_size, c_int, c_int, c_int, c_fp]),
     "fvfi_upsample2_tapsum": (c_int, [c_fp, c_int, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),

@@ -83,8 +83,12 @@ def use_tc(x):
 
 
 class _ConvTC(torch.autograd.Function):
-    """act(conv(pad(x), w) + b) with the FORWARD on the tcgen05 kernel (activations saved for backward); the backward (dgrad, wgrad,
-    bias grad) is ATen's convolution_backward on the saved input -- hand-written dgrad / wgrad kernels are not built."""
+    """act(conv(pad(x), w) + b), forward AND backward on libfvfi (no cuDNN / ATen convolution on the training path):
+    forward = the tcgen05 kernel, activations saved; backward (csrc/conv_bwd.cu, include/fvfi.h "Backward of the same convolutions"):
+    ``fvfi_conv2d_grad_act`` (g = gy * act'(y) into a zero canvas + bias gradient), the data gradient as the tcgen05 kernel run
+    over that canvas with the flipped / transposed filter in 3xTF32 (+ ``fvfi_reflect_pad_backward_nhwc``), and
+    ``fvfi_conv2d_wgrad_nhwc`` (pixel-split fp32 GEMM, fixed summation order).  Replaces what the reference gets from
+    torch.nn.Conv2d's autograd in src/fusion_net/trainer.py:246-259."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, padding_mode, act):
@@ -96,33 +100,43 @@ class _ConvTC(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, weight, y = ctx.saved_tensors
-        act, p = ctx.act, weight.shape[2] // 2
-        if act == "relu":
-            g = gy * (y > 0)
-        elif act == "elu":
-            g = gy * torch.where(y > 0, torch.ones_like(y), y + 1)          # d/dx elu = exp(x) = y + 1 for x < 0
-        elif act == "tanh":
-            g = gy * (1 - y * y)
-        elif act == "sigmoid":
-            g = gy * y * (1 - y)
-        else:
-            assert act in (None, "none"), "no backward for activation %r" % (act,)
-            g = gy
-        g = g.contiguous(memory_format=torch.channels_last)
-        xin = x.float()
-        if xin.shape[1] > weight.shape[1]:
-            xin = xin[:, :weight.shape[1]]
-        reflect = ctx.padding_mode == "reflect" and p > 0
-        if reflect:
-            xin = torch.nn.functional.pad(xin, (p, p, p, p), mode="reflect")
-        mask = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]]
-        gx, gw, gb = torch.ops.aten.convolution_backward(g, xin, weight, [weight.shape[0]] if ctx.has_bias else None, [1, 1],
-                                                         [0, 0] if reflect else [p, p], [1, 1], False, [0, 0], 1, mask)
-        if gx is not None and reflect:
-            gx = torch.ops.aten.reflection_pad2d_backward(gx, x.float()[:, :weight.shape[1]], [p, p, p, p])
-        if gx is not None and gx.shape[1] < x.shape[1]:
-            gx = torch.nn.functional.pad(gx, (0, 0, 0, 0, 0, x.shape[1] - gx.shape[1]))
-        return gx, gw, (gb if ctx.has_bias else None), None, None
+        assert ctx.act in (None, "none", "relu", "elu", "tanh", "sigmoid"), "no backward for activation %r" % (ctx.act,)
+        Cout, Cin, K, _ = weight.shape
+        B, Cx, H, W = x.shape
+        P = K // 2
+        reflect = ctx.padding_mode == "reflect" and P > 0
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        L, dev, f32 = _lib.lib(), x.device, torch.float32
+        gyc, yc, xc = to_nhwc(gy.detach().float()), to_nhwc(y), to_nhwc(x.detach().float())
+        border = P if (need_x and reflect) else 0          # the full correlation of the data gradient needs the zero frame
+        Hc, Wc = H + 2 * border, W + 2 * border
+        canvas = torch.empty((B, Cout, Hc, Wc), dtype=f32, device=dev, memory_format=torch.channels_last)
+        gb = torch.empty(Cout, dtype=f32, device=dev) if need_b else None
+        with torch.cuda.device(dev):
+            ws = torch.empty(L.fvfi_conv2d_grad_act_workspace_floats(B, H, W, Cout, border), dtype=f32, device=dev) if need_b else None
+            _lib.check(L.fvfi_conv2d_grad_act(gyc.data_ptr(), gyc.stride(3), yc.data_ptr(), yc.stride(3), canvas.data_ptr(), B, H, W,
+                                              Cout, border, ACT[ctx.act], _lib.ptr(gb), _lib.ptr(ws), _lib.stream_ptr()))
+            gw = None
+            if need_w:
+                gw = torch.empty((Cout, Cin, K, K), dtype=f32, device=dev)
+                ws2 = torch.empty(L.fvfi_conv2d_wgrad_workspace_floats(B, H, W, Cin, Cout, K), dtype=f32, device=dev)
+                _lib.check(L.fvfi_conv2d_wgrad_nhwc(xc.data_ptr(), xc.stride(3), canvas.data_ptr() + 4 * Cout * (border * Wc + border),
+                                                    Cout, Wc, Hc * Wc, gw.data_ptr(), B, H, W, Cin, Cout, K, 1 if reflect else 0,
+                                                    ws2.data_ptr(), _lib.stream_ptr()))
+            gx = None
+            if need_x:
+                wt = weight.detach().float().flip(2, 3).transpose(0, 1).contiguous()       # [Cin, Cout, K, K], taps mirrored
+                with torch.no_grad(), forced_precision("tf32x3"):
+                    gxp = conv2d(canvas, wt, None, "zeros", None)                          # [B, Cin, Hc, Wc]
+                if reflect:
+                    gx = torch.empty((B, Cx, H, W), dtype=f32, device=dev, memory_format=torch.channels_last)
+                    if Cx > Cin:
+                        gx.zero_()
+                    _lib.check(L.fvfi_reflect_pad_backward_nhwc(gxp.data_ptr(), gxp.stride(3), gx.data_ptr(), gx.stride(3), B, H, W,
+                                                                Cin, P, _lib.stream_ptr()))
+                else:
+                    gx = gxp if Cx == Cin else torch.nn.functional.pad(gxp, (0, 0, 0, 0, 0, Cx - Cin))
+        return gx, gw, gb, None, None
 
 
 ACT = {None: 0, "none": 0, "relu": 1, "elu": 2, "tanh": 3, "sigmoid": 4, "softmax": 5}

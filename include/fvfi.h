@@ -152,6 +152,31 @@ int fvfi_conv2d_nhwc_upsampled(const float* x, int x_pixel_stride, int Hs, int W
  * Synchronises the device. */
 int fvfi_conv2d_overflow_count(void);
 
+/* ---------------------------------------------------------------------------------------
+ * Backward of the same convolutions, for the FusionNet training step (src/fusion_net/trainer.py:246-259; the reference takes
+ * these gradients from torch.nn.Conv2d's cuDNN autograd for the layers of src/fusion_net/fusion_net.py:24-36).
+ * With y = act(conv(pad(x), w) + b) and g = dL/dy * act'(y):
+ *   fvfi_conv2d_grad_act: g written into the interior of a zero canvas g_canvas [B, H+2*border, W+2*border, C] (contiguous NHWC;
+ *     border = 0: plain g) from gy and the SAVED OUTPUT y (activation 0 none -- y may be NULL --, 1 ReLU, 2 ELU, 3 tanh, 4 sigmoid),
+ *     and, if gbias != NULL, the bias gradient gbias[C] = sum over pixels of g (fixed summation order).  workspace:
+ *     fvfi_conv2d_grad_act_workspace_floats floats (only needed with gbias).
+ *   data gradient: dL/d(pad x) = fvfi_conv2d_nhwc(g_canvas with border K/2, weights [Cin,Cout,K,K] = w[o,c,K-1-ky,K-1-kx], zero
+ *     padding, FVFI_CONV_TF32X3 -- gradients have no bounded range) on [B, H+2*(K/2), W+2*(K/2)]; for pad_mode zeros the interior
+ *     of that result is dL/dx, for reflect padding fvfi_reflect_pad_backward_nhwc folds the mirrored border back
+ *     (the adjoint of torch's 'reflect' padding; gx [B,H,W,C], H, W > P).
+ *   fvfi_conv2d_wgrad_nhwc: gw_oihw [Cout,Cin,K,K] = sum_{b,y,x} g[b,y,x,o] * pad(x)[b,y+ky,x+kx,c].  g may live inside a canvas:
+ *     pixel (b,y,x) at ((b * g_image_pixels + y * g_row_pixels + x) * g_pixel_stride.  Split over pixel ranges into partial sums
+ *     (workspace: fvfi_conv2d_wgrad_workspace_floats floats) that are added in a fixed order: bit-reproducible. */
+size_t fvfi_conv2d_grad_act_workspace_floats(int B, int H, int W, int C, int border);
+int fvfi_conv2d_grad_act(const float* gy, int gy_pixel_stride, const float* y, int y_pixel_stride, float* g_canvas, int B, int H,
+                         int W, int C, int border, int activation, float* gbias, float* workspace, void* stream);
+int fvfi_reflect_pad_backward_nhwc(const float* gxp, int gxp_pixel_stride, float* gx, int gx_pixel_stride, int B, int H, int W, int C,
+                                   int P, void* stream);
+size_t fvfi_conv2d_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout, int K);
+int fvfi_conv2d_wgrad_nhwc(const float* x, int x_pixel_stride, const float* g, int g_pixel_stride, long long g_row_pixels,
+                           long long g_image_pixels, float* gw_oihw, int B, int H, int W, int Cin, int Cout, int K, int pad_mode,
+                           float* workspace, void* stream);
+
 /* Direct (CUDA-core, fp32 FFMA) 1x1 convolution for Cout <= 8 -- the layers that are a pure stream of the activation:
  * PhaseNet's per-level prediction Conv2d(64, 8, 1) + tanh (src/phase_net/phase_net.py:197-200) and FusionNet's last
  * Conv2d(32, 3, 1) (src/fusion_net/fusion_net.py:36).  x [npix, x_pixel_stride] NHWC pixels (32-byte aligned, Cin a multiple

@@ -315,3 +315,80 @@ def test_conv_two_source_resampled_concat(B, Cup, Cd, Cout, K, hs, ws, H, W, pre
     ref = F.elu(F.conv2d(xr, w.double(), b.double()))
     assert float((y.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
     conv.check_overflow()
+
+
+BWD_CASES = [
+    # B, Cin, Cout, K, H, W, mode, act, scale of gy  -- the seven layers of FusionNet (fusion_net.py:24-36) at reduced size + edge cases
+    (2, 18, 32, 5, 40, 56, "reflect", "relu", 1.0),
+    (2, 32, 64, 5, 20, 28, "reflect", "relu", 1.0),
+    (2, 64, 128, 3, 10, 14, "reflect", "relu", 1.0),
+    (2, 128, 128, 3, 5, 7, "reflect", "relu", 1.0),
+    (1, 128, 64, 5, 10, 14, "reflect", None, 1.0),
+    (1, 64, 32, 5, 20, 28, "reflect", None, 1e-7),       # gradients far below fp16's range: the data gradient runs in 3xTF32
+    (2, 32, 3, 1, 40, 56, "zeros", None, 1.0),
+    (1, 24, 5, 3, 31, 45, "zeros", "elu", 1.0),
+    (1, 16, 40, 3, 17, 19, "reflect", "tanh", 1e3),
+    (3, 7, 33, 3, 9, 11, "zeros", "sigmoid", 1.0),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,K,H,W,mode,act,gscale", BWD_CASES)
+def test_conv_backward_matches_fp64(B, Cin, Cout, K, H, W, mode, act, gscale):
+    """dL/dx, dL/dw, dL/db of conv2d's autograd Function (csrc/conv_bwd.cu + the tcgen05 kernel as dgrad) against torch's fp64
+    autograd of the same expression; no ATen convolution kernel may run in the backward."""
+    from fvfi import conv, _lib
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((B, Cin, H, W), device="cuda", generator=g)
+    w = torch.randn((Cout, Cin, K, K), device="cuda", generator=g) / (Cin * K * K) ** 0.5
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    gy = torch.randn((B, Cout, H, W), device="cuda", generator=g) * gscale
+    xg, wg, bg = (t.clone().requires_grad_(True) for t in (x, w, b))
+    with torch.enable_grad():
+        y = conv.conv2d(xg, wg, bg, mode, act)
+    n0 = _lib.lib().fvfi_launch_count()
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        y.backward(gy)
+        torch.cuda.synchronize()
+    assert _lib.lib().fvfi_launch_count() - n0 >= 5
+    foreign = [e.key for e in prof.key_averages() if "cudnn" in e.key.lower() or "convolution" in e.key.lower() or "gemm" in e.key.lower()]
+    assert not foreign, foreign
+    # fp64 reference built on the GPU kernel's own forward output for the activation mask (a ReLU mask is discontinuous)
+    xd, wd, bd = (t.double().clone().requires_grad_(True) for t in (x, w, b))
+    p = K // 2
+    xr = F.pad(xd, (p, p, p, p), mode="reflect") if (mode == "reflect" and p) else xd
+    pre = F.conv2d(xr, wd, bd, padding=0 if (mode == "reflect" and p) else p)
+    yd = y.detach().double()
+    dact = {None: torch.ones_like(yd), "relu": (yd > 0).double(), "elu": torch.where(yd > 0, torch.ones_like(yd), yd + 1),
+            "tanh": 1 - yd * yd, "sigmoid": yd * (1 - yd)}[act]
+    pre.backward(gy.double() * dact)
+    for name, got, ref in (("gx", xg.grad, xd.grad), ("gw", wg.grad, wd.grad), ("gb", bg.grad, bd.grad)):
+        err = float((got.double() - ref).abs().max())
+        scale = float(ref.abs().max())
+        print("%s max abs err %.2e (max |ref| %.2e)" % (name, err, scale))
+        assert got.shape == ref.shape
+        assert err <= 2e-5 * scale + 1e-30, (name, err, scale)
+
+
+def test_conv_backward_is_reproducible_and_handles_padded_input_channels():
+    """Two backward passes give identical bits (fixed summation order: the data-parallel parity check relies on it); an input
+    with zero padding channels beyond the weight's Cin gets zero gradient there."""
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.zeros((2, 24, 24, 40), device="cuda")
+    x[:, :18] = torch.randn((2, 18, 24, 40), device="cuda", generator=g)
+    w = torch.randn((32, 18, 5, 5), device="cuda", generator=g) * 0.05
+    b = torch.randn((32,), device="cuda", generator=g)
+    gy = torch.randn((2, 32, 24, 40), device="cuda", generator=g)
+    outs = []
+    for _ in range(2):
+        xg, wg, bg = (t.clone().requires_grad_(True) for t in (x, w, b))
+        with torch.enable_grad():
+            conv.conv2d(xg, wg, bg, "reflect", "relu").backward(gy)
+        outs.append((xg.grad.clone(), wg.grad.clone(), bg.grad.clone()))
+    for a, c in zip(*outs):
+        assert torch.equal(a, c)
+    assert outs[0][0].shape == x.shape and float(outs[0][0][:, 18:].abs().max()) == 0.0
+    xd, wd, bd = x[:, :18].double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    F.relu(F.conv2d(F.pad(xd, (2, 2, 2, 2), mode="reflect"), wd, bd)).backward(gy.double())
+    assert float((outs[0][0][:, :18].double() - xd.grad).abs().max()) <= 2e-5 * float(xd.grad.abs().max())
+    assert float((outs[0][1].double() - wd.grad).abs().max()) <= 2e-5 * float(wd.grad.abs().max())
