@@ -43,42 +43,69 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
 // block (CX, PY): thread (tx, ty) owns channels tx, tx + CX, ... of the canvas pixels ty, ty + PY, ... of the block's range
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int GA_THREADS = 256;
-constexpr int GA_MAX_CPT = 8;       // channels per thread (C <= 8 * 32 at CX = 32; CX grows with C)
+constexpr int GA_MAX_CPT = 8;       // channel items per thread (VEC: float4 quads)
 
+// One block walks canvas rows blockIdx.x, blockIdx.x + gridDim.x, ...; thread (tx, ty) owns the channel items tx, tx + CX, ... of the
+// row's pixels ty, ty + PY, ...  VEC: an item is a float4 channel quad (C, both pixel strides multiples of 4, 16-byte aligned bases).
+template <bool VEC>
 __global__ void __launch_bounds__(GA_THREADS) grad_act_kernel(const float* __restrict__ gy, int gy_ps, const float* __restrict__ y,
                                                              int y_ps, float* __restrict__ canvas, int B, int H, int W, int C,
-                                                             int border, int act, float* __restrict__ bias_part,
-                                                             long long px_per_block) {
+                                                             int border, int act, float* __restrict__ bias_part) {
     extern __shared__ float red[];                       // [PY][C]
+    constexpr int E = VEC ? 4 : 1;
     const int CX = blockDim.x, PY = blockDim.y;
     const int Hc = H + 2 * border, Wc = W + 2 * border;
-    const long long npix = (long long)B * Hc * Wc;
-    const long long p0 = (long long)blockIdx.x * px_per_block, p1 = min(p0 + px_per_block, npix);
-    float sum[GA_MAX_CPT];
+    const int items = C / E;
+    float sum[GA_MAX_CPT][E];
 #pragma unroll
-    for (int i = 0; i < GA_MAX_CPT; ++i) sum[i] = 0.f;
-    for (long long p = p0 + threadIdx.y; p < p1; p += PY) {
-        const int b = (int)(p / ((long long)Hc * Wc));
-        const int r = (int)(p - (long long)b * Hc * Wc);
-        const int yy = r / Wc - border, xx = r % Wc - border;
-        const bool inside = yy >= 0 && yy < H && xx >= 0 && xx < W;
-        const size_t src = ((size_t)b * H + (inside ? yy : 0)) * W + (inside ? xx : 0);
+    for (int i = 0; i < GA_MAX_CPT; ++i)
 #pragma unroll
-        for (int i = 0; i < GA_MAX_CPT; ++i) {
-            const int c = threadIdx.x + i * CX;
-            if (c < C) {
-                float v = 0.f;
-                if (inside) v = __ldg(gy + src * gy_ps + c) * (act ? act_grad_from_output(__ldg(y + src * y_ps + c), act) : 1.f);
-                canvas[(size_t)p * C + c] = v;
-                sum[i] += v;
+        for (int e = 0; e < E; ++e) sum[i][e] = 0.f;
+    for (int row = blockIdx.x; row < B * Hc; row += gridDim.x) {
+        const int b = row / Hc, yy = row - b * Hc - border;
+        const bool row_in = yy >= 0 && yy < H;
+        float* crow = canvas + (size_t)row * Wc * C;
+        const size_t srow = ((size_t)b * H + (row_in ? yy : 0)) * W;
+        for (int xc = threadIdx.y; xc < Wc; xc += PY) {
+            const int xx = xc - border;
+            const bool inside = row_in && xx >= 0 && xx < W;
+            const size_t src = srow + (inside ? xx : 0);
+#pragma unroll
+            for (int i = 0; i < GA_MAX_CPT; ++i) {
+                const int it = threadIdx.x + i * CX;
+                if (it >= items) continue;
+                float v[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = 0.f;
+                if (inside) {
+                    if (VEC) {
+                        const float4 gv = __ldg(reinterpret_cast<const float4*>(gy + src * gy_ps) + it);
+                        v[0] = gv.x; v[E > 1 ? 1 : 0] = gv.y; v[E > 2 ? 2 : 0] = gv.z; v[E > 3 ? 3 : 0] = gv.w;
+                        if (act) {
+                            const float4 yv = __ldg(reinterpret_cast<const float4*>(y + src * y_ps) + it);
+                            v[0] *= act_grad_from_output(yv.x, act);
+                            v[E > 1 ? 1 : 0] *= act_grad_from_output(yv.y, act);
+                            v[E > 2 ? 2 : 0] *= act_grad_from_output(yv.z, act);
+                            v[E > 3 ? 3 : 0] *= act_grad_from_output(yv.w, act);
+                        }
+                    } else {
+                        v[0] = __ldg(gy + src * gy_ps + it) * (act ? act_grad_from_output(__ldg(y + src * y_ps + it), act) : 1.f);
+                    }
+                }
+                if (VEC) reinterpret_cast<float4*>(crow + (size_t)xc * C)[it] = make_float4(v[0], v[E > 1 ? 1 : 0], v[E > 2 ? 2 : 0], v[E > 3 ? 3 : 0]);
+                else crow[(size_t)xc * C + it] = v[0];
+#pragma unroll
+                for (int e = 0; e < E; ++e) sum[i][e] += v[e];
             }
         }
     }
     if (bias_part == nullptr) return;
 #pragma unroll
     for (int i = 0; i < GA_MAX_CPT; ++i) {
-        const int c = threadIdx.x + i * CX;
-        if (c < C) red[threadIdx.y * C + c] = sum[i];
+        const int it = threadIdx.x + i * CX;
+        if (it < items)
+#pragma unroll
+            for (int e = 0; e < E; ++e) red[threadIdx.y * C + it * E + e] = sum[i][e];
     }
     __syncthreads();
     for (int c = threadIdx.y * CX + threadIdx.x; c < C; c += CX * PY) {
@@ -88,19 +115,20 @@ __global__ void __launch_bounds__(GA_THREADS) grad_act_kernel(const float* __res
     }
 }
 
-// out[i] = sum_s part[s * n + i], fixed order; remap: wgrad partials are [Cout][tap][Cin], the gradient is OIHW [Cout][Cin][tap]
-__global__ void sum_partials_kernel(const float* __restrict__ part, int S, size_t n, float* __restrict__ out, int Cin, int taps) {
+// out[i] = sum_s part[s * n + i], fixed order; remap: wgrad partials are [Cout][tap][CinP], the gradient is OIHW [Cout][Cin][tap]
+__global__ void sum_partials_kernel(const float* __restrict__ part, int S, size_t n, float* __restrict__ out, int Cin, int CinP, int taps) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float s = 0.f;
-    for (int k = 0; k < S; ++k) s += __ldg(part + (size_t)k * n + i);
     size_t o = i;
     if (taps > 0) {
-        const size_t per = (size_t)Cin * taps;
+        const size_t per = (size_t)CinP * taps;
         const size_t co = i / per, r = i - co * per;
-        const int t = (int)(r / Cin), c = (int)(r - (size_t)t * Cin);
-        o = co * per + (size_t)c * taps + t;
+        const int t = (int)(r / CinP), c = (int)(r - (size_t)t * CinP);
+        if (c >= Cin) return;
+        o = (co * Cin + c) * taps + t;
     }
+    float s = 0.f;
+    for (int k = 0; k < S; ++k) s += __ldg(part + (size_t)k * n + i);
     out[o] = s;
 }
 
@@ -137,7 +165,7 @@ __global__ void reflect_fold_kernel(const float* __restrict__ gxp, int gxp_ps, f
 // ------------------------------------------------------------------------------------------------------------------
 // weight gradient
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int WG_THREADS = 256, WG_TN = 64, WG_TK = 16;
+constexpr int WG_THREADS = 256, WG_TK = 16, WG_TN = 128;
 
 struct WgradArgs {
     const float* x;      // [B,H,W,x_ps] NHWC
@@ -146,99 +174,140 @@ struct WgradArgs {
     int x_ps, g_ps;
     long long g_row, g_img;     // pixels
     int B, H, W, Cin, Cout, K, P, reflect;
-    int Ntot;            // K*K*Cin, n = tap*Cin + c
+    int CinP;            // im2col columns per tap: Cin, or Cin rounded up to 4 when the pixels of x can be read as float4
+    int Ntot;            // K*K*CinP, n = tap*CinP + c  (columns with c >= Cin are dead)
+    int x_vec;           // x pixels can be read as float4 channel quads
+    int g_vec;           // g rows can be read as float4 (Cout, g_ps multiples of 4, 16-byte aligned base)
     long long npix, px_per_split;
 };
 
 __device__ __forceinline__ int reflect_index(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
 
-template <int MI>      // output channels per thread; the CTA tile is (16*MI) x 64
+// CTA tile TM x 128 (TM = 4*WM*MI output channels, 128 im2col columns), 16 pixels per staged chunk, 8 warps as WM x (8/WM).
+// A warp covers 4 channel groups x 8 column groups, so a k-step costs it ONE shared-memory wavefront per 128-bit operand read
+// (8 adjacent column quads = 128 B; 4 channel groups <= 128 B) for MI*NB FFMAs per thread: FFMA-bound, not shared-memory-bound.
+// Thread (tm, tn): channels tm*MI .. +MI, column quads 4*tn + (128/NQ)*q, q < NQ = NB/4.
+template <int MI, int NB, int WM>
 __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgradArgs a) {
-    constexpr int TM = 16 * MI;
-    constexpr int A_PER = TM * WG_TK / WG_THREADS;          // A elements a thread stages per chunk (MI)
+    constexpr int TM = 4 * WM * MI, WN = 8 / WM, TN = 8 * WN * NB, NQ = NB / 4, SB = TN / 16;
+    static_assert(TN == WG_TN && TM * WG_TK / WG_THREADS >= 1, "tile shape");
+    constexpr int SA = TM * WG_TK / WG_THREADS;          // A elements a thread stages per chunk
     __shared__ __align__(16) float As[WG_TK][TM];
-    __shared__ __align__(16) float Bs[WG_TK][WG_TN];
-    const int tid = threadIdx.x;
-    const int tn = tid & 15, tm = tid >> 4;
-    const int n0 = blockIdx.x * WG_TN, m0 = blockIdx.y * TM;
+    __shared__ __align__(16) float Bs[WG_TK][TN];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tm = (warp % WM) * 4 + (lane >> 3), tn = (warp / WM) * 8 + (lane & 7);
+    const int n0 = blockIdx.x * TN, m0 = blockIdx.y * TM;
     const long long p_begin = (long long)blockIdx.z * a.px_per_split;
     const long long p_end = min(p_begin + a.px_per_split, a.npix);
 
-    // staging roles: A -- row ka = tid / 16, channels ma .. ma+MI-1;   B -- row kb = tid / 16, columns nb .. nb+3
+    // staging roles: pixel row krow = tid / 16 of the chunk; A -- channels ma .. ma+SA-1;  B -- column quads 4*(tid & 15) + 64*q
     const int krow = tid >> 4;
-    const int ma = (tid & 15) * A_PER;
-    const int nb = (tid & 15) * 4;
-    int bdy[4], bdx[4], bc[4];
+    const int ma = (tid & 15) * SA;
+    int bcol[SB];                                         // c | (dy + 8) << 16 | (dx + 8) << 20, or -1 beyond the last column
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int n = n0 + nb + j;
+    for (int j = 0; j < SB; ++j) {
+        const int n = n0 + 64 * (j >> 2) + 4 * (tid & 15) + (j & 3);
         if (n < a.Ntot) {
-            const int t = n / a.Cin;
-            bc[j] = n - t * a.Cin;
-            bdy[j] = t / a.K - a.P;
-            bdx[j] = t % a.K - a.P;
+            const int t = n / a.CinP;
+            bcol[j] = (n - t * a.CinP) | ((t / a.K - a.P + 8) << 16) | ((t % a.K - a.P + 8) << 20);
         } else {
-            bc[j] = -1; bdy[j] = 0; bdx[j] = 0;
+            bcol[j] = -1;
         }
     }
-    float ra[A_PER], rb[4];
+    float ra[SA], rb[SB];
     auto fetch = [&](long long pbase) {
         const long long p = pbase + krow;
         const bool live = p < p_end;
         int b = 0, y = 0, x = 0;
         if (live) {
-            const long long hw = (long long)a.H * a.W;
+            const unsigned hw = (unsigned)(a.H * a.W);
             b = (int)(p / hw);
-            const int r = (int)(p - (long long)b * hw);
-            y = r / a.W;
-            x = r - y * a.W;
+            const unsigned r = (unsigned)(p - (long long)b * hw);
+            y = (int)(r / (unsigned)a.W);
+            x = (int)(r - (unsigned)y * (unsigned)a.W);
         }
         const float* gp = a.g + ((size_t)b * a.g_img + (size_t)y * a.g_row + x) * a.g_ps + m0 + ma;
+        if (SA >= 4 && a.g_vec && m0 + ma + SA <= a.Cout) {
 #pragma unroll
-        for (int i = 0; i < A_PER; ++i) ra[i] = (live && m0 + ma + i < a.Cout) ? __ldg(gp + i) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float v = 0.f;
-            if (live && bc[j] >= 0) {
-                int yy = y + bdy[j], xx = x + bdx[j];
-                bool ok = true;
-                if (a.reflect) {
-                    yy = reflect_index(yy, a.H);
-                    xx = reflect_index(xx, a.W);
-                } else {
-                    ok = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
-                }
-                if (ok) v = __ldg(a.x + (((size_t)b * a.H + yy) * a.W + xx) * a.x_ps + bc[j]);
+            for (int i = 0; i + 3 < SA; i += 4) {
+                const float4 v = live ? __ldg(reinterpret_cast<const float4*>(gp + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                ra[i] = v.x; ra[i + 1] = v.y; ra[i + 2] = v.z; ra[i + 3] = v.w;
             }
-            rb[j] = v;
+        } else {
+#pragma unroll
+            for (int i = 0; i < SA; ++i) ra[i] = (live && m0 + ma + i < a.Cout) ? __ldg(gp + i) : 0.f;
+        }
+        const float* xb = a.x + (size_t)b * a.H * a.W * a.x_ps;
+        if (a.x_vec) {                                   // a column quad = 4 adjacent channels of one tap: one 128-bit load
+#pragma unroll
+            for (int j = 0; j < SB; j += 4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live && bcol[j] >= 0) {
+                    int yy = y + ((bcol[j] >> 16) & 15) - 8, xx = x + ((bcol[j] >> 20) & 15) - 8;
+                    bool ok = true;
+                    if (a.reflect) {
+                        yy = reflect_index(yy, a.H);
+                        xx = reflect_index(xx, a.W);
+                    } else {
+                        ok = (unsigned)yy < (unsigned)a.H && (unsigned)xx < (unsigned)a.W;
+                    }
+                    if (ok) v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)(yy * a.W + xx) * a.x_ps + (bcol[j] & 0xffff)));
+                }
+                rb[j] = v.x; rb[j + 1] = v.y; rb[j + 2] = v.z; rb[j + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                float v = 0.f;
+                if (live && bcol[j] >= 0) {
+                    int yy = y + ((bcol[j] >> 16) & 15) - 8, xx = x + ((bcol[j] >> 20) & 15) - 8;
+                    bool ok = true;
+                    if (a.reflect) {
+                        yy = reflect_index(yy, a.H);
+                        xx = reflect_index(xx, a.W);
+                    } else {
+                        ok = (unsigned)yy < (unsigned)a.H && (unsigned)xx < (unsigned)a.W;
+                    }
+                    if (ok) v = __ldg(xb + (size_t)(yy * a.W + xx) * a.x_ps + (bcol[j] & 0xffff));
+                }
+                rb[j] = v;
+            }
         }
     };
 
-    float acc[MI][4];
+    float acc[MI][NB];
 #pragma unroll
     for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < NB; ++j) acc[i][j] = 0.f;
 
     if (p_begin < p_end) fetch(p_begin);
     for (long long pb = p_begin; pb < p_end; pb += WG_TK) {
 #pragma unroll
-        for (int i = 0; i < A_PER; ++i) As[krow][ma + i] = ra[i];
-        *reinterpret_cast<float4*>(&Bs[krow][nb]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+        for (int i = 0; i < SA; ++i) As[krow][ma + i] = ra[i];
+#pragma unroll
+        for (int q = 0; q < SB / 4; ++q)
+            *reinterpret_cast<float4*>(&Bs[krow][64 * q + 4 * (tid & 15)]) = make_float4(rb[4 * q], rb[4 * q + 1], rb[4 * q + 2], rb[4 * q + 3]);
         __syncthreads();
         if (pb + WG_TK < p_end) fetch(pb + WG_TK);
 #pragma unroll
         for (int k = 0; k < WG_TK; ++k) {
             float av[MI];
 #pragma unroll
-            for (int i = 0; i < MI; ++i) av[i] = As[k][tm * MI + i];
-            const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tn * 4]);
+            for (int i = 0; i < MI; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(&As[k][tm * MI + i]);
+                av[i] = v.x; av[i + 1] = v.y; av[i + 2] = v.z; av[i + 3] = v.w;
+            }
 #pragma unroll
-            for (int i = 0; i < MI; ++i) {
-                acc[i][0] = fmaf(av[i], bv.x, acc[i][0]);
-                acc[i][1] = fmaf(av[i], bv.y, acc[i][1]);
-                acc[i][2] = fmaf(av[i], bv.z, acc[i][2]);
-                acc[i][3] = fmaf(av[i], bv.w, acc[i][3]);
+            for (int q = 0; q < NQ; ++q) {
+                const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][(TN / NQ) * q + 4 * tn]);
+#pragma unroll
+                for (int i = 0; i < MI; ++i) {
+                    acc[i][4 * q + 0] = fmaf(av[i], bv.x, acc[i][4 * q + 0]);
+                    acc[i][4 * q + 1] = fmaf(av[i], bv.y, acc[i][4 * q + 1]);
+                    acc[i][4 * q + 2] = fmaf(av[i], bv.z, acc[i][4 * q + 2]);
+                    acc[i][4 * q + 3] = fmaf(av[i], bv.w, acc[i][4 * q + 3]);
+                }
             }
         }
         __syncthreads();
@@ -249,8 +318,8 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgradArgs a) {
         const int m = m0 + tm * MI + i;
         if (m >= a.Cout) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tn * 4 + j;
+        for (int j = 0; j < NB; ++j) {
+            const int n = n0 + (TN / NQ) * (j >> 2) + 4 * tn + (j & 3);
             if (n < a.Ntot) out[(size_t)m * a.Ntot + n] = acc[i][j];
         }
     }
@@ -259,15 +328,14 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgradArgs a) {
 static int wgrad_tile_m(int Cout) { return Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128); }
 
 static int wgrad_splits(int Cout, int Ntot, long long npix) {
-    const int tm = wgrad_tile_m(Cout);
-    const long long tiles = (long long)ceil_div(Ntot, WG_TN) * ceil_div(Cout, tm);
+    const long long tiles = (long long)ceil_div(Ntot, WG_TN) * ceil_div(Cout, wgrad_tile_m(Cout));
     const long long want = 4LL * std::max(sm_count(), 1);                 // ~4 CTAs per SM in flight
     long long S = std::max(1LL, (want + tiles - 1) / tiles);
     const long long max_s = std::max(1LL, npix / (8 * WG_TK));            // at least 8 chunks per split
     return (int)std::min(S, max_s);
 }
 
-static int grad_act_blocks(long long npix) { return (int)std::min<long long>(std::max<long long>(npix / 512, 1), 1184); }
+static int grad_act_blocks(int rows) { return std::min(rows, 8 * std::max(sm_count(), 1)); }
 
 }  // namespace fvfi
 
@@ -276,8 +344,8 @@ using namespace fvfi;
 extern "C" {
 
 size_t fvfi_conv2d_grad_act_workspace_floats(int B, int H, int W, int C, int border) {
-    const long long npix = (long long)B * (H + 2 * border) * (W + 2 * border);
-    return (size_t)grad_act_blocks(npix) * (size_t)C;
+    (void)W;
+    return (size_t)grad_act_blocks(B * (H + 2 * border)) * (size_t)C;
 }
 
 int fvfi_conv2d_grad_act(const float* gy, int gy_pixel_stride, const float* y, int y_pixel_stride, float* g_canvas, int B, int H,
@@ -287,19 +355,25 @@ int fvfi_conv2d_grad_act(const float* gy, int gy_pixel_stride, const float* y, i
                    "fvfi_conv2d_grad_act: activation %d needs the saved output y (0 none, 1 ReLU, 2 ELU, 3 tanh, 4 sigmoid)", activation);
     FVFI_CHECK_ARG(gy_pixel_stride >= C && (y == nullptr || y_pixel_stride >= C), "fvfi_conv2d_grad_act: pixel stride < C");
     FVFI_CHECK_ARG(gbias == nullptr || workspace != nullptr, "fvfi_conv2d_grad_act: the bias gradient needs the workspace");
-    int CX = 32;
-    while (CX * GA_MAX_CPT < C && CX < GA_THREADS) CX *= 2;
-    FVFI_CHECK_ARG(CX * GA_MAX_CPT >= C, "fvfi_conv2d_grad_act: C = %d > %d", C, GA_THREADS * GA_MAX_CPT);
+    const bool vec = C % 4 == 0 && gy_pixel_stride % 4 == 0 && (y == nullptr || y_pixel_stride % 4 == 0) &&
+                     (((size_t)gy | (size_t)g_canvas | (size_t)y) & 15) == 0;
+    const int items = vec ? C / 4 : C;
+    int CX = 8;
+    while (CX < items && CX < GA_THREADS) CX *= 2;
+    FVFI_CHECK_ARG(CX * GA_MAX_CPT >= items, "fvfi_conv2d_grad_act: C = %d too large", C);
     const int PY = GA_THREADS / CX;
-    const long long npix = (long long)B * (H + 2 * border) * (W + 2 * border);
-    const int blocks = grad_act_blocks(npix);
-    const long long per = (npix + blocks - 1) / blocks;
+    const int blocks = grad_act_blocks(B * (H + 2 * border));
     cudaStream_t st = (cudaStream_t)stream;
-    grad_act_kernel<<<blocks, dim3(CX, PY), gbias ? (size_t)PY * C * sizeof(float) : 0, st>>>(
-        gy, gy_pixel_stride, y, y_pixel_stride, g_canvas, B, H, W, C, border, activation, gbias ? workspace : nullptr, per);
+    const size_t smem = gbias ? (size_t)PY * C * sizeof(float) : 0;
+    if (vec)
+        grad_act_kernel<true><<<blocks, dim3(CX, PY), smem, st>>>(gy, gy_pixel_stride, y, y_pixel_stride, g_canvas, B, H, W, C, border,
+                                                                 activation, gbias ? workspace : nullptr);
+    else
+        grad_act_kernel<false><<<blocks, dim3(CX, PY), smem, st>>>(gy, gy_pixel_stride, y, y_pixel_stride, g_canvas, B, H, W, C, border,
+                                                                  activation, gbias ? workspace : nullptr);
     FVFI_LAUNCH_CHECK();
     if (gbias) {
-        sum_partials_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, blocks, (size_t)C, gbias, 0, 0);
+        sum_partials_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, blocks, (size_t)C, gbias, 0, 0, 0);
         FVFI_LAUNCH_CHECK();
     }
     return FVFI_OK;
@@ -317,8 +391,10 @@ int fvfi_reflect_pad_backward_nhwc(const float* gxp, int gxp_pixel_stride, float
 }
 
 size_t fvfi_conv2d_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout, int K) {
-    const int Ntot = K * K * Cin;
-    return (size_t)wgrad_splits(Cout, Ntot, (long long)B * H * W) * (size_t)Cout * (size_t)Ntot;
+    // columns per tap: Cin, or Cin rounded up to 4 when the call finds x readable as float4 -- cover both
+    const long long npix = (long long)B * H * W;
+    const int n1 = K * K * Cin, n2 = K * K * ((Cin + 3) / 4 * 4);
+    return std::max((size_t)wgrad_splits(Cout, n1, npix) * (size_t)n1, (size_t)wgrad_splits(Cout, n2, npix) * (size_t)n2) * (size_t)Cout;
 }
 
 int fvfi_conv2d_wgrad_nhwc(const float* x, int x_pixel_stride, const float* g, int g_pixel_stride, long long g_row_pixels,
@@ -333,21 +409,24 @@ int fvfi_conv2d_wgrad_nhwc(const float* x, int x_pixel_stride, const float* g, i
     a.x = x; a.g = g; a.part = workspace;
     a.x_ps = x_pixel_stride; a.g_ps = g_pixel_stride; a.g_row = g_row_pixels; a.g_img = g_image_pixels;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.K = K; a.P = K / 2; a.reflect = pad_mode;
-    a.Ntot = K * K * Cin;
+    a.x_vec = (x_pixel_stride % 4 == 0 && x_pixel_stride >= (Cin + 3) / 4 * 4 && ((size_t)x & 15) == 0) ? 1 : 0;
+    a.CinP = a.x_vec ? (Cin + 3) / 4 * 4 : Cin;
+    a.Ntot = K * K * a.CinP;
     a.npix = (long long)B * H * W;
     const int S = wgrad_splits(Cout, a.Ntot, a.npix);
     long long per = (a.npix + S - 1) / S;
     per = (per + WG_TK - 1) / WG_TK * WG_TK;
     a.px_per_split = per;
+    a.g_vec = (Cout % 4 == 0 && g_pixel_stride % 4 == 0 && ((size_t)g & 15) == 0) ? 1 : 0;
     const int tm = wgrad_tile_m(Cout);
     const dim3 grid(ceil_div(a.Ntot, WG_TN), ceil_div(Cout, tm), S);
     cudaStream_t st = (cudaStream_t)stream;
-    if (tm == 32) wgrad_kernel<2><<<grid, WG_THREADS, 0, st>>>(a);
-    else if (tm == 64) wgrad_kernel<4><<<grid, WG_THREADS, 0, st>>>(a);
-    else wgrad_kernel<8><<<grid, WG_THREADS, 0, st>>>(a);
+    if (tm == 32) wgrad_kernel<4, 4, 2><<<grid, WG_THREADS, 0, st>>>(a);
+    else if (tm == 64) wgrad_kernel<4, 8, 4><<<grid, WG_THREADS, 0, st>>>(a);
+    else wgrad_kernel<8, 8, 4><<<grid, WG_THREADS, 0, st>>>(a);
     FVFI_LAUNCH_CHECK();
     const size_t n = (size_t)Cout * a.Ntot;
-    sum_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, S, n, gw_oihw, Cin, K * K);
+    sum_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, S, n, gw_oihw, Cin, a.CinP, K * K);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }

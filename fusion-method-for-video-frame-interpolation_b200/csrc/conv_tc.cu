@@ -285,7 +285,18 @@ __device__ __forceinline__ int reflect101(int i, int n) {   // torch 'reflect': 
 __global__ void conv_weight_scale_kernel(const float* __restrict__ w, size_t count, float* __restrict__ hdr, int prec) {
     __shared__ float red[32];
     float m = 0.f;
-    for (size_t i = threadIdx.x; i < count; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+    if (prec == PREC_F16X3) {                           // 3xTF32 needs no scale (its header is constant)
+        size_t i = threadIdx.x;
+        float m1 = 0.f, m2 = 0.f, m3 = 0.f;             // four loads in flight per thread
+        for (; i + 3 * (size_t)blockDim.x < count; i += 4 * (size_t)blockDim.x) {
+            m = fmaxf(m, fabsf(__ldg(w + i)));
+            m1 = fmaxf(m1, fabsf(__ldg(w + i + blockDim.x)));
+            m2 = fmaxf(m2, fabsf(__ldg(w + i + 2 * (size_t)blockDim.x)));
+            m3 = fmaxf(m3, fabsf(__ldg(w + i + 3 * (size_t)blockDim.x)));
+        }
+        for (; i < count; i += blockDim.x) m = fmaxf(m, fabsf(__ldg(w + i)));
+        m = fmaxf(fmaxf(m, m1), fmaxf(m2, m3));
+    }
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
     __syncthreads();

@@ -72,6 +72,8 @@ class FusionNet(torch.nn.Module):
             raise NotImplementedError("fvfi FusionNet runs on CUDA tensors only (no CPU fallback)")
         grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.live_parameters()))
         skip = []
+        if grad and x.shape[1] % 4:        # zero channels up to a multiple of 4: the weight-gradient kernel then reads float4 pixel quads
+            x = nn.functional.pad(x, (0, 0, 0, 0, 0, 4 - x.shape[1] % 4))
         x = tc.to_nhwc(x)
         for layer in self.encoder_layers:
             x = tc.conv_module(layer, x, "relu")                          # fusion_net.py:52-56
