@@ -335,6 +335,114 @@ static int wgrad_splits(int Cout, int Ntot, long long npix) {
     return (int)std::min(S, max_s);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// the other differentiable steps of FusionNet's training forward (src/fusion_net/fusion_net.py:52-77)
+// ------------------------------------------------------------------------------------------------------------------
+// nn.MaxPool2d(2, 2) backward: the gradient of a window goes to its FIRST maximum in scan order (ATen's rule: `val > max`)
+__global__ void __launch_bounds__(256) max_pool2_bwd_kernel(const float* __restrict__ x, int x_ps, const float* __restrict__ gy, int gy_ps,
+                                                           float* __restrict__ gx, int gx_ps, int B, int Hi, int Wi, int C) {
+    const int Ho = Hi >> 1, Wo = Wi >> 1;
+    const size_t total = (size_t)B * Hi * Wi * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        size_t p = i / C;
+        const int w = (int)(p % Wi);
+        p /= Wi;
+        const int h = (int)(p % Hi), b = (int)(p / Hi);
+        float g = 0.f;
+        const int oy = h >> 1, ox = w >> 1;
+        if (oy < Ho && ox < Wo) {
+            const float* win = x + (((size_t)b * Hi + 2 * oy) * Wi + 2 * ox) * x_ps + c;
+            float m = __ldg(win);
+            int arg = 0;
+            const float v1 = __ldg(win + x_ps), v2 = __ldg(win + (size_t)Wi * x_ps), v3 = __ldg(win + (size_t)(Wi + 1) * x_ps);
+            if (v1 > m) { m = v1; arg = 1; }
+            if (v2 > m) { m = v2; arg = 2; }
+            if (v3 > m) { m = v3; arg = 3; }
+            if (arg == ((h & 1) << 1 | (w & 1))) g = __ldg(gy + (((size_t)b * Ho + oy) * Wo + ox) * gy_ps + c);
+        }
+        gx[(((size_t)b * Hi + h) * Wi + w) * gx_ps + c] = g;
+    }
+}
+
+// adjoint of fvfi_resize_bilinear_nhwc_fused for upsampling factors <= 3 per axis, in gather form: input pixel (i, j) collects
+// w_y(o, i) * w_x(p, j) * gy[o, p] over the outputs whose two source rows / columns include it (weights from the SAME
+// bilinear_src as the forward), times relu'(x) when the forward resampled max(x, 0).
+constexpr int RB_MAXC = 10;        // candidate outputs per axis: 2 * 3 + margins
+__device__ __forceinline__ int resize_adjoint_weights(int i, int n_in, int n_out, float scale, int align, int* o0, float* w) {
+    // outputs o with source coordinate in (i - 1, i + 1): o in [(i - 1) / scale - 1, (i + 1) / scale + 1]
+    const float inv = scale > 0.f ? 1.f / scale : 0.f;
+    int lo = max(0, (int)floorf(((float)i - 1.f) * inv) - 1);
+    int hi = min(n_out - 1, (int)ceilf(((float)i + 1.f) * inv) + 1);
+    if (scale == 0.f) { lo = 0; hi = n_out - 1; }
+    if (hi - lo + 1 > RB_MAXC) hi = lo + RB_MAXC - 1;
+    *o0 = lo;
+    const int n = hi - lo + 1;
+    for (int k = 0; k < RB_MAXC; ++k) {
+        float ww = 0.f;
+        if (k < n) {
+            int i0, i1;
+            float l;
+            bilinear_src(lo + k, scale, align, n_in, i0, i1, l);
+            if (i0 == i) ww += 1.f - l;
+            if (i1 == i) ww += l;
+        }
+        w[k] = ww;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(256) resize_bilinear_bwd_kernel(const float* __restrict__ gy, int gy_ps, const float* __restrict__ x,
+                                                                 int x_ps, float* __restrict__ gx, int gx_ps, int B, int Hi, int Wi, int Ho,
+                                                                 int Wo, int C, int align, float sy, float sx, int relu_input) {
+    // one thread per (input pixel, channel quad-or-single); the block's threads share nothing, the weights are per pixel
+    const int cq = (C + 3) / 4;
+    const size_t total = (size_t)B * Hi * Wi * cq;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(q % cq) * 4;
+        size_t p = q / cq;
+        const int j = (int)(p % Wi);
+        p /= Wi;
+        const int i = (int)(p % Hi), b = (int)(p / Hi);
+        float wy[RB_MAXC], wx[RB_MAXC];
+        int oy0, ox0;
+        const int ny = resize_adjoint_weights(i, Hi, Ho, sy, align, &oy0, wy);
+        const int nx = resize_adjoint_weights(j, Wi, Wo, sx, align, &ox0, wx);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int nc = min(4, C - c0);
+        for (int a = 0; a < ny; ++a) {
+            if (wy[a] == 0.f) continue;
+            const float* row = gy + (((size_t)b * Ho + oy0 + a) * Wo + ox0) * gy_ps + c0;
+            for (int e = 0; e < nx; ++e) {
+                const float w = wy[a] * wx[e];
+                if (w == 0.f) continue;
+                for (int c = 0; c < nc; ++c) acc[c] = fmaf(w, __ldg(row + (size_t)e * gy_ps + c), acc[c]);
+            }
+        }
+        const size_t pix = ((size_t)b * Hi + i) * Wi + j;
+        for (int c = 0; c < nc; ++c) {
+            float v = acc[c];
+            if (relu_input && !(__ldg(x + pix * x_ps + c0 + c) > 0.f)) v = 0.f;
+            gx[pix * gx_ps + c0 + c] = v;
+        }
+    }
+}
+
+// out = clamp(base + tanh(x), 0, 1) (fvfi_fusion_blend; fusion_net.py:67-77):  gx = gout * [0 < base + tanh x < 1] * (1 - tanh^2 x),
+// gbase (optional) = gout * [..]
+__global__ void __launch_bounds__(256) fusion_blend_bwd_kernel(const float* __restrict__ base, const float* __restrict__ x,
+                                                              const float* __restrict__ gout, float* __restrict__ gx,
+                                                              float* __restrict__ gbase, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float t = tanhf(__ldg(x + i));
+        const float o = __ldg(base + i) + t;
+        const float g = (o > 0.f && o < 1.f) ? __ldg(gout + i) : 0.f;
+        gx[i] = g * (1.f - t * t);
+        if (gbase) gbase[i] = g;
+    }
+}
+
+
 static int grad_act_blocks(int rows) { return std::min(rows, 8 * std::max(sm_count(), 1)); }
 
 }  // namespace fvfi
@@ -427,6 +535,41 @@ int fvfi_conv2d_wgrad_nhwc(const float* x, int x_pixel_stride, const float* g, i
     FVFI_LAUNCH_CHECK();
     const size_t n = (size_t)Cout * a.Ntot;
     sum_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, S, n, gw_oihw, Cin, a.CinP, K * K);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
+
+int fvfi_max_pool2_backward_nhwc(const float* x, int x_pixel_stride, const float* gy, int gy_pixel_stride, float* gx, int gx_pixel_stride,
+                                 int B, int Hi, int Wi, int C, void* stream) {
+    FVFI_CHECK_ARG(x && gy && gx && B > 0 && Hi > 1 && Wi > 1 && C > 0, "fvfi_max_pool2_backward_nhwc: bad arguments");
+    FVFI_CHECK_ARG(x_pixel_stride >= C && gy_pixel_stride >= C && gx_pixel_stride >= C, "fvfi_max_pool2_backward_nhwc: pixel stride < C");
+    const size_t total = (size_t)B * Hi * Wi * C;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
+    max_pool2_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_pixel_stride, gy, gy_pixel_stride, gx, gx_pixel_stride, B, Hi, Wi, C);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
+
+int fvfi_resize_bilinear_backward_nhwc(const float* gy, int gy_pixel_stride, const float* x, int x_pixel_stride, float* gx,
+                                       int gx_pixel_stride, int B, int Hi, int Wi, int Ho, int Wo, int C, int align_corners,
+                                       int relu_input, void* stream) {
+    FVFI_CHECK_ARG(gy && gx && B > 0 && Hi > 0 && Wi > 0 && C > 0, "fvfi_resize_bilinear_backward_nhwc: bad arguments");
+    FVFI_CHECK_ARG(Ho >= Hi && Wo >= Wi && Ho <= 3 * Hi && Wo <= 3 * Wi, "fvfi_resize_bilinear_backward_nhwc: upsampling by at most 3 per axis");
+    FVFI_CHECK_ARG(!relu_input || x != nullptr, "fvfi_resize_bilinear_backward_nhwc: relu_input needs the forward input x");
+    FVFI_CHECK_ARG(gy_pixel_stride >= C && gx_pixel_stride >= C && (!x || x_pixel_stride >= C), "fvfi_resize_bilinear_backward_nhwc: pixel stride < C");
+    const size_t total = (size_t)B * Hi * Wi * ((C + 3) / 4);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
+    resize_bilinear_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gy, gy_pixel_stride, x, x_pixel_stride, gx, gx_pixel_stride, B, Hi, Wi,
+                                                                        Ho, Wo, C, align_corners, bilinear_scale(Hi, Ho, align_corners),
+                                                                        bilinear_scale(Wi, Wo, align_corners), relu_input);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
+
+int fvfi_fusion_blend_backward(const float* base, const float* x, const float* gout, float* gx, float* gbase, size_t n, void* stream) {
+    FVFI_CHECK_ARG(base && x && gout && gx && n > 0, "fvfi_fusion_blend_backward: bad arguments");
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 16);
+    fusion_blend_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(base, x, gout, gx, gbase, n);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }

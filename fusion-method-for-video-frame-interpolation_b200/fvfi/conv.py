@@ -329,6 +329,9 @@ def resize_bilinear(x, size, align_corners, out=None, out_channel_offset=0, relu
     wider channels_last buffer; the result is written to channels [out_channel_offset, out_channel_offset + C).
     ``relu_input``: interpolate max(x, 0); ``add`` ([B,C,Ho,Wo]): added to the result -- FusionNet's decoder step
     ``Upsample(ReLU(x)) + skip`` (fusion_net.py:60-62) as one pass."""
+    if torch.is_grad_enabled() and (x.requires_grad or (add is not None and add.requires_grad)):
+        assert out is None and out_channel_offset == 0, "resize_bilinear under autograd returns a fresh tensor"
+        return _ResizeFused.apply(x, add, (int(size[0]), int(size[1])), bool(align_corners), bool(relu_input))
     B, C, Hi, Wi = x.shape
     Ho, Wo = int(size[0]), int(size[1])
     xc = to_nhwc(x.float())
@@ -360,8 +363,60 @@ def put_planar(x, out, out_channel_offset):
 
 
 def max_pool2(x):
-    """nn.MaxPool2d(2, stride=2) on NHWC storage."""
+    """nn.MaxPool2d(2, stride=2) on NHWC storage (differentiable: fvfi_max_pool2_backward_nhwc)."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _MaxPool2.apply(x)
     return avg_pool2(x, _fn="fvfi_max_pool2_nhwc")
+
+
+class _MaxPool2(torch.autograd.Function):
+    """nn.MaxPool2d(2, 2) of FusionNet's encoder (fusion_net.py:39,56) for the training step."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = to_nhwc(x.detach().float())
+        ctx.save_for_backward(xc)
+        return avg_pool2(xc, _fn="fvfi_max_pool2_nhwc")
+
+    @staticmethod
+    def backward(ctx, gy):
+        (xc,) = ctx.saved_tensors
+        B, C, H, W = xc.shape
+        g = to_nhwc(gy.detach().float())
+        gx = torch.empty((B, C, H, W), dtype=torch.float32, device=xc.device, memory_format=torch.channels_last)
+        with torch.cuda.device(xc.device):
+            _lib.check(_lib.lib().fvfi_max_pool2_backward_nhwc(xc.data_ptr(), xc.stride(3), g.data_ptr(), g.stride(3), gx.data_ptr(),
+                                                               gx.stride(3), B, H, W, C, _lib.stream_ptr()))
+        return gx
+
+
+class _ResizeFused(torch.autograd.Function):
+    """y = resize(relu_input ? max(x, 0) : x) + add  (FusionNet's decoder step, fusion_net.py:60-62) for the training step:
+    forward fvfi_resize_bilinear_nhwc_fused, backward fvfi_resize_bilinear_backward_nhwc (the addend receives gy itself)."""
+
+    @staticmethod
+    def forward(ctx, x, add, size, align_corners, relu_input):
+        xc = to_nhwc(x.detach().float())
+        with torch.no_grad():
+            y = resize_bilinear(xc, size, align_corners, relu_input=relu_input, add=None if add is None else add.detach())
+        ctx.save_for_backward(xc)
+        ctx.cfg = (size, align_corners, relu_input, add is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (xc,) = ctx.saved_tensors
+        (Ho, Wo), align, relu_in, has_add = ctx.cfg
+        B, C, Hi, Wi = xc.shape
+        g = to_nhwc(gy.detach().float())
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty((B, C, Hi, Wi), dtype=torch.float32, device=xc.device, memory_format=torch.channels_last)
+            with torch.cuda.device(xc.device):
+                _lib.check(_lib.lib().fvfi_resize_bilinear_backward_nhwc(g.data_ptr(), g.stride(3), xc.data_ptr(), xc.stride(3),
+                                                                         gx.data_ptr(), gx.stride(3), B, Hi, Wi, Ho, Wo, C,
+                                                                         1 if align else 0, 1 if relu_in else 0, _lib.stream_ptr()))
+        return gx, (gy if (has_add and ctx.needs_input_grad[1]) else None), None, None, None
 
 
 def avg_pool2(x, _fn="fvfi_avg_pool2_nhwc"):

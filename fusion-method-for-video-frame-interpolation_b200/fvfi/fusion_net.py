@@ -3,8 +3,8 @@
 Same constructor, parameter names (``net.*`` dead weights kept for state-dict compatibility,
 ``encoder_layers.*``, ``bottleneck_layer.*``, ``decoder_layers.*``) and ``forward(base, adacof, phase,
 other, maps, save=False, variant=0)``.  The final ``tanh -> base + res -> clamp(0,1)``
-(fusion_net.py:67-77) is one fused CUDA kernel (fvfi_fusion_blend) in inference; under autograd
-the torch expression is used so gradients flow (training step).
+(fusion_net.py:67-77) is one fused CUDA kernel (fvfi_fusion_blend), differentiable through
+fvfi_fusion_blend_backward (training step).
 """
 import torch
 import torch.nn as nn
@@ -14,7 +14,9 @@ from . import conv as tc
 
 
 def fusion_blend(base, x):
-    """clamp(base + tanh(x), 0, 1) -- fusion_net.py:67-77."""
+    """clamp(base + tanh(x), 0, 1) -- fusion_net.py:67-77 (differentiable: fvfi_fusion_blend_backward)."""
+    if torch.is_grad_enabled() and (x.requires_grad or base.requires_grad):
+        return _FusionBlend.apply(base, x)
     base = base.contiguous()
     x = x.contiguous()
     out = torch.empty_like(base)
@@ -22,6 +24,26 @@ def fusion_blend(base, x):
         _lib.check(_lib.lib().fvfi_fusion_blend(base.data_ptr(), x.data_ptr(), out.data_ptr(), base.numel(),
                                                 _lib.stream_ptr()))
     return out
+
+
+class _FusionBlend(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, base, x):
+        base, x = base.detach().contiguous().float(), x.detach().contiguous().float()
+        ctx.save_for_backward(base, x)
+        with torch.no_grad():
+            return fusion_blend(base, x)
+
+    @staticmethod
+    def backward(ctx, gout):
+        base, x = ctx.saved_tensors
+        g = gout.detach().contiguous().float()
+        gx = torch.empty_like(x)
+        gbase = torch.empty_like(base) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().fvfi_fusion_blend_backward(base.data_ptr(), x.data_ptr(), g.data_ptr(), gx.data_ptr(),
+                                                             _lib.ptr(gbase), x.numel(), _lib.stream_ptr()))
+        return gbase, gx
 
 
 class FusionNet(torch.nn.Module):
@@ -64,9 +86,10 @@ class FusionNet(torch.nn.Module):
 
     @tc.range_checked
     def forward(self, base, adacof, phase, other, maps, save=False, variant=0):
-        """fusion_net.py:46-77.  Every convolution (+ its ReLU) is one tcgen05 kernel -- in inference AND under autograd (training:
-        ``conv.conv2d`` saves the activations and differentiates through its autograd Function); pooling, upsampling and the skip
-        additions are the fused NHWC kernels in inference and the differentiable torch operators under autograd."""
+        """fusion_net.py:46-77.  ONE path for inference and training: every convolution (+ its ReLU) is one tcgen05 kernel, pooling,
+        ``Upsample(ReLU(x)) + skip`` and the final ``clamp(base + tanh)`` are the fused NHWC kernels; under autograd each of them is
+        an autograd Function whose backward is a libfvfi kernel too (csrc/conv_bwd.cu) -- no ATen convolution / pooling /
+        interpolation kernel runs in the training step of the trained network."""
         x = torch.cat([base, adacof, phase, other, maps], 1)
         if not x.is_cuda:
             raise NotImplementedError("fvfi FusionNet runs on CUDA tensors only (no CPU fallback)")
@@ -78,21 +101,14 @@ class FusionNet(torch.nn.Module):
         for layer in self.encoder_layers:
             x = tc.conv_module(layer, x, "relu")                          # fusion_net.py:52-56
             skip.append(x)
-            x = nn.functional.max_pool2d(x, 2, 2) if grad else tc.max_pool2(x)
+            x = tc.max_pool2(x)
         x = tc.conv_module(self.bottleneck_layer, x, "relu")              # the ReLU of the first decoder step folded in (:58-61)
         for i, (layer, s) in enumerate(zip(self.decoder_layers, skip[::-1])):
-            if grad:                                                       # Upsample(ReLU(x)) + skip, differentiable form
-                x = nn.functional.interpolate(x if i == 0 else torch.relu(x), scale_factor=2, mode='bilinear') + s
-            else:                                                          # ... as one pass (fvfi_resize_bilinear_nhwc_fused)
-                x = tc.resize_bilinear(x, (x.shape[2] * 2, x.shape[3] * 2), False, relu_input=i > 0, add=s)
+            # Upsample(ReLU(x)) + skip as one pass (fvfi_resize_bilinear_nhwc_fused)
+            x = tc.resize_bilinear(x, (x.shape[2] * 2, x.shape[3] * 2), False, relu_input=i > 0, add=s)
             x = tc.conv_module(layer, x, None)
         x = x.contiguous()
         anchor = phase if variant == 1 else base
-        if grad:
-            res = self.tanh(x)
-            if save:
-                self.residuals.append(torch.sum(res).cpu().detach().item())
-            return (anchor + res).clamp(0, 1)
         if save:
-            self.residuals.append(torch.sum(torch.tanh(x)).cpu().item())
+            self.residuals.append(torch.sum(torch.tanh(x.detach())).cpu().item())
         return fusion_blend(anchor, x)

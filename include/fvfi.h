@@ -177,6 +177,22 @@ int fvfi_conv2d_wgrad_nhwc(const float* x, int x_pixel_stride, const float* g, i
                            long long g_image_pixels, float* gw_oihw, int B, int H, int W, int Cin, int Cout, int K, int pad_mode,
                            float* workspace, void* stream);
 
+/* The other differentiable steps of FusionNet's training forward (src/fusion_net/fusion_net.py:52-77; the reference differentiates
+ * nn.MaxPool2d, nn.Upsample and tanh / clamp through torch autograd):
+ *   fvfi_max_pool2_backward_nhwc: gx [B,Hi,Wi,C] from gy [B,Hi/2,Wi/2,C] and the forward input x; the gradient of a window goes to its
+ *     first maximum in scan order (ATen's rule); an odd last row / column gets zero.
+ *   fvfi_resize_bilinear_backward_nhwc: adjoint of fvfi_resize_bilinear_nhwc_fused (upsampling by at most 3 per axis): gx [B,Hi,Wi,C]
+ *     from gy [B,Ho,Wo,C]; relu_input: the forward resampled max(x, 0), so gx is zero where x <= 0 (x = the forward input).  The
+ *     addend of the fused forward receives gy unchanged.
+ *   fvfi_fusion_blend_backward: out = clamp(base + tanh(x), 0, 1) -> gx = gout * [0 < out < 1] * (1 - tanh(x)^2), gbase (or NULL) =
+ *     gout * [0 < out < 1]; n elements. */
+int fvfi_max_pool2_backward_nhwc(const float* x, int x_pixel_stride, const float* gy, int gy_pixel_stride, float* gx, int gx_pixel_stride,
+                                 int B, int Hi, int Wi, int C, void* stream);
+int fvfi_resize_bilinear_backward_nhwc(const float* gy, int gy_pixel_stride, const float* x, int x_pixel_stride, float* gx,
+                                       int gx_pixel_stride, int B, int Hi, int Wi, int Ho, int Wo, int C, int align_corners,
+                                       int relu_input, void* stream);
+int fvfi_fusion_blend_backward(const float* base, const float* x, const float* gout, float* gx, float* gbase, size_t n, void* stream);
+
 /* Direct (CUDA-core, fp32 FFMA) 1x1 convolution for Cout <= 8 -- the layers that are a pure stream of the activation:
  * PhaseNet's per-level prediction Conv2d(64, 8, 1) + tanh (src/phase_net/phase_net.py:197-200) and FusionNet's last
  * Conv2d(32, 3, 1) (src/fusion_net/fusion_net.py:36).  x [npix, x_pixel_stride] NHWC pixels (32-byte aligned, Cin a multiple

@@ -392,3 +392,60 @@ def test_conv_backward_is_reproducible_and_handles_padded_input_channels():
     F.relu(F.conv2d(F.pad(xd, (2, 2, 2, 2), mode="reflect"), wd, bd)).backward(gy.double())
     assert float((outs[0][0][:, :18].double() - xd.grad).abs().max()) <= 2e-5 * float(xd.grad.abs().max())
     assert float((outs[0][1].double() - wd.grad).abs().max()) <= 2e-5 * float(wd.grad.abs().max())
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 16, 24), (1, 3, 9, 7), (1, 64, 8, 8)])
+def test_max_pool2_backward_matches_torch(B, C, H, W):
+    """fvfi_max_pool2_backward_nhwc vs torch autograd of F.max_pool2d (incl. ties after a ReLU and odd sizes)."""
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.relu(torch.randn((B, C, H, W), device="cuda", generator=g))        # ~half zeros: tied windows
+    gy = torch.randn((B, C, H // 2, W // 2), device="cuda", generator=g)
+    xa = x.clone().requires_grad_(True)
+    with torch.enable_grad():
+        ya = conv.max_pool2(xa)
+    ya.backward(gy)
+    xb = x.clone().requires_grad_(True)
+    yb = F.max_pool2d(xb, 2, 2)
+    yb.backward(gy)
+    assert torch.equal(ya.detach(), yb.detach())
+    assert torch.equal(xa.grad, xb.grad)
+
+
+@pytest.mark.parametrize("B,C,Hi,Wi,Ho,Wo,align,relu_in", [
+    (2, 32, 8, 12, 16, 24, False, True), (1, 128, 4, 4, 8, 8, False, False), (1, 5, 7, 9, 14, 18, True, False),
+    (1, 8, 5, 6, 13, 17, False, True), (1, 4, 6, 6, 6, 6, False, False)])
+def test_resize_bilinear_backward_matches_torch(B, C, Hi, Wi, Ho, Wo, align, relu_in):
+    """fvfi_resize_bilinear_backward_nhwc (adjoint of the fused resize: ReLU on the input, skip added on the way out) vs torch autograd."""
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn((B, C, Hi, Wi), device="cuda", generator=g)
+    add = torch.randn((B, C, Ho, Wo), device="cuda", generator=g)
+    gy = torch.randn((B, C, Ho, Wo), device="cuda", generator=g)
+    xa, aa = x.clone().requires_grad_(True), add.clone().requires_grad_(True)
+    with torch.enable_grad():
+        ya = conv.resize_bilinear(xa, (Ho, Wo), align, relu_input=relu_in, add=aa)
+    ya.backward(gy)
+    xb, ab = x.double().requires_grad_(True), add.double().requires_grad_(True)
+    yb = F.interpolate(torch.relu(xb) if relu_in else xb, size=(Ho, Wo), mode="bilinear", align_corners=align) + ab
+    yb.backward(gy.double())
+    assert float((ya.detach().double() - yb.detach()).abs().max()) <= 1e-5
+    assert float((xa.grad.double() - xb.grad).abs().max()) <= 1e-5 * max(1.0, float(xb.grad.abs().max()))
+    assert torch.equal(aa.grad, gy)
+
+
+def test_fusion_blend_backward_matches_torch():
+    from fvfi.fusion_net import fusion_blend
+    g = torch.Generator(device="cuda").manual_seed(5)
+    base = torch.rand((2, 3, 20, 28), device="cuda", generator=g)
+    x = torch.randn((2, 3, 20, 28), device="cuda", generator=g)
+    gout = torch.randn((2, 3, 20, 28), device="cuda", generator=g)
+    ba, xa = base.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    with torch.enable_grad():
+        oa = fusion_blend(ba, xa)
+    oa.backward(gout)
+    bb, xb = base.double().requires_grad_(True), x.double().requires_grad_(True)
+    ob = (bb + torch.tanh(xb)).clamp(0, 1)
+    ob.backward(gout.double())
+    assert float((oa.detach().double() - ob.detach()).abs().max()) <= 2e-6
+    assert float((xa.grad.double() - xb.grad).abs().max()) <= 1e-5 and float((ba.grad.double() - bb.grad).abs().max()) <= 1e-6

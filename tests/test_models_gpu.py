@@ -260,7 +260,13 @@ def test_training_step_gradients_match_oracle():
     assert _lib.lib().fvfi_launch_count() - n0 >= 7, "the training forward must run its 7 convolutions on the tcgen05 kernel"
     assert pred.requires_grad
     lg = torch.nn.functional.l1_loss(target.cuda(), torch.clip(pred, 0, 1))
-    lg.backward()
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        lg.backward()
+        torch.cuda.synchronize()
+    foreign = [e.key for e in prof.key_averages()
+               if any(k in e.key.lower() for k in ("cudnn", "convolution", "gemm", "max_pool", "upsample", "wgrad", "dgrad"))
+               and "fvfi::" not in e.key]
+    assert not foreign, "the backward of the trained network must run on libfvfi kernels: %s" % foreign
     assert abs(float(lo.detach()) - float(lg.detach())) <= 1e-6
     og = dict(ofn.named_parameters())
     for n, p in gfn.named_parameters():
