@@ -44,6 +44,14 @@ class PhaseNetBlock(nn.Module):
             f = tc.conv_module(self.feature_map[3], f, "elu")
             c = tc.conv_module(self.prediction_map[0], f, "tanh")
             return f, c
+        if x.is_cuda:
+            # training / autograd: the three convolutions -- forward AND backward -- on libfvfi (conv._ConvTC: tcgen05 forward and
+            # data gradient, csrc/conv_bwd.cu weight / bias gradients); BatchNorm (batch statistics in train mode) stays torch's
+            fm = self.feature_map
+            f = fm[2](fm[1](tc.conv_module(fm[0], x, None)))
+            f = tc.conv_module(fm[3], f, "elu")
+            c = tc.conv_module(self.prediction_map[0], f, "tanh")
+            return f, c
         f = self.feature_map(x)
         c = self.prediction_map(f)
         return f, c

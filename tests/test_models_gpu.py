@@ -443,3 +443,33 @@ def test_level0_difference_reconstruction_is_linear():
     assert d.shape == ref.shape
     assert float((d - ref).abs().max()) <= 5e-6 * max(1.0, float(ref.abs().max()))
     assert float((d2 - d).abs().max()) <= 5e-6 * max(1.0, float(ref.abs().max()))
+
+
+def test_phasenet_block_training_gradients_match_torch():
+    """PhaseNetBlock in train mode (phase_net.py:179-207): convolutions forward + backward on libfvfi, BatchNorm with batch statistics;
+    outputs and every parameter gradient equal torch's eager fp64 evaluation of the same block."""
+    import copy
+    from fvfi.phase_net import PhaseNetBlock
+    torch.manual_seed(3)
+    for c_in, k in ((88, (3, 3)), (81, (1, 1)), (2, (1, 1))):
+        blk = PhaseNetBlock(c_in, 64, 8, k, torch.device("cuda"))
+        blk.train()
+        ref = copy.deepcopy(blk).double()
+        x = torch.randn((3, c_in, 24, 20), device="cuda")
+        gf, gc = torch.randn((3, 64, 24, 20), device="cuda"), torch.randn((3, 8, 24, 20), device="cuda")
+        from fvfi import _lib
+        n0 = _lib.lib().fvfi_launch_count()
+        f, c = blk(x)
+        assert _lib.lib().fvfi_launch_count() - n0 >= 3
+        (f * gf).sum().add((c * gc).sum()).backward()
+        fr = ref.feature_map(x.double())
+        cr = ref.prediction_map(fr)
+        (fr * gf.double()).sum().add((cr * gc.double()).sum()).backward()
+        assert float((f.detach().double() - fr.detach()).abs().max()) <= 2e-5 * float(fr.detach().abs().max())
+        assert float((c.detach().double() - cr.detach()).abs().max()) <= 2e-5
+        for (n, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
+            d = float((p.grad.double() - q.grad).abs().max())
+            # the bias in front of the BatchNorm has an exactly zero gradient (the batch mean is removed): fp32 leaves the rounding of
+            # a cancelling sum over 1440 pixels of O(10) terms there
+            tol = 1e-3 if n == "feature_map.0.bias" else 5e-5 * max(1.0, float(q.grad.abs().max()))
+            assert d <= tol, (c_in, n, d, float(q.grad.abs().max()))
