@@ -479,6 +479,9 @@ def multi_gpu_records(device, rank, world, local_rank):
                         "step_ms_by_launch_mode": {k: round(v, 3) for k, v in step_ms_mode.items()},
                         "allreduce_ms": round(ar_ms, 4), "allreduce_floats": int(tr.bucket.flat.numel()),
                         "collective": "one flat fp32 bucket, NCCL all-reduce (sum) + divide",
+                        "backward": "libfvfi kernels: data gradient = the tcgen05 convolution over a zero canvas with the flipped filter "
+                                    "(3xTF32), weight / bias gradients fp32 split over pixel ranges with a fixed summation order "
+                                    "(csrc/conv_bwd.cu); no ATen / cuDNN convolution, pooling or interpolation kernel in the step",
                         "grad_max_abs_diff_vs_single_process": grad_err, "grad_max_abs": grad_ref,
                         "loss_distributed": loss_dist, "loss_single_process": loss_single,
                         "weights": "rank r initialised with seed r, rank 0's broadcast by the trainer"}
