@@ -96,8 +96,13 @@ class PipelineWorkload:
         ms = sum(r[1].elapsed_time(r[2]) for r in rec)
         # per shape class: algorithmic FLOP/s and the algorithmic DRAM bytes (activation in + out, fp32) each launch must move
         classes = {}
-        for fl, e0, e1, nl, (B, Cin, Cout, K, H, W, act) in rec:
-            key = "%d->%d k%d @%dx%d%s" % (Cin, Cout, K, H, W, "" if act is None else " " + act)
+        fused = {"launches": 0, "ms": 0.0, "flops": 0.0}
+        for fl, e0, e1, nl, (B, Cin, Cout, K, H, W, act), up in rec:
+            key = "%d->%d k%d @%dx%d%s%s" % (Cin, Cout, K, H, W, "" if act is None else " " + act, " [resampling in the loader]" if up else "")
+            if up:
+                fused["launches"] += nl
+                fused["ms"] += e0.elapsed_time(e1)
+                fused["flops"] += fl
             c = classes.setdefault(key, [0, 0.0, 0.0, 0.0])
             c[0] += nl
             c[1] += fl
@@ -106,6 +111,7 @@ class PipelineWorkload:
         top = sorted(classes.items(), key=lambda kv: -kv[1][2])[:12]
         table = [{"layer": k, "launches": v[0], "ms": round(v[2], 3), "tflops": round(v[1] / v[2] / 1e9, 1),
                   "algorithmic_dram_gb": round(v[3] / 1e9, 3), "dram_gbs_at_this_time": round(v[3] / v[2] / 1e6, 1)} for k, v in top]
+        self._fused_up = fused
         return flops, ms, sum(r[3] for r in rec), table
 
     def _time_hbm_kernels(self, peak):
@@ -198,6 +204,14 @@ class PipelineWorkload:
                 # `by_layer_class` lists, per shape class of this step, time, algorithmic TFLOP/s and the ALGORITHMIC DRAM bytes
                 # (fp32 activations in + out); measured DRAM bytes of representative launches: profiles/ (ncu --set full)
                 "by_layer_class": table,
+                # round 2 moved the bilinear resampling in front of KernelEstimation's Upsample blocks / head tails and PhaseNet's
+                # level inputs INTO the loaders of these launches (the stand-alone resize kernels they replace were ~45 ms per step
+                # outside this kernel in round 1): their time is convolution + resampling, their FLOP count is the convolution's alone
+                "launches_with_resampling_loader": {"launches": self._fused_up["launches"], "ms": round(self._fused_up["ms"], 2),
+                                                    "tflops": round(self._fused_up["flops"] / max(self._fused_up["ms"], 1e-9) / 1e9, 1)},
+                "plain_launches": {"launches": launches - self._fused_up["launches"], "ms": round(ms - self._fused_up["ms"], 2),
+                                   "tflops": round((flops - self._fused_up["flops"]) / max(ms - self._fused_up["ms"], 1e-9) / 1e9, 1),
+                                   "frac": round((flops - self._fused_up["flops"]) / max(ms - self._fused_up["ms"], 1e-9) / 1e9 / tpeak, 4)},
                 "ms_per_step_in_kernel": round(ms, 2), "share_of_step": round(ms / max(step_ms, 1e-9), 3),
                 "algorithmic_flops_per_step": flops,
                 "other_kernels": self._time_hbm_kernels(peak), "hbm_peak": peak, "hbm_peak_source": peak_src,

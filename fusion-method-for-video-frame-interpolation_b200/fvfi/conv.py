@@ -281,7 +281,7 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
                                                     1 if nchw_out else (2 if pad_out else 0), precision, _lib.stream_ptr()))
         if timing is not None:
             e1.record()
-            timing.append((2.0 * B * H * W * Cin * Cout * KH * KW, e0, e1, len(parts), (B, Cin, Cout, KH, H, W, act)))
+            timing.append((2.0 * B * H * W * Cin * Cout * KH * KW, e0, e1, len(parts), (B, Cin, Cout, KH, H, W, act), upsample is not None))
     return out
 
 

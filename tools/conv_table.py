@@ -19,8 +19,8 @@ pipe(d1, d2)
 torch.cuda.synchronize()
 rec, tc.timing = tc.timing, None
 agg = collections.OrderedDict()
-for fl, e0, e1, parts, shape in rec:
-    a = agg.setdefault(shape, [0, 0.0, 0.0])
+for fl, e0, e1, parts, shape, up in rec:
+    a = agg.setdefault(shape + (('up',) if up else ()), [0, 0.0, 0.0])
     a[0] += 1; a[1] += fl; a[2] += e0.elapsed_time(e1)
 tot = sum(a[2] for a in agg.values())
 print("total conv %.2f ms, %.1f TFLOP/s" % (tot, sum(a[1] for a in agg.values()) / tot / 1e9))
