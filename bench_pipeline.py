@@ -7,6 +7,7 @@
 Under torchrun (N > 1) the default line also carries a `train` record (configs[4]) and a `pipeline4k` record (configs[3]),
 measured outside the headline's timed region (multi_gpu_records).
 """
+import json
 import os
 import time
 
@@ -112,6 +113,7 @@ class PipelineWorkload:
         table = [{"layer": k, "launches": v[0], "ms": round(v[2], 3), "tflops": round(v[1] / v[2] / 1e9, 1),
                   "algorithmic_dram_gb": round(v[3] / 1e9, 3), "dram_gbs_at_this_time": round(v[3] / v[2] / 1e6, 1)} for k, v in top]
         self._fused_up = fused
+        self._alg_dram = sum(4.0 * B * H * W * (Cin + Cout) for _, _, _, _, (B, Cin, Cout, K, H, W, act), _ in rec)
         return flops, ms, sum(r[3] for r in rec), table
 
     def _time_hbm_kernels(self, peak):
@@ -186,6 +188,22 @@ class PipelineWorkload:
                         "algorithmic_bytes_per_call": pb})
         return out
 
+    def _ncu_traffic(self, launches):
+        """DRAM bytes per launch of the convolution kernel from the committed ncu capture of this step's launch sequence
+        (profiles/r02_conv_traffic.json, written by tools/ncu_conv_step.py; a profiler figure, not measured live), next to the
+        algorithmic bytes (fp32 activations in + out) of the launches timed here."""
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_conv_traffic.json")
+        self._traffic_detail = {"algorithmic_dram_bytes_per_step": self._alg_dram,
+                                "algorithmic_dram_bytes_per_launch": self._alg_dram / max(launches, 1)}
+        try:
+            t = json.load(open(path))
+        except Exception:
+            return None
+        self._traffic_detail.update({"measured_dram_bytes_per_step": t["dram_bytes_per_step"], "measured_launches_per_step": t["launches_per_step"],
+                                     "measured_over_algorithmic": round(t["dram_bytes_per_step"] / max(self._alg_dram, 1.0), 3),
+                                     "source": t["source"]})
+        return t["dram_bytes_per_launch"] if t["launches_per_step"] == launches else t["dram_bytes_per_step"] / max(launches, 1)
+
     def roofline(self, peak, peak_src):
         """Dominant kernel of the step = the tcgen05 convolution (tensor-bound).  `achieved` counts ALGORITHMIC FLOPs
         (one multiply-add per tap, channel pair and pixel); every one of them is executed as three fp16 tensor-core
@@ -199,7 +217,8 @@ class PipelineWorkload:
         step_ms = sum(stages.values())
         return {"bound": "tensor", "kernel": "conv_split_kernel<ACT, PREC_F16X3> (all %d launches of one step)" % launches,
                 "achieved": round(ach, 1), "peak": tpeak, "unit": "TFLOP/s", "frac": round(ach / tpeak, 4),
-                "mma_frac": round(3 * ach / tpeak, 4), "traffic": None, "peak_source": tsrc,
+                "mma_frac": round(3 * ach / tpeak, 4), "traffic": self._ncu_traffic(launches), "peak_source": tsrc,
+                "traffic_detail": self._traffic_detail,
                 # `achieved` aggregates several hundred launches of different shapes, so there is no single per-launch DRAM figure:
                 # `by_layer_class` lists, per shape class of this step, time, algorithmic TFLOP/s and the ALGORITHMIC DRAM bytes
                 # (fp32 activations in + out); measured DRAM bytes of representative launches: profiles/ (ncu --set full)

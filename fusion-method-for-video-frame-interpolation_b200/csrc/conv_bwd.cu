@@ -188,7 +188,7 @@ __device__ __forceinline__ int reflect_index(int i, int n) { return i < 0 ? -i :
 // (8 adjacent column quads = 128 B; 4 channel groups <= 128 B) for MI*NB FFMAs per thread: FFMA-bound, not shared-memory-bound.
 // Thread (tm, tn): channels tm*MI .. +MI, column quads 4*tn + (128/NQ)*q, q < NQ = NB/4.
 template <int MI, int NB, int WM>
-__global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgradArgs a) {
+__global__ void __launch_bounds__(WG_THREADS, (MI * NB <= 16 ? 4 : 2)) wgrad_kernel(const WgradArgs a) {
     constexpr int TM = 4 * WM * MI, WN = 8 / WM, TN = 8 * WN * NB, NQ = NB / 4, SB = TN / 16;
     static_assert(TN == WG_TN && TM * WG_TK / WG_THREADS >= 1, "tile shape");
     constexpr int SA = TM * WG_TK / WG_THREADS;          // A elements a thread stages per chunk
