@@ -3,6 +3,8 @@
 CPU restatement of ``skimage.color.rgb2lab`` / ``lab2rgb`` (the reference calls them in
 src/train/transform.py:6-49; scikit-image is not installed here and not vendored).  Published
 algorithm: sRGB companding (IEC 61966-2-1), linear RGB -> XYZ (D65, 2 degree observer), CIE 1976 L*a*b*.
+Coarse independent anchor: OpenCV's float RGB<->Lab (same standard, table-interpolated) agrees to <= 0.5 Lab units / 2e-3 RGB
+(tests/test_models_oracle.py::test_lab_oracle_agrees_with_opencv) -- it catches a wrong constant, it does not pin the last digits.
 """
 import numpy as np
 

@@ -123,3 +123,20 @@ def test_lab_round_trip_and_known_values():
     assert np.allclose(lab.rgb2lab(np.ones((1, 1, 3)))[0, 0], [100, 0, 0], atol=2e-2)
     assert np.allclose(lab.rgb2lab(np.zeros((1, 1, 3)))[0, 0], [0, 0, 0], atol=1e-9)
     assert abs(lab.rgb2lab(np.full((1, 1, 3), 0.5))[0, 0, 0] - 53.389) < 1e-2
+
+
+def test_lab_oracle_agrees_with_opencv():
+    """Coarse, independent anchor for the UNPINNED Lab oracle (scikit-image, what the reference calls in src/train/transform.py:6-49,
+    is not installed): OpenCV's float RGB<->Lab implements the same standard (sRGB companding, D65, CIE 1976) with table-interpolated
+    gamma / cube root, so it agrees only to a few tenths of a Lab unit -- enough to catch a wrong white point, matrix or threshold
+    (each of which moves values by > 1 unit), not enough to pin the last digits."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import lab
+    rng = np.random.default_rng(0)
+    rgb = rng.random((96, 80, 3)).astype(np.float32)
+    rgb[:8] *= 0.02                                        # the linear segment of the sRGB curve and of f(t)
+    ours = lab.rgb2lab(rgb)
+    theirs = cv2.cvtColor(rgb, cv2.COLOR_RGB2Lab).astype(np.float64)
+    assert float(np.abs(ours - theirs).max()) <= 0.5, float(np.abs(ours - theirs).max())
+    back = cv2.cvtColor(theirs.astype(np.float32), cv2.COLOR_Lab2RGB).astype(np.float64)
+    assert float(np.abs(lab.lab2rgb(theirs) - back).max()) <= 2e-3
