@@ -365,6 +365,23 @@ __global__ void __launch_bounds__(256) max_pool2_bwd_kernel(const float* __restr
     }
 }
 
+// nn.AvgPool2d(2, 2) backward: every pixel of a window receives gy / 4; an odd last row / column gets zero
+__global__ void __launch_bounds__(256) avg_pool2_bwd_kernel(const float* __restrict__ gy, int gy_ps, float* __restrict__ gx, int gx_ps,
+                                                           int B, int Hi, int Wi, int C) {
+    const int Ho = Hi >> 1, Wo = Wi >> 1;
+    const size_t total = (size_t)B * Hi * Wi * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        size_t p = i / C;
+        const int w = (int)(p % Wi);
+        p /= Wi;
+        const int h = (int)(p % Hi), b = (int)(p / Hi);
+        const int oy = h >> 1, ox = w >> 1;
+        const float g = (oy < Ho && ox < Wo) ? 0.25f * __ldg(gy + (((size_t)b * Ho + oy) * Wo + ox) * gy_ps + c) : 0.f;
+        gx[(((size_t)b * Hi + h) * Wi + w) * gx_ps + c] = g;
+    }
+}
+
 // adjoint of fvfi_resize_bilinear_nhwc_fused for upsampling factors <= 3 per axis, in gather form: input pixel (i, j) collects
 // w_y(o, i) * w_x(p, j) * gy[o, p] over the outputs whose two source rows / columns include it (weights from the SAME
 // bilinear_src as the forward), times relu'(x) when the forward resampled max(x, 0).
@@ -546,6 +563,17 @@ int fvfi_max_pool2_backward_nhwc(const float* x, int x_pixel_stride, const float
     const size_t total = (size_t)B * Hi * Wi * C;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
     max_pool2_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_pixel_stride, gy, gy_pixel_stride, gx, gx_pixel_stride, B, Hi, Wi, C);
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
+
+int fvfi_avg_pool2_backward_nhwc(const float* gy, int gy_pixel_stride, float* gx, int gx_pixel_stride, int B, int Hi, int Wi, int C,
+                                 void* stream) {
+    FVFI_CHECK_ARG(gy && gx && B > 0 && Hi > 1 && Wi > 1 && C > 0, "fvfi_avg_pool2_backward_nhwc: bad arguments");
+    FVFI_CHECK_ARG(gy_pixel_stride >= C && gx_pixel_stride >= C, "fvfi_avg_pool2_backward_nhwc: pixel stride < C");
+    const size_t total = (size_t)B * Hi * Wi * C;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
+    avg_pool2_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gy, gy_pixel_stride, gx, gx_pixel_stride, B, Hi, Wi, C);
     FVFI_LAUNCH_CHECK();
     return FVFI_OK;
 }

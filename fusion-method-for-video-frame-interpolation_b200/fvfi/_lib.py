@@ -51,6 +51,7 @@ _PROTOS = {
     "fvfi_conv2d_wgrad_workspace_floats": (c_size, [c_int] * 6),
     "fvfi_conv2d_wgrad_nhwc": (c_int, [c_fp, c_int, c_fp, c_int, ctypes.c_longlong, ctypes.c_longlong, c_fp] + [c_int] * 7 + [c_fp, c_fp]),
     "fvfi_max_pool2_backward_nhwc": (c_int, [c_fp, c_int, c_fp, c_int, c_fp, c_int] + [c_int] * 4 + [c_fp]),
+    "fvfi_avg_pool2_backward_nhwc": (c_int, [c_fp, c_int, c_fp, c_int] + [c_int] * 4 + [c_fp]),
     "fvfi_resize_bilinear_backward_nhwc": (c_int, [c_fp, c_int, c_fp, c_int, c_fp, c_int] + [c_int] * 8 + [c_fp]),
     "fvfi_fusion_blend_backward": (c_int, [c_fp] * 5 + [c_size, c_fp]),
     "fvfi_nchw_to_nhwc_slice": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),

@@ -169,24 +169,54 @@ class KernelEstimation(torch.nn.Module):
             self._first_cache = hit
         return hit[1]
 
+    @staticmethod
+    def _seq_train(seq, x):
+        """The same nn.Sequential under autograd: every step is an autograd Function over libfvfi kernels (conv + activation:
+        conv._ConvTC, tcgen05 forward and data gradient, csrc/conv_bwd.cu weight / bias gradients; Upsample: conv._ResizeFused);
+        only the channel softmax is torch's."""
+        mods = list(seq)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, torch.nn.Conv2d):
+                nxt = mods[i + 1] if i + 1 < len(mods) else None
+                act = {torch.nn.ReLU: "relu", torch.nn.Sigmoid: "sigmoid"}.get(type(nxt))
+                x = tc.conv_module(m, x, act)
+                i += 2 if act else 1
+            elif isinstance(m, torch.nn.Upsample):
+                assert m.mode == 'bilinear' and m.scale_factor == 2
+                x = tc.resize_bilinear(x, (x.shape[2] * 2, x.shape[3] * 2), bool(m.align_corners))
+                i += 1
+            else:
+                x = m(x)
+                i += 1
+        return x
+
+    def _forward_train(self, rfield0, rfield2):
+        """fusion_adacofnet.py:109-155 with gradients: the differentiable counterpart of ``_forward_tc`` (no fused epilogues /
+        loaders, one libfvfi autograd Function per module)."""
+        x = tc.to_nhwc(torch.cat([rfield0, rfield2, rfield0.new_zeros((rfield0.shape[0], 2) + tuple(rfield0.shape[2:]))], 1))
+        run, pool = self._seq_train, tc.avg_pool2
+        c1 = run(self.moduleConv1, x)
+        c2 = run(self.moduleConv2, pool(c1))
+        c3 = run(self.moduleConv3, pool(c2))
+        c4 = run(self.moduleConv4, pool(c3))
+        c5 = run(self.moduleConv5, pool(c4))
+        d5 = run(self.moduleUpsample5, run(self.moduleDeconv5, pool(c5)))
+        d4 = run(self.moduleUpsample4, run(self.moduleDeconv4, d5 + c5))
+        d3 = run(self.moduleUpsample3, run(self.moduleDeconv3, d4 + c4))
+        d2 = run(self.moduleUpsample2, run(self.moduleDeconv2, d3 + c3))
+        comb = d2 + c2
+        return tuple(run(h, comb) for h in (self.moduleWeight1, self.moduleAlpha1, self.moduleBeta1, self.moduleWeight2,
+                                            self.moduleAlpha2, self.moduleBeta2, self.moduleOcclusion))
+
     @tc.range_checked
     def forward(self, rfield0, rfield2):
-        if tc.use_tc(rfield0) and not self.training:
-            return self._forward_tc(rfield0, rfield2)
-        x = torch.cat([rfield0, rfield2], 1)
-        c1 = self.moduleConv1(x)
-        c2 = self.moduleConv2(self.modulePool1(c1))
-        c3 = self.moduleConv3(self.modulePool2(c2))
-        c4 = self.moduleConv4(self.modulePool3(c3))
-        c5 = self.moduleConv5(self.modulePool4(c4))
-        d5 = self.moduleUpsample5(self.moduleDeconv5(self.modulePool5(c5)))
-        d4 = self.moduleUpsample4(self.moduleDeconv4(d5 + c5))
-        d3 = self.moduleUpsample3(self.moduleDeconv3(d4 + c4))
-        d2 = self.moduleUpsample2(self.moduleDeconv2(d3 + c3))
-        comb = d2 + c2
-        return (self.moduleWeight1(comb), self.moduleAlpha1(comb), self.moduleBeta1(comb),
-                self.moduleWeight2(comb), self.moduleAlpha2(comb), self.moduleBeta2(comb),
-                self.moduleOcclusion(comb))
+        if not rfield0.is_cuda:
+            raise NotImplementedError("fvfi KernelEstimation runs on CUDA tensors only (no CPU fallback)")
+        grad = torch.is_grad_enabled() and (rfield0.requires_grad or rfield2.requires_grad
+                                            or any(p.requires_grad for p in self.parameters()))
+        return self._forward_train(rfield0, rfield2) if grad else self._forward_tc(rfield0, rfield2)
 
 
 class AdaCoFNet(torch.nn.Module):

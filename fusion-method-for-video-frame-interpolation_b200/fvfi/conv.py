@@ -419,8 +419,30 @@ class _ResizeFused(torch.autograd.Function):
         return gx, (gy if (has_add and ctx.needs_input_grad[1]) else None), None, None, None
 
 
+class _AvgPool2(torch.autograd.Function):
+    """nn.AvgPool2d(2, 2) of KernelEstimation's encoder (fusion_adacofnet.py:62-70) under autograd."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        with torch.no_grad():
+            return avg_pool2(x.detach())
+
+    @staticmethod
+    def backward(ctx, gy):
+        B, C, H, W = ctx.shape
+        g = to_nhwc(gy.detach().float())
+        gx = torch.empty((B, C, H, W), dtype=torch.float32, device=g.device, memory_format=torch.channels_last)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().fvfi_avg_pool2_backward_nhwc(g.data_ptr(), g.stride(3), gx.data_ptr(), gx.stride(3), B, H, W, C,
+                                                               _lib.stream_ptr()))
+        return gx
+
+
 def avg_pool2(x, _fn="fvfi_avg_pool2_nhwc"):
-    """nn.AvgPool2d(kernel_size=2, stride=2) on NHWC storage."""
+    """nn.AvgPool2d(kernel_size=2, stride=2) on NHWC storage (differentiable: fvfi_avg_pool2_backward_nhwc)."""
+    if _fn == "fvfi_avg_pool2_nhwc" and torch.is_grad_enabled() and x.requires_grad:
+        return _AvgPool2.apply(x)
     B, C, H, W = x.shape
     xc = to_nhwc(x.float())
     out = torch.empty((B, C, H // 2, W // 2), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)

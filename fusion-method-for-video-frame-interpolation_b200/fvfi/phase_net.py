@@ -52,9 +52,7 @@ class PhaseNetBlock(nn.Module):
             f = tc.conv_module(fm[3], f, "elu")
             c = tc.conv_module(self.prediction_map[0], f, "tanh")
             return f, c
-        f = self.feature_map(x)
-        c = self.prediction_map(f)
-        return f, c
+        raise NotImplementedError("fvfi PhaseNetBlock runs on CUDA tensors only (no CPU fallback)")
 
     def forward_resampled(self, feature, direct, size):
         """``forward(cat(interpolate(feature, size), direct))`` without the concatenated tensor: the first convolution's loaders

@@ -188,6 +188,10 @@ int fvfi_conv2d_wgrad_nhwc(const float* x, int x_pixel_stride, const float* g, i
  *     gout * [0 < out < 1]; n elements. */
 int fvfi_max_pool2_backward_nhwc(const float* x, int x_pixel_stride, const float* gy, int gy_pixel_stride, float* gx, int gx_pixel_stride,
                                  int B, int Hi, int Wi, int C, void* stream);
+/* nn.AvgPool2d(2, 2) backward (KernelEstimation's encoder, src/fusion_net/fusion_adacofnet.py:62-70, under autograd): every pixel of a
+ * window receives gy / 4. */
+int fvfi_avg_pool2_backward_nhwc(const float* gy, int gy_pixel_stride, float* gx, int gx_pixel_stride, int B, int Hi, int Wi, int C,
+                                 void* stream);
 int fvfi_resize_bilinear_backward_nhwc(const float* gy, int gy_pixel_stride, const float* x, int x_pixel_stride, float* gx,
                                        int gx_pixel_stride, int B, int Hi, int Wi, int Ho, int Wo, int C, int align_corners,
                                        int relu_input, void* stream);

@@ -57,9 +57,9 @@ def test_gaussian_and_median_vs_scipy(H, W):
 @pytest.fixture(params=["inference", "autograd"])
 def conv_backend(request):
     """The module tests run twice: under no_grad (the fused tcgen05 inference forwards) and with autograd enabled (the
-    differentiable graphs the trainers use: FusionNet's convolutions still run on the tcgen05 kernel through conv2d's autograd
-    Function; PhaseNet / KernelEstimation use their step-by-step torch graph).  There is no back-end switch: which form runs is
-    decided by torch.is_grad_enabled() alone."""
+    differentiable graphs the trainers use: every convolution, pooling and resize step of FusionNet / KernelEstimation / PhaseNetBlock
+    is an autograd Function over the same libfvfi kernels).  There is no back-end switch: which form runs is decided by
+    torch.is_grad_enabled() alone."""
     with (torch.no_grad() if request.param == "inference" else torch.enable_grad()):
         yield request.param
 
@@ -473,3 +473,47 @@ def test_phasenet_block_training_gradients_match_torch():
             # a cancelling sum over 1440 pixels of O(10) terms there
             tol = 1e-3 if n == "feature_map.0.bias" else 5e-5 * max(1.0, float(q.grad.abs().max()))
             assert d <= tol, (c_in, n, d, float(q.grad.abs().max()))
+
+
+def test_kernel_estimation_gradients_match_torch():
+    """KernelEstimation under autograd (fusion_adacofnet.py:109-155): every module forward + backward on libfvfi (conv._ConvTC,
+    _AvgPool2, _ResizeFused); the seven outputs and all parameter gradients equal torch's eager fp64 evaluation of the same modules."""
+    import copy
+    from fvfi.adacofnet import KernelEstimation
+    from fvfi import _lib
+    torch.manual_seed(5)
+    ke = KernelEstimation(5).cuda()
+    ref = copy.deepcopy(ke).double()
+    a, b = torch.rand((1, 3, 64, 96), device="cuda") - 0.4, torch.rand((1, 3, 64, 96), device="cuda") - 0.4
+    gouts = [torch.randn((1, c, 64, 96), device="cuda") for c in (25, 25, 25, 25, 25, 25, 1)]
+    n0 = _lib.lib().fvfi_launch_count()
+    with torch.enable_grad():
+        outs = ke(a, b)
+        assert _lib.lib().fvfi_launch_count() - n0 >= 46, "46 convolutions on libfvfi"
+        sum((o * g).sum() for o, g in zip(outs, gouts)).backward()
+
+    def eager(m, r0, r2):                       # the reference's forward, module by module, in fp64
+        x = torch.cat([r0, r2], 1)
+        c1 = m.moduleConv1(x)
+        c2 = m.moduleConv2(m.modulePool1(c1))
+        c3 = m.moduleConv3(m.modulePool2(c2))
+        c4 = m.moduleConv4(m.modulePool3(c3))
+        c5 = m.moduleConv5(m.modulePool4(c4))
+        d5 = m.moduleUpsample5(m.moduleDeconv5(m.modulePool5(c5)))
+        d4 = m.moduleUpsample4(m.moduleDeconv4(d5 + c5))
+        d3 = m.moduleUpsample3(m.moduleDeconv3(d4 + c4))
+        comb = m.moduleUpsample2(m.moduleDeconv2(d3 + c3)) + c2
+        return [h(comb) for h in (m.moduleWeight1, m.moduleAlpha1, m.moduleBeta1, m.moduleWeight2, m.moduleAlpha2, m.moduleBeta2,
+                                  m.moduleOcclusion)]
+    routs = eager(ref, a.double(), b.double())
+    sum((o * g.double()).sum() for o, g in zip(routs, gouts)).backward()
+    for o, r in zip(outs, routs):
+        assert float((o.detach().double() - r.detach()).abs().max()) <= 2e-5 * max(1.0, float(r.detach().abs().max()))
+    worst = 0.0
+    for (n, p), (_, q) in zip(ke.named_parameters(), ref.named_parameters()):
+        d = float((p.grad.double() - q.grad).abs().max())
+        # ReLU masks can flip on isolated pixels between the fp32 and fp64 forward; compare in norm as well
+        rel = float((p.grad.double() - q.grad).norm()) / (float(q.grad.norm()) + 1e-12)
+        worst = max(worst, rel)
+        assert rel <= 2e-3, (n, rel, d)
+    print("KernelEstimation gradients: worst relative L2 error %.2e" % worst)
