@@ -45,8 +45,8 @@ class PhaseNetTrainer:
     """PhaseNet training step -- mirror of ``Trainer.predict`` + ``Trainer.train`` of the reference's ``src/train/trainer.py``
     in ``mode == 'phase'`` (:65-165): decompose frame 1, frame 2 and the target (Lab planes), PhaseNet on the two input
     pyramids, reconstruct, PhaseNet loss (src/train/loss.py) = L1 on the image + wrapped phase difference per level, Adam.
-    The decomposition needs no gradient; the reconstruction back-propagates through fvfi_pyr_reconstruct_backward; the network
-    runs on torch's autograd convolutions.  Data parallel like FusionTrainer (one flat gradient bucket)."""
+    The decomposition needs no gradient; the reconstruction back-propagates through fvfi_pyr_reconstruct_backward; the network's
+    convolutions run forward and backward on libfvfi (conv._ConvTC), BatchNorm's batch statistics are torch's.  Data parallel like FusionTrainer (one flat gradient bucket)."""
 
     def __init__(self, pyr, phase_net, lr=1e-3, weight_decay=0.0, group=None):
         from .dist import FlatGradBucket
