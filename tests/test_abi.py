@@ -105,3 +105,31 @@ def test_state_dicts_load_into_reference_modules():
         if os.path.exists(path) and os.path.getsize(path) > 10000:
             sd = torch.load(path, map_location="cpu")
             (PhaseNet(types.SimpleNamespace(height=12, nbands=4), cpu, 2) if "phase" in name else FusionNet()).load_state_dict(sd, strict=True)
+
+
+def test_backward_entry_points_validate_arguments():
+    """The backward C-ABI (include/fvfi.h "Backward of the same convolutions") rejects bad arguments with FVFI_EINVAL and a message that
+    names the entry point, before any CUDA call (so this runs without a GPU)."""
+    from fvfi import _lib
+    L = _lib.lib()
+    cases = [
+        ("fvfi_conv2d_wgrad_nhwc", lambda: L.fvfi_conv2d_wgrad_nhwc(None, 18, None, 32, 256, 65536, None, 8, 256, 256, 18, 32, 5, 1, None, None)),
+        ("fvfi_conv2d_wgrad_nhwc", lambda: L.fvfi_conv2d_wgrad_nhwc(16, 18, 16, 32, 256, 65536, 16, 8, 256, 256, 18, 32, 4, 1, 16, None)),   # even K
+        ("fvfi_conv2d_wgrad_nhwc", lambda: L.fvfi_conv2d_wgrad_nhwc(16, 8, 16, 32, 256, 65536, 16, 8, 256, 256, 18, 32, 5, 1, 16, None)),    # stride < Cin
+        ("fvfi_conv2d_wgrad_nhwc", lambda: L.fvfi_conv2d_wgrad_nhwc(16, 18, 16, 32, 2, 4, 16, 1, 2, 2, 18, 32, 5, 1, 16, None)),             # reflect: H <= K/2
+        ("fvfi_conv2d_grad_act", lambda: L.fvfi_conv2d_grad_act(None, 32, None, 32, None, 8, 256, 256, 32, 2, 1, None, None, None)),
+        ("fvfi_conv2d_grad_act", lambda: L.fvfi_conv2d_grad_act(16, 32, None, 32, 16, 8, 256, 256, 32, 2, 1, None, None, None)),             # ReLU needs y
+        ("fvfi_conv2d_grad_act", lambda: L.fvfi_conv2d_grad_act(16, 32, 16, 32, 16, 8, 256, 256, 32, 2, 1, 16, None, None)),                 # gbias needs workspace
+        ("fvfi_reflect_pad_backward_nhwc", lambda: L.fvfi_reflect_pad_backward_nhwc(16, 32, 16, 32, 1, 2, 2, 32, 2, None)),                 # H <= P
+        ("fvfi_resize_bilinear_backward_nhwc", lambda: L.fvfi_resize_bilinear_backward_nhwc(16, 32, None, 32, 16, 32, 1, 8, 8, 40, 16, 32, 0, 0, None)),
+        ("fvfi_resize_bilinear_backward_nhwc", lambda: L.fvfi_resize_bilinear_backward_nhwc(16, 32, None, 32, 16, 32, 1, 8, 8, 16, 16, 32, 0, 1, None)),
+        ("fvfi_max_pool2_backward_nhwc", lambda: L.fvfi_max_pool2_backward_nhwc(None, 1, None, 1, None, 1, 1, 4, 4, 1, None)),
+        ("fvfi_avg_pool2_backward_nhwc", lambda: L.fvfi_avg_pool2_backward_nhwc(16, 1, 16, 1, 1, 1, 4, 1, None)),                           # Hi < 2
+        ("fvfi_fusion_blend_backward", lambda: L.fvfi_fusion_blend_backward(None, None, None, None, None, 10, None)),
+    ]
+    for name, call in cases:
+        rc = call()
+        assert rc != 0, name
+        assert name in L.fvfi_last_error().decode(), (name, L.fvfi_last_error())
+    assert L.fvfi_conv2d_wgrad_workspace_floats(8, 256, 256, 18, 32, 5) >= 32 * 25 * 20
+    assert L.fvfi_conv2d_grad_act_workspace_floats(8, 256, 256, 32, 2) >= 32
