@@ -349,6 +349,22 @@ def test_phasenet_training_step():
     assert losses[-1] < losses[0]
 
 
+def test_median_full_tiles_and_ties_vs_scipy():
+    """The tracked-median path of median_rank_kernel on full-width tiles (77 x 16 outputs for k = 50), several tile rows / columns, window
+    sizes with a non-power-of-two bitmap share per lane, and heavily TIED data (values quantised to a few levels, saturated at 0 / 1 the
+    way the recipe's clamped uncertainty maps are): bit-equal to scipy's rank filter."""
+    from scipy.ndimage import median_filter
+    from fvfi import filters
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand((2, 150, 260), generator=g)
+    x[1] = (x[1] * 6).floor() / 5                          # 6 distinct values
+    x[0] = (x[0] * 1.6 - 0.3).clamp(0, 1)                  # ~19 % zeros, ~19 % ones
+    for size in (50, 31, 21):
+        m = filters.median_filter(x.cuda(), size).cpu().numpy()
+        ref = np.stack([median_filter(mm.numpy(), size=size) for mm in x])
+        assert np.array_equal(m, ref), size
+
+
 @pytest.mark.parametrize("H,W,chunk", [(64, 96, None), (120, 70, 2)])
 def test_phasenet_forward_fused_matches_stepwise(H, W, chunk):
     """PhaseNet.forward_fused (regrouping, normalisation, concat, amplitude blend and de-normalisation fused into two kernels,
