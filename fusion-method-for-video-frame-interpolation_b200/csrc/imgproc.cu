@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) gauss1d_kernel(const float* __restrict__ 
 // keeps the 256-rank block that holds it and the number of set bits before that block, updated from the ranks that leave / enter the
 // window (two ballots per round), so a pixel counts one block (one word per lane + redux.add) and bisects one word with popcounts
 // (a full recount of the 256-word bitmap + warp scan + __fns per pixel was half of the kernel: 1.65 -> 1.14 ms per 1080p map).
+// The sort keeps 16 consecutive elements per thread in registers for the passes with j <= 8 (1.14 -> 0.90 ms).
 // Fallback (median_bisect_kernel): per-thread bisection over the key space, any k <= 96.
 __device__ __forceinline__ unsigned f2key(float f) {
     const unsigned u = __float_as_uint(f);
@@ -122,11 +123,34 @@ __device__ __forceinline__ float key2f(unsigned k) {
 constexpr int MR_TH = 16, MR_THREADS = MR_TH * 32;
 constexpr int MR_MAX_N = 8192;
 
+// element i of the sort array lives at i + (i >> 4): a thread's 16 consecutive elements (the register-local passes) then start
+// 34 words apart, which spreads the lanes of a 64-bit access over all banks
+__device__ __forceinline__ int mr_sk(int i) { return i + (i >> 4); }
+constexpr int MR_E = 16;                                               // elements per thread in the register-local passes
+
+// compare-exchange passes j = JS, JS/2, .., 1 of bitonic stage kk on the 16 elements a thread holds (element e = index base + e)
+template <int JS>
+__device__ __forceinline__ void mr_local_passes(unsigned long long* v, int base, int kk) {
+#pragma unroll
+    for (int j = JS; j >= 1; j >>= 1) {
+#pragma unroll
+        for (int e = 0; e < MR_E; ++e) {
+            if ((e & j) == 0) {
+                const bool asc = ((base + e) & kk) == 0;
+                const unsigned long long a = v[e], b = v[e | j];
+                const bool sw = (a > b) == asc;
+                v[e] = sw ? b : a;
+                v[e | j] = sw ? a : b;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(MR_THREADS) median_rank_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                  int H, int W, int k, int rank, int npad, int MR_TW) {
-    extern __shared__ unsigned long long pairs[];                      // npad (key << 32 | pos)
+    extern __shared__ unsigned long long pairs[];                      // npad + npad/16 (key << 32 | pos), skewed: mr_sk
     const int RW = MR_TW + k - 1, RH = MR_TH + k - 1, n = RW * RH;
-    unsigned short* rank_of = (unsigned short*)(pairs + npad);         // n
+    unsigned short* rank_of = (unsigned short*)(pairs + npad + (npad >> 4));   // n
     const int nwords = (n + 31) >> 5;
     const int wpl = (nwords + 31) >> 5;                                // bitmap words per lane
     unsigned* bitmaps = (unsigned*)(rank_of + ((n + 7) & ~7));         // MR_TH x (wpl*32), 16-byte aligned
@@ -141,21 +165,55 @@ __global__ void __launch_bounds__(MR_THREADS) median_rank_kernel(const float* __
             const unsigned key = f2key(src[(size_t)reflect_idx(y0 + r - lo_off, H) * W + reflect_idx(x0 + c - lo_off, W)]);
             v = ((unsigned long long)key << 32) | (unsigned)q;
         }
-        pairs[q] = v;
+        pairs[mr_sk(q)] = v;
     }
     __syncthreads();
-    for (int kk = 2; kk <= npad; kk <<= 1) {
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int p = threadIdx.x; p < (npad >> 1); p += MR_THREADS) {      // one thread per compare-exchange pair
-                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));           // p with a zero inserted at bit log2(j)
-                const int ixj = i | j;
-                const unsigned long long a = pairs[i], b = pairs[ixj];
-                if ((a > b) == ((i & kk) == 0)) { pairs[i] = b; pairs[ixj] = a; }
+    if (npad == MR_E * MR_THREADS) {
+        // Every thread keeps 16 consecutive elements in registers for the passes with j <= 8 (46 of the 91 passes of an 8192-entry
+        // network): stages kk = 2 .. 16 entirely, and the last four passes of every later stage -- one shared-memory round trip per
+        // stage instead of four.  The passes with j >= 16 go through shared memory, one thread per compare-exchange pair.
+        unsigned long long v[MR_E];
+        const int base = threadIdx.x * MR_E, pb = mr_sk(base);
+#pragma unroll
+        for (int e = 0; e < MR_E; ++e) v[e] = pairs[pb + e];
+        mr_local_passes<1>(v, base, 2);
+        mr_local_passes<2>(v, base, 4);
+        mr_local_passes<4>(v, base, 8);
+        mr_local_passes<8>(v, base, 16);
+#pragma unroll
+        for (int e = 0; e < MR_E; ++e) pairs[pb + e] = v[e];
+        __syncthreads();
+        for (int kk = 32; kk <= npad; kk <<= 1) {
+            for (int j = kk >> 1; j >= MR_E; j >>= 1) {
+                for (int p = threadIdx.x; p < (npad >> 1); p += MR_THREADS) {
+                    const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));       // p with a zero inserted at bit log2(j)
+                    const int pi = mr_sk(i), pj = mr_sk(i | j);
+                    const unsigned long long a = pairs[pi], b = pairs[pj];
+                    if ((a > b) == ((i & kk) == 0)) { pairs[pi] = b; pairs[pj] = a; }
+                }
+                __syncthreads();
             }
+#pragma unroll
+            for (int e = 0; e < MR_E; ++e) v[e] = pairs[pb + e];
+            mr_local_passes<8>(v, base, kk);
+#pragma unroll
+            for (int e = 0; e < MR_E; ++e) pairs[pb + e] = v[e];
             __syncthreads();
         }
+    } else {
+        for (int kk = 2; kk <= npad; kk <<= 1) {
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int p = threadIdx.x; p < (npad >> 1); p += MR_THREADS) {  // one thread per compare-exchange pair
+                    const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                    const int pi = mr_sk(i), pj = mr_sk(i | j);
+                    const unsigned long long a = pairs[pi], b = pairs[pj];
+                    if ((a > b) == ((i & kk) == 0)) { pairs[pi] = b; pairs[pj] = a; }
+                }
+                __syncthreads();
+            }
+        }
     }
-    for (int r = threadIdx.x; r < n; r += MR_THREADS) rank_of[(unsigned)(pairs[r] & 0xffffffffu)] = (unsigned short)r;
+    for (int r = threadIdx.x; r < n; r += MR_THREADS) rank_of[(unsigned)(pairs[mr_sk(r)] & 0xffffffffu)] = (unsigned short)r;
     const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
     unsigned* bm = bitmaps + ty * (wpl * 32);
     for (int i = lane; i < wpl * 32; i += 32) bm[i] = 0u;
@@ -229,7 +287,7 @@ __global__ void __launch_bounds__(MR_THREADS) median_rank_kernel(const float* __
                 if (nd >= cc) { nd -= cc; bit += sft; }
             }
             const int r = ((ob * wpl + lane) << 5) + (int)bit;
-            out[(size_t)blockIdx.z * plane + (size_t)y * W + x0 + tx] = key2f((unsigned)(pairs[r] >> 32));
+            out[(size_t)blockIdx.z * plane + (size_t)y * W + x0 + tx] = key2f((unsigned)(pairs[mr_sk(r)] >> 32));
         }
         __syncwarp();
     }
@@ -318,7 +376,7 @@ extern "C" int fvfi_median_filter(const float* in, float* out, int N, int H, int
         int npad = 1;
         while (npad < n) npad <<= 1;
         const int nwords = (n + 31) / 32, wpl = (nwords + 31) / 32;
-        const size_t smem = (size_t)npad * 8 + (size_t)((n + 7) & ~7) * 2 + (size_t)MR_TH * wpl * 32 * 4;
+        const size_t smem = (size_t)(npad + (npad >> 4)) * 8 + (size_t)((n + 7) & ~7) * 2 + (size_t)MR_TH * wpl * 32 * 4;
         if (smem > 48 * 1024)
             FVFI_SMEM_OPT_IN(median_rank_kernel, smem);
         dim3 grid(ceil_div(W, MR_TW), ceil_div(H, MR_TH), N);
