@@ -78,6 +78,7 @@ struct ConvArgs {
     int out_nchw;          // 1: y is planar [B,Cout,H,W] (coefficient maps for the warp kernel)
     int cout_store;        // NHWC channels written per pixel: Cout, or round16(Cout) with the padding zero-filled
     int MT, RW, RH, NPIX;  // tiles per CTA, staged region geometry
+    int KCS;               // 16-byte units between the K chunks of an A stage: NPIX rounded up to 2 (mod 8), see the host side
     int nchunks, last_ksteps, astages, bstages, tmem_cols;
     int wide, tcols;       // WIDE MMA pairing (Npad <= 32); TMEM columns per accumulator tile (Npad or 2*Npad)
     int nacc;              // TMEM accumulator buffers (2 when they fit: epilogue of tile j-1 overlaps the MMAs of tile j)
@@ -690,7 +691,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             for (int u = 0; u < UMAX; ++u) {
                 const int q = threadIdx.x + u * CV_LOADERS;
                 if (q < total) {
-                    const int o = (q & kmask) * A.NPIX + (q >> ksh);
+                    const int o = (q & kmask) * A.KCS + (q >> ksh);
                     if (PREC == PREC_F16X3) {
                         unsigned hw[4], lw[4];
 #pragma unroll
@@ -788,7 +789,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                     const float ly = w0.x, lx = w0.y, hy = 1.f - ly, hx = 1.f - lx;
 #pragma unroll
                     for (int e = 0; e < CPK; ++e) w[e] = bilerp(hy, hx, ly, lx, a0[e], b0[e], c0[e], d0[e]);
-                    put(kg * A.NPIX + pix, w);
+                    put(kg * A.KCS + pix, w);
                 }
                 {
                     const float ly = w1.x, lx = w1.y, hy = 1.f - ly, hx = 1.f - lx;
@@ -798,7 +799,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                         const float b = kind == 0 ? b0[e] : b1[e], d = kind == 0 ? d0[e] : d1[e];
                         w[e] = off1 >= 0 ? bilerp(hy, hx, ly, lx, a, b, cc, d) : 0.f;
                     }
-                    put(kg * A.NPIX + pix + 1, w);
+                    put(kg * A.KCS + pix + 1, w);
                 }
             }
             fence_async_smem();
@@ -892,7 +893,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
             // instruction descriptor: D=F32, A=B=TF32 (format 2) or F16 (format 0), K-major both, N = Npad, M = 128
             const unsigned fmt = (PREC == PREC_F16X3) ? 0u : 2u;
             const unsigned idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(A.Npad >> 3) << 17) | ((128u >> 4) << 24);
-            const unsigned a_lbo = (unsigned)A.NPIX * 16u, a_sbo = (unsigned)A.RW * 16u;
+            const unsigned a_lbo = (unsigned)A.KCS * 16u, a_sbo = (unsigned)A.RW * 16u;
             const unsigned b_lbo = 2u * (unsigned)A.Npad * 16u, b_sbo = 128u;     // K chunks are [hi rows; lo rows] apart
             const unsigned b_half = (unsigned)A.Npad * 16u;                        // B_lo rows follow the B_hi rows
             const unsigned idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(A.Npad >> 2) << 17) | ((128u >> 4) << 24);
@@ -997,7 +998,16 @@ static int conv_geometry(ConvArgs& a, int prec, size_t* smem_bytes) {
         a.RW = 8 * mt + a.KW - 1;
         a.RH = CV_ROWS + a.KH - 1;
         a.NPIX = a.RW * a.RH;
-        a.a_stage_bytes = (unsigned)a.NPIX * CV_KCHUNKS * 16u * 2u;    // hi + lo
+        // K-chunk stride of the A stage = NPIX 16-byte units rounded up to 2 (mod 8): the four K chunks of a pixel (what four
+        // consecutive loader lanes store) then start 32 bytes apart modulo the 128-byte bank row, and a quarter-warp's 128-bit
+        // stores (two pixels x four K chunks) cover all 32 banks once (ncu on 32->32 @1088x1920: the unpadded stride put K chunks
+        // 0/2 and 1/3 on the same banks -- 8 instead of 4 wavefronts per STS.128, 20 M of the layer's 150 M LSU wavefronts)
+#ifdef FVFI_CONV_NO_KCS_PAD
+        a.KCS = a.NPIX;
+#else
+        a.KCS = a.NPIX + ((2 - a.NPIX) & 7);
+#endif
+        a.a_stage_bytes = (unsigned)a.KCS * CV_KCHUNKS * 16u * 2u;    // hi + lo
         if (a.NPIX * CV_KCHUNKS > CV_LOADERS * CV_UMAX) continue;          // the loaders keep a whole K chunk in registers (UMAX)
         const size_t misc = 512 + (size_t)a.NPIX * 4 + 1024 + 16 + (a.up ? (size_t)a.NPIX * 16 : 0);
         const int min_b = std::min(2, a.nchunks * taps);
