@@ -1,5 +1,5 @@
 """Same-process A/B of a boolean switch of fvfi.conv on one pipeline call (1080p, B frame pairs), alternating:
-    python tools/ab_switch.py fuse_avgpool [B] [rounds]"""
+    python tools/ab_switch.py fuse_avgpool [B] [rounds] [value ...]"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -31,12 +31,13 @@ def run(flag, reps=3):
 
 for _ in range(2):
     run(True)
-res = {True: [], False: []}
+vals = [True, False] if len(sys.argv) <= 4 else [eval(v) for v in sys.argv[4:]]
+res = {v: [] for v in vals}
 outs = {}
 for _ in range(rounds):
-    for flag in (True, False):
+    for flag in vals:
         ms, outs[flag] = run(flag)
         res[flag].append(ms)
-for flag in (True, False):
+for flag in vals:
     print("%s = %s: %s  mean %.2f ms" % (name, flag, " ".join("%.2f" % v for v in res[flag]), sum(res[flag]) / len(res[flag])))
-print("outputs identical:", bool(torch.equal(outs[True], outs[False])))
+print("outputs identical:", all(bool(torch.equal(outs[vals[0]], outs[v])) for v in vals[1:]))
