@@ -95,11 +95,6 @@ struct ConvArgs {
     // (PhaseNet: previous level's features resampled + this level's values, src/phase_net/phase_net.py:138-148)
     const float* x2;
     int ldx2, up_chunks;
-    // fused nn.AvgPool2d(2, 2) of the result (KernelEstimation's encoder, fusion_adacofnet.py:62-70, 111-123): pool [B,H/2,W/2,Cout] NHWC is
-    // written by the epilogue from the finished values (a 2x2 window lies inside one warp's 4 rows x 8 columns of the tile); y may then
-    // be null (the full-resolution tensor is not needed: moduleConv1)
-    float* pool;
-    int ldp;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -486,23 +481,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                         if (n0 + i < A.cout_store) dst[n0 + i] = v[i];
                 }
             };
-            // fused 2x2 average pooling: ((a + b) + (c + d)) * 0.25 in the order of avg_pool2_nhwc_kernel (bit-identical); lane l holds pixel
-            // (row l >> 3, column l & 7) of the warp's 4 x 8 block, its window partners are lanes l ^ 1 and l ^ 8; the top-left lane stores
-            auto pool16 = [&](int t, int n0, const float* v) {
-                float sum[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float a = v[i] + __shfl_xor_sync(0xffffffffu, v[i], 1);
-                    sum[i] = (a + __shfl_xor_sync(0xffffffffu, a, 8)) * 0.25f;
-                }
-                const int ocol = T.x0 + t * 8 + (m & 7);
-                if ((m & 9) == 0 && orow < A.H && ocol < A.W) {
-                    float* dst = A.pool + (((size_t)T.img * (A.H >> 1) + (orow >> 1)) * (A.W >> 1) + (ocol >> 1)) * A.ldp + n0;
-#pragma unroll
-                    for (int i = 0; i < 16; i += 8)
-                        if (n0 + i < A.Cout) stg256(dst + i, sum + i);
-                }
-            };
             auto emit = [&](int t, int n0, const float* r, float smax, float sinv) {
                 float v[16];
 #pragma unroll
@@ -536,8 +514,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_split_kernel(const ConvArg
                         }
                     }
                 }
-                if (A.pool) pool16(t, n0, v);
-                if (A.y) store16(t, n0, v);
+                store16(t, n0, v);
             };
             if (ACT == ACT_SOFTMAX) {
                 for (int t = 0; t < A.MT; ++t) {
@@ -1137,44 +1114,15 @@ extern "C" int fvfi_conv2d_nhwc_residual(const float* x, int x_pixel_stride, con
                                       y_pixel_stride, B, H, W, Cin, Cout, KH, KW, pad_mode, activation, out_nchw, precision, stream);
 }
 
-static int conv2d_impl(const float* x, int x_pixel_stride, int Hs, int Ws, int align_corners, const float* x_direct,
-                       int x_direct_pixel_stride, int cin_upsampled, const float* packed_weight, const float* bias,
-                       const float* residual, int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H, int W, int Cin,
-                       int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw, int precision, float* y_pool,
-                       int y_pool_pixel_stride, void* stream);
-
 extern "C" int fvfi_conv2d_nhwc_upsampled(const float* x, int x_pixel_stride, int Hs, int Ws, int align_corners, const float* x_direct,
                                           int x_direct_pixel_stride, int cin_upsampled,
                                           const float* packed_weight, const float* bias, const float* residual,
                                           int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H, int W, int Cin,
                                           int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw, int precision,
                                           void* stream) {
-    FVFI_CHECK_ARG(y, "conv2d: null pointer");
-    return conv2d_impl(x, x_pixel_stride, Hs, Ws, align_corners, x_direct, x_direct_pixel_stride, cin_upsampled, packed_weight, bias,
-                       residual, residual_pixel_stride, y, y_pixel_stride, B, H, W, Cin, Cout, KH, KW, pad_mode, activation, out_nchw,
-                       precision, nullptr, 0, stream);
-}
-
-extern "C" int fvfi_conv2d_nhwc_avgpool(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias, float* y,
-                                        int y_pixel_stride, float* y_pool, int y_pool_pixel_stride, int B, int H, int W, int Cin,
-                                        int Cout, int KH, int KW, int pad_mode, int activation, int precision, void* stream) {
-    FVFI_CHECK_ARG(y_pool && (H % 2) == 0 && (W % 2) == 0, "conv2d_avgpool: needs y_pool and even H, W (got %dx%d)", H, W);
-    FVFI_CHECK_ARG(activation != ACT_SOFTMAX, "conv2d_avgpool: no softmax");
-    FVFI_CHECK_ARG((Cout % 8) == 0 && (y_pool_pixel_stride % 8) == 0 && y_pool_pixel_stride >= Cout && (((size_t)y_pool) & 31) == 0,
-                   "conv2d_avgpool: Cout and the pooled pixel stride must be multiples of 8 (stride >= Cout), y_pool 32-byte aligned");
-    FVFI_CHECK_ARG(!y || y_pixel_stride >= Cout, "conv2d_avgpool: pixel stride smaller than channel count");
-    return conv2d_impl(x, x_pixel_stride, 0, 0, 0, nullptr, 0, 0, packed_weight, bias, nullptr, 0, y, y ? y_pixel_stride : Cout, B, H, W, Cin,
-                       Cout, KH, KW, pad_mode, activation, 0, precision, y_pool, y_pool_pixel_stride, stream);
-}
-
-static int conv2d_impl(const float* x, int x_pixel_stride, int Hs, int Ws, int align_corners, const float* x_direct,
-                       int x_direct_pixel_stride, int cin_upsampled, const float* packed_weight, const float* bias,
-                       const float* residual, int residual_pixel_stride, float* y, int y_pixel_stride, int B, int H, int W, int Cin,
-                       int Cout, int KH, int KW, int pad_mode, int activation, int out_nchw, int precision, float* y_pool,
-                       int y_pool_pixel_stride, void* stream) {
     FVFI_CHECK_ARG(!residual || (activation != ACT_SOFTMAX && residual_pixel_stride >= Cout),
                    "conv2d: a residual needs a pixel stride >= Cout and no softmax");
-    FVFI_CHECK_ARG(x && packed_weight && (y || y_pool), "conv2d: null pointer");
+    FVFI_CHECK_ARG(x && packed_weight && y, "conv2d: null pointer");
     FVFI_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && B <= 65535, "conv2d: bad dimension");
     FVFI_CHECK_ARG((KH == 1 || KH == 3 || KH == 5) && KW == KH, "conv2d: kernel must be 1x1, 3x3 or 5x5");
     FVFI_CHECK_ARG(pad_mode == PAD_ZERO || pad_mode == PAD_REFLECT, "conv2d: pad_mode must be 0 (zero) or 1 (reflect)");
@@ -1186,7 +1134,6 @@ static int conv2d_impl(const float* x, int x_pixel_stride, int Hs, int Ws, int a
     a.x = x; a.hdr = packed_weight; a.wpack = packed_weight + CV_HDR; a.bias = bias; a.y = y;
     a.ldx = x_pixel_stride; a.ldy = y_pixel_stride; a.out_nchw = (out_nchw == 1) ? 1 : 0;
     a.res = residual; a.ldr = residual_pixel_stride;
-    a.pool = y_pool; a.ldp = y_pool_pixel_stride;
     a.up = (Hs > 0 || Ws > 0) ? 1 : 0;
     if (a.up) {
         const int cpk = cv_cpk(precision), cin_r = (Cin + cpk - 1) / cpk * cpk;

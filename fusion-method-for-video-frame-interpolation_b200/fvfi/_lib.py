@@ -44,7 +44,6 @@ _PROTOS = {
     "fvfi_conv2d_nhwc_residual": (c_int, [c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_int] + [c_int] * 11 + [c_fp]),
     "fvfi_conv2d_nhwc_upsampled": (c_int, [c_fp, c_int, c_int, c_int, c_int, c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_int]
                                    + [c_int] * 11 + [c_fp]),
-    "fvfi_conv2d_nhwc_avgpool": (c_int, [c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_int] + [c_int] * 10 + [c_fp]),
     "fvfi_conv2d_overflow_count": (c_int, []),
     "fvfi_conv2d_grad_act_workspace_floats": (c_size, [c_int] * 5),
     "fvfi_conv2d_grad_act": (c_int, [c_fp, c_int, c_fp, c_int, c_fp] + [c_int] * 6 + [c_fp, c_fp, c_fp]),

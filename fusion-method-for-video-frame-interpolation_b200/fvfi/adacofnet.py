@@ -85,11 +85,9 @@ class KernelEstimation(torch.nn.Module):
         self.moduleOcclusion = Subnet(1, nn.Sigmoid(), last_in=64)
 
     @staticmethod
-    def _seq_tc(seq, x, nchw_last=False, residual=None, pool=None):
+    def _seq_tc(seq, x, nchw_last=False, residual=None):
         """Run an nn.Sequential of Conv2d / ReLU / Upsample / Softmax / Sigmoid: conv + activation is one tcgen05 kernel,
-        bilinear upsampling is the NHWC resize kernel; with ``nchw_last`` the final conv writes planar NCHW.
-        ``pool`` ("both" / "only"): the AvgPool2d(2, 2) that follows the block rides on the epilogue of its last convolution
-        (returns (y, pooled) / pooled)."""
+        bilinear upsampling is the NHWC resize kernel; with ``nchw_last`` the final conv writes planar NCHW."""
         mods = list(seq)
         last_conv = max(i for i, m in enumerate(mods) if isinstance(m, torch.nn.Conv2d))
         i = 0
@@ -104,7 +102,7 @@ class KernelEstimation(torch.nn.Module):
                 pad = (i + 2 < len(mods) and isinstance(mods[i + 2], torch.nn.Upsample) and m.out_channels % 4 != 0)
                 x = tc.conv_module(m, x, act, nchw_out=nchw_last and i == last_conv, pad_out=pad,
                                    residual=residual if i == last_conv else None,   # skip connection after the last conv + act
-                                   upsample=up, avgpool=pool if i == last_conv else None)
+                                   upsample=up)
                 up = None
                 i += 2 if act else 1
             elif (isinstance(m, torch.nn.Upsample) and i + 1 == last_conv and mods[last_conv].out_channels == 1
@@ -138,16 +136,15 @@ class KernelEstimation(torch.nn.Module):
     def _forward_tc_x(self, x):
         """``x``: [B,8,H,W] channels_last = (frame0 - mean | frame2 - mean | two zero channels)."""
         run = self._seq_tc
-        # modulePool1..5 ride on the epilogue of the block before them (fvfi_conv2d_nhwc_avgpool); c1 itself is never needed
-        p1 = run(self.moduleConv1, x, pool="only")
-        c2, p2 = run(self.moduleConv2, p1, pool="both")
-        del p1
-        c3, p3 = run(self.moduleConv3, p2, pool="both")
-        c4, p4 = run(self.moduleConv4, p3, pool="both")
-        c5, p5 = run(self.moduleConv5, p4, pool="both")
-        del p2, p3, p4
+        pool = tc.avg_pool2                    # modulePool1..5 = AvgPool2d(2, 2), on NHWC with 256-bit accesses
+        c1 = run(self.moduleConv1, x)
+        c2 = run(self.moduleConv2, pool(c1))
+        del c1
+        c3 = run(self.moduleConv3, pool(c2))
+        c4 = run(self.moduleConv4, pool(c3))
+        c5 = run(self.moduleConv5, pool(c4))
         # the skip additions (fusion_adacofnet.py:128-138) ride on the epilogue of the Upsample modules' convolution
-        s5 = run(self.moduleUpsample5, run(self.moduleDeconv5, p5), residual=c5)            # d5 + c5
+        s5 = run(self.moduleUpsample5, run(self.moduleDeconv5, pool(c5)), residual=c5)      # d5 + c5
         s4 = run(self.moduleUpsample4, run(self.moduleDeconv4, s5), residual=c4)            # d4 + c4
         s3 = run(self.moduleUpsample3, run(self.moduleDeconv3, s4), residual=c3)            # d3 + c3
         comb = run(self.moduleUpsample2, run(self.moduleDeconv2, s3), residual=c2)          # d2 + c2

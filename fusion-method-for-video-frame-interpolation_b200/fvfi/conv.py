@@ -204,11 +204,8 @@ def to_nhwc(x):
 fuse_upsample = True    # Upsample -> Conv2d as one kernel (A/B switch for tools/; the unfused form is resize_bilinear + conv2d)
 
 
-fuse_avgpool = True     # Conv2d -> ReLU -> AvgPool2d(2, 2) with the pooling in the convolution's epilogue (A/B switch for tools/)
-
-
 def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_out=False, pad_out=False, residual=None,
-           upsample=None, x_direct=None, avgpool=None):
+           upsample=None, x_direct=None):
     """x [B,Cin,H,W] (any memory format; channels_last avoids a copy) -> [B,Cout,H,W] channels_last
     (``nchw_out=True``: plain contiguous NCHW, written directly by the epilogue).
     Equivalent to act(F.conv2d(pad(x), weight, bias)) with 'same' padding (K//2) in zeros or reflect mode;
@@ -219,9 +216,7 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
     ``upsample=((H, W), align_corners)``: the convolution runs on the bilinear resampling of ``x`` to [H, W]
     (torch.nn.Upsample -> Conv2d in one kernel, fvfi_conv2d_nhwc_upsampled); inference only.
     ``x_direct`` [B,C2,H,W] (with ``upsample``): the input is ``cat(resize(x), x_direct)`` along the channels -- the concatenated
-    tensor is never built (x.shape[1] must be a multiple of the K chunk: 32 channels, 16 for tf32x3).
-    ``avgpool``: "both" -> returns (y, avg_pool2(y)), "only" -> returns avg_pool2(y) alone; the 2x2 averages are written by the epilogue
-    (fvfi_conv2d_nhwc_avgpool, bit-identical to the separate pooling kernel); inference only, even H and W, Cout a multiple of 8."""
+    tensor is never built (x.shape[1] must be a multiple of the K chunk: 32 channels, 16 for tf32x3)."""
     if not x.is_cuda:
         raise NotImplementedError("fvfi.conv.conv2d: CUDA tensors only")
     if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
@@ -231,34 +226,6 @@ def conv2d(x, weight, bias=None, padding_mode="zeros", act=None, out=None, nchw_
         return _ConvTC.apply(x, weight, bias, padding_mode, act)
     B, Cin, H, W = x.shape
     Cout, Cin_w, KH, KW = weight.shape
-    if avgpool is not None:
-        assert avgpool in ("both", "only")
-        fused = (fuse_avgpool and upsample is None and residual is None and out is None and not nchw_out and not pad_out
-                 and act != "softmax" and H % 2 == 0 and W % 2 == 0 and Cout % 8 == 0 and not (KH == 1 and Cout <= 8))
-        if not fused:
-            y = conv2d(x, weight, bias, padding_mode, act, out, nchw_out, pad_out, residual, upsample, x_direct)
-            return (y, avg_pool2(y)) if avgpool == "both" else avg_pool2(y)
-        assert Cin >= Cin_w and KH == KW and KH in (1, 3, 5)
-        xc = to_nhwc(x.float())
-        y = (torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
-             if avgpool == "both" else None)
-        yp = torch.empty((B, Cout, H // 2, W // 2), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
-        L = _lib.lib()
-        b = None if bias is None else bias.detach().contiguous().float()
-        with torch.cuda.device(x.device):
-            parts = _packed(weight)
-            if timing is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            for (o, n, buf) in parts:
-                _lib.check(L.fvfi_conv2d_nhwc_avgpool(xc.data_ptr(), xc.stride(3), buf.data_ptr(), None if b is None else b.data_ptr() + 4 * o,
-                                                      None if y is None else y.data_ptr() + 4 * o, Cout, yp.data_ptr() + 4 * o, Cout, B, H, W,
-                                                      Cin_w, n, KH, KW, {"zeros": 0, "reflect": 1}[padding_mode], ACT[act], precision,
-                                                      _lib.stream_ptr()))
-            if timing is not None:
-                e1.record()
-                timing.append((2.0 * B * H * W * Cin_w * Cout * KH * KW, e0, e1, len(parts), (B, Cin_w, Cout, KH, H, W, act), False))
-        return (y, yp) if avgpool == "both" else yp
     xd, cin_up = None, 0
     if x_direct is not None:
         chunk = 32 if precision == PRECISIONS["f16x3"] else 16
@@ -485,14 +452,14 @@ def avg_pool2(x, _fn="fvfi_avg_pool2_nhwc"):
     return out
 
 
-def conv_module(conv, x, act=None, nchw_out=False, pad_out=False, residual=None, upsample=None, x_direct=None, avgpool=None):
+def conv_module(conv, x, act=None, nchw_out=False, pad_out=False, residual=None, upsample=None, x_direct=None):
     """Run an nn.Conv2d (stride 1, dilation 1, padding == K//2) through the tensor-core kernel."""
     k = conv.kernel_size[0]
     assert conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
     assert conv.padding == (k // 2, k // 2) or (k == 1 and conv.padding == (0, 0))
     mode = "zeros" if k == 1 else conv.padding_mode
     return conv2d(x, conv.weight, conv.bias, mode, act, nchw_out=nchw_out, pad_out=pad_out, residual=residual, upsample=upsample,
-                  x_direct=x_direct, avgpool=avgpool)
+                  x_direct=x_direct)
 
 
 def conv_bn_module(conv, bn, x, act=None, upsample=None, x_direct=None):

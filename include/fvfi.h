@@ -147,14 +147,6 @@ int fvfi_conv2d_nhwc_upsampled(const float* x, int x_pixel_stride, int Hs, int W
                                int x_direct_pixel_stride, int cin_upsampled, const float* packed_weight, const float* bias, const float* residual, int residual_pixel_stride,
                                float* y, int y_pixel_stride, int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad_mode,
                                int activation, int out_nchw, int precision, void* stream);
-/* Conv2d -> (activation) -> nn.AvgPool2d(2, 2) with the pooling done by the epilogue (KernelEstimation's encoder: `Basic` block followed
- * by modulePool1..5, src/fusion_net/fusion_adacofnet.py:62-70, 111-123): y_pool [B,H/2,W/2,>=Cout] NHWC receives the 2x2 averages of
- * act(conv(x) + bias) -- bit-identical to fvfi_avg_pool2_nhwc of the full result; y [B,H,W,>=Cout] receives the full result, or is NULL
- * when only the pooled tensor is needed (moduleConv1, whose output is not a skip connection).  H, W even; Cout and y_pool_pixel_stride
- * multiples of 8, y_pool 32-byte aligned; NHWC output only, no softmax. */
-int fvfi_conv2d_nhwc_avgpool(const float* x, int x_pixel_stride, const float* packed_weight, const float* bias, float* y,
-                             int y_pixel_stride, float* y_pool, int y_pool_pixel_stride, int B, int H, int W, int Cin, int Cout, int KH,
-                             int KW, int pad_mode, int activation, int precision, void* stream);
 /* FVFI_CONV_F16X3 scales activations by 2^4 before the fp16 split; |x| > 4094 would leave fp16's range.  Returns 1
  * (and clears the flag) if any convolution since the last call saw such a value, 0 if not, -1 on error.
  * Synchronises the device. */

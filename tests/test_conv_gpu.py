@@ -449,24 +449,3 @@ def test_fusion_blend_backward_matches_torch():
     ob.backward(gout.double())
     assert float((oa.detach().double() - ob.detach()).abs().max()) <= 2e-6
     assert float((xa.grad.double() - xb.grad).abs().max()) <= 1e-5 and float((ba.grad.double() - bb.grad).abs().max()) <= 1e-6
-
-
-@pytest.mark.parametrize("B,Cin,Cout,H,W,act", [(2, 8, 32, 34, 50, "relu"), (1, 32, 64, 48, 72, "relu"), (2, 64, 128, 18, 26, "relu"),
-                                                (1, 128, 512, 12, 20, "relu"), (1, 32, 32, 64, 96, None)])
-def test_conv_fused_avgpool_is_bit_identical(B, Cin, Cout, H, W, act, prec):
-    """Conv2d -> ReLU -> AvgPool2d(2, 2) with the pooling in the convolution's epilogue (fvfi_conv2d_nhwc_avgpool; KernelEstimation's
-    `Basic` block + modulePool, fusion_adacofnet.py:62-70,111-123): both outputs are bit-identical to convolution + pooling kernel, in
-    the "both" and the "only" form, for tiles cut by the image border and for Cout split over several launches."""
-    from fvfi import conv
-    g = torch.Generator(device="cuda").manual_seed(6)
-    x = torch.randn((B, Cin, H, W), device="cuda", generator=g)
-    w = torch.randn((Cout, Cin, 3, 3), device="cuda", generator=g) / (Cin * 9) ** 0.5
-    b = torch.randn((Cout,), device="cuda", generator=g)
-    y0 = conv.conv2d(x, w, b, "zeros", act)
-    p0 = conv.avg_pool2(y0)
-    y1, p1 = conv.conv2d(x, w, b, "zeros", act, avgpool="both")
-    p2 = conv.conv2d(x, w, b, "zeros", act, avgpool="only")
-    assert torch.equal(y0, y1) and torch.equal(p0, p1) and torch.equal(p0, p2)
-    ref = F.avg_pool2d(y0, 2, 2)
-    assert float((p1 - ref).abs().max()) <= 1e-6 * max(1.0, float(ref.abs().max()))
-    conv.check_overflow()
