@@ -97,6 +97,83 @@ __global__ void __launch_bounds__(256) gauss1d_kernel(const float* __restrict__ 
     out[(size_t)blockIdx.y * plane + p] = acc * norm;
 }
 
+// Fast path for a compile-time radius (sigma = 5 -> 20, the recipe's call): the generic kernel above issues 2R+1 global loads with a
+// reflected index each per output (~330 instructions per pixel).  Here the 2R+1 weights live in registers (full unroll) and
+//   * along y: a thread owns one column and GR consecutive output rows; every input row r it loads (GR + 2R loads for GR outputs) is
+//     added to all outputs it reaches -- in ascending r, i.e. in the generic kernel's tap order: the results are bit-identical;
+//   * along x: a block stages its row segment (+ R on each side, reflected) in shared memory once, a thread owns GX consecutive
+//     outputs and walks the GX + 2R staged values the same way.
+constexpr int GR = 16, GX = 4, GAUSS_XT = 256;
+
+template <int R>
+__device__ __forceinline__ void gauss_weights(float sigma, float* w, float& norm) {       // same arithmetic as the generic kernel
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i <= 2 * R; ++i) {
+        const int d = i < R ? R - i : i - R;
+        w[i] = expf(-0.5f * (float)(d * d) / (sigma * sigma));
+    }
+#pragma unroll
+    for (int i = 0; i <= 2 * R; ++i) s += w[i];
+    norm = 1.f / s;
+}
+
+template <int R>
+__global__ void __launch_bounds__(128) gauss_y_fast_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                           float sigma) {
+    float w[2 * R + 1], norm;
+    gauss_weights<R>(sigma, w, norm);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const int y0 = blockIdx.y * GR;
+    const size_t plane = (size_t)H * W;
+    const float* src = in + (size_t)blockIdx.z * plane + x;
+    float acc[GR];
+#pragma unroll
+    for (int j = 0; j < GR; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < GR + 2 * R; ++rr) {                       // input row y0 - R + rr reaches outputs j with |rr - R - j| <= R
+        const float v = __ldg(src + (size_t)reflect_idx(y0 - R + rr, H) * W);
+#pragma unroll
+        for (int j = 0; j < GR; ++j) {
+            if (rr - j >= 0 && rr - j <= 2 * R) acc[j] = fmaf(v, w[rr - j], acc[j]);     // tap t = rr - j - R, ascending in rr
+        }
+    }
+    float* dst = out + (size_t)blockIdx.z * plane + x;
+#pragma unroll
+    for (int j = 0; j < GR; ++j)
+        if (y0 + j < H) dst[(size_t)(y0 + j) * W] = acc[j] * norm;
+}
+
+template <int R>
+__global__ void __launch_bounds__(GAUSS_XT / GX) gauss_x_fast_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                                    float sigma) {
+    __shared__ float seg[GAUSS_XT + 2 * R];
+    float w[2 * R + 1], norm;
+    gauss_weights<R>(sigma, w, norm);
+    const int x0 = blockIdx.x * GAUSS_XT, y = blockIdx.y;
+    const size_t plane = (size_t)H * W;
+    const float* src = in + (size_t)blockIdx.z * plane + (size_t)y * W;
+    for (int i = threadIdx.x; i < GAUSS_XT + 2 * R; i += blockDim.x) seg[i] = __ldg(src + reflect_idx(x0 - R + i, W));
+    __syncthreads();
+    const int xo = threadIdx.x * GX;
+    float acc[GX];
+#pragma unroll
+    for (int j = 0; j < GX; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < GX + 2 * R; ++rr) {
+        const float v = seg[xo + rr];
+#pragma unroll
+        for (int j = 0; j < GX; ++j) {
+            if (rr - j >= 0 && rr - j <= 2 * R) acc[j] = fmaf(v, w[rr - j], acc[j]);
+        }
+    }
+    float* dst = out + (size_t)blockIdx.z * plane + (size_t)y * W + x0 + xo;
+#pragma unroll
+    for (int j = 0; j < GX; ++j)
+        if (x0 + xo + j < W) dst[j] = acc[j] * norm;
+}
+
 // ---- exact k x k median (rank k*k/2, window [i - k/2, i + k - k/2 - 1], reflect) -------------------------
 // Order statistics must be exact (scipy's rank filter), so no histogram approximation.
 //
@@ -355,6 +432,13 @@ extern "C" int fvfi_gaussian_filter(const float* in, float* out, float* tmp, int
     const size_t plane = (size_t)H * W;
     dim3 grid((unsigned)((plane + 255) / 256), N);
     // scipy filters axis 0 (rows, i.e. along y) first, then axis 1
+    if (radius == 20 && H > 20 && W > 20) {            // the recipe's sigma = 5: register-weight kernels (bit-identical to the generic ones)
+        gauss_y_fast_kernel<20><<<dim3(ceil_div(W, 128), ceil_div(H, GR), N), 128, 0, (cudaStream_t)stream>>>(in, tmp, H, W, sigma);
+        FVFI_LAUNCH_CHECK();
+        gauss_x_fast_kernel<20><<<dim3(ceil_div(W, GAUSS_XT), H, N), GAUSS_XT / GX, 0, (cudaStream_t)stream>>>(tmp, out, H, W, sigma);
+        FVFI_LAUNCH_CHECK();
+        return FVFI_OK;
+    }
     gauss1d_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, tmp, H, W, sigma, radius);
     FVFI_LAUNCH_CHECK();
     gauss1d_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(tmp, out, H, W, sigma, radius);
