@@ -394,7 +394,7 @@ int adacof_tma_launch(const float* in1, const float* in2, const float* w1, const
                       const float* w2, const float* a2, const float* b2, const float* occ, float* t1, float* t2,
                       float* frame, float* mask, int nframes, int B, int Hin, int Win, int H, int W, int F, int dil,
                       cudaStream_t s, int* handled, const float* bwd_gout = nullptr, float* bwd_gw = nullptr,
-                      float* bwd_goi = nullptr, float* bwd_goj = nullptr);
+                      float* bwd_goi = nullptr, float* bwd_goj = nullptr, int out_rows = 0);
 
 }  // namespace fvfi
 
@@ -493,6 +493,21 @@ extern "C" int fvfi_adacofnet_tail(const float* t1, const float* t2, const float
     adacofnet_tail_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t1, t2, occ, w1, a1, b1, w2, a2, b2, frame, mask,
                                                                   C, plane, FF);
     FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
+
+extern "C" int fvfi_adacofnet_warp_blend_rows(const float* in1, const float* in2, const float* w1, const float* a1,
+                                              const float* b1, const float* w2, const float* a2, const float* b2,
+                                              const float* occ, float* frame, float* mask, int out_rows, int B, int Hin, int Win,
+                                              int H, int W, int F, int dilation, void* stream) {
+    if (int rc = check_dims(B, 3, Hin, Win, H, W, F, dilation)) return rc;
+    FVFI_CHECK_ARG(in1 && in2 && w1 && a1 && b1 && w2 && a2 && b2 && occ && frame, "adacofnet_warp_blend_rows: null pointer");
+    FVFI_CHECK_ARG(out_rows > 0 && out_rows <= H, "adacofnet_warp_blend_rows: out_rows must be in [1, H]");
+    int handled = 0;
+    if (int rc = adacof_tma_launch(in1, in2, w1, a1, b1, w2, a2, b2, occ, nullptr, nullptr, frame, mask, 2, B, Hin, Win, H, W, F,
+                                   dilation, (cudaStream_t)stream, &handled, nullptr, nullptr, nullptr, nullptr, out_rows))
+        return rc;
+    FVFI_CHECK_ARG(handled, "adacofnet_warp_blend_rows: needs the TMA-streamed kernel (F = 5, dilation 1, W %% 4 == 0, 16-byte aligned maps)");
     return FVFI_OK;
 }
 

@@ -46,6 +46,7 @@ struct TmaArgs {
     float* goj;
     int Hin, Win, H, W;
     int tiles_x, tiles_y, ntiles;
+    int out_rows;              // rows of the OUTPUT planes t / frame / mask (<= H: the /32 padding rows are not written), plane = out_rows * W
 };
 
 __device__ __forceinline__ unsigned xs_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -112,7 +113,7 @@ adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ 
     unsigned long long* empty = full + XSTAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t plane = (size_t)A.H * A.W, plane_in = (size_t)A.Hin * A.Win;
+    const size_t plane = (size_t)A.H * A.W, plane_in = (size_t)A.Hin * A.Win, oplane = (size_t)A.out_rows * A.W;
     if (threadIdx.x == 0) {
         for (int s = 0; s < XSTAGES; ++s) { xbar_init(&full[s], 1); xbar_init(&empty[s], XH); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -256,27 +257,28 @@ adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) xbar_arrive(&empty[s]);          // this warp is done with the stage
             }
-            if (!BWD && live) {
+            const bool live_out = live && gi < A.out_rows;        // p = gi * W + gj also indexes the (shorter) output planes
+            if (!BWD && live_out) {
                 float* const t = A.t[f];
                 if (t) {
-                    st_stream(t + ((size_t)T.n * 3 + 0) * plane + p, acc0);
-                    st_stream(t + ((size_t)T.n * 3 + 1) * plane + p, acc1);
-                    st_stream(t + ((size_t)T.n * 3 + 2) * plane + p, acc2);
+                    st_stream(t + ((size_t)T.n * 3 + 0) * oplane + p, acc0);
+                    st_stream(t + ((size_t)T.n * 3 + 1) * oplane + p, acc1);
+                    st_stream(t + ((size_t)T.n * 3 + 2) * oplane + p, acc2);
                 }
             }
             if (NFRAMES == 2) {
                 const float var = (s2i - s1i * s1i * (2.f - s0)) + (s2j - s1j * s1j * (2.f - s0));
                 if (f == 0) {
                     keep0 = acc0; keep1 = acc1; keep2 = acc2; keepv = var;
-                } else if (live) {
+                } else if (live_out) {
                     if (A.frame) {  // fusion_adacofnet.py:198
                         const float o = ld_stream(A.occ + (size_t)T.n * plane + p);
-                        st_stream(A.frame + ((size_t)T.n * 3 + 0) * plane + p, o * keep0 + (1.f - o) * acc0);
-                        st_stream(A.frame + ((size_t)T.n * 3 + 1) * plane + p, o * keep1 + (1.f - o) * acc1);
-                        st_stream(A.frame + ((size_t)T.n * 3 + 2) * plane + p, o * keep2 + (1.f - o) * acc2);
+                        st_stream(A.frame + ((size_t)T.n * 3 + 0) * oplane + p, o * keep0 + (1.f - o) * acc0);
+                        st_stream(A.frame + ((size_t)T.n * 3 + 1) * oplane + p, o * keep1 + (1.f - o) * acc1);
+                        st_stream(A.frame + ((size_t)T.n * 3 + 2) * oplane + p, o * keep2 + (1.f - o) * acc2);
                     }
                     if (A.mask)  // fusion_adacofnet.py:211-213
-                        st_stream(A.mask + (size_t)T.n * plane + p, fminf(fmaxf(fmaxf(keepv, var), 0.f), 20.f) / 20.f);
+                        st_stream(A.mask + (size_t)T.n * oplane + p, fminf(fmaxf(fmaxf(keepv, var), 0.f), 20.f) / 20.f);
                 }
             }
         }
@@ -330,7 +332,7 @@ int adacof_tma_launch(const float* in1, const float* in2, const float* w1, const
                       const float* w2, const float* a2, const float* b2, const float* occ, float* t1, float* t2,
                       float* frame, float* mask, int nframes, int B, int Hin, int Win, int H, int W, int F, int dil,
                       cudaStream_t s, int* handled, const float* bwd_gout = nullptr, float* bwd_gw = nullptr,
-                      float* bwd_goi = nullptr, float* bwd_goj = nullptr) {
+                      float* bwd_goi = nullptr, float* bwd_goj = nullptr, int out_rows = 0) {
     *handled = 0;
     if (F != XF || dil != 1 || (W & 3) || !aligned16(w1) || !aligned16(a1) || !aligned16(b1)) return FVFI_OK;
     if (nframes == 2 && (!aligned16(w2) || !aligned16(a2) || !aligned16(b2))) return FVFI_OK;
@@ -345,6 +347,7 @@ int adacof_tma_launch(const float* in1, const float* in2, const float* w1, const
     A.in[0] = in1; A.in[1] = in2; A.occ = occ; A.t[0] = t1; A.t[1] = t2; A.frame = frame; A.mask = mask;
     A.gout = bwd_gout; A.gw = bwd_gw; A.goi = bwd_goi; A.goj = bwd_goj;
     A.Hin = Hin; A.Win = Win; A.H = H; A.W = W;
+    A.out_rows = (out_rows > 0 && out_rows < H) ? out_rows : H;
     A.tiles_x = ceil_div(W, XW);
     A.tiles_y = ceil_div(H, XH);
     const long long nt = (long long)A.tiles_x * A.tiles_y * B;

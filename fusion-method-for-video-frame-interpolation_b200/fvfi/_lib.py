@@ -33,6 +33,7 @@ _PROTOS = {
     "fvfi_adacof_backward": (c_int, [c_fp] * 9 + [c_int] * 10 + [c_fp]),
     "fvfi_adacofnet_tail": (c_int, [c_fp] * 11 + [c_int] * 5 + [c_fp]),
     "fvfi_adacofnet_warp_blend": (c_int, [c_fp] * 13 + [c_int] * 7 + [c_fp]),
+    "fvfi_adacofnet_warp_blend_rows": (c_int, [c_fp] * 11 + [c_int] * 8 + [c_fp]),
     "fvfi_fusion_blend": (c_int, [c_fp] * 3 + [c_size, c_fp]),
     "fvfi_rgb2lab": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_fp]),
     "fvfi_lab2rgb": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_fp]),

@@ -250,6 +250,12 @@ class AdaCoFNet(torch.nn.Module):
                                                       B, h0, w0, hp, wp, k, ctypes.cast(mean, ctypes.c_void_p),
                                                       _lib.stream_ptr()))
         W1, A1, B1, W2, A2, B2, Occ = self.get_kernel._forward_tc_x(x)
+        if not return_warped and wp == w0 and hp != h0:
+            # only rows were padded: the kernel writes the h0 rows of the result directly (no crop copies)
+            r = adacof.adacofnet_warp_blend_rows(p0, p2, W1.contiguous(), A1.contiguous(), B1.contiguous(), W2.contiguous(),
+                                                 A2.contiguous(), B2.contiguous(), Occ.contiguous(), self.dilation, h0)
+            if r is not None:
+                return None, None, r[0], r[1]
         t1, t2, frame1, mask = adacof.adacofnet_warp_blend(p0, p2, W1.contiguous(), A1.contiguous(), B1.contiguous(),
                                                            W2.contiguous(), A2.contiguous(), B2.contiguous(),
                                                            Occ.contiguous(), self.dilation, want_t=return_warped)

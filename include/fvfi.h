@@ -88,6 +88,14 @@ int fvfi_adacofnet_warp_blend(const float* in1, const float* in2, const float* w
                               const float* occ, float* t1, float* t2, float* frame, float* mask, int B,
                               int Hin, int Win, int H, int W, int F, int dilation, void* stream);
 
+/* Same synthesis for frames that were reflect-padded at the bottom to a multiple of 32 rows (fusion_adacofnet.py:179-188, 214-226: the
+ * reference crops the result back): frame [B,3,out_rows,W] and mask [B,1,out_rows,W] (mask may be NULL) receive only the first out_rows
+ * rows, so the crop copies never happen; no warped frames are returned.  Needs the TMA-streamed kernel (F = 5, dilation 1, W % 4 == 0,
+ * 16-byte aligned coefficient maps), FVFI_EINVAL otherwise. */
+int fvfi_adacofnet_warp_blend_rows(const float* in1, const float* in2, const float* w1, const float* a1, const float* b1,
+                                   const float* w2, const float* a2, const float* b2, const float* occ, float* frame, float* mask,
+                                   int out_rows, int B, int Hin, int Win, int H, int W, int F, int dilation, void* stream);
+
 /* FusionNet's last step (src/fusion_net/fusion_net.py:67-77): out = clamp(base + tanh(x), 0, 1). */
 int fvfi_fusion_blend(const float* base, const float* x_pre_tanh, float* out, size_t n, void* stream);
 

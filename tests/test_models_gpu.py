@@ -563,3 +563,20 @@ def test_fusion_trainer_steps_are_bit_reproducible():
     assert all(torch.equal(a, b) for a, b in zip(g1, g2))
     assert all(np.isfinite(v) for v in l1) and l1[-1] < l1[0]
     assert float(g1[0].abs().max()) > 0
+
+
+def test_adacofnet_row_cropped_synthesis_matches_crop():
+    """Frames whose height is not a multiple of 32 but whose width is (1080p: 1080 -> 1088 rows): the fused synthesis writes the unpadded
+    rows itself (fvfi_adacofnet_warp_blend_rows) -- frame and uncertainty mask bit-identical to synthesis on the padded size + crop."""
+    import types
+    from fvfi.adacofnet import AdaCoFNet
+    state = fp.seeded_state(8)
+    net = AdaCoFNet(types.SimpleNamespace(kernel_size=5, dilation=1, gpu_id=0)).cuda().eval()
+    net.load_state_dict(state["adacof"])
+    g = torch.Generator().manual_seed(8)
+    f0, f2 = torch.rand((2, 3, 70, 96), generator=g).cuda(), torch.rand((2, 3, 70, 96), generator=g).cuda()
+    with torch.no_grad():
+        _, _, fa, ma = net(f0, f2, return_warped=False)        # rows written directly
+        t1, t2, fb, mb = net(f0, f2, return_warped=True)       # padded synthesis, cropped afterwards
+    assert fa.shape == (2, 3, 70, 96) and ma.shape == (2, 1, 70, 96) and fa.is_contiguous()
+    assert torch.equal(fa, fb) and torch.equal(ma, mb)
