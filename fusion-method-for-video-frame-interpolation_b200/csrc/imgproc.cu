@@ -743,6 +743,55 @@ extern "C" int fvfi_phasenet_outputs(const float* pred, int pred_pixel_stride, c
     return FVFI_OK;
 }
 
+// torch.cat of planar [B,c_s,H,W] tensors along the channels, written as ONE NHWC tensor (FusionNet's input,
+// src/fusion_net/fusion_net.py:47: cat([base, adacof, phase, other, maps], 1)): a thread owns a pixel, reads its NQ*4 channel planes
+// (coalesced across the warp) and stores the record as NQ 128-bit words; channels beyond the concatenation are written as zeros.
+namespace fvfi {
+struct ConcatTable {
+    const float* ptr[32];        // plane 0 of the source that supplies channel j (null: zero)
+    unsigned long long bstride[32];   // floats between consecutive batch items of that source
+};
+template <int NQ>
+__global__ void __launch_bounds__(256) planar_concat_nhwc_kernel(const ConcatTable T, float* __restrict__ y, size_t plane, int ldy) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= plane) return;
+    const int b = blockIdx.y;
+    float v[4 * NQ];
+#pragma unroll
+    for (int j = 0; j < 4 * NQ; ++j) v[j] = T.ptr[j] ? ld_stream(T.ptr[j] + (size_t)b * T.bstride[j] + p) : 0.f;
+    float4* dst = reinterpret_cast<float4*>(y + ((size_t)b * plane + p) * ldy);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+}  // namespace fvfi
+
+extern "C" int fvfi_planar_concat_nhwc(const float* const* sources, const int* channels, int nsources, float* y, int y_pixel_stride,
+                                       int B, int H, int W, void* stream) {
+    FVFI_CHECK_ARG(sources && channels && nsources > 0 && y && B > 0 && H > 0 && W > 0 && B <= 65535, "planar_concat_nhwc: bad argument");
+    fvfi::ConcatTable T{};
+    const size_t plane = (size_t)H * W;
+    int C = 0;
+    for (int s = 0; s < nsources; ++s) {
+        FVFI_CHECK_ARG(sources[s] && channels[s] > 0 && C + channels[s] <= 32, "planar_concat_nhwc: null source or more than 32 channels");
+        for (int c = 0; c < channels[s]; ++c, ++C) {
+            T.ptr[C] = sources[s] + (size_t)c * plane;
+            T.bstride[C] = (unsigned long long)channels[s] * plane;
+        }
+    }
+    const int nq = (C + 3) / 4;
+    FVFI_CHECK_ARG((y_pixel_stride % 4) == 0 && y_pixel_stride >= 4 * nq && (((size_t)y) & 15) == 0,
+                   "planar_concat_nhwc: y needs a pixel stride that is a multiple of 4 and >= the channel count rounded up to 4, 16-byte aligned");
+    dim3 grid((unsigned)((plane + 255) / 256), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nq) {
+#define FVFI_PC(N) case N: fvfi::planar_concat_nhwc_kernel<N><<<grid, 256, 0, st>>>(T, y, plane, y_pixel_stride); break;
+        FVFI_PC(1) FVFI_PC(2) FVFI_PC(3) FVFI_PC(4) FVFI_PC(5) FVFI_PC(6) FVFI_PC(7) FVFI_PC(8)
+#undef FVFI_PC
+    }
+    FVFI_LAUNCH_CHECK();
+    return FVFI_OK;
+}
+
 extern "C" int fvfi_nchw_to_nhwc_slice(const float* x, float* y, int y_pixel_stride, int B, int C, int H, int W, void* stream) {
     FVFI_CHECK_ARG(x && y && B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535 && y_pixel_stride >= C, "nchw_to_nhwc_slice: bad argument");
     const size_t plane = (size_t)H * W;

@@ -55,6 +55,7 @@ _PROTOS = {
     "fvfi_avg_pool2_backward_nhwc": (c_int, [c_fp, c_int, c_fp, c_int] + [c_int] * 4 + [c_fp]),
     "fvfi_resize_bilinear_backward_nhwc": (c_int, [c_fp, c_int, c_fp, c_int, c_fp, c_int] + [c_int] * 8 + [c_fp]),
     "fvfi_fusion_blend_backward": (c_int, [c_fp] * 5 + [c_size, c_fp]),
+    "fvfi_planar_concat_nhwc": (c_int, [c_fp, c_fp, c_int, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "fvfi_nchw_to_nhwc_slice": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "fvfi_conv1x1_nhwc": (c_int, [c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_size, c_int, c_int, c_int, c_fp]),
     "fvfi_upsample2_tapsum": (c_int, [c_fp, c_int, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),

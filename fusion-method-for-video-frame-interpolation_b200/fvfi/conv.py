@@ -351,6 +351,24 @@ def resize_bilinear(x, size, align_corners, out=None, out_channel_offset=0, relu
     return out
 
 
+def planar_concat_nhwc(tensors):
+    """torch.cat(tensors, 1) of contiguous planar [B,c,H,W] tensors as ONE channels_last tensor with the channel count rounded up to 4
+    (zeros), written by one kernel (fvfi_planar_concat_nhwc): returns [B, round4(sum c), H, W]."""
+    import ctypes
+    B, _, H, W = tensors[0].shape
+    ts = [t.contiguous().float() for t in tensors]
+    assert all(t.is_cuda and t.shape[0] == B and tuple(t.shape[2:]) == (H, W) for t in ts)
+    C = sum(int(t.shape[1]) for t in ts)
+    C4 = (C + 3) // 4 * 4
+    out = torch.empty((B, C4, H, W), dtype=torch.float32, device=ts[0].device, memory_format=torch.channels_last)
+    ptrs = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    chans = (ctypes.c_int * len(ts))(*[int(t.shape[1]) for t in ts])
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().fvfi_planar_concat_nhwc(ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(chans, ctypes.c_void_p), len(ts),
+                                                      out.data_ptr(), out.stride(3), B, H, W, _lib.stream_ptr()))
+    return out
+
+
 def put_planar(x, out, out_channel_offset):
     """out[:, off:off+C] = x for a contiguous planar x [B,C,H,W] and a channels_last ``out`` (one kernel, no temporaries)."""
     B, C, H, W = x.shape

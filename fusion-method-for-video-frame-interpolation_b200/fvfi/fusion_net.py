@@ -90,14 +90,18 @@ class FusionNet(torch.nn.Module):
         ``Upsample(ReLU(x)) + skip`` and the final ``clamp(base + tanh)`` are the fused NHWC kernels; under autograd each of them is
         an autograd Function whose backward is a libfvfi kernel too (csrc/conv_bwd.cu) -- no ATen convolution / pooling /
         interpolation kernel runs in the training step of the trained network."""
-        x = torch.cat([base, adacof, phase, other, maps], 1)
-        if not x.is_cuda:
+        parts = [base, adacof, phase, other, maps]
+        if not all(t.is_cuda for t in parts):
             raise NotImplementedError("fvfi FusionNet runs on CUDA tensors only (no CPU fallback)")
-        grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.live_parameters()))
+        grad = torch.is_grad_enabled() and (any(t.requires_grad for t in parts) or any(p.requires_grad for p in self.live_parameters()))
         skip = []
-        if grad and x.shape[1] % 4:        # zero channels up to a multiple of 4: the weight-gradient kernel then reads float4 pixel quads
-            x = nn.functional.pad(x, (0, 0, 0, 0, 0, 4 - x.shape[1] % 4))
-        x = tc.to_nhwc(x)
+        if grad or sum(int(t.shape[1]) for t in parts) > 32:
+            x = torch.cat(parts, 1)
+            if x.shape[1] % 4:             # zero channels up to a multiple of 4: the weight-gradient kernel then reads float4 pixel quads
+                x = nn.functional.pad(x, (0, 0, 0, 0, 0, 4 - x.shape[1] % 4))
+            x = tc.to_nhwc(x)
+        else:                              # the concatenation written NHWC (18 -> 20 channels) by one kernel: no planar cat, no transposing copy
+            x = tc.planar_concat_nhwc(parts)
         for layer in self.encoder_layers:
             x = tc.conv_module(layer, x, "relu")                          # fusion_net.py:52-56
             skip.append(x)

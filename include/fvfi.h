@@ -264,6 +264,14 @@ int fvfi_max_pool2_nhwc(const float* x, int x_pixel_stride, float* y, int y_pixe
  * channel slice): PhaseNet's concat of phase / amplitude planes with NHWC features (src/phase_net/phase_net.py:141). */
 int fvfi_nchw_to_nhwc_slice(const float* x, float* y, int y_pixel_stride, int B, int C, int H, int W, void* stream);
 
+/* torch.cat(sources, dim=1) of planar tensors [B,channels[s],H,W] written as ONE NHWC tensor y [B,H,W,y_pixel_stride] (FusionNet's
+ * input, src/fusion_net/fusion_net.py:47: cat([base, adacof, phase, other, maps], 1), which the tensor-core convolution wants NHWC): the
+ * concatenated planar tensor and its transposing copy never exist.  sources / channels: HOST arrays of nsources device pointers / channel
+ * counts (at most 32 channels in total); channels between the total and its multiple of 4 are written as zeros; y_pixel_stride a multiple
+ * of 4 that covers them, y 16-byte aligned. */
+int fvfi_planar_concat_nhwc(const float* const* sources, const int* channels, int nsources, float* y, int y_pixel_stride, int B, int H,
+                            int W, void* stream);
+
 /* Host-buffer variants for end-to-end timing: pointers are HOST memory (pinned preferred);
  * the call does H2D, the kernel(s), D2H and synchronises. */
 int fvfi_adacof_forward_host(const float* input, const float* weight, const float* off_i, const float* off_j,

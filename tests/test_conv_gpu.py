@@ -449,3 +449,17 @@ def test_fusion_blend_backward_matches_torch():
     ob.backward(gout.double())
     assert float((oa.detach().double() - ob.detach()).abs().max()) <= 2e-6
     assert float((xa.grad.double() - xb.grad).abs().max()) <= 1e-5 and float((ba.grad.double() - bb.grad).abs().max()) <= 1e-6
+
+
+def test_planar_concat_nhwc_matches_cat():
+    """fvfi_planar_concat_nhwc == torch.cat(..., 1) padded with zero channels to a multiple of 4, stored channels_last (FusionNet's input,
+    fusion_net.py:47)."""
+    from fvfi import conv
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for chans, (B, H, W) in (((3, 3, 3, 6, 3), (2, 30, 44)), ((1,), (1, 5, 7)), ((8, 8, 16), (3, 16, 16)), ((5, 2), (1, 33, 19))):
+        parts = [torch.randn((B, c, H, W), device="cuda", generator=g) for c in chans]
+        out = conv.planar_concat_nhwc(parts)
+        C = sum(chans)
+        ref = torch.cat(parts, 1)
+        assert out.shape == (B, (C + 3) // 4 * 4, H, W) and out.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(out[:, :C], ref) and float(out[:, C:].abs().sum()) == 0.0
