@@ -1,5 +1,5 @@
 """Same-process A/B of a boolean switch of fvfi.conv on one pipeline call (1080p, B frame pairs), alternating:
-    python tools/ab_switch.py fuse_avgpool [B] [rounds] [value ...]"""
+    python tools/ab_switch.py fuse_upsample [B] [rounds] [value ...]"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
