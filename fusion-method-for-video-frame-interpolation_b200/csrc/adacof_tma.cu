@@ -97,7 +97,9 @@ __device__ __forceinline__ XTile x_tile(const TmaArgs& A, int tile) {
 }
 
 // NFRAMES: 1 = forward, 2 = fused two-frame synthesis, 0 = fused backward (gW, g_alpha, g_beta from one gather; algebra in adacof.cu)
-template <int NFRAMES, int XSTAGES, int MINB>
+// STATS (NFRAMES == 2): accumulate the offset moments of both frames for the flow-variance mask; false when the caller passes no mask
+// (the recipe's three baseline passes use the synthesised frame only, src/fusion_net/interpolate_twoframe.py:228-238)
+template <int NFRAMES, int XSTAGES, int MINB, bool STATS = true>
 __global__ void __launch_bounds__(XTHREADS, MINB)
 adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ CUtensorMap ma0,
                const __grid_constant__ CUtensorMap mb0, const __grid_constant__ CUtensorMap mw1,
@@ -246,7 +248,7 @@ adacof_fwd_tma(const __grid_constant__ CUtensorMap mw0, const __grid_constant__ 
                         acc1 = fmaf(w, v00.y * w00 + v10.y * w10 + v01.y * w01 + v11.y * w11, acc1);
                         acc2 = fmaf(w, v00.z * w00 + v10.z * w10 + v01.z * w01 + v11.z * w11, acc2);
                     }
-                    if (NFRAMES == 2) {
+                    if (NFRAMES == 2 && STATS) {
                         s0 += w;
                         s1i = fmaf(w, al, s1i);
                         s2i = fmaf(w * al, al, s2i);
@@ -354,16 +356,17 @@ int adacof_tma_launch(const float* in1, const float* in2, const float* w1, const
     if (nt > 0x7fffffffLL) return FVFI_OK;
     A.ntiles = (int)nt;
     const int nsm = sm_count() > 0 ? sm_count() : 148;
-#define FVFI_TMA_LAUNCH(NF, ST, MB)                                                                                       \
+#define FVFI_TMA_LAUNCH(NF, ST, MB, ...)                                                                                  \
     {                                                                                                                     \
         const size_t smem = (size_t)ST * XSTAGE_FLOATS * sizeof(float) + 2 * XREGION_BYTES + 128;                        \
         const unsigned grid = (unsigned)std::min<long long>(nt, (long long)MB * nsm);                                    \
-        FVFI_SMEM_OPT_IN((adacof_fwd_tma<NF, ST, MB>), smem);                                                             \
-        adacof_fwd_tma<NF, ST, MB><<<grid, XTHREADS, smem, s>>>(mw0, ma0, mb0, mw1, ma1, mb1, A);                       \
+        FVFI_SMEM_OPT_IN((adacof_fwd_tma<NF, ST, MB, ##__VA_ARGS__>), smem);                                              \
+        adacof_fwd_tma<NF, ST, MB, ##__VA_ARGS__><<<grid, XTHREADS, smem, s>>>(mw0, ma0, mb0, mw1, ma1, mb1, A);        \
     }
     if (nframes == 0) FVFI_TMA_LAUNCH(0, 3, 2) else
     // measured (tools/prof_adacof.py): the single warp is fastest with a 3-deep ring and 2 CTAs/SM, the fused synthesis (more
     // arithmetic per byte: moments, blend) with a 2-deep ring and 3 CTAs/SM (67 KB each, 72 registers)
+    if (nframes == 2 && !mask) FVFI_TMA_LAUNCH(2, 2, 3, false) else
     if (nframes == 2) FVFI_TMA_LAUNCH(2, 2, 3) else FVFI_TMA_LAUNCH(1, 3, 2)
 #undef FVFI_TMA_LAUNCH
     FVFI_LAUNCH_CHECK();

@@ -113,10 +113,11 @@ def adacofnet_warp_blend(frame0_padded, frame2_padded, Weight1, Alpha1, Beta1, W
 
 
 def adacofnet_warp_blend_rows(frame0_padded, frame2_padded, Weight1, Alpha1, Beta1, Weight2, Alpha2, Beta2, Occlusion, dilation,
-                              out_rows):
+                              out_rows, want_mask=True):
     """``adacofnet_warp_blend(...)[2:]`` cropped to the first ``out_rows`` rows by the kernel itself (the frames were reflect-padded at
     the bottom to a multiple of 32, fusion_adacofnet.py:179-188): returns (frame1 [B,3,out_rows,W], mask [B,1,out_rows,W]) or None
-    when the shape is not one the TMA-streamed kernel takes."""
+    when the shape is not one the TMA-streamed kernel takes.  ``want_mask=False``: mask is None and the kernel skips the offset
+    moments (the recipe's baseline passes use the frame only)."""
     B, C, Hin, Win, H, W, F = _geometry(frame0_padded, Weight1, dilation)
     if C != 3 or F != 5 or int(dilation) != 1 or W % 4 or not (0 < out_rows <= H):
         return None
@@ -126,11 +127,11 @@ def adacofnet_warp_blend_rows(frame0_padded, frame2_padded, Weight1, Alpha1, Bet
     for t in (frame0_padded, frame2_padded, Occlusion) + maps:
         assert t.is_contiguous() and t.is_cuda and t.dtype == torch.float32
     frame = torch.empty((B, 3, out_rows, W), dtype=torch.float32, device=Weight1.device)
-    mask = torch.empty((B, 1, out_rows, W), dtype=torch.float32, device=Weight1.device)
+    mask = torch.empty((B, 1, out_rows, W), dtype=torch.float32, device=Weight1.device) if want_mask else None
     with torch.cuda.device(Weight1.device):
         _lib.check(_lib.lib().fvfi_adacofnet_warp_blend_rows(
             frame0_padded.data_ptr(), frame2_padded.data_ptr(), Weight1.data_ptr(), Alpha1.data_ptr(), Beta1.data_ptr(),
-            Weight2.data_ptr(), Alpha2.data_ptr(), Beta2.data_ptr(), Occlusion.data_ptr(), frame.data_ptr(), mask.data_ptr(),
+            Weight2.data_ptr(), Alpha2.data_ptr(), Beta2.data_ptr(), Occlusion.data_ptr(), frame.data_ptr(), _lib.ptr(mask),
             int(out_rows), B, Hin, Win, H, W, F, int(dilation), _lib.stream_ptr()))
     return frame, mask
 

@@ -232,7 +232,7 @@ class AdaCoFNet(torch.nn.Module):
         self.modulePad = torch.nn.ReplicationPad2d([self.kernel_pad] * 4)
         self.moduleAdaCoF = adacof.FunctionAdaCoF.apply
 
-    def _forward_fused_prep(self, frame0, frame2, return_warped):
+    def _forward_fused_prep(self, frame0, frame2, return_warped, want_mask=True):
         """Inference form of lines 176-213: reflect pad / normalise / concat / NHWC and the replicate pad in ONE kernel
         (fvfi_adacofnet_prep), kernel estimation, fused two-warp synthesis."""
         import ctypes
@@ -253,7 +253,7 @@ class AdaCoFNet(torch.nn.Module):
         if not return_warped and wp == w0 and hp != h0:
             # only rows were padded: the kernel writes the h0 rows of the result directly (no crop copies)
             r = adacof.adacofnet_warp_blend_rows(p0, p2, W1.contiguous(), A1.contiguous(), B1.contiguous(), W2.contiguous(),
-                                                 A2.contiguous(), B2.contiguous(), Occ.contiguous(), self.dilation, h0)
+                                                 A2.contiguous(), B2.contiguous(), Occ.contiguous(), self.dilation, h0, want_mask)
             if r is not None:
                 return None, None, r[0], r[1]
         t1, t2, frame1, mask = adacof.adacofnet_warp_blend(p0, p2, W1.contiguous(), A1.contiguous(), B1.contiguous(),
@@ -270,13 +270,15 @@ class AdaCoFNet(torch.nn.Module):
         self.load_state_dict(state_dict)
 
     @tc.range_checked
-    def forward(self, frame0, frame2, return_warped=True):
+    def forward(self, frame0, frame2, return_warped=True, want_mask=True):
+        """fusion_adacofnet.py:172-240.  ``return_warped=False`` / ``want_mask=False`` (extensions, default = the reference's four
+        outputs): the two warped frames / the uncertainty mask are returned as None and not computed."""
         h0, w0 = int(frame0.shape[2]), int(frame0.shape[3])
         if h0 != int(frame2.shape[2]) or w0 != int(frame2.shape[3]):
             sys.exit('Frame sizes do not match')                                   # fusion_adacofnet.py:177-178
         if (tc.use_tc(frame0) and not self.training and frame0.shape[1] == 3 and frame0.dtype == torch.float32
                 and not (frame0.requires_grad or frame2.requires_grad)):
-            return self._forward_fused_prep(frame0, frame2, return_warped)
+            return self._forward_fused_prep(frame0, frame2, return_warped, want_mask)
         if h0 % 32 != 0:
             pad_h = 32 - (h0 % 32)
             frame0 = F.pad(frame0, (0, 0, 0, pad_h), mode='reflect')

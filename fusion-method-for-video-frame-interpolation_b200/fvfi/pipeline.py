@@ -224,12 +224,12 @@ class FusionPipeline(torch.nn.Module):
         # baseline (:228-238)
         if self.pair_baseline and 2 * B <= self.max_batch_adacof:
             # passes 2 and 3 (:229, :233) are independent: ONE AdaCoFNet call on a 2B batch (twice the tiles for the coarse layers)
-            inb = self.adacof(torch.cat((rgb1, phase_pred), 0), torch.cat((phase_pred, rgb2), 0), return_warped=False)[2]
+            inb = self.adacof(torch.cat((rgb1, phase_pred), 0), torch.cat((phase_pred, rgb2), 0), return_warped=False, want_mask=False)[2]
             inb1, inb2 = inb[:B], inb[B:]
         else:
-            inb1 = self.adacof(rgb1, phase_pred, return_warped=False)[2]
-            inb2 = self.adacof(phase_pred, rgb2, return_warped=False)[2]
-        base = self.adacof(inb1, inb2, return_warped=False)[2]
+            inb1 = self.adacof(rgb1, phase_pred, return_warped=False, want_mask=False)[2]
+            inb2 = self.adacof(phase_pred, rgb2, return_warped=False, want_mask=False)[2]
+        base = self.adacof(inb1, inb2, return_warped=False, want_mask=False)[2]
         self._tick('adacofnet#2-4')
         if fork:
             main.wait_stream(side)
