@@ -19,6 +19,9 @@
 //                                 CUDA cores on purpose: 62 GFLOP per training step in total, fp32-exact products, and the
 //                                 tensor-core form would need both operands pixel-major (MN-major tf32), which tcgen05's shared-memory
 //                                 descriptors do not offer without a transposing loader.
+//   fvfi_max_pool2_backward_nhwc / fvfi_avg_pool2_backward_nhwc / fvfi_resize_bilinear_backward_nhwc / fvfi_fusion_blend_backward
+//                                 adjoints of the other differentiable steps of FusionNet (src/fusion_net/fusion_net.py:52-77) and of
+//                                 KernelEstimation's pooling / Upsample modules (src/fusion_net/fusion_adacofnet.py:29-36,62-70).
 #include <algorithm>
 
 #include "common.cuh"
