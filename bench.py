@@ -146,13 +146,14 @@ class AdaCoFWorkload:
         return {
             "bound": "hbm", "kernel": "adacof_fwd_tma<1,3,2> (TMA-streamed coefficients; offsets ~ N(0, 3^2): the adversarial gather)", "achieved": round(ach_f, 1), "peak": peak,
             "unit": "GB/s", "frac": round(ach_f / peak, 4),
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, ncu --set full (profiles/r01_adacof_*):
-            # 5.39 GB per launch = the algorithmic bytes, i.e. every coefficient map is read from HBM exactly once
-            "traffic": 5.39e9, "peak_source": peak_src,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, ncu --set full on the final tree
+            # (profiles/r02_adacof_final_summary.txt): 5.395 + 0.200 GB per launch = 1.03 x the algorithmic bytes, i.e. every
+            # coefficient map is read from HBM exactly once; backward 5.620 + 4.970 GB = 1.02 x
+            "traffic": 5.595e9, "peak_source": peak_src,
             "ms_per_launch": round(fwd, 4), "algorithmic_bytes_per_launch": self.bytes_fwd,
             "other_kernels": [{"kernel": "adacof_fwd_tma<0,3,2> (fused backward: gW, g_alpha, g_beta; TMA-streamed coefficients)", "achieved": round(ach_b, 1),
                                "frac": round(ach_b / peak, 4), "ms_per_launch": round(bwd, 4),
-                               "algorithmic_bytes_per_launch": self.bytes_bwd}],
+                               "algorithmic_bytes_per_launch": self.bytes_bwd, "traffic": 10.590e9}],
         }
 
     def reference_gpu_kernels(self, steps=3):

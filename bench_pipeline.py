@@ -139,6 +139,7 @@ class PipelineWorkload:
         px = B * H * W
         i1, i2 = mk(B, 3, H + 4, W + 4), mk(B, 3, H + 4, W + 4)
         w1 = torch.softmax(mkn(B, 25, H, W), 1)
+        w2 = torch.softmax(mkn(B, 25, H, W), 1)
         occ = mk(B, 1, H, W)
         gout = mkn(B, 3, H, W)
         nb_syn = 4 * (6 * 25 * px + 2 * 3 * B * (H + 4) * (W + 4) + px + 3 * px + px)
@@ -149,18 +150,24 @@ class PipelineWorkload:
         for label, mkoff in (("smooth offsets U(-0.5,0.5)", lambda: mk(B, 25, H, W) - 0.5),
                              ("i.i.d. offsets N(0,3^2) clipped to +-16 (configs[1])", lambda: (3 * mkn(B, 25, H, W)).clamp_(-16, 16))):
             a1, b1 = mkoff(), mkoff()
-            ms = timeit(lambda: adacof.adacofnet_warp_blend(i1, i2, w1, a1, b1, w1, b1, a1, occ, 1, want_t=False))
+            # the second frame gets its OWN three coefficient tensors: nb_syn counts six maps, and re-using frame 1's would turn half of
+            # that into L2 hits (ncu, profiles/r02_adacof_final_summary.txt: 5.8 instead of 10.8 GB of DRAM traffic per launch)
+            a2, b2 = mkoff(), mkoff()
+            ms = timeit(lambda: adacof.adacofnet_warp_blend(i1, i2, w1, a1, b1, w2, a2, b2, occ, 1, want_t=False))
             out.append({"kernel": "adacof_fwd_tma<2,..> fused synthesis (two warps + blend + uncertainty), " + label, "bound": "hbm",
                         "achieved": round(nb_syn / ms / 1e6, 1), "unit": "GB/s", "frac": round(nb_syn / ms / 1e6 / peak, 4),
-                        "ms_per_launch": round(ms, 4), "algorithmic_bytes_per_launch": nb_syn})
+                        "ms_per_launch": round(ms, 4), "algorithmic_bytes_per_launch": nb_syn,
+                        "traffic": 10.925e9 if B == 8 else None})     # ncu dram bytes, profiles/r02_adacof_final_summary.txt
             ms = timeit(lambda: adacof.adacof_forward(i1, w1, a1, b1, 1))
             out.append({"kernel": "adacof_fwd_tma<1,..> warp forward (configs[1] shape B=8), " + label, "bound": "hbm",
                         "achieved": round(nb_fwd / ms / 1e6, 1), "unit": "GB/s", "frac": round(nb_fwd / ms / 1e6 / peak, 4),
-                        "ms_per_launch": round(ms, 4), "algorithmic_bytes_per_launch": nb_fwd})
+                        "ms_per_launch": round(ms, 4), "algorithmic_bytes_per_launch": nb_fwd,
+                        "traffic": 5.595e9 if B == 8 else None})      # ncu dram bytes, profiles/r02_adacof_final_summary.txt
             ms = timeit(lambda: adacof.adacof_backward(gout, i1, w1, a1, b1, 1, "none"))
             out.append({"kernel": "adacof_fwd_tma<0,..> fused backward gW/g_alpha/g_beta (configs[1] shape B=8), " + label, "bound": "hbm",
                         "achieved": round(nb_bwd / ms / 1e6, 1), "unit": "GB/s", "frac": round(nb_bwd / ms / 1e6 / peak, 4),
-                        "ms_per_launch": round(ms, 4), "algorithmic_bytes_per_launch": nb_bwd})
+                        "ms_per_launch": round(ms, 4), "algorithmic_bytes_per_launch": nb_bwd,
+                        "traffic": 10.590e9 if B == 8 else None})
             if label.startswith("i.i.d."):
                 try:     # same-box bar: the reference's own CUDA kernels on the same tensors (oracle/_ref cubins; evidence only)
                     from oracle import ref_kernels
@@ -171,8 +178,8 @@ class PipelineWorkload:
                                     "fwd_ms": round(f, 3), "bwd_ms": round(b, 3)})
                 except Exception as ex:
                     out.append({"kernel": "reference kernels", "error": repr(ex)[:160]})
-            del a1, b1
-        del i1, i2, w1, occ, gout
+            del a1, b1, a2, b2
+        del i1, i2, w1, w2, occ, gout
         torch.cuda.empty_cache()
         N = 12 * B
         x = mk(N, self.H, self.W)

@@ -16,6 +16,8 @@ gout = torch.randn((B, 3, H, W), device="cuda", generator=g)
 out = torch.empty((B, 3, H, W), device="cuda")
 a1, b1 = mk(B, 25, H, W) - 0.5, mk(B, 25, H, W) - 0.5
 occ = mk(B, 1, H, W)
+w2 = torch.softmax(torch.randn((B, 25, H, W), device="cuda", generator=g), 1)     # frame 2: its own coefficient tensors (no L2 re-use)
+a2, b2 = mk(B, 25, H, W) - 0.5, mk(B, 25, H, W) - 0.5
 def t(fn, reps=5):
     for _ in range(2): fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -30,7 +32,7 @@ bs = 4 * (150 * px + 6 * B * (H + 4) * (W + 4) + 5 * px)
 tf = t(lambda: adacof.adacof_forward(inp, w, oi, oj, 1, out=out))
 tfs = t(lambda: adacof.adacof_forward(inp, w, a1, b1, 1, out=out))
 tb = t(lambda: adacof.adacof_backward(gout, inp, w, oi, oj, 1, "none"))
-ts = t(lambda: adacof.adacofnet_warp_blend(inp, inp, w, a1, b1, w, b1, a1, occ, 1, want_t=False))
+ts = t(lambda: adacof.adacofnet_warp_blend(inp, inp, w, a1, b1, w2, a2, b2, occ, 1, want_t=False))
 print("fwd random  %.3f ms %.0f GB/s | fwd smooth %.3f ms %.0f GB/s | bwd random %.3f ms %.0f GB/s | fused smooth %.3f ms %.0f GB/s" %
       (tf, bf / tf / 1e6, tfs, bf / tfs / 1e6, tb, bb / tb / 1e6, ts, bs / ts / 1e6))
 # true gradInput (extension): warp-aggregated atomic scatter, on top of the gradient kernel
