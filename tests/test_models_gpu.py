@@ -404,6 +404,41 @@ def test_phasenet_forward_fused_matches_stepwise(H, W, chunk):
         assert float((pyr.inv_filter_sparse(out_m, use_high=False) - pyr.inv_filter(ref_m)).abs().max()) <= 2e-6
 
 
+@pytest.mark.parametrize("gain", [4.0, 0.37])
+def test_phasenet_output_is_invariant_to_the_input_gain(gain):
+    """SURVEY 8(c) invariant (v): normalize_vals divides every level by its own maximum and reverse_normalize multiplies it back
+    (src/phase_net/phase_net.py:42-78,80-105), so scaling the decomposed planes by a constant must leave the predicted phases
+    unchanged and scale the predicted amplitudes / low pass / reconstruction by exactly that constant (up to the eps = 1e-8 in
+    the denominators and fp32 rounding) -- through the GPU decomposition, the fused value plumbing, the tcgen05 convolutions and
+    the reconstruction."""
+    import math
+    from fvfi import utils
+    from fvfi.phase_net import PhaseNet
+    from fvfi.pyramid import Pyramid
+    torch.manual_seed(11)
+    H, W, P = 96, 128, 3
+    planes = torch.rand((2 * P, H, W), device="cuda")
+    height = utils.calc_pyr_height(planes)
+    pyr = Pyramid(height=height, nbands=4, scale_factor=math.sqrt(2), device=torch.device("cuda"))
+    net = PhaseNet(pyr, torch.device("cuda"), num_img=2).eval()
+    with torch.no_grad():
+        out1 = net.forward_fused(pyr.filter(planes, want_high=False), pyr.last_amp_max)
+        img1 = pyr.inv_filter_sparse(out1, use_high=False)
+        outg = net.forward_fused(pyr.filter(gain * planes, want_high=False), pyr.last_amp_max)
+        imgg = pyr.inv_filter_sparse(outg, use_high=False)
+    tol = 5e-6          # the eps in the denominators and fp32 rounding of the normalised network inputs (~1e-7) through the convolutions
+    for l in range(height - 2):
+        amax = float(out1.amplitude[l].abs().max())
+        assert float((outg.amplitude[l] - gain * out1.amplitude[l]).abs().max()) <= tol * gain * amax
+        # phases: compare where the amplitude is not negligible (atan2 of a rounding-level coefficient is arbitrary)
+        live = out1.amplitude[l] > 1e-3 * amax
+        d = (outg.phase[l] - out1.phase[l])[live]
+        d = torch.atan2(torch.sin(d), torch.cos(d))
+        assert float(d.abs().max()) <= 2e-4
+    assert float((outg.low_level - gain * out1.low_level).abs().max()) <= 1e-5 * gain * float(out1.low_level.abs().max())
+    assert float((imgg - gain * img1).abs().max()) <= 2e-5 * gain * float(img1.abs().max())
+
+
 @pytest.mark.parametrize("B,H,W", [(2, 40, 72), (1, 64, 96), (3, 33, 50)])
 def test_adacofnet_prep_kernel(B, H, W):
     """fvfi_adacofnet_prep == reflect pad to multiples of 32 (fusion_adacofnet.py:182-192), moduleNormalize (utility.py:86-87), concat,

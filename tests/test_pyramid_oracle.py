@@ -86,3 +86,39 @@ def test_golden_reference_wrapper(golden_dir):
             ph = z["phase%d" % l]
             d = np.angle(np.exp(1j * (torch.angle(zc).numpy() - ph)))
             assert np.abs(d[z["amp%d" % l] > 1e-3]).max() < 1e-3
+
+
+@pytest.mark.parametrize("H,W,height", [(256, 256, 12), (1080, 1920, 17), (2160, 3840, 19), (2048, 2048, 18), (64, 64, 8)])
+def test_calc_pyr_height_is_buildable(H, W, height):
+    """SURVEY 8(c) invariant (iv): the height the recipe derives from the frame size (src/train/utils.py:168-171) leaves a low-pass
+    residual of at least 7 px per side at every size of BASELINE.json's configs, and the level table has `height - 1` entries."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    "fusion-method-for-video-frame-interpolation_b200"))
+    from fvfi import pyr_plan
+    assert pyr_plan.calc_pyr_height(torch.empty((1, H, W))) == height
+    sizes = ss.level_sizes(H, W, height, S2)
+    assert len(sizes) == height - 1
+    assert min(sizes[-1]) >= 7
+    assert all(a[0] >= b[0] and a[1] >= b[1] for a, b in zip(sizes, sizes[1:]))
+
+
+def test_power_complementary_masks_fp64():
+    """SURVEY 8(c) invariant (ii): analysis followed by synthesis is the identity because the radial masks are power complementary
+    (lo_l^2 + hi_l^2 = 1) and the four angular masks tile the half plane -- in fp64 the round trip is limited only by the 1024-step
+    lookup table of the published algorithm (~1e-5), and it is the same for an image and for 3x that image (linearity)."""
+    pyr = ss.SCFpyr_PyTorch(height=9, nbands=4, scale_factor=S2, precision="fp64")
+    x = torch.rand(1, 1, 96, 160, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    r1 = pyr.reconstruct(pyr.build(x))
+    r3 = pyr.reconstruct(pyr.build(3 * x))
+    e1 = float((r1 - x.squeeze(1)).abs().max())
+    assert e1 <= 3e-5
+    assert float((r3 - 3 * r1).abs().max()) <= 1e-12
+    # energy bookkeeping of one level: removing a band level removes exactly that level's contribution
+    c = pyr.build(x)
+    c_wo = list(c)
+    c_wo[3] = 0
+    only = [torch.zeros_like(c[0])] + [0] * (len(c) - 2) + [torch.zeros_like(c[-1])]
+    only[1] = [torch.zeros_like(b) for b in c[1]]       # reconstruct() reads the band count from level 1
+    only[3] = c[3]
+    assert float((pyr.reconstruct(c_wo) + pyr.reconstruct(only) - r1).abs().max()) <= 1e-12
