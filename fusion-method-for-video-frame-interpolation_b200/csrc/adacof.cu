@@ -16,6 +16,8 @@
 // re-reads them once per channel), lanes of a warp own 32 consecutive pixels of a row so the
 // 3*F*F coefficient reads are full 128 B lines, and the frame taps are gathered through the
 // read-only L1/L2 path.  The smem-staged "tiled" family lives in adacof_tiled.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fvfi {
@@ -245,6 +247,98 @@ adacof_grad_input_scatter(const float* __restrict__ gout, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// True gradInput, CTA-AGGREGATED form (the default of gin_mode = FVFI_GIN_TRUE): the warp-aggregated kernel above still issues one
+// global reduction per (tap, corner, channel) whenever neighbouring lanes hit DIFFERENT samples -- the normal case of a smooth flow
+// field: 5e9 reductions for B = 8 at 1088 x 1920, 11.8 ms, atomics-bound.  Here a CTA owns a 64 x 16 output tile and accumulates the
+// contributions of its 1024 pixels x F^2 taps x 4 corners in a SHARED-MEMORY image of the frame region the tile can reach
+// ((16 + (F-1) d + 2*8 + 1) x (64 + (F-1) d + 2*8 + 1) samples x 3 channels, UNCLAMPED coordinates: 37.7 KB for F = 5, d = 1), then
+// flushes every non-zero sample with ONE global reduction at its clamped frame position (clamp-to-edge folds the out-of-frame part of
+// the region onto the border samples, adacof.py:30-52) -- 4-9 global reductions per output pixel instead of 300.  Offsets that leave the
+// region (beyond the halo of 8) go straight to global memory.  A warp works on 32 adjacent pixels of one row, so for smooth fields its
+// shared-memory updates fall on adjacent words (conflict-free); colliding lanes are serialised by the hardware's CAS loop.
+// ---------------------------------------------------------------------------------------------
+constexpr int GT_W = 64, GT_H = 16, GT_HALO = 8, GT_THREADS = 256;
+
+__global__ void __launch_bounds__(GT_THREADS)
+adacof_grad_input_tile(const float* __restrict__ gout, const float* __restrict__ weight, const float* __restrict__ off_i,
+                       const float* __restrict__ off_j, float* __restrict__ gin, int Hin, int Win, int H, int W, int F, int dil,
+                       int RH, int RW) {
+    constexpr int C = 3;
+    extern __shared__ float gt_region[];                 // [3][RH * RW]
+    const int RP = RH * RW;
+    const int i0 = blockIdx.y * GT_H, j0 = blockIdx.x * GT_W, n = blockIdx.z;
+    for (int p = threadIdx.x; p < C * RP; p += GT_THREADS) gt_region[p] = 0.f;
+    __syncthreads();
+    const size_t plane = (size_t)H * W, plane_in = (size_t)Hin * Win;
+    float* G = gin + (size_t)n * C * plane_in;
+    const int jl = threadIdx.x & (GT_W - 1);             // a warp = 32 adjacent pixels of one row
+    const int j = j0 + jl;
+    for (int il = threadIdx.x / GT_W; il < GT_H; il += GT_THREADS / GT_W) {
+        const int i = i0 + il;
+        if (!(i < H && j < W)) continue;
+        float g[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) g[c] = ld_stream(gout + ((size_t)n * C + c) * plane + (size_t)i * W + j);
+        size_t q = (size_t)n * F * F * plane + (size_t)i * W + j;
+        for (int k = 0; k < F; ++k) {
+          for (int l0 = 0; l0 < F; l0 += 5) {             // up to five taps of the row at a time: their 15 coefficient loads are in flight together
+            float wv[5], av[5], bv[5];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                const bool on = l0 + u < F;
+                wv[u] = on ? ld_stream(weight + q + (size_t)u * plane) : 0.f;
+                av[u] = on ? ld_stream(off_i + q + (size_t)u * plane) : 0.f;
+                bv[u] = on ? ld_stream(off_j + q + (size_t)u * plane) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                const int l = l0 + u;
+                if (l >= F) continue;
+                const float w = wv[u], al = av[u], be = bv[u];
+                const int A = (int)al, B = (int)be;                          // truncation, adacof.py:27-28
+                const float a = al - (float)A, b = be - (float)B;
+                const float na = 1.f - a, nb = 1.f - b;
+                const float w00 = na * nb, w10 = a * nb, w01 = na * b, w11 = a * b;
+                const float d0 = g[0] * w, d1 = g[1] * w, d2 = g[2] * w;
+                const int rr = il + k * dil + A + GT_HALO, cc = jl + l * dil + B + GT_HALO;     // region coordinates of the (r, c) corner
+                if ((unsigned)rr < (unsigned)(RH - 1) && (unsigned)cc < (unsigned)(RW - 1)) {
+                    float* R0 = gt_region + rr * RW + cc;
+                    atomicAdd(R0, d0 * w00);              atomicAdd(R0 + RP, d1 * w00);              atomicAdd(R0 + 2 * RP, d2 * w00);
+                    atomicAdd(R0 + RW, d0 * w10);         atomicAdd(R0 + RP + RW, d1 * w10);         atomicAdd(R0 + 2 * RP + RW, d2 * w10);
+                    atomicAdd(R0 + 1, d0 * w01);          atomicAdd(R0 + RP + 1, d1 * w01);          atomicAdd(R0 + 2 * RP + 1, d2 * w01);
+                    atomicAdd(R0 + RW + 1, d0 * w11);     atomicAdd(R0 + RP + RW + 1, d1 * w11);     atomicAdd(R0 + 2 * RP + RW + 1, d2 * w11);
+                } else {                                  // beyond the halo: global reductions at the clamped positions
+                    const int r = i + k * dil + A, cg = j + l * dil + B;
+                    const int r0 = min(max(r, 0), Hin - 1), r1 = min(max(r + 1, 0), Hin - 1);
+                    const int c0 = min(max(cg, 0), Win - 1), c1 = min(max(cg + 1, 0), Win - 1);
+                    float* P00 = G + (size_t)r0 * Win + c0;
+                    float* P10 = G + (size_t)r1 * Win + c0;
+                    float* P01 = G + (size_t)r0 * Win + c1;
+                    float* P11 = G + (size_t)r1 * Win + c1;
+                    atomicAdd(P00, d0 * w00); atomicAdd(P00 + plane_in, d1 * w00); atomicAdd(P00 + 2 * plane_in, d2 * w00);
+                    atomicAdd(P10, d0 * w10); atomicAdd(P10 + plane_in, d1 * w10); atomicAdd(P10 + 2 * plane_in, d2 * w10);
+                    atomicAdd(P01, d0 * w01); atomicAdd(P01 + plane_in, d1 * w01); atomicAdd(P01 + 2 * plane_in, d2 * w01);
+                    atomicAdd(P11, d0 * w11); atomicAdd(P11 + plane_in, d1 * w11); atomicAdd(P11 + 2 * plane_in, d2 * w11);
+                }
+            }
+            q += (size_t)min(5, F - l0) * plane;
+          }
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < RP; p += GT_THREADS) {
+        const int r = p / RW, c = p - r * RW;
+        const int gr = min(max(i0 - GT_HALO + r, 0), Hin - 1), gc = min(max(j0 - GT_HALO + c, 0), Win - 1);
+        float* dst = G + (size_t)gr * Win + gc;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            const float v = gt_region[ch * RP + p];
+            if (v != 0.f) atomicAdd(dst + (size_t)ch * plane_in, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // AdaCoFNet tail: frame = occ*t1 + (1-occ)*t2 and the flow-variance mask
 // (fusion_adacofnet.py:198-213).  One pass per frame using running moments:
 //   mean = S1 = sum w*d ;  var = sum w (mean-d)^2 = S2 - mean^2 (2 - S0)
@@ -452,8 +546,20 @@ extern "C" int fvfi_adacof_backward(const float* gout, const float* input, const
         FVFI_CUDA(cudaMemsetAsync(gin, 0, (size_t)B * C * Hin * Win * sizeof(float), s));
     if (gin_mode == FVFI_GIN_TRUE) {     // true adjoint (extension): warp-aggregated scatter, independent of the gradient path below
         FVFI_CHECK_ARG((long long)Hin * Win <= 0x7fffffffLL, "adacof_backward: frame too large for the gradInput scatter");
-        dim3 sblock(32, 8), sgrid(ceil_div(W, 32), ceil_div(H, 8), B);
-        adacof_grad_input_scatter<<<sgrid, sblock, 0, s>>>(gout, weight, off_i, off_j, gin, Hin, Win, H, W, F, dilation);
+        // default: CTA-aggregated in shared memory (adacof_grad_input_tile); the warp-aggregated kernel when the reachable region
+        // does not fit (large F * dilation) or on request (FVFI_GIN_SCATTER=warp: tests / A-B timing)
+        const int RH = GT_H + (F - 1) * dilation + 2 * GT_HALO + 1, RW = GT_W + (F - 1) * dilation + 2 * GT_HALO + 1;
+        const size_t tile_smem = (size_t)3 * RH * RW * sizeof(float);
+        const char* how = getenv("FVFI_GIN_SCATTER");
+        if (tile_smem <= 96 * 1024 && !(how && how[0] == 'w')) {
+            FVFI_SMEM_OPT_IN(adacof_grad_input_tile, tile_smem);
+            dim3 tgrid(ceil_div(W, GT_W), ceil_div(H, GT_H), B);
+            adacof_grad_input_tile<<<tgrid, GT_THREADS, tile_smem, s>>>(gout, weight, off_i, off_j, gin, Hin, Win, H, W, F, dilation,
+                                                                      RH, RW);
+        } else {
+            dim3 sblock(32, 8), sgrid(ceil_div(W, 32), ceil_div(H, 8), B);
+            adacof_grad_input_scatter<<<sgrid, sblock, 0, s>>>(gout, weight, off_i, off_j, gin, Hin, Win, H, W, F, dilation);
+        }
         FVFI_LAUNCH_CHECK();
     }
     if (C == 3 && (algo == 0 || algo == 3)) {

@@ -8,8 +8,9 @@ memsets (adacof.py:382-438).
 
 ``gin_mode`` (module attribute, default "zeros") selects what ``gradInput`` is:
   "zeros" -- reference semantics, gradInput == 0 (adacof.py:382,445)
-  "true"  -- extension: the true adjoint (csrc/adacof.cu adacof_grad_input_scatter: warp-aggregated atomic scatter --
-             lanes grouped by target address with __match_any_sync, one reduction per distinct address)
+  "true"  -- extension: the true adjoint (csrc/adacof.cu: adacof_grad_input_tile, CTA-aggregated in shared memory with one global
+             reduction per touched frame sample; adacof_grad_input_scatter, warp-aggregated -- lanes grouped by target address with
+             __match_any_sync, one reduction per distinct address -- for large F * dilation or FVFI_GIN_SCATTER=warp)
 """
 import math
 

@@ -42,7 +42,10 @@ enum { FVFI_CONV_TF32X3 = 0, FVFI_CONV_F16X3 = 1 };
 enum {
     FVFI_GIN_NONE = 0,  /* gin pointer ignored */
     FVFI_GIN_ZEROS = 1, /* reference semantics: gradInput = zeros (adacof.py:382,445) */
-    FVFI_GIN_TRUE = 2   /* extension: true adjoint; adacof_grad_input_scatter groups the lanes of a warp by target address (__match_any_sync) and issues one red.add per distinct address */
+    FVFI_GIN_TRUE = 2   /* extension: true adjoint.  Default adacof_grad_input_tile: every CTA accumulates its 64x16 output pixels in a
+                           shared-memory image of the reachable frame region, one global red.add per touched sample; large F*dilation or
+                           FVFI_GIN_SCATTER=warp: adacof_grad_input_scatter groups the lanes of a warp by target address
+                           (__match_any_sync) and issues one red.add per distinct address */
 };
 
 int fvfi_version(void);

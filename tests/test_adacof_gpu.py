@@ -164,13 +164,17 @@ def test_autograd_function_and_true_grad_input():
 
 @pytest.mark.parametrize("shape", [(2, 3, 40, 56, 5, 1), (1, 3, 33, 47, 5, 2), (1, 3, 24, 40, 3, 1), (1, 3, 17, 70, 5, 1)])
 @pytest.mark.parametrize("offsets", ["iid", "zero", "smooth", "clamped"])
-def test_true_grad_input_warp_aggregated_scatter(shape, offsets):
-    """gin_mode "true" (extension beyond the reference, which returns zeros): the warp-aggregated atomic scatter
-    (adacof_grad_input_scatter: __match_any_sync groups lanes by target address, one reduction per distinct address) equals the
-    serial adjoint of the oracle -- for scattered addresses (no aggregation), identical addresses in every lane (zero offsets with
-    F = 1 neighbours / clamped far-out offsets: whole warps collapse onto border samples) and smooth fields (partial groups);
-    ragged widths leave inactive lanes in the last warp.  The other three gradients come from the same fast path as mode "none"."""
+@pytest.mark.parametrize("scatter", ["tile", "warp"])
+def test_true_grad_input_warp_aggregated_scatter(shape, offsets, scatter, monkeypatch):
+    """gin_mode "true" (extension beyond the reference, which returns zeros), both forms of the scatter: "tile" (default,
+    adacof_grad_input_tile: a CTA accumulates its 64 x 16 pixels' contributions in a shared-memory image of the reachable frame
+    region and flushes each non-zero sample with one global reduction; offsets beyond the halo go straight to global memory -- the
+    "clamped" case) and "warp" (adacof_grad_input_scatter: __match_any_sync groups lanes by target address, one reduction per
+    distinct address; FVFI_GIN_SCATTER=warp) equal the serial adjoint of the oracle -- for scattered addresses, identical addresses in
+    every lane (zero offsets / clamped far-out offsets: whole warps collapse onto border samples) and smooth fields; ragged widths leave
+    inactive lanes in the last warp.  The other three gradients come from the same fast path as mode "none"."""
     from fvfi import adacof
+    monkeypatch.setenv("FVFI_GIN_SCATTER", scatter)
     B, C, H, W, F, d = shape
     inp, w, oi, oj, g = oa.synth(B, C, H, W, F, d, seed=23)
     if offsets == "zero":
