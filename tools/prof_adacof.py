@@ -35,7 +35,7 @@ tb = t(lambda: adacof.adacof_backward(gout, inp, w, oi, oj, 1, "none"))
 ts = t(lambda: adacof.adacofnet_warp_blend(inp, inp, w, a1, b1, w2, a2, b2, occ, 1, want_t=False))
 print("fwd random  %.3f ms %.0f GB/s | fwd smooth %.3f ms %.0f GB/s | bwd random %.3f ms %.0f GB/s | fused smooth %.3f ms %.0f GB/s" %
       (tf, bf / tf / 1e6, tfs, bf / tfs / 1e6, tb, bb / tb / 1e6, ts, bs / ts / 1e6))
-# true gradInput (extension): warp-aggregated atomic scatter, on top of the gradient kernel
+# true gradInput (extension): CTA-aggregated scatter (FVFI_GIN_SCATTER=warp: the warp-aggregated kernel), on top of the gradient kernel
 for name, (x, y) in (("random", (oi, oj)), ("smooth", (a1, b1)), ("zero", (torch.zeros_like(a1), torch.zeros_like(a1)))):
     t_none = t(lambda: adacof.adacof_backward(gout, inp, w, x, y, 1, "none"), 3)
     t_true = t(lambda: adacof.adacof_backward(gout, inp, w, x, y, 1, "true"), 3)
