@@ -162,7 +162,9 @@ def test_autograd_function_and_true_grad_input():
     assert np.abs(gin.cpu().numpy() - ref).max() <= 2e-4  # atomics: order-dependent fp32 sums
 
 
-@pytest.mark.parametrize("shape", [(2, 3, 40, 56, 5, 1), (1, 3, 33, 47, 5, 2), (1, 3, 24, 40, 3, 1), (1, 3, 17, 70, 5, 1)])
+# (.., 7, 2): the tile form's region needs the > 48 KB shared-memory opt-in; (.., 11, 4): it does not fit at all -> warp-aggregated kernel
+@pytest.mark.parametrize("shape", [(2, 3, 40, 56, 5, 1), (1, 3, 33, 47, 5, 2), (1, 3, 24, 40, 3, 1), (1, 3, 17, 70, 5, 1),
+                                   (1, 3, 24, 40, 7, 2), (1, 3, 12, 20, 11, 4)])
 @pytest.mark.parametrize("offsets", ["iid", "zero", "smooth", "clamped"])
 @pytest.mark.parametrize("scatter", ["tile", "warp"])
 def test_true_grad_input_warp_aggregated_scatter(shape, offsets, scatter, monkeypatch):
