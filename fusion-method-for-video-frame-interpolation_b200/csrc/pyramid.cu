@@ -41,7 +41,13 @@ namespace fvfi {
 constexpr int MAX_LEVELS = 40;
 constexpr int MAX_BANDS = 8;
 constexpr int MAX_SET = 24;                       // jobs per merged launch
-constexpr int PYR_THREADS = 256;
+// 9 warps per CTA, 3 CTAs per SM (72 registers): the kernels are latency-bound at 24 resident warps -- same-call A/B on 12 planes of 1080p
+// (closing session): 256 threads 5.13 / 6.56 ms decompose / reconstruct, 288: 5.00 / 6.30, 320 (64 registers, spills): 5.04 / 6.32;
+// PYR_MIN_CTAS 2: 5.99 / 7.47, 4 (64 registers): 5.19 / 6.58.  Results are bit-identical for any block size.
+#ifndef PYR_NTHREADS
+#define PYR_NTHREADS 288
+#endif
+constexpr int PYR_THREADS = PYR_NTHREADS;
 #ifndef PYR_MIN_CTAS
 #define PYR_MIN_CTAS 3
 #endif
@@ -493,7 +499,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_rows_fwd(const Le
     float2* bq = smem + (size_t)rb * pitch;
     const unsigned mag_w = J.mag_w;
     const size_t plane = (size_t)h * w;
-    constexpr int U = 4;                      // independent global loads in flight per thread
+    constexpr int U = 8;                      // independent global loads in flight per thread
     const int total = rows * w;
     for (int q0 = threadIdx.x; q0 < total; q0 += U * blockDim.x) {
         float2 z[U];
@@ -635,7 +641,7 @@ __global__ void __launch_bounds__(PYR_THREADS, PYR_MIN_CTAS) k_cols_inv_decomp(c
     // band levels: the combined radial x angular mask of band b (plan table, equal to the oracle's masks); else the radial mask
     const float* radial = band ? (use_rec_table ? J.band_rec : J.band_build) + (size_t)b * h * w : J.radial;
     {
-        constexpr int U = 4;                  // two dependent global loads per element: batch them
+        constexpr int U = 8;                  // two dependent global loads per element: batch them
         for (int q0 = threadIdx.x; q0 < E_; q0 += U * blockDim.x) {
             float m[U];
             float2 xv[U];
